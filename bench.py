@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py — MM-RCA fusion head fwd+bwd throughput (BASELINE.json metric, config 2).
+
+  python bench.py --gpus N --steps K --warmup W            # B200 path (libmmrca.so kernels)
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's algorithm on the host CPU cores
+
+A "step" is one pass of the hot path over one batch of synthetic pooled features: forward, CrossEntropyLoss,
+backward (run_one_epoch body restricted to the head, reference main_both.py:106-112), at batch 4096 per GPU
+(weak scaling).  For N > 1 the script is launched once per rank by torchrun; every rank processes its own
+batch and the flat head-gradient bucket is all-reduced once per step (plain data parallelism).
+
+One JSON line on stdout (rank 0):
+  value        samples/s with inputs already resident in HBM (device-timed, max over ranks)
+  e2e          the same metric through the public host API with HOST buffers: pinned H2D of the features and
+               labels and D2H of loss + logits inside the timed region (double-buffered on a copy stream)
+  roofline     dominant kernel: algorithmic FLOPs per launch / its CUDA-event duration, vs the measured
+               bf16 tensor peak (MEASURED_PEAKS.json) — the roof SURVEY.md §8(d) assigns to the fused head
+  cpu_baseline the oracle port of the reference timed on this box's host cores (N = 1 only)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D_IMG, D_TXT, N_CLASSES = 1280, 768, 4
+BATCH = 4096                       # BASELINE.json configs[1]
+FLOPS_FWD = 2_895_872              # matmul FLOPs per sample, forward
+FLOPS_FWD_BWD = 7_245_824          # forward + backward, features frozen (reference TL phase)
+BYTES_PER_SAMPLE = 8_216           # features fp32 + label + logits (algorithmic HBM minimum)
+L2_BYTES = 126 * 2 ** 20
+
+
+def attn_flops(p_in, dkq, dv):
+    return dict(proj=2 * 16 * p_in * (2 * dkq + dv), scores=2 * 16 * 16 * dkq, pv=2 * 16 * 16 * dv)
+
+
+# algorithmic FLOPs per SAMPLE each kernel is responsible for; recompute is overhead
+def kernel_flops():
+    sa_i, sa_t, ca = attn_flops(80, 128, 96), attn_flops(48, 128, 96), attn_flops(96, 64, 48)
+    f = {}
+    f["attn_fwd<80,128,96,self>"] = sum(sa_i.values())
+    f["attn_fwd<48,128,96,self>"] = sum(sa_t.values())
+    f["attn_fwd<96,64,48,cross>"] = sum(ca.values())
+    # backward kernels: attention backward (dP, dV = 2 pv; dQ, dK = 2 scores) + input grads where needed
+    f["attn_bwd<80,128,96,self>"] = 2 * sa_i["pv"] + 2 * sa_i["scores"]
+    f["attn_bwd<48,128,96,self>"] = 2 * sa_t["pv"] + 2 * sa_t["scores"]
+    f["attn_bwd<96,64,48,cross>"] = 2 * ca["pv"] + 2 * ca["scores"] + ca["proj"]
+    f["wgrad<80>"] = sa_i["proj"] / 3.0      # three launches (q, k, v) share the block's projection FLOPs
+    f["wgrad<48>"] = sa_t["proj"] / 3.0
+    f["wgrad<96>"] = ca["proj"] / 3.0
+    f["classifier_fwd"] = 2 * 4 * 3584
+    f["classifier_bwd"] = 2 * 2 * 4 * 3584
+    f["cross_entropy"] = 0
+    return f
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_burst=float(d["bf16_tflops"]),
+                    bf16_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synth_batches(n, batch, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randn(n, batch, D_IMG, generator=g)
+    txt = torch.randn(n, batch, D_TXT, generator=g)
+    lab = torch.randint(0, N_CLASSES, (n, batch), generator=g)
+    return img, txt, lab
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """The reference's own algorithm for this path on the host CPU: the oracle port (torch CPU restatement
+    pinned to the reference by tests/golden; the Python reference itself cannot travel to the GPU box)."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import mmrca_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    p = orc.init_head_params(seed=0)
+    img, txt, lab = synth_batches(2, args.batch, 0)
+    step = lambda i: orc.head_loss_and_grads(p, img[i % 2], txt[i % 2], lab[i % 2], True, False, False)
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i)
+    dt = time.perf_counter() - t0
+    val = args.steps * args.batch / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "mmrca_head_fwd_bwd_samples_per_s", "value": val, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"MM_RCA --reverse fusion head fwd+CE+bwd, batch {args.batch}, features 1280+768, "
+                               "4 classes, dropout off (BASELINE.json configs[1])"},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{args.steps} steps of batch {args.batch} after {args.warmup} warm-up"},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def cpu_baseline(batch, budget_s=12.0, max_steps=60):
+    import torch
+    from oracle import mmrca_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    p = orc.init_head_params(seed=0)
+    img, txt, lab = synth_batches(1, batch, 0)
+    orc.head_loss_and_grads(p, img[0], txt[0], lab[0], True, False, False)
+    n, t0 = 0, time.perf_counter()
+    while n < max_steps and (time.perf_counter() - t0 < budget_s or n < 3):
+        orc.head_loss_and_grads(p, img[0], txt[0], lab[0], True, False, False)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n * batch / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} fwd+CE+bwd steps of batch {batch} ({dt:.1f} s) of the torch-CPU oracle port"}
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import garbage_classification_rca_b200 as g
+    from garbage_classification_rca_b200 import _native as N
+    from garbage_classification_rca_b200.training import HeadDataParallel
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, W = args.batch, args.steps, args.warmup
+    compute = N.COMPUTE_BF16 if args.compute == "bf16" else N.COMPUTE_FP32
+    params = g.functional.init_head_parameters(dev, seed=0)
+    step = g.HeadTrainStep(params, B, D_IMG, D_TXT, reverse=True, compute=compute)
+    dp = HeadDataParallel(step)
+    # inputs larger than L2: rotate over NB distinct batches
+    per_batch = B * (D_IMG + D_TXT) * 4
+    NB = max(2, -(-2 * L2_BYTES // per_batch))
+    img_h, txt_h, lab_h = synth_batches(NB, B, 1234 + rank)
+    img_d, txt_d, lab_d = img_h.to(dev), txt_h.to(dev), lab_h.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step(i):
+        step.zero_grad()
+        dp(img_d[i % NB], txt_d[i % NB], lab_d[i % NB])
+
+    # ---- value: device-resident inputs -------------------------------------------------------------
+    for i in range(W):
+        device_step(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    N.kernel_launches(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        device_step(W + i)
+    e1.record()
+    barrier()
+    launches = N.kernel_launches()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    loss_val = float(step.loss.item())
+
+    # ---- roofline: second pass with per-kernel CUDA events on the launch stream ----------------------
+    per_kernel = {}
+    N.timing_begin(launches + 64)
+    for i in range(K):
+        device_step(W + i)
+    for name, t in N.timing_end(launches + 64):
+        per_kernel.setdefault(name, []).append(t)
+    torch.cuda.synchronize()
+
+    # ---- e2e: host buffers, double-buffered H2D on a copy stream, D2H of loss + logits ---------------
+    img_p, txt_p, lab_p = img_h.pin_memory(), txt_h.pin_memory(), lab_h.pin_memory()
+    out_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+    out_logits = torch.empty(B, N_CLASSES, dtype=torch.float32).pin_memory()
+    slots = [(torch.empty(B, D_IMG, device=dev), torch.empty(B, D_TXT, device=dev),
+              torch.empty(B, dtype=torch.int64, device=dev)) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(dev)
+    main = torch.cuda.current_stream(dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def h2d(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s])
+            slots[s][0].copy_(img_p[i % NB], non_blocking=True)
+            slots[s][1].copy_(txt_p[i % NB], non_blocking=True)
+            slots[s][2].copy_(lab_p[i % NB], non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_loop(n):
+        for s in range(2):
+            consumed[s].record(main)
+        h2d(0)
+        for i in range(n):
+            if i + 1 < n:
+                h2d(i + 1)
+            s = i % 2
+            main.wait_event(ready[s])
+            step.zero_grad()
+            dp(*slots[s])
+            consumed[s].record(main)
+            out_loss.copy_(step.loss, non_blocking=True)
+            out_logits.copy_(step.logits, non_blocking=True)
+        main.synchronize()
+
+    e2e_loop(max(W, 2))
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    e2e_loop(K)
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    value = world * B * K / (ms * 1e-3)
+    e2e = world * B * K / (ms_e2e * 1e-3)
+    kf = kernel_flops()
+    share = {k: sum(v) / K for k, v in per_kernel.items()}           # ms per step per kernel name
+    total_k = sum(share.values()) or 1.0
+    dom = max(share, key=share.get)
+    dom_ms = statistics.mean(per_kernel[dom])
+    dom_flops = kf.get(dom, 0) * B
+    achieved = dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    peak = peaks["bf16_sustained"]
+    step_tflops = value / world * FLOPS_FWD_BWD / 1e12
+    out = {
+        "metric": "mmrca_head_fwd_bwd_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if compute == N.COMPUTE_FP32 else "bf16", "data": "synthetic",
+        "config": {"workload": f"MM_RCA --reverse fusion head fwd+CE+bwd, batch {B}/GPU, features 1280+768, "
+                               "4 classes, dropout off, backbones frozen (BASELINE.json configs[1])",
+                   "parallelism": f"dp{world}", "global_batch": world * B,
+                   "l2": f"inputs rotate over {NB} distinct batches ({NB * per_batch >> 20} MiB > 126 MiB L2)",
+                   "compute": args.compute, "loss": loss_val},
+        "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": B * (D_IMG + D_TXT) * 4 + B * 8,
+                "d2h_bytes_per_step": 4 + B * N_CLASSES * 4, "ms_per_step": ms_e2e / K},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"] + " bf16 sustained",
+                     "kernel_ms": dom_ms, "kernel_share_of_step": share[dom] / total_k,
+                     "timing": f"second pass of {K} steps with per-kernel CUDA events on the launch stream"},
+        "roofline_step": {"bound": "tensor", "achieved": step_tflops, "peak": peak, "unit": "TFLOP/s",
+                          "frac": step_tflops / peak, "flops_per_sample": FLOPS_FWD_BWD,
+                          "hbm_view": {"achieved_gbs": value / world * BYTES_PER_SAMPLE / 1e9,
+                                       "peak_gbs": peaks["hbm_gbs"]}},
+        "kernels_ms_per_step": {k: round(v, 4) for k, v in sorted(share.items(), key=lambda kv: -kv[1])},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(B)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--compute", default="fp32", choices=("fp32", "bf16"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

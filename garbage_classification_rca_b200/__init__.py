@@ -1,0 +1,11 @@
+"""B200-native MM-RCA late-fusion head (drop-in for the hot path of espiriki/Garbage_Classification_RCA).
+
+Host side: Python/PyTorch mirror of the reference model API (multimodal_model.py).
+Device side: hand-written sm_100a CUDA kernels behind a C ABI (include/mmrca.h, libmmrca.so).
+"""
+from . import _native, functional
+from .functional import (HeadTrainStep, attention_block, concat_width, cross_entropy, final_linear_name,
+                         head_param_names, mmrca_head)
+
+__all__ = ["_native", "functional", "HeadTrainStep", "attention_block", "concat_width", "cross_entropy",
+           "final_linear_name", "head_param_names", "mmrca_head"]

@@ -1,0 +1,548 @@
+// C ABI of the MM-RCA head (include/mmrca.h): argument checking, workspace carve-up and
+// kernel launches.  No allocation, no synchronisation: everything is enqueued on the
+// caller's stream.  There is no CPU path — without an sm_100 device every call fails.
+#include "../../include/mmrca.h"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "mmrca_attn_fp32.cuh"
+#include "mmrca_misc_fp32.cuh"
+
+namespace mmrca {
+
+static thread_local char g_err[512] = "";
+static thread_local int g_launches = 0;
+
+// ---- optional per-kernel timing (mmrca_timing_begin / _end) -------------------------------------
+struct TimingRec { const char* name; cudaEvent_t e0, e1; };
+static thread_local TimingRec* g_trec = nullptr;
+static thread_local int g_tcap = 0, g_tn = 0;
+
+struct LaunchScope {   // counts the launch and, when timing is on, brackets it with events on its stream
+  cudaStream_t st; int idx;
+  LaunchScope(const char* name, cudaStream_t s) : st(s), idx(-1) {
+    ++g_launches;
+    if (g_trec && g_tn < g_tcap) {
+      idx = g_tn++;
+      g_trec[idx].name = name;
+      cudaEventRecord(g_trec[idx].e0, st);
+    }
+  }
+  ~LaunchScope() { if (idx >= 0) cudaEventRecord(g_trec[idx].e1, st); }
+};
+
+static int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+  snprintf(g_err, sizeof(g_err), fmt, a, b);
+  return code;
+}
+
+#define MMRCA_CUDA(call)                                                                   \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) return fail(MMRCA_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+struct DeviceInfo { int ok; int sms; };
+
+static int device_info(DeviceInfo* out) {
+  static DeviceInfo cache[64];
+  static bool have[64];
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    cudaGetLastError();
+    return fail(MMRCA_ERR_NO_DEVICE, "no CUDA device: the MM-RCA head has no CPU fallback%s%s");
+  }
+  if (!have[dev]) {
+    int major = 0, sms = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cache[dev].ok = (major == 10);
+    cache[dev].sms = sms;
+    have[dev] = true;
+  }
+  *out = cache[dev];
+  if (!out->ok) return fail(MMRCA_ERR_NO_DEVICE, "device is not compute capability 10.x (sm_100a kernels only)%s%s");
+  return MMRCA_OK;
+}
+
+template <class K>
+static int set_smem(K kernel, size_t bytes) {
+  MMRCA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
+  return MMRCA_OK;
+}
+
+// ---- attention block dispatch -------------------------------------------------------------------
+template <int DIN, int DKQ, int DV, bool SELF, int GF, int GB>
+static int launch_attn(bool backward, const AttnArgs& a, int sms, cudaStream_t st) {
+  if (!backward) {
+    using C = AttnCfg<DIN, DKQ, DV, SELF, GF, false>;
+    int rc = set_smem(attn_fwd_kernel<C>, C::SMEM_BYTES);
+    if (rc) return rc;
+    const int tiles = (a.batch + C::G - 1) / C::G;
+    LaunchScope ls(SELF ? (DIN == 48 ? "attn_fwd<48,128,96,self>" : DIN == 64 ? "attn_fwd<64,128,96,self>"
+                                                                             : "attn_fwd<80,128,96,self>")
+                        : "attn_fwd<96,64,48,cross>", st);
+    attn_fwd_kernel<C><<<min(tiles, sms), kThreads, C::SMEM_BYTES, st>>>(a);
+  } else {
+    using C = AttnCfg<DIN, DKQ, DV, SELF, GB, true>;
+    int rc = set_smem(attn_bwd_kernel<C>, C::SMEM_BYTES);
+    if (rc) return rc;
+    const int tiles = (a.batch + C::G - 1) / C::G;
+    LaunchScope ls(SELF ? (DIN == 48 ? "attn_bwd<48,128,96,self>" : DIN == 64 ? "attn_bwd<64,128,96,self>"
+                                                                             : "attn_bwd<80,128,96,self>")
+                        : "attn_bwd<96,64,48,cross>", st);
+    attn_bwd_kernel<C><<<min(tiles, sms), kThreads, C::SMEM_BYTES, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+
+static int attn_dispatch(bool backward, bool self, int d_in, int d_kq, int d_v, const AttnArgs& a, int sms,
+                         cudaStream_t st) {
+  if (a.batch <= 0) return MMRCA_OK;
+  if (self && d_kq == MMRCA_SA_DKQ && d_v == MMRCA_SA_DV) {
+    if (d_in == 48) return launch_attn<48, 128, 96, true, 4, 4>(backward, a, sms, st);
+    if (d_in == 64) return launch_attn<64, 128, 96, true, 4, 2>(backward, a, sms, st);
+    if (d_in == 80) return launch_attn<80, 128, 96, true, 4, 2>(backward, a, sms, st);
+  }
+  if (!self && d_in == MMRCA_SA_DV && d_kq == MMRCA_CA_DKQ && d_v == MMRCA_CA_DV)
+    return launch_attn<96, 64, 48, false, 4, 4>(backward, a, sms, st);
+  return fail(MMRCA_ERR_INVALID,
+              "unsupported attention block shape: need self (d_in in {48,64,80},128,96) or cross (96,64,48)%s%s");
+}
+
+static AttnArgs make_attn_args(const MmrcaAttnParams& p, const float* xq, const float* xkv, int batch, int reverse) {
+  AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.xq = xq; a.xkv = xkv;
+  a.wq = p.wq; a.bq = p.bq; a.wk = p.wk; a.bk = p.bk; a.wv = p.wv; a.bv = p.bv;
+  a.ln_g = p.ln_g; a.ln_b = p.ln_b;
+  a.batch = batch; a.reverse = reverse;
+  return a;
+}
+
+static int launch_wgrad(int K, const float* dy, int ldy, int col0, int ncols, const float* x, const float* norms,
+                        int rows, float* dw, float* db, int sms, cudaStream_t st) {
+  const int ny = (ncols + kWgCols - 1) / kWgCols;
+  const int tiles = (rows + kWgRows - 1) / kWgRows;
+  int gx = (4 * sms + ny - 1) / ny;
+  if (gx > tiles) gx = tiles;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, ny);
+  LaunchScope ls(K == 48 ? "wgrad<48>" : K == 64 ? "wgrad<64>" : K == 80 ? "wgrad<80>" : "wgrad<96>", st);
+  switch (K) {
+    case 48: wgrad_kernel<48><<<grid, kThreads, 0, st>>>(dy, ldy, col0, ncols, x, norms, rows, dw, db); break;
+    case 64: wgrad_kernel<64><<<grid, kThreads, 0, st>>>(dy, ldy, col0, ncols, x, norms, rows, dw, db); break;
+    case 80: wgrad_kernel<80><<<grid, kThreads, 0, st>>>(dy, ldy, col0, ncols, x, norms, rows, dw, db); break;
+    case 96: wgrad_kernel<96><<<grid, kThreads, 0, st>>>(dy, ldy, col0, ncols, x, norms, rows, dw, db); break;
+    default: return fail(MMRCA_ERR_INVALID, "unsupported wgrad K%s%s");
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+
+// dW/db of one block from the row-space grads dy = [dQ|dK|dV] (written by attn_bwd_kernel)
+static int attn_wgrads(bool self, int d_in, int d_kq, int d_v, const float* dy, const float* xq, const float* xkv,
+                       const float* norms, int batch, const MmrcaAttnGrads& g, int sms, cudaStream_t st) {
+  const int nall = 2 * d_kq + d_v, rows = batch * kL;
+  int rc;
+  // W_query/W_key/W_value are separate tensors in the state_dict, so three (or, for a shared
+  // source, still three) reductions with their own destination pointers.
+  if ((rc = launch_wgrad(d_in, dy, nall, 0, d_kq, xq, norms, rows, g.wq, g.bq, sms, st))) return rc;
+  if ((rc = launch_wgrad(d_in, dy, nall, d_kq, d_kq, self ? xq : xkv, norms, rows, g.wk, g.bk, sms, st))) return rc;
+  if ((rc = launch_wgrad(d_in, dy, nall, 2 * d_kq, d_v, self ? xq : xkv, norms, rows, g.wv, g.bv, sms, st))) return rc;
+  return MMRCA_OK;
+}
+
+// ---- classifier dispatch --------------------------------------------------------------------------
+template <int NC>
+static void launch_classifier(bool backward, const CatArgs& a, int sms, cudaStream_t st) {
+  LaunchScope ls(backward ? "classifier_bwd" : "classifier_fwd", st);
+  if (!backward) {
+    int grid = (a.batch + kWarps - 1) / kWarps;
+    if (grid > 8 * sms) grid = 8 * sms;
+    classifier_fwd_kernel<NC><<<grid, kThreads, 0, st>>>(a);
+  } else {
+    const int ny = (a.D + kThreads * 4 - 1) / (kThreads * 4);
+    int gx = (4 * sms + ny - 1) / ny;
+    if (gx > a.batch) gx = a.batch;
+    classifier_bwd_kernel<NC><<<dim3(gx, ny), kThreads, 0, st>>>(a);
+  }
+}
+
+static int classifier_dispatch(bool backward, int nc, const CatArgs& a, int sms, cudaStream_t st) {
+  if (a.batch <= 0) return MMRCA_OK;
+  switch (nc) {
+    case 1: launch_classifier<1>(backward, a, sms, st); break;
+    case 2: launch_classifier<2>(backward, a, sms, st); break;
+    case 3: launch_classifier<3>(backward, a, sms, st); break;
+    case 4: launch_classifier<4>(backward, a, sms, st); break;
+    case 5: launch_classifier<5>(backward, a, sms, st); break;
+    case 6: launch_classifier<6>(backward, a, sms, st); break;
+    case 7: launch_classifier<7>(backward, a, sms, st); break;
+    case 8: launch_classifier<8>(backward, a, sms, st); break;
+    default: return fail(MMRCA_ERR_INVALID, "n_classes must be in [1, 8]%s%s");
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+
+// ---- workspace --------------------------------------------------------------------------------------
+struct Workspace {
+  float *norm_img, *norm_txt, *t_sa, *i_sa, *t_i, *i_t;          // forward (kept for the backward)
+  float *d_t_sa, *d_i_sa, *d_t_i, *d_i_t, *dy, *dlogits;          // training only
+  size_t bytes;
+};
+
+static size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+
+static Workspace carve(const MmrcaHeadDesc& d, bool training, void* base) {
+  Workspace w;
+  memset(&w, 0, sizeof(w));
+  char* p = static_cast<char*>(base);
+  size_t off = 0;
+  const size_t B = size_t(d.batch > 0 ? d.batch : 0);
+  auto take = [&](size_t floats) { float* r = reinterpret_cast<float*>(p + off); off += align_up(floats * 4); return r; };
+  w.norm_img = take(B); w.norm_txt = take(B);
+  w.t_sa = take(B * kL * MMRCA_SA_DV); w.i_sa = take(B * kL * MMRCA_SA_DV);
+  w.t_i = take(B * kL * MMRCA_CA_DV); w.i_t = take(B * kL * MMRCA_CA_DV);
+  if (training) {
+    w.d_t_sa = take(B * kL * MMRCA_SA_DV); w.d_i_sa = take(B * kL * MMRCA_SA_DV);
+    w.d_t_i = take(B * kL * MMRCA_CA_DV); w.d_i_t = take(B * kL * MMRCA_CA_DV);
+    w.dy = take(B * kL * (2 * MMRCA_SA_DKQ + MMRCA_SA_DV));
+    w.dlogits = take(B * size_t(d.n_classes > 0 ? d.n_classes : 0));
+  }
+  w.bytes = off;
+  return w;
+}
+
+static int check_desc(const MmrcaHeadDesc* d) {
+  if (!d) return fail(MMRCA_ERR_INVALID, "null desc%s%s");
+  if (d->batch < 0) return fail(MMRCA_ERR_INVALID, "negative batch%s%s");
+  auto okdim = [](int v) { return v == 768 || v == 1024 || v == 1280; };
+  if (!okdim(d->d_img) || !okdim(d->d_txt))
+    return fail(MMRCA_ERR_INVALID, "d_img / d_txt must be one of 768, 1024, 1280 (16 chunks of 48/64/80)%s%s");
+  if (d->n_classes < 1 || d->n_classes > 8) return fail(MMRCA_ERR_INVALID, "n_classes must be in [1, 8]%s%s");
+  if ((d->flags & MMRCA_FLAG_FEATURES_ONLY) && (d->flags & MMRCA_FLAG_CROSS_ATTENTION_ONLY)) {
+    // the reference's if/elif gives features_only precedence (multimodal_model.py:694-726)
+  }
+  if (d->compute != MMRCA_COMPUTE_FP32 && d->compute != MMRCA_COMPUTE_BF16)
+    return fail(MMRCA_ERR_INVALID, "unknown compute mode%s%s");
+  if (d->compute == MMRCA_COMPUTE_BF16)
+    return fail(MMRCA_ERR_INVALID, "bf16 tensor-core path is not compiled into this build%s%s");
+  return MMRCA_OK;
+}
+
+static int concat_width(const MmrcaHeadDesc& d) {
+  const int ca = 2 * kL * MMRCA_CA_DV;
+  if (d.flags & MMRCA_FLAG_FEATURES_ONLY) return d.d_img + d.d_txt;
+  if (d.flags & MMRCA_FLAG_CROSS_ATTENTION_ONLY) return ca;
+  return ca + d.d_img + d.d_txt;
+}
+
+// concat order: multimodal_model.py:694-716
+static CatArgs make_cat_args(const MmrcaHeadDesc& d, const Workspace& w, const float* img, const float* txt,
+                             const uint8_t* mask, float scale, const float* wf, const float* bf) {
+  CatArgs c;
+  memset(&c, 0, sizeof(c));
+  const bool fo = d.flags & MMRCA_FLAG_FEATURES_ONLY, co = !fo && (d.flags & MMRCA_FLAG_CROSS_ATTENTION_ONLY);
+  int n = 0;
+  if (!fo) {
+    c.seg[n].src = w.t_i; c.seg[n].width = kL * MMRCA_CA_DV; ++n;
+    c.seg[n].src = w.i_t; c.seg[n].width = kL * MMRCA_CA_DV; ++n;
+  }
+  if (!co) {
+    c.seg[n].src = img; c.seg[n].norms = w.norm_img; c.seg[n].width = d.d_img; ++n;
+    c.seg[n].src = txt; c.seg[n].norms = w.norm_txt; c.seg[n].width = d.d_txt; ++n;
+  }
+  c.nseg = n;
+  c.D = concat_width(d);
+  c.batch = d.batch;
+  c.mask = mask; c.scale = scale;
+  c.wf = wf; c.bf = bf;
+  return c;
+}
+
+// L2 norms of the raw features when no attention block computes them (features_only skips the
+// attention blocks: the reference runs and discards them, multimodal_model.py:676-692).
+__global__ void __launch_bounds__(kThreads) l2norm_kernel(const float* __restrict__ x, float* __restrict__ norms,
+                                                          int batch, int d) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = blockIdx.x * kWarps + warp; b < batch; b += gridDim.x * kWarps) {
+    const float4* xs = reinterpret_cast<const float4*>(x + size_t(b) * d);
+    float ss = 0.f;
+    for (int j = lane; j < d / 4; j += 32) {
+      const float4 v = __ldg(xs + j);
+      ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ss))));
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) norms[b] = sqrtf(ss);
+  }
+}
+
+static int head_forward_impl(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, const float* img, const float* txt,
+                             const uint8_t* mask, float scale, float* logits, const Workspace& w, int sms,
+                             cudaStream_t st) {
+  const bool fo = d.flags & MMRCA_FLAG_FEATURES_ONLY;
+  const int rev = (d.flags & MMRCA_FLAG_REVERSE) ? 1 : 0;
+  int rc;
+  if (d.batch == 0) return MMRCA_OK;
+  if (fo) {
+    const int grid = min((d.batch + kWarps - 1) / kWarps, 8 * sms);
+    { LaunchScope ls("l2norm", st); l2norm_kernel<<<grid, kThreads, 0, st>>>(img, w.norm_img, d.batch, d.d_img); }
+    { LaunchScope ls("l2norm", st); l2norm_kernel<<<grid, kThreads, 0, st>>>(txt, w.norm_txt, d.batch, d.d_txt); }
+    MMRCA_CUDA(cudaGetLastError());
+  } else {
+    AttnArgs a = make_attn_args(p.sa_txt, txt, txt, d.batch, 0);            // multimodal_model.py:677-678
+    a.normalise = 1; a.norms = w.norm_txt; a.out = w.t_sa;
+    if ((rc = attn_dispatch(false, true, d.d_txt / kL, MMRCA_SA_DKQ, MMRCA_SA_DV, a, sms, st))) return rc;
+    a = make_attn_args(p.sa_img, img, img, d.batch, 0);                      // :679-680
+    a.normalise = 1; a.norms = w.norm_img; a.out = w.i_sa;
+    if ((rc = attn_dispatch(false, true, d.d_img / kL, MMRCA_SA_DKQ, MMRCA_SA_DV, a, sms, st))) return rc;
+    a = make_attn_args(p.ca1, w.t_sa, w.i_sa, d.batch, rev);                 // :683-684
+    a.out = w.t_i;
+    if ((rc = attn_dispatch(false, false, MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV, a, sms, st))) return rc;
+    a = make_attn_args(p.ca2, w.i_sa, w.t_sa, d.batch, rev);                 // :685-686
+    a.out = w.i_t;
+    if ((rc = attn_dispatch(false, false, MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV, a, sms, st))) return rc;
+  }
+  CatArgs c = make_cat_args(d, w, img, txt, mask, scale, p.wf, p.bf);
+  c.logits = logits;
+  return classifier_dispatch(false, d.n_classes, c, sms, st);
+}
+
+static int head_backward_impl(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, const float* img, const float* txt,
+                              const uint8_t* mask, float scale, const float* dlogits, const MmrcaHeadGrads& g,
+                              float* d_img, float* d_txt, const Workspace& w, int sms, cudaStream_t st) {
+  const bool fo = d.flags & MMRCA_FLAG_FEATURES_ONLY, co = !fo && (d.flags & MMRCA_FLAG_CROSS_ATTENTION_ONLY);
+  const int rev = (d.flags & MMRCA_FLAG_REVERSE) ? 1 : 0;
+  const bool want_feat = d_img != nullptr || d_txt != nullptr;
+  int rc;
+  if (d.batch == 0) return MMRCA_OK;
+  if (want_feat && !(d_img && d_txt))
+    return fail(MMRCA_ERR_INVALID, "d_img_feat and d_txt_feat must both be given or both be NULL%s%s");
+  // 1. classifier: dWf, dbf, d(T_I), d(I_T) and the direct feature terms d(img_n), d(txt_n)
+  CatArgs c = make_cat_args(d, w, img, txt, mask, scale, p.wf, p.bf);
+  c.dlogits = dlogits; c.g_wf = g.wf; c.g_bf = g.bf;
+  {
+    int n = 0;
+    if (!fo) { c.seg[n++].dst = w.d_t_i; c.seg[n++].dst = w.d_i_t; }
+    if (!co) { c.seg[n++].dst = want_feat ? d_img : nullptr; c.seg[n++].dst = want_feat ? d_txt : nullptr; }
+  }
+  if ((rc = classifier_dispatch(true, d.n_classes, c, sms, st))) return rc;
+  if (!fo) {
+    // 2. cross_attention_1(text SA -> q, image SA -> k,v): d_t_sa = dq-path, d_i_sa = dkv-path
+    AttnArgs a = make_attn_args(p.ca1, w.t_sa, w.i_sa, d.batch, rev);
+    a.dout = w.d_t_i; a.dy = w.dy; a.dxq = w.d_t_sa; a.dxkv = w.d_i_sa; a.acc_dxq = 0; a.acc_dxkv = 0;
+    a.g_ln_g = g.ca1.ln_g; a.g_ln_b = g.ca1.ln_b;
+    if ((rc = attn_dispatch(true, false, MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV, a, sms, st))) return rc;
+    if ((rc = attn_wgrads(false, MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV, w.dy, w.t_sa, w.i_sa, nullptr, d.batch,
+                          g.ca1, sms, st))) return rc;
+    // 3. cross_attention_2(image SA -> q, text SA -> k,v): accumulates into both
+    a = make_attn_args(p.ca2, w.i_sa, w.t_sa, d.batch, rev);
+    a.dout = w.d_i_t; a.dy = w.dy; a.dxq = w.d_i_sa; a.dxkv = w.d_t_sa; a.acc_dxq = 1; a.acc_dxkv = 1;
+    a.g_ln_g = g.ca2.ln_g; a.g_ln_b = g.ca2.ln_b;
+    if ((rc = attn_dispatch(true, false, MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV, a, sms, st))) return rc;
+    if ((rc = attn_wgrads(false, MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV, w.dy, w.i_sa, w.t_sa, nullptr, d.batch,
+                          g.ca2, sms, st))) return rc;
+    // 4. self-attention blocks; their input grads land on the normalised features
+    a = make_attn_args(p.sa_txt, txt, txt, d.batch, 0);
+    a.normalise = 1; a.norms = w.norm_txt;
+    a.dout = w.d_t_sa; a.dy = w.dy; a.dxq = want_feat ? d_txt : nullptr; a.acc_dxq = co ? 0 : 1;
+    a.g_ln_g = g.sa_txt.ln_g; a.g_ln_b = g.sa_txt.ln_b;
+    if ((rc = attn_dispatch(true, true, d.d_txt / kL, MMRCA_SA_DKQ, MMRCA_SA_DV, a, sms, st))) return rc;
+    if ((rc = attn_wgrads(true, d.d_txt / kL, MMRCA_SA_DKQ, MMRCA_SA_DV, w.dy, txt, txt, w.norm_txt, d.batch,
+                          g.sa_txt, sms, st))) return rc;
+    a = make_attn_args(p.sa_img, img, img, d.batch, 0);
+    a.normalise = 1; a.norms = w.norm_img;
+    a.dout = w.d_i_sa; a.dy = w.dy; a.dxq = want_feat ? d_img : nullptr; a.acc_dxq = co ? 0 : 1;
+    a.g_ln_g = g.sa_img.ln_g; a.g_ln_b = g.sa_img.ln_b;
+    if ((rc = attn_dispatch(true, true, d.d_img / kL, MMRCA_SA_DKQ, MMRCA_SA_DV, a, sms, st))) return rc;
+    if ((rc = attn_wgrads(true, d.d_img / kL, MMRCA_SA_DKQ, MMRCA_SA_DV, w.dy, img, img, w.norm_img, d.batch,
+                          g.sa_img, sms, st))) return rc;
+  }
+  // 5. through x / ||x||
+  if (want_feat) {
+    const int grid = min((d.batch + kWarps - 1) / kWarps, 8 * sms);
+    { LaunchScope ls("l2norm_bwd", st); l2norm_bwd_kernel<<<grid, kThreads, 0, st>>>(img, w.norm_img, d_img, d.batch, d.d_img); }
+    { LaunchScope ls("l2norm_bwd", st); l2norm_bwd_kernel<<<grid, kThreads, 0, st>>>(txt, w.norm_txt, d_txt, d.batch, d.d_txt); }
+    MMRCA_CUDA(cudaGetLastError());
+  }
+  return MMRCA_OK;
+}
+
+static int launch_ce(const float* logits, const int64_t* labels, const MmrcaCeDesc* ce, int batch, int nc,
+                     float* loss, float* dlogits, cudaStream_t st) {
+  if (nc < 1 || nc > kCeMaxClasses) return fail(MMRCA_ERR_INVALID, "n_classes must be in [1, 16]%s%s");
+  if (batch <= 0) return fail(MMRCA_ERR_INVALID, "cross entropy needs batch > 0%s%s");
+  {
+    LaunchScope ls("cross_entropy", st);
+    cross_entropy_kernel<<<1, kCeThreads, 0, st>>>(logits, labels, ce ? ce->class_weight : nullptr,
+                                                   ce ? ce->label_smoothing : 0.f, batch, nc, loss, dlogits);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+
+}  // namespace mmrca
+
+using namespace mmrca;
+
+extern "C" {
+
+int mmrca_query(int what) {
+  switch (what) {
+    case MMRCA_QUERY_ABI_VERSION: return MMRCA_ABI_VERSION;
+    case MMRCA_QUERY_DEVICE_OK: { DeviceInfo di; return device_info(&di) == MMRCA_OK ? 1 : 0; }
+    case MMRCA_QUERY_SM_COUNT: { DeviceInfo di; return device_info(&di) == MMRCA_OK ? di.sms : 0; }
+    case MMRCA_QUERY_KERNEL_LAUNCHES: return g_launches;
+    case MMRCA_QUERY_RESET_LAUNCHES: { int v = g_launches; g_launches = 0; return v; }
+    case MMRCA_QUERY_HAS_BF16: return 0;
+    default: return -1;
+  }
+}
+
+const char* mmrca_last_error(void) { return g_err; }
+
+int mmrca_timing_begin(int32_t max_records) {
+  if (g_trec) return -fail(MMRCA_ERR_INVALID, "timing already active on this thread%s%s");
+  if (max_records <= 0) return -fail(MMRCA_ERR_INVALID, "max_records must be positive%s%s");
+  TimingRec* r = new TimingRec[max_records];
+  for (int i = 0; i < max_records; ++i) {
+    if (cudaEventCreate(&r[i].e0) != cudaSuccess || cudaEventCreate(&r[i].e1) != cudaSuccess) {
+      delete[] r;
+      return -fail(MMRCA_ERR_CUDA, "cudaEventCreate failed%s%s");
+    }
+  }
+  g_trec = r; g_tcap = max_records; g_tn = 0;
+  return 0;
+}
+
+int mmrca_timing_end(MmrcaKernelTime* out, int32_t max_out) {
+  if (!g_trec) return -fail(MMRCA_ERR_INVALID, "timing is not active on this thread%s%s");
+  const int n = g_tn;
+  int rc = n;
+  for (int i = 0; i < n; ++i) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(g_trec[i].e1) != cudaSuccess ||
+        cudaEventElapsedTime(&ms, g_trec[i].e0, g_trec[i].e1) != cudaSuccess) {
+      rc = -fail(MMRCA_ERR_CUDA, "reading a timing event failed%s%s");
+      break;
+    }
+    if (out && i < max_out) { out[i].name = g_trec[i].name; out[i].ms = ms; }
+  }
+  for (int i = 0; i < g_tcap; ++i) { cudaEventDestroy(g_trec[i].e0); cudaEventDestroy(g_trec[i].e1); }
+  delete[] g_trec;
+  g_trec = nullptr; g_tcap = g_tn = 0;
+  return rc;
+}
+
+size_t mmrca_head_workspace_bytes(const MmrcaHeadDesc* desc, int training) {
+  if (!desc) return 0;
+  return carve(*desc, training != 0, nullptr).bytes;
+}
+
+int mmrca_head_forward(const MmrcaHeadDesc* desc, const MmrcaHeadParams* params, const float* img_feat,
+                       const float* txt_feat, const uint8_t* drop_mask, float drop_scale, float* logits,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  int rc;
+  if ((rc = check_desc(desc))) return rc;
+  if (!params || !img_feat || !txt_feat || !logits || !workspace)
+    return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
+  DeviceInfo di;
+  if ((rc = device_info(&di))) return rc;
+  Workspace w = carve(*desc, false, workspace);
+  if (workspace_bytes < w.bytes) return fail(MMRCA_ERR_WORKSPACE, "workspace too small%s%s");
+  return head_forward_impl(*desc, *params, img_feat, txt_feat, drop_mask, drop_scale, logits, w, di.sms,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int mmrca_head_backward(const MmrcaHeadDesc* desc, const MmrcaHeadParams* params, const float* img_feat,
+                        const float* txt_feat, const uint8_t* drop_mask, float drop_scale, const float* dlogits,
+                        const MmrcaHeadGrads* grads, float* d_img_feat, float* d_txt_feat, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  int rc;
+  if ((rc = check_desc(desc))) return rc;
+  if (!params || !img_feat || !txt_feat || !dlogits || !grads || !workspace)
+    return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
+  DeviceInfo di;
+  if ((rc = device_info(&di))) return rc;
+  Workspace w = carve(*desc, true, workspace);
+  if (workspace_bytes < w.bytes) return fail(MMRCA_ERR_WORKSPACE, "workspace too small (training size needed)%s%s");
+  return head_backward_impl(*desc, *params, img_feat, txt_feat, drop_mask, drop_scale, dlogits, *grads, d_img_feat,
+                            d_txt_feat, w, di.sms, static_cast<cudaStream_t>(stream));
+}
+
+int mmrca_cross_entropy(const float* logits, const int64_t* labels, const MmrcaCeDesc* ce, int32_t batch,
+                        int32_t n_classes, float* loss_out, float* dlogits, void* stream) {
+  if (!logits || !labels) return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
+  DeviceInfo di;
+  int rc;
+  if ((rc = device_info(&di))) return rc;
+  return launch_ce(logits, labels, ce, batch, n_classes, loss_out, dlogits, static_cast<cudaStream_t>(stream));
+}
+
+int mmrca_head_train_step(const MmrcaHeadDesc* desc, const MmrcaHeadParams* params, const float* img_feat,
+                          const float* txt_feat, const uint8_t* drop_mask, float drop_scale, const int64_t* labels,
+                          const MmrcaCeDesc* ce, float* logits, float* loss_out, const MmrcaHeadGrads* grads,
+                          float* d_img_feat, float* d_txt_feat, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  int rc;
+  if ((rc = check_desc(desc))) return rc;
+  if (!params || !img_feat || !txt_feat || !labels || !logits || !loss_out || !grads || !workspace)
+    return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
+  DeviceInfo di;
+  if ((rc = device_info(&di))) return rc;
+  Workspace w = carve(*desc, true, workspace);
+  if (workspace_bytes < w.bytes) return fail(MMRCA_ERR_WORKSPACE, "workspace too small (training size needed)%s%s");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((rc = head_forward_impl(*desc, *params, img_feat, txt_feat, drop_mask, drop_scale, logits, w, di.sms, st)))
+    return rc;
+  if ((rc = launch_ce(logits, labels, ce, desc->batch, desc->n_classes, loss_out, w.dlogits, st))) return rc;
+  return head_backward_impl(*desc, *params, img_feat, txt_feat, drop_mask, drop_scale, w.dlogits, *grads, d_img_feat,
+                            d_txt_feat, w, di.sms, st);
+}
+
+int mmrca_attention_forward(const MmrcaAttnParams* p, const float* x_q, const float* x_kv, int32_t batch,
+                            int32_t d_in, int32_t d_kq, int32_t d_v, int32_t reverse, int32_t normalise,
+                            float* norms_out, float* out, int32_t compute, void* stream) {
+  if (!p || !x_q || !x_kv || !out) return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
+  if (compute != MMRCA_COMPUTE_FP32) return fail(MMRCA_ERR_INVALID, "only MMRCA_COMPUTE_FP32 is compiled in%s%s");
+  if (normalise && (x_q != x_kv || !norms_out))
+    return fail(MMRCA_ERR_INVALID, "normalise needs x_kv == x_q and a norms_out buffer%s%s");
+  DeviceInfo di;
+  int rc;
+  if ((rc = device_info(&di))) return rc;
+  AttnArgs a = make_attn_args(*p, x_q, x_kv, batch, reverse ? 1 : 0);
+  a.normalise = normalise ? 1 : 0; a.norms = norms_out; a.out = out;
+  return attn_dispatch(false, x_q == x_kv, d_in, d_kq, d_v, a, di.sms, static_cast<cudaStream_t>(stream));
+}
+
+size_t mmrca_attention_backward_scratch_bytes(int32_t batch, int32_t d_kq, int32_t d_v) {
+  return align_up(size_t(batch > 0 ? batch : 0) * kL * size_t(2 * d_kq + d_v) * sizeof(float));
+}
+
+int mmrca_attention_backward(const MmrcaAttnParams* p, const float* x_q, const float* x_kv, const float* d_out,
+                             int32_t batch, int32_t d_in, int32_t d_kq, int32_t d_v, int32_t reverse,
+                             const MmrcaAttnGrads* grads, float* d_x_q, float* d_x_kv, void* scratch,
+                             size_t scratch_bytes, int32_t compute, void* stream) {
+  if (!p || !x_q || !x_kv || !d_out || !grads || !scratch) return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
+  if (compute != MMRCA_COMPUTE_FP32) return fail(MMRCA_ERR_INVALID, "only MMRCA_COMPUTE_FP32 is compiled in%s%s");
+  if (scratch_bytes < mmrca_attention_backward_scratch_bytes(batch, d_kq, d_v))
+    return fail(MMRCA_ERR_WORKSPACE, "scratch too small%s%s");
+  const bool self = x_q == x_kv;
+  if (self && d_x_kv) return fail(MMRCA_ERR_INVALID, "self attention: pass d_x_kv = NULL, d_x_q receives the sum%s%s");
+  DeviceInfo di;
+  int rc;
+  if ((rc = device_info(&di))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AttnArgs a = make_attn_args(*p, x_q, x_kv, batch, reverse ? 1 : 0);
+  a.dout = d_out; a.dy = static_cast<float*>(scratch); a.dxq = d_x_q; a.dxkv = d_x_kv;
+  a.g_ln_g = grads->ln_g; a.g_ln_b = grads->ln_b;
+  if ((rc = attn_dispatch(true, self, d_in, d_kq, d_v, a, di.sms, st))) return rc;
+  return attn_wgrads(self, d_in, d_kq, d_v, a.dy, x_q, x_kv, nullptr, batch, *grads, di.sms, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,352 @@
+"""Host-side entry points of the MM-RCA fusion head: torch tensors in, libmmrca.so (C ABI) underneath.
+
+PyTorch is plumbing here (device memory, current stream, autograd bookkeeping); all arithmetic of
+the hot path — CVPR_code/multimodal_model.py:661-728 of the reference, its CrossEntropyLoss
+(main_both.py:87-93) and the backward through both (main_both.py:112) — runs in the sm_100a kernels.
+Nothing here falls back to torch ops or the CPU: non-CUDA inputs raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _native as N
+
+NUM_PATCHES = 16
+SA_DKQ, SA_DV, CA_DKQ, CA_DV = 128, 96, 64, 48
+
+_ATTN_LEAVES = ("W_query.weight", "W_query.bias", "W_key.weight", "W_key.bias",
+                "W_value.weight", "W_value.bias", "norm.weight", "norm.bias")
+_ATTN_FIELDS = ("wq", "bq", "wk", "bk", "wv", "bv", "ln_g", "ln_b")
+# order of the attention blocks inside MmrcaHeadParams
+_BLOCKS = (("sa_img", "self_attention_image"), ("sa_txt", "self_attention_text"),
+           ("ca1", "cross_attention_1"), ("ca2", "cross_attention_2"))
+
+
+def final_linear_name(features_only: bool, cross_attention_only: bool) -> str:
+    """Classifier used by the forward — reference multimodal_model.py:721-726."""
+    if features_only:
+        return "final_features_only_linear"
+    if cross_attention_only:
+        return "cross_attention_only_linear"
+    return "final_with_everything"
+
+
+def head_param_names(features_only: bool = False, cross_attention_only: bool = False) -> List[str]:
+    """state_dict names of the 34 tensors MM_RCA.forward reads, in the order of MmrcaHeadParams."""
+    names = [f"{mod}.{leaf}" for _, mod in _BLOCKS for leaf in _ATTN_LEAVES]
+    fin = final_linear_name(features_only, cross_attention_only)
+    return names + [f"{fin}.weight", f"{fin}.bias"]
+
+
+def head_param_shapes(d_img: int = 1280, d_txt: int = 768, n_classes: int = 4, features_only: bool = False,
+                      cross_attention_only: bool = False) -> List[Tuple[str, Tuple[int, ...]]]:
+    """(name, shape) of the head tensors in head_param_names order (reference multimodal_model.py:249-292)."""
+    out = []
+    dims = {"self_attention_image": (d_img // NUM_PATCHES, SA_DKQ, SA_DV),
+            "self_attention_text": (d_txt // NUM_PATCHES, SA_DKQ, SA_DV),
+            "cross_attention_1": (SA_DV, CA_DKQ, CA_DV), "cross_attention_2": (SA_DV, CA_DKQ, CA_DV)}
+    for _, mod in _BLOCKS:
+        d_in, d_kq, d_v = dims[mod]
+        out += [(f"{mod}.W_query.weight", (d_kq, d_in)), (f"{mod}.W_query.bias", (d_kq,)),
+                (f"{mod}.W_key.weight", (d_kq, d_in)), (f"{mod}.W_key.bias", (d_kq,)),
+                (f"{mod}.W_value.weight", (d_v, d_in)), (f"{mod}.W_value.bias", (d_v,)),
+                (f"{mod}.norm.weight", (d_v,)), (f"{mod}.norm.bias", (d_v,))]
+    fin = final_linear_name(features_only, cross_attention_only)
+    D = concat_width(d_img, d_txt, features_only, cross_attention_only)
+    return out + [(f"{fin}.weight", (n_classes, D)), (f"{fin}.bias", (n_classes,))]
+
+
+def init_head_parameters(device, d_img: int = 1280, d_txt: int = 768, n_classes: int = 4,
+                         features_only: bool = False, cross_attention_only: bool = False,
+                         seed: int = 0) -> List[torch.Tensor]:
+    """Random-init head tensors with the distributions torch.nn.Linear / LayerNorm use in the reference
+    ctor (uniform(-1/sqrt(fan_in), 1/sqrt(fan_in)); LayerNorm weight 1, bias 0)."""
+    g = torch.Generator().manual_seed(seed)
+    ps = []
+    for name, shape in head_param_shapes(d_img, d_txt, n_classes, features_only, cross_attention_only):
+        if name.endswith("norm.weight"):
+            t = torch.ones(shape)
+        elif name.endswith("norm.bias"):
+            t = torch.zeros(shape)
+        else:
+            fan_in = shape[1] if len(shape) == 2 else dict(head_param_shapes(
+                d_img, d_txt, n_classes, features_only, cross_attention_only))[name[:-4] + "weight"][1]
+            k = 1.0 / (fan_in ** 0.5)
+            t = (torch.rand(shape, generator=g) * 2 - 1) * k
+        ps.append(t.to(device))
+    return ps
+
+
+def concat_width(d_img: int, d_txt: int, features_only: bool, cross_attention_only: bool) -> int:
+    ca = 2 * NUM_PATCHES * CA_DV
+    if features_only:
+        return d_img + d_txt
+    if cross_attention_only:
+        return ca
+    return ca + d_img + d_txt
+
+
+def make_flags(reverse: bool, features_only: bool, cross_attention_only: bool) -> int:
+    return ((N.FLAG_REVERSE if reverse else 0) | (N.FLAG_FEATURES_ONLY if features_only else 0)
+            | (N.FLAG_CROSS_ATTENTION_ONLY if cross_attention_only else 0))
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _check_dev(t: torch.Tensor, what: str, dtype=torch.float32) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} must be a CUDA tensor: the MM-RCA head has no CPU fallback")
+    if t.dtype != dtype:
+        raise TypeError(f"{what} must be {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _head_struct(tensors: Sequence[Optional[torch.Tensor]]) -> N.HeadParams:
+    """Pack 34 tensors (order of head_param_names) into the MmrcaHeadParams / MmrcaHeadGrads layout."""
+    hp = N.HeadParams()
+    it = iter(tensors)
+    for field, _ in _BLOCKS:
+        blk = getattr(hp, field)
+        for leaf in _ATTN_FIELDS:
+            t = next(it)
+            setattr(blk, leaf, t.data_ptr() if t is not None else None)
+    for leaf in ("wf", "bf"):
+        t = next(it)
+        setattr(hp, leaf, t.data_ptr() if t is not None else None)
+    return hp
+
+
+def _desc(batch: int, d_img: int, d_txt: int, n_classes: int, flags: int, compute: int) -> N.HeadDesc:
+    return N.HeadDesc(batch, d_img, d_txt, n_classes, flags, compute)
+
+
+def workspace_bytes(batch: int, d_img: int, d_txt: int, n_classes: int, flags: int, compute: int,
+                    training: bool) -> int:
+    d = _desc(batch, d_img, d_txt, n_classes, flags, compute)
+    return int(N.lib().mmrca_head_workspace_bytes(C.byref(d), 1 if training else 0))
+
+
+class FlatGrads:
+    """One contiguous fp32 buffer holding the gradients of all head tensors (the single NCCL
+    all-reduce bucket, SURVEY.md §8 e) plus per-tensor views in head_param_names order."""
+
+    def __init__(self, params: Sequence[torch.Tensor]):
+        dev = params[0].device
+        # 4-float alignment per tensor keeps every view 16-byte aligned
+        self.offsets, off = [], 0
+        for p in params:
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.views = [self.flat[o:o + p.numel()].view(p.shape) for o, p in zip(self.offsets, params)]
+
+    def zero_(self):
+        self.flat.zero_()
+        return self
+
+
+class _HeadFunction(torch.autograd.Function):
+    """logits = MM_RCA head(img_feat, txt_feat); backward recomputes attention internals on chip."""
+
+    @staticmethod
+    def forward(ctx, img, txt, drop_mask, drop_scale, flags, n_classes, compute, *params):
+        img = _check_dev(img, "image features")
+        txt = _check_dev(txt, "text features")
+        params = [_check_dev(p, "head parameter") for p in params]
+        if drop_mask is not None:
+            drop_mask = _check_dev(drop_mask, "dropout mask", torch.uint8)
+        B, d_img, d_txt = img.shape[0], img.shape[1], txt.shape[1]
+        if txt.shape[0] != B:
+            raise ValueError("image and text feature batches differ")
+        needs_bwd = any(ctx.needs_input_grad)
+        desc = _desc(B, d_img, d_txt, n_classes, flags, compute)
+        L = N.lib()
+        ws = torch.empty(max(1, L.mmrca_head_workspace_bytes(C.byref(desc), 1 if needs_bwd else 0)),
+                         dtype=torch.uint8, device=img.device)
+        logits = torch.empty(B, n_classes, dtype=torch.float32, device=img.device)
+        hp = _head_struct(params)
+        with torch.cuda.device(img.device):
+            N.check(L.mmrca_head_forward(C.byref(desc), C.byref(hp), img.data_ptr(), txt.data_ptr(),
+                                         drop_mask.data_ptr() if drop_mask is not None else None,
+                                         float(drop_scale), logits.data_ptr(), ws.data_ptr(), ws.numel(),
+                                         _stream_ptr(img.device)), "mmrca_head_forward")
+        ctx.save_for_backward(img, txt, drop_mask, ws, *params)
+        ctx.cfg = (drop_scale, flags, n_classes, compute)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        img, txt, drop_mask, ws, *params = ctx.saved_tensors
+        drop_scale, flags, n_classes, compute = ctx.cfg
+        dlogits = _check_dev(dlogits, "dlogits")
+        B = img.shape[0]
+        desc = _desc(B, img.shape[1], txt.shape[1], n_classes, flags, compute)
+        fg = FlatGrads(params)
+        want_feat = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        d_img = torch.empty_like(img) if want_feat else None
+        d_txt = torch.empty_like(txt) if want_feat else None
+        hp, hg = _head_struct(params), _head_struct(fg.views)
+        L = N.lib()
+        with torch.cuda.device(img.device):
+            N.check(L.mmrca_head_backward(C.byref(desc), C.byref(hp), img.data_ptr(), txt.data_ptr(),
+                                          drop_mask.data_ptr() if drop_mask is not None else None,
+                                          float(drop_scale), dlogits.data_ptr(), C.byref(hg),
+                                          d_img.data_ptr() if want_feat else None,
+                                          d_txt.data_ptr() if want_feat else None,
+                                          ws.data_ptr(), ws.numel(), _stream_ptr(img.device)),
+                    "mmrca_head_backward")
+        features_only = bool(flags & N.FLAG_FEATURES_ONLY)
+        pg = []
+        for i, v in enumerate(fg.views):
+            need = ctx.needs_input_grad[7 + i]
+            # features_only: the attention blocks are outside the graph in the reference (their result is
+            # discarded, multimodal_model.py:676-699) -> grad None, like autograd there.
+            pg.append(v if need and not (features_only and i < 32) else None)
+        return (d_img if ctx.needs_input_grad[0] else None, d_txt if ctx.needs_input_grad[1] else None,
+                None, None, None, None, None, *pg)
+
+
+def mmrca_head(img_feat: torch.Tensor, txt_feat: torch.Tensor, params: Sequence[torch.Tensor], *,
+               reverse: bool, features_only: bool = False, cross_attention_only: bool = False,
+               n_classes: int = 4, drop_mask: Optional[torch.Tensor] = None, drop_scale: float = 1.0,
+               compute: int = N.COMPUTE_FP32) -> torch.Tensor:
+    """Fusion head of MM_RCA.forward (reference multimodal_model.py:661-728) on pooled features.
+
+    params: the 34 tensors in head_param_names(features_only, cross_attention_only) order.
+    drop_mask: uint8 keep-mask [B, D] standing in for self.drop (:719), kept values scaled by drop_scale.
+    """
+    flags = make_flags(reverse, features_only, cross_attention_only)
+    return _HeadFunction.apply(img_feat, txt_feat, drop_mask, drop_scale, flags, n_classes, compute, *params)
+
+
+def cross_entropy(logits: torch.Tensor, labels: torch.Tensor, class_weight: Optional[torch.Tensor] = None,
+                  label_smoothing: float = 0.0, want_dlogits: bool = True
+                  ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """torch.nn.CrossEntropyLoss(weight, label_smoothing) forward + dL/dlogits (reference
+    main_both.py:87-93,110) in one kernel.  Returns (loss[1], dlogits or None)."""
+    logits = _check_dev(logits, "logits")
+    labels = _check_dev(labels, "labels", torch.int64)
+    cw = _check_dev(class_weight, "class weights") if class_weight is not None else None
+    B, nc = logits.shape
+    loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+    dl = torch.empty_like(logits) if want_dlogits else None
+    ce = N.CeDesc(cw.data_ptr() if cw is not None else None, float(label_smoothing))
+    with torch.cuda.device(logits.device):
+        N.check(N.lib().mmrca_cross_entropy(logits.data_ptr(), labels.data_ptr(), C.byref(ce), B, nc,
+                                            loss.data_ptr(), dl.data_ptr() if dl is not None else None,
+                                            _stream_ptr(logits.device)), "mmrca_cross_entropy")
+    return loss, dl
+
+
+class HeadTrainStep:
+    """Persistent buffers for the one-call training step of the head (forward + CrossEntropyLoss +
+    backward = the body of run_one_epoch, reference main_both.py:106-112, restricted to the head).
+
+    Gradients are ACCUMULATED into `grads.flat` (like loss.backward()); call zero_grad() between
+    optimizer steps.  `grads.flat` is the bucket a data-parallel job all-reduces once per step."""
+
+    def __init__(self, params: Sequence[torch.Tensor], batch: int, d_img: int, d_txt: int, *, reverse: bool,
+                 features_only: bool = False, cross_attention_only: bool = False, n_classes: int = 4,
+                 class_weight: Optional[torch.Tensor] = None, label_smoothing: float = 0.0,
+                 compute: int = N.COMPUTE_FP32, feature_grads: bool = False):
+        self.params = [_check_dev(p.detach(), "head parameter") for p in params]
+        dev = self.params[0].device
+        self.flags = make_flags(reverse, features_only, cross_attention_only)
+        self.desc = _desc(batch, d_img, d_txt, n_classes, self.flags, compute)
+        self.grads = FlatGrads(self.params)
+        self.hp, self.hg = _head_struct(self.params), _head_struct(self.grads.views)
+        L = N.lib()
+        self.ws = torch.empty(max(1, L.mmrca_head_workspace_bytes(C.byref(self.desc), 1)), dtype=torch.uint8,
+                              device=dev)
+        self.logits = torch.empty(batch, n_classes, dtype=torch.float32, device=dev)
+        self.loss = torch.empty(1, dtype=torch.float32, device=dev)
+        self.cw = _check_dev(class_weight, "class weights") if class_weight is not None else None
+        self.ce = N.CeDesc(self.cw.data_ptr() if self.cw is not None else None, float(label_smoothing))
+        self.d_img = torch.empty(batch, d_img, dtype=torch.float32, device=dev) if feature_grads else None
+        self.d_txt = torch.empty(batch, d_txt, dtype=torch.float32, device=dev) if feature_grads else None
+        self.device = dev
+
+    def zero_grad(self):
+        self.grads.zero_()
+
+    def __call__(self, img: torch.Tensor, txt: torch.Tensor, labels: torch.Tensor,
+                 drop_mask: Optional[torch.Tensor] = None, drop_scale: float = 1.0):
+        img, txt = _check_dev(img, "image features"), _check_dev(txt, "text features")
+        labels = _check_dev(labels, "labels", torch.int64)
+        if img.shape != (self.desc.batch, self.desc.d_img) or txt.shape != (self.desc.batch, self.desc.d_txt):
+            raise ValueError("feature shapes do not match the shapes this step was built for")
+        if drop_mask is not None:
+            drop_mask = _check_dev(drop_mask, "dropout mask", torch.uint8)
+        with torch.cuda.device(self.device):
+            N.check(N.lib().mmrca_head_train_step(
+                C.byref(self.desc), C.byref(self.hp), img.data_ptr(), txt.data_ptr(),
+                drop_mask.data_ptr() if drop_mask is not None else None, float(drop_scale), labels.data_ptr(),
+                C.byref(self.ce), self.logits.data_ptr(), self.loss.data_ptr(), C.byref(self.hg),
+                self.d_img.data_ptr() if self.d_img is not None else None,
+                self.d_txt.data_ptr() if self.d_txt is not None else None,
+                self.ws.data_ptr(), self.ws.numel(), _stream_ptr(self.device)), "mmrca_head_train_step")
+        return self.loss, self.logits
+
+
+def _attn_struct(tensors: Sequence[torch.Tensor]) -> N.AttnParams:
+    ap = N.AttnParams()
+    for f, t in zip(_ATTN_FIELDS, tensors):
+        setattr(ap, f, t.data_ptr())
+    return ap
+
+
+class _AttentionFunction(torch.autograd.Function):
+    """One SelfAttention (x_kv is x_q) / ReverseCrossAttention block, reference multimodal_model.py:39-108."""
+
+    @staticmethod
+    def forward(ctx, x_q, x_kv, reverse, is_self, compute, *params):
+        x_q = _check_dev(x_q, "x_q")
+        x_kv = x_q if is_self else _check_dev(x_kv, "x_kv")
+        params = [_check_dev(p, "attention parameter") for p in params]
+        B, Lr, d_in = x_q.shape
+        if Lr != NUM_PATCHES or x_kv.shape != x_q.shape:
+            raise ValueError("attention block expects [B, 16, d_in] inputs of equal shape (square attention, "
+                             "reference multimodal_model.py:93)")
+        d_kq, d_v = params[0].shape[0], params[4].shape[0]
+        out = torch.empty(B, Lr, d_v, dtype=torch.float32, device=x_q.device)
+        ap = _attn_struct(params)
+        with torch.cuda.device(x_q.device):
+            N.check(N.lib().mmrca_attention_forward(C.byref(ap), x_q.data_ptr(), x_kv.data_ptr(), B, d_in, d_kq,
+                                                    d_v, 1 if reverse else 0, 0, None, out.data_ptr(), compute,
+                                                    _stream_ptr(x_q.device)), "mmrca_attention_forward")
+        ctx.save_for_backward(x_q, x_kv, *params)
+        ctx.cfg = (reverse, is_self, compute, d_in, d_kq, d_v)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x_q, x_kv, *params = ctx.saved_tensors
+        reverse, is_self, compute, d_in, d_kq, d_v = ctx.cfg
+        d_out = _check_dev(d_out, "d_out")
+        B = x_q.shape[0]
+        L = N.lib()
+        fg = FlatGrads(params)
+        scratch = torch.empty(max(1, L.mmrca_attention_backward_scratch_bytes(B, d_kq, d_v)), dtype=torch.uint8,
+                              device=x_q.device)
+        dxq = torch.empty_like(x_q)
+        dxkv = None if is_self else torch.empty_like(x_kv)
+        ap, ag = _attn_struct(params), _attn_struct(fg.views)
+        with torch.cuda.device(x_q.device):
+            N.check(L.mmrca_attention_backward(C.byref(ap), x_q.data_ptr(), x_kv.data_ptr(), d_out.data_ptr(), B,
+                                               d_in, d_kq, d_v, 1 if reverse else 0, C.byref(ag), dxq.data_ptr(),
+                                               dxkv.data_ptr() if dxkv is not None else None, scratch.data_ptr(),
+                                               scratch.numel(), compute, _stream_ptr(x_q.device)),
+                    "mmrca_attention_backward")
+        return (dxq, dxkv, None, None, None, *fg.views)
+
+
+def attention_block(x_q: torch.Tensor, x_kv: Optional[torch.Tensor], params: Sequence[torch.Tensor], *,
+                    reverse: bool = False, compute: int = N.COMPUTE_FP32) -> torch.Tensor:
+    """params: (Wq, bq, Wk, bk, Wv, bv, ln_weight, ln_bias).  x_kv=None -> self attention."""
+    is_self = x_kv is None or x_kv is x_q
+    return _AttentionFunction.apply(x_q, x_q if is_self else x_kv, reverse, is_self, compute, *params)

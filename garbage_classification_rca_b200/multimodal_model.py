@@ -1,0 +1,368 @@
+"""Drop-in mirror of the reference's model API for the MM-RCA late-fusion path.
+
+Same class names, constructor arguments, forward(_input_ids, _attention_mask, _images, eval,
+remove_image, remove_text) signature, helper methods and .pth state_dict layout as
+CVPR_code/multimodal_model.py of espiriki/Garbage_Classification_RCA — but everything after the
+backbones (reference :661-728) runs in the sm_100a kernels behind libmmrca.so.  The image / text
+backbones stay stock torchvision / HuggingFace modules (north_star).
+
+Deviations, all documented in SURVEY.md §0:
+  * trailing ctor args are defaulted (batch_size=16, reverse=False, features_only=False,
+    cross_attention_only=False) so that the reference's own 8/9-argument call sites work;
+  * `pretrained=` / `compute=` / `dropout_generator=` keyword-only extensions;
+  * features_only skips the attention blocks the reference computes and discards (:676-699).
+"""
+from __future__ import annotations
+
+import math
+import sys
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _native as N
+from . import functional as F
+
+_TEXT_HIDDEN = {"distilbert": 768, "bert": 768, "bart": 1024}
+IMAGE_FEATURES = 1280   # reference :258 (EfficientNetV2 pooled width)
+
+
+# ---------------------------------------------------------------------------------------------
+# backbones (stock modules; reference :11-36, :113-153)
+# ---------------------------------------------------------------------------------------------
+class EfficientNetV2MFullFeatureExtractor(nn.Module):
+    """Re-registers slices of torchvision's EfficientNetV2 `features` under the names the reference
+    uses (stem, stage1..stage6, final_conv — reference :14-23) so checkpoint keys interchange, and
+    returns (stage-3 map, stage-6 map, pooled vector) like reference :25-36."""
+
+    STAGES = ("stage1", "stage2", "stage3", "stage4", "stage5", "stage6")
+
+    def __init__(self, model: nn.Module):
+        super().__init__()
+        feats = model.features
+        self.stem = feats[:2]
+        for i, name in enumerate(self.STAGES):
+            setattr(self, name, feats[2 + i])
+        self.final_conv = feats[8]
+        self.avgpool = model.avgpool
+        self.classifier = model.classifier   # registered but never applied (reference :23)
+
+    def forward(self, x):
+        x = self.stem(x)
+        taps = {}
+        for name in self.STAGES:
+            x = getattr(self, name)(x)
+            taps[name] = x
+        pooled = torch.flatten(self.avgpool(self.final_conv(x)), 1)
+        return taps["stage3"], taps["stage6"], pooled
+
+
+def _freeze(m: nn.Module) -> nn.Module:
+    for p in m.parameters():
+        p.requires_grad = False
+    return m
+
+
+def eff_net_v2(pretrained: bool = True) -> nn.Module:
+    """EfficientNetV2-M feature extractor, frozen, classifier trimmed to its Dropout (reference :113-126)."""
+    from torchvision.models import efficientnet_v2_m
+    model = _freeze(efficientnet_v2_m(weights="IMAGENET1K_V1" if pretrained else None))
+    model.classifier = nn.Sequential(model.classifier[0])
+    return EfficientNetV2MFullFeatureExtractor(model)
+
+
+def distilbert(pretrained: bool = True) -> nn.Module:
+    from transformers import DistilBertConfig, DistilBertModel
+    m = DistilBertModel.from_pretrained("distilbert-base-uncased") if pretrained else DistilBertModel(DistilBertConfig())
+    return _freeze(m)
+
+
+def bert(pretrained: bool = True) -> nn.Module:
+    from transformers import BertConfig, BertModel
+    m = BertModel.from_pretrained("bert-base-uncased") if pretrained else BertModel(BertConfig())
+    return _freeze(m)
+
+
+def bart(pretrained: bool = True) -> nn.Module:
+    from transformers import BartConfig, BartModel
+    m = BartModel.from_pretrained("facebook/bart-large") if pretrained else BartModel(BartConfig())
+    return _freeze(m)
+
+
+_TEXT_FACTORIES = {"bert": bert, "distilbert": distilbert, "bart": bart}
+
+
+def decision(probability: float) -> bool:
+    """Host-side coin flip of the modality dropout (reference :110-111)."""
+    return np.random.rand(1)[0] < probability
+
+
+# ---------------------------------------------------------------------------------------------
+# attention blocks: parameter holders whose forward is one fused CUDA kernel
+# ---------------------------------------------------------------------------------------------
+class _AttentionBase(nn.Module):
+    def __init__(self, d_in_q: int, d_in_kv: int, d_out_kq: int, d_out_v: int):
+        super().__init__()
+        self.d_out_kq = d_out_kq
+        self.W_query = nn.Linear(d_in_q, d_out_kq)
+        self.W_key = nn.Linear(d_in_kv, d_out_kq)
+        self.W_value = nn.Linear(d_in_kv, d_out_v)
+        self.norm = nn.LayerNorm(d_out_v)
+        self.relu = nn.ReLU()
+        self.compute = N.COMPUTE_FP32
+
+    def _params(self) -> Tuple[torch.Tensor, ...]:
+        return (self.W_query.weight, self.W_query.bias, self.W_key.weight, self.W_key.bias,
+                self.W_value.weight, self.W_value.bias, self.norm.weight, self.norm.bias)
+
+
+class SelfAttention(_AttentionBase):
+    """Reference :39-68: softmax(QK^T/sqrt(d_kq)) V -> LayerNorm -> ReLU, one kernel."""
+
+    def __init__(self, d_in, d_out_kq, d_out_v, name):
+        super().__init__(d_in, d_in, d_out_kq, d_out_v)
+        self.name = name
+
+    def forward(self, x):
+        return F.attention_block(x, None, self._params(), reverse=False, compute=self.compute)
+
+
+class ReverseCrossAttention(_AttentionBase):
+    """Reference :71-108: queries from x_1, keys/values from x_2; with `reverse` the weights become
+    (1 - A) / (L - 1) (:97-98)."""
+
+    def __init__(self, d_in_x1, d_in_x2, d_out_kq, d_out_v, reverse):
+        super().__init__(d_in_x1, d_in_x2, d_out_kq, d_out_v)
+        self.reverse = reverse
+
+    def forward(self, x_1, x_2):
+        if x_1.shape[1] != x_2.shape[1]:
+            raise AssertionError("ReverseCrossAttention needs square attention (reference :93)")
+        return F.attention_block(x_1, x_2, self._params(), reverse=bool(self.reverse), compute=self.compute)
+
+
+class Hadamard2(nn.Module):
+    """Reference :822-831 (dead for MM_RCA; kept because its tensors are in every checkpoint)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.kernel1 = nn.Parameter(torch.randn(dim))
+        self.kernel2 = nn.Parameter(torch.randn(dim))
+        self.bias = nn.Parameter(torch.zeros(dim))
+
+    def forward(self, x1, x2):
+        return torch.tanh(x1 * self.kernel1 + x2 * self.kernel2 + self.bias)
+
+
+# ---------------------------------------------------------------------------------------------
+# the shared base: allocates the parameters of EVERY fusion variant so they share one state_dict
+# ---------------------------------------------------------------------------------------------
+class EffV2MediumAndDistilbertGated(nn.Module):
+    """Shared constructor of all fusion variants (reference :156-328).  Registration order and names
+    reproduce the reference state_dict (tests/golden/state_dict_layout.json)."""
+
+    def __init__(self, n_classes, drop_ratio, image_or_text_dropout_chance, img_prob_dropout, num_neurons_fc,
+                 text_model_name, batch_size=16, reverse=False, features_only=False, cross_attention_only=False,
+                 *, pretrained: bool = True, compute: int = N.COMPUTE_FP32,
+                 dropout_generator: Optional[torch.Generator] = None):
+        super().__init__()
+        self.text_model_name = text_model_name
+        self.features_only = features_only
+        self.cross_attention_only = cross_attention_only
+        self.reverse = reverse
+        self.n_classes = n_classes
+        self.compute = compute
+        self.dropout_generator = dropout_generator
+        print("Only features:", self.features_only)
+        print("Only cross attention:", self.cross_attention_only)
+        if text_model_name not in _TEXT_FACTORIES:
+            print("Wrong text model:", text_model_name)
+            sys.exit(1)
+        self.text_model = _TEXT_FACTORIES[text_model_name](pretrained)
+        self.image_model = eff_net_v2(pretrained)
+
+        self.fc_layer_neurons = num_neurons_fc
+        self.image_or_text_dropout_chance = image_or_text_dropout_chance
+        self.img_dropout_prob = img_prob_dropout
+        self.batch_size = batch_size
+        self.gated_output_hidden_size = 256
+        self.num_patches = F.NUM_PATCHES
+        hidden_txt = self.text_model.config.hidden_size
+        print("Text model hidden size:", hidden_txt)
+        input_size_txt, input_size_img = 768, IMAGE_FEATURES          # literals, reference :257-258
+        self.txt_patch_size = input_size_txt // self.num_patches
+        self.img_patch_size = input_size_img // self.num_patches
+        print("txt patch size: ", self.txt_patch_size)
+        print("img patch size: ", self.img_patch_size)
+        self.modality_dim = 400
+        ca_flat = F.CA_DV * self.num_patches * 2                     # 1536
+
+        h, g = num_neurons_fc, self.gated_output_hidden_size
+        table: List[Tuple[str, Optional[Callable[[], nn.Module]]]] = [
+            ("drop", lambda: nn.Dropout(p=drop_ratio)),
+            ("image_dropout", lambda: nn.Dropout2d(p=1.0)),
+            ("text_dropout", lambda: nn.Dropout1d(p=1.0)),
+            ("image_to_hidden_size", lambda: nn.Linear(IMAGE_FEATURES, h)),
+            ("text_to_hidden_size", lambda: nn.Linear(hidden_txt, h)),
+            ("concat_layer", lambda: nn.Linear(2 * h, h)),
+            ("fc_layer", lambda: nn.Linear(h, n_classes)),
+            ("hyper_tang_layer", nn.Tanh),
+            ("softmax_layer", lambda: nn.Softmax(dim=1)),
+            ("image_features_hidden_layer", lambda: nn.Linear(IMAGE_FEATURES, g)),
+            ("text_features_hidden_layer", lambda: nn.Linear(hidden_txt, g)),
+            ("z_layer", lambda: nn.Linear(2 * g, g)),
+            ("fc_layer_gated", lambda: nn.Linear(g, n_classes)),
+            ("clip_fc_layer", lambda: nn.Linear(batch_size, n_classes)),
+            ("trans_conv", lambda: nn.ConvTranspose1d(8, 8, kernel_size=2, stride=2, padding=0, output_padding=0)),
+            ("logit_scale", None),
+            ("output_all_features", lambda: nn.Linear(640, 4)),
+            ("self_attention_image", lambda: SelfAttention(self.img_patch_size, F.SA_DKQ, F.SA_DV, "Img block")),
+            ("self_attention_text", lambda: SelfAttention(self.txt_patch_size, F.SA_DKQ, F.SA_DV, "Txt block")),
+            ("cross_attention_1", lambda: ReverseCrossAttention(F.SA_DV, F.SA_DV, F.CA_DKQ, F.CA_DV, reverse)),
+            ("cross_attention_2", lambda: ReverseCrossAttention(F.SA_DV, F.SA_DV, F.CA_DKQ, F.CA_DV, reverse)),
+            ("final", lambda: nn.Linear(ca_flat, n_classes)),
+            ("final_features_only_linear",
+             (lambda: nn.Linear(IMAGE_FEATURES + 768, n_classes)) if features_only else "skip"),
+            ("cross_attention_only_linear",
+             (lambda: nn.Linear(ca_flat, n_classes)) if cross_attention_only else "skip"),
+            ("final_with_everything", lambda: nn.Linear(ca_flat + IMAGE_FEATURES + 768, n_classes)),
+            ("final_hierarchical_image", lambda: nn.Linear(1280 + 2560 + 2048, 512)),
+            ("final_hierarchical_text", lambda: nn.Linear(768 * 3, 512)),
+            ("final_hierarchical_all", lambda: nn.Linear(512 * 2, n_classes)),
+            ("relu", nn.ReLU),
+            ("gru_text", lambda: nn.GRU(self.modality_dim, self.modality_dim, batch_first=True)),
+            ("gru_audio", lambda: nn.GRU(self.modality_dim, self.modality_dim, batch_first=True)),
+            ("fusion", lambda: Hadamard2(self.modality_dim)),
+            ("gru_bimodal", lambda: _quiet_gru(self.modality_dim, 500)),
+            ("dropout1", lambda: nn.Dropout(0.86)),
+            ("concat_fc", lambda: nn.Linear(self.modality_dim + 500, 450)),
+            ("dropout2", lambda: nn.Dropout(0.86)),
+            ("modality_image_to_dim", lambda: nn.Linear(1280, self.modality_dim)),
+            ("modality_text_to_dim", lambda: nn.Linear(768, self.modality_dim)),
+            ("classifier", lambda: nn.Linear(450, 4)),
+        ]
+        for name, factory in table:
+            if factory == "skip":
+                continue
+            if name == "logit_scale":
+                self.logit_scale = nn.Parameter(torch.ones([]) * np.log(1 / 0.07))   # reference :244-245
+                continue
+            setattr(self, name, factory())
+        for blk in (self.self_attention_image, self.self_attention_text, self.cross_attention_1,
+                    self.cross_attention_2):
+            blk.compute = compute
+        self._head_names = F.head_param_names(bool(features_only), bool(cross_attention_only))
+
+    # ---- helpers the drivers call (reference :397-418) -------------------------------------------
+    def get_tokenizer(self):
+        from transformers import BartTokenizer, BertTokenizer, DistilBertTokenizer
+        src = {"bert": (BertTokenizer, "bert-base-uncased"),
+               "distilbert": (DistilBertTokenizer, "distilbert-base-uncased"),
+               "bart": (BartTokenizer, "facebook/bart-large")}[self.text_model_name]
+        self.tokenizer = src[0].from_pretrained(src[1])
+        return self.tokenizer
+
+    def get_image_size(self):
+        return (480, 480)
+
+    def get_max_token_size(self):
+        from transformers import BartConfig, BertConfig, DistilBertConfig
+        cfg = {"bert": BertConfig, "distilbert": DistilBertConfig, "bart": BartConfig}[self.text_model_name]
+        self.config = cfg().max_position_embeddings
+        return self.config
+
+    def drop_modalities(self, _eval, remove_image, remove_text):
+        """Host-side modality gating (reference :420-455): zero the whole image batch or the
+        token ids + attention mask; in training two numpy coin flips decide."""
+        zero_image = zero_text = False
+        if _eval:
+            zero_image, zero_text = bool(remove_image), bool(remove_text)
+            if zero_image:
+                print("    Eval: zero image")
+            if zero_text:
+                print("    Eval: zero text")
+        elif decision(self.image_or_text_dropout_chance):
+            if decision(self.img_dropout_prob):
+                print("    Train: zeroing image\n")
+                zero_image = True
+            else:
+                print("    Train: zeroing text\n")
+                zero_text = True
+        if zero_image:
+            self._images = torch.zeros_like(self._images)
+        if zero_text:
+            self._input_ids = torch.zeros_like(self._input_ids)
+            self._attention_mask = torch.zeros_like(self._attention_mask)
+
+    # ---- shared pieces of the subclass forwards -------------------------------------------------
+    def _backbone_features(self, output_hidden_states: bool = False):
+        kw = {"output_hidden_states": True} if output_hidden_states else {}
+        text_output = self.text_model(input_ids=self._input_ids, attention_mask=self._attention_mask, **kw)
+        text_features = text_output[0][:, 0]
+        image_out = self.image_model(self._images)
+        return text_output, text_features, image_out
+
+    def head_parameters(self) -> List[torch.Tensor]:
+        """The tensors MM_RCA.forward reads, in MmrcaHeadParams order."""
+        sd = dict(self.named_parameters())
+        return [sd[n] for n in self._head_names]
+
+    def forward(self, _input_ids, _attention_mask, _images, eval=False, remove_image=False, remove_text=False):
+        raise NotImplementedError(
+            "only the MM_RCA late-fusion path is rebuilt B200-native in this package; the gated / classic / "
+            "normalized / CLIP variants keep their parameters (state_dict parity) but have no forward here")
+
+
+def _quiet_gru(inp, hid):
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return nn.GRU(inp, hid, batch_first=True, dropout=0.35)   # reference :318 (warns: 1 layer + dropout)
+
+
+class MM_RCA(EffV2MediumAndDistilbertGated):
+    """Multimodal reverse-cross-attention classifier (reference :636-728)."""
+
+    def _dropout_mask(self, batch: int, width: int, device) -> Tuple[Optional[torch.Tensor], float]:
+        p = float(self.drop.p)
+        if not self.training or p <= 0.0:
+            return None, 1.0
+        if p >= 1.0:
+            return torch.zeros(batch, width, dtype=torch.uint8, device=device), 0.0
+        keep = torch.rand(batch, width, device=device, generator=self.dropout_generator) >= p
+        return keep.to(torch.uint8), 1.0 / (1.0 - p)
+
+    def forward_features(self, image_features: torch.Tensor, text_features: torch.Tensor,
+                         drop_mask: Optional[torch.Tensor] = None, drop_scale: Optional[float] = None):
+        """Fusion head on pooled features [B,1280] / [B,768] (reference :661-728).  `drop_mask` overrides
+        the internally drawn dropout mask (parity tests pass the mask torch.nn.Dropout drew)."""
+        image_features = image_features.float()
+        text_features = text_features.float()
+        if drop_mask is None:
+            width = F.concat_width(image_features.shape[1], text_features.shape[1], bool(self.features_only),
+                                   bool(self.cross_attention_only))
+            drop_mask, drop_scale = self._dropout_mask(image_features.shape[0], width, image_features.device)
+        elif drop_scale is None:
+            drop_scale = 1.0 / (1.0 - float(self.drop.p))
+        return F.mmrca_head(image_features, text_features, self.head_parameters(), reverse=bool(self.reverse),
+                            features_only=bool(self.features_only),
+                            cross_attention_only=bool(self.cross_attention_only), n_classes=self.n_classes,
+                            drop_mask=drop_mask, drop_scale=drop_scale, compute=self.compute)
+
+    def forward(self, _input_ids, _attention_mask, _images, eval=False, remove_image=False, remove_text=False):
+        self._images = _images
+        self._input_ids = _input_ids
+        self._attention_mask = _attention_mask
+        self.drop_modalities(eval, remove_image, remove_text)
+        _, text_features, (_, _, image_features) = self._backbone_features()
+        return self.forward_features(image_features, text_features)
+
+
+def load_reference_state_dict(model: nn.Module, state_dict, strict: bool = True):
+    """load_state_dict that also accepts checkpoints saved from an nn.DataParallel wrapper
+    (`module.` prefix)."""
+    if state_dict and all(k.startswith("module.") for k in state_dict):
+        state_dict = {k[len("module."):]: v for k, v in state_dict.items()}
+    return model.load_state_dict(state_dict, strict=strict)

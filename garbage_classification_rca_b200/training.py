@@ -1,0 +1,143 @@
+"""Training-loop pieces around the hot path: the reference's loss / backward / optimizer-step semantics
+(main_both.py:81-134), model dispatch (main_both.py:272-343), checkpoint save (main_both.py:201-226)
+and the data-parallel plumbing the reference never had (it only wraps nn.DataParallel and that path
+crashes): one process per GPU, batch-sharded, ONE all-reduce of the flat head-gradient
+bucket per optimizer step.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import _native as N
+from . import functional as F
+
+
+# ---- loss -----------------------------------------------------------------------------------------------
+class _CrossEntropyFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, weight, label_smoothing):
+        loss, dlogits = F.cross_entropy(logits, labels, weight, label_smoothing, want_dlogits=True)
+        ctx.save_for_backward(dlogits)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (dlogits,) = ctx.saved_tensors
+        return dlogits * grad_out, None, None, None
+
+
+class CrossEntropyLoss(nn.Module):
+    """torch.nn.CrossEntropyLoss(weight=, label_smoothing=) with mean reduction (what run_one_epoch builds,
+    reference main_both.py:87-93), as one fused forward+dlogits kernel."""
+
+    def __init__(self, weight: Optional[torch.Tensor] = None, label_smoothing: float = 0.0):
+        super().__init__()
+        self.register_buffer("weight", weight)
+        self.label_smoothing = label_smoothing
+
+    def forward(self, logits, labels):
+        return _CrossEntropyFunction.apply(logits, labels, self.weight, self.label_smoothing)
+
+
+# ---- model dispatch -------------------------------------------------------------------------------------
+def build_model(args, n_classes: int = 4, pretrained: bool = True):
+    """--late_fusion dispatch (reference main_both.py:272-343).  Only the MM-RCA path is rebuilt here."""
+    from . import multimodal_model as mm
+    compute = N.COMPUTE_BF16 if getattr(args, "compute", "fp32") == "bf16" else N.COMPUTE_FP32
+    common = (n_classes, args.model_dropout, args.image_text_dropout, args.image_prob_dropout,
+              args.num_neurons_FC, args.text_model, args.batch_size, args.reverse)
+    if args.late_fusion == "MM_RCA":
+        return mm.MM_RCA(*common, args.features_only, args.cross_attention_only, pretrained=pretrained,
+                         compute=compute)
+    raise SystemExit(f"late fusion strategy {args.late_fusion!r} is outside the B200-native hot path "
+                     "(MM_RCA is; see SURVEY.md §8)")
+
+
+# ---- data-parallel plumbing -----------------------------------------------------------------------------
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) slice of n samples owned by `rank` (balanced to within one sample)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
+    """The single collective of a data-parallel head step: sum the flat gradient bucket over ranks and
+    divide by the world size (equal shards + per-rank mean loss == global mean loss; with class weights
+    the per-rank normaliser differs, SURVEY.md §8 e)."""
+    if dist.is_available() and dist.is_initialized():
+        world = dist.get_world_size(group)
+        if world > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            flat.div_(world)
+    return flat
+
+
+class HeadDataParallel:
+    """Batch-sharded training of the fusion head on precomputed features: each rank runs the one-call
+    train step on its shard, then ONE all-reduce of `step.grads.flat` (94 820 floats, 379 KB)."""
+
+    def __init__(self, step: F.HeadTrainStep, group=None):
+        self.step = step
+        self.group = group
+
+    def __call__(self, img, txt, labels, drop_mask=None, drop_scale=1.0, sync: bool = True):
+        loss, logits = self.step(img, txt, labels, drop_mask, drop_scale)
+        if sync:   # sync=False == DDP.no_sync() while accumulating (reference steps every acc_steps batches)
+            allreduce_mean_(self.step.grads.flat, self.group)
+        return loss, logits
+
+
+def attach_flat_grads(params: Sequence[nn.Parameter], grads: F.FlatGrads) -> None:
+    """Point every head parameter's .grad at its view of the flat bucket so a stock torch optimizer
+    consumes the kernels' output without copies."""
+    for p, v in zip(params, grads.views):
+        p.grad = v
+
+
+# ---- one epoch, reference semantics ---------------------------------------------------------------------
+def run_one_epoch(epoch_num, model, data_loader, len_train_data, hw_device, batch_size, train_optimizer, weights,
+                  use_class_weights, acc_steps, smoothing, verbose: bool = False):
+    """Mirror of run_one_epoch (reference main_both.py:81-134) including its quirks: gradients are NOT
+    scaled by 1/acc_steps (the division happens after backward, :112-114), the optimizer steps every
+    acc_steps batches and on the last batch, and the loss is read back every batch (:128-130)."""
+    n_batches = math.ceil(len_train_data / batch_size)
+    cw = torch.tensor(weights, dtype=torch.float32, device=hw_device) if use_class_weights else None
+    criterion = CrossEntropyLoss(weight=cw, label_smoothing=smoothing)
+    batch_loss: List[torch.Tensor] = []
+    n_total = len(data_loader)
+    for batch_idx, (data, labels) in enumerate(data_loader):
+        ids = data["text"]["tokens"].to(hw_device)
+        mask = data["text"]["attention_mask"].to(hw_device)
+        images = data["image"]["raw_image"].to(hw_device)
+        labels = labels.to(hw_device)
+        out = model(_input_ids=ids, _attention_mask=mask, _images=images)
+        loss = criterion(out, labels)
+        loss.backward()
+        if acc_steps != 0:
+            loss = loss / acc_steps
+            if (batch_idx + 1) % acc_steps == 0 or batch_idx + 1 == n_total:
+                train_optimizer.step()
+                train_optimizer.zero_grad()
+        else:
+            train_optimizer.step()
+            train_optimizer.zero_grad()
+        if verbose:
+            print("Batch {}/{} on epoch {}".format(batch_idx, n_batches, epoch_num))
+        batch_loss.append(loss.detach().cpu())
+    return n_batches, batch_loss
+
+
+def save_model_weights(model: nn.Module, path: str, device) -> str:
+    """state_dict-only checkpoint written from the CPU copy (reference main_both.py:201-226)."""
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    model.to("cpu")
+    torch.save(model.state_dict(), path)
+    model.to(device)
+    return path

@@ -1,0 +1,200 @@
+/*
+ * mmrca.h — C ABI of the B200-native MM-RCA late-fusion head.
+ *
+ * This is the drop-in boundary for the hot path of espiriki/Garbage_Classification_RCA:
+ * everything MM_RCA.forward does after the two backbones returned their pooled
+ * features (CVPR_code/multimodal_model.py:661-728), the CrossEntropyLoss applied to
+ * its logits (main_both.py:87-93,110) and loss.backward() through both
+ * (main_both.py:112).  The reference is pure Python/PyTorch, so "the FFI a maintainer
+ * would bind" is a ctypes stub called from MM_RCA.forward / a torch.autograd.Function;
+ * INTEGRATION.md shows it.
+ *
+ * Conventions
+ *   - plain C, no torch types: raw DEVICE pointers + sizes + a cudaStream_t passed as void*;
+ *   - every call only enqueues work on `stream`: no allocation, no synchronisation, no host
+ *     callbacks; the caller owns every buffer (PyTorch tensors in the Python host layer);
+ *   - re-entrant per device/stream (nn.DataParallel calls forward from N threads);
+ *   - return 0 on success, non-zero MMRCA_ERR_* otherwise; mmrca_last_error() gives the
+ *     thread-local message.  There is NO CPU fallback: without an sm_100 device the calls fail.
+ *   - all matrices are row-major, weights in torch.nn.Linear layout [out_features, in_features].
+ *
+ * Fixed by the reference ctor literals (multimodal_model.py:249-258): 16 chunks per sample,
+ * self-attention 128 (q/k) / 96 (v), cross-attention 64 / 48.
+ */
+#ifndef MMRCA_H_
+#define MMRCA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMRCA_ABI_VERSION 1
+
+#define MMRCA_NUM_PATCHES 16 /* multimodal_model.py:249 */
+#define MMRCA_SA_DKQ 128     /* :251 */
+#define MMRCA_SA_DV 96       /* :252 */
+#define MMRCA_CA_DKQ 64      /* :254 */
+#define MMRCA_CA_DV 48       /* :255 */
+
+/* error codes */
+#define MMRCA_OK 0
+#define MMRCA_ERR_INVALID 1     /* bad argument / unsupported shape */
+#define MMRCA_ERR_CUDA 2        /* a CUDA runtime call failed */
+#define MMRCA_ERR_NO_DEVICE 3   /* no sm_100 device: there is no fallback path */
+#define MMRCA_ERR_WORKSPACE 4   /* workspace too small */
+
+/* MmrcaHeadDesc.flags — the reference's constructor switches (multimodal_model.py:166-168) */
+#define MMRCA_FLAG_REVERSE 1u              /* --reverse: (1-A)/(L-1) weights, :95-99 */
+#define MMRCA_FLAG_FEATURES_ONLY 2u        /* --features_only: concat = [img, txt], :694-699 */
+#define MMRCA_FLAG_CROSS_ATTENTION_ONLY 4u /* --cross_attention_only: concat = [T_I, I_T], :701-706 */
+
+/* MmrcaHeadDesc.compute */
+#define MMRCA_COMPUTE_FP32 0 /* fp32 SIMT kernels: the 1e-4-relative contract */
+#define MMRCA_COMPUTE_BF16 1 /* bf16 tcgen05 tensor-core kernels, fp32 accumulate: the 2e-2-absolute contract */
+
+/* mmrca_query() selectors */
+#define MMRCA_QUERY_ABI_VERSION 0
+#define MMRCA_QUERY_DEVICE_OK 1      /* 1 if the current device is compute capability 10.x */
+#define MMRCA_QUERY_SM_COUNT 2
+#define MMRCA_QUERY_KERNEL_LAUNCHES 3 /* kernels launched by this library on this thread since last reset */
+#define MMRCA_QUERY_RESET_LAUNCHES 4
+#define MMRCA_QUERY_HAS_BF16 5       /* 1 if the bf16 tensor-core path is compiled in */
+
+/* One SelfAttention / ReverseCrossAttention block (multimodal_model.py:39-108):
+ * W_query/W_key/W_value Linear weights+biases and the LayerNorm affine. */
+typedef struct MmrcaAttnParams {
+  const float* wq; /* [d_kq, d_in] */
+  const float* bq; /* [d_kq] */
+  const float* wk; /* [d_kq, d_in] */
+  const float* bk; /* [d_kq] */
+  const float* wv; /* [d_v, d_in] */
+  const float* bv; /* [d_v] */
+  const float* ln_g; /* [d_v] */
+  const float* ln_b; /* [d_v] */
+} MmrcaAttnParams;
+
+typedef struct MmrcaAttnGrads {
+  float* wq; float* bq; float* wk; float* bk; float* wv; float* bv; float* ln_g; float* ln_b;
+} MmrcaAttnGrads;
+
+/* Parameters read by MM_RCA.forward (34 tensors, 94 820 scalars in the full variant). */
+typedef struct MmrcaHeadParams {
+  MmrcaAttnParams sa_img; /* self_attention_image, :266 */
+  MmrcaAttnParams sa_txt; /* self_attention_text,  :268 */
+  MmrcaAttnParams ca1;    /* cross_attention_1 (Q: text SA, K/V: image SA), :271, :683 */
+  MmrcaAttnParams ca2;    /* cross_attention_2 (Q: image SA, K/V: text SA), :275, :685 */
+  const float* wf;        /* classifier selected by flags, [n_classes, D]: final_with_everything (:290) /
+                             final_features_only_linear (:282) / cross_attention_only_linear (:286) */
+  const float* bf;        /* [n_classes] */
+} MmrcaHeadParams;
+
+/* Gradient destinations, same layout.  The backward ACCUMULATES (+=) into them, like
+ * loss.backward() accumulates into .grad; the caller zeroes them (optimizer.zero_grad()). */
+typedef struct MmrcaHeadGrads {
+  MmrcaAttnGrads sa_img, sa_txt, ca1, ca2;
+  float* wf;
+  float* bf;
+} MmrcaHeadGrads;
+
+typedef struct MmrcaHeadDesc {
+  int32_t batch;     /* B */
+  int32_t d_img;     /* pooled image feature width (1280, :258); multiple of 16*4 */
+  int32_t d_txt;     /* pooled text feature width (768, :257) */
+  int32_t n_classes; /* 4 */
+  uint32_t flags;    /* MMRCA_FLAG_* */
+  int32_t compute;   /* MMRCA_COMPUTE_* */
+} MmrcaHeadDesc;
+
+/* Cross-entropy configuration: torch.nn.CrossEntropyLoss(weight=, label_smoothing=), mean
+ * reduction (main_both.py:87-93). class_weight may be NULL. */
+typedef struct MmrcaCeDesc {
+  const float* class_weight; /* device [n_classes] or NULL */
+  float label_smoothing;
+} MmrcaCeDesc;
+
+int mmrca_query(int what);
+const char* mmrca_last_error(void);
+
+/* Bytes of device scratch the calls below need for this desc (monotone in batch).
+ * `training` != 0 adds the backward buffers.  The forward leaves the per-block activations
+ * (SA / CA outputs, feature norms) in the workspace; a backward for the same inputs must be
+ * given the same, unmodified workspace. */
+size_t mmrca_head_workspace_bytes(const MmrcaHeadDesc* desc, int training);
+
+/* MM_RCA.forward from the pooled features on (multimodal_model.py:661-728).
+ *   img_feat [B, d_img], txt_feat [B, d_txt] fp32
+ *   drop_mask: uint8 [B, D] keep-mask of self.drop (:719) or NULL (eval / p = 0); kept values are
+ *              scaled by drop_scale = 1/(1-p)
+ *   logits   [B, n_classes] fp32 out */
+int mmrca_head_forward(const MmrcaHeadDesc* desc, const MmrcaHeadParams* params,
+                       const float* img_feat, const float* txt_feat,
+                       const uint8_t* drop_mask, float drop_scale,
+                       float* logits, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of mmrca_head_forward given dL/dlogits (what autograd hands to the head when
+ * loss.backward() runs, main_both.py:112).  Attention internals are recomputed on chip.
+ *   grads: accumulated into (+=);  d_img_feat / d_txt_feat: written if non-NULL (fine-tune phase,
+ *   main_both.py:687-694), may be NULL when the backbones are frozen. */
+int mmrca_head_backward(const MmrcaHeadDesc* desc, const MmrcaHeadParams* params,
+                        const float* img_feat, const float* txt_feat,
+                        const uint8_t* drop_mask, float drop_scale,
+                        const float* dlogits, const MmrcaHeadGrads* grads,
+                        float* d_img_feat, float* d_txt_feat,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* CrossEntropyLoss forward + dL/dlogits (main_both.py:87-93,110): loss_out [1], dlogits [B, C]
+ * (either may be NULL).  labels int64 [B]. */
+int mmrca_cross_entropy(const float* logits, const int64_t* labels, const MmrcaCeDesc* ce,
+                        int32_t batch, int32_t n_classes, float* loss_out, float* dlogits,
+                        void* stream);
+
+/* One training step of the head: forward + CrossEntropyLoss + backward in one call
+ * (run_one_epoch body, main_both.py:106-112, restricted to the fusion head).
+ * Writes logits [B, C] and loss [1], accumulates grads, optionally writes feature grads. */
+int mmrca_head_train_step(const MmrcaHeadDesc* desc, const MmrcaHeadParams* params,
+                          const float* img_feat, const float* txt_feat,
+                          const uint8_t* drop_mask, float drop_scale,
+                          const int64_t* labels, const MmrcaCeDesc* ce,
+                          float* logits, float* loss_out, const MmrcaHeadGrads* grads,
+                          float* d_img_feat, float* d_txt_feat,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stand-alone attention block = SelfAttention.forward (multimodal_model.py:51-68, x_kv == x_q,
+ * reverse = 0) or ReverseCrossAttention.forward (:82-108).  x_q, x_kv: [B, 16, d_in];
+ * out: [B, 16, d_v].  (d_in, d_kq, d_v) must be one of the head's blocks:
+ * (d_in in {48, 64, 80}, 128, 96) or (96, 64, 48).  `normalise` != 0 applies the per-sample
+ * L2 normalisation of :662-665 to x_q (== x_kv) first and writes the norms to norms_out [B]. */
+int mmrca_attention_forward(const MmrcaAttnParams* p, const float* x_q, const float* x_kv,
+                            int32_t batch, int32_t d_in, int32_t d_kq, int32_t d_v,
+                            int32_t reverse, int32_t normalise, float* norms_out,
+                            float* out, int32_t compute, void* stream);
+
+/* Backward of mmrca_attention_forward: recomputes the block from x_q / x_kv, then
+ *   d_x_q, d_x_kv [B,16,d_in]: written (NULL to skip; for x_kv == x_q pass d_x_kv = NULL and d_x_q
+ *   receives the sum);  grads: accumulated;  scratch: device buffer of
+ *   mmrca_attention_backward_scratch_bytes(batch, d_kq, d_v) bytes. */
+size_t mmrca_attention_backward_scratch_bytes(int32_t batch, int32_t d_kq, int32_t d_v);
+int mmrca_attention_backward(const MmrcaAttnParams* p, const float* x_q, const float* x_kv,
+                             const float* d_out, int32_t batch, int32_t d_in, int32_t d_kq,
+                             int32_t d_v, int32_t reverse, const MmrcaAttnGrads* grads,
+                             float* d_x_q, float* d_x_kv, void* scratch, size_t scratch_bytes,
+                             int32_t compute, void* stream);
+
+/* Per-kernel timing for roofline reports: between begin and end every kernel this library launches on
+ * the calling thread is bracketed by a pair of CUDA events on ITS launch stream (up to max_records
+ * launches).  mmrca_timing_end synchronises those events (the only call here that blocks), writes up to
+ * max_out records and returns the number of launches recorded, or a negative MMRCA_ERR_* code. */
+typedef struct MmrcaKernelTime {
+  const char* name; /* static string, e.g. "attn_bwd<80,128,96,self>" */
+  float ms;
+} MmrcaKernelTime;
+int mmrca_timing_begin(int32_t max_records);
+int mmrca_timing_end(MmrcaKernelTime* out, int32_t max_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMRCA_H_ */
