@@ -170,13 +170,15 @@ class _HeadFunction(torch.autograd.Function):
                          dtype=torch.uint8, device=img.device)
         logits = torch.empty(B, n_classes, dtype=torch.float32, device=img.device)
         hp = _head_struct(params)
+        ctx.save_for_backward(img, txt, drop_mask, ws, *params)
+        ctx.cfg = (drop_scale, flags, n_classes, compute)
+        if B == 0:      # empty shard: nothing to launch (a zero-size tensor has a null data pointer)
+            return logits
         with torch.cuda.device(img.device):
             N.check(L.mmrca_head_forward(C.byref(desc), C.byref(hp), img.data_ptr(), txt.data_ptr(),
                                          drop_mask.data_ptr() if drop_mask is not None else None,
                                          float(drop_scale), logits.data_ptr(), ws.data_ptr(), ws.numel(),
                                          _stream_ptr(img.device)), "mmrca_head_forward")
-        ctx.save_for_backward(img, txt, drop_mask, ws, *params)
-        ctx.cfg = (drop_scale, flags, n_classes, compute)
         return logits
 
     @staticmethod
@@ -193,13 +195,12 @@ class _HeadFunction(torch.autograd.Function):
         hp, hg = _head_struct(params), _head_struct(fg.views)
         L = N.lib()
         with torch.cuda.device(img.device):
-            N.check(L.mmrca_head_backward(C.byref(desc), C.byref(hp), img.data_ptr(), txt.data_ptr(),
-                                          drop_mask.data_ptr() if drop_mask is not None else None,
-                                          float(drop_scale), dlogits.data_ptr(), C.byref(hg),
-                                          d_img.data_ptr() if want_feat else None,
-                                          d_txt.data_ptr() if want_feat else None,
-                                          ws.data_ptr(), ws.numel(), _stream_ptr(img.device)),
-                    "mmrca_head_backward")
+            if B > 0:
+                N.check(L.mmrca_head_backward(C.byref(desc), C.byref(hp), img.data_ptr(), txt.data_ptr(),
+                    drop_mask.data_ptr() if drop_mask is not None else None, float(drop_scale),
+                    dlogits.data_ptr(), C.byref(hg), d_img.data_ptr() if want_feat else None,
+                    d_txt.data_ptr() if want_feat else None, ws.data_ptr(), ws.numel(),
+                    _stream_ptr(img.device)), "mmrca_head_backward")
         features_only = bool(flags & N.FLAG_FEATURES_ONLY)
         pg = []
         for i, v in enumerate(fg.views):

@@ -1,0 +1,129 @@
+"""CPU (no GPU): the C-ABI library builds, loads and exports every symbol include/mmrca.h declares; the
+Python mirror reproduces the reference's constructor / state_dict layout / flag surface; the product
+path refuses to run without its CUDA device instead of falling back."""
+import hashlib
+import io
+import json
+import os
+import re
+from contextlib import redirect_stdout
+
+import pytest
+import torch
+
+from tests._util import GOLDEN
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(native_lib):
+    from garbage_classification_rca_b200 import _native
+    hdr = open(os.path.join(ROOT, "include", "mmrca.h")).read()
+    declared = set(re.findall(r"\b(mmrca_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_native.EXPORTS)
+    for sym in declared:
+        assert hasattr(native_lib, sym), sym
+    assert native_lib.mmrca_query(_native.QUERY_ABI_VERSION) == _native.ABI_VERSION
+
+
+def test_workspace_size_is_monotone(native_lib):
+    from garbage_classification_rca_b200 import functional as F
+    prev = 0
+    for b in (0, 1, 7, 256, 4096):
+        inf = F.workspace_bytes(b, 1280, 768, 4, 1, 0, training=False)
+        trn = F.workspace_bytes(b, 1280, 768, 4, 1, 0, training=True)
+        assert trn >= inf >= prev
+        prev = inf
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback(native_lib):
+    import garbage_classification_rca_b200 as g
+    assert native_lib.mmrca_query(g._native.QUERY_DEVICE_OK) == 0
+    params = g.functional.init_head_parameters("cpu")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        g.mmrca_head(torch.randn(2, 1280), torch.randn(2, 768), params, reverse=True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        g.cross_entropy(torch.randn(2, 4), torch.zeros(2, dtype=torch.long))
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "garbage_classification_rca_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src, f"{f} mentions the oracle"
+
+
+@pytest.fixture(scope="module")
+def layout():
+    with open(os.path.join(GOLDEN, "state_dict_layout.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.mark.parametrize("flags", [(False, False), (True, False), (False, True)])
+def test_state_dict_layout_matches_reference(layout, flags):
+    """Names, shapes, dtypes and ORDER of the reference's state_dict (SURVEY.md §5 checkpoint row): 88 head
+    tensors incl. the dead gated/CLIP/GRU ones, image_model.{stem,stage1..}, conditional classifier keys."""
+    from garbage_classification_rca_b200 import multimodal_model as M
+    fo, co = flags
+    with redirect_stdout(io.StringIO()) as out:
+        m = M.MM_RCA(4, 0.6, 0.0, 0.7, 256, "distilbert", 16, True, fo, co, pretrained=False)
+    assert "txt patch size:  48" in out.getvalue() and "img patch size:  80" in out.getvalue()
+    ref = layout[f"distilbert|features_only={int(fo)}|cross_attention_only={int(co)}"]
+    ours = [[k, list(v.shape), str(v.dtype)] for k, v in m.state_dict().items()]
+    assert len(ours) == ref["order_total"]
+    head = [e for e in ours if not e[0].startswith(("image_model.", "text_model."))]
+    assert head == ref["head"]
+    assert [e[0] for e in ours].index(head[0][0]) == ref["head_first_index"]
+    for pre, dg in ref["backbones"].items():
+        sub = [e for e in ours if e[0].startswith(pre)]
+        h = hashlib.sha256("\n".join(f"{k}:{s}:{d}" for k, s, d in sub).encode()).hexdigest()
+        assert (len(sub), h, sub[0][0], sub[-1][0]) == (dg["count"], dg["sha256"], dg["first"], dg["last"])
+    # the 34 tensors the forward reads, frozen backbones, helper methods
+    assert len(m.head_parameters()) == 34
+    assert sum(p.numel() for p in m.head_parameters()) == {(False, False): 94820, (True, False): 88676,
+                                                          (False, True): 86628}[flags]
+    assert not any(p.requires_grad for p in m.text_model.parameters())
+    assert m.get_image_size() == (480, 480) and m.get_max_token_size() == 512
+
+
+def test_reference_call_sites_with_fewer_args_construct():
+    """calculate_test_accuracy_both.py:162-171 passes 9 positional args, main_both.py:319-327 passes 8
+    (TypeError in the reference): the trailing switches default here."""
+    from garbage_classification_rca_b200 import multimodal_model as M
+    with redirect_stdout(io.StringIO()):
+        m = M.MM_RCA(4, 0.6, 0.0, 0.7, 256, "distilbert", 16, True, False, pretrained=False)
+    assert m.cross_attention_only is False and m.reverse is True
+    with pytest.raises(SystemExit):
+        with redirect_stdout(io.StringIO()):
+            M.MM_RCA(4, 0.6, 0.0, 0.7, 256, "roberta", 16, True, False, False, pretrained=False)
+
+
+def test_option_surface():
+    from garbage_classification_rca_b200.options import args_parser
+    a = args_parser(["--late_fusion=MM_RCA", "--reverse", "--features-only"])
+    assert (a.late_fusion, a.reverse, a.features_only, a.cross_attention_only) == ("MM_RCA", True, True, False)
+    a = args_parser(["--no-reverse", "--cross_attention_only", "--model_dropout", "0.3"])
+    assert (a.reverse, a.cross_attention_only, a.model_dropout) == (False, True, 0.3)
+    d = args_parser([])
+    assert (d.late_fusion, d.model_dropout, d.batch_size, d.num_neurons_FC, d.label_smoothing) == \
+        ("gated", 0.6, 16, 256, 0.0)
+
+
+def test_drop_modalities_matches_reference_semantics():
+    """eval=True + remove_* zero the image batch / ids+mask (reference :424-435); training with
+    image_or_text_dropout_chance = 0 never drops (:444-455)."""
+    from garbage_classification_rca_b200 import multimodal_model as M
+    m = M.MM_RCA.__new__(M.MM_RCA)
+    m.image_or_text_dropout_chance, m.img_dropout_prob = 0.0, 0.7
+    ids = torch.arange(12).reshape(2, 6)
+    m._images, m._input_ids, m._attention_mask = torch.ones(2, 3, 4, 4), ids.clone(), torch.ones_like(ids)
+    with redirect_stdout(io.StringIO()):
+        m.drop_modalities(False, False, False)
+        assert m._images.sum() > 0 and torch.equal(m._input_ids, ids)
+        m.drop_modalities(True, True, False)
+        assert m._images.sum() == 0 and torch.equal(m._input_ids, ids)
+        m.drop_modalities(True, False, True)
+        assert m._input_ids.sum() == 0 and m._attention_mask.sum() == 0
