@@ -54,7 +54,7 @@ class CeDesc(C.Structure):
 EXPORTS = ("mmrca_query", "mmrca_last_error", "mmrca_head_workspace_bytes", "mmrca_head_forward",
            "mmrca_head_backward", "mmrca_cross_entropy", "mmrca_head_train_step", "mmrca_attention_forward",
            "mmrca_attention_backward_scratch_bytes", "mmrca_attention_backward", "mmrca_timing_begin",
-           "mmrca_timing_end")
+           "mmrca_timing_end", "mmrca_dev_umma_selftest", "mmrca_attention_forward_scratch_bytes")
 
 
 def _sources_newer_than_lib() -> bool:
@@ -119,8 +119,11 @@ def lib() -> C.CDLL:
                                             _fp, C.POINTER(CeDesc), _fp, _fp, C.POINTER(HeadParams), _fp, _fp,
                                             _fp, C.c_size_t, _fp]
         L.mmrca_head_train_step.restype = C.c_int
+        L.mmrca_attention_forward_scratch_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+        L.mmrca_attention_forward_scratch_bytes.restype = C.c_size_t
         L.mmrca_attention_forward.argtypes = [C.POINTER(AttnParams), _fp, _fp, C.c_int32, C.c_int32, C.c_int32,
-                                              C.c_int32, C.c_int32, C.c_int32, _fp, _fp, C.c_int32, _fp]
+                                              C.c_int32, C.c_int32, C.c_int32, _fp, _fp, _fp, C.c_size_t,
+                                              C.c_int32, _fp]
         L.mmrca_attention_forward.restype = C.c_int
         L.mmrca_attention_backward_scratch_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
         L.mmrca_attention_backward_scratch_bytes.restype = C.c_size_t
@@ -132,6 +135,8 @@ def lib() -> C.CDLL:
         L.mmrca_timing_begin.restype = C.c_int
         L.mmrca_timing_end.argtypes = [C.POINTER(KernelTime), C.c_int32]
         L.mmrca_timing_end.restype = C.c_int
+        L.mmrca_dev_umma_selftest.argtypes = [C.c_int32, _fp, _fp, _fp, C.c_int32, C.c_int32, _fp]
+        L.mmrca_dev_umma_selftest.restype = C.c_int
         if L.mmrca_query(QUERY_ABI_VERSION) != ABI_VERSION:
             raise RuntimeError("libmmrca.so ABI version mismatch: rebuild it")
         _lib = L

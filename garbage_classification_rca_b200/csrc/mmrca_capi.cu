@@ -9,6 +9,8 @@
 
 #include "mmrca_attn_fp32.cuh"
 #include "mmrca_misc_fp32.cuh"
+#include "mmrca_attn_tc.cuh"
+#include "mmrca_tc_selftest.cuh"
 
 namespace mmrca {
 
@@ -43,6 +45,8 @@ static int fail(int code, const char* fmt, const char* a = "", const char* b = "
     cudaError_t e_ = (call);                                                               \
     if (e_ != cudaSuccess) return fail(MMRCA_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
   } while (0)
+
+static size_t align_up_256(size_t v) { return (v + 255) & ~size_t(255); }
 
 struct DeviceInfo { int ok; int sms; };
 
@@ -111,6 +115,65 @@ static int attn_dispatch(bool backward, bool self, int d_in, int d_kq, int d_v, 
     return launch_attn<96, 64, 48, false, 4, 4>(backward, a, sms, st);
   return fail(MMRCA_ERR_INVALID,
               "unsupported attention block shape: need self (d_in in {48,64,80},128,96) or cross (96,64,48)%s%s");
+}
+
+// ---- bf16 tensor-core attention blocks -----------------------------------------------------------------
+template <int DIN, int DKQ, int DV, bool SELF>
+static int launch_attn_tc(const TcAttnArgs& a, int sms, cudaStream_t st) {
+  using C = TcCfg<DIN, DKQ, DV, SELF>;
+  int rc = set_smem(attn_fwd_tc_kernel<C>, C::SMEM_BYTES);
+  if (rc) return rc;
+  const int tiles = (a.batch + kTcG - 1) / kTcG;
+  {
+    LaunchScope ls(SELF ? (DIN == 48 ? "attn_fwd_tc<48,128,96,self>" : DIN == 64 ? "attn_fwd_tc<64,128,96,self>"
+                                                                               : "attn_fwd_tc<80,128,96,self>")
+                        : "attn_fwd_tc<96,64,48,cross>", st);
+    attn_fwd_tc_kernel<C><<<min(tiles, sms), kTcThreads, C::SMEM_BYTES, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+
+static int attn_tc_dispatch(bool self, int d_in, int d_kq, int d_v, const TcAttnArgs& a, int sms, cudaStream_t st) {
+  if (a.batch <= 0) return MMRCA_OK;
+  if (self && d_kq == MMRCA_SA_DKQ && d_v == MMRCA_SA_DV) {
+    if (d_in == 48) return launch_attn_tc<48, 128, 96, true>(a, sms, st);
+    if (d_in == 64) return launch_attn_tc<64, 128, 96, true>(a, sms, st);
+    if (d_in == 80) return launch_attn_tc<80, 128, 96, true>(a, sms, st);
+  }
+  if (!self && d_in == MMRCA_SA_DV && d_kq == MMRCA_CA_DKQ && d_v == MMRCA_CA_DV)
+    return launch_attn_tc<96, 64, 48, false>(a, sms, st);
+  return fail(MMRCA_ERR_INVALID,
+              "unsupported attention block shape: need self (d_in in {48,64,80},128,96) or cross (96,64,48)%s%s");
+}
+
+static size_t wblob_bytes(int d_in, int d_kq, int d_v) {
+  return align_up_256(size_t(d_in / 8) * size_t((2 * d_kq + d_v) / 8) * 128);
+}
+
+static int launch_pack(const PackArgs& pa, cudaStream_t st) {
+  {
+    LaunchScope ls("pack_weights_bf16", st);
+    pack_weights_kernel<<<dim3(8, pa.njobs), 256, 0, st>>>(pa);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+
+static PackJob make_pack_job(const MmrcaAttnParams& p, void* dst, int d_in, int d_kq, int d_v) {
+  PackJob j;
+  j.wq = p.wq; j.wk = p.wk; j.wv = p.wv; j.dst = dst; j.din = d_in; j.dkq = d_kq; j.dv = d_v;
+  return j;
+}
+
+static TcAttnArgs make_tc_args(const MmrcaAttnParams& p, const void* blob, const float* xq, const float* xkv,
+                               int batch, int reverse) {
+  TcAttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.xq = xq; a.xkv = xkv; a.wblob = blob;
+  a.bq = p.bq; a.bk = p.bk; a.bv = p.bv; a.ln_g = p.ln_g; a.ln_b = p.ln_b;
+  a.batch = batch; a.reverse = reverse;
+  return a;
 }
 
 static AttnArgs make_attn_args(const MmrcaAttnParams& p, const float* xq, const float* xkv, int batch, int reverse) {
@@ -193,10 +256,11 @@ static int classifier_dispatch(bool backward, int nc, const CatArgs& a, int sms,
 struct Workspace {
   float *norm_img, *norm_txt, *t_sa, *i_sa, *t_i, *i_t;          // forward (kept for the backward)
   float *d_t_sa, *d_i_sa, *d_t_i, *d_i_t, *dy, *dlogits;          // training only
+  void* wblob[4];                                                   // bf16 packed weights: sa_img, sa_txt, ca1, ca2
   size_t bytes;
 };
 
-static size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+static size_t align_up(size_t v) { return align_up_256(v); }
 
 static Workspace carve(const MmrcaHeadDesc& d, bool training, void* base) {
   Workspace w;
@@ -208,6 +272,12 @@ static Workspace carve(const MmrcaHeadDesc& d, bool training, void* base) {
   w.norm_img = take(B); w.norm_txt = take(B);
   w.t_sa = take(B * kL * MMRCA_SA_DV); w.i_sa = take(B * kL * MMRCA_SA_DV);
   w.t_i = take(B * kL * MMRCA_CA_DV); w.i_t = take(B * kL * MMRCA_CA_DV);
+  if (d.compute == MMRCA_COMPUTE_BF16) {
+    w.wblob[0] = take(wblob_bytes(d.d_img / kL, MMRCA_SA_DKQ, MMRCA_SA_DV) / 4);
+    w.wblob[1] = take(wblob_bytes(d.d_txt / kL, MMRCA_SA_DKQ, MMRCA_SA_DV) / 4);
+    w.wblob[2] = take(wblob_bytes(MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV) / 4);
+    w.wblob[3] = take(wblob_bytes(MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV) / 4);
+  }
   if (training) {
     w.d_t_sa = take(B * kL * MMRCA_SA_DV); w.d_i_sa = take(B * kL * MMRCA_SA_DV);
     w.d_t_i = take(B * kL * MMRCA_CA_DV); w.d_i_t = take(B * kL * MMRCA_CA_DV);
@@ -230,8 +300,6 @@ static int check_desc(const MmrcaHeadDesc* d) {
   }
   if (d->compute != MMRCA_COMPUTE_FP32 && d->compute != MMRCA_COMPUTE_BF16)
     return fail(MMRCA_ERR_INVALID, "unknown compute mode%s%s");
-  if (d->compute == MMRCA_COMPUTE_BF16)
-    return fail(MMRCA_ERR_INVALID, "bf16 tensor-core path is not compiled into this build%s%s");
   return MMRCA_OK;
 }
 
@@ -294,6 +362,27 @@ static int head_forward_impl(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, c
     { LaunchScope ls("l2norm", st); l2norm_kernel<<<grid, kThreads, 0, st>>>(img, w.norm_img, d.batch, d.d_img); }
     { LaunchScope ls("l2norm", st); l2norm_kernel<<<grid, kThreads, 0, st>>>(txt, w.norm_txt, d.batch, d.d_txt); }
     MMRCA_CUDA(cudaGetLastError());
+  } else if (d.compute == MMRCA_COMPUTE_BF16) {
+    PackArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.njobs = 4;
+    pa.job[0] = make_pack_job(p.sa_img, w.wblob[0], d.d_img / kL, MMRCA_SA_DKQ, MMRCA_SA_DV);
+    pa.job[1] = make_pack_job(p.sa_txt, w.wblob[1], d.d_txt / kL, MMRCA_SA_DKQ, MMRCA_SA_DV);
+    pa.job[2] = make_pack_job(p.ca1, w.wblob[2], MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV);
+    pa.job[3] = make_pack_job(p.ca2, w.wblob[3], MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV);
+    if ((rc = launch_pack(pa, st))) return rc;
+    TcAttnArgs a = make_tc_args(p.sa_txt, w.wblob[1], txt, txt, d.batch, 0);
+    a.normalise = 1; a.norms = w.norm_txt; a.out = w.t_sa;
+    if ((rc = attn_tc_dispatch(true, d.d_txt / kL, MMRCA_SA_DKQ, MMRCA_SA_DV, a, sms, st))) return rc;
+    a = make_tc_args(p.sa_img, w.wblob[0], img, img, d.batch, 0);
+    a.normalise = 1; a.norms = w.norm_img; a.out = w.i_sa;
+    if ((rc = attn_tc_dispatch(true, d.d_img / kL, MMRCA_SA_DKQ, MMRCA_SA_DV, a, sms, st))) return rc;
+    a = make_tc_args(p.ca1, w.wblob[2], w.t_sa, w.i_sa, d.batch, rev);
+    a.out = w.t_i;
+    if ((rc = attn_tc_dispatch(false, MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV, a, sms, st))) return rc;
+    a = make_tc_args(p.ca2, w.wblob[3], w.i_sa, w.t_sa, d.batch, rev);
+    a.out = w.i_t;
+    if ((rc = attn_tc_dispatch(false, MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV, a, sms, st))) return rc;
   } else {
     AttnArgs a = make_attn_args(p.sa_txt, txt, txt, d.batch, 0);            // multimodal_model.py:677-678
     a.normalise = 1; a.norms = w.norm_txt; a.out = w.t_sa;
@@ -399,7 +488,7 @@ int mmrca_query(int what) {
     case MMRCA_QUERY_SM_COUNT: { DeviceInfo di; return device_info(&di) == MMRCA_OK ? di.sms : 0; }
     case MMRCA_QUERY_KERNEL_LAUNCHES: return g_launches;
     case MMRCA_QUERY_RESET_LAUNCHES: { int v = g_launches; g_launches = 0; return v; }
-    case MMRCA_QUERY_HAS_BF16: return 0;
+    case MMRCA_QUERY_HAS_BF16: return 1;
     default: return -1;
   }
 }
@@ -505,16 +594,36 @@ int mmrca_head_train_step(const MmrcaHeadDesc* desc, const MmrcaHeadParams* para
                             d_txt_feat, w, di.sms, st);
 }
 
+size_t mmrca_attention_forward_scratch_bytes(int32_t d_in, int32_t d_kq, int32_t d_v, int32_t compute) {
+  return compute == MMRCA_COMPUTE_BF16 ? wblob_bytes(d_in, d_kq, d_v) : 0;
+}
+
 int mmrca_attention_forward(const MmrcaAttnParams* p, const float* x_q, const float* x_kv, int32_t batch,
                             int32_t d_in, int32_t d_kq, int32_t d_v, int32_t reverse, int32_t normalise,
-                            float* norms_out, float* out, int32_t compute, void* stream) {
+                            float* norms_out, float* out, void* scratch, size_t scratch_bytes, int32_t compute,
+                            void* stream) {
   if (!p || !x_q || !x_kv || !out) return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
-  if (compute != MMRCA_COMPUTE_FP32) return fail(MMRCA_ERR_INVALID, "only MMRCA_COMPUTE_FP32 is compiled in%s%s");
+  if (compute != MMRCA_COMPUTE_FP32 && compute != MMRCA_COMPUTE_BF16)
+    return fail(MMRCA_ERR_INVALID, "unknown compute mode%s%s");
   if (normalise && (x_q != x_kv || !norms_out))
     return fail(MMRCA_ERR_INVALID, "normalise needs x_kv == x_q and a norms_out buffer%s%s");
   DeviceInfo di;
   int rc;
   if ((rc = device_info(&di))) return rc;
+  if (compute == MMRCA_COMPUTE_BF16) {
+    if (d_in % 16 || d_kq % 16 || d_v % 16 || d_in <= 0) return fail(MMRCA_ERR_INVALID, "unsupported block shape%s%s");
+    if (!scratch || scratch_bytes < wblob_bytes(d_in, d_kq, d_v))
+      return fail(MMRCA_ERR_WORKSPACE, "bf16 attention forward needs mmrca_attention_forward_scratch_bytes()%s%s");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PackArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.njobs = 1;
+    pa.job[0] = make_pack_job(*p, scratch, d_in, d_kq, d_v);
+    if (batch > 0 && (rc = launch_pack(pa, st))) return rc;
+    TcAttnArgs ta = make_tc_args(*p, scratch, x_q, x_kv, batch, reverse ? 1 : 0);
+    ta.normalise = normalise ? 1 : 0; ta.norms = norms_out; ta.out = out;
+    return attn_tc_dispatch(x_q == x_kv, d_in, d_kq, d_v, ta, di.sms, st);
+  }
   AttnArgs a = make_attn_args(*p, x_q, x_kv, batch, reverse ? 1 : 0);
   a.normalise = normalise ? 1 : 0; a.norms = norms_out; a.out = out;
   return attn_dispatch(false, x_q == x_kv, d_in, d_kq, d_v, a, di.sms, static_cast<cudaStream_t>(stream));
@@ -529,7 +638,8 @@ int mmrca_attention_backward(const MmrcaAttnParams* p, const float* x_q, const f
                              const MmrcaAttnGrads* grads, float* d_x_q, float* d_x_kv, void* scratch,
                              size_t scratch_bytes, int32_t compute, void* stream) {
   if (!p || !x_q || !x_kv || !d_out || !grads || !scratch) return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
-  if (compute != MMRCA_COMPUTE_FP32) return fail(MMRCA_ERR_INVALID, "only MMRCA_COMPUTE_FP32 is compiled in%s%s");
+  if (compute != MMRCA_COMPUTE_FP32 && compute != MMRCA_COMPUTE_BF16)
+    return fail(MMRCA_ERR_INVALID, "unknown compute mode%s%s");
   if (scratch_bytes < mmrca_attention_backward_scratch_bytes(batch, d_kq, d_v))
     return fail(MMRCA_ERR_WORKSPACE, "scratch too small%s%s");
   const bool self = x_q == x_kv;
@@ -543,6 +653,26 @@ int mmrca_attention_backward(const MmrcaAttnParams* p, const float* x_q, const f
   a.g_ln_g = grads->ln_g; a.g_ln_b = grads->ln_b;
   if ((rc = attn_dispatch(true, self, d_in, d_kq, d_v, a, di.sms, st))) return rc;
   return attn_wgrads(self, d_in, d_kq, d_v, a.dy, x_q, x_kv, nullptr, batch, *grads, di.sms, st);
+}
+
+int mmrca_dev_umma_selftest(int32_t mode, const float* a, const float* b, float* out, int32_t n, int32_t k,
+                            void* stream) {
+  if (!a || !b || !out) return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
+  if (n < 16 || n > 256 || n % 16 || k < 16 || k % 16 || mode < 0 || mode > 3)
+    return fail(MMRCA_ERR_INVALID, "selftest needs 16 <= n <= 256, n % 16 == 0, k % 16 == 0, mode in [0,3]%s%s");
+  DeviceInfo di;
+  int rc;
+  if ((rc = device_info(&di))) return rc;
+  const size_t smem = tc::umma_selftest_smem_bytes(n, k);
+  if (smem > 200 * 1024) return fail(MMRCA_ERR_INVALID, "selftest operands do not fit shared memory%s%s");
+  if ((rc = set_smem(tc::umma_selftest_kernel, smem))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    LaunchScope ls("umma_selftest", st);
+    tc::umma_selftest_kernel<<<1, 128, smem, st>>>(mode, a, b, out, n, k);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
 }
 
 }  // extern "C"

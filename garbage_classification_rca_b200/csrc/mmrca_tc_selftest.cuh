@@ -1,0 +1,110 @@
+// Diagnostic kernel for the UMMA building blocks (mmrca_tc.cuh): one 128 x N x K bf16 GEMM with fp32
+// accumulation through shared-memory descriptors -> tcgen05.mma -> TMEM -> tcgen05.ld, in all four
+// operand-major combinations the head kernels use.  Exercised by tests/test_tc_blocks_gpu.py.
+#pragma once
+#include "mmrca_tc.cuh"
+
+namespace mmrca {
+namespace tc {
+
+// mode bit 0: B is MN-major (source b[K][N]) instead of K-major (source b[N][K])
+// mode bit 1: A is MN-major (source a[K][128]) instead of K-major (source a[128][K])
+// out[128][N] = A * B^T (logical A[128][K], B[N][K]).  N % 16 == 0, N <= 256, K % 16 == 0.
+__global__ void __launch_bounds__(128, 1) umma_selftest_kernel(int mode, const float* __restrict__ a,
+                                                              const float* __restrict__ b, float* __restrict__ out,
+                                                              int N, int K) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool a_mn = mode & 2, b_mn = mode & 1;
+  const int M = 128;
+  // operand geometry (bytes)
+  const uint32_t a_sbo = 128, a_lbo = (M / 8) * 128 + 16;
+  const uint32_t b_sbo = 128, b_lbo = (N / 8) * 128 + 16;
+  const uint32_t a_bytes = (K / 8) * a_lbo, b_off = (a_bytes + 127) & ~127u;
+  uint8_t* sa = smem;
+  uint8_t* sb = smem + b_off;
+
+  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  if (warp == 0) {
+    uint32_t cols = 32;
+    while (cols < uint32_t(N)) cols <<= 1;
+    tmem_alloc(&tmem_base, cols);
+  }
+  // ---- stage A ----
+  if (!a_mn) {   // source a[128][K]: chunk (r, kc) = 8 consecutive k
+    for (int i = tid; i < M * (K / 8); i += 128) {
+      const int r = i / (K / 8), kc = i % (K / 8);
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = a[r * K + kc * 8 + e];
+      *reinterpret_cast<uint4*>(sa + core_off(r, kc, a_lbo, a_sbo)) = pack_bf16x8(v);
+    }
+  } else {       // source a[K][128]: chunk (k, mc) = 8 consecutive m
+    for (int i = tid; i < K * (M / 8); i += 128) {
+      const int k = i / (M / 8), mc = i % (M / 8);
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = a[k * M + mc * 8 + e];
+      *reinterpret_cast<uint4*>(sa + uint32_t(mc) * a_sbo + uint32_t(k >> 3) * a_lbo + uint32_t(k & 7) * 16u) =
+          pack_bf16x8(v);
+    }
+  }
+  // ---- stage B ----
+  if (!b_mn) {   // source b[N][K]
+    for (int i = tid; i < N * (K / 8); i += 128) {
+      const int n = i / (K / 8), kc = i % (K / 8);
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = b[n * K + kc * 8 + e];
+      *reinterpret_cast<uint4*>(sb + core_off(n, kc, b_lbo, b_sbo)) = pack_bf16x8(v);
+    }
+  } else {       // source b[K][N]
+    for (int i = tid; i < K * (N / 8); i += 128) {
+      const int k = i / (N / 8), nc = i % (N / 8);
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = b[k * N + nc * 8 + e];
+      *reinterpret_cast<uint4*>(sb + uint32_t(nc) * b_sbo + uint32_t(k >> 3) * b_lbo + uint32_t(k & 7) * 16u) =
+          pack_bf16x8(v);
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t taddr = tmem_base;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_bf16(M, N, a_mn ? 1 : 0, b_mn ? 1 : 0);
+    const uint64_t ad = make_smem_desc(smem_u32(sa), a_lbo, a_sbo);
+    const uint64_t bd = make_smem_desc(smem_u32(sb), b_lbo, b_sbo);
+    for (int ks = 0; ks < K / 16; ++ks)
+      umma_bf16(taddr, desc_advance(ad, ks * 2 * a_lbo), desc_advance(bd, ks * 2 * b_lbo), idesc, ks > 0);
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after_sync();
+  const int r = warp * 32 + lane;
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    tmem_ld16(taddr + (uint32_t(warp * 32) << 16) + uint32_t(c0), v);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) out[r * N + c0 + e] = v[e];
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t cols = 32;
+    while (cols < uint32_t(N)) cols <<= 1;
+    tmem_dealloc(taddr, cols);
+  }
+}
+
+inline size_t umma_selftest_smem_bytes(int N, int K) {
+  const size_t a_lbo = (128 / 8) * 128 + 16, b_lbo = (size_t(N) / 8) * 128 + 16;
+  return (((K / 8) * a_lbo + 127) & ~size_t(127)) + (K / 8) * b_lbo + 128;
+}
+
+}  // namespace tc
+}  // namespace mmrca

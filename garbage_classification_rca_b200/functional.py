@@ -316,10 +316,14 @@ class _AttentionFunction(torch.autograd.Function):
         d_kq, d_v = params[0].shape[0], params[4].shape[0]
         out = torch.empty(B, Lr, d_v, dtype=torch.float32, device=x_q.device)
         ap = _attn_struct(params)
+        L = N.lib()
+        sb = int(L.mmrca_attention_forward_scratch_bytes(d_in, d_kq, d_v, compute))
+        scratch = torch.empty(sb, dtype=torch.uint8, device=x_q.device) if sb else None
         with torch.cuda.device(x_q.device):
-            N.check(N.lib().mmrca_attention_forward(C.byref(ap), x_q.data_ptr(), x_kv.data_ptr(), B, d_in, d_kq,
-                                                    d_v, 1 if reverse else 0, 0, None, out.data_ptr(), compute,
-                                                    _stream_ptr(x_q.device)), "mmrca_attention_forward")
+            N.check(L.mmrca_attention_forward(C.byref(ap), x_q.data_ptr(), x_kv.data_ptr(), B, d_in, d_kq,
+                                              d_v, 1 if reverse else 0, 0, None, out.data_ptr(),
+                                              scratch.data_ptr() if sb else None, sb, compute,
+                                              _stream_ptr(x_q.device)), "mmrca_attention_forward")
         ctx.save_for_backward(x_q, x_kv, *params)
         ctx.cfg = (reverse, is_self, compute, d_in, d_kq, d_v)
         return out

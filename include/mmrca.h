@@ -166,11 +166,14 @@ int mmrca_head_train_step(const MmrcaHeadDesc* desc, const MmrcaHeadParams* para
  * reverse = 0) or ReverseCrossAttention.forward (:82-108).  x_q, x_kv: [B, 16, d_in];
  * out: [B, 16, d_v].  (d_in, d_kq, d_v) must be one of the head's blocks:
  * (d_in in {48, 64, 80}, 128, 96) or (96, 64, 48).  `normalise` != 0 applies the per-sample
- * L2 normalisation of :662-665 to x_q (== x_kv) first and writes the norms to norms_out [B]. */
+ * L2 normalisation of :662-665 to x_q (== x_kv) first and writes the norms to norms_out [B].
+ * scratch: device buffer of mmrca_attention_forward_scratch_bytes() bytes (the bf16 path packs the
+ * weights into it; 0 bytes / NULL for MMRCA_COMPUTE_FP32). */
+size_t mmrca_attention_forward_scratch_bytes(int32_t d_in, int32_t d_kq, int32_t d_v, int32_t compute);
 int mmrca_attention_forward(const MmrcaAttnParams* p, const float* x_q, const float* x_kv,
                             int32_t batch, int32_t d_in, int32_t d_kq, int32_t d_v,
                             int32_t reverse, int32_t normalise, float* norms_out,
-                            float* out, int32_t compute, void* stream);
+                            float* out, void* scratch, size_t scratch_bytes, int32_t compute, void* stream);
 
 /* Backward of mmrca_attention_forward: recomputes the block from x_q / x_kv, then
  *   d_x_q, d_x_kv [B,16,d_in]: written (NULL to skip; for x_kv == x_q pass d_x_kv = NULL and d_x_q
@@ -193,6 +196,12 @@ typedef struct MmrcaKernelTime {
 } MmrcaKernelTime;
 int mmrca_timing_begin(int32_t max_records);
 int mmrca_timing_end(MmrcaKernelTime* out, int32_t max_out);
+
+/* Diagnostic: one 128 x N x K bf16 tcgen05 GEMM (fp32 accumulate in TMEM) through the library's operand
+ * staging.  mode bit 0: b is [K][N] (MN-major) instead of [N][K]; bit 1: a is [K][128] instead of [128][K].
+ * out[128][N] = A B^T.  N % 16 == 0, 16 <= N <= 256, K % 16 == 0, operands must fit shared memory. */
+int mmrca_dev_umma_selftest(int32_t mode, const float* a, const float* b, float* out, int32_t n, int32_t k,
+                            void* stream);
 
 #ifdef __cplusplus
 }

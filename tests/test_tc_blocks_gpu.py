@@ -1,0 +1,26 @@
+"""GPU: the tcgen05 building blocks (shared-memory operand descriptors, UMMA issue, TMEM read-back) in the
+four operand-major combinations the head kernels use, against a torch fp32 matmul of the bf16-rounded
+operands (fp32 accumulation: only summation order differs)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("shape", [(176, 80), (64, 96), (112, 96), (256, 48), (96, 128), (16, 16)])
+def test_umma_selftest(native_lib, mode, shape):
+    from garbage_classification_rca_b200 import _native as N
+    n, k = shape
+    g = torch.Generator().manual_seed(mode * 100 + n + k)
+    A = torch.randn(128, k, generator=g)
+    B = torch.randn(n, k, generator=g)
+    a_src = (A.t().contiguous() if mode & 2 else A).cuda()
+    b_src = (B.t().contiguous() if mode & 1 else B).cuda()
+    out = torch.full((128, n), float("nan"), device="cuda")
+    N.check(native_lib.mmrca_dev_umma_selftest(mode, a_src.data_ptr(), b_src.data_ptr(), out.data_ptr(), n, k,
+                                               torch.cuda.current_stream().cuda_stream), "selftest")
+    torch.cuda.synchronize()
+    ref = A.bfloat16().float() @ B.bfloat16().float().t()
+    err = (out.cpu() - ref).abs().max().item()
+    assert err < 1e-3 * max(1.0, ref.abs().max().item()), f"mode {mode} n {n} k {k}: max err {err}"
