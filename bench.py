@@ -58,6 +58,17 @@ def kernel_flops():
     f["classifier_fwd"] = 2 * 4 * 3584
     f["classifier_bwd"] = 2 * 2 * 4 * 3584
     f["cross_entropy"] = 0
+    # bf16 tensor-core pipeline (mmrca_head_tc*.cuh).  Algorithmic = the reference's formulation (Q/K/V projections,
+    # per-sample 16x16 attention), not the MMAs the kernels actually issue ("algorithmic work").
+    bwd_sa = lambda a: a["proj"] + 2 * (a["scores"] + a["pv"])            # frozen features: no input gradient
+    bwd_ca = lambda a: 2 * a["proj"] + 2 * (a["scores"] + a["pv"])
+    f["sa_fwd_bf16"] = sum(sa_i.values()) + sum(sa_t.values()) + 2 * 4 * 2048
+    f["ca_fwd_bf16"] = 2 * sum(ca.values()) + 2 * 4 * 1536
+    f["ca_bwd_bf16"] = 2 * bwd_ca(ca) + 2 * 2 * 4 * 1536
+    f["sa_bwd_bf16<80>"] = bwd_sa(sa_i) + 2 * 4 * 1280
+    f["sa_bwd_bf16<48>"] = bwd_sa(sa_t) + 2 * 4 * 768
+    for k in ("prep_bf16", "finalize_bf16", "cross_entropy4", "bias_grad"):
+        f[k] = 0
     return f
 
 
@@ -330,7 +341,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--compute", default="fp32", choices=("fp32", "bf16"))
+    ap.add_argument("--compute", default="bf16", choices=("fp32", "bf16"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

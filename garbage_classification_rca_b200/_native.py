@@ -22,7 +22,9 @@ SOURCES = ["mmrca_capi.cu"]
 
 # mmrca.h constants
 FLAG_REVERSE, FLAG_FEATURES_ONLY, FLAG_CROSS_ATTENTION_ONLY = 1, 2, 4
-COMPUTE_FP32, COMPUTE_BF16 = 0, 1
+FLAG_FEATURE_GRADS = 256
+COMPUTE_FP32, COMPUTE_BF16, COMPUTE_BF16_FUSED = 0, 1, 2
+WS_TEXT_SA_IMAGE, WS_IMAGE_SA_IMAGE = 0, 1
 QUERY_ABI_VERSION, QUERY_DEVICE_OK, QUERY_SM_COUNT, QUERY_KERNEL_LAUNCHES, QUERY_RESET_LAUNCHES, QUERY_HAS_BF16 = range(6)
 ABI_VERSION = 1
 
@@ -54,7 +56,8 @@ class CeDesc(C.Structure):
 EXPORTS = ("mmrca_query", "mmrca_last_error", "mmrca_head_workspace_bytes", "mmrca_head_forward",
            "mmrca_head_backward", "mmrca_cross_entropy", "mmrca_head_train_step", "mmrca_attention_forward",
            "mmrca_attention_backward_scratch_bytes", "mmrca_attention_backward", "mmrca_timing_begin",
-           "mmrca_timing_end", "mmrca_dev_umma_selftest", "mmrca_attention_forward_scratch_bytes")
+           "mmrca_timing_end", "mmrca_dev_umma_selftest", "mmrca_attention_forward_scratch_bytes",
+           "mmrca_head_workspace_offset")
 
 
 def _sources_newer_than_lib() -> bool:
@@ -107,6 +110,8 @@ def lib() -> C.CDLL:
         L.mmrca_last_error.restype = C.c_char_p
         L.mmrca_head_workspace_bytes.argtypes = [C.POINTER(HeadDesc), C.c_int]
         L.mmrca_head_workspace_bytes.restype = C.c_size_t
+        L.mmrca_head_workspace_offset.argtypes = [C.POINTER(HeadDesc), C.c_int, C.c_int]
+        L.mmrca_head_workspace_offset.restype = C.c_longlong
         L.mmrca_head_forward.argtypes = [C.POINTER(HeadDesc), C.POINTER(HeadParams), _fp, _fp, _fp, C.c_float,
                                          _fp, _fp, C.c_size_t, _fp]
         L.mmrca_head_forward.restype = C.c_int

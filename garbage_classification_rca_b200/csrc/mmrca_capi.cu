@@ -11,6 +11,8 @@
 #include "mmrca_misc_fp32.cuh"
 #include "mmrca_attn_tc.cuh"
 #include "mmrca_tc_selftest.cuh"
+#include "mmrca_head_tc.cuh"
+#include "mmrca_head_tc_bwd.cuh"
 
 namespace mmrca {
 
@@ -257,6 +259,11 @@ struct Workspace {
   float *norm_img, *norm_txt, *t_sa, *i_sa, *t_i, *i_t;          // forward (kept for the backward)
   float *d_t_sa, *d_i_sa, *d_t_i, *d_i_t, *dy, *dlogits;          // training only
   void* wblob[4];                                                   // bf16 packed weights: sa_img, sa_txt, ca1, ca2
+  // fused bf16 pipeline (mmrca_head_tc.cuh)
+  void* fblob[4];                                                   // per block: bz | bv | bc blobs
+  void* t_img; void* i_img;                                         // SA output images, [tiles][kSaTileBytes]
+  void* dx_img[4];                                                  // training: dXq / dXkv images of CA1, then CA2
+  float* gm[4]; size_t gm_floats;                                   // training: dM_ext^T per block (contiguous)
   size_t bytes;
 };
 
@@ -272,17 +279,29 @@ static Workspace carve(const MmrcaHeadDesc& d, bool training, void* base) {
   w.norm_img = take(B); w.norm_txt = take(B);
   w.t_sa = take(B * kL * MMRCA_SA_DV); w.i_sa = take(B * kL * MMRCA_SA_DV);
   w.t_i = take(B * kL * MMRCA_CA_DV); w.i_t = take(B * kL * MMRCA_CA_DV);
-  if (d.compute == MMRCA_COMPUTE_BF16) {
-    w.wblob[0] = take(wblob_bytes(d.d_img / kL, MMRCA_SA_DKQ, MMRCA_SA_DV) / 4);
-    w.wblob[1] = take(wblob_bytes(d.d_txt / kL, MMRCA_SA_DKQ, MMRCA_SA_DV) / 4);
-    w.wblob[2] = take(wblob_bytes(MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV) / 4);
-    w.wblob[3] = take(wblob_bytes(MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV) / 4);
+  if (d.compute != MMRCA_COMPUTE_FP32) {
+    const size_t tiles = (B + 7) / 8;
+    w.fblob[0] = take(htc::SaCfg<80>::W_BYTES / 4);
+    w.fblob[1] = take(htc::SaCfg<48>::W_BYTES / 4);
+    w.fblob[2] = take(htc::CaCfg::W_BYTES / 4);
+    w.fblob[3] = take(htc::CaCfg::W_BYTES / 4);
+    w.t_img = take(tiles * htc::kSaTileBytes / 4);
+    w.i_img = take(tiles * htc::kSaTileBytes / 4);
   }
   if (training) {
     w.d_t_sa = take(B * kL * MMRCA_SA_DV); w.d_i_sa = take(B * kL * MMRCA_SA_DV);
     w.d_t_i = take(B * kL * MMRCA_CA_DV); w.d_i_t = take(B * kL * MMRCA_CA_DV);
     w.dy = take(B * kL * (2 * MMRCA_SA_DKQ + MMRCA_SA_DV));
     w.dlogits = take(B * size_t(d.n_classes > 0 ? d.n_classes : 0));
+    if (d.compute != MMRCA_COMPUTE_FP32) {
+      const size_t tiles = (B + 7) / 8;
+      for (int i = 0; i < 4; ++i) w.dx_img[i] = take(tiles * htc::kSaTileBytes / 4);
+      const int dins[4] = {80, 48, MMRCA_SA_DV, MMRCA_SA_DV};
+      char* g0 = p + off;
+      for (int i = 0; i < 4; ++i) { w.gm[i] = reinterpret_cast<float*>(p + off); off += size_t(dins[i]) * 128 * 4; }
+      w.gm_floats = size_t(p + off - g0) / 4;
+      off = align_up(off);
+    }
   }
   w.bytes = off;
   return w;
@@ -298,9 +317,16 @@ static int check_desc(const MmrcaHeadDesc* d) {
   if ((d->flags & MMRCA_FLAG_FEATURES_ONLY) && (d->flags & MMRCA_FLAG_CROSS_ATTENTION_ONLY)) {
     // the reference's if/elif gives features_only precedence (multimodal_model.py:694-726)
   }
-  if (d->compute != MMRCA_COMPUTE_FP32 && d->compute != MMRCA_COMPUTE_BF16)
+  if (d->compute != MMRCA_COMPUTE_FP32 && d->compute != MMRCA_COMPUTE_BF16 && d->compute != MMRCA_COMPUTE_BF16_FUSED)
     return fail(MMRCA_ERR_INVALID, "unknown compute mode%s%s");
   return MMRCA_OK;
+}
+
+// The fused bf16 pipeline covers the reference's literal dimensions (multimodal_model.py:249-258: 1280 / 768
+// features, 4 classes) without a materialised dropout mask; everything else runs on the fp32 kernels.
+static bool fused_ok(const MmrcaHeadDesc& d, const uint8_t* mask) {
+  return d.compute != MMRCA_COMPUTE_FP32 && d.d_img == 1280 && d.d_txt == 768 && d.n_classes == 4 &&
+         !(d.flags & (MMRCA_FLAG_FEATURES_ONLY | MMRCA_FLAG_FEATURE_GRADS)) && mask == nullptr;
 }
 
 static int concat_width(const MmrcaHeadDesc& d) {
@@ -350,6 +376,172 @@ __global__ void __launch_bounds__(kThreads) l2norm_kernel(const float* __restric
   }
 }
 
+// ---- fused bf16 pipeline: forward -----------------------------------------------------------------------------
+static htc::PrepBlock make_prep_block(const MmrcaAttnParams& p, void* blob, int din, int dkq, int dv) {
+  htc::PrepBlock b;
+  b.wq = p.wq; b.bq = p.bq; b.wk = p.wk; b.wv = p.wv; b.bv = p.bv;
+  b.bz = blob;
+  b.bvb = static_cast<uint8_t*>(blob) + htc::blob_bytes(din, din + 16);
+  b.din = din; b.dkq = dkq; b.dv = dv;
+  return b;
+}
+
+static int launch_prep_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, float* logits, const Workspace& w,
+                             float* zero0, int nzero0, cudaStream_t st) {
+  const bool co = d.flags & MMRCA_FLAG_CROSS_ATTENTION_ONLY;
+  htc::PrepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.blk[0] = make_prep_block(p.sa_img, w.fblob[0], 80, MMRCA_SA_DKQ, MMRCA_SA_DV);
+  a.blk[1] = make_prep_block(p.sa_txt, w.fblob[1], 48, MMRCA_SA_DKQ, MMRCA_SA_DV);
+  a.blk[2] = make_prep_block(p.ca1, w.fblob[2], MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV);
+  a.blk[3] = make_prep_block(p.ca2, w.fblob[3], MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV);
+  const int ca = kL * MMRCA_CA_DV;   // 768: width of T_I / I_T in the concat (multimodal_model.py:708-716)
+  int n = 0;
+  a.src[n].bc = static_cast<uint8_t*>(w.fblob[2]) + htc::CaCfg::BZ_BYTES + htc::CaCfg::BV_BYTES;
+  a.src[n].off = 0; a.src[n].w = MMRCA_CA_DV; ++n;
+  a.src[n].bc = static_cast<uint8_t*>(w.fblob[3]) + htc::CaCfg::BZ_BYTES + htc::CaCfg::BV_BYTES;
+  a.src[n].off = ca; a.src[n].w = MMRCA_CA_DV; ++n;
+  if (!co) {
+    a.src[n].bc = static_cast<uint8_t*>(w.fblob[0]) + htc::SaCfg<80>::BZ_BYTES + htc::SaCfg<80>::BV_BYTES;
+    a.src[n].off = 2 * ca; a.src[n].w = 80; ++n;
+    a.src[n].bc = static_cast<uint8_t*>(w.fblob[1]) + htc::SaCfg<48>::BZ_BYTES + htc::SaCfg<48>::BV_BYTES;
+    a.src[n].off = 2 * ca + d.d_img; a.src[n].w = 48; ++n;
+  }
+  a.nsrc = n;
+  a.wf = p.wf; a.bf = p.bf; a.D = concat_width(d);
+  a.logits = logits; a.batch = d.batch;
+  a.zero0 = zero0; a.nzero0 = nzero0;
+  {
+    LaunchScope ls("prep_bf16", st);
+    htc::prep_kernel<<<4 * 148, 256, 0, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+
+static int head_forward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, const float* img, const float* txt,
+                              float* logits, const Workspace& w, int sms, cudaStream_t st) {
+  const bool co = d.flags & MMRCA_FLAG_CROSS_ATTENTION_ONLY;
+  int rc;
+  if ((rc = launch_prep_fused(d, p, logits, w, nullptr, 0, st))) return rc;
+  const int tiles = (d.batch + 7) / 8;
+  const int grid = min(tiles, sms);
+  {
+    htc::SaFwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.role[0].feat = img; a.role[0].norms = w.norm_img; a.role[0].ln_g = p.sa_img.ln_g; a.role[0].ln_b = p.sa_img.ln_b;
+    a.role[0].blobs = w.fblob[0]; a.role[0].out_tiles = w.i_img;
+    a.role[1].feat = txt; a.role[1].norms = w.norm_txt; a.role[1].ln_g = p.sa_txt.ln_g; a.role[1].ln_b = p.sa_txt.ln_b;
+    a.role[1].blobs = w.fblob[1]; a.role[1].out_tiles = w.t_img;
+    a.logits = co ? nullptr : logits;
+    a.batch = d.batch;
+    if ((rc = set_smem(htc::sa_fwd_kernel, htc::SaFwdLayout::BYTES))) return rc;
+    LaunchScope ls("sa_fwd_bf16", st);
+    htc::sa_fwd_kernel<<<grid, htc::kCtaThreads, htc::SaFwdLayout::BYTES, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  {
+    htc::CaFwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dir[0].blobs = w.fblob[2]; a.dir[0].ln_g = p.ca1.ln_g; a.dir[0].ln_b = p.ca1.ln_b;
+    a.dir[1].blobs = w.fblob[3]; a.dir[1].ln_g = p.ca2.ln_g; a.dir[1].ln_b = p.ca2.ln_b;
+    a.t_tiles = w.t_img; a.i_tiles = w.i_img;
+    a.logits = logits; a.batch = d.batch; a.reverse = (d.flags & MMRCA_FLAG_REVERSE) ? 1 : 0;
+    if ((rc = set_smem(htc::ca_fwd_kernel, htc::CaFwdLayout::BYTES))) return rc;
+    LaunchScope ls("ca_fwd_bf16", st);
+    htc::ca_fwd_kernel<<<grid, htc::kCtaThreads, htc::CaFwdLayout::BYTES, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+
+// ---- fused bf16 pipeline: backward --------------------------------------------------------------------------
+static int head_backward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, const float* img, const float* txt,
+                               const float* dlogits, const MmrcaHeadGrads& g, const Workspace& w, int sms,
+                               cudaStream_t st) {
+  const bool co = d.flags & MMRCA_FLAG_CROSS_ATTENTION_ONLY;
+  const int tiles = (d.batch + 7) / 8, D = concat_width(d), ca = kL * MMRCA_CA_DV;
+  int rc;
+  MMRCA_CUDA(cudaMemsetAsync(w.gm[0], 0, w.gm_floats * sizeof(float), st));
+  {
+    htc::CaBwdArgs a;
+    memset(&a, 0, sizeof(a));
+    const MmrcaAttnParams* ap[2] = {&p.ca1, &p.ca2};
+    const MmrcaAttnGrads* ag[2] = {&g.ca1, &g.ca2};
+    for (int i = 0; i < 2; ++i) {
+      a.dir[i].blobs = w.fblob[2 + i]; a.dir[i].ln_g = ap[i]->ln_g; a.dir[i].ln_b = ap[i]->ln_b;
+      a.dir[i].gm = w.gm[2 + i]; a.dir[i].g_wv = ag[i]->wv; a.dir[i].g_bv = ag[i]->bv;
+      a.dir[i].g_ln_g = ag[i]->ln_g; a.dir[i].g_ln_b = ag[i]->ln_b;
+      a.dir[i].g_wf = g.wf + i * ca;
+      a.dir[i].dxq_img = w.dx_img[2 * i]; a.dir[i].dxkv_img = w.dx_img[2 * i + 1];
+    }
+    a.t_tiles = w.t_img; a.i_tiles = w.i_img; a.dlogits = dlogits; a.D = D;
+    a.batch = d.batch; a.reverse = (d.flags & MMRCA_FLAG_REVERSE) ? 1 : 0;
+    if ((rc = set_smem(htc::ca_bwd_kernel, htc::CaBwdSmem::BYTES))) return rc;
+    LaunchScope ls("ca_bwd_bf16", st);
+    htc::ca_bwd_kernel<<<dim3(min(tiles, max(1, sms / 2)), 2), htc::kCtaThreads, htc::CaBwdSmem::BYTES, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  {
+    // text SA output: query source of CA1, key/value source of CA2; image SA output: the other way round
+    htc::SaBwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.feat = img; a.blobs = w.fblob[0]; a.ln_g = p.sa_img.ln_g; a.ln_b = p.sa_img.ln_b;
+    a.dout_a = w.dx_img[1]; a.dout_b = w.dx_img[2];
+    a.dlogits = co ? nullptr : dlogits;
+    a.gm = w.gm[0]; a.g_wv = g.sa_img.wv; a.g_bv = g.sa_img.bv; a.g_ln_g = g.sa_img.ln_g; a.g_ln_b = g.sa_img.ln_b;
+    a.g_wf = co ? nullptr : g.wf + 2 * ca; a.D = D; a.batch = d.batch;
+    if ((rc = set_smem(htc::sa_bwd_kernel<80>, htc::SaBwdSmem<80>::BYTES))) return rc;
+    {
+      LaunchScope ls("sa_bwd_bf16<80>", st);
+      htc::sa_bwd_kernel<80><<<min(tiles, sms), htc::kCtaThreads, htc::SaBwdSmem<80>::BYTES, st>>>(a);
+    }
+    MMRCA_CUDA(cudaGetLastError());
+    a.feat = txt; a.blobs = w.fblob[1]; a.ln_g = p.sa_txt.ln_g; a.ln_b = p.sa_txt.ln_b;
+    a.dout_a = w.dx_img[0]; a.dout_b = w.dx_img[3];
+    a.gm = w.gm[1]; a.g_wv = g.sa_txt.wv; a.g_bv = g.sa_txt.bv; a.g_ln_g = g.sa_txt.ln_g; a.g_ln_b = g.sa_txt.ln_b;
+    a.g_wf = co ? nullptr : g.wf + 2 * ca + d.d_img;
+    if ((rc = set_smem(htc::sa_bwd_kernel<48>, htc::SaBwdSmem<48>::BYTES))) return rc;
+    {
+      LaunchScope ls("sa_bwd_bf16<48>", st);
+      htc::sa_bwd_kernel<48><<<min(tiles, sms), htc::kCtaThreads, htc::SaBwdSmem<48>::BYTES, st>>>(a);
+    }
+    MMRCA_CUDA(cudaGetLastError());
+  }
+  {
+    htc::FinArgs a;
+    memset(&a, 0, sizeof(a));
+    const MmrcaAttnParams* ap[4] = {&p.sa_img, &p.sa_txt, &p.ca1, &p.ca2};
+    const MmrcaAttnGrads* ag[4] = {&g.sa_img, &g.sa_txt, &g.ca1, &g.ca2};
+    const int dins[4] = {80, 48, MMRCA_SA_DV, MMRCA_SA_DV};
+    const int dkqs[4] = {MMRCA_SA_DKQ, MMRCA_SA_DKQ, MMRCA_CA_DKQ, MMRCA_CA_DKQ};
+    for (int i = 0; i < 4; ++i) {
+      a.blk[i].gm = w.gm[i]; a.blk[i].wq = ap[i]->wq; a.blk[i].bq = ap[i]->bq; a.blk[i].wk = ap[i]->wk;
+      a.blk[i].g_wq = ag[i]->wq; a.blk[i].g_bq = ag[i]->bq; a.blk[i].g_wk = ag[i]->wk;
+      a.blk[i].din = dins[i]; a.blk[i].dkq = dkqs[i];
+    }
+    a.nblk = 4;
+    LaunchScope ls("finalize_bf16", st);
+    htc::finalize_kernel<<<dim3(84, 4), 256, 0, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+
+static int launch_ce4(const float* logits, const int64_t* labels, const MmrcaCeDesc* ce, int batch, float* loss,
+                      float* dlogits, float* g_bf, int sms, cudaStream_t st) {
+  MMRCA_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  htc::Ce4Args a;
+  a.logits = logits; a.labels = labels; a.cw = ce ? ce->class_weight : nullptr; a.eps = ce ? ce->label_smoothing : 0.f;
+  a.batch = batch; a.dlogits = dlogits; a.loss = loss; a.g_bf = g_bf;
+  {
+    LaunchScope ls("cross_entropy4", st);
+    htc::ce4_kernel<<<max(1, min((batch + 255) / 256, sms)), 256, 0, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+
 static int head_forward_impl(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, const float* img, const float* txt,
                              const uint8_t* mask, float scale, float* logits, const Workspace& w, int sms,
                              cudaStream_t st) {
@@ -357,32 +549,12 @@ static int head_forward_impl(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, c
   const int rev = (d.flags & MMRCA_FLAG_REVERSE) ? 1 : 0;
   int rc;
   if (d.batch == 0) return MMRCA_OK;
+  if (fused_ok(d, mask)) return head_forward_fused(d, p, img, txt, logits, w, sms, st);
   if (fo) {
     const int grid = min((d.batch + kWarps - 1) / kWarps, 8 * sms);
     { LaunchScope ls("l2norm", st); l2norm_kernel<<<grid, kThreads, 0, st>>>(img, w.norm_img, d.batch, d.d_img); }
     { LaunchScope ls("l2norm", st); l2norm_kernel<<<grid, kThreads, 0, st>>>(txt, w.norm_txt, d.batch, d.d_txt); }
     MMRCA_CUDA(cudaGetLastError());
-  } else if (d.compute == MMRCA_COMPUTE_BF16) {
-    PackArgs pa;
-    memset(&pa, 0, sizeof(pa));
-    pa.njobs = 4;
-    pa.job[0] = make_pack_job(p.sa_img, w.wblob[0], d.d_img / kL, MMRCA_SA_DKQ, MMRCA_SA_DV);
-    pa.job[1] = make_pack_job(p.sa_txt, w.wblob[1], d.d_txt / kL, MMRCA_SA_DKQ, MMRCA_SA_DV);
-    pa.job[2] = make_pack_job(p.ca1, w.wblob[2], MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV);
-    pa.job[3] = make_pack_job(p.ca2, w.wblob[3], MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV);
-    if ((rc = launch_pack(pa, st))) return rc;
-    TcAttnArgs a = make_tc_args(p.sa_txt, w.wblob[1], txt, txt, d.batch, 0);
-    a.normalise = 1; a.norms = w.norm_txt; a.out = w.t_sa;
-    if ((rc = attn_tc_dispatch(true, d.d_txt / kL, MMRCA_SA_DKQ, MMRCA_SA_DV, a, sms, st))) return rc;
-    a = make_tc_args(p.sa_img, w.wblob[0], img, img, d.batch, 0);
-    a.normalise = 1; a.norms = w.norm_img; a.out = w.i_sa;
-    if ((rc = attn_tc_dispatch(true, d.d_img / kL, MMRCA_SA_DKQ, MMRCA_SA_DV, a, sms, st))) return rc;
-    a = make_tc_args(p.ca1, w.wblob[2], w.t_sa, w.i_sa, d.batch, rev);
-    a.out = w.t_i;
-    if ((rc = attn_tc_dispatch(false, MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV, a, sms, st))) return rc;
-    a = make_tc_args(p.ca2, w.wblob[3], w.i_sa, w.t_sa, d.batch, rev);
-    a.out = w.i_t;
-    if ((rc = attn_tc_dispatch(false, MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV, a, sms, st))) return rc;
   } else {
     AttnArgs a = make_attn_args(p.sa_txt, txt, txt, d.batch, 0);            // multimodal_model.py:677-678
     a.normalise = 1; a.norms = w.norm_txt; a.out = w.t_sa;
@@ -402,9 +574,19 @@ static int head_forward_impl(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, c
   return classifier_dispatch(false, d.n_classes, c, sms, st);
 }
 
+__global__ void __launch_bounds__(256) colsum4_kernel(const float* __restrict__ dl, int batch, float* __restrict__ out) {
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int b = blockIdx.x * 256 + threadIdx.x; b < batch; b += gridDim.x * 256) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(dl) + b);
+    s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+  }
+  for (int c = 0; c < 4; ++c) { s[c] = warp_sum(s[c]); if ((threadIdx.x & 31) == 0) atomicAdd(out + c, s[c]); }
+}
+
 static int head_backward_impl(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, const float* img, const float* txt,
                               const uint8_t* mask, float scale, const float* dlogits, const MmrcaHeadGrads& g,
-                              float* d_img, float* d_txt, const Workspace& w, int sms, cudaStream_t st) {
+                              float* d_img, float* d_txt, const Workspace& w, int sms, cudaStream_t st,
+                              bool w_skip_bias_grad = false) {
   const bool fo = d.flags & MMRCA_FLAG_FEATURES_ONLY, co = !fo && (d.flags & MMRCA_FLAG_CROSS_ATTENTION_ONLY);
   const int rev = (d.flags & MMRCA_FLAG_REVERSE) ? 1 : 0;
   const bool want_feat = d_img != nullptr || d_txt != nullptr;
@@ -412,6 +594,18 @@ static int head_backward_impl(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, 
   if (d.batch == 0) return MMRCA_OK;
   if (want_feat && !(d_img && d_txt))
     return fail(MMRCA_ERR_INVALID, "d_img_feat and d_txt_feat must both be given or both be NULL%s%s");
+  if (fused_ok(d, mask)) {
+    if (want_feat)
+      return fail(MMRCA_ERR_INVALID, "feature gradients need MMRCA_FLAG_FEATURE_GRADS in the desc of the forward AND "
+                                     "the backward (the bf16 pipeline keeps parameter gradients only)%s%s");
+    // classifier bias gradient: column sums of dlogits (the fused cross-entropy adds it itself in train_step)
+    if (g.bf && !w_skip_bias_grad) {
+      LaunchScope ls("bias_grad", st);
+      colsum4_kernel<<<min((d.batch + 255) / 256, sms), 256, 0, st>>>(dlogits, d.batch, g.bf);
+      MMRCA_CUDA(cudaGetLastError());
+    }
+    return head_backward_fused(d, p, img, txt, dlogits, g, w, sms, st);
+  }
   // 1. classifier: dWf, dbf, d(T_I), d(I_T) and the direct feature terms d(img_n), d(txt_n)
   CatArgs c = make_cat_args(d, w, img, txt, mask, scale, p.wf, p.bf);
   c.dlogits = dlogits; c.g_wf = g.wf; c.g_bf = g.bf;
@@ -533,6 +727,18 @@ size_t mmrca_head_workspace_bytes(const MmrcaHeadDesc* desc, int training) {
   return carve(*desc, training != 0, nullptr).bytes;
 }
 
+long long mmrca_head_workspace_offset(const MmrcaHeadDesc* desc, int training, int what) {
+  if (!desc) return -1;
+  Workspace w = carve(*desc, training != 0, nullptr);
+  const void* p = nullptr;
+  switch (what) {
+    case MMRCA_WS_TEXT_SA_IMAGE: p = w.t_img; break;
+    case MMRCA_WS_IMAGE_SA_IMAGE: p = w.i_img; break;
+    default: return -1;
+  }
+  return p ? static_cast<long long>(reinterpret_cast<const char*>(p) - static_cast<const char*>(nullptr)) : -1;
+}
+
 int mmrca_head_forward(const MmrcaHeadDesc* desc, const MmrcaHeadParams* params, const float* img_feat,
                        const float* txt_feat, const uint8_t* drop_mask, float drop_scale, float* logits,
                        void* workspace, size_t workspace_bytes, void* stream) {
@@ -589,6 +795,11 @@ int mmrca_head_train_step(const MmrcaHeadDesc* desc, const MmrcaHeadParams* para
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if ((rc = head_forward_impl(*desc, *params, img_feat, txt_feat, drop_mask, drop_scale, logits, w, di.sms, st)))
     return rc;
+  if (fused_ok(*desc, drop_mask)) {
+    if ((rc = launch_ce4(logits, labels, ce, desc->batch, loss_out, w.dlogits, grads->bf, di.sms, st))) return rc;
+    return head_backward_impl(*desc, *params, img_feat, txt_feat, drop_mask, drop_scale, w.dlogits, *grads, d_img_feat,
+                              d_txt_feat, w, di.sms, st, true);
+  }
   if ((rc = launch_ce(logits, labels, ce, desc->batch, desc->n_classes, loss_out, w.dlogits, st))) return rc;
   return head_backward_impl(*desc, *params, img_feat, txt_feat, drop_mask, drop_scale, w.dlogits, *grads, d_img_feat,
                             d_txt_feat, w, di.sms, st);
@@ -658,8 +869,8 @@ int mmrca_attention_backward(const MmrcaAttnParams* p, const float* x_q, const f
 int mmrca_dev_umma_selftest(int32_t mode, const float* a, const float* b, float* out, int32_t n, int32_t k,
                             void* stream) {
   if (!a || !b || !out) return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
-  if (n < 16 || n > 256 || n % 16 || k < 16 || k % 16 || mode < 0 || mode > 3)
-    return fail(MMRCA_ERR_INVALID, "selftest needs 16 <= n <= 256, n % 16 == 0, k % 16 == 0, mode in [0,3]%s%s");
+  if (n < 16 || n > 256 || n % 16 || k < 16 || k % 16 || mode < 0 || mode > 7)
+    return fail(MMRCA_ERR_INVALID, "selftest needs 16 <= n <= 256, n % 16 == 0, k % 16 == 0, mode in [0,7]%s%s");
   DeviceInfo di;
   int rc;
   if ((rc = device_info(&di))) return rc;

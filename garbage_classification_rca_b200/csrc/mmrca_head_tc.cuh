@@ -1,0 +1,699 @@
+// bf16 tensor-core pipeline of the MM-RCA head (MMRCA_COMPUTE_BF16): forward kernels.
+//
+// Reference path: CVPR_code/multimodal_model.py:661-728 (MM_RCA.forward after the backbones), with
+// SelfAttention (:39-68) and ReverseCrossAttention (:71-108).  Every contraction is a tcgen05.mma with fp32
+// accumulation in TMEM; every per-row step (bias, softmax, LayerNorm, ReLU) runs on one thread per row.
+//
+// Algebra used here (exact in real arithmetic, it only changes where bf16 rounding happens):
+//   scores: Q K^T = (Xq Wq^T + bq)(Xkv Wk^T + bk)^T.  The terms that are constant along a score ROW cancel in the
+//   softmax, so   softmax(Q K^T / sqrt(d)) = softmax(Z Xkv^T)   with   Z = Xq M + u,
+//   M = Wq^T Wk / sqrt(d)  [d_in x d_in],   u = Wk^T bq / sqrt(d)  [d_in].
+//   d_in (48/80/96) is smaller than 2*d_kq (256/128), so Z replaces both Q and K: fewer projection columns,
+//   a shorter score contraction, fewer accumulator read-backs.  W_key.bias drops out exactly (its gradient is
+//   analytically zero in the reference too).
+//   biases ride in the GEMM: every activation operand carries a constant-one column at k = d_in (and zeros up
+//   to d_in+16), the weight blobs carry u / b_value in that row.
+//   classifier (:719-726): logits[b][c] = sum_{chunk r, j} F[(b,r)][j] Wf[c][off + r*w + j] is computed per
+//   source as one N=64 MMA  D[(b,r)][(r',c)] = sum_j F[(b,r)][j] Wf[c][off + r'*w + j];  the thread that owns
+//   row (b,r) keeps columns (r,0..3) and a 16-lane shuffle sums the sample's chunks.
+//
+// Tiles: 8 samples = 128 rows (row = 16*sample + chunk).  MMAs whose rows are tile rows and whose result is only
+// converted (projections, classifier) use M=128: TMEM lane = row.  The attention core (scores, P V) uses two M=64
+// MMAs per tile (samples 0-3 / 4-7): only the 4x4 sample blocks of a half are computed instead of 8x8, the
+// score block of a row sits at a warp-uniform column, and P is 2 x [64 x 64] instead of [128 x 128].  The two
+// M=64 accumulators interleave in TMEM lanes: warp q of a warpgroup holds rows 16q..16q+15 of half 0 in lanes
+// 0-15 and of half 1 in lanes 16-31 ("s-mapping"), while an M=128 accumulator has row 32q+lane ("p-mapping").
+//
+// A CTA has two warpgroups, each an independent pipeline on its own tile with its own shared-memory operand
+// buffers, TMEM columns and mbarrier: one warpgroup's read-backs overlap the other's MMAs.  Weights are packed
+// once per step (prep_kernel) into bf16 blobs in the canonical no-swizzle core-matrix layout and land in shared
+// memory through the bulk-copy engine (TMA).  Activations between the SA and CA kernels travel as bf16 operand
+// IMAGES (the exact bytes the next kernel's MMA descriptor wants), written coalesced and reloaded by TMA.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mmrca_attn_fp32.cuh"
+#include "mmrca_tc.cuh"
+
+namespace mmrca {
+namespace htc {
+
+using namespace tc;
+
+constexpr int kWgThreads = 128;
+constexpr int kCtaThreads = 256;
+constexpr uint32_t kCS = 128 * 16 + 16;   // bytes between 8-column groups of a 128-row operand (+16: bank spread)
+constexpr uint32_t kRS = 128;             // bytes between 8-row groups
+constexpr uint32_t kPCS = 64 * 16 + 16;   // same for one 64-row half of P / dS
+constexpr uint32_t kPHalf = 8 * kPCS;     // one [64 x 64] half
+constexpr int kDV_SA = 96, kDV_CA = 48, kDKQ_SA = 128, kDKQ_CA = 64;
+constexpr int kNCls = 64;                 // 16 chunks x 4 classes
+constexpr int kClasses = 4;
+
+__host__ __device__ constexpr uint32_t op_bytes(int cols) { return uint32_t(cols / 8) * kCS; }
+__host__ __device__ constexpr uint32_t blob_bytes(int n, int k) { return uint32_t(k / 8) * uint32_t(n) * 16u; }
+__host__ __device__ constexpr uint32_t al128(uint32_t v) { return (v + 127u) & ~127u; }
+
+__device__ __forceinline__ uint32_t row_off(int r) { return uint32_t(r >> 3) * kRS + uint32_t(r & 7) * 16u; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// prep: weights -> bf16 blobs, zero the step's accumulators, logits = classifier bias.
+// blob of a B operand Bm[n][k] (K-major): byte(n, k) = (k/8) * (N*16) + n*16 + (k%8)*2
+// ---------------------------------------------------------------------------------------------------------------
+struct PrepBlock {
+  const float* wq; const float* bq; const float* wk; const float* wv; const float* bv;
+  void* bz;      // [n = d_in][k = d_in + 16]:  M^T, row k = d_in holds u
+  void* bvb;     // [n = d_v ][k = d_in + 16]:  W_value, row k = d_in holds b_value
+  int din, dkq, dv;
+};
+struct PrepSrc { void* bc; int off, w; };   // classifier source: columns [off, off + 16*w) of the concat
+struct PrepArgs {
+  PrepBlock blk[4];
+  PrepSrc src[4];
+  int nsrc;
+  const float* wf; const float* bf; int D;   // classifier [4][D]
+  float* logits; int batch;                  // initialised with the bias (null: skip)
+  float* zero0; int nzero0;                  // fp32 regions to clear (step accumulators)
+};
+
+__global__ void __launch_bounds__(256) prep_kernel(const PrepArgs a) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+  const int gwarp = gtid >> 5, nwarp = gsz >> 5, lane = threadIdx.x & 31;
+  // (a) Z blobs: one warp per (k', kc): 8 outputs M[k][k'] (k = 8kc..8kc+7), lanes split the d_kq sum
+  int base = 0;
+  for (int b = 0; b < 4; ++b) {
+    const PrepBlock& B = a.blk[b];
+    if (!B.bz) continue;
+    const int kcs = (B.din + 16) / 8, ntask = B.din * kcs;
+    const float scale = rsqrtf(float(B.dkq));
+    for (int t = gwarp - base; t < ntask; t += nwarp) {
+      if (t < 0) continue;
+      const int kp = t / kcs, kc = t - kp * kcs;
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (kc * 8 < B.din) {
+#pragma unroll 4
+        for (int n = lane; n < B.dkq; n += 32) {
+          const float wk = __ldg(B.wk + size_t(n) * B.din + kp);
+          const float4 q0 = __ldg(reinterpret_cast<const float4*>(B.wq + size_t(n) * B.din + kc * 8));
+          const float4 q1 = __ldg(reinterpret_cast<const float4*>(B.wq + size_t(n) * B.din + kc * 8 + 4));
+          acc[0] = fmaf(q0.x, wk, acc[0]); acc[1] = fmaf(q0.y, wk, acc[1]); acc[2] = fmaf(q0.z, wk, acc[2]);
+          acc[3] = fmaf(q0.w, wk, acc[3]); acc[4] = fmaf(q1.x, wk, acc[4]); acc[5] = fmaf(q1.y, wk, acc[5]);
+          acc[6] = fmaf(q1.z, wk, acc[6]); acc[7] = fmaf(q1.w, wk, acc[7]);
+        }
+      } else if (kc * 8 == B.din) {
+        for (int n = lane; n < B.dkq; n += 32) acc[0] = fmaf(__ldg(B.bq + n), __ldg(B.wk + size_t(n) * B.din + kp), acc[0]);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = warp_sum(acc[e]) * scale;
+      if (lane == 0)
+        *reinterpret_cast<uint4*>(static_cast<uint8_t*>(B.bz) + size_t(kc) * (B.din * 16) + kp * 16) = pack_bf16x8(acc);
+    }
+    base = (base + ntask) % nwarp;   // rotate the starting warp so the blocks' tasks spread over the grid
+  }
+  // (b) V blobs: thread per (n, kc)
+  for (int b = 0; b < 4; ++b) {
+    const PrepBlock& B = a.blk[b];
+    if (!B.bvb) continue;
+    const int kcs = (B.din + 16) / 8;
+    for (int t = gtid; t < B.dv * kcs; t += gsz) {
+      const int n = t / kcs, kc = t - n * kcs;
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (kc * 8 < B.din) {
+        const float4 lo = __ldg(reinterpret_cast<const float4*>(B.wv + size_t(n) * B.din + kc * 8));
+        const float4 hi = __ldg(reinterpret_cast<const float4*>(B.wv + size_t(n) * B.din + kc * 8 + 4));
+        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+      } else if (kc * 8 == B.din) {
+        v[0] = __ldg(B.bv + n);
+      }
+      *reinterpret_cast<uint4*>(static_cast<uint8_t*>(B.bvb) + size_t(kc) * (B.dv * 16) + n * 16) = pack_bf16x8(v);
+    }
+  }
+  // (c) classifier blobs: Bc[n = r'*4 + c][k = j] = Wf[c][off + r'*w + j]
+  for (int s = 0; s < a.nsrc; ++s) {
+    const PrepSrc& S = a.src[s];
+    const int kcs = S.w / 8;
+    for (int t = gtid; t < kNCls * kcs; t += gsz) {
+      const int n = t / kcs, kc = t - n * kcs, rp = n >> 2, c = n & 3;
+      const float* p = a.wf + size_t(c) * a.D + S.off + rp * S.w + kc * 8;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = __ldg(p + e);
+      *reinterpret_cast<uint4*>(static_cast<uint8_t*>(S.bc) + size_t(kc) * (kNCls * 16) + n * 16) = pack_bf16x8(v);
+    }
+  }
+  // (d) accumulators, logits
+  for (int i = gtid; i < a.nzero0; i += gsz) a.zero0[i] = 0.f;
+  if (a.logits)
+    for (int i = gtid; i < a.batch * kClasses; i += gsz) a.logits[i] = __ldg(a.bf + (i & 3));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// shared pieces of the tile kernels
+// ---------------------------------------------------------------------------------------------------------------
+struct WgCtx {
+  int wt, q, lane;        // thread in warpgroup, warp in warpgroup, lane
+  int wg;                 // warpgroup in CTA
+  uint32_t tmem;          // TMEM base of this warpgroup (lane 0, first column)
+  uint32_t lane_base;     // (32*q) << 16
+  uint64_t* bar;          // MMA-completion mbarrier of this warpgroup
+  uint32_t ph;            // its phase
+  // p-mapping: row of an M=128 accumulator
+  int rp;
+  // s-mapping: row of the interleaved M=64 accumulators
+  int h, i, rs;
+};
+
+__device__ __forceinline__ WgCtx make_ctx(int wg_threads_base, uint32_t tmem, uint64_t* bar) {
+  WgCtx c;
+  c.wt = threadIdx.x - wg_threads_base;
+  c.q = c.wt >> 5; c.lane = c.wt & 31; c.wg = threadIdx.x >> 7;
+  c.tmem = tmem; c.lane_base = uint32_t(32 * c.q) << 16;
+  c.bar = bar; c.ph = 0;
+  c.rp = c.wt;
+  c.h = c.lane >> 4; c.i = c.lane & 15; c.rs = 64 * c.h + 16 * c.q + c.i;
+  return c;
+}
+
+// operands written by this warpgroup -> visible to the tensor core; warpgroup barrier
+__device__ __forceinline__ void wg_sync_for_mma(const WgCtx& c) {
+  fence_proxy_async();
+  tc_fence_before_sync();
+  named_bar_sync(1 + c.wg, kWgThreads);
+  tc_fence_after_sync();
+}
+__device__ __forceinline__ void wg_wait_mma(WgCtx& c) {
+  mbar_wait(c.bar, c.ph);
+  c.ph ^= 1;
+  tc_fence_after_sync();
+}
+
+// K-major operand (rows x K cols, chunk stride cs): D (+)= A B^T over `ksteps` K=16 steps
+__device__ __forceinline__ void mma_steps(uint32_t d, uint64_t ad, uint32_t a_step, uint64_t bd, uint32_t b_step,
+                                          uint32_t idesc, int ksteps, bool acc) {
+  for (int ks = 0; ks < ksteps; ++ks)
+    umma_bf16(d, desc_advance(ad, ks * a_step), desc_advance(bd, ks * b_step), idesc, (acc || ks > 0) ? 1u : 0u);
+}
+
+// TMEM columns [c0, c0+16) of my row -> bf16 -> two 16-byte chunks of a 128-row operand
+__device__ __forceinline__ void store_chunks16(uint8_t* op, int row, int col0, const uint32_t (&r)[16]) {
+  float lo[8], hi[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { lo[e] = __uint_as_float(r[e]); hi[e] = __uint_as_float(r[8 + e]); }
+  *reinterpret_cast<uint4*>(op + uint32_t(col0 >> 3) * kCS + row_off(row)) = pack_bf16x8(lo);
+  *reinterpret_cast<uint4*>(op + uint32_t((col0 >> 3) + 1) * kCS + row_off(row)) = pack_bf16x8(hi);
+}
+
+// accumulator columns [col, col+NC) of my row (p-mapping) -> bf16 operand
+template <int NC>
+__device__ __forceinline__ void acc_to_operand(const WgCtx& c, uint32_t col, uint8_t* op) {
+  static_assert(NC % 16 == 0, "16-column steps");
+#pragma unroll
+  for (int c0 = 0; c0 < NC; c0 += 32) {
+    uint32_t r0[16], r1[16];
+    tmem_ld16_nw(c.tmem + c.lane_base + col + c0, r0);
+    if (c0 + 16 < NC) tmem_ld16_nw(c.tmem + c.lane_base + col + c0 + 16, r1);
+    tmem_wait_ld();
+    store_chunks16(op, c.rp, c0, r0);
+    if (c0 + 16 < NC) store_chunks16(op, c.rp, c0 + 16, r1);
+  }
+}
+
+// classifier read-back (p-mapping): D[(b,r)][(r',c)], keep r' == r, sum the sample's 16 chunks, add to logits
+__device__ __forceinline__ void cls_readback(const WgCtx& c, uint32_t col, float* logits, int b, bool valid) {
+  uint32_t v[4][16];
+#pragma unroll
+  for (int qq = 0; qq < 4; ++qq) tmem_ld16_nw(c.tmem + c.lane_base + col + 16 * qq, v[qq]);
+  tmem_wait_ld();
+  const int r = c.rp & 15, grp = r >> 2, m = r & 3;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int qq = 0; qq < 4; ++qq) {
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const uint32_t x = m == 0 ? v[qq][cc] : m == 1 ? v[qq][4 + cc] : m == 2 ? v[qq][8 + cc] : v[qq][12 + cc];
+      if (grp == qq) s[cc] = __uint_as_float(x);
+    }
+  }
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s[cc] += __shfl_xor_sync(0xffffffffu, s[cc], o);
+  }
+  if (r == 0 && valid) {
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) atomicAdd(logits + size_t(b) * kClasses + cc, s[cc]);
+  }
+}
+
+// softmax over my row's 16 scores (s-mapping), optional reverse weights (multimodal_model.py:58-60, :89-98);
+// p[] returns the weights that multiply V
+__device__ __forceinline__ void softmax16(const WgCtx& c, uint32_t col_s, bool reverse, float (&p)[16]) {
+  uint32_t r[16];
+  tmem_ld16_nw(c.tmem + c.lane_base + col_s + 16 * c.q, r);
+  tmem_wait_ld();
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { p[j] = __uint_as_float(r[j]); m = fmaxf(m, p[j]); }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { p[j] = __expf(p[j] - m); sum += p[j]; }
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float a = p[j] * inv;
+    p[j] = reverse ? (1.0f - a) * (1.0f / float(kL - 1)) : a;
+  }
+}
+
+// my row of one [64 x 64] half of P / dS: the sample's 16 columns are chunks 2q, 2q+1, the rest is zero
+__device__ __forceinline__ void store_p_row(const WgCtx& c, uint8_t* pbuf, const float (&p)[16], bool zero_rest) {
+  uint8_t* base = pbuf + c.h * kPHalf + row_off(16 * c.q + c.i);
+  const float lo[8] = {p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7]};
+  const float hi[8] = {p[8], p[9], p[10], p[11], p[12], p[13], p[14], p[15]};
+#pragma unroll
+  for (int kc = 0; kc < 8; ++kc) {
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (kc == 2 * c.q) v = pack_bf16x8(lo);
+    else if (kc == 2 * c.q + 1) v = pack_bf16x8(hi);
+    else if (!zero_rest) continue;
+    *reinterpret_cast<uint4*>(base + kc * kPCS) = v;
+  }
+}
+
+// LayerNorm statistics of my context row (s-mapping accumulator columns [col, col+DV))
+template <int DV>
+__device__ __forceinline__ void ln_stats_tmem(const WgCtx& c, uint32_t col, float& mean, float& rstd) {
+  float s = 0.f, ss = 0.f;
+#pragma unroll
+  for (int c0 = 0; c0 < DV; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld16_nw(c.tmem + c.lane_base + col + c0, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int e = 0; e < 16; ++e) { const float x = __uint_as_float(r[e]); s += x; ss = fmaf(x, x, ss); }
+  }
+  mean = s * (1.0f / float(DV));
+  const float var = fmaxf(ss * (1.0f / float(DV)) - mean * mean, 0.f);
+  rstd = rsqrtf(var + kLnEps);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// self-attention forward: features -> SA output image (bf16 operand layout) + the classifier's feature term
+// ---------------------------------------------------------------------------------------------------------------
+template <int DIN_>
+struct SaCfg {
+  static constexpr int DIN = DIN_, KE = DIN_ + 16, DV = kDV_SA;
+  static constexpr uint32_t BZ_LBO = DIN * 16, BZ_BYTES = blob_bytes(DIN, KE);
+  static constexpr uint32_t BV_LBO = DV * 16, BV_BYTES = blob_bytes(DV, KE);
+  static constexpr uint32_t BC_LBO = kNCls * 16, BC_BYTES = blob_bytes(kNCls, DIN);
+  static constexpr uint32_t W_BYTES = BZ_BYTES + BV_BYTES + BC_BYTES;
+  // TMEM columns (relative to the warpgroup base)
+  static constexpr uint32_t COL_Z = 0, COL_V = DIN, COL_CLS = DIN + DV, COL_S = 0, COL_C = 64;
+  static_assert(DIN + DV + kNCls <= 256, "warpgroup TMEM budget");
+};
+
+constexpr uint32_t kSaTileBytes = op_bytes(kDV_SA);   // one SA output image: [128 x 96] bf16 = 12 chunk columns
+
+struct SaRole {
+  const float* feat;      // [B][16*DIN] fp32
+  float* norms;           // [B] (out)
+  const float* ln_g; const float* ln_b;
+  const void* blobs;      // bz | bv | bc, contiguous
+  void* out_tiles;        // [tiles][kSaTileBytes]
+};
+struct SaFwdArgs {
+  SaRole role[2];         // 0: image (DIN 80), 1: text (DIN 48)
+  float* logits;          // += feature term (null: classifier does not see the features)
+  int batch;
+};
+
+// warpgroup buffers of the SA forward (sized for the wider role)
+struct SaFwdSmem {
+  static constexpr uint32_t X = 0;                                   // [128 x (80+16)]
+  static constexpr uint32_t ZP = al128(X + op_bytes(96));             // Z [128 x 80]; later P (2 x [64 x 64])
+  static constexpr uint32_t V = al128(ZP + op_bytes(80));             // [128 x 96]
+  static constexpr uint32_t BYTES = al128(V + op_bytes(96));
+  static_assert(op_bytes(80) >= 2 * kPHalf, "P aliases Z");
+};
+struct SaFwdLayout {
+  static constexpr uint32_t W0 = 0;                                               // image blobs
+  static constexpr uint32_t W1 = al128(W0 + SaCfg<80>::W_BYTES);                   // text blobs
+  static constexpr uint32_t WG0 = al128(W1 + SaCfg<48>::W_BYTES);
+  static constexpr uint32_t WG1 = WG0 + SaFwdSmem::BYTES;
+  static constexpr uint32_t LN = WG1 + SaFwdSmem::BYTES;                            // 2 roles x (gamma, beta) x 96 fp32
+  static constexpr uint32_t BAR = al128(LN + 2 * 2 * 96 * 4);                       // mbarriers + tmem slot
+  static constexpr uint32_t BYTES = BAR + 64;
+  static_assert(BYTES <= 232448, "SA forward does not fit shared memory");
+};
+
+// load + L2-normalise (multimodal_model.py:662-665) this warp's two samples into the bf16 operand
+template <int DIN>
+__device__ __forceinline__ void stage_features(const WgCtx& c, uint8_t* xop, const float* __restrict__ feat,
+                                               float* __restrict__ norms, int b0, int batch) {
+  constexpr int KCS = DIN / 8, ITEMS = kL * KCS, PER = (ITEMS + 31) / 32;
+  float v[2][PER][8];
+  float ss[2] = {0.f, 0.f};
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int b = b0 + 2 * c.q + s;
+    const float* base = feat + size_t(b) * (kL * DIN);
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int it = c.lane + 32 * k;
+      float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+      if (b < batch && (ITEMS % 32 == 0 || it < ITEMS)) {
+        lo = __ldg(reinterpret_cast<const float4*>(base + it * 8));
+        hi = __ldg(reinterpret_cast<const float4*>(base + it * 8 + 4));
+      }
+      v[s][k][0] = lo.x; v[s][k][1] = lo.y; v[s][k][2] = lo.z; v[s][k][3] = lo.w;
+      v[s][k][4] = hi.x; v[s][k][5] = hi.y; v[s][k][6] = hi.z; v[s][k][7] = hi.w;
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+#pragma unroll
+    for (int k = 0; k < PER; ++k)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ss[s] = fmaf(v[s][k][e], v[s][k][e], ss[s]);
+    ss[s] = warp_sum(ss[s]);
+  }
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int g = 2 * c.q + s, b = b0 + g;
+    const float nrm = sqrtf(ss[s]);
+    const float inv = b < batch ? 1.0f / nrm : 0.f;      // no epsilon, like the reference
+    if (c.lane == 0 && b < batch && norms) norms[b] = nrm;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int it = c.lane + 32 * k;
+      if (ITEMS % 32 != 0 && it >= ITEMS) continue;
+      const int row = it / KCS, kc = it - row * KCS;
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = v[s][k][e] * inv;
+      *reinterpret_cast<uint4*>(xop + uint32_t(kc) * kCS + row_off(g * kL + row)) = pack_bf16x8(o);
+    }
+  }
+  // the bias column: x[row][DIN] = 1, x[row][DIN+1 .. DIN+15] = 0
+  *reinterpret_cast<uint4*>(xop + uint32_t(KCS) * kCS + row_off(c.wt)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+  *reinterpret_cast<uint4*>(xop + uint32_t(KCS + 1) * kCS + row_off(c.wt)) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+template <class C>
+__device__ __forceinline__ void sa_fwd_tile(WgCtx& c, const SaFwdArgs& a, const SaRole& R, uint8_t* wsm, uint8_t* bsm,
+                                            const float* ln_s, int tile, bool reverse_unused) {
+  (void)reverse_unused;
+  const int b0 = tile * 8;
+  uint8_t* xop = bsm + SaFwdSmem::X;
+  uint8_t* zop = bsm + SaFwdSmem::ZP;
+  uint8_t* vop = bsm + SaFwdSmem::V;
+  stage_features<C::DIN>(c, xop, R.feat, R.norms, b0, a.batch);
+  wg_sync_for_mma(c);
+  // ---- Z | V | classifier feature term: three MMA chains over the same A operand ------------------------------
+  if (c.wt == 0) {
+    const uint64_t ax = make_smem_desc(smem_u32(xop), kCS, kRS);
+    mma_steps(c.tmem + C::COL_Z, ax, 2 * kCS, make_smem_desc(smem_u32(wsm), C::BZ_LBO, 128), 2 * C::BZ_LBO,
+              make_idesc_bf16(128, C::DIN, 0, 0), C::KE / 16, false);
+    mma_steps(c.tmem + C::COL_V, ax, 2 * kCS, make_smem_desc(smem_u32(wsm + C::BZ_BYTES), C::BV_LBO, 128),
+              2 * C::BV_LBO, make_idesc_bf16(128, C::DV, 0, 0), C::KE / 16, false);
+    if (a.logits)
+      mma_steps(c.tmem + C::COL_CLS, ax, 2 * kCS,
+                make_smem_desc(smem_u32(wsm + C::BZ_BYTES + C::BV_BYTES), C::BC_LBO, 128), 2 * C::BC_LBO,
+                make_idesc_bf16(128, kNCls, 0, 0), C::DIN / 16, false);
+    umma_commit(c.bar);
+  }
+  wg_wait_mma(c);
+  acc_to_operand<C::DIN>(c, C::COL_Z, zop);
+  acc_to_operand<C::DV>(c, C::COL_V, vop);
+  if (a.logits) cls_readback(c, C::COL_CLS, a.logits, b0 + (c.rp >> 4), b0 + (c.rp >> 4) < a.batch);
+  wg_sync_for_mma(c);
+  // ---- scores: two M=64 halves, S_h = Z_h X_h^T --------------------------------------------------------------
+  if (c.wt == 0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      mma_steps(c.tmem + (uint32_t(16 * h) << 16) + C::COL_S, make_smem_desc(smem_u32(zop + h * 8 * kRS), kCS, kRS),
+                2 * kCS, make_smem_desc(smem_u32(xop + h * 8 * kRS), kCS, kRS), 2 * kCS,
+                make_idesc_bf16(64, 64, 0, 0), C::DIN / 16, false);
+    umma_commit(c.bar);
+  }
+  wg_wait_mma(c);
+  {
+    float p[16];
+    softmax16(c, C::COL_S, false, p);     // SelfAttention has no reverse weights
+    store_p_row(c, zop, p, true);         // P reuses Z's bytes: every chunk of my row is rewritten
+  }
+  wg_sync_for_mma(c);
+  // ---- context: C_h = P_h V_h -----------------------------------------------------------------------------------
+  if (c.wt == 0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      mma_steps(c.tmem + (uint32_t(16 * h) << 16) + C::COL_C, make_smem_desc(smem_u32(zop + h * kPHalf), kPCS, kRS),
+                2 * kPCS, make_smem_desc(smem_u32(vop + h * 8 * kRS), kRS, kCS), 2 * kRS,
+                make_idesc_bf16(64, C::DV, 0, 1), 4, false);
+    umma_commit(c.bar);
+  }
+  wg_wait_mma(c);
+  // ---- LayerNorm + ReLU (multimodal_model.py:65-66) -> bf16 image row ------------------------------------------
+  {
+    float mean, rstd;
+    ln_stats_tmem<C::DV>(c, C::COL_C, mean, rstd);
+    uint8_t* dst = static_cast<uint8_t*>(R.out_tiles) + size_t(tile) * kSaTileBytes + row_off(c.rs);
+#pragma unroll
+    for (int c0 = 0; c0 < C::DV; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16_nw(c.tmem + c.lane_base + C::COL_C + c0, r);
+      tmem_wait_ld();
+      float o[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        o[e] = fmaxf(fmaf((__uint_as_float(r[e]) - mean) * rstd, ln_s[c0 + e], ln_s[96 + c0 + e]), 0.f);
+      const float lo[8] = {o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]};
+      const float hi[8] = {o[8], o[9], o[10], o[11], o[12], o[13], o[14], o[15]};
+      *reinterpret_cast<uint4*>(dst + uint32_t(c0 >> 3) * kCS) = pack_bf16x8(lo);
+      *reinterpret_cast<uint4*>(dst + uint32_t((c0 >> 3) + 1) * kCS) = pack_bf16x8(hi);
+    }
+  }
+  tc_fence_before_sync();
+  named_bar_sync(1 + c.wg, kWgThreads);   // TMEM columns and operand buffers are reused by the next tile
+  tc_fence_after_sync();
+}
+
+__global__ void __launch_bounds__(kCtaThreads, 1) sa_fwd_kernel(const SaFwdArgs a) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  using L = SaFwdLayout;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::BAR);    // [0]: weights, [1], [2]: warpgroup MMA barriers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  float* ln_s = reinterpret_cast<float*>(sm + L::LN);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(&bars[0], SaCfg<80>::W_BYTES + SaCfg<48>::W_BYTES);
+    bulk_g2s(sm + L::W0, a.role[0].blobs, SaCfg<80>::W_BYTES, &bars[0]);
+    bulk_g2s(sm + L::W1, a.role[1].blobs, SaCfg<48>::W_BYTES, &bars[0]);
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  for (int i = tid; i < 2 * 96; i += kCtaThreads) {
+    const int r = i / 96, k = i - r * 96;
+    ln_s[r * 192 + k] = a.role[r].ln_g[k];
+    ln_s[r * 192 + 96 + k] = a.role[r].ln_b[k];
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  mbar_wait(&bars[0], 0);
+  const int wg = tid >> 7;
+  WgCtx c = make_ctx(wg * kWgThreads, tmem + uint32_t(wg) * 256u, &bars[1 + wg]);
+  uint8_t* bsm = sm + (wg == 0 ? L::WG0 : L::WG1);
+  const int tiles = (a.batch + 7) / 8;
+  int round = 0;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++round) {
+    const int role = (wg + round) & 1;     // the two warpgroups take the tile's two modalities, alternating
+    if (role == 0) sa_fwd_tile<SaCfg<80>>(c, a, a.role[0], sm + L::W0, bsm, ln_s, tile, false);
+    else           sa_fwd_tile<SaCfg<48>>(c, a, a.role[1], sm + L::W1, bsm, ln_s + 192, tile, false);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// cross-attention forward (both directions): SA images -> classifier logits
+// ---------------------------------------------------------------------------------------------------------------
+struct CaCfg {
+  static constexpr int DIN = kDV_SA, KE = DIN + 16, DV = kDV_CA;
+  static constexpr uint32_t BZ_LBO = DIN * 16, BZ_BYTES = blob_bytes(DIN, KE);
+  static constexpr uint32_t BV_LBO = DV * 16, BV_BYTES = blob_bytes(DV, KE);
+  static constexpr uint32_t BC_LBO = kNCls * 16, BC_BYTES = blob_bytes(kNCls, DV);
+  static constexpr uint32_t W_BYTES = BZ_BYTES + BV_BYTES + BC_BYTES;
+  static constexpr uint32_t COL_Z = 0, COL_V = DIN, COL_S = 0, COL_C = 64, COL_CLS = 112;
+};
+
+struct CaDir {
+  const void* blobs;        // bz | bv | bc
+  const float* ln_g; const float* ln_b;
+};
+struct CaFwdArgs {
+  CaDir dir[2];             // 0: cross_attention_1 (q: text SA, kv: image SA); 1: cross_attention_2 (:683-686)
+  const void* t_tiles;      // text SA images
+  const void* i_tiles;      // image SA images
+  float* logits;
+  int batch, reverse;
+};
+struct CaFwdSmem {
+  static constexpr uint32_t XQ = 0;                                   // [128 x 112]; Z, P, Out reuse its first 96 columns
+  static constexpr uint32_t XKV = al128(XQ + op_bytes(112));
+  static constexpr uint32_t V = al128(XKV + op_bytes(112));           // [128 x 48]
+  static constexpr uint32_t BYTES = al128(V + op_bytes(48));
+};
+struct CaFwdLayout {
+  static constexpr uint32_t W0 = 0;
+  static constexpr uint32_t W1 = al128(W0 + CaCfg::W_BYTES);
+  static constexpr uint32_t WG0 = al128(W1 + CaCfg::W_BYTES);
+  static constexpr uint32_t WG1 = WG0 + CaFwdSmem::BYTES;
+  static constexpr uint32_t LN = WG1 + CaFwdSmem::BYTES;              // 2 dirs x (gamma, beta) x 48
+  static constexpr uint32_t BAR = al128(LN + 2 * 2 * 48 * 4);         // weights, 2 x MMA, 2 x tile-load barriers, tmem slot
+  static constexpr uint32_t BYTES = BAR + 64;
+  static_assert(BYTES <= 232448, "CA forward does not fit shared memory");
+};
+
+__device__ __forceinline__ void write_bias_columns(uint8_t* op, int kc0, int row) {
+  *reinterpret_cast<uint4*>(op + uint32_t(kc0) * kCS + row_off(row)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+  *reinterpret_cast<uint4*>(op + uint32_t(kc0 + 1) * kCS + row_off(row)) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+__device__ __forceinline__ void ca_fwd_tile(WgCtx& c, const CaFwdArgs& a, int d, uint8_t* wsm, uint8_t* bsm,
+                                            const float* ln_s, uint64_t* bar_ld, uint32_t& ph_ld, int tile) {
+  using C = CaCfg;
+  const int b0 = tile * 8;
+  uint8_t* xq = bsm + CaFwdSmem::XQ;
+  uint8_t* xkv = bsm + CaFwdSmem::XKV;
+  uint8_t* vop = bsm + CaFwdSmem::V;
+  // ---- SA images of this tile through the bulk-copy engine ---------------------------------------------------
+  if (c.wt == 0) {
+    const uint8_t* qsrc = static_cast<const uint8_t*>(d == 0 ? a.t_tiles : a.i_tiles) + size_t(tile) * kSaTileBytes;
+    const uint8_t* ksrc = static_cast<const uint8_t*>(d == 0 ? a.i_tiles : a.t_tiles) + size_t(tile) * kSaTileBytes;
+    mbar_arrive_expect_tx(bar_ld, 2 * kSaTileBytes);
+    bulk_g2s(xq, qsrc, kSaTileBytes, bar_ld);
+    bulk_g2s(xkv, ksrc, kSaTileBytes, bar_ld);
+  }
+  write_bias_columns(xq, C::DIN / 8, c.wt);     // (Z / P / Out reuse only the first 96 columns of xq, but the
+  write_bias_columns(xkv, C::DIN / 8, c.wt);    //  image load of the next tile must not race with stale readers)
+  mbar_wait(bar_ld, ph_ld);
+  ph_ld ^= 1;
+  wg_sync_for_mma(c);
+  if (c.wt == 0) {
+    mma_steps(c.tmem + C::COL_Z, make_smem_desc(smem_u32(xq), kCS, kRS), 2 * kCS,
+              make_smem_desc(smem_u32(wsm), C::BZ_LBO, 128), 2 * C::BZ_LBO, make_idesc_bf16(128, C::DIN, 0, 0),
+              C::KE / 16, false);
+    mma_steps(c.tmem + C::COL_V, make_smem_desc(smem_u32(xkv), kCS, kRS), 2 * kCS,
+              make_smem_desc(smem_u32(wsm + C::BZ_BYTES), C::BV_LBO, 128), 2 * C::BV_LBO,
+              make_idesc_bf16(128, C::DV, 0, 0), C::KE / 16, false);
+    umma_commit(c.bar);
+  }
+  wg_wait_mma(c);
+  acc_to_operand<C::DIN>(c, C::COL_Z, xq);      // Z overwrites the query image (its projection is done)
+  acc_to_operand<C::DV>(c, C::COL_V, vop);
+  wg_sync_for_mma(c);
+  if (c.wt == 0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      mma_steps(c.tmem + (uint32_t(16 * h) << 16) + C::COL_S, make_smem_desc(smem_u32(xq + h * 8 * kRS), kCS, kRS),
+                2 * kCS, make_smem_desc(smem_u32(xkv + h * 8 * kRS), kCS, kRS), 2 * kCS,
+                make_idesc_bf16(64, 64, 0, 0), C::DIN / 16, false);
+    umma_commit(c.bar);
+  }
+  wg_wait_mma(c);
+  {
+    float p[16];
+    softmax16(c, C::COL_S, a.reverse != 0, p);
+    store_p_row(c, xq, p, true);
+  }
+  wg_sync_for_mma(c);
+  if (c.wt == 0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      mma_steps(c.tmem + (uint32_t(16 * h) << 16) + C::COL_C, make_smem_desc(smem_u32(xq + h * kPHalf), kPCS, kRS),
+                2 * kPCS, make_smem_desc(smem_u32(vop + h * 8 * kRS), kRS, kCS), 2 * kRS,
+                make_idesc_bf16(64, C::DV, 0, 1), 4, false);
+    umma_commit(c.bar);
+  }
+  wg_wait_mma(c);
+  // ---- LayerNorm + ReLU (:105-106) -> classifier operand ------------------------------------------------------
+  {
+    float mean, rstd;
+    ln_stats_tmem<C::DV>(c, C::COL_C, mean, rstd);
+#pragma unroll
+    for (int c0 = 0; c0 < C::DV; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16_nw(c.tmem + c.lane_base + C::COL_C + c0, r);
+      tmem_wait_ld();
+      float o[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        o[e] = fmaxf(fmaf((__uint_as_float(r[e]) - mean) * rstd, ln_s[c0 + e], ln_s[48 + c0 + e]), 0.f);
+      const float lo[8] = {o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]};
+      const float hi[8] = {o[8], o[9], o[10], o[11], o[12], o[13], o[14], o[15]};
+      *reinterpret_cast<uint4*>(xq + uint32_t(c0 >> 3) * kCS + row_off(c.rs)) = pack_bf16x8(lo);
+      *reinterpret_cast<uint4*>(xq + uint32_t((c0 >> 3) + 1) * kCS + row_off(c.rs)) = pack_bf16x8(hi);
+    }
+  }
+  wg_sync_for_mma(c);
+  if (c.wt == 0) {
+    mma_steps(c.tmem + C::COL_CLS, make_smem_desc(smem_u32(xq), kCS, kRS), 2 * kCS,
+              make_smem_desc(smem_u32(wsm + C::BZ_BYTES + C::BV_BYTES), C::BC_LBO, 128), 2 * C::BC_LBO,
+              make_idesc_bf16(128, kNCls, 0, 0), C::DV / 16, false);
+    umma_commit(c.bar);
+  }
+  wg_wait_mma(c);
+  cls_readback(c, C::COL_CLS, a.logits, b0 + (c.rp >> 4), b0 + (c.rp >> 4) < a.batch);
+  tc_fence_before_sync();
+  named_bar_sync(1 + c.wg, kWgThreads);
+  tc_fence_after_sync();
+}
+
+__global__ void __launch_bounds__(kCtaThreads, 1) ca_fwd_kernel(const CaFwdArgs a) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  using L = CaFwdLayout;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::BAR);   // [0] weights, [1],[2] MMA, [3],[4] tile loads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  float* ln_s = reinterpret_cast<float*>(sm + L::LN);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(&bars[0], 2 * CaCfg::W_BYTES);
+    bulk_g2s(sm + L::W0, a.dir[0].blobs, CaCfg::W_BYTES, &bars[0]);
+    bulk_g2s(sm + L::W1, a.dir[1].blobs, CaCfg::W_BYTES, &bars[0]);
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  for (int i = tid; i < 2 * 48; i += kCtaThreads) {
+    const int d = i / 48, k = i - d * 48;
+    ln_s[d * 96 + k] = a.dir[d].ln_g[k];
+    ln_s[d * 96 + 48 + k] = a.dir[d].ln_b[k];
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  mbar_wait(&bars[0], 0);
+  const int wg = tid >> 7;
+  WgCtx c = make_ctx(wg * kWgThreads, tmem + uint32_t(wg) * 256u, &bars[1 + wg]);
+  uint8_t* bsm = sm + (wg == 0 ? L::WG0 : L::WG1);
+  uint32_t ph_ld = 0;
+  const int tiles = (a.batch + 7) / 8;
+  int round = 0;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++round) {
+    const int d = (wg + round) & 1;
+    ca_fwd_tile(c, a, d, sm + (d == 0 ? L::W0 : L::W1), bsm, ln_s + d * 96, &bars[3 + wg], ph_ld, tile);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace htc
+}  // namespace mmrca

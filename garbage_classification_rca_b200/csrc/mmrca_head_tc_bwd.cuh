@@ -1,0 +1,825 @@
+// bf16 tensor-core pipeline of the MM-RCA head: cross-entropy, backward kernels, gradient finalisation.
+//
+// Backward of CVPR_code/multimodal_model.py:661-728 + CrossEntropyLoss (main_both.py:87-93,110-112), in the
+// algebra of mmrca_head_tc.cuh (Z = Xq M + u replaces Q and K).  Per attention block and 128-row tile:
+//   recompute   Z, V, S, P, C                    (nothing but the block inputs is read back from HBM)
+//   LayerNorm   dy = dOut [y > 0],  dC = rstd (dy g - mean(dy g) - xhat mean(dy g xhat))
+//   attention   dP = dC V^T,  dV = P^T dC,  dS = softmax'(dP),  dZ = dS Xkv
+//   inputs      dXq = dZ M^T,  dXkv = dS^T Z + dV Wv            (CA blocks: they feed the SA backward)
+//   parameters  dM_ext += Xq_ext^T dZ,  dWv_ext += Xkv_ext^T dV   (the ones column of X_ext yields du, db_value)
+//               dWf^T  += F^T DL        (classifier rows of this source; DL = dlogits spread on the chunk diagonal)
+//               [dgamma | dbeta] += [dy xhat | dy]^T 1
+// Every contraction, including the reductions over the batch, is a tcgen05.mma.  The parameter gradients stay in
+// TMEM for the whole persistent CTA and are flushed once at the end with lane-coalesced atomics; dW_query,
+// dW_key, db_query follow from dM, du in finalize_kernel (dM = Wq^T dWk-ish products of size d_in^2, once per step).
+// A CTA owns one tile at a time; its two warpgroups own the same rows and split the columns / the kinds of
+// operand they emit, so the per-row scalars (softmax, LayerNorm statistics) are computed redundantly instead of
+// being exchanged.
+#pragma once
+#include "mmrca_head_tc.cuh"
+
+namespace mmrca {
+namespace htc {
+
+// ---------------------------------------------------------------------------------------------------------------
+// CrossEntropyLoss(weight, label_smoothing), mean reduction (main_both.py:87-93), 4 classes, many CTAs.
+// Every CTA recomputes the normaliser sum_b w[y_b] from the labels, so dlogits leave normalised in one pass.
+// ---------------------------------------------------------------------------------------------------------------
+struct Ce4Args {
+  const float* logits; const int64_t* labels; const float* cw; float eps; int batch;
+  float* dlogits;     // [B][4]
+  float* loss;        // [1], zeroed beforehand (accumulated)
+  float* g_bf;        // [4] accumulated (null: skip)
+};
+
+__global__ void __launch_bounds__(256) ce4_kernel(const Ce4Args a) {
+  __shared__ float red[8];
+  __shared__ float s_den;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float den = float(a.batch);
+  if (a.cw) {
+    float w = 0.f;
+    for (int b = tid; b < a.batch; b += 256) w += __ldg(a.cw + a.labels[b]);
+    w = warp_sum(w);
+    if (lane == 0) red[warp] = w;
+    __syncthreads();
+    if (tid == 0) { float t = 0.f; for (int i = 0; i < 8; ++i) t += red[i]; s_den = t; }
+    __syncthreads();
+    den = s_den;
+  }
+  const float inv_den = 1.0f / den;
+  float wc[4] = {1.f, 1.f, 1.f, 1.f};
+  if (a.cw) { for (int c = 0; c < 4; ++c) wc[c] = __ldg(a.cw + c); }
+  float lsum = 0.f, db[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int b = blockIdx.x * 256 + tid; b < a.batch; b += gridDim.x * 256) {
+    const float4 zz = __ldg(reinterpret_cast<const float4*>(a.logits) + b);
+    float z[4] = {zz.x, zz.y, zz.z, zz.w};
+    const float m = fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3]));
+    const float se = expf(z[0] - m) + expf(z[1] - m) + expf(z[2] - m) + expf(z[3] - m);
+    const float lse = m + logf(se);
+    const int y = int(a.labels[b]);
+    float t[4], tsum = 0.f, li = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      t[c] = (a.eps * 0.25f) * wc[c] + (c == y ? (1.f - a.eps) * wc[c] : 0.f);
+      z[c] -= lse;
+      li -= t[c] * z[c];
+      tsum += t[c];
+    }
+    lsum += li;
+    float d[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { d[c] = (expf(z[c]) * tsum - t[c]) * inv_den; db[c] += d[c]; }
+    if (a.dlogits) reinterpret_cast<float4*>(a.dlogits)[b] = make_float4(d[0], d[1], d[2], d[3]);
+  }
+  lsum = warp_sum(lsum);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) db[c] = warp_sum(db[c]);
+  if (lane == 0) {
+    if (a.loss) atomicAdd(a.loss, lsum * inv_den);
+    if (a.g_bf) { for (int c = 0; c < 4; ++c) atomicAdd(a.g_bf + c, db[c]); }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// shared pieces of the backward tile kernels (CTA = 256 threads, both warpgroups on the same rows)
+// ---------------------------------------------------------------------------------------------------------------
+struct BwCtx {
+  int tid, w, q, lane;      // w: warpgroup (column / operand-kind split)
+  uint32_t tmem, lane_base;
+  uint64_t* bar; uint32_t ph;
+  int rp;                   // p-mapping row
+  int h, i, rs;             // s-mapping
+};
+__device__ __forceinline__ BwCtx make_bwctx(uint32_t tmem, uint64_t* bar) {
+  BwCtx c;
+  c.tid = threadIdx.x; c.w = c.tid >> 7; c.q = (c.tid >> 5) & 3; c.lane = c.tid & 31;
+  c.tmem = tmem; c.lane_base = uint32_t(32 * c.q) << 16; c.bar = bar; c.ph = 0;
+  c.rp = c.tid & 127;
+  c.h = c.lane >> 4; c.i = c.lane & 15; c.rs = 64 * c.h + 16 * c.q + c.i;
+  return c;
+}
+__device__ __forceinline__ void cta_sync_for_mma() {
+  fence_proxy_async();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+}
+__device__ __forceinline__ void cta_wait_mma(BwCtx& c) {
+  mbar_wait(c.bar, c.ph);
+  c.ph ^= 1;
+  tc_fence_after_sync();
+}
+__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float (&f)[8]) {
+  f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+  f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+  f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+  f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+__device__ __forceinline__ void ld16f(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  tmem_ld16_nw(taddr, r);
+  tmem_wait_ld();
+#pragma unroll
+  for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
+}
+__device__ __forceinline__ void st_chunks16(uint8_t* op, int row, int col0, const float (&v)[16]) {
+  const float lo[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
+  const float hi[8] = {v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]};
+  *reinterpret_cast<uint4*>(op + uint32_t(col0 >> 3) * kCS + row_off(row)) = pack_bf16x8(lo);
+  *reinterpret_cast<uint4*>(op + uint32_t((col0 >> 3) + 1) * kCS + row_off(row)) = pack_bf16x8(hi);
+}
+// accumulator columns [col + c_lo, col + c_hi) of `row`'s lane -> operand columns [c_lo, c_hi)
+__device__ __forceinline__ void acc_cols_to_operand(const BwCtx& c, uint32_t col, int c_lo, int c_hi, uint8_t* op, int row) {
+#pragma unroll 1
+  for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+    float v[16];
+    ld16f(c.tmem + c.lane_base + col + c0, v);
+    st_chunks16(op, row, c0, v);
+  }
+}
+
+// DL[row (b,r)][(r',c)] = dlogits[b][c] [r' == r]: warpgroup w writes column groups 4w .. 4w+3 of the row
+__device__ __forceinline__ void stage_dl(const BwCtx& c, uint8_t* dl, const float* __restrict__ dlogits, int b0, int batch) {
+  const int g = c.rp >> 4, r = c.rp & 15, b = b0 + g;
+  float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (b < batch) d = __ldg(reinterpret_cast<const float4*>(dlogits) + b);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int kc = 4 * c.w + k;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (kc == (r >> 1)) {
+      const uint32_t lo = pack_bf16x2(d.x, d.y), hi = pack_bf16x2(d.z, d.w);
+      if (r & 1) { v.z = lo; v.w = hi; } else { v.x = lo; v.y = hi; }
+    }
+    *reinterpret_cast<uint4*>(dl + uint32_t(kc) * kCS + row_off(c.rp)) = v;
+  }
+}
+
+// softmax backward on my row (s-mapping): p[] are the weights that multiplied V; ds[] = dL/dS
+__device__ __forceinline__ void softmax_bwd16(const BwCtx& c, uint32_t col_dp, bool reverse, const float (&p)[16], float (&ds)[16]) {
+  float dp[16];
+  ld16f(c.tmem + c.lane_base + col_dp + 16 * c.q, dp);
+  float dot0 = 0.f, dot1 = 0.f;
+  float a[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    a[j] = reverse ? 1.0f - float(kL - 1) * p[j] : p[j];                 // A from (1 - A)/(L - 1)
+    dp[j] = reverse ? dp[j] * (-1.0f / float(kL - 1)) : dp[j];           // dA
+    if (j & 1) dot1 = fmaf(dp[j], a[j], dot1); else dot0 = fmaf(dp[j], a[j], dot0);
+  }
+  const float dot = dot0 + dot1;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) ds[j] = a[j] * (dp[j] - dot);
+}
+// my row of a [64 x 64] half: warpgroup w writes the column groups of parity w (data group 2q+w, zeros elsewhere)
+__device__ __forceinline__ void store_half_row_split(const BwCtx& c, uint8_t* buf, const float (&v)[16], bool zero_rest) {
+  uint8_t* base = buf + c.h * kPHalf + row_off(16 * c.q + c.i);
+  float x[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) x[e] = c.w ? v[8 + e] : v[e];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int kc = 2 * k + c.w;
+    if (kc == 2 * c.q + c.w) *reinterpret_cast<uint4*>(base + kc * kPCS) = pack_bf16x8(x);
+    else if (zero_rest) *reinterpret_cast<uint4*>(base + kc * kPCS) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+__device__ __forceinline__ void softmax16_bw(const BwCtx& c, uint32_t col_s, bool reverse, float (&p)[16]) {
+  float s[16];
+  ld16f(c.tmem + c.lane_base + col_s + 16 * c.q, s);
+  float m0 = fmaxf(s[0], s[1]), m1 = fmaxf(s[2], s[3]);
+#pragma unroll
+  for (int j = 4; j < 16; j += 2) { m0 = fmaxf(m0, s[j]); m1 = fmaxf(m1, s[j + 1]); }
+  const float m = fmaxf(m0, m1);
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) { p[j] = __expf(s[j] - m); p[j + 1] = __expf(s[j + 1] - m); s0 += p[j]; s1 += p[j + 1]; }
+  const float inv = 1.0f / (s0 + s1);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float a = p[j] * inv;
+    p[j] = reverse ? (1.0f - a) * (1.0f / float(kL - 1)) : a;
+  }
+}
+template <int DV>
+__device__ __forceinline__ void ln_stats_bw(const BwCtx& c, uint32_t col, float& mean, float& rstd) {
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 1
+  for (int c0 = 0; c0 < DV; c0 += 16) {
+    float x[16];
+    ld16f(c.tmem + c.lane_base + col + c0, x);
+#pragma unroll
+    for (int e = 0; e < 16; e += 2) { s0 += x[e]; s1 += x[e + 1]; q0 = fmaf(x[e], x[e], q0); q1 = fmaf(x[e + 1], x[e + 1], q1); }
+  }
+  mean = (s0 + s1) * (1.0f / float(DV));
+  const float var = fmaxf((q0 + q1) * (1.0f / float(DV)) - mean * mean, 0.f);
+  rstd = rsqrtf(var + kLnEps);
+}
+
+// flush one persistent M=128 accumulator: lane = m.  dst(m, n) gives the address; columns split by warpgroup.
+template <class F>
+__device__ __forceinline__ void flush_acc(const BwCtx& c, uint32_t col, int ncols, int m_valid, F dst) {
+  const int m = c.rp;
+#pragma unroll 1
+  for (int n0 = 16 * c.w; n0 < ncols; n0 += 32) {
+    float v[16];
+    ld16f(c.tmem + c.lane_base + col + n0, v);
+    if (m < m_valid) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        float* p = dst(m, n0 + e);
+        if (p) atomicAdd(p, v[e]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// cross-attention backward, one direction per blockIdx.y
+// ---------------------------------------------------------------------------------------------------------------
+struct CaBwdDir {
+  const void* blobs;              // bz | bv | bc
+  const float* ln_g; const float* ln_b;
+  float* gm;                      // [96][128] fp32: dM_ext^T (row n = k', column m = k; m = 96 holds du)
+  float* g_wv; float* g_bv;       // [48][96], [48]
+  float* g_ln_g; float* g_ln_b;   // [48]
+  float* g_wf;                    // classifier rows of this source: &dWf[0][off], row stride D
+  void* dxq_img; void* dxkv_img;  // [tiles][kSaTileBytes] out
+};
+struct CaBwdArgs {
+  CaBwdDir dir[2];
+  const void* t_tiles; const void* i_tiles;
+  const float* dlogits;           // [B][4]
+  int D;                          // concat width (row stride of dWf)
+  int batch, reverse;
+};
+struct CaBwdSmem {
+  static constexpr uint32_t XQ = 0;                                  // [128 x 112]
+  static constexpr uint32_t XKV = XQ + op_bytes(112);
+  static constexpr uint32_t Z = XKV + op_bytes(112);                 // [128 x 96]
+  static constexpr uint32_t V = Z + op_bytes(96);                    // [128 x 48]; later dV
+  static constexpr uint32_t OUT = V + op_bytes(48);                  // [128 x 48]
+  static constexpr uint32_t DC = OUT + op_bytes(48);                 // [128 x 48]
+  static constexpr uint32_t DYX = DC + op_bytes(48);                 // [128 x 96]: dy*xhat | dy; later dZ
+  static constexpr uint32_t DLS = DYX + op_bytes(96);                // DL [128 x 64]; later dS (2 x [64 x 64])
+  static constexpr uint32_t P = DLS + 2 * kPHalf;                    // 2 x [64 x 64]
+  static constexpr uint32_t ONES = P + 2 * kPHalf;                   // [16][128] ones
+  static constexpr uint32_t W = al128(ONES + 4096);
+  static constexpr uint32_t LN = W + CaCfg::W_BYTES;                 // gamma, beta [48] fp32
+  static constexpr uint32_t BAR = al128(LN + 2 * 48 * 4);
+  static constexpr uint32_t BYTES = BAR + 64;
+  static_assert(2 * kPHalf >= op_bytes(64), "dS aliases DL");
+  static_assert(BYTES <= 232448, "CA backward does not fit shared memory");
+};
+struct CaBwdCols {   // TMEM columns
+  static constexpr uint32_t Z = 0, V = 96, DOUT = 144, S = 0, C = 64, DP = 0, DV = 64, DZ = 112, DXQ = 0, DXKV = 96;
+  static constexpr uint32_t G_M = 256, G_WV = 352, G_WF = 400, G_LN = 464;
+};
+
+__global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs a) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  using S = CaBwdSmem; using T = CaBwdCols; using C = CaCfg;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::BAR);     // [0] weights, [1] MMA, [2] tile load
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  float* ln_s = reinterpret_cast<float*>(sm + S::LN);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int d = blockIdx.y;
+  const CaBwdDir& D = a.dir[d];
+  const bool reverse = a.reverse != 0;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(&bars[0], C::W_BYTES);
+    bulk_g2s(sm + S::W, D.blobs, C::W_BYTES, &bars[0]);
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  for (int i = tid; i < 48; i += kCtaThreads) { ln_s[i] = D.ln_g[i]; ln_s[48 + i] = D.ln_b[i]; }
+  for (uint32_t i = tid; i < (2 * kPHalf + 4096) / 16; i += kCtaThreads) {     // P zeros, then the ones operand
+    const uint32_t off = i * 16;
+    reinterpret_cast<uint4*>(sm + S::P)[i] =
+        off < 2 * kPHalf ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  }
+  if (tid < 128) { write_bias_columns(sm + S::XQ, C::DIN / 8, tid); write_bias_columns(sm + S::XKV, C::DIN / 8, tid); }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  mbar_wait(&bars[0], 0);
+  BwCtx c = make_bwctx(tmem, &bars[1]);
+  uint32_t ph_ld = 0;
+  uint8_t *xq = sm + S::XQ, *xkv = sm + S::XKV, *zb = sm + S::Z, *vb = sm + S::V, *ob = sm + S::OUT, *dcb = sm + S::DC,
+          *dyx = sm + S::DYX, *dls = sm + S::DLS, *pb = sm + S::P, *ones = sm + S::ONES, *wsm = sm + S::W;
+  const uint8_t* bz = wsm; const uint8_t* bv = wsm + C::BZ_BYTES; const uint8_t* bc = wsm + C::BZ_BYTES + C::BV_BYTES;
+  const int tiles = (a.batch + 7) / 8;
+  bool first = true;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int b0 = tile * 8;
+    // ---- P0: block inputs (SA images) by TMA; DL from dlogits ---------------------------------------------------
+    if (tid == 0) {
+      const uint8_t* qsrc = static_cast<const uint8_t*>(d == 0 ? a.t_tiles : a.i_tiles) + size_t(tile) * kSaTileBytes;
+      const uint8_t* ksrc = static_cast<const uint8_t*>(d == 0 ? a.i_tiles : a.t_tiles) + size_t(tile) * kSaTileBytes;
+      mbar_arrive_expect_tx(&bars[2], 2 * kSaTileBytes);
+      bulk_g2s(xq, qsrc, kSaTileBytes, &bars[2]);
+      bulk_g2s(xkv, ksrc, kSaTileBytes, &bars[2]);
+    }
+    stage_dl(c, dls, a.dlogits, b0, a.batch);
+    mbar_wait(&bars[2], ph_ld); ph_ld ^= 1;
+    cta_sync_for_mma();
+    // ---- P1: Z, V (M=128) and dOut = DL Wf_src^T (two M=64 halves, s-mapping like C) ----------------------------
+    if (tid == 0) {
+      mma_steps(tmem + T::Z, make_smem_desc(smem_u32(xq), kCS, kRS), 2 * kCS, make_smem_desc(smem_u32(bz), C::BZ_LBO, 128),
+                2 * C::BZ_LBO, make_idesc_bf16(128, C::DIN, 0, 0), C::KE / 16, false);
+      mma_steps(tmem + T::V, make_smem_desc(smem_u32(xkv), kCS, kRS), 2 * kCS, make_smem_desc(smem_u32(bv), C::BV_LBO, 128),
+                2 * C::BV_LBO, make_idesc_bf16(128, C::DV, 0, 0), C::KE / 16, false);
+      for (int h = 0; h < 2; ++h)
+        mma_steps(tmem + (uint32_t(16 * h) << 16) + T::DOUT, make_smem_desc(smem_u32(dls + h * 8 * kRS), kCS, kRS), 2 * kCS,
+                  make_smem_desc(smem_u32(bc), 128, C::BC_LBO), 2 * 128, make_idesc_bf16(64, C::DV, 0, 1), kNCls / 16, false);
+      umma_commit(c.bar);
+    }
+    cta_wait_mma(c);
+    // ---- P2: Z, V -> operands (columns split) ---------------------------------------------------------------------
+    acc_cols_to_operand(c, T::Z, 48 * c.w, 48 * c.w + 48, zb, c.rp);
+    if (c.w == 0) acc_cols_to_operand(c, T::V, 0, 32, vb, c.rp); else acc_cols_to_operand(c, T::V, 32, 48, vb, c.rp);
+    cta_sync_for_mma();
+    // ---- P3: scores ----------------------------------------------------------------------------------------------------
+    if (tid == 0) {
+      for (int h = 0; h < 2; ++h)
+        mma_steps(tmem + (uint32_t(16 * h) << 16) + T::S, make_smem_desc(smem_u32(zb + h * 8 * kRS), kCS, kRS), 2 * kCS,
+                  make_smem_desc(smem_u32(xkv + h * 8 * kRS), kCS, kRS), 2 * kCS, make_idesc_bf16(64, 64, 0, 0), C::DIN / 16, false);
+      umma_commit(c.bar);
+    }
+    cta_wait_mma(c);
+    float p[16];
+    softmax16_bw(c, T::S, reverse, p);
+    store_half_row_split(c, pb, p, false);
+    cta_sync_for_mma();
+    // ---- P5: context ---------------------------------------------------------------------------------------------------
+    if (tid == 0) {
+      for (int h = 0; h < 2; ++h)
+        mma_steps(tmem + (uint32_t(16 * h) << 16) + T::C, make_smem_desc(smem_u32(pb + h * kPHalf), kPCS, kRS), 2 * kPCS,
+                  make_smem_desc(smem_u32(vb + h * 8 * kRS), kRS, kCS), 2 * kRS, make_idesc_bf16(64, C::DV, 0, 1), 4, false);
+      umma_commit(c.bar);
+    }
+    cta_wait_mma(c);
+    // ---- P6: LayerNorm / ReLU backward on my row --------------------------------------------------------------------
+    {
+      float mean, rstd;
+      ln_stats_bw<C::DV>(c, T::C, mean, rstd);
+      float m1a = 0.f, m1b = 0.f, m2a = 0.f, m2b = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < C::DV; c0 += 16) {
+        float x[16], g[16], o[16], t1[16], t2[16];
+        ld16f(c.tmem + c.lane_base + T::C + c0, x);
+        ld16f(c.tmem + c.lane_base + T::DOUT + c0, g);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float gam = ln_s[c0 + e];
+          const float xh = (x[e] - mean) * rstd;
+          const float y = fmaf(xh, gam, ln_s[48 + c0 + e]);
+          const float dy = y > 0.f ? g[e] : 0.f;
+          const float dxh = dy * gam;
+          if (e & 1) { m1b += dxh; m2b = fmaf(dxh, xh, m2b); } else { m1a += dxh; m2a = fmaf(dxh, xh, m2a); }
+          o[e] = fmaxf(y, 0.f); t1[e] = dy * xh; t2[e] = dy;
+        }
+        if (c.w == 0) st_chunks16(ob, c.rs, c0, o);
+        else { st_chunks16(dyx, c.rs, c0, t1); st_chunks16(dyx, c.rs, C::DV + c0, t2); }
+      }
+      if (c.w == 0) {
+        const float m1 = (m1a + m1b) * (1.0f / float(C::DV)), m2 = (m2a + m2b) * (1.0f / float(C::DV));
+#pragma unroll 1
+        for (int c0 = 0; c0 < C::DV; c0 += 16) {
+          float x[16], g[16], o[16];
+          ld16f(c.tmem + c.lane_base + T::C + c0, x);
+          ld16f(c.tmem + c.lane_base + T::DOUT + c0, g);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float gam = ln_s[c0 + e];
+            const float xh = (x[e] - mean) * rstd;
+            const float y = fmaf(xh, gam, ln_s[48 + c0 + e]);
+            const float dxh = y > 0.f ? g[e] * gam : 0.f;
+            o[e] = rstd * (dxh - m1 - xh * m2);
+          }
+          st_chunks16(dcb, c.rs, c0, o);
+        }
+      }
+    }
+    cta_sync_for_mma();
+    // ---- P7: dP; classifier-weight and LayerNorm-affine gradients into their persistent accumulators ----------
+    if (tid == 0) {
+      for (int h = 0; h < 2; ++h)
+        mma_steps(tmem + (uint32_t(16 * h) << 16) + T::DP, make_smem_desc(smem_u32(dcb + h * 8 * kRS), kCS, kRS), 2 * kCS,
+                  make_smem_desc(smem_u32(vb + h * 8 * kRS), kCS, kRS), 2 * kCS, make_idesc_bf16(64, 64, 0, 0), C::DV / 16, false);
+      mma_steps(tmem + T::G_WF, make_smem_desc(smem_u32(ob), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(dls), kRS, kCS), 2 * kRS,
+                make_idesc_bf16(64, kNCls, 1, 1), 8, !first);
+      mma_steps(tmem + T::G_LN, make_smem_desc(smem_u32(dyx), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(ones), 256, 128), 512,
+                make_idesc_bf16(128, 16, 1, 0), 8, !first);
+      umma_commit(c.bar);
+    }
+    cta_wait_mma(c);
+    // ---- P8: softmax backward -> dS (reuses DL's bytes: rewrite every column group of my row) ------------------
+    {
+      float ds[16];
+      softmax_bwd16(c, T::DP, reverse, p, ds);
+      store_half_row_split(c, dls, ds, true);
+    }
+    cta_sync_for_mma();
+    // ---- P9: dV = P^T dC, dZ = dS Xkv ----------------------------------------------------------------------------------
+    if (tid == 0) {
+      for (int h = 0; h < 2; ++h) {
+        mma_steps(tmem + (uint32_t(16 * h) << 16) + T::DV, make_smem_desc(smem_u32(pb + h * kPHalf), kRS, kPCS), 2 * kRS,
+                  make_smem_desc(smem_u32(dcb + h * 8 * kRS), kRS, kCS), 2 * kRS, make_idesc_bf16(64, C::DV, 1, 1), 4, false);
+        mma_steps(tmem + (uint32_t(16 * h) << 16) + T::DZ, make_smem_desc(smem_u32(dls + h * kPHalf), kPCS, kRS), 2 * kPCS,
+                  make_smem_desc(smem_u32(xkv + h * 8 * kRS), kRS, kCS), 2 * kRS, make_idesc_bf16(64, C::DIN, 0, 1), 4, false);
+      }
+      umma_commit(c.bar);
+    }
+    cta_wait_mma(c);
+    // ---- P10: dV, dZ -> operands (dV over V, dZ over dy*xhat | dy) ------------------------------------------------
+    if (c.w == 0) acc_cols_to_operand(c, T::DZ, 0, 80, dyx, c.rs);
+    else { acc_cols_to_operand(c, T::DZ, 80, 96, dyx, c.rs); acc_cols_to_operand(c, T::DV, 0, 48, vb, c.rs); }
+    cta_sync_for_mma();
+    // ---- P11: parameter gradients (persistent) and the gradients of the block inputs -----------------------------
+    if (tid == 0) {
+      mma_steps(tmem + T::G_M, make_smem_desc(smem_u32(xq), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(dyx), kRS, kCS), 2 * kRS,
+                make_idesc_bf16(128, C::DIN, 1, 1), 8, !first);
+      mma_steps(tmem + T::G_WV, make_smem_desc(smem_u32(xkv), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(vb), kRS, kCS), 2 * kRS,
+                make_idesc_bf16(128, C::DV, 1, 1), 8, !first);
+      // dXq = dZ M^T  (B: the Z blob read along its other axis)
+      mma_steps(tmem + T::DXQ, make_smem_desc(smem_u32(dyx), kCS, kRS), 2 * kCS, make_smem_desc(smem_u32(bz), 128, C::BZ_LBO), 2 * 128,
+                make_idesc_bf16(128, C::DIN, 0, 1), C::DIN / 16, false);
+      // dXkv = dS^T Z + dV Wv
+      for (int h = 0; h < 2; ++h) {
+        mma_steps(tmem + (uint32_t(16 * h) << 16) + T::DXKV, make_smem_desc(smem_u32(dls + h * kPHalf), kRS, kPCS), 2 * kRS,
+                  make_smem_desc(smem_u32(zb + h * 8 * kRS), kRS, kCS), 2 * kRS, make_idesc_bf16(64, C::DIN, 1, 1), 4, false);
+        mma_steps(tmem + (uint32_t(16 * h) << 16) + T::DXKV, make_smem_desc(smem_u32(vb + h * 8 * kRS), kCS, kRS), 2 * kCS,
+                  make_smem_desc(smem_u32(bv), 128, C::BV_LBO), 2 * 128, make_idesc_bf16(64, C::DIN, 0, 1), C::DV / 16, true);
+      }
+      umma_commit(c.bar);
+    }
+    cta_wait_mma(c);
+    // ---- P12: input gradients -> bf16 images for the SA backward ---------------------------------------------------
+    {
+      uint8_t* gq = static_cast<uint8_t*>(D.dxq_img) + size_t(tile) * kSaTileBytes;
+      uint8_t* gk = static_cast<uint8_t*>(D.dxkv_img) + size_t(tile) * kSaTileBytes;
+      // (global images use the same [column group][row] geometry as the shared-memory operands)
+      acc_cols_to_operand(c, T::DXQ, 48 * c.w, 48 * c.w + 48, gq, c.rp);
+      acc_cols_to_operand(c, T::DXKV, 48 * c.w, 48 * c.w + 48, gk, c.rs);
+    }
+    first = false;
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+  }
+  // ---- flush the persistent accumulators ---------------------------------------------------------------------------
+  if (!first) {
+    flush_acc(c, T::G_M, C::DIN, C::DIN + 1, [&](int m, int n) { return D.gm + size_t(n) * 128 + m; });
+    flush_acc(c, T::G_WV, C::DV, C::DIN + 1,
+              [&](int m, int n) { return m < C::DIN ? D.g_wv + size_t(n) * C::DIN + m : D.g_bv + n; });
+    // dWf^T: an M=64 accumulator keeps row m = 16q + lane in the lower half of each warp's lanes
+    {
+      const int j = 16 * c.q + c.lane;
+#pragma unroll 1
+      for (int n0 = 16 * c.w; n0 < kNCls; n0 += 32) {
+        float v[16];
+        ld16f(c.tmem + c.lane_base + T::G_WF + n0, v);
+        if (c.lane < 16 && j < C::DV) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int n = n0 + e, rp = n >> 2, cls = n & 3;
+            atomicAdd(D.g_wf + size_t(cls) * a.D + rp * C::DV + j, v[e]);
+          }
+        }
+      }
+    }
+    if (c.w == 0) {
+      float v[16];
+      ld16f(c.tmem + c.lane_base + T::G_LN, v);
+      if (c.rp < C::DV) atomicAdd(D.g_ln_g + c.rp, v[0]);
+      else if (c.rp < 2 * C::DV) atomicAdd(D.g_ln_b + (c.rp - C::DV), v[0]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// self-attention backward (features frozen: parameter gradients only), one modality per launch
+// ---------------------------------------------------------------------------------------------------------------
+struct SaBwdArgs {
+  const float* feat;              // [B][16*DIN]
+  const void* blobs;              // bz | bv | bc
+  const float* ln_g; const float* ln_b;
+  const void* dout_a; const void* dout_b;   // dOut = a + b (images written by ca_bwd_kernel)
+  const float* dlogits;           // [B][4] or null (classifier does not see the features)
+  float* gm;                      // [DIN][128]
+  float* g_wv; float* g_bv; float* g_ln_g; float* g_ln_b;
+  float* g_wf; int D;             // classifier rows of the feature source
+  int batch;
+};
+template <int DIN_>
+struct SaBwdSmem {
+  using C = SaCfg<DIN_>;
+  static constexpr uint32_t X = 0;                                   // [128 x (DIN+16)]
+  static constexpr uint32_t ZP = X + op_bytes(C::KE);                // Z [128 x DIN]; later P
+  static constexpr uint32_t ZP_BYTES = op_bytes(DIN_) > 2 * kPHalf ? op_bytes(DIN_) : 2 * kPHalf;
+  static constexpr uint32_t V = ZP + ZP_BYTES;                       // [128 x 96]; later dV
+  static constexpr uint32_t DC = V + op_bytes(96);                   // [128 x 96]
+  static constexpr uint32_t DYX = DC + op_bytes(96);                 // [128 x 192]: dy*xhat | dy; later dZ [128 x DIN]
+  static constexpr uint32_t DLS = DYX + op_bytes(192);               // DL; later dS
+  static constexpr uint32_t ONES = DLS + 2 * kPHalf;
+  static constexpr uint32_t W = al128(ONES + 4096);
+  static constexpr uint32_t LN = W + C::W_BYTES;
+  static constexpr uint32_t BAR = al128(LN + 2 * 96 * 4);
+  static constexpr uint32_t BYTES = BAR + 64;
+  static_assert(BYTES <= 232448, "SA backward does not fit shared memory");
+};
+template <int DIN_>
+struct SaBwdCols {
+  static constexpr uint32_t Z = 0, V = DIN_, S = 0, C = 64, DP = 0, DV = 0, DZ = 96;   // working: [0, 176)
+  static constexpr uint32_t G_M = 176, G_WV = G_M + DIN_, G_WF = G_WV + 96, G_LN = G_WF + 64;  // G_LN: 2 x 16 columns
+  static_assert(G_LN + 32 <= 512, "TMEM budget");
+};
+
+template <int DIN_>
+__global__ void __launch_bounds__(kCtaThreads, 1) sa_bwd_kernel(const SaBwdArgs a) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  using S = SaBwdSmem<DIN_>; using T = SaBwdCols<DIN_>; using C = SaCfg<DIN_>;
+  constexpr int DIN = DIN_, DV = C::DV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::BAR);     // [0] weights, [1] MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  float* ln_s = reinterpret_cast<float*>(sm + S::LN);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(&bars[0], C::W_BYTES);
+    bulk_g2s(sm + S::W, a.blobs, C::W_BYTES, &bars[0]);
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  for (int i = tid; i < DV; i += kCtaThreads) { ln_s[i] = a.ln_g[i]; ln_s[DV + i] = a.ln_b[i]; }
+  for (uint32_t i = tid; i < 4096 / 16; i += kCtaThreads)
+    reinterpret_cast<uint4*>(sm + S::ONES)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  mbar_wait(&bars[0], 0);
+  BwCtx c = make_bwctx(tmem, &bars[1]);
+  uint8_t *xb = sm + S::X, *zp = sm + S::ZP, *vb = sm + S::V, *dcb = sm + S::DC, *dyx = sm + S::DYX, *dls = sm + S::DLS,
+          *ones = sm + S::ONES, *wsm = sm + S::W;
+  const uint8_t* bz = wsm; const uint8_t* bv = wsm + C::BZ_BYTES; const uint8_t* bc = wsm + C::BZ_BYTES + C::BV_BYTES;
+  (void)bc;
+  const bool cls = a.dlogits != nullptr;
+  const int tiles = (a.batch + 7) / 8;
+  bool first = true;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int b0 = tile * 8;
+    // ---- P0: features -> normalised bf16 operand (8 warps, one sample each); DL ------------------------------------
+    {
+      constexpr int KCS = DIN / 8, ITEMS = kL * KCS, PER = (ITEMS + 31) / 32;
+      const int g = warp, b = b0 + g;
+      const float* base = a.feat + size_t(b) * (kL * DIN);
+      float v[PER][8];
+      float ss0 = 0.f, ss1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int it = c.lane + 32 * k;
+        float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+        if (b < a.batch && (ITEMS % 32 == 0 || it < ITEMS)) {
+          lo = __ldg(reinterpret_cast<const float4*>(base + it * 8));
+          hi = __ldg(reinterpret_cast<const float4*>(base + it * 8 + 4));
+        }
+        v[k][0] = lo.x; v[k][1] = lo.y; v[k][2] = lo.z; v[k][3] = lo.w; v[k][4] = hi.x; v[k][5] = hi.y; v[k][6] = hi.z; v[k][7] = hi.w;
+      }
+#pragma unroll
+      for (int k = 0; k < PER; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) { ss0 = fmaf(v[k][e], v[k][e], ss0); ss1 = fmaf(v[k][e + 1], v[k][e + 1], ss1); }
+      const float nrm = sqrtf(warp_sum(ss0 + ss1));
+      const float inv = b < a.batch ? 1.0f / nrm : 0.f;
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int it = c.lane + 32 * k;
+        if (ITEMS % 32 != 0 && it >= ITEMS) continue;
+        const int row = it / KCS, kc = it - row * KCS;
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = v[k][e] * inv;
+        *reinterpret_cast<uint4*>(xb + uint32_t(kc) * kCS + row_off(g * kL + row)) = pack_bf16x8(o);
+      }
+      if (tid < 128) write_bias_columns(xb, KCS, tid);
+      if (cls) stage_dl(c, dls, a.dlogits, b0, a.batch);
+    }
+    cta_sync_for_mma();
+    // ---- P1: Z, V; classifier-weight gradient of the feature source dWf^T += X^T DL --------------------------------
+    if (tid == 0) {
+      const uint64_t ax = make_smem_desc(smem_u32(xb), kCS, kRS);
+      mma_steps(tmem + T::Z, ax, 2 * kCS, make_smem_desc(smem_u32(bz), C::BZ_LBO, 128), 2 * C::BZ_LBO,
+                make_idesc_bf16(128, DIN, 0, 0), C::KE / 16, false);
+      mma_steps(tmem + T::V, ax, 2 * kCS, make_smem_desc(smem_u32(bv), C::BV_LBO, 128), 2 * C::BV_LBO,
+                make_idesc_bf16(128, DV, 0, 0), C::KE / 16, false);
+      if (cls)
+        mma_steps(tmem + T::G_WF, make_smem_desc(smem_u32(xb), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(dls), kRS, kCS), 2 * kRS,
+                  make_idesc_bf16(128, kNCls, 1, 1), 8, !first);
+      umma_commit(c.bar);
+    }
+    cta_wait_mma(c);
+    {
+      constexpr int ZH = (DIN / 16 + 1) / 2 * 16;     // split Z's columns in 16-column steps
+      if (c.w == 0) { acc_cols_to_operand(c, T::Z, 0, ZH, zp, c.rp); acc_cols_to_operand(c, T::V, 0, 32, vb, c.rp); }
+      else { acc_cols_to_operand(c, T::Z, ZH, DIN, zp, c.rp); acc_cols_to_operand(c, T::V, 32, 96, vb, c.rp); }
+    }
+    cta_sync_for_mma();
+    if (tid == 0) {
+      for (int h = 0; h < 2; ++h)
+        mma_steps(tmem + (uint32_t(16 * h) << 16) + T::S, make_smem_desc(smem_u32(zp + h * 8 * kRS), kCS, kRS), 2 * kCS,
+                  make_smem_desc(smem_u32(xb + h * 8 * kRS), kCS, kRS), 2 * kCS, make_idesc_bf16(64, 64, 0, 0), DIN / 16, false);
+      umma_commit(c.bar);
+    }
+    cta_wait_mma(c);
+    float p[16];
+    softmax16_bw(c, T::S, false, p);
+    store_half_row_split(c, zp, p, true);        // P reuses Z's bytes (the frozen-feature backward needs Z no more)
+    cta_sync_for_mma();
+    if (tid == 0) {
+      for (int h = 0; h < 2; ++h)
+        mma_steps(tmem + (uint32_t(16 * h) << 16) + T::C, make_smem_desc(smem_u32(zp + h * kPHalf), kPCS, kRS), 2 * kPCS,
+                  make_smem_desc(smem_u32(vb + h * 8 * kRS), kRS, kCS), 2 * kRS, make_idesc_bf16(64, DV, 0, 1), 4, false);
+      umma_commit(c.bar);
+    }
+    cta_wait_mma(c);
+    // ---- LayerNorm / ReLU backward; dOut = sum of the two images written by the CA backward ----------------------
+    {
+      float mean, rstd;
+      ln_stats_bw<DV>(c, T::C, mean, rstd);
+      const uint8_t* ga = static_cast<const uint8_t*>(a.dout_a) + size_t(tile) * kSaTileBytes + row_off(c.rs);
+      const uint8_t* gb = static_cast<const uint8_t*>(a.dout_b) + size_t(tile) * kSaTileBytes + row_off(c.rs);
+      float m1a = 0.f, m1b = 0.f, m2a = 0.f, m2b = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < DV; c0 += 16) {
+        float x[16], g[16], t1[16], t2[16];
+        {
+          float f0[8], f1[8], f2[8], f3[8];
+          unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(ga + uint32_t(c0 >> 3) * kCS)), f0);
+          unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(gb + uint32_t(c0 >> 3) * kCS)), f1);
+          unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(ga + uint32_t((c0 >> 3) + 1) * kCS)), f2);
+          unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(gb + uint32_t((c0 >> 3) + 1) * kCS)), f3);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { g[e] = f0[e] + f1[e]; g[8 + e] = f2[e] + f3[e]; }
+        }
+        ld16f(c.tmem + c.lane_base + T::C + c0, x);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float gam = ln_s[c0 + e];
+          const float xh = (x[e] - mean) * rstd;
+          const float y = fmaf(xh, gam, ln_s[DV + c0 + e]);
+          const float dy = y > 0.f ? g[e] : 0.f;
+          const float dxh = dy * gam;
+          if (e & 1) { m1b += dxh; m2b = fmaf(dxh, xh, m2b); } else { m1a += dxh; m2a = fmaf(dxh, xh, m2a); }
+          t1[e] = dy * xh; t2[e] = dy;
+        }
+        if (c.w == 1) { st_chunks16(dyx, c.rs, c0, t1); st_chunks16(dyx, c.rs, DV + c0, t2); }
+      }
+      if (c.w == 0) {
+        const float m1 = (m1a + m1b) * (1.0f / float(DV)), m2 = (m2a + m2b) * (1.0f / float(DV));
+#pragma unroll 1
+        for (int c0 = 0; c0 < DV; c0 += 16) {
+          float x[16], g[16], o[16];
+          {
+            float f0[8], f1[8], f2[8], f3[8];
+            unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(ga + uint32_t(c0 >> 3) * kCS)), f0);
+            unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(gb + uint32_t(c0 >> 3) * kCS)), f1);
+            unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(ga + uint32_t((c0 >> 3) + 1) * kCS)), f2);
+            unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(gb + uint32_t((c0 >> 3) + 1) * kCS)), f3);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { g[e] = f0[e] + f1[e]; g[8 + e] = f2[e] + f3[e]; }
+          }
+          ld16f(c.tmem + c.lane_base + T::C + c0, x);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float gam = ln_s[c0 + e];
+            const float xh = (x[e] - mean) * rstd;
+            const float y = fmaf(xh, gam, ln_s[DV + c0 + e]);
+            const float dxh = y > 0.f ? g[e] * gam : 0.f;
+            o[e] = rstd * (dxh - m1 - xh * m2);
+          }
+          st_chunks16(dcb, c.rs, c0, o);
+        }
+      }
+    }
+    cta_sync_for_mma();
+    // ---- dP; LayerNorm-affine gradients (M = 192 = two M=128 MMAs over the [dy*xhat | dy] operand) ----------------
+    if (tid == 0) {
+      for (int h = 0; h < 2; ++h)
+        mma_steps(tmem + (uint32_t(16 * h) << 16) + T::DP, make_smem_desc(smem_u32(dcb + h * 8 * kRS), kCS, kRS), 2 * kCS,
+                  make_smem_desc(smem_u32(vb + h * 8 * kRS), kCS, kRS), 2 * kCS, make_idesc_bf16(64, 64, 0, 0), DV / 16, false);
+      for (int mt = 0; mt < 2; ++mt)
+        mma_steps(tmem + T::G_LN + 16 * mt, make_smem_desc(smem_u32(dyx + mt * 16 * kCS), kRS, kCS), 2 * kRS,
+                  make_smem_desc(smem_u32(ones), 256, 128), 512, make_idesc_bf16(128, 16, 1, 0), 8, !first);
+      umma_commit(c.bar);
+    }
+    cta_wait_mma(c);
+    {
+      float ds[16];
+      softmax_bwd16(c, T::DP, false, p, ds);
+      store_half_row_split(c, dls, ds, true);
+    }
+    cta_sync_for_mma();
+    if (tid == 0) {
+      for (int h = 0; h < 2; ++h) {
+        mma_steps(tmem + (uint32_t(16 * h) << 16) + T::DV, make_smem_desc(smem_u32(zp + h * kPHalf), kRS, kPCS), 2 * kRS,
+                  make_smem_desc(smem_u32(dcb + h * 8 * kRS), kRS, kCS), 2 * kRS, make_idesc_bf16(64, DV, 1, 1), 4, false);
+        mma_steps(tmem + (uint32_t(16 * h) << 16) + T::DZ, make_smem_desc(smem_u32(dls + h * kPHalf), kPCS, kRS), 2 * kPCS,
+                  make_smem_desc(smem_u32(xb + h * 8 * kRS), kRS, kCS), 2 * kRS, make_idesc_bf16(64, DIN, 0, 1), 4, false);
+      }
+      umma_commit(c.bar);
+    }
+    cta_wait_mma(c);
+    if (c.w == 0) { acc_cols_to_operand(c, T::DZ, 0, DIN, dyx, c.rs); acc_cols_to_operand(c, T::DV, 0, 16, vb, c.rs); }
+    else acc_cols_to_operand(c, T::DV, 16, 96, vb, c.rs);
+    cta_sync_for_mma();
+    if (tid == 0) {
+      mma_steps(tmem + T::G_M, make_smem_desc(smem_u32(xb), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(dyx), kRS, kCS), 2 * kRS,
+                make_idesc_bf16(128, DIN, 1, 1), 8, !first);
+      mma_steps(tmem + T::G_WV, make_smem_desc(smem_u32(xb), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(vb), kRS, kCS), 2 * kRS,
+                make_idesc_bf16(128, DV, 1, 1), 8, !first);
+      umma_commit(c.bar);
+    }
+    cta_wait_mma(c);
+    first = false;
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+  }
+  if (!first) {
+    flush_acc(c, T::G_M, DIN, DIN + 1, [&](int m, int n) { return a.gm + size_t(n) * 128 + m; });
+    flush_acc(c, T::G_WV, DV, DIN + 1, [&](int m, int n) { return m < DIN ? a.g_wv + size_t(n) * DIN + m : a.g_bv + n; });
+    if (cls)
+      flush_acc(c, T::G_WF, kNCls, DIN, [&](int m, int n) { return a.g_wf + size_t(n & 3) * a.D + (n >> 2) * DIN + m; });
+    {
+      float v[16];
+      ld16f(c.tmem + c.lane_base + T::G_LN + 16 * c.w, v);
+      const int col = 128 * c.w + c.rp;             // row of the [dy*xhat | dy]^T 1 product
+      if (col < DV) atomicAdd(a.g_ln_g + col, v[0]);
+      else if (col < 2 * DV) atomicAdd(a.g_ln_b + (col - DV), v[0]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dW_query, dW_key, db_query from dM, du (chain rule through M = Wq^T Wk / sqrt(d), u = Wk^T bq / sqrt(d))
+// ---------------------------------------------------------------------------------------------------------------
+struct FinBlock {
+  const float* gm;     // [DIN][128]: gm[k'][k] = dM[k][k'], gm[k'][DIN] = du[k']
+  const float* wq; const float* bq; const float* wk;
+  float* g_wq; float* g_bq; float* g_wk;
+  int din, dkq;
+};
+struct FinArgs { FinBlock blk[4]; int nblk; };
+
+__global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
+  // blockIdx.y = block; consecutive threads own consecutive k (coalesced gm rows, broadcast weight reads)
+  const FinBlock& B = a.blk[blockIdx.y];
+  const float s = rsqrtf(float(B.dkq));
+  const int nw = B.dkq * B.din, din = B.din;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 2 * nw + B.dkq; t += gridDim.x * blockDim.x) {
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    if (t < nw) {              // dWq[n][k] += s sum_k' dM[k][k'] Wk[n][k']
+      const int n = t / din, k = t - n * din;
+      const float* g = B.gm + k;
+      const float* w = B.wk + size_t(n) * din;
+#pragma unroll 4
+      for (int kp = 0; kp < din; kp += 4) {
+        acc0 = fmaf(__ldg(g + size_t(kp) * 128), __ldg(w + kp), acc0);
+        acc1 = fmaf(__ldg(g + size_t(kp + 1) * 128), __ldg(w + kp + 1), acc1);
+        acc2 = fmaf(__ldg(g + size_t(kp + 2) * 128), __ldg(w + kp + 2), acc2);
+        acc3 = fmaf(__ldg(g + size_t(kp + 3) * 128), __ldg(w + kp + 3), acc3);
+      }
+      atomicAdd(B.g_wq + t, (acc0 + acc1 + acc2 + acc3) * s);
+    } else if (t < 2 * nw) {   // dWk[n][k'] += s (sum_k Wq[n][k] dM[k][k'] + bq[n] du[k'])
+      const int u = t - nw, n = u / din, kp = u - n * din;
+      const float* g = B.gm + size_t(kp) * 128;
+      const float* w = B.wq + size_t(n) * din;
+      acc0 = __ldg(B.bq + n) * __ldg(g + din);
+#pragma unroll 4
+      for (int k = 0; k < din; k += 4) {
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(g + k));
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + k));
+        acc0 = fmaf(gv.x, wv.x, acc0); acc1 = fmaf(gv.y, wv.y, acc1); acc2 = fmaf(gv.z, wv.z, acc2); acc3 = fmaf(gv.w, wv.w, acc3);
+      }
+      atomicAdd(B.g_wk + u, (acc0 + acc1 + acc2 + acc3) * s);
+    } else {                   // dbq[n] += s sum_k' du[k'] Wk[n][k']
+      const int n = t - 2 * nw;
+      for (int kp = 0; kp < din; ++kp) acc0 = fmaf(__ldg(B.gm + size_t(kp) * 128 + din), __ldg(B.wk + size_t(n) * din + kp), acc0);
+      atomicAdd(B.g_bq + n, acc0 * s);
+    }
+  }
+}
+
+}  // namespace htc
+}  // namespace mmrca

@@ -9,6 +9,8 @@ namespace tc {
 
 // mode bit 0: B is MN-major (source b[K][N]) instead of K-major (source b[N][K])
 // mode bit 1: A is MN-major (source a[K][128]) instead of K-major (source a[128][K])
+// mode bit 2: two M=64 MMAs (rows 0-63 and 64-127) instead of one M=128; the second accumulator sits 16 TMEM
+//             lanes up, i.e. a warp's lanes 0-15 hold rows 16q.. of the first half and lanes 16-31 rows 64+16q..
 // out[128][N] = A * B^T (logical A[128][K], B[N][K]).  N % 16 == 0, N <= 256, K % 16 == 0.
 __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(int mode, const float* __restrict__ a,
                                                               const float* __restrict__ b, float* __restrict__ out,
@@ -75,17 +77,26 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(int mode, const f
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t taddr = tmem_base;
+  const bool halves = mode & 4;
   if (tid == 0) {
-    const uint32_t idesc = make_idesc_bf16(M, N, a_mn ? 1 : 0, b_mn ? 1 : 0);
     const uint64_t ad = make_smem_desc(smem_u32(sa), a_lbo, a_sbo);
     const uint64_t bd = make_smem_desc(smem_u32(sb), b_lbo, b_sbo);
-    for (int ks = 0; ks < K / 16; ++ks)
-      umma_bf16(taddr, desc_advance(ad, ks * 2 * a_lbo), desc_advance(bd, ks * 2 * b_lbo), idesc, ks > 0);
+    if (!halves) {
+      const uint32_t idesc = make_idesc_bf16(M, N, a_mn ? 1 : 0, b_mn ? 1 : 0);
+      for (int ks = 0; ks < K / 16; ++ks)
+        umma_bf16(taddr, desc_advance(ad, ks * 2 * a_lbo), desc_advance(bd, ks * 2 * b_lbo), idesc, ks > 0);
+    } else {
+      const uint32_t idesc = make_idesc_bf16(64, N, a_mn ? 1 : 0, b_mn ? 1 : 0);
+      for (int h = 0; h < 2; ++h)     // 64 rows = 8 row groups (K-major) or 8 m-chunks (MN-major): 8 * a_sbo either way
+        for (int ks = 0; ks < K / 16; ++ks)
+          umma_bf16(taddr + (uint32_t(16 * h) << 16), desc_advance(ad, h * 8 * a_sbo + ks * 2 * a_lbo),
+                    desc_advance(bd, ks * 2 * b_lbo), idesc, ks > 0);
+    }
     umma_commit(&bar);
   }
   mbar_wait(&bar, 0);
   tc_fence_after_sync();
-  const int r = warp * 32 + lane;
+  const int r = halves ? 64 * (lane >> 4) + 16 * warp + (lane & 15) : warp * 32 + lane;
   for (int c0 = 0; c0 < N; c0 += 16) {
     float v[16];
     tmem_ld16(taddr + (uint32_t(warp * 32) << 16) + uint32_t(c0), v);

@@ -164,6 +164,8 @@ class _HeadFunction(torch.autograd.Function):
         if txt.shape[0] != B:
             raise ValueError("image and text feature batches differ")
         needs_bwd = any(ctx.needs_input_grad)
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            flags |= N.FLAG_FEATURE_GRADS      # fine-tune phase: the backward must return feature gradients
         desc = _desc(B, d_img, d_txt, n_classes, flags, compute)
         L = N.lib()
         ws = torch.empty(max(1, L.mmrca_head_workspace_bytes(C.byref(desc), 1 if needs_bwd else 0)),
@@ -257,7 +259,7 @@ class HeadTrainStep:
                  compute: int = N.COMPUTE_FP32, feature_grads: bool = False):
         self.params = [_check_dev(p.detach(), "head parameter") for p in params]
         dev = self.params[0].device
-        self.flags = make_flags(reverse, features_only, cross_attention_only)
+        self.flags = make_flags(reverse, features_only, cross_attention_only) | (N.FLAG_FEATURE_GRADS if feature_grads else 0)
         self.desc = _desc(batch, d_img, d_txt, n_classes, self.flags, compute)
         self.grads = FlatGrads(self.params)
         self.hp, self.hg = _head_struct(self.params), _head_struct(self.grads.views)

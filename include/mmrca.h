@@ -50,10 +50,15 @@ extern "C" {
 #define MMRCA_FLAG_REVERSE 1u              /* --reverse: (1-A)/(L-1) weights, :95-99 */
 #define MMRCA_FLAG_FEATURES_ONLY 2u        /* --features_only: concat = [img, txt], :694-699 */
 #define MMRCA_FLAG_CROSS_ATTENTION_ONLY 4u /* --cross_attention_only: concat = [T_I, I_T], :701-706 */
+#define MMRCA_FLAG_FEATURE_GRADS 256u      /* the backward will be asked for d_img_feat / d_txt_feat (fine-tune phase,
+                                              main_both.py:687-694): set it for the forward too */
 
 /* MmrcaHeadDesc.compute */
 #define MMRCA_COMPUTE_FP32 0 /* fp32 SIMT kernels: the 1e-4-relative contract */
-#define MMRCA_COMPUTE_BF16 1 /* bf16 tcgen05 tensor-core kernels, fp32 accumulate: the 2e-2-absolute contract */
+#define MMRCA_COMPUTE_BF16 1 /* bf16 tcgen05 tensor-core pipeline, fp32 accumulate: the 2e-2-absolute contract.
+                                Covers the reference's literal shapes (1280 / 768 features, 4 classes) with frozen
+                                features and no materialised dropout mask; other cases run the fp32 kernels. */
+#define MMRCA_COMPUTE_BF16_FUSED 2 /* alias of MMRCA_COMPUTE_BF16 (kept for ABI v1 callers) */
 
 /* mmrca_query() selectors */
 #define MMRCA_QUERY_ABI_VERSION 0
@@ -123,6 +128,12 @@ const char* mmrca_last_error(void);
  * (SA / CA outputs, feature norms) in the workspace; a backward for the same inputs must be
  * given the same, unmodified workspace. */
 size_t mmrca_head_workspace_bytes(const MmrcaHeadDesc* desc, int training);
+
+/* Test hook: byte offset of an intermediate inside the workspace (-1 if this desc has none).
+ * The SA "images" are the bf16 [tiles][12 column groups][128 rows][8] operand layout of the fused pipeline. */
+#define MMRCA_WS_TEXT_SA_IMAGE 0
+#define MMRCA_WS_IMAGE_SA_IMAGE 1
+long long mmrca_head_workspace_offset(const MmrcaHeadDesc* desc, int training, int what);
 
 /* MM_RCA.forward from the pooled features on (multimodal_model.py:661-728).
  *   img_feat [B, d_img], txt_feat [B, d_txt] fp32

@@ -7,7 +7,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5, 6, 7])
 @pytest.mark.parametrize("shape", [(176, 80), (64, 96), (112, 96), (256, 48), (96, 128), (16, 16)])
 def test_umma_selftest(native_lib, mode, shape):
     from garbage_classification_rca_b200 import _native as N
@@ -15,7 +15,7 @@ def test_umma_selftest(native_lib, mode, shape):
     g = torch.Generator().manual_seed(mode * 100 + n + k)
     A = torch.randn(128, k, generator=g)
     B = torch.randn(n, k, generator=g)
-    a_src = (A.t().contiguous() if mode & 2 else A).cuda()
+    a_src = (A.t().contiguous() if mode & 2 else A).cuda()   # bit 2 (value 4): two M=64 MMAs
     b_src = (B.t().contiguous() if mode & 1 else B).cuda()
     out = torch.full((128, n), float("nan"), device="cuda")
     N.check(native_lib.mmrca_dev_umma_selftest(mode, a_src.data_ptr(), b_src.data_ptr(), out.data_ptr(), n, k,
