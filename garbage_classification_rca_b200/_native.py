@@ -26,7 +26,7 @@ FLAG_FEATURE_GRADS = 256
 COMPUTE_FP32, COMPUTE_BF16, COMPUTE_BF16_FUSED = 0, 1, 2
 WS_TEXT_SA_IMAGE, WS_IMAGE_SA_IMAGE = 0, 1
 QUERY_ABI_VERSION, QUERY_DEVICE_OK, QUERY_SM_COUNT, QUERY_KERNEL_LAUNCHES, QUERY_RESET_LAUNCHES, QUERY_HAS_BF16 = range(6)
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _fp = C.c_void_p  # device pointers travel as integers
 
@@ -42,7 +42,7 @@ class HeadParams(C.Structure):
 
 class HeadDesc(C.Structure):
     _fields_ = [("batch", C.c_int32), ("d_img", C.c_int32), ("d_txt", C.c_int32), ("n_classes", C.c_int32),
-                ("flags", C.c_uint32), ("compute", C.c_int32)]
+                ("flags", C.c_uint32), ("compute", C.c_int32), ("drop_p", C.c_float), ("drop_seed", C.c_uint64)]
 
 
 class KernelTime(C.Structure):
@@ -57,7 +57,7 @@ EXPORTS = ("mmrca_query", "mmrca_last_error", "mmrca_head_workspace_bytes", "mmr
            "mmrca_head_backward", "mmrca_cross_entropy", "mmrca_head_train_step", "mmrca_attention_forward",
            "mmrca_attention_backward_scratch_bytes", "mmrca_attention_backward", "mmrca_timing_begin",
            "mmrca_timing_end", "mmrca_dev_umma_selftest", "mmrca_attention_forward_scratch_bytes",
-           "mmrca_head_workspace_offset")
+           "mmrca_head_workspace_offset", "mmrca_dropout_mask")
 
 
 def _sources_newer_than_lib() -> bool:
@@ -142,6 +142,8 @@ def lib() -> C.CDLL:
         L.mmrca_timing_end.restype = C.c_int
         L.mmrca_dev_umma_selftest.argtypes = [C.c_int32, _fp, _fp, _fp, C.c_int32, C.c_int32, _fp]
         L.mmrca_dev_umma_selftest.restype = C.c_int
+        L.mmrca_dropout_mask.argtypes = [C.c_uint64, C.c_float, C.c_int32, C.c_int32, _fp, _fp]
+        L.mmrca_dropout_mask.restype = C.c_int
         if L.mmrca_query(QUERY_ABI_VERSION) != ABI_VERSION:
             raise RuntimeError("libmmrca.so ABI version mismatch: rebuild it")
         _lib = L

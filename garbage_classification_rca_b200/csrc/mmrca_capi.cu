@@ -9,7 +9,7 @@
 
 #include "mmrca_attn_fp32.cuh"
 #include "mmrca_misc_fp32.cuh"
-#include "mmrca_attn_tc.cuh"
+#include "mmrca_dropout.cuh"
 #include "mmrca_tc_selftest.cuh"
 #include "mmrca_head_tc.cuh"
 #include "mmrca_head_tc_bwd.cuh"
@@ -119,65 +119,6 @@ static int attn_dispatch(bool backward, bool self, int d_in, int d_kq, int d_v, 
               "unsupported attention block shape: need self (d_in in {48,64,80},128,96) or cross (96,64,48)%s%s");
 }
 
-// ---- bf16 tensor-core attention blocks -----------------------------------------------------------------
-template <int DIN, int DKQ, int DV, bool SELF>
-static int launch_attn_tc(const TcAttnArgs& a, int sms, cudaStream_t st) {
-  using C = TcCfg<DIN, DKQ, DV, SELF>;
-  int rc = set_smem(attn_fwd_tc_kernel<C>, C::SMEM_BYTES);
-  if (rc) return rc;
-  const int tiles = (a.batch + kTcG - 1) / kTcG;
-  {
-    LaunchScope ls(SELF ? (DIN == 48 ? "attn_fwd_tc<48,128,96,self>" : DIN == 64 ? "attn_fwd_tc<64,128,96,self>"
-                                                                               : "attn_fwd_tc<80,128,96,self>")
-                        : "attn_fwd_tc<96,64,48,cross>", st);
-    attn_fwd_tc_kernel<C><<<min(tiles, sms), kTcThreads, C::SMEM_BYTES, st>>>(a);
-  }
-  MMRCA_CUDA(cudaGetLastError());
-  return MMRCA_OK;
-}
-
-static int attn_tc_dispatch(bool self, int d_in, int d_kq, int d_v, const TcAttnArgs& a, int sms, cudaStream_t st) {
-  if (a.batch <= 0) return MMRCA_OK;
-  if (self && d_kq == MMRCA_SA_DKQ && d_v == MMRCA_SA_DV) {
-    if (d_in == 48) return launch_attn_tc<48, 128, 96, true>(a, sms, st);
-    if (d_in == 64) return launch_attn_tc<64, 128, 96, true>(a, sms, st);
-    if (d_in == 80) return launch_attn_tc<80, 128, 96, true>(a, sms, st);
-  }
-  if (!self && d_in == MMRCA_SA_DV && d_kq == MMRCA_CA_DKQ && d_v == MMRCA_CA_DV)
-    return launch_attn_tc<96, 64, 48, false>(a, sms, st);
-  return fail(MMRCA_ERR_INVALID,
-              "unsupported attention block shape: need self (d_in in {48,64,80},128,96) or cross (96,64,48)%s%s");
-}
-
-static size_t wblob_bytes(int d_in, int d_kq, int d_v) {
-  return align_up_256(size_t(d_in / 8) * size_t((2 * d_kq + d_v) / 8) * 128);
-}
-
-static int launch_pack(const PackArgs& pa, cudaStream_t st) {
-  {
-    LaunchScope ls("pack_weights_bf16", st);
-    pack_weights_kernel<<<dim3(8, pa.njobs), 256, 0, st>>>(pa);
-  }
-  MMRCA_CUDA(cudaGetLastError());
-  return MMRCA_OK;
-}
-
-static PackJob make_pack_job(const MmrcaAttnParams& p, void* dst, int d_in, int d_kq, int d_v) {
-  PackJob j;
-  j.wq = p.wq; j.wk = p.wk; j.wv = p.wv; j.dst = dst; j.din = d_in; j.dkq = d_kq; j.dv = d_v;
-  return j;
-}
-
-static TcAttnArgs make_tc_args(const MmrcaAttnParams& p, const void* blob, const float* xq, const float* xkv,
-                               int batch, int reverse) {
-  TcAttnArgs a;
-  memset(&a, 0, sizeof(a));
-  a.xq = xq; a.xkv = xkv; a.wblob = blob;
-  a.bq = p.bq; a.bk = p.bk; a.bv = p.bv; a.ln_g = p.ln_g; a.ln_b = p.ln_b;
-  a.batch = batch; a.reverse = reverse;
-  return a;
-}
-
 static AttnArgs make_attn_args(const MmrcaAttnParams& p, const float* xq, const float* xkv, int batch, int reverse) {
   AttnArgs a;
   memset(&a, 0, sizeof(a));
@@ -258,7 +199,7 @@ static int classifier_dispatch(bool backward, int nc, const CatArgs& a, int sms,
 struct Workspace {
   float *norm_img, *norm_txt, *t_sa, *i_sa, *t_i, *i_t;          // forward (kept for the backward)
   float *d_t_sa, *d_i_sa, *d_t_i, *d_i_t, *dy, *dlogits;          // training only
-  void* wblob[4];                                                   // bf16 packed weights: sa_img, sa_txt, ca1, ca2
+  uint8_t* mask;                                                    // seeded dropout materialised for the fp32 kernels
   // fused bf16 pipeline (mmrca_head_tc.cuh)
   void* fblob[4];                                                   // per block: bz | bv | bc blobs
   void* t_img; void* i_img;                                         // SA output images, [tiles][kSaTileBytes]
@@ -268,6 +209,29 @@ struct Workspace {
 };
 
 static size_t align_up(size_t v) { return align_up_256(v); }
+
+static int concat_width(const MmrcaHeadDesc& d) {
+  const int ca = 2 * kL * MMRCA_CA_DV;
+  if (d.flags & MMRCA_FLAG_FEATURES_ONLY) return d.d_img + d.d_txt;
+  if (d.flags & MMRCA_FLAG_CROSS_ATTENTION_ONLY) return ca;
+  return ca + d.d_img + d.d_txt;
+}
+
+// seeded dropout of the concat (mmrca_dropout.cuh) from the desc; thresh == 0 when off
+static DropSpec make_drop(const MmrcaHeadDesc& d) {
+  DropSpec s;
+  memset(&s, 0, sizeof(s));
+  s.D = concat_width(d);
+  s.scale = 1.0f;
+  if (d.drop_p > 0.f) {
+    const float p = d.drop_p < 1.f ? d.drop_p : 1.f;
+    s.seed_lo = uint32_t(d.drop_seed & 0xffffffffu);
+    s.seed_hi = uint32_t(d.drop_seed >> 32);
+    s.thresh = uint32_t(p * 65536.0f + 0.5f);
+    s.scale = p < 1.f ? 1.0f / (1.0f - p) : 0.f;
+  }
+  return s;
+}
 
 static Workspace carve(const MmrcaHeadDesc& d, bool training, void* base) {
   Workspace w;
@@ -279,6 +243,7 @@ static Workspace carve(const MmrcaHeadDesc& d, bool training, void* base) {
   w.norm_img = take(B); w.norm_txt = take(B);
   w.t_sa = take(B * kL * MMRCA_SA_DV); w.i_sa = take(B * kL * MMRCA_SA_DV);
   w.t_i = take(B * kL * MMRCA_CA_DV); w.i_t = take(B * kL * MMRCA_CA_DV);
+  if (d.drop_p > 0.f) w.mask = reinterpret_cast<uint8_t*>(take((B * size_t(concat_width(d)) + 3) / 4));
   if (d.compute != MMRCA_COMPUTE_FP32) {
     const size_t tiles = (B + 7) / 8;
     w.fblob[0] = take(htc::SaCfg<80>::W_BYTES / 4);
@@ -319,6 +284,7 @@ static int check_desc(const MmrcaHeadDesc* d) {
   }
   if (d->compute != MMRCA_COMPUTE_FP32 && d->compute != MMRCA_COMPUTE_BF16 && d->compute != MMRCA_COMPUTE_BF16_FUSED)
     return fail(MMRCA_ERR_INVALID, "unknown compute mode%s%s");
+  if (!(d->drop_p >= 0.f && d->drop_p <= 1.f)) return fail(MMRCA_ERR_INVALID, "drop_p must be in [0, 1]%s%s");
   return MMRCA_OK;
 }
 
@@ -327,13 +293,6 @@ static int check_desc(const MmrcaHeadDesc* d) {
 static bool fused_ok(const MmrcaHeadDesc& d, const uint8_t* mask) {
   return d.compute != MMRCA_COMPUTE_FP32 && d.d_img == 1280 && d.d_txt == 768 && d.n_classes == 4 &&
          !(d.flags & (MMRCA_FLAG_FEATURES_ONLY | MMRCA_FLAG_FEATURE_GRADS)) && mask == nullptr;
-}
-
-static int concat_width(const MmrcaHeadDesc& d) {
-  const int ca = 2 * kL * MMRCA_CA_DV;
-  if (d.flags & MMRCA_FLAG_FEATURES_ONLY) return d.d_img + d.d_txt;
-  if (d.flags & MMRCA_FLAG_CROSS_ATTENTION_ONLY) return ca;
-  return ca + d.d_img + d.d_txt;
 }
 
 // concat order: multimodal_model.py:694-716
@@ -388,7 +347,6 @@ static htc::PrepBlock make_prep_block(const MmrcaAttnParams& p, void* blob, int 
 
 static int launch_prep_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, float* logits, const Workspace& w,
                              float* zero0, int nzero0, cudaStream_t st) {
-  const bool co = d.flags & MMRCA_FLAG_CROSS_ATTENTION_ONLY;
   htc::PrepArgs a;
   memset(&a, 0, sizeof(a));
   a.blk[0] = make_prep_block(p.sa_img, w.fblob[0], 80, MMRCA_SA_DKQ, MMRCA_SA_DV);
@@ -401,13 +359,7 @@ static int launch_prep_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, f
   a.src[n].off = 0; a.src[n].w = MMRCA_CA_DV; ++n;
   a.src[n].bc = static_cast<uint8_t*>(w.fblob[3]) + htc::CaCfg::BZ_BYTES + htc::CaCfg::BV_BYTES;
   a.src[n].off = ca; a.src[n].w = MMRCA_CA_DV; ++n;
-  if (!co) {
-    a.src[n].bc = static_cast<uint8_t*>(w.fblob[0]) + htc::SaCfg<80>::BZ_BYTES + htc::SaCfg<80>::BV_BYTES;
-    a.src[n].off = 2 * ca; a.src[n].w = 80; ++n;
-    a.src[n].bc = static_cast<uint8_t*>(w.fblob[1]) + htc::SaCfg<48>::BZ_BYTES + htc::SaCfg<48>::BV_BYTES;
-    a.src[n].off = 2 * ca + d.d_img; a.src[n].w = 48; ++n;
-  }
-  a.nsrc = n;
+  a.nsrc = n;      // (the feature sources of the classifier run in fp32 inside sa_fwd_kernel / ce_feat_kernel)
   a.wf = p.wf; a.bf = p.bf; a.D = concat_width(d);
   a.logits = logits; a.batch = d.batch;
   a.zero0 = zero0; a.nzero0 = nzero0;
@@ -430,10 +382,11 @@ static int head_forward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, 
     htc::SaFwdArgs a;
     memset(&a, 0, sizeof(a));
     a.role[0].feat = img; a.role[0].norms = w.norm_img; a.role[0].ln_g = p.sa_img.ln_g; a.role[0].ln_b = p.sa_img.ln_b;
-    a.role[0].blobs = w.fblob[0]; a.role[0].out_tiles = w.i_img;
+    a.role[0].blobs = w.fblob[0]; a.role[0].out_tiles = w.i_img; a.role[0].cls_off = 2 * kL * MMRCA_CA_DV;
     a.role[1].feat = txt; a.role[1].norms = w.norm_txt; a.role[1].ln_g = p.sa_txt.ln_g; a.role[1].ln_b = p.sa_txt.ln_b;
-    a.role[1].blobs = w.fblob[1]; a.role[1].out_tiles = w.t_img;
+    a.role[1].blobs = w.fblob[1]; a.role[1].out_tiles = w.t_img; a.role[1].cls_off = 2 * kL * MMRCA_CA_DV + d.d_img;
     a.logits = co ? nullptr : logits;
+    a.wf = p.wf; a.drop = make_drop(d);
     a.batch = d.batch;
     if ((rc = set_smem(htc::sa_fwd_kernel, htc::SaFwdLayout::BYTES))) return rc;
     LaunchScope ls("sa_fwd_bf16", st);
@@ -447,6 +400,7 @@ static int head_forward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, 
     a.dir[1].blobs = w.fblob[3]; a.dir[1].ln_g = p.ca2.ln_g; a.dir[1].ln_b = p.ca2.ln_b;
     a.t_tiles = w.t_img; a.i_tiles = w.i_img;
     a.logits = logits; a.batch = d.batch; a.reverse = (d.flags & MMRCA_FLAG_REVERSE) ? 1 : 0;
+    a.drop = make_drop(d);
     if ((rc = set_smem(htc::ca_fwd_kernel, htc::CaFwdLayout::BYTES))) return rc;
     LaunchScope ls("ca_fwd_bf16", st);
     htc::ca_fwd_kernel<<<grid, htc::kCtaThreads, htc::CaFwdLayout::BYTES, st>>>(a);
@@ -459,7 +413,6 @@ static int head_forward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, 
 static int head_backward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, const float* img, const float* txt,
                                const float* dlogits, const MmrcaHeadGrads& g, const Workspace& w, int sms,
                                cudaStream_t st) {
-  const bool co = d.flags & MMRCA_FLAG_CROSS_ATTENTION_ONLY;
   const int tiles = (d.batch + 7) / 8, D = concat_width(d), ca = kL * MMRCA_CA_DV;
   int rc;
   MMRCA_CUDA(cudaMemsetAsync(w.gm[0], 0, w.gm_floats * sizeof(float), st));
@@ -477,6 +430,7 @@ static int head_backward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p,
     }
     a.t_tiles = w.t_img; a.i_tiles = w.i_img; a.dlogits = dlogits; a.D = D;
     a.batch = d.batch; a.reverse = (d.flags & MMRCA_FLAG_REVERSE) ? 1 : 0;
+    a.drop = make_drop(d);
     if ((rc = set_smem(htc::ca_bwd_kernel, htc::CaBwdSmem::BYTES))) return rc;
     LaunchScope ls("ca_bwd_bf16", st);
     htc::ca_bwd_kernel<<<dim3(min(tiles, max(1, sms / 2)), 2), htc::kCtaThreads, htc::CaBwdSmem::BYTES, st>>>(a);
@@ -488,9 +442,8 @@ static int head_backward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p,
     memset(&a, 0, sizeof(a));
     a.feat = img; a.blobs = w.fblob[0]; a.ln_g = p.sa_img.ln_g; a.ln_b = p.sa_img.ln_b;
     a.dout_a = w.dx_img[1]; a.dout_b = w.dx_img[2];
-    a.dlogits = co ? nullptr : dlogits;
     a.gm = w.gm[0]; a.g_wv = g.sa_img.wv; a.g_bv = g.sa_img.bv; a.g_ln_g = g.sa_img.ln_g; a.g_ln_b = g.sa_img.ln_b;
-    a.g_wf = co ? nullptr : g.wf + 2 * ca; a.D = D; a.batch = d.batch;
+    a.batch = d.batch;
     if ((rc = set_smem(htc::sa_bwd_kernel<80>, htc::SaBwdSmem<80>::BYTES))) return rc;
     {
       LaunchScope ls("sa_bwd_bf16<80>", st);
@@ -500,7 +453,6 @@ static int head_backward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p,
     a.feat = txt; a.blobs = w.fblob[1]; a.ln_g = p.sa_txt.ln_g; a.ln_b = p.sa_txt.ln_b;
     a.dout_a = w.dx_img[0]; a.dout_b = w.dx_img[3];
     a.gm = w.gm[1]; a.g_wv = g.sa_txt.wv; a.g_bv = g.sa_txt.bv; a.g_ln_g = g.sa_txt.ln_g; a.g_ln_b = g.sa_txt.ln_b;
-    a.g_wf = co ? nullptr : g.wf + 2 * ca + d.d_img;
     if ((rc = set_smem(htc::sa_bwd_kernel<48>, htc::SaBwdSmem<48>::BYTES))) return rc;
     {
       LaunchScope ls("sa_bwd_bf16<48>", st);
@@ -528,15 +480,24 @@ static int head_backward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p,
   return MMRCA_OK;
 }
 
-static int launch_ce4(const float* logits, const int64_t* labels, const MmrcaCeDesc* ce, int batch, float* loss,
-                      float* dlogits, float* g_bf, int sms, cudaStream_t st) {
-  MMRCA_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
-  htc::Ce4Args a;
+// cross-entropy (labels != null) or given dlogits, + classifier bias gradient + the feature-source rows of dWf
+static int launch_ce_feat(const MmrcaHeadDesc& d, const float* logits, const int64_t* labels, const MmrcaCeDesc* ce,
+                          float* loss, float* dlogits, const MmrcaHeadGrads& g, bool bias_grad, const float* img,
+                          const float* txt, const Workspace& w, int sms, cudaStream_t st) {
+  const bool co = d.flags & MMRCA_FLAG_CROSS_ATTENTION_ONLY;
+  if (labels) MMRCA_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  htc::CeFeatArgs a;
+  memset(&a, 0, sizeof(a));
   a.logits = logits; a.labels = labels; a.cw = ce ? ce->class_weight : nullptr; a.eps = ce ? ce->label_smoothing : 0.f;
-  a.batch = batch; a.dlogits = dlogits; a.loss = loss; a.g_bf = g_bf;
+  a.batch = d.batch; a.dlogits = dlogits; a.loss = loss; a.g_bf = bias_grad ? g.bf : nullptr;
+  a.drop = make_drop(d);
+  if (!co && g.wf) {
+    a.img = img; a.txt = txt; a.norm_img = w.norm_img; a.norm_txt = w.norm_txt; a.g_wf = g.wf;
+    a.off_img = 2 * kL * MMRCA_CA_DV; a.off_txt = a.off_img + d.d_img;
+  }
   {
-    LaunchScope ls("cross_entropy4", st);
-    htc::ce4_kernel<<<max(1, min((batch + 255) / 256, sms)), 256, 0, st>>>(a);
+    LaunchScope ls("ce_feat", st);
+    htc::ce_feat_kernel<<<max(1, min((d.batch + 7) / 8, 2 * sms)), 256, 0, st>>>(a);
   }
   MMRCA_CUDA(cudaGetLastError());
   return MMRCA_OK;
@@ -550,6 +511,15 @@ static int head_forward_impl(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, c
   int rc;
   if (d.batch == 0) return MMRCA_OK;
   if (fused_ok(d, mask)) return head_forward_fused(d, p, img, txt, logits, w, sms, st);
+  if (!mask && d.drop_p > 0.f) {      // seeded dropout: the fp32 kernels read the materialised mask
+    const DropSpec ds = make_drop(d);
+    {
+      LaunchScope ls("dropout_mask", st);
+      dropout_mask_kernel<<<min(4 * sms, max(1, int((size_t(d.batch) * ds.D / 2 + 255) / 256))), 256, 0, st>>>(ds, d.batch, w.mask);
+    }
+    MMRCA_CUDA(cudaGetLastError());
+    mask = w.mask; scale = ds.scale;
+  }
   if (fo) {
     const int grid = min((d.batch + kWarps - 1) / kWarps, 8 * sms);
     { LaunchScope ls("l2norm", st); l2norm_kernel<<<grid, kThreads, 0, st>>>(img, w.norm_img, d.batch, d.d_img); }
@@ -574,19 +544,10 @@ static int head_forward_impl(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, c
   return classifier_dispatch(false, d.n_classes, c, sms, st);
 }
 
-__global__ void __launch_bounds__(256) colsum4_kernel(const float* __restrict__ dl, int batch, float* __restrict__ out) {
-  float s[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int b = blockIdx.x * 256 + threadIdx.x; b < batch; b += gridDim.x * 256) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(dl) + b);
-    s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-  }
-  for (int c = 0; c < 4; ++c) { s[c] = warp_sum(s[c]); if ((threadIdx.x & 31) == 0) atomicAdd(out + c, s[c]); }
-}
-
 static int head_backward_impl(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, const float* img, const float* txt,
                               const uint8_t* mask, float scale, const float* dlogits, const MmrcaHeadGrads& g,
                               float* d_img, float* d_txt, const Workspace& w, int sms, cudaStream_t st,
-                              bool w_skip_bias_grad = false) {
+                              bool ce_done = false) {
   const bool fo = d.flags & MMRCA_FLAG_FEATURES_ONLY, co = !fo && (d.flags & MMRCA_FLAG_CROSS_ATTENTION_ONLY);
   const int rev = (d.flags & MMRCA_FLAG_REVERSE) ? 1 : 0;
   const bool want_feat = d_img != nullptr || d_txt != nullptr;
@@ -598,14 +559,13 @@ static int head_backward_impl(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, 
     if (want_feat)
       return fail(MMRCA_ERR_INVALID, "feature gradients need MMRCA_FLAG_FEATURE_GRADS in the desc of the forward AND "
                                      "the backward (the bf16 pipeline keeps parameter gradients only)%s%s");
-    // classifier bias gradient: column sums of dlogits (the fused cross-entropy adds it itself in train_step)
-    if (g.bf && !w_skip_bias_grad) {
-      LaunchScope ls("bias_grad", st);
-      colsum4_kernel<<<min((d.batch + 255) / 256, sms), 256, 0, st>>>(dlogits, d.batch, g.bf);
-      MMRCA_CUDA(cudaGetLastError());
-    }
+    // classifier bias gradient and the feature-source rows of dWf from the given dlogits (train_step has done
+    // both inside its cross-entropy kernel)
+    if (!ce_done && (rc = launch_ce_feat(d, nullptr, nullptr, nullptr, nullptr, const_cast<float*>(dlogits), g, g.bf != nullptr,
+                                         img, txt, w, sms, st))) return rc;
     return head_backward_fused(d, p, img, txt, dlogits, g, w, sms, st);
   }
+  if (!mask && d.drop_p > 0.f) { mask = w.mask; scale = make_drop(d).scale; }   // materialised by the forward
   // 1. classifier: dWf, dbf, d(T_I), d(I_T) and the direct feature terms d(img_n), d(txt_n)
   CatArgs c = make_cat_args(d, w, img, txt, mask, scale, p.wf, p.bf);
   c.dlogits = dlogits; c.g_wf = g.wf; c.g_bf = g.bf;
@@ -796,7 +756,8 @@ int mmrca_head_train_step(const MmrcaHeadDesc* desc, const MmrcaHeadParams* para
   if ((rc = head_forward_impl(*desc, *params, img_feat, txt_feat, drop_mask, drop_scale, logits, w, di.sms, st)))
     return rc;
   if (fused_ok(*desc, drop_mask)) {
-    if ((rc = launch_ce4(logits, labels, ce, desc->batch, loss_out, w.dlogits, grads->bf, di.sms, st))) return rc;
+    if ((rc = launch_ce_feat(*desc, logits, labels, ce, loss_out, w.dlogits, *grads, grads->bf != nullptr, img_feat,
+                             txt_feat, w, di.sms, st))) return rc;
     return head_backward_impl(*desc, *params, img_feat, txt_feat, drop_mask, drop_scale, w.dlogits, *grads, d_img_feat,
                               d_txt_feat, w, di.sms, st, true);
   }
@@ -805,36 +766,22 @@ int mmrca_head_train_step(const MmrcaHeadDesc* desc, const MmrcaHeadParams* para
                             d_txt_feat, w, di.sms, st);
 }
 
-size_t mmrca_attention_forward_scratch_bytes(int32_t d_in, int32_t d_kq, int32_t d_v, int32_t compute) {
-  return compute == MMRCA_COMPUTE_BF16 ? wblob_bytes(d_in, d_kq, d_v) : 0;
-}
+size_t mmrca_attention_forward_scratch_bytes(int32_t, int32_t, int32_t, int32_t) { return 0; }
 
 int mmrca_attention_forward(const MmrcaAttnParams* p, const float* x_q, const float* x_kv, int32_t batch,
                             int32_t d_in, int32_t d_kq, int32_t d_v, int32_t reverse, int32_t normalise,
                             float* norms_out, float* out, void* scratch, size_t scratch_bytes, int32_t compute,
                             void* stream) {
+  (void)scratch; (void)scratch_bytes;
   if (!p || !x_q || !x_kv || !out) return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
-  if (compute != MMRCA_COMPUTE_FP32 && compute != MMRCA_COMPUTE_BF16)
-    return fail(MMRCA_ERR_INVALID, "unknown compute mode%s%s");
+  if (compute != MMRCA_COMPUTE_FP32)
+    return fail(MMRCA_ERR_INVALID, "stand-alone attention blocks run in fp32 only: the bf16 tensor-core pipeline exists "
+                                   "as the fused head (mmrca_head_*)%s%s");
   if (normalise && (x_q != x_kv || !norms_out))
     return fail(MMRCA_ERR_INVALID, "normalise needs x_kv == x_q and a norms_out buffer%s%s");
   DeviceInfo di;
   int rc;
   if ((rc = device_info(&di))) return rc;
-  if (compute == MMRCA_COMPUTE_BF16) {
-    if (d_in % 16 || d_kq % 16 || d_v % 16 || d_in <= 0) return fail(MMRCA_ERR_INVALID, "unsupported block shape%s%s");
-    if (!scratch || scratch_bytes < wblob_bytes(d_in, d_kq, d_v))
-      return fail(MMRCA_ERR_WORKSPACE, "bf16 attention forward needs mmrca_attention_forward_scratch_bytes()%s%s");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    PackArgs pa;
-    memset(&pa, 0, sizeof(pa));
-    pa.njobs = 1;
-    pa.job[0] = make_pack_job(*p, scratch, d_in, d_kq, d_v);
-    if (batch > 0 && (rc = launch_pack(pa, st))) return rc;
-    TcAttnArgs ta = make_tc_args(*p, scratch, x_q, x_kv, batch, reverse ? 1 : 0);
-    ta.normalise = normalise ? 1 : 0; ta.norms = norms_out; ta.out = out;
-    return attn_tc_dispatch(x_q == x_kv, d_in, d_kq, d_v, ta, di.sms, st);
-  }
   AttnArgs a = make_attn_args(*p, x_q, x_kv, batch, reverse ? 1 : 0);
   a.normalise = normalise ? 1 : 0; a.norms = norms_out; a.out = out;
   return attn_dispatch(false, x_q == x_kv, d_in, d_kq, d_v, a, di.sms, static_cast<cudaStream_t>(stream));
@@ -849,8 +796,8 @@ int mmrca_attention_backward(const MmrcaAttnParams* p, const float* x_q, const f
                              const MmrcaAttnGrads* grads, float* d_x_q, float* d_x_kv, void* scratch,
                              size_t scratch_bytes, int32_t compute, void* stream) {
   if (!p || !x_q || !x_kv || !d_out || !grads || !scratch) return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
-  if (compute != MMRCA_COMPUTE_FP32 && compute != MMRCA_COMPUTE_BF16)
-    return fail(MMRCA_ERR_INVALID, "unknown compute mode%s%s");
+  if (compute != MMRCA_COMPUTE_FP32)
+    return fail(MMRCA_ERR_INVALID, "stand-alone attention blocks run in fp32 only%s%s");
   if (scratch_bytes < mmrca_attention_backward_scratch_bytes(batch, d_kq, d_v))
     return fail(MMRCA_ERR_WORKSPACE, "scratch too small%s%s");
   const bool self = x_q == x_kv;
@@ -864,6 +811,28 @@ int mmrca_attention_backward(const MmrcaAttnParams* p, const float* x_q, const f
   a.g_ln_g = grads->ln_g; a.g_ln_b = grads->ln_b;
   if ((rc = attn_dispatch(true, self, d_in, d_kq, d_v, a, di.sms, st))) return rc;
   return attn_wgrads(self, d_in, d_kq, d_v, a.dy, x_q, x_kv, nullptr, batch, *grads, di.sms, st);
+}
+
+int mmrca_dropout_mask(uint64_t seed, float p, int32_t batch, int32_t width, uint8_t* mask_out, void* stream) {
+  if (!mask_out || batch < 0 || width <= 0 || (width & 1) || !(p >= 0.f && p <= 1.f))
+    return fail(MMRCA_ERR_INVALID, "dropout mask needs an even width, p in [0, 1] and an output buffer%s%s");
+  DeviceInfo di;
+  int rc;
+  if ((rc = device_info(&di))) return rc;
+  if (batch == 0) return MMRCA_OK;
+  MmrcaHeadDesc d;
+  memset(&d, 0, sizeof(d));
+  d.drop_p = p; d.drop_seed = seed;
+  DropSpec ds = make_drop(d);
+  ds.D = width;
+  if (p == 0.f) ds.thresh = 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    LaunchScope ls("dropout_mask", st);
+    dropout_mask_kernel<<<min(4 * di.sms, max(1, int((size_t(batch) * width / 2 + 255) / 256))), 256, 0, st>>>(ds, batch, mask_out);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
 }
 
 int mmrca_dev_umma_selftest(int32_t mode, const float* a, const float* b, float* out, int32_t n, int32_t k,

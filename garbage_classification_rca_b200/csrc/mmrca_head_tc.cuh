@@ -13,9 +13,13 @@
 //   analytically zero in the reference too).
 //   biases ride in the GEMM: every activation operand carries a constant-one column at k = d_in (and zeros up
 //   to d_in+16), the weight blobs carry u / b_value in that row.
-//   classifier (:719-726): logits[b][c] = sum_{chunk r, j} F[(b,r)][j] Wf[c][off + r*w + j] is computed per
-//   source as one N=64 MMA  D[(b,r)][(r',c)] = sum_j F[(b,r)][j] Wf[c][off + r'*w + j];  the thread that owns
-//   row (b,r) keeps columns (r,0..3) and a 16-lane shuffle sums the sample's chunks.
+//   classifier (:719-726), cross-attention sources T_I / I_T: logits[b][c] = sum_{chunk r, j} F[(b,r)][j]
+//   Wf[c][off + r*w + j] is one N=64 MMA  D[(b,r)][(r',c)] = sum_j F[(b,r)][j] Wf[c][off + r'*w + j];  the thread
+//   that owns row (b,r) keeps columns (r,0..3) and a 16-lane shuffle sums the sample's chunks.
+//   classifier, feature sources (normalised image / text features, 2048 of the 3584 concat columns): plain fp32
+//   FMAs on the registers that already hold the sample while it is normalised (8 k FMA per sample), so the
+//   part of the logits that decides the argmax carries no bf16 rounding at all.
+//   dropout (:719): a counter-based keep mask regenerated wherever the concat is touched (mmrca_dropout.cuh).
 //
 // Tiles: 8 samples = 128 rows (row = 16*sample + chunk).  MMAs whose rows are tile rows and whose result is only
 // converted (projections, classifier) use M=128: TMEM lane = row.  The attention core (scores, P V) uses two M=64
@@ -35,6 +39,7 @@
 #include <stdint.h>
 
 #include "mmrca_attn_fp32.cuh"
+#include "mmrca_dropout.cuh"
 #include "mmrca_tc.cuh"
 
 namespace mmrca {
@@ -307,11 +312,10 @@ struct SaCfg {
   static constexpr int DIN = DIN_, KE = DIN_ + 16, DV = kDV_SA;
   static constexpr uint32_t BZ_LBO = DIN * 16, BZ_BYTES = blob_bytes(DIN, KE);
   static constexpr uint32_t BV_LBO = DV * 16, BV_BYTES = blob_bytes(DV, KE);
-  static constexpr uint32_t BC_LBO = kNCls * 16, BC_BYTES = blob_bytes(kNCls, DIN);
-  static constexpr uint32_t W_BYTES = BZ_BYTES + BV_BYTES + BC_BYTES;
+  static constexpr uint32_t W_BYTES = BZ_BYTES + BV_BYTES;
   // TMEM columns (relative to the warpgroup base)
-  static constexpr uint32_t COL_Z = 0, COL_V = DIN, COL_CLS = DIN + DV, COL_S = 0, COL_C = 64;
-  static_assert(DIN + DV + kNCls <= 256, "warpgroup TMEM budget");
+  static constexpr uint32_t COL_Z = 0, COL_V = DIN, COL_S = 0, COL_C = 64;
+  static_assert(DIN + DV <= 256, "warpgroup TMEM budget");
 };
 
 constexpr uint32_t kSaTileBytes = op_bytes(kDV_SA);   // one SA output image: [128 x 96] bf16 = 12 chunk columns
@@ -320,12 +324,15 @@ struct SaRole {
   const float* feat;      // [B][16*DIN] fp32
   float* norms;           // [B] (out)
   const float* ln_g; const float* ln_b;
-  const void* blobs;      // bz | bv | bc, contiguous
+  const void* blobs;      // bz | bv, contiguous
   void* out_tiles;        // [tiles][kSaTileBytes]
+  int cls_off;            // first concat column of this feature source (classifier, dropout)
 };
 struct SaFwdArgs {
   SaRole role[2];         // 0: image (DIN 80), 1: text (DIN 48)
   float* logits;          // += feature term (null: classifier does not see the features)
+  const float* wf;        // classifier weight [4][D] fp32
+  DropSpec drop;          // drop.D = D
   int batch;
 };
 
@@ -348,10 +355,13 @@ struct SaFwdLayout {
   static_assert(BYTES <= 232448, "SA forward does not fit shared memory");
 };
 
-// load + L2-normalise (multimodal_model.py:662-665) this warp's two samples into the bf16 operand
+// load + L2-normalise (multimodal_model.py:662-665) this warp's two samples into the bf16 operand; while the
+// sample sits in registers, its classifier term  logits[b][c] += sum_j drop(x_j / ||x||) Wf[c][off + j]  in fp32
 template <int DIN>
 __device__ __forceinline__ void stage_features(const WgCtx& c, uint8_t* xop, const float* __restrict__ feat,
-                                               float* __restrict__ norms, int b0, int batch) {
+                                               float* __restrict__ norms, int b0, int batch,
+                                               float* __restrict__ logits, const float* __restrict__ wf, int cls_off,
+                                               const DropSpec& drop) {
   constexpr int KCS = DIN / 8, ITEMS = kL * KCS, PER = (ITEMS + 31) / 32;
   float v[2][PER][8];
   float ss[2] = {0.f, 0.f};
@@ -378,6 +388,53 @@ __device__ __forceinline__ void stage_features(const WgCtx& c, uint8_t* xop, con
 #pragma unroll
       for (int e = 0; e < 8; ++e) ss[s] = fmaf(v[s][k][e], v[s][k][e], ss[s]);
     ss[s] = warp_sum(ss[s]);
+  }
+  if (logits) {
+    float acc[2][kClasses];
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int cc = 0; cc < kClasses; ++cc) acc[s][cc] = 0.f;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int it = c.lane + 32 * k;
+      if (ITEMS % 32 != 0 && it >= ITEMS) continue;
+      float t[2][8];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t[s][e] = v[s][k][e];
+        if (drop.thresh) {
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            float m0, m1;
+            drop_pair(drop, uint32_t(b0 + 2 * c.q + s), uint32_t(cls_off + it * 8 + e), m0, m1);
+            t[s][e] *= m0; t[s][e + 1] *= m1;
+          }
+        }
+      }
+#pragma unroll
+      for (int cc = 0; cc < kClasses; ++cc) {
+        const float* wp = wf + size_t(cc) * drop.D + cls_off + it * 8;
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[s][cc] = fmaf(t[s][e], w[e], acc[s][cc]);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int b = b0 + 2 * c.q + s;
+      const float inv = 1.0f / sqrtf(ss[s]);      // no epsilon, like the reference
+#pragma unroll
+      for (int cc = 0; cc < kClasses; ++cc) {
+        const float r = warp_sum(acc[s][cc]) * inv;
+        if (c.lane == 0 && b < batch) atomicAdd(logits + size_t(b) * kClasses + cc, r);
+      }
+    }
   }
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
@@ -409,25 +466,20 @@ __device__ __forceinline__ void sa_fwd_tile(WgCtx& c, const SaFwdArgs& a, const 
   uint8_t* xop = bsm + SaFwdSmem::X;
   uint8_t* zop = bsm + SaFwdSmem::ZP;
   uint8_t* vop = bsm + SaFwdSmem::V;
-  stage_features<C::DIN>(c, xop, R.feat, R.norms, b0, a.batch);
+  stage_features<C::DIN>(c, xop, R.feat, R.norms, b0, a.batch, a.logits, a.wf, R.cls_off, a.drop);
   wg_sync_for_mma(c);
-  // ---- Z | V | classifier feature term: three MMA chains over the same A operand ------------------------------
+  // ---- Z | V: two MMA chains over the same A operand ---------------------------------------------------------------
   if (c.wt == 0) {
     const uint64_t ax = make_smem_desc(smem_u32(xop), kCS, kRS);
     mma_steps(c.tmem + C::COL_Z, ax, 2 * kCS, make_smem_desc(smem_u32(wsm), C::BZ_LBO, 128), 2 * C::BZ_LBO,
               make_idesc_bf16(128, C::DIN, 0, 0), C::KE / 16, false);
     mma_steps(c.tmem + C::COL_V, ax, 2 * kCS, make_smem_desc(smem_u32(wsm + C::BZ_BYTES), C::BV_LBO, 128),
               2 * C::BV_LBO, make_idesc_bf16(128, C::DV, 0, 0), C::KE / 16, false);
-    if (a.logits)
-      mma_steps(c.tmem + C::COL_CLS, ax, 2 * kCS,
-                make_smem_desc(smem_u32(wsm + C::BZ_BYTES + C::BV_BYTES), C::BC_LBO, 128), 2 * C::BC_LBO,
-                make_idesc_bf16(128, kNCls, 0, 0), C::DIN / 16, false);
     umma_commit(c.bar);
   }
   wg_wait_mma(c);
   acc_to_operand<C::DIN>(c, C::COL_Z, zop);
   acc_to_operand<C::DV>(c, C::COL_V, vop);
-  if (a.logits) cls_readback(c, C::COL_CLS, a.logits, b0 + (c.rp >> 4), b0 + (c.rp >> 4) < a.batch);
   wg_sync_for_mma(c);
   // ---- scores: two M=64 halves, S_h = Z_h X_h^T --------------------------------------------------------------
   if (c.wt == 0) {
@@ -541,6 +593,7 @@ struct CaFwdArgs {
   const void* t_tiles;      // text SA images
   const void* i_tiles;      // image SA images
   float* logits;
+  DropSpec drop;            // concat columns of direction d: [d * 768, d * 768 + 768)
   int batch, reverse;
 };
 struct CaFwdSmem {
@@ -626,6 +679,7 @@ __device__ __forceinline__ void ca_fwd_tile(WgCtx& c, const CaFwdArgs& a, int d,
   {
     float mean, rstd;
     ln_stats_tmem<C::DV>(c, C::COL_C, mean, rstd);
+    const uint32_t cat0 = uint32_t(d * kL * C::DV + (c.rs & 15) * C::DV);   // my row's first concat column (:689-716)
 #pragma unroll
     for (int c0 = 0; c0 < C::DV; c0 += 16) {
       uint32_t r[16];
@@ -635,6 +689,14 @@ __device__ __forceinline__ void ca_fwd_tile(WgCtx& c, const CaFwdArgs& a, int d,
 #pragma unroll
       for (int e = 0; e < 16; ++e)
         o[e] = fmaxf(fmaf((__uint_as_float(r[e]) - mean) * rstd, ln_s[c0 + e], ln_s[48 + c0 + e]), 0.f);
+      if (a.drop.thresh) {      // self.drop (:719) acts on the classifier's copy only
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+          float m0, m1;
+          drop_pair(a.drop, uint32_t(b0 + (c.rs >> 4)), cat0 + c0 + e, m0, m1);
+          o[e] *= m0; o[e + 1] *= m1;
+        }
+      }
       const float lo[8] = {o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]};
       const float hi[8] = {o[8], o[9], o[10], o[11], o[12], o[13], o[14], o[15]};
       *reinterpret_cast<uint4*>(xq + uint32_t(c0 >> 3) * kCS + row_off(c.rs)) = pack_bf16x8(lo);

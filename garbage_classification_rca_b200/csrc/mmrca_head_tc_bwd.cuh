@@ -7,7 +7,8 @@
 //   attention   dP = dC V^T,  dV = P^T dC,  dS = softmax'(dP),  dZ = dS Xkv
 //   inputs      dXq = dZ M^T,  dXkv = dS^T Z + dV Wv            (CA blocks: they feed the SA backward)
 //   parameters  dM_ext += Xq_ext^T dZ,  dWv_ext += Xkv_ext^T dV   (the ones column of X_ext yields du, db_value)
-//               dWf^T  += F^T DL        (classifier rows of this source; DL = dlogits spread on the chunk diagonal)
+//               dWf^T  += F^T DL        (classifier rows of a cross-attention source; DL = dlogits spread on the
+//                                        chunk diagonal.  The rows of the feature sources: ce_feat_kernel, fp32)
 //               [dgamma | dbeta] += [dy xhat | dy]^T 1
 // Every contraction, including the reductions over the batch, is a tcgen05.mma.  The parameter gradients stay in
 // TMEM for the whole persistent CTA and are flushed once at the end with lane-coalesced atomics; dW_query,
@@ -22,22 +23,39 @@ namespace mmrca {
 namespace htc {
 
 // ---------------------------------------------------------------------------------------------------------------
-// CrossEntropyLoss(weight, label_smoothing), mean reduction (main_both.py:87-93), 4 classes, many CTAs.
-// Every CTA recomputes the normaliser sum_b w[y_b] from the labels, so dlogits leave normalised in one pass.
+// CrossEntropyLoss(weight, label_smoothing), mean reduction (main_both.py:87-93), 4 classes, fused with the two
+// reductions over the batch that need nothing but dlogits and the raw features:
+//   db_f[c]          += sum_b dlogits[b][c]
+//   dWf[c][off + j]  += sum_b dlogits[b][c] drop(x[b][j] / ||x_b||)      (feature sources of the concat, fp32)
+// A CTA owns a contiguous slice of samples; thread t owns 8 of the 2048 feature columns for the whole slice
+// (32 register accumulators), so HBM/L2 sees each feature row once, as coalesced 16-byte loads, and the result
+// leaves as one 16-byte atomic per class and 4 columns.  Every CTA recomputes the normaliser sum_b w[y_b] from
+// the labels, so dlogits leave normalised in one pass.  labels == null: dlogits are given (autograd backward).
 // ---------------------------------------------------------------------------------------------------------------
-struct Ce4Args {
+struct CeFeatArgs {
   const float* logits; const int64_t* labels; const float* cw; float eps; int batch;
-  float* dlogits;     // [B][4]
-  float* loss;        // [1], zeroed beforehand (accumulated)
+  float* dlogits;     // [B][4]: written when labels != null, read otherwise
+  float* loss;        // [1], zeroed beforehand (accumulated); CE mode only
   float* g_bf;        // [4] accumulated (null: skip)
+  const float* img; const float* txt;             // [B][1280], [B][768] raw features (null: no feature term)
+  const float* norm_img; const float* norm_txt;   // [B] L2 norms written by the forward
+  float* g_wf;        // [4][D]
+  int off_img, off_txt;                           // first concat column of each feature source
+  DropSpec drop;      // drop.D = D
 };
+constexpr int kCeChunk = 64;        // samples staged per pass
+constexpr int kFeatImg = 1280, kFeatTxt = 768;
+static_assert(kFeatImg + kFeatTxt == 8 * 256, "one thread per 8 feature columns");
 
-__global__ void __launch_bounds__(256) ce4_kernel(const Ce4Args a) {
+__global__ void __launch_bounds__(256) ce_feat_kernel(const CeFeatArgs a) {
   __shared__ float red[8];
   __shared__ float s_den;
+  __shared__ float4 dl_s[kCeChunk];
+  __shared__ float inv_s[2][kCeChunk];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool ce = a.labels != nullptr;
   float den = float(a.batch);
-  if (a.cw) {
+  if (ce && a.cw) {
     float w = 0.f;
     for (int b = tid; b < a.batch; b += 256) w += __ldg(a.cw + a.labels[b]);
     w = warp_sum(w);
@@ -49,34 +67,103 @@ __global__ void __launch_bounds__(256) ce4_kernel(const Ce4Args a) {
   }
   const float inv_den = 1.0f / den;
   float wc[4] = {1.f, 1.f, 1.f, 1.f};
-  if (a.cw) { for (int c = 0; c < 4; ++c) wc[c] = __ldg(a.cw + c); }
+  if (ce && a.cw) { for (int c = 0; c < 4; ++c) wc[c] = __ldg(a.cw + c); }
+  const int per = (a.batch + gridDim.x - 1) / gridDim.x;
+  const int s0 = blockIdx.x * per, s1 = min(a.batch, s0 + per);
+  // my 8 feature columns
+  const bool is_img = tid * 8 < kFeatImg;
+  const int j = is_img ? tid * 8 : tid * 8 - kFeatImg;
+  const int fw = is_img ? kFeatImg : kFeatTxt;
+  const float* feat = is_img ? a.img : a.txt;
+  const int cat0 = (is_img ? a.off_img : a.off_txt) + j;
+  float acc[4][8];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[c][e] = 0.f;
   float lsum = 0.f, db[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int b = blockIdx.x * 256 + tid; b < a.batch; b += gridDim.x * 256) {
-    const float4 zz = __ldg(reinterpret_cast<const float4*>(a.logits) + b);
-    float z[4] = {zz.x, zz.y, zz.z, zz.w};
-    const float m = fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3]));
-    const float se = expf(z[0] - m) + expf(z[1] - m) + expf(z[2] - m) + expf(z[3] - m);
-    const float lse = m + logf(se);
-    const int y = int(a.labels[b]);
-    float t[4], tsum = 0.f, li = 0.f;
+  for (int c0 = s0; c0 < s1; c0 += kCeChunk) {
+    const int n = min(kCeChunk, s1 - c0);
+    if (tid < n) {
+      const int b = c0 + tid;
+      float d[4];
+      if (ce) {
+        const float4 zz = __ldg(reinterpret_cast<const float4*>(a.logits) + b);
+        float z[4] = {zz.x, zz.y, zz.z, zz.w};
+        const float m = fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3]));
+        const float se = expf(z[0] - m) + expf(z[1] - m) + expf(z[2] - m) + expf(z[3] - m);
+        const float lse = m + logf(se);
+        const int y = int(a.labels[b]);
+        float t[4], tsum = 0.f, li = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          t[c] = (a.eps * 0.25f) * wc[c] + (c == y ? (1.f - a.eps) * wc[c] : 0.f);
+          z[c] -= lse;
+          li -= t[c] * z[c];
+          tsum += t[c];
+        }
+        lsum += li;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) d[c] = (expf(z[c]) * tsum - t[c]) * inv_den;
+        if (a.dlogits) reinterpret_cast<float4*>(a.dlogits)[b] = make_float4(d[0], d[1], d[2], d[3]);
+      } else {
+        const float4 dd = __ldg(reinterpret_cast<const float4*>(a.dlogits) + b);
+        d[0] = dd.x; d[1] = dd.y; d[2] = dd.z; d[3] = dd.w;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) db[c] += d[c];
+      dl_s[tid] = make_float4(d[0], d[1], d[2], d[3]);
+      if (a.g_wf) { inv_s[0][tid] = 1.0f / __ldg(a.norm_img + b); inv_s[1][tid] = 1.0f / __ldg(a.norm_txt + b); }
+    }
+    __syncthreads();
+    if (a.g_wf) {
+#pragma unroll 4
+      for (int i = 0; i < n; ++i) {
+        const int b = c0 + i;
+        const float4 x0 = __ldg(reinterpret_cast<const float4*>(feat + size_t(b) * fw + j));
+        const float4 x1 = __ldg(reinterpret_cast<const float4*>(feat + size_t(b) * fw + j + 4));
+        float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        const float inv = inv_s[is_img ? 0 : 1][i];
+        if (a.drop.thresh) {
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            float m0, m1;
+            drop_pair(a.drop, uint32_t(b), uint32_t(cat0 + e), m0, m1);
+            x[e] *= m0 * inv; x[e + 1] *= m1 * inv;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[e] *= inv;
+        }
+        const float4 d = dl_s[i];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          acc[0][e] = fmaf(d.x, x[e], acc[0][e]); acc[1][e] = fmaf(d.y, x[e], acc[1][e]);
+          acc[2][e] = fmaf(d.z, x[e], acc[2][e]); acc[3][e] = fmaf(d.w, x[e], acc[3][e]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (a.g_wf && s0 < s1) {
+    const bool vec = ((reinterpret_cast<uintptr_t>(a.g_wf) | (size_t(a.drop.D) * 4) | (size_t(cat0) * 4)) & 15) == 0;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      t[c] = (a.eps * 0.25f) * wc[c] + (c == y ? (1.f - a.eps) * wc[c] : 0.f);
-      z[c] -= lse;
-      li -= t[c] * z[c];
-      tsum += t[c];
-    }
-    lsum += li;
-    float d[4];
+      float* dst = a.g_wf + size_t(c) * a.drop.D + cat0;
+      if (vec) {
+        atomicAdd(reinterpret_cast<float4*>(dst), make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]));
+        atomicAdd(reinterpret_cast<float4*>(dst) + 1, make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]));
+      } else {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { d[c] = (expf(z[c]) * tsum - t[c]) * inv_den; db[c] += d[c]; }
-    if (a.dlogits) reinterpret_cast<float4*>(a.dlogits)[b] = make_float4(d[0], d[1], d[2], d[3]);
+        for (int e = 0; e < 8; ++e) atomicAdd(dst + e, acc[c][e]);
+      }
+    }
   }
   lsum = warp_sum(lsum);
 #pragma unroll
   for (int c = 0; c < 4; ++c) db[c] = warp_sum(db[c]);
-  if (lane == 0) {
-    if (a.loss) atomicAdd(a.loss, lsum * inv_den);
+  if (lane == 0 && warp * 32 < kCeChunk) {
+    if (ce && a.loss) atomicAdd(a.loss, lsum * inv_den);
     if (a.g_bf) { for (int c = 0; c < 4; ++c) atomicAdd(a.g_bf + c, db[c]); }
   }
 }
@@ -129,14 +216,48 @@ __device__ __forceinline__ void st_chunks16(uint8_t* op, int row, int col0, cons
   *reinterpret_cast<uint4*>(op + uint32_t(col0 >> 3) * kCS + row_off(row)) = pack_bf16x8(lo);
   *reinterpret_cast<uint4*>(op + uint32_t((col0 >> 3) + 1) * kCS + row_off(row)) = pack_bf16x8(hi);
 }
-// accumulator columns [col + c_lo, col + c_hi) of `row`'s lane -> operand columns [c_lo, c_hi)
-__device__ __forceinline__ void acc_cols_to_operand(const BwCtx& c, uint32_t col, int c_lo, int c_hi, uint8_t* op, int row) {
+// f(c0, v[16]) for the accumulator columns [c_lo, c_hi) of my lane, 16 at a time; the next 16 are in flight
+// while f runs (tcgen05.ld is asynchronous until tcgen05.wait::ld)
+template <class F>
+__device__ __forceinline__ void for_cols16(uint32_t taddr, int c_lo, int c_hi, F f) {
+  if (c_lo >= c_hi) return;
+  uint32_t nx[16];
+  tmem_ld16_nw(taddr + c_lo, nx);
 #pragma unroll 1
   for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+    tmem_wait_ld();
     float v[16];
-    ld16f(c.tmem + c.lane_base + col + c0, v);
-    st_chunks16(op, row, c0, v);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(nx[e]);
+    if (c0 + 16 < c_hi) tmem_ld16_nw(taddr + c0 + 16, nx);
+    f(c0, v);
   }
+}
+// the same over two accumulators at once: f(c0, x[16], y[16])
+template <class F>
+__device__ __forceinline__ void for_cols16x2(uint32_t ta, uint32_t tb, int c_lo, int c_hi, F f) {
+  if (c_lo >= c_hi) return;
+  uint32_t na[16], nb[16];
+  tmem_ld16_nw(ta + c_lo, na);
+  tmem_ld16_nw(tb + c_lo, nb);
+#pragma unroll 1
+  for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+    tmem_wait_ld();
+    float x[16], y[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) { x[e] = __uint_as_float(na[e]); y[e] = __uint_as_float(nb[e]); }
+    if (c0 + 16 < c_hi) { tmem_ld16_nw(ta + c0 + 16, na); tmem_ld16_nw(tb + c0 + 16, nb); }
+    f(c0, x, y);
+  }
+}
+// accumulator columns [col + c_lo, col + c_hi) of `row`'s lane -> operand columns [c_lo, c_hi)
+__device__ __forceinline__ void acc_cols_to_operand(const BwCtx& c, uint32_t col, int c_lo, int c_hi, uint8_t* op, int row) {
+  for_cols16(c.tmem + c.lane_base + col, c_lo, c_hi, [&](int c0, const float (&v)[16]) { st_chunks16(op, row, c0, v); });
+}
+__device__ __forceinline__ void mbar_wait_ph(uint64_t* bar, uint32_t& ph) {
+  mbar_wait(bar, ph);
+  ph ^= 1;
+  tc_fence_after_sync();
 }
 
 // DL[row (b,r)][(r',c)] = dlogits[b][c] [r' == r]: warpgroup w writes column groups 4w .. 4w+3 of the row
@@ -205,13 +326,10 @@ __device__ __forceinline__ void softmax16_bw(const BwCtx& c, uint32_t col_s, boo
 template <int DV>
 __device__ __forceinline__ void ln_stats_bw(const BwCtx& c, uint32_t col, float& mean, float& rstd) {
   float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll 1
-  for (int c0 = 0; c0 < DV; c0 += 16) {
-    float x[16];
-    ld16f(c.tmem + c.lane_base + col + c0, x);
+  for_cols16(c.tmem + c.lane_base + col, 0, DV, [&](int, const float (&x)[16]) {
 #pragma unroll
     for (int e = 0; e < 16; e += 2) { s0 += x[e]; s1 += x[e + 1]; q0 = fmaf(x[e], x[e], q0); q1 = fmaf(x[e + 1], x[e + 1], q1); }
-  }
+  });
   mean = (s0 + s1) * (1.0f / float(DV));
   const float var = fmaxf((q0 + q1) * (1.0f / float(DV)) - mean * mean, 0.f);
   rstd = rsqrtf(var + kLnEps);
@@ -252,6 +370,7 @@ struct CaBwdArgs {
   const void* t_tiles; const void* i_tiles;
   const float* dlogits;           // [B][4]
   int D;                          // concat width (row stride of dWf)
+  DropSpec drop;                  // concat columns of direction d: [d * 768, d * 768 + 768)
   int batch, reverse;
 };
 struct CaBwdSmem {
@@ -268,7 +387,7 @@ struct CaBwdSmem {
   static constexpr uint32_t W = al128(ONES + 4096);
   static constexpr uint32_t LN = W + CaCfg::W_BYTES;                 // gamma, beta [48] fp32
   static constexpr uint32_t BAR = al128(LN + 2 * 48 * 4);
-  static constexpr uint32_t BYTES = BAR + 64;
+  static constexpr uint32_t BYTES = BAR + 128;
   static_assert(2 * kPHalf >= op_bytes(64), "dS aliases DL");
   static_assert(BYTES <= 232448, "CA backward does not fit shared memory");
 };
@@ -280,15 +399,18 @@ struct CaBwdCols {   // TMEM columns
 __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs a) {
   extern __shared__ __align__(128) uint8_t sm[];
   using S = CaBwdSmem; using T = CaBwdCols; using C = CaCfg;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::BAR);     // [0] weights, [1] MMA, [2] tile load
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  // mbarriers: [0] weights, [1] MMAs whose result is read back next, [2] tile load,
+  //            [3] dWf / dgamma|dbeta MMAs (G2), [4] dM / dWv MMAs (G3): nobody reads those results until the flush,
+  //            they are only waited for before one of their operand buffers is overwritten
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
   float* ln_s = reinterpret_cast<float*>(sm + S::LN);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int d = blockIdx.y;
   const CaBwdDir& D = a.dir[d];
   const bool reverse = a.reverse != 0;
   if (tid == 0) {
-    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
     mbar_arrive_expect_tx(&bars[0], C::W_BYTES);
     bulk_g2s(sm + S::W, D.blobs, C::W_BYTES, &bars[0]);
@@ -307,7 +429,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
   const uint32_t tmem = *tmem_slot;
   mbar_wait(&bars[0], 0);
   BwCtx c = make_bwctx(tmem, &bars[1]);
-  uint32_t ph_ld = 0;
+  uint32_t ph_ld = 0, ph_g2 = 0, ph_g3 = 0;
   uint8_t *xq = sm + S::XQ, *xkv = sm + S::XKV, *zb = sm + S::Z, *vb = sm + S::V, *ob = sm + S::OUT, *dcb = sm + S::DC,
           *dyx = sm + S::DYX, *dls = sm + S::DLS, *pb = sm + S::P, *ones = sm + S::ONES, *wsm = sm + S::W;
   const uint8_t* bz = wsm; const uint8_t* bv = wsm + C::BZ_BYTES; const uint8_t* bc = wsm + C::BZ_BYTES + C::BV_BYTES;
@@ -315,7 +437,9 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
   bool first = true;
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int b0 = tile * 8;
-    // ---- P0: block inputs (SA images) by TMA; DL from dlogits ---------------------------------------------------
+    // ---- P0: DL from dlogits; block inputs (SA images) by TMA once the previous tile's dM / dWv MMAs are done ----
+    stage_dl(c, dls, a.dlogits, b0, a.batch);
+    if (!first) mbar_wait_ph(&bars[4], ph_g3);
     if (tid == 0) {
       const uint8_t* qsrc = static_cast<const uint8_t*>(d == 0 ? a.t_tiles : a.i_tiles) + size_t(tile) * kSaTileBytes;
       const uint8_t* ksrc = static_cast<const uint8_t*>(d == 0 ? a.i_tiles : a.t_tiles) + size_t(tile) * kSaTileBytes;
@@ -323,7 +447,6 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
       bulk_g2s(xq, qsrc, kSaTileBytes, &bars[2]);
       bulk_g2s(xkv, ksrc, kSaTileBytes, &bars[2]);
     }
-    stage_dl(c, dls, a.dlogits, b0, a.batch);
     mbar_wait(&bars[2], ph_ld); ph_ld ^= 1;
     cta_sync_for_mma();
     // ---- P1: Z, V (M=128) and dOut = DL Wf_src^T (two M=64 halves, s-mapping like C) ----------------------------
@@ -362,65 +485,72 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
       umma_commit(c.bar);
     }
     cta_wait_mma(c);
-    // ---- P6: LayerNorm / ReLU backward on my row --------------------------------------------------------------------
+    // ---- P6: LayerNorm / ReLU backward on my row: warpgroup 0 emits Out and dC, warpgroup 1 dy*xhat | dy ----------
     {
       float mean, rstd;
       ln_stats_bw<C::DV>(c, T::C, mean, rstd);
+      // self.drop (multimodal_model.py:719) sits between this block's output and the classifier: the keep bits of
+      // my row's 48 concat columns scale both what the classifier saw (Out, for dWf) and what it sends back (dOut)
+      const bool dropping = a.drop.thresh != 0;
+      const uint64_t keep = dropping ? drop_bits(a.drop, uint32_t(b0 + (c.rs >> 4)),
+                                                 uint32_t(d * kL * C::DV + (c.rs & 15) * C::DV), C::DV) : ~uint64_t(0);
+      const float dscale = dropping ? a.drop.scale : 1.0f;
       float m1a = 0.f, m1b = 0.f, m2a = 0.f, m2b = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < C::DV; c0 += 16) {
-        float x[16], g[16], o[16], t1[16], t2[16];
-        ld16f(c.tmem + c.lane_base + T::C + c0, x);
-        ld16f(c.tmem + c.lane_base + T::DOUT + c0, g);
+      const uint32_t tc_ = c.tmem + c.lane_base + T::C, tg_ = c.tmem + c.lane_base + T::DOUT;
+      for_cols16x2(tc_, tg_, 0, C::DV, [&](int c0, const float (&x)[16], const float (&g)[16]) {
+        float o[16], t1[16], t2[16];
+        const uint32_t kb = uint32_t(keep >> c0);
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const float gam = ln_s[c0 + e];
           const float xh = (x[e] - mean) * rstd;
           const float y = fmaf(xh, gam, ln_s[48 + c0 + e]);
-          const float dy = y > 0.f ? g[e] : 0.f;
+          const float mk = (kb >> e) & 1u ? dscale : 0.f;
+          const float dy = y > 0.f ? g[e] * mk : 0.f;
           const float dxh = dy * gam;
           if (e & 1) { m1b += dxh; m2b = fmaf(dxh, xh, m2b); } else { m1a += dxh; m2a = fmaf(dxh, xh, m2a); }
-          o[e] = fmaxf(y, 0.f); t1[e] = dy * xh; t2[e] = dy;
+          o[e] = fmaxf(y, 0.f) * mk; t1[e] = dy * xh; t2[e] = dy;
         }
         if (c.w == 0) st_chunks16(ob, c.rs, c0, o);
         else { st_chunks16(dyx, c.rs, c0, t1); st_chunks16(dyx, c.rs, C::DV + c0, t2); }
-      }
+      });
       if (c.w == 0) {
         const float m1 = (m1a + m1b) * (1.0f / float(C::DV)), m2 = (m2a + m2b) * (1.0f / float(C::DV));
-#pragma unroll 1
-        for (int c0 = 0; c0 < C::DV; c0 += 16) {
-          float x[16], g[16], o[16];
-          ld16f(c.tmem + c.lane_base + T::C + c0, x);
-          ld16f(c.tmem + c.lane_base + T::DOUT + c0, g);
+        for_cols16x2(tc_, tg_, 0, C::DV, [&](int c0, const float (&x)[16], const float (&g)[16]) {
+          float o[16];
+          const uint32_t kb = uint32_t(keep >> c0);
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
             const float gam = ln_s[c0 + e];
             const float xh = (x[e] - mean) * rstd;
             const float y = fmaf(xh, gam, ln_s[48 + c0 + e]);
-            const float dxh = y > 0.f ? g[e] * gam : 0.f;
+            const float mk = (kb >> e) & 1u ? dscale : 0.f;
+            const float dxh = y > 0.f ? g[e] * mk * gam : 0.f;
             o[e] = rstd * (dxh - m1 - xh * m2);
           }
           st_chunks16(dcb, c.rs, c0, o);
-        }
+        });
       }
     }
     cta_sync_for_mma();
-    // ---- P7: dP; classifier-weight and LayerNorm-affine gradients into their persistent accumulators ----------
+    // ---- P7: dP (read back next); classifier-weight and LayerNorm-affine gradients (persistent, group G2) ------
     if (tid == 0) {
       for (int h = 0; h < 2; ++h)
         mma_steps(tmem + (uint32_t(16 * h) << 16) + T::DP, make_smem_desc(smem_u32(dcb + h * 8 * kRS), kCS, kRS), 2 * kCS,
                   make_smem_desc(smem_u32(vb + h * 8 * kRS), kCS, kRS), 2 * kCS, make_idesc_bf16(64, 64, 0, 0), C::DV / 16, false);
+      umma_commit(c.bar);
       mma_steps(tmem + T::G_WF, make_smem_desc(smem_u32(ob), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(dls), kRS, kCS), 2 * kRS,
                 make_idesc_bf16(64, kNCls, 1, 1), 8, !first);
       mma_steps(tmem + T::G_LN, make_smem_desc(smem_u32(dyx), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(ones), 256, 128), 512,
                 make_idesc_bf16(128, 16, 1, 0), 8, !first);
-      umma_commit(c.bar);
+      umma_commit(&bars[3]);
     }
     cta_wait_mma(c);
-    // ---- P8: softmax backward -> dS (reuses DL's bytes: rewrite every column group of my row) ------------------
+    // ---- P8: softmax backward -> dS (reuses DL's bytes once G2 has read them) ----------------------------------------
     {
       float ds[16];
       softmax_bwd16(c, T::DP, reverse, p, ds);
+      mbar_wait_ph(&bars[3], ph_g2);
       store_half_row_split(c, dls, ds, true);
     }
     cta_sync_for_mma();
@@ -439,12 +569,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
     if (c.w == 0) acc_cols_to_operand(c, T::DZ, 0, 80, dyx, c.rs);
     else { acc_cols_to_operand(c, T::DZ, 80, 96, dyx, c.rs); acc_cols_to_operand(c, T::DV, 0, 48, vb, c.rs); }
     cta_sync_for_mma();
-    // ---- P11: parameter gradients (persistent) and the gradients of the block inputs -----------------------------
+    // ---- P11: gradients of the block inputs (read back next), then the parameter gradients (persistent, G3) ------
     if (tid == 0) {
-      mma_steps(tmem + T::G_M, make_smem_desc(smem_u32(xq), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(dyx), kRS, kCS), 2 * kRS,
-                make_idesc_bf16(128, C::DIN, 1, 1), 8, !first);
-      mma_steps(tmem + T::G_WV, make_smem_desc(smem_u32(xkv), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(vb), kRS, kCS), 2 * kRS,
-                make_idesc_bf16(128, C::DV, 1, 1), 8, !first);
       // dXq = dZ M^T  (B: the Z blob read along its other axis)
       mma_steps(tmem + T::DXQ, make_smem_desc(smem_u32(dyx), kCS, kRS), 2 * kCS, make_smem_desc(smem_u32(bz), 128, C::BZ_LBO), 2 * 128,
                 make_idesc_bf16(128, C::DIN, 0, 1), C::DIN / 16, false);
@@ -456,6 +582,11 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
                   make_smem_desc(smem_u32(bv), 128, C::BV_LBO), 2 * 128, make_idesc_bf16(64, C::DIN, 0, 1), C::DV / 16, true);
       }
       umma_commit(c.bar);
+      mma_steps(tmem + T::G_M, make_smem_desc(smem_u32(xq), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(dyx), kRS, kCS), 2 * kRS,
+                make_idesc_bf16(128, C::DIN, 1, 1), 8, !first);
+      mma_steps(tmem + T::G_WV, make_smem_desc(smem_u32(xkv), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(vb), kRS, kCS), 2 * kRS,
+                make_idesc_bf16(128, C::DV, 1, 1), 8, !first);
+      umma_commit(&bars[4]);
     }
     cta_wait_mma(c);
     // ---- P12: input gradients -> bf16 images for the SA backward ---------------------------------------------------
@@ -473,6 +604,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
   }
   // ---- flush the persistent accumulators ---------------------------------------------------------------------------
   if (!first) {
+    mbar_wait_ph(&bars[4], ph_g3);
     flush_acc(c, T::G_M, C::DIN, C::DIN + 1, [&](int m, int n) { return D.gm + size_t(n) * 128 + m; });
     flush_acc(c, T::G_WV, C::DV, C::DIN + 1,
               [&](int m, int n) { return m < C::DIN ? D.g_wv + size_t(n) * C::DIN + m : D.g_bv + n; });
@@ -512,10 +644,8 @@ struct SaBwdArgs {
   const void* blobs;              // bz | bv | bc
   const float* ln_g; const float* ln_b;
   const void* dout_a; const void* dout_b;   // dOut = a + b (images written by ca_bwd_kernel)
-  const float* dlogits;           // [B][4] or null (classifier does not see the features)
   float* gm;                      // [DIN][128]
   float* g_wv; float* g_bv; float* g_ln_g; float* g_ln_b;
-  float* g_wf; int D;             // classifier rows of the feature source
   int batch;
 };
 template <int DIN_>
@@ -527,18 +657,18 @@ struct SaBwdSmem {
   static constexpr uint32_t V = ZP + ZP_BYTES;                       // [128 x 96]; later dV
   static constexpr uint32_t DC = V + op_bytes(96);                   // [128 x 96]
   static constexpr uint32_t DYX = DC + op_bytes(96);                 // [128 x 192]: dy*xhat | dy; later dZ [128 x DIN]
-  static constexpr uint32_t DLS = DYX + op_bytes(192);               // DL; later dS
+  static constexpr uint32_t DLS = DYX + op_bytes(192);               // dS (2 x [64 x 64])
   static constexpr uint32_t ONES = DLS + 2 * kPHalf;
   static constexpr uint32_t W = al128(ONES + 4096);
   static constexpr uint32_t LN = W + C::W_BYTES;
   static constexpr uint32_t BAR = al128(LN + 2 * 96 * 4);
-  static constexpr uint32_t BYTES = BAR + 64;
+  static constexpr uint32_t BYTES = BAR + 128;
   static_assert(BYTES <= 232448, "SA backward does not fit shared memory");
 };
 template <int DIN_>
 struct SaBwdCols {
   static constexpr uint32_t Z = 0, V = DIN_, S = 0, C = 64, DP = 0, DV = 0, DZ = 96;   // working: [0, 176)
-  static constexpr uint32_t G_M = 176, G_WV = G_M + DIN_, G_WF = G_WV + 96, G_LN = G_WF + 64;  // G_LN: 2 x 16 columns
+  static constexpr uint32_t G_M = 176, G_WV = G_M + DIN_, G_LN = G_WV + 96;  // G_LN: 2 x 16 columns
   static_assert(G_LN + 32 <= 512, "TMEM budget");
 };
 
@@ -547,12 +677,14 @@ __global__ void __launch_bounds__(kCtaThreads, 1) sa_bwd_kernel(const SaBwdArgs 
   extern __shared__ __align__(128) uint8_t sm[];
   using S = SaBwdSmem<DIN_>; using T = SaBwdCols<DIN_>; using C = SaCfg<DIN_>;
   constexpr int DIN = DIN_, DV = C::DV;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::BAR);     // [0] weights, [1] MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  // mbarriers: [0] weights, [1] MMAs read back next, [2] dOut images (TMA), [3] unused, [4] G2: dgamma|dbeta,
+  //            [5] G3: dM, dWv  (G*: persistent accumulators, waited for only before an operand buffer is reused)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
   float* ln_s = reinterpret_cast<float*>(sm + S::LN);
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
-    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+    for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
     mbar_arrive_expect_tx(&bars[0], C::W_BYTES);
     bulk_g2s(sm + S::W, a.blobs, C::W_BYTES, &bars[0]);
@@ -567,16 +699,16 @@ __global__ void __launch_bounds__(kCtaThreads, 1) sa_bwd_kernel(const SaBwdArgs 
   const uint32_t tmem = *tmem_slot;
   mbar_wait(&bars[0], 0);
   BwCtx c = make_bwctx(tmem, &bars[1]);
+  uint32_t ph_ld = 0, ph_g2 = 0, ph_g3 = 0;
   uint8_t *xb = sm + S::X, *zp = sm + S::ZP, *vb = sm + S::V, *dcb = sm + S::DC, *dyx = sm + S::DYX, *dls = sm + S::DLS,
           *ones = sm + S::ONES, *wsm = sm + S::W;
-  const uint8_t* bz = wsm; const uint8_t* bv = wsm + C::BZ_BYTES; const uint8_t* bc = wsm + C::BZ_BYTES + C::BV_BYTES;
-  (void)bc;
-  const bool cls = a.dlogits != nullptr;
+  const uint8_t* bz = wsm; const uint8_t* bv = wsm + C::BZ_BYTES;
   const int tiles = (a.batch + 7) / 8;
   bool first = true;
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int b0 = tile * 8;
-    // ---- P0: features -> normalised bf16 operand (8 warps, one sample each); DL ------------------------------------
+    // ---- P0: features -> normalised bf16 operand (8 warps, one sample each).  The global loads are issued before
+    //      waiting for the previous tile's dM / dWv MMAs (G3), which still read the operand buffers. -----------------
     {
       constexpr int KCS = DIN / 8, ITEMS = kL * KCS, PER = (ITEMS + 31) / 32;
       const int g = warp, b = b0 + g;
@@ -592,6 +724,20 @@ __global__ void __launch_bounds__(kCtaThreads, 1) sa_bwd_kernel(const SaBwdArgs 
           hi = __ldg(reinterpret_cast<const float4*>(base + it * 8 + 4));
         }
         v[k][0] = lo.x; v[k][1] = lo.y; v[k][2] = lo.z; v[k][3] = lo.w; v[k][4] = hi.x; v[k][5] = hi.y; v[k][6] = hi.z; v[k][7] = hi.w;
+      }
+      {   // next tile of this CTA -> L2
+        const int nb0 = (tile + int(gridDim.x)) * 8;
+        const size_t off = size_t(nb0) * (kL * DIN) + size_t(tid) * 32;
+        if (nb0 + 8 <= a.batch && tid * 32 < 8 * kL * DIN) {
+          prefetch_l2(a.feat + off);
+          if (tid * 32 + 256 * 32 < 8 * kL * DIN) prefetch_l2(a.feat + off + 256 * 32);
+        }
+      }
+      if (!first) mbar_wait_ph(&bars[5], ph_g3);
+      if (tid == 0) {     // dOut images of this tile -> the (now free) dy*xhat | dy buffer
+        mbar_arrive_expect_tx(&bars[2], 2 * kSaTileBytes);
+        bulk_g2s(dyx, static_cast<const uint8_t*>(a.dout_a) + size_t(tile) * kSaTileBytes, kSaTileBytes, &bars[2]);
+        bulk_g2s(dyx + kSaTileBytes, static_cast<const uint8_t*>(a.dout_b) + size_t(tile) * kSaTileBytes, kSaTileBytes, &bars[2]);
       }
 #pragma unroll
       for (int k = 0; k < PER; ++k)
@@ -610,19 +756,15 @@ __global__ void __launch_bounds__(kCtaThreads, 1) sa_bwd_kernel(const SaBwdArgs 
         *reinterpret_cast<uint4*>(xb + uint32_t(kc) * kCS + row_off(g * kL + row)) = pack_bf16x8(o);
       }
       if (tid < 128) write_bias_columns(xb, KCS, tid);
-      if (cls) stage_dl(c, dls, a.dlogits, b0, a.batch);
     }
     cta_sync_for_mma();
-    // ---- P1: Z, V; classifier-weight gradient of the feature source dWf^T += X^T DL --------------------------------
+    // ---- P1: Z, V ------------------------------------------------------------------------------------------------------
     if (tid == 0) {
       const uint64_t ax = make_smem_desc(smem_u32(xb), kCS, kRS);
       mma_steps(tmem + T::Z, ax, 2 * kCS, make_smem_desc(smem_u32(bz), C::BZ_LBO, 128), 2 * C::BZ_LBO,
                 make_idesc_bf16(128, DIN, 0, 0), C::KE / 16, false);
       mma_steps(tmem + T::V, ax, 2 * kCS, make_smem_desc(smem_u32(bv), C::BV_LBO, 128), 2 * C::BV_LBO,
                 make_idesc_bf16(128, DV, 0, 0), C::KE / 16, false);
-      if (cls)
-        mma_steps(tmem + T::G_WF, make_smem_desc(smem_u32(xb), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(dls), kRS, kCS), 2 * kRS,
-                  make_idesc_bf16(128, kNCls, 1, 1), 8, !first);
       umma_commit(c.bar);
     }
     cta_wait_mma(c);
@@ -650,26 +792,50 @@ __global__ void __launch_bounds__(kCtaThreads, 1) sa_bwd_kernel(const SaBwdArgs 
       umma_commit(c.bar);
     }
     cta_wait_mma(c);
-    // ---- LayerNorm / ReLU backward; dOut = sum of the two images written by the CA backward ----------------------
+    // ---- LayerNorm / ReLU backward.  dOut = image a + image b (written by the CA backward) sits in shared memory
+    //      where dy*xhat | dy will go: every thread first reads its whole row (statistics), then, after a CTA
+    //      barrier, rewrites its own half of the columns in place. -------------------------------------------------
     {
+      mbar_wait(&bars[2], ph_ld); ph_ld ^= 1;
       float mean, rstd;
       ln_stats_bw<DV>(c, T::C, mean, rstd);
-      const uint8_t* ga = static_cast<const uint8_t*>(a.dout_a) + size_t(tile) * kSaTileBytes + row_off(c.rs);
-      const uint8_t* gb = static_cast<const uint8_t*>(a.dout_b) + size_t(tile) * kSaTileBytes + row_off(c.rs);
+      uint8_t* ga = dyx + row_off(c.rs);
+      uint8_t* gb = dyx + kSaTileBytes + row_off(c.rs);
+      const uint32_t tc_ = c.tmem + c.lane_base + T::C;
       float m1a = 0.f, m1b = 0.f, m2a = 0.f, m2b = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < DV; c0 += 16) {
-        float x[16], g[16], t1[16], t2[16];
+      for_cols16(tc_, 0, DV, [&](int c0, const float (&x)[16]) {
+        float g[16];
         {
           float f0[8], f1[8], f2[8], f3[8];
-          unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(ga + uint32_t(c0 >> 3) * kCS)), f0);
-          unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(gb + uint32_t(c0 >> 3) * kCS)), f1);
-          unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(ga + uint32_t((c0 >> 3) + 1) * kCS)), f2);
-          unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(gb + uint32_t((c0 >> 3) + 1) * kCS)), f3);
+          unpack_bf16x8(*reinterpret_cast<const uint4*>(ga + uint32_t(c0 >> 3) * kCS), f0);
+          unpack_bf16x8(*reinterpret_cast<const uint4*>(gb + uint32_t(c0 >> 3) * kCS), f1);
+          unpack_bf16x8(*reinterpret_cast<const uint4*>(ga + uint32_t((c0 >> 3) + 1) * kCS), f2);
+          unpack_bf16x8(*reinterpret_cast<const uint4*>(gb + uint32_t((c0 >> 3) + 1) * kCS), f3);
 #pragma unroll
           for (int e = 0; e < 8; ++e) { g[e] = f0[e] + f1[e]; g[8 + e] = f2[e] + f3[e]; }
         }
-        ld16f(c.tmem + c.lane_base + T::C + c0, x);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float gam = ln_s[c0 + e];
+          const float xh = (x[e] - mean) * rstd;
+          const float y = fmaf(xh, gam, ln_s[DV + c0 + e]);
+          const float dxh = y > 0.f ? g[e] * gam : 0.f;
+          if (e & 1) { m1b += dxh; m2b = fmaf(dxh, xh, m2b); } else { m1a += dxh; m2a = fmaf(dxh, xh, m2a); }
+        }
+      });
+      __syncthreads();
+      const float m1 = (m1a + m1b) * (1.0f / float(DV)), m2 = (m2a + m2b) * (1.0f / float(DV));
+      for_cols16(tc_, 48 * c.w, 48 * c.w + 48, [&](int c0, const float (&x)[16]) {
+        float g[16], o[16], t1[16], t2[16];
+        {
+          float f0[8], f1[8], f2[8], f3[8];
+          unpack_bf16x8(*reinterpret_cast<const uint4*>(ga + uint32_t(c0 >> 3) * kCS), f0);
+          unpack_bf16x8(*reinterpret_cast<const uint4*>(gb + uint32_t(c0 >> 3) * kCS), f1);
+          unpack_bf16x8(*reinterpret_cast<const uint4*>(ga + uint32_t((c0 >> 3) + 1) * kCS), f2);
+          unpack_bf16x8(*reinterpret_cast<const uint4*>(gb + uint32_t((c0 >> 3) + 1) * kCS), f3);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { g[e] = f0[e] + f1[e]; g[8 + e] = f2[e] + f3[e]; }
+        }
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const float gam = ln_s[c0 + e];
@@ -677,48 +843,25 @@ __global__ void __launch_bounds__(kCtaThreads, 1) sa_bwd_kernel(const SaBwdArgs 
           const float y = fmaf(xh, gam, ln_s[DV + c0 + e]);
           const float dy = y > 0.f ? g[e] : 0.f;
           const float dxh = dy * gam;
-          if (e & 1) { m1b += dxh; m2b = fmaf(dxh, xh, m2b); } else { m1a += dxh; m2a = fmaf(dxh, xh, m2a); }
+          o[e] = rstd * (dxh - m1 - xh * m2);
           t1[e] = dy * xh; t2[e] = dy;
         }
-        if (c.w == 1) { st_chunks16(dyx, c.rs, c0, t1); st_chunks16(dyx, c.rs, DV + c0, t2); }
-      }
-      if (c.w == 0) {
-        const float m1 = (m1a + m1b) * (1.0f / float(DV)), m2 = (m2a + m2b) * (1.0f / float(DV));
-#pragma unroll 1
-        for (int c0 = 0; c0 < DV; c0 += 16) {
-          float x[16], g[16], o[16];
-          {
-            float f0[8], f1[8], f2[8], f3[8];
-            unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(ga + uint32_t(c0 >> 3) * kCS)), f0);
-            unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(gb + uint32_t(c0 >> 3) * kCS)), f1);
-            unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(ga + uint32_t((c0 >> 3) + 1) * kCS)), f2);
-            unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(gb + uint32_t((c0 >> 3) + 1) * kCS)), f3);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { g[e] = f0[e] + f1[e]; g[8 + e] = f2[e] + f3[e]; }
-          }
-          ld16f(c.tmem + c.lane_base + T::C + c0, x);
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float gam = ln_s[c0 + e];
-            const float xh = (x[e] - mean) * rstd;
-            const float y = fmaf(xh, gam, ln_s[DV + c0 + e]);
-            const float dxh = y > 0.f ? g[e] * gam : 0.f;
-            o[e] = rstd * (dxh - m1 - xh * m2);
-          }
-          st_chunks16(dcb, c.rs, c0, o);
-        }
-      }
+        st_chunks16(dcb, c.rs, c0, o);
+        st_chunks16(dyx, c.rs, c0, t1);            // over image a's chunks of my row
+        st_chunks16(dyx, c.rs, DV + c0, t2);       // over image b's (DV columns = one image)
+      });
     }
     cta_sync_for_mma();
-    // ---- dP; LayerNorm-affine gradients (M = 192 = two M=128 MMAs over the [dy*xhat | dy] operand) ----------------
+    // ---- dP (read back next); then (G2) the LayerNorm-affine gradients: M = 192 = two M=128 MMAs ------------------
     if (tid == 0) {
       for (int h = 0; h < 2; ++h)
         mma_steps(tmem + (uint32_t(16 * h) << 16) + T::DP, make_smem_desc(smem_u32(dcb + h * 8 * kRS), kCS, kRS), 2 * kCS,
                   make_smem_desc(smem_u32(vb + h * 8 * kRS), kCS, kRS), 2 * kCS, make_idesc_bf16(64, 64, 0, 0), DV / 16, false);
+      umma_commit(c.bar);
       for (int mt = 0; mt < 2; ++mt)
         mma_steps(tmem + T::G_LN + 16 * mt, make_smem_desc(smem_u32(dyx + mt * 16 * kCS), kRS, kCS), 2 * kRS,
                   make_smem_desc(smem_u32(ones), 256, 128), 512, make_idesc_bf16(128, 16, 1, 0), 8, !first);
-      umma_commit(c.bar);
+      umma_commit(&bars[4]);
     }
     cta_wait_mma(c);
     {
@@ -737,27 +880,23 @@ __global__ void __launch_bounds__(kCtaThreads, 1) sa_bwd_kernel(const SaBwdArgs 
       umma_commit(c.bar);
     }
     cta_wait_mma(c);
+    mbar_wait_ph(&bars[4], ph_g2);                 // dgamma|dbeta have read dy*xhat | dy: its bytes become dZ
     if (c.w == 0) { acc_cols_to_operand(c, T::DZ, 0, DIN, dyx, c.rs); acc_cols_to_operand(c, T::DV, 0, 16, vb, c.rs); }
     else acc_cols_to_operand(c, T::DV, 16, 96, vb, c.rs);
     cta_sync_for_mma();
-    if (tid == 0) {
+    if (tid == 0) {       // G3: nobody waits for these before the next tile's feature loads are in flight
       mma_steps(tmem + T::G_M, make_smem_desc(smem_u32(xb), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(dyx), kRS, kCS), 2 * kRS,
                 make_idesc_bf16(128, DIN, 1, 1), 8, !first);
       mma_steps(tmem + T::G_WV, make_smem_desc(smem_u32(xb), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(vb), kRS, kCS), 2 * kRS,
                 make_idesc_bf16(128, DV, 1, 1), 8, !first);
-      umma_commit(c.bar);
+      umma_commit(&bars[5]);
     }
-    cta_wait_mma(c);
     first = false;
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
   }
   if (!first) {
+    mbar_wait_ph(&bars[5], ph_g3);
     flush_acc(c, T::G_M, DIN, DIN + 1, [&](int m, int n) { return a.gm + size_t(n) * 128 + m; });
     flush_acc(c, T::G_WV, DV, DIN + 1, [&](int m, int n) { return m < DIN ? a.g_wv + size_t(n) * DIN + m : a.g_bv + n; });
-    if (cls)
-      flush_acc(c, T::G_WF, kNCls, DIN, [&](int m, int n) { return a.g_wf + size_t(n & 3) * a.D + (n >> 2) * DIN + m; });
     {
       float v[16];
       ld16f(c.tmem + c.lane_base + T::G_LN + 16 * c.w, v);

@@ -121,13 +121,24 @@ def _head_struct(tensors: Sequence[Optional[torch.Tensor]]) -> N.HeadParams:
     return hp
 
 
-def _desc(batch: int, d_img: int, d_txt: int, n_classes: int, flags: int, compute: int) -> N.HeadDesc:
-    return N.HeadDesc(batch, d_img, d_txt, n_classes, flags, compute)
+def _desc(batch: int, d_img: int, d_txt: int, n_classes: int, flags: int, compute: int,
+          drop_p: float = 0.0, drop_seed: int = 0) -> N.HeadDesc:
+    return N.HeadDesc(batch, d_img, d_txt, n_classes, flags, compute, float(drop_p), int(drop_seed) & (2 ** 64 - 1))
+
+
+def dropout_mask(seed: int, p: float, batch: int, width: int, device) -> torch.Tensor:
+    """uint8 keep-mask [batch, width] the seeded dropout of the head draws for (seed, p) — what the kernels
+    regenerate on chip (mmrca_dropout.cuh); for the fp32 kernels, parity tests and debugging."""
+    out = torch.empty(batch, width, dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        N.check(N.lib().mmrca_dropout_mask(int(seed) & (2 ** 64 - 1), float(p), batch, width, out.data_ptr(),
+                                           _stream_ptr(device)), "mmrca_dropout_mask")
+    return out
 
 
 def workspace_bytes(batch: int, d_img: int, d_txt: int, n_classes: int, flags: int, compute: int,
-                    training: bool) -> int:
-    d = _desc(batch, d_img, d_txt, n_classes, flags, compute)
+                    training: bool, drop_p: float = 0.0) -> int:
+    d = _desc(batch, d_img, d_txt, n_classes, flags, compute, drop_p)
     return int(N.lib().mmrca_head_workspace_bytes(C.byref(d), 1 if training else 0))
 
 
@@ -154,7 +165,7 @@ class _HeadFunction(torch.autograd.Function):
     """logits = MM_RCA head(img_feat, txt_feat); backward recomputes attention internals on chip."""
 
     @staticmethod
-    def forward(ctx, img, txt, drop_mask, drop_scale, flags, n_classes, compute, *params):
+    def forward(ctx, img, txt, drop_mask, drop_scale, flags, n_classes, compute, drop_p, drop_seed, *params):
         img = _check_dev(img, "image features")
         txt = _check_dev(txt, "text features")
         params = [_check_dev(p, "head parameter") for p in params]
@@ -166,14 +177,14 @@ class _HeadFunction(torch.autograd.Function):
         needs_bwd = any(ctx.needs_input_grad)
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             flags |= N.FLAG_FEATURE_GRADS      # fine-tune phase: the backward must return feature gradients
-        desc = _desc(B, d_img, d_txt, n_classes, flags, compute)
+        desc = _desc(B, d_img, d_txt, n_classes, flags, compute, drop_p, drop_seed)
         L = N.lib()
         ws = torch.empty(max(1, L.mmrca_head_workspace_bytes(C.byref(desc), 1 if needs_bwd else 0)),
                          dtype=torch.uint8, device=img.device)
         logits = torch.empty(B, n_classes, dtype=torch.float32, device=img.device)
         hp = _head_struct(params)
         ctx.save_for_backward(img, txt, drop_mask, ws, *params)
-        ctx.cfg = (drop_scale, flags, n_classes, compute)
+        ctx.cfg = (drop_scale, flags, n_classes, compute, drop_p, drop_seed)
         if B == 0:      # empty shard: nothing to launch (a zero-size tensor has a null data pointer)
             return logits
         with torch.cuda.device(img.device):
@@ -186,10 +197,10 @@ class _HeadFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits):
         img, txt, drop_mask, ws, *params = ctx.saved_tensors
-        drop_scale, flags, n_classes, compute = ctx.cfg
+        drop_scale, flags, n_classes, compute, drop_p, drop_seed = ctx.cfg
         dlogits = _check_dev(dlogits, "dlogits")
         B = img.shape[0]
-        desc = _desc(B, img.shape[1], txt.shape[1], n_classes, flags, compute)
+        desc = _desc(B, img.shape[1], txt.shape[1], n_classes, flags, compute, drop_p, drop_seed)
         fg = FlatGrads(params)
         want_feat = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         d_img = torch.empty_like(img) if want_feat else None
@@ -206,25 +217,30 @@ class _HeadFunction(torch.autograd.Function):
         features_only = bool(flags & N.FLAG_FEATURES_ONLY)
         pg = []
         for i, v in enumerate(fg.views):
-            need = ctx.needs_input_grad[7 + i]
+            need = ctx.needs_input_grad[9 + i]
             # features_only: the attention blocks are outside the graph in the reference (their result is
             # discarded, multimodal_model.py:676-699) -> grad None, like autograd there.
             pg.append(v if need and not (features_only and i < 32) else None)
         return (d_img if ctx.needs_input_grad[0] else None, d_txt if ctx.needs_input_grad[1] else None,
-                None, None, None, None, None, *pg)
+                None, None, None, None, None, None, None, *pg)
 
 
 def mmrca_head(img_feat: torch.Tensor, txt_feat: torch.Tensor, params: Sequence[torch.Tensor], *,
                reverse: bool, features_only: bool = False, cross_attention_only: bool = False,
                n_classes: int = 4, drop_mask: Optional[torch.Tensor] = None, drop_scale: float = 1.0,
-               compute: int = N.COMPUTE_FP32) -> torch.Tensor:
+               drop_p: float = 0.0, drop_seed: int = 0, compute: int = N.COMPUTE_FP32) -> torch.Tensor:
     """Fusion head of MM_RCA.forward (reference multimodal_model.py:661-728) on pooled features.
 
     params: the 34 tensors in head_param_names(features_only, cross_attention_only) order.
-    drop_mask: uint8 keep-mask [B, D] standing in for self.drop (:719), kept values scaled by drop_scale.
+    self.drop (:719), two ways:
+      drop_p > 0 (+ drop_seed): the kernels draw the keep mask themselves (dropout_mask() returns the same mask);
+      drop_mask: a caller-drawn uint8 keep-mask [B, D], kept values scaled by drop_scale (fp32 kernels).
     """
     flags = make_flags(reverse, features_only, cross_attention_only)
-    return _HeadFunction.apply(img_feat, txt_feat, drop_mask, drop_scale, flags, n_classes, compute, *params)
+    if drop_mask is not None:
+        drop_p, drop_seed = 0.0, 0
+    return _HeadFunction.apply(img_feat, txt_feat, drop_mask, drop_scale, flags, n_classes, compute,
+                               float(drop_p), int(drop_seed), *params)
 
 
 def cross_entropy(logits: torch.Tensor, labels: torch.Tensor, class_weight: Optional[torch.Tensor] = None,
@@ -256,11 +272,11 @@ class HeadTrainStep:
     def __init__(self, params: Sequence[torch.Tensor], batch: int, d_img: int, d_txt: int, *, reverse: bool,
                  features_only: bool = False, cross_attention_only: bool = False, n_classes: int = 4,
                  class_weight: Optional[torch.Tensor] = None, label_smoothing: float = 0.0,
-                 compute: int = N.COMPUTE_FP32, feature_grads: bool = False):
+                 compute: int = N.COMPUTE_FP32, feature_grads: bool = False, drop_p: float = 0.0):
         self.params = [_check_dev(p.detach(), "head parameter") for p in params]
         dev = self.params[0].device
         self.flags = make_flags(reverse, features_only, cross_attention_only) | (N.FLAG_FEATURE_GRADS if feature_grads else 0)
-        self.desc = _desc(batch, d_img, d_txt, n_classes, self.flags, compute)
+        self.desc = _desc(batch, d_img, d_txt, n_classes, self.flags, compute, drop_p, 0)
         self.grads = FlatGrads(self.params)
         self.hp, self.hg = _head_struct(self.params), _head_struct(self.grads.views)
         L = N.lib()
@@ -278,7 +294,9 @@ class HeadTrainStep:
         self.grads.zero_()
 
     def __call__(self, img: torch.Tensor, txt: torch.Tensor, labels: torch.Tensor,
-                 drop_mask: Optional[torch.Tensor] = None, drop_scale: float = 1.0):
+                 drop_mask: Optional[torch.Tensor] = None, drop_scale: float = 1.0, drop_seed: int = 0):
+        """drop_seed: seed of this step's dropout mask when the step was built with drop_p > 0."""
+        self.desc.drop_seed = int(drop_seed) & (2 ** 64 - 1)
         img, txt = _check_dev(img, "image features"), _check_dev(txt, "text features")
         labels = _check_dev(labels, "labels", torch.int64)
         if img.shape != (self.desc.batch, self.desc.d_img) or txt.shape != (self.desc.batch, self.desc.d_txt):

@@ -100,7 +100,8 @@ def decision(probability: float) -> bool:
 
 
 # ---------------------------------------------------------------------------------------------
-# attention blocks: parameter holders whose forward is one fused CUDA kernel
+# attention blocks: parameter holders; called on their own they run one fused fp32 CUDA kernel each (the bf16
+# tensor-core pipeline exists as the whole fused head, MM_RCA.forward_features)
 # ---------------------------------------------------------------------------------------------
 class _AttentionBase(nn.Module):
     def __init__(self, d_in_q: int, d_in_kv: int, d_out_kq: int, d_out_v: int):
@@ -111,7 +112,6 @@ class _AttentionBase(nn.Module):
         self.W_value = nn.Linear(d_in_kv, d_out_v)
         self.norm = nn.LayerNorm(d_out_v)
         self.relu = nn.ReLU()
-        self.compute = N.COMPUTE_FP32
 
     def _params(self) -> Tuple[torch.Tensor, ...]:
         return (self.W_query.weight, self.W_query.bias, self.W_key.weight, self.W_key.bias,
@@ -126,7 +126,7 @@ class SelfAttention(_AttentionBase):
         self.name = name
 
     def forward(self, x):
-        return F.attention_block(x, None, self._params(), reverse=False, compute=self.compute)
+        return F.attention_block(x, None, self._params(), reverse=False)
 
 
 class ReverseCrossAttention(_AttentionBase):
@@ -140,7 +140,7 @@ class ReverseCrossAttention(_AttentionBase):
     def forward(self, x_1, x_2):
         if x_1.shape[1] != x_2.shape[1]:
             raise AssertionError("ReverseCrossAttention needs square attention (reference :93)")
-        return F.attention_block(x_1, x_2, self._params(), reverse=bool(self.reverse), compute=self.compute)
+        return F.attention_block(x_1, x_2, self._params(), reverse=bool(self.reverse))
 
 
 class Hadamard2(nn.Module):
@@ -250,9 +250,6 @@ class EffV2MediumAndDistilbertGated(nn.Module):
                 self.logit_scale = nn.Parameter(torch.ones([]) * np.log(1 / 0.07))   # reference :244-245
                 continue
             setattr(self, name, factory())
-        for blk in (self.self_attention_image, self.self_attention_text, self.cross_attention_1,
-                    self.cross_attention_2):
-            blk.compute = compute
         self._head_names = F.head_param_names(bool(features_only), bool(cross_attention_only))
 
     # ---- helpers the drivers call (reference :397-418) -------------------------------------------
@@ -325,14 +322,16 @@ def _quiet_gru(inp, hid):
 class MM_RCA(EffV2MediumAndDistilbertGated):
     """Multimodal reverse-cross-attention classifier (reference :636-728)."""
 
-    def _dropout_mask(self, batch: int, width: int, device) -> Tuple[Optional[torch.Tensor], float]:
+    def _dropout_seed(self) -> Tuple[float, int]:
+        """(p, seed) of this forward's dropout (self.drop, reference :190/:719).  The seed comes from torch's
+        CPU generator (or `dropout_generator`), so torch.manual_seed makes training runs repeatable; the keep
+        mask itself is drawn inside the kernels (F.dropout_mask(seed, p, ...) returns it)."""
         p = float(self.drop.p)
         if not self.training or p <= 0.0:
-            return None, 1.0
-        if p >= 1.0:
-            return torch.zeros(batch, width, dtype=torch.uint8, device=device), 0.0
-        keep = torch.rand(batch, width, device=device, generator=self.dropout_generator) >= p
-        return keep.to(torch.uint8), 1.0 / (1.0 - p)
+            return 0.0, 0
+        seed = int(torch.randint(0, 2 ** 62, (1,), generator=self.dropout_generator).item())
+        self.last_dropout_seed = seed
+        return min(p, 1.0), seed
 
     def forward_features(self, image_features: torch.Tensor, text_features: torch.Tensor,
                          drop_mask: Optional[torch.Tensor] = None, drop_scale: Optional[float] = None):
@@ -340,16 +339,17 @@ class MM_RCA(EffV2MediumAndDistilbertGated):
         the internally drawn dropout mask (parity tests pass the mask torch.nn.Dropout drew)."""
         image_features = image_features.float()
         text_features = text_features.float()
+        drop_p, drop_seed = 0.0, 0
         if drop_mask is None:
-            width = F.concat_width(image_features.shape[1], text_features.shape[1], bool(self.features_only),
-                                   bool(self.cross_attention_only))
-            drop_mask, drop_scale = self._dropout_mask(image_features.shape[0], width, image_features.device)
+            drop_p, drop_seed = self._dropout_seed()
+            drop_scale = 1.0
         elif drop_scale is None:
             drop_scale = 1.0 / (1.0 - float(self.drop.p))
         return F.mmrca_head(image_features, text_features, self.head_parameters(), reverse=bool(self.reverse),
                             features_only=bool(self.features_only),
                             cross_attention_only=bool(self.cross_attention_only), n_classes=self.n_classes,
-                            drop_mask=drop_mask, drop_scale=drop_scale, compute=self.compute)
+                            drop_mask=drop_mask, drop_scale=drop_scale, drop_p=drop_p, drop_seed=drop_seed,
+                            compute=self.compute)
 
     def forward(self, _input_ids, _attention_mask, _images, eval=False, remove_image=False, remove_text=False):
         self._images = _images

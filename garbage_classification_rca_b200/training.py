@@ -87,8 +87,8 @@ class HeadDataParallel:
         self.step = step
         self.group = group
 
-    def __call__(self, img, txt, labels, drop_mask=None, drop_scale=1.0, sync: bool = True):
-        loss, logits = self.step(img, txt, labels, drop_mask, drop_scale)
+    def __call__(self, img, txt, labels, drop_mask=None, drop_scale=1.0, sync: bool = True, drop_seed: int = 0):
+        loss, logits = self.step(img, txt, labels, drop_mask, drop_scale, drop_seed)
         if sync:   # sync=False == DDP.no_sync() while accumulating (reference steps every acc_steps batches)
             allreduce_mean_(self.step.grads.flat, self.group)
         return loss, logits

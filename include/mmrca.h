@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MMRCA_ABI_VERSION 1
+#define MMRCA_ABI_VERSION 2
 
 #define MMRCA_NUM_PATCHES 16 /* multimodal_model.py:249 */
 #define MMRCA_SA_DKQ 128     /* :251 */
@@ -57,7 +57,8 @@ extern "C" {
 #define MMRCA_COMPUTE_FP32 0 /* fp32 SIMT kernels: the 1e-4-relative contract */
 #define MMRCA_COMPUTE_BF16 1 /* bf16 tcgen05 tensor-core pipeline, fp32 accumulate: the 2e-2-absolute contract.
                                 Covers the reference's literal shapes (1280 / 768 features, 4 classes) with frozen
-                                features and no materialised dropout mask; other cases run the fp32 kernels. */
+                                features and seeded dropout (MmrcaHeadDesc.drop_p / drop_seed); a caller-supplied
+                                drop_mask, feature gradients, other widths and features_only run the fp32 kernels. */
 #define MMRCA_COMPUTE_BF16_FUSED 2 /* alias of MMRCA_COMPUTE_BF16 (kept for ABI v1 callers) */
 
 /* mmrca_query() selectors */
@@ -111,6 +112,13 @@ typedef struct MmrcaHeadDesc {
   int32_t n_classes; /* 4 */
   uint32_t flags;    /* MMRCA_FLAG_* */
   int32_t compute;   /* MMRCA_COMPUTE_* */
+  /* self.drop = nn.Dropout(drop_ratio) on the concat (multimodal_model.py:190, :719), train mode only.
+   * drop_p > 0 and drop_mask == NULL: the library draws the keep mask itself, a pure function of
+   * (drop_seed, drop_p, sample, concat column) that forward and backward regenerate on chip; kept values are
+   * scaled by 1/(1-drop_p).  mmrca_dropout_mask() materialises the same mask.  The backward must be given the
+   * same drop_p / drop_seed as its forward.  drop_p == 0 (eval): no dropout. */
+  float drop_p;
+  uint64_t drop_seed;
 } MmrcaHeadDesc;
 
 /* Cross-entropy configuration: torch.nn.CrossEntropyLoss(weight=, label_smoothing=), mean
@@ -137,8 +145,8 @@ long long mmrca_head_workspace_offset(const MmrcaHeadDesc* desc, int training, i
 
 /* MM_RCA.forward from the pooled features on (multimodal_model.py:661-728).
  *   img_feat [B, d_img], txt_feat [B, d_txt] fp32
- *   drop_mask: uint8 [B, D] keep-mask of self.drop (:719) or NULL (eval / p = 0); kept values are
- *              scaled by drop_scale = 1/(1-p)
+ *   drop_mask: caller-drawn uint8 [B, D] keep-mask of self.drop (:719), kept values scaled by drop_scale =
+ *              1/(1-p); overrides desc->drop_p.  NULL: eval (drop_p == 0) or seeded dropout (drop_p > 0)
  *   logits   [B, n_classes] fp32 out */
 int mmrca_head_forward(const MmrcaHeadDesc* desc, const MmrcaHeadParams* params,
                        const float* img_feat, const float* txt_feat,
@@ -173,13 +181,17 @@ int mmrca_head_train_step(const MmrcaHeadDesc* desc, const MmrcaHeadParams* para
                           float* d_img_feat, float* d_txt_feat,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* uint8 keep-mask [batch, width] (1 = kept) that the seeded dropout of a head with concat width `width` draws for
+ * (seed, p): what the kernels regenerate on chip.  For the fp32 kernels, tests and debugging. */
+int mmrca_dropout_mask(uint64_t seed, float p, int32_t batch, int32_t width, uint8_t* mask_out, void* stream);
+
 /* Stand-alone attention block = SelfAttention.forward (multimodal_model.py:51-68, x_kv == x_q,
  * reverse = 0) or ReverseCrossAttention.forward (:82-108).  x_q, x_kv: [B, 16, d_in];
  * out: [B, 16, d_v].  (d_in, d_kq, d_v) must be one of the head's blocks:
  * (d_in in {48, 64, 80}, 128, 96) or (96, 64, 48).  `normalise` != 0 applies the per-sample
  * L2 normalisation of :662-665 to x_q (== x_kv) first and writes the norms to norms_out [B].
- * scratch: device buffer of mmrca_attention_forward_scratch_bytes() bytes (the bf16 path packs the
- * weights into it; 0 bytes / NULL for MMRCA_COMPUTE_FP32). */
+ * compute must be MMRCA_COMPUTE_FP32 (the bf16 tensor-core pipeline exists only as the fused head);
+ * scratch is unused (mmrca_attention_forward_scratch_bytes() returns 0; kept for ABI stability). */
 size_t mmrca_attention_forward_scratch_bytes(int32_t d_in, int32_t d_kq, int32_t d_v, int32_t compute);
 int mmrca_attention_forward(const MmrcaAttnParams* p, const float* x_q, const float* x_kv,
                             int32_t batch, int32_t d_in, int32_t d_kq, int32_t d_v,

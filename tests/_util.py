@@ -62,3 +62,24 @@ def assert_grad_close(name, ours, ref, tol, scale=1.0):
         return
     e = rel_err(ours, ref)
     assert e < tol, f"{name}: rel err {e:.3e} >= {tol:.1e} (max|ref| = {np.abs(ref).max():.3e})"
+
+
+def grad_summary(ours, ref, significant=1e-3):
+    """Whole-gradient error metrics for the bf16 pipeline (dicts name -> array).  W_key.bias is excluded (its
+    reference gradient is rounding noise); the per-tensor figure only looks at tensors whose largest reference
+    entry is at least `significant` x the largest entry of the whole gradient."""
+    names = [n for n in ref if n in ours and not is_key_bias(n)]
+    r = {n: np.asarray(ref[n], dtype=np.float64).ravel() for n in names}
+    o = {n: np.asarray(ours[n], dtype=np.float64).ravel() for n in names}
+    scale = max(np.abs(v).max() for v in r.values())
+    fr, fo = np.concatenate([r[n] for n in names]), np.concatenate([o[n] for n in names])
+    worst, worst_name = 0.0, ""
+    for n in names:
+        if np.abs(r[n]).max() >= significant * scale:
+            e = np.linalg.norm(o[n] - r[n]) / np.linalg.norm(r[n])
+            if e > worst:
+                worst, worst_name = float(e), n
+    return {"flat_l2_rel": float(np.linalg.norm(fo - fr) / np.linalg.norm(fr)),
+            "cos": float(fo @ fr / (np.linalg.norm(fo) * np.linalg.norm(fr))),
+            "worst_l2_rel": worst, "worst_name": worst_name,
+            "max_err_over_global": float(max(np.abs(o[n] - r[n]).max() for n in names) / scale)}

@@ -282,10 +282,11 @@ def test_module_drop_in_with_stub_backbones(pkg):
     sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
     ref = orc.head_forward(sd, img, txt, True)
     assert rel_err(out.cpu().numpy(), ref.numpy()) < LOGITS_REL_FP32
-    # training mode: dropout p=0.6 is drawn by the module; parity through the returned mask
+    # training mode: dropout p=0.6 is drawn inside the kernels from a seed the module takes from torch's
+    # generator; parity through the materialised mask of that seed
     m.train()
-    mask, scale = m._dropout_mask(10, 3584, img.device if False else torch.device("cuda"))
-    out = m.forward_features(img.cuda(), txt.cuda(), drop_mask=mask, drop_scale=scale)
+    out = m.forward_features(img.cuda(), txt.cuda())
+    mask, scale = pkg.functional.dropout_mask(m.last_dropout_seed, 0.6, 10, 3584, "cuda"), 1.0 / (1.0 - 0.6)
     ref = orc.head_forward(sd, img, txt, True, drop_mask=mask.cpu(), drop_scale=scale)
     assert rel_err(out.detach().cpu().numpy(), ref.numpy()) < LOGITS_REL_FP32
     assert 0.3 < mask.float().mean().item() < 0.5
