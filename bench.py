@@ -65,9 +65,10 @@ def kernel_flops():
     f["sa_fwd_bf16"] = sum(sa_i.values()) + sum(sa_t.values()) + 2 * 4 * 2048
     f["ca_fwd_bf16"] = 2 * sum(ca.values()) + 2 * 4 * 1536
     f["ca_bwd_bf16"] = 2 * bwd_ca(ca) + 2 * 2 * 4 * 1536
-    f["sa_bwd_bf16<80>"] = bwd_sa(sa_i) + 2 * 4 * 1280
-    f["sa_bwd_bf16<48>"] = bwd_sa(sa_t) + 2 * 4 * 768
-    for k in ("prep_bf16", "finalize_bf16", "cross_entropy4", "bias_grad"):
+    f["sa_bwd_bf16<80>"] = bwd_sa(sa_i)
+    f["sa_bwd_bf16<48>"] = bwd_sa(sa_t)
+    f["ce_feat"] = 2 * 4 * 2048                # dWf rows of the feature sources
+    for k in ("prep_bf16", "finalize_bf16", "dropout_mask"):
         f[k] = 0
     return f
 
@@ -82,8 +83,64 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
 
 
+class NvmlClockSampler:
+    """SM clock and throttle reasons polled through NVML from a thread while the timed region runs (the region
+    is a few milliseconds long: nvidia-smi's 200 ms loop would not land a single sample inside it)."""
+    HW_SLOWDOWN, SW_POWER_CAP, HW_THERMAL, SW_THERMAL = 0x8, 0x4, 0x40, 0x20
+
+    def __init__(self, index):
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        uuid = None
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ent = vis.split(",")[index].strip()
+            if ent.startswith("GPU-"):
+                uuid = ent
+            else:
+                index = int(ent)
+        self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid) if uuid else pynvml.nvmlDeviceGetHandleByIndex(index)
+        self.sm, self.reasons, self.run, self.thread = [], 0, False, None
+        self.get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+
+    def _poll(self):
+        nv = self.nv
+        while self.run:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.reasons |= int(self.get_reasons(self.h))
+            except Exception:
+                break
+            time.sleep(0.0005)
+
+    def start(self):
+        self.run = True
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.run = False
+        if self.thread:
+            self.thread.join(timeout=1.0)
+        names = [n for n, bit in (("hw_slowdown", self.HW_SLOWDOWN), ("hw_thermal_slowdown", self.HW_THERMAL),
+                                  ("sw_thermal_slowdown", self.SW_THERMAL), ("sw_power_cap", self.SW_POWER_CAP))
+                 if self.reasons & bit]
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(self.sm), "reasons": names, "source": "nvml"}
+
+
+def make_clock_sampler(index):
+    try:
+        return NvmlClockSampler(index)
+    except Exception:
+        return ClockSampler(index)
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """Fallback: nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -122,6 +179,20 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(kernel, batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full`
+    capture (profiles/traffic.json, written by tools/ncu_summary.py traffic), if it was taken at this batch."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as fh:
+            d = json.load(fh)
+        if int(d.get("batch", -1)) != batch:
+            return None
+        return d["kernels"].get(kernel)
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def synth_batches(n, batch, seed):
     import torch
     g = torch.Generator().manual_seed(seed)
@@ -143,7 +214,9 @@ def run_reference(args, rank, world):
     torch.set_num_threads(cores)
     p = orc.init_head_params(seed=0)
     img, txt, lab = synth_batches(2, args.batch, 0)
-    step = lambda i: orc.head_loss_and_grads(p, img[i % 2], txt[i % 2], lab[i % 2], True, False, False)
+    dm, ds = cpu_drop_mask(args.batch, args.dropout)
+    step = lambda i: orc.head_loss_and_grads(p, img[i % 2], txt[i % 2], lab[i % 2], True, False, False,
+                                             drop_mask=dm, drop_scale=ds)
     for i in range(args.warmup):
         step(i)
     t0 = time.perf_counter()
@@ -156,23 +229,35 @@ def run_reference(args, rank, world):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"MM_RCA --reverse fusion head fwd+CE+bwd, batch {args.batch}, features 1280+768, "
-                               "4 classes, dropout off (BASELINE.json configs[1])"},
+                               f"4 classes, train mode with dropout p={args.dropout} (fixed mask), backbones frozen "
+                               "(BASELINE.json configs[1])"},
         "cpu_baseline": {"value": val, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{args.steps} steps of batch {args.batch} after {args.warmup} warm-up"},
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
 
-def cpu_baseline(batch, budget_s=12.0, max_steps=60):
+def cpu_drop_mask(batch, p):
+    """A fixed keep mask for the CPU arms (drawing it is not part of the head; torch's own dropout would add the
+    Philox draw to the CPU time, a fixed mask leaves it out in the CPU's favour)."""
+    import torch
+    if p <= 0:
+        return None, 1.0
+    g = torch.Generator().manual_seed(7)
+    return (torch.rand(batch, 3584, generator=g) >= p).to(torch.uint8), 1.0 / (1.0 - p)
+
+
+def cpu_baseline(batch, dropout, budget_s=12.0, max_steps=400):
     import torch
     from oracle import mmrca_oracle as orc
     torch.set_num_threads(os.cpu_count() or 1)
     p = orc.init_head_params(seed=0)
     img, txt, lab = synth_batches(1, batch, 0)
-    orc.head_loss_and_grads(p, img[0], txt[0], lab[0], True, False, False)
+    dm, ds = cpu_drop_mask(batch, dropout)
+    orc.head_loss_and_grads(p, img[0], txt[0], lab[0], True, False, False, drop_mask=dm, drop_scale=ds)
     n, t0 = 0, time.perf_counter()
     while n < max_steps and (time.perf_counter() - t0 < budget_s or n < 3):
-        orc.head_loss_and_grads(p, img[0], txt[0], lab[0], True, False, False)
+        orc.head_loss_and_grads(p, img[0], txt[0], lab[0], True, False, False, drop_mask=dm, drop_scale=ds)
         n += 1
     dt = time.perf_counter() - t0
     return {"value": n * batch / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
@@ -193,7 +278,7 @@ def run_b200(args, rank, world, local_rank):
     B, K, W = args.batch, args.steps, args.warmup
     compute = N.COMPUTE_BF16 if args.compute == "bf16" else N.COMPUTE_FP32
     params = g.functional.init_head_parameters(dev, seed=0)
-    step = g.HeadTrainStep(params, B, D_IMG, D_TXT, reverse=True, compute=compute)
+    step = g.HeadTrainStep(params, B, D_IMG, D_TXT, reverse=True, compute=compute, drop_p=args.dropout)
     dp = HeadDataParallel(step)
     # inputs larger than L2: rotate over NB distinct batches
     per_batch = B * (D_IMG + D_TXT) * 4
@@ -208,12 +293,12 @@ def run_b200(args, rank, world, local_rank):
 
     def device_step(i):
         step.zero_grad()
-        dp(img_d[i % NB], txt_d[i % NB], lab_d[i % NB])
+        dp(img_d[i % NB], txt_d[i % NB], lab_d[i % NB], drop_seed=1000 + i)     # a fresh dropout mask every step
 
     # ---- value: device-resident inputs -------------------------------------------------------------
     for i in range(W):
         device_step(i)
-    sampler = ClockSampler(local_rank)
+    sampler = make_clock_sampler(local_rank) if rank == 0 else None
     if rank == 0:
         sampler.start()
     barrier()
@@ -268,7 +353,7 @@ def run_b200(args, rank, world, local_rank):
             s = i % 2
             main.wait_event(ready[s])
             step.zero_grad()
-            dp(*slots[s])
+            dp(*slots[s], drop_seed=5000 + i)
             consumed[s].record(main)
             out_loss.copy_(step.loss, non_blocking=True)
             out_logits.copy_(step.logits, non_blocking=True)
@@ -276,12 +361,16 @@ def run_b200(args, rank, world, local_rank):
 
     e2e_loop(max(W, 2))
     barrier()
+    sampler2 = make_clock_sampler(local_rank) if rank == 0 else None
+    if rank == 0:
+        sampler2.start()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     e2e_loop(K)
     t1.record()
     barrier()
     ms_e2e = t0.elapsed_time(t1)
+    clocks_e2e = sampler2.stop() if rank == 0 else None
 
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev)
@@ -309,16 +398,17 @@ def run_b200(args, rank, world, local_rank):
         "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if compute == N.COMPUTE_FP32 else "bf16", "data": "synthetic",
         "config": {"workload": f"MM_RCA --reverse fusion head fwd+CE+bwd, batch {B}/GPU, features 1280+768, "
-                               "4 classes, dropout off, backbones frozen (BASELINE.json configs[1])",
+                               f"4 classes, train mode with dropout p={args.dropout} (in-kernel seeded mask, new seed "
+                               "every step), backbones frozen (BASELINE.json configs[1])",
                    "parallelism": f"dp{world}", "global_batch": world * B,
                    "l2": f"inputs rotate over {NB} distinct batches ({NB * per_batch >> 20} MiB > 126 MiB L2)",
                    "compute": args.compute, "loss": loss_val},
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": B * (D_IMG + D_TXT) * 4 + B * 8,
                 "d2h_bytes_per_step": 4 + B * N_CLASSES * 4, "ms_per_step": ms_e2e / K},
         "gpu_launches": launches,
-        "clocks": clocks,
+        "clocks": dict(clocks, e2e_region=clocks_e2e),
         "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"] + " bf16 sustained",
+                     "frac": achieved / peak, "traffic": ncu_traffic(dom, B), "peak_source": peaks["source"] + " bf16 sustained",
                      "kernel_ms": dom_ms, "kernel_share_of_step": share[dom] / total_k,
                      "timing": f"second pass of {K} steps with per-kernel CUDA events on the launch stream"},
         "roofline_step": {"bound": "tensor", "achieved": step_tflops, "peak": peak, "unit": "TFLOP/s",
@@ -328,7 +418,7 @@ def run_b200(args, rank, world, local_rank):
         "kernels_ms_per_step": {k: round(v, 4) for k, v in sorted(share.items(), key=lambda kv: -kv[1])},
     }
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(B)
+        out["cpu_baseline"] = cpu_baseline(B, args.dropout)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -342,6 +432,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--compute", default="bf16", choices=("fp32", "bf16"))
+    ap.add_argument("--dropout", type=float, default=0.6, help="model_dropout (reference options.py:25 default 0.6)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -203,6 +203,7 @@ struct Workspace {
   // fused bf16 pipeline (mmrca_head_tc.cuh)
   void* fblob[4];                                                   // per block: bz | bv | bc blobs
   void* t_img; void* i_img;                                         // SA output images, [tiles][kSaTileBytes]
+  void* x_img; void* x_txt;                                         // normalised feature images (SA inputs)
   void* dx_img[4];                                                  // training: dXq / dXkv images of CA1, then CA2
   float* gm[4]; size_t gm_floats;                                   // training: dM_ext^T per block (contiguous)
   size_t bytes;
@@ -252,6 +253,8 @@ static Workspace carve(const MmrcaHeadDesc& d, bool training, void* base) {
     w.fblob[3] = take(htc::CaCfg::W_BYTES / 4);
     w.t_img = take(tiles * htc::kSaTileBytes / 4);
     w.i_img = take(tiles * htc::kSaTileBytes / 4);
+    w.x_img = take(tiles * htc::x_tile_bytes(80) / 4);
+    w.x_txt = take(tiles * htc::x_tile_bytes(48) / 4);
   }
   if (training) {
     w.d_t_sa = take(B * kL * MMRCA_SA_DV); w.d_i_sa = take(B * kL * MMRCA_SA_DV);
@@ -345,8 +348,10 @@ static htc::PrepBlock make_prep_block(const MmrcaAttnParams& p, void* blob, int 
   return b;
 }
 
-static int launch_prep_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, float* logits, const Workspace& w,
-                             float* zero0, int nzero0, cudaStream_t st) {
+// weights -> bf16 blobs; features -> normalised bf16 images, norms, logits = bias + fp32 feature terms
+static int launch_prep_feat(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, const float* img, const float* txt,
+                            float* logits, const Workspace& w, int sms, cudaStream_t st) {
+  const bool co = d.flags & MMRCA_FLAG_CROSS_ATTENTION_ONLY;
   htc::PrepArgs a;
   memset(&a, 0, sizeof(a));
   a.blk[0] = make_prep_block(p.sa_img, w.fblob[0], 80, MMRCA_SA_DKQ, MMRCA_SA_DV);
@@ -354,18 +359,23 @@ static int launch_prep_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, f
   a.blk[2] = make_prep_block(p.ca1, w.fblob[2], MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV);
   a.blk[3] = make_prep_block(p.ca2, w.fblob[3], MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV);
   const int ca = kL * MMRCA_CA_DV;   // 768: width of T_I / I_T in the concat (multimodal_model.py:708-716)
-  int n = 0;
-  a.src[n].bc = static_cast<uint8_t*>(w.fblob[2]) + htc::CaCfg::BZ_BYTES + htc::CaCfg::BV_BYTES;
-  a.src[n].off = 0; a.src[n].w = MMRCA_CA_DV; ++n;
-  a.src[n].bc = static_cast<uint8_t*>(w.fblob[3]) + htc::CaCfg::BZ_BYTES + htc::CaCfg::BV_BYTES;
-  a.src[n].off = ca; a.src[n].w = MMRCA_CA_DV; ++n;
-  a.nsrc = n;      // (the feature sources of the classifier run in fp32 inside sa_fwd_kernel / ce_feat_kernel)
-  a.wf = p.wf; a.bf = p.bf; a.D = concat_width(d);
-  a.logits = logits; a.batch = d.batch;
-  a.zero0 = zero0; a.nzero0 = nzero0;
+  a.src[0].bc = static_cast<uint8_t*>(w.fblob[2]) + htc::CaCfg::BZ_BYTES + htc::CaCfg::BV_BYTES;
+  a.src[0].off = 0; a.src[0].w = MMRCA_CA_DV;
+  a.src[1].bc = static_cast<uint8_t*>(w.fblob[3]) + htc::CaCfg::BZ_BYTES + htc::CaCfg::BV_BYTES;
+  a.src[1].off = ca; a.src[1].w = MMRCA_CA_DV;
+  a.nsrc = 2;      // (the feature sources of the classifier run in fp32: prep_feat_kernel / ce_feat_kernel)
+  a.wf = p.wf; a.D = concat_width(d);
+  htc::FeatArgs f;
+  memset(&f, 0, sizeof(f));
+  f.src[0].feat = img; f.src[0].x_tiles = w.x_img; f.src[0].norms = w.norm_img; f.src[0].cls_off = 2 * ca;
+  f.src[1].feat = txt; f.src[1].x_tiles = w.x_txt; f.src[1].norms = w.norm_txt; f.src[1].cls_off = 2 * ca + d.d_img;
+  f.logits = logits; f.wf = p.wf; f.bf = p.bf; f.with_features = co ? 0 : 1;
+  f.drop = make_drop(d); f.batch = d.batch;
+  const int prep_ctas = htc::kPrepCtas;
+  const int feat_ctas = max(1, min((d.batch + 7) / 8, 2 * sms));
   {
-    LaunchScope ls("prep_bf16", st);
-    htc::prep_kernel<<<4 * 148, 256, 0, st>>>(a);
+    LaunchScope ls("prep_feat", st);
+    htc::prep_feat_kernel<<<prep_ctas + feat_ctas, 256, htc::kFeatSmemBytes, st>>>(a, f, prep_ctas);
   }
   MMRCA_CUDA(cudaGetLastError());
   return MMRCA_OK;
@@ -373,20 +383,17 @@ static int launch_prep_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, f
 
 static int head_forward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, const float* img, const float* txt,
                               float* logits, const Workspace& w, int sms, cudaStream_t st) {
-  const bool co = d.flags & MMRCA_FLAG_CROSS_ATTENTION_ONLY;
   int rc;
-  if ((rc = launch_prep_fused(d, p, logits, w, nullptr, 0, st))) return rc;
+  if ((rc = launch_prep_feat(d, p, img, txt, logits, w, sms, st))) return rc;
   const int tiles = (d.batch + 7) / 8;
   const int grid = min(tiles, sms);
   {
     htc::SaFwdArgs a;
     memset(&a, 0, sizeof(a));
-    a.role[0].feat = img; a.role[0].norms = w.norm_img; a.role[0].ln_g = p.sa_img.ln_g; a.role[0].ln_b = p.sa_img.ln_b;
-    a.role[0].blobs = w.fblob[0]; a.role[0].out_tiles = w.i_img; a.role[0].cls_off = 2 * kL * MMRCA_CA_DV;
-    a.role[1].feat = txt; a.role[1].norms = w.norm_txt; a.role[1].ln_g = p.sa_txt.ln_g; a.role[1].ln_b = p.sa_txt.ln_b;
-    a.role[1].blobs = w.fblob[1]; a.role[1].out_tiles = w.t_img; a.role[1].cls_off = 2 * kL * MMRCA_CA_DV + d.d_img;
-    a.logits = co ? nullptr : logits;
-    a.wf = p.wf; a.drop = make_drop(d);
+    a.role[0].x_tiles = w.x_img; a.role[0].ln_g = p.sa_img.ln_g; a.role[0].ln_b = p.sa_img.ln_b;
+    a.role[0].blobs = w.fblob[0]; a.role[0].out_tiles = w.i_img;
+    a.role[1].x_tiles = w.x_txt; a.role[1].ln_g = p.sa_txt.ln_g; a.role[1].ln_b = p.sa_txt.ln_b;
+    a.role[1].blobs = w.fblob[1]; a.role[1].out_tiles = w.t_img;
     a.batch = d.batch;
     if ((rc = set_smem(htc::sa_fwd_kernel, htc::SaFwdLayout::BYTES))) return rc;
     LaunchScope ls("sa_fwd_bf16", st);
@@ -440,7 +447,7 @@ static int head_backward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p,
     // text SA output: query source of CA1, key/value source of CA2; image SA output: the other way round
     htc::SaBwdArgs a;
     memset(&a, 0, sizeof(a));
-    a.feat = img; a.blobs = w.fblob[0]; a.ln_g = p.sa_img.ln_g; a.ln_b = p.sa_img.ln_b;
+    a.x_tiles = w.x_img; a.blobs = w.fblob[0]; a.ln_g = p.sa_img.ln_g; a.ln_b = p.sa_img.ln_b;
     a.dout_a = w.dx_img[1]; a.dout_b = w.dx_img[2];
     a.gm = w.gm[0]; a.g_wv = g.sa_img.wv; a.g_bv = g.sa_img.bv; a.g_ln_g = g.sa_img.ln_g; a.g_ln_b = g.sa_img.ln_b;
     a.batch = d.batch;
@@ -450,7 +457,7 @@ static int head_backward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p,
       htc::sa_bwd_kernel<80><<<min(tiles, sms), htc::kCtaThreads, htc::SaBwdSmem<80>::BYTES, st>>>(a);
     }
     MMRCA_CUDA(cudaGetLastError());
-    a.feat = txt; a.blobs = w.fblob[1]; a.ln_g = p.sa_txt.ln_g; a.ln_b = p.sa_txt.ln_b;
+    a.x_tiles = w.x_txt; a.blobs = w.fblob[1]; a.ln_g = p.sa_txt.ln_g; a.ln_b = p.sa_txt.ln_b;
     a.dout_a = w.dx_img[0]; a.dout_b = w.dx_img[3];
     a.gm = w.gm[1]; a.g_wv = g.sa_txt.wv; a.g_bv = g.sa_txt.bv; a.g_ln_g = g.sa_txt.ln_g; a.g_ln_b = g.sa_txt.ln_b;
     if ((rc = set_smem(htc::sa_bwd_kernel<48>, htc::SaBwdSmem<48>::BYTES))) return rc;
@@ -473,8 +480,10 @@ static int head_backward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p,
       a.blk[i].din = dins[i]; a.blk[i].dkq = dkqs[i];
     }
     a.nblk = 4;
+    int ctas = 0;
+    for (int i = 0; i < 4; ++i) ctas += dkqs[i] / htc::kFinRows;
     LaunchScope ls("finalize_bf16", st);
-    htc::finalize_kernel<<<dim3(84, 4), 256, 0, st>>>(a);
+    htc::finalize_kernel<<<ctas, 256, htc::kFinSmemBytes, st>>>(a);
   }
   MMRCA_CUDA(cudaGetLastError());
   return MMRCA_OK;
@@ -482,8 +491,8 @@ static int head_backward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p,
 
 // cross-entropy (labels != null) or given dlogits, + classifier bias gradient + the feature-source rows of dWf
 static int launch_ce_feat(const MmrcaHeadDesc& d, const float* logits, const int64_t* labels, const MmrcaCeDesc* ce,
-                          float* loss, float* dlogits, const MmrcaHeadGrads& g, bool bias_grad, const float* img,
-                          const float* txt, const Workspace& w, int sms, cudaStream_t st) {
+                          float* loss, float* dlogits, const MmrcaHeadGrads& g, bool bias_grad, const Workspace& w,
+                          cudaStream_t st) {
   const bool co = d.flags & MMRCA_FLAG_CROSS_ATTENTION_ONLY;
   if (labels) MMRCA_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
   htc::CeFeatArgs a;
@@ -492,12 +501,14 @@ static int launch_ce_feat(const MmrcaHeadDesc& d, const float* logits, const int
   a.batch = d.batch; a.dlogits = dlogits; a.loss = loss; a.g_bf = bias_grad ? g.bf : nullptr;
   a.drop = make_drop(d);
   if (!co && g.wf) {
-    a.img = img; a.txt = txt; a.norm_img = w.norm_img; a.norm_txt = w.norm_txt; a.g_wf = g.wf;
+    a.x_img = w.x_img; a.x_txt = w.x_txt; a.g_wf = g.wf;
     a.off_img = 2 * kL * MMRCA_CA_DV; a.off_txt = a.off_img + d.d_img;
   }
   {
+    const int tiles = (d.batch + 7) / 8;
+    const dim3 grid(a.g_wf ? htc::kStripsImg + htc::kStripsTxt : 1, (tiles + htc::kCeSliceTiles - 1) / htc::kCeSliceTiles);
     LaunchScope ls("ce_feat", st);
-    htc::ce_feat_kernel<<<max(1, min((d.batch + 7) / 8, 2 * sms)), 256, 0, st>>>(a);
+    htc::ce_feat_kernel<<<grid, 256, 0, st>>>(a);
   }
   MMRCA_CUDA(cudaGetLastError());
   return MMRCA_OK;
@@ -562,7 +573,7 @@ static int head_backward_impl(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, 
     // classifier bias gradient and the feature-source rows of dWf from the given dlogits (train_step has done
     // both inside its cross-entropy kernel)
     if (!ce_done && (rc = launch_ce_feat(d, nullptr, nullptr, nullptr, nullptr, const_cast<float*>(dlogits), g, g.bf != nullptr,
-                                         img, txt, w, sms, st))) return rc;
+                                         w, st))) return rc;
     return head_backward_fused(d, p, img, txt, dlogits, g, w, sms, st);
   }
   if (!mask && d.drop_p > 0.f) { mask = w.mask; scale = make_drop(d).scale; }   // materialised by the forward
@@ -756,8 +767,8 @@ int mmrca_head_train_step(const MmrcaHeadDesc* desc, const MmrcaHeadParams* para
   if ((rc = head_forward_impl(*desc, *params, img_feat, txt_feat, drop_mask, drop_scale, logits, w, di.sms, st)))
     return rc;
   if (fused_ok(*desc, drop_mask)) {
-    if ((rc = launch_ce_feat(*desc, logits, labels, ce, loss_out, w.dlogits, *grads, grads->bf != nullptr, img_feat,
-                             txt_feat, w, di.sms, st))) return rc;
+    if ((rc = launch_ce_feat(*desc, logits, labels, ce, loss_out, w.dlogits, *grads, grads->bf != nullptr, w, st)))
+      return rc;
     return head_backward_impl(*desc, *params, img_feat, txt_feat, drop_mask, drop_scale, w.dlogits, *grads, d_img_feat,
                               d_txt_feat, w, di.sms, st, true);
   }

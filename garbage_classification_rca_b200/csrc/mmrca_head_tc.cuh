@@ -64,7 +64,7 @@ __host__ __device__ constexpr uint32_t al128(uint32_t v) { return (v + 127u) & ~
 __device__ __forceinline__ uint32_t row_off(int r) { return uint32_t(r >> 3) * kRS + uint32_t(r & 7) * 16u; }
 
 // ---------------------------------------------------------------------------------------------------------------
-// prep: weights -> bf16 blobs, zero the step's accumulators, logits = classifier bias.
+// prep: weights -> bf16 blobs, zero the step's accumulators.
 // blob of a B operand Bm[n][k] (K-major): byte(n, k) = (k/8) * (N*16) + n*16 + (k%8)*2
 // ---------------------------------------------------------------------------------------------------------------
 struct PrepBlock {
@@ -78,45 +78,63 @@ struct PrepArgs {
   PrepBlock blk[4];
   PrepSrc src[4];
   int nsrc;
-  const float* wf; const float* bf; int D;   // classifier [4][D]
-  float* logits; int batch;                  // initialised with the bias (null: skip)
+  const float* wf; int D;                    // classifier [4][D]
   float* zero0; int nzero0;                  // fp32 regions to clear (step accumulators)
 };
 
-__global__ void __launch_bounds__(256) prep_kernel(const PrepArgs a) {
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-  const int gwarp = gtid >> 5, nwarp = gsz >> 5, lane = threadIdx.x & 31;
-  // (a) Z blobs: one warp per (k', kc): 8 outputs M[k][k'] (k = 8kc..8kc+7), lanes split the d_kq sum
-  int base = 0;
-  for (int b = 0; b < 4; ++b) {
-    const PrepBlock& B = a.blk[b];
-    if (!B.bz) continue;
-    const int kcs = (B.din + 16) / 8, ntask = B.din * kcs;
-    const float scale = rsqrtf(float(B.dkq));
-    for (int t = gwarp - base; t < ntask; t += nwarp) {
-      if (t < 0) continue;
-      const int kp = t / kcs, kc = t - kp * kcs;
-      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (kc * 8 < B.din) {
-#pragma unroll 4
-        for (int n = lane; n < B.dkq; n += 32) {
-          const float wk = __ldg(B.wk + size_t(n) * B.din + kp);
-          const float4 q0 = __ldg(reinterpret_cast<const float4*>(B.wq + size_t(n) * B.din + kc * 8));
-          const float4 q1 = __ldg(reinterpret_cast<const float4*>(B.wq + size_t(n) * B.din + kc * 8 + 4));
-          acc[0] = fmaf(q0.x, wk, acc[0]); acc[1] = fmaf(q0.y, wk, acc[1]); acc[2] = fmaf(q0.z, wk, acc[2]);
-          acc[3] = fmaf(q0.w, wk, acc[3]); acc[4] = fmaf(q1.x, wk, acc[4]); acc[5] = fmaf(q1.y, wk, acc[5]);
-          acc[6] = fmaf(q1.z, wk, acc[6]); acc[7] = fmaf(q1.w, wk, acc[7]);
-        }
-      } else if (kc * 8 == B.din) {
-        for (int n = lane; n < B.dkq; n += 32) acc[0] = fmaf(__ldg(B.bq + n), __ldg(B.wk + size_t(n) * B.din + kp), acc[0]);
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = warp_sum(acc[e]) * scale;
-      if (lane == 0)
-        *reinterpret_cast<uint4*>(static_cast<uint8_t*>(B.bz) + size_t(kc) * (B.din * 16) + kp * 16) = pack_bf16x8(acc);
+constexpr int kPrepZTasks = (80 + 16) / 8 + (48 + 16) / 8 + 2 * (96 + 16) / 8;   // one CTA per (block, 8-column group kc)
+constexpr int kPrepCtas = kPrepZTasks + 16;
+
+constexpr uint32_t kPrepSmemBytes = (128 * 80 + 128 * 8) * 4;     // W_key of the widest block + one 8-column slab of W_query
+
+__device__ __forceinline__ void prep_body(const PrepArgs& a, int cta, int nctas, float* smf) {
+  // (a) Z blobs.  CTA = (block, kc); thread = k'.  M[k][k'] = scale sum_n Wq[n][k] Wk[n][k'] for the 8 k of the group.
+  //     W_key and the W_query slab are staged in shared memory first, every load of the CTA in flight at once: the
+  //     weights come from HBM (the features have swept the L2 since the last step) and a dependent chain of d_kq
+  //     global loads per thread would cost d_kq memory latencies.
+  if (cta < kPrepZTasks) {
+    int b = 0, kc = cta;
+    for (; b < 4; ++b) {
+      const int kcs = (a.blk[b].din + 16) / 8;
+      if (kc < kcs) break;
+      kc -= kcs;
     }
-    base = (base + ntask) % nwarp;   // rotate the starting warp so the blocks' tasks spread over the grid
+    const PrepBlock& B = a.blk[b];
+    if (!B.bz) return;
+    const int din = B.din, dkq = B.dkq;
+    float* wk_s = smf;                  // [dkq][din]
+    float* wq_s = smf + dkq * din;      // [dkq][8]: columns kc*8 .. kc*8+7 of W_query, or b_query in column 0
+    for (int i = threadIdx.x; i < dkq * din / 4; i += blockDim.x)
+      reinterpret_cast<float4*>(wk_s)[i] = __ldg(reinterpret_cast<const float4*>(B.wk) + i);
+    for (int i = threadIdx.x; i < dkq * 2; i += blockDim.x) {
+      const int n = i >> 1, h = i & 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kc * 8 < din) v = __ldg(reinterpret_cast<const float4*>(B.wq + size_t(n) * din + kc * 8 + 4 * h));
+      else if (kc * 8 == din && h == 0) v.x = __ldg(B.bq + n);
+      reinterpret_cast<float4*>(wq_s)[i] = v;
+    }
+    __syncthreads();
+    const int kp = threadIdx.x;
+    if (kp >= din) return;
+    const float scale = rsqrtf(float(dkq));
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (kc * 8 <= din) {
+#pragma unroll 4
+      for (int n = 0; n < dkq; ++n) {
+        const float wk = wk_s[n * din + kp];
+        const float4 q0 = *reinterpret_cast<const float4*>(wq_s + n * 8);
+        const float4 q1 = *reinterpret_cast<const float4*>(wq_s + n * 8 + 4);
+        acc[0] = fmaf(q0.x, wk, acc[0]); acc[1] = fmaf(q0.y, wk, acc[1]); acc[2] = fmaf(q0.z, wk, acc[2]);
+        acc[3] = fmaf(q0.w, wk, acc[3]); acc[4] = fmaf(q1.x, wk, acc[4]); acc[5] = fmaf(q1.y, wk, acc[5]);
+        acc[6] = fmaf(q1.z, wk, acc[6]); acc[7] = fmaf(q1.w, wk, acc[7]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] *= scale;
+    *reinterpret_cast<uint4*>(static_cast<uint8_t*>(B.bz) + size_t(kc) * (din * 16) + kp * 16) = pack_bf16x8(acc);
+    return;
   }
+  const int gtid = (cta - kPrepZTasks) * blockDim.x + threadIdx.x, gsz = (nctas - kPrepZTasks) * blockDim.x;
   // (b) V blobs: thread per (n, kc)
   for (int b = 0; b < 4; ++b) {
     const PrepBlock& B = a.blk[b];
@@ -148,10 +166,133 @@ __global__ void __launch_bounds__(256) prep_kernel(const PrepArgs a) {
       *reinterpret_cast<uint4*>(static_cast<uint8_t*>(S.bc) + size_t(kc) * (kNCls * 16) + n * 16) = pack_bf16x8(v);
     }
   }
-  // (d) accumulators, logits
+  // (d) accumulators
   for (int i = gtid; i < a.nzero0; i += gsz) a.zero0[i] = 0.f;
-  if (a.logits)
-    for (int i = gtid; i < a.batch * kClasses; i += gsz) a.logits[i] = __ldg(a.bf + (i & 3));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// features: L2-normalise (multimodal_model.py:662-665), emit the bf16 operand images the SA kernels load by TMA,
+// the norms, and logits = bias + the classifier's feature-source terms in fp32 (:708-726, dropout :719 included).
+// HBM-bound streaming: one warp per sample, persistent CTAs that keep the 4 x 2048 feature columns of the classifier
+// weight in shared memory.  A 16-byte item is (chunk row r, 8-column group kc), kc fastest: a warp reads 1 KB of
+// contiguous feature floats per instruction and its shared-memory weight reads are conflict-free.
+// Image of a tile (8 samples = 128 rows): [KCS + 2 column groups][128 rows][8 bf16], column-group stride kCS;
+// group KCS holds the constant-one column that carries the projection biases, group KCS + 1 zeros.
+// ---------------------------------------------------------------------------------------------------------------
+struct FeatSrc {
+  const float* feat;      // [B][16 * din] fp32
+  void* x_tiles;          // [tiles][x_tile_bytes(din)] out
+  float* norms;           // [B] out
+  int cls_off;            // first concat column of this source
+};
+struct FeatArgs {
+  FeatSrc src[2];         // 0: image (din 80), 1: text (din 48)
+  float* logits;          // [B][4] out: bias (+ feature terms when with_features)
+  const float* wf; const float* bf;
+  int with_features;      // the classifier sees the features (not cross_attention_only)
+  DropSpec drop;          // drop.D = concat width
+  int batch;
+};
+__host__ __device__ constexpr uint32_t x_tile_bytes(int din) { return op_bytes(din + 16); }
+constexpr int kFeatCols = 16 * 80 + 16 * 48;                 // 2048 feature columns of the concat
+constexpr uint32_t kFeatSmemBytes = kClasses * kFeatCols * 4 > kPrepSmemBytes ? kClasses * kFeatCols * 4 : kPrepSmemBytes;
+
+template <int DIN>
+__device__ __forceinline__ void feat_load(const FeatSrc& S, int b, bool live, int lane, float (&v)[(kL * DIN / 8 + 31) / 32][8]) {
+  constexpr int ITEMS = kL * DIN / 8, PER = (ITEMS + 31) / 32;
+  const float* base = S.feat + size_t(b) * (kL * DIN);
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int it = lane + 32 * k;
+    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+    if (live && (ITEMS % 32 == 0 || it < ITEMS)) {
+      lo = __ldg(reinterpret_cast<const float4*>(base + it * 8));
+      hi = __ldg(reinterpret_cast<const float4*>(base + it * 8 + 4));
+    }
+    v[k][0] = lo.x; v[k][1] = lo.y; v[k][2] = lo.z; v[k][3] = lo.w; v[k][4] = hi.x; v[k][5] = hi.y; v[k][6] = hi.z; v[k][7] = hi.w;
+  }
+}
+
+// ws: this source's [4][16 * DIN] slice of the classifier weight in shared memory
+template <int DIN>
+__device__ __forceinline__ void feat_emit(const FeatArgs& a, const FeatSrc& S, const float* ws, int b, bool live, int lane,
+                                          const float (&v)[(kL * DIN / 8 + 31) / 32][8], float (&cls)[kClasses]) {
+  constexpr int KCS = DIN / 8, ITEMS = kL * KCS, PER = (ITEMS + 31) / 32;
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < PER; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ss = fmaf(v[k][e], v[k][e], ss);
+  const float nrm = sqrtf(warp_sum(ss));
+  const float inv = live ? 1.0f / nrm : 0.f;        // no epsilon, like the reference
+  if (lane == 0 && live) S.norms[b] = nrm;
+  uint8_t* tile = static_cast<uint8_t*>(S.x_tiles) + size_t(b >> 3) * x_tile_bytes(DIN);
+  const int r0 = (b & 7) * kL;
+  float acc[kClasses] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int it = lane + 32 * k;
+    if (ITEMS % 32 != 0 && it >= ITEMS) continue;
+    const int row = it / KCS, kc = it - row * KCS;
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = v[k][e] * inv;
+    *reinterpret_cast<uint4*>(tile + uint32_t(kc) * kCS + row_off(r0 + row)) = pack_bf16x8(o);
+    if (a.with_features && live) {
+      if (a.drop.thresh) {
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          float m0, m1;
+          drop_pair(a.drop, uint32_t(b), uint32_t(S.cls_off + it * 8 + e), m0, m1);
+          o[e] *= m0; o[e + 1] *= m1;
+        }
+      }
+#pragma unroll
+      for (int cc = 0; cc < kClasses; ++cc) {
+        const float4 w0 = *reinterpret_cast<const float4*>(ws + cc * (kL * DIN) + it * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(ws + cc * (kL * DIN) + it * 8 + 4);
+        acc[cc] = fmaf(o[0], w0.x, fmaf(o[1], w0.y, fmaf(o[2], w0.z, fmaf(o[3], w0.w, acc[cc]))));
+        acc[cc] = fmaf(o[4], w1.x, fmaf(o[5], w1.y, fmaf(o[6], w1.z, fmaf(o[7], w1.w, acc[cc]))));
+      }
+    }
+  }
+  // the bias column groups of my 16 rows: lanes 0-15 the ones column, lanes 16-31 the zero group
+  *reinterpret_cast<uint4*>(tile + uint32_t(KCS + (lane >> 4)) * kCS + row_off(r0 + (lane & 15))) =
+      make_uint4(lane < 16 ? 0x00003F80u : 0u, 0u, 0u, 0u);
+#pragma unroll
+  for (int cc = 0; cc < kClasses; ++cc) cls[cc] += warp_sum(acc[cc]);
+}
+
+__global__ void __launch_bounds__(256) prep_feat_kernel(const PrepArgs pa, const FeatArgs fa, int prep_ctas) {
+  extern __shared__ __align__(16) float wsm_f[];      // [4][1280] image columns, then [4][768] text columns
+  if (int(blockIdx.x) < prep_ctas) { prep_body(pa, blockIdx.x, prep_ctas, wsm_f); return; }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (fa.with_features) {
+    for (int i = threadIdx.x; i < kClasses * kFeatCols / 4; i += 256) {
+      const int f = 4 * i;
+      int cc, j, off;
+      if (f < kClasses * 1280) { cc = f / 1280; j = f - cc * 1280; off = fa.src[0].cls_off; }
+      else { const int g = f - kClasses * 1280; cc = g / 768; j = g - cc * 768; off = fa.src[1].cls_off; }
+      reinterpret_cast<float4*>(wsm_f)[i] = __ldg(reinterpret_cast<const float4*>(fa.wf + size_t(cc) * fa.drop.D + off + j));
+    }
+  }
+  __syncthreads();
+  const int nb = ((fa.batch + 7) / 8) * 8;      // whole tiles: the padding samples of the last tile become zero rows
+  const int stride = (int(gridDim.x) - prep_ctas) * 8;
+  for (int b = (int(blockIdx.x) - prep_ctas) * 8 + warp; b < nb; b += stride) {
+    const bool live = b < fa.batch;
+    float vi[5][8], vt[3][8];
+    feat_load<80>(fa.src[0], b, live, lane, vi);
+    feat_load<48>(fa.src[1], b, live, lane, vt);
+    float cls[kClasses] = {0.f, 0.f, 0.f, 0.f};
+    feat_emit<80>(fa, fa.src[0], wsm_f, b, live, lane, vi, cls);
+    feat_emit<48>(fa, fa.src[1], wsm_f + kClasses * 1280, b, live, lane, vt, cls);
+    if (lane < kClasses && live) {
+      float r = cls[0];
+      r = lane == 1 ? cls[1] : r; r = lane == 2 ? cls[2] : r; r = lane == 3 ? cls[3] : r;
+      fa.logits[size_t(b) * kClasses + lane] = __ldg(fa.bf + lane) + r;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -321,18 +462,13 @@ struct SaCfg {
 constexpr uint32_t kSaTileBytes = op_bytes(kDV_SA);   // one SA output image: [128 x 96] bf16 = 12 chunk columns
 
 struct SaRole {
-  const float* feat;      // [B][16*DIN] fp32
-  float* norms;           // [B] (out)
+  const void* x_tiles;    // [tiles][x_tile_bytes(DIN)]: normalised bf16 operand images (prep_feat_kernel)
   const float* ln_g; const float* ln_b;
   const void* blobs;      // bz | bv, contiguous
   void* out_tiles;        // [tiles][kSaTileBytes]
-  int cls_off;            // first concat column of this feature source (classifier, dropout)
 };
 struct SaFwdArgs {
   SaRole role[2];         // 0: image (DIN 80), 1: text (DIN 48)
-  float* logits;          // += feature term (null: classifier does not see the features)
-  const float* wf;        // classifier weight [4][D] fp32
-  DropSpec drop;          // drop.D = D
   int batch;
 };
 
@@ -351,123 +487,28 @@ struct SaFwdLayout {
   static constexpr uint32_t WG1 = WG0 + SaFwdSmem::BYTES;
   static constexpr uint32_t LN = WG1 + SaFwdSmem::BYTES;                            // 2 roles x (gamma, beta) x 96 fp32
   static constexpr uint32_t BAR = al128(LN + 2 * 2 * 96 * 4);                       // mbarriers + tmem slot
-  static constexpr uint32_t BYTES = BAR + 64;
+  static constexpr uint32_t BYTES = BAR + 128;
   static_assert(BYTES <= 232448, "SA forward does not fit shared memory");
 };
 
-// load + L2-normalise (multimodal_model.py:662-665) this warp's two samples into the bf16 operand; while the
-// sample sits in registers, its classifier term  logits[b][c] += sum_j drop(x_j / ||x||) Wf[c][off + j]  in fp32
-template <int DIN>
-__device__ __forceinline__ void stage_features(const WgCtx& c, uint8_t* xop, const float* __restrict__ feat,
-                                               float* __restrict__ norms, int b0, int batch,
-                                               float* __restrict__ logits, const float* __restrict__ wf, int cls_off,
-                                               const DropSpec& drop) {
-  constexpr int KCS = DIN / 8, ITEMS = kL * KCS, PER = (ITEMS + 31) / 32;
-  float v[2][PER][8];
-  float ss[2] = {0.f, 0.f};
-#pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    const int b = b0 + 2 * c.q + s;
-    const float* base = feat + size_t(b) * (kL * DIN);
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-      const int it = c.lane + 32 * k;
-      float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
-      if (b < batch && (ITEMS % 32 == 0 || it < ITEMS)) {
-        lo = __ldg(reinterpret_cast<const float4*>(base + it * 8));
-        hi = __ldg(reinterpret_cast<const float4*>(base + it * 8 + 4));
-      }
-      v[s][k][0] = lo.x; v[s][k][1] = lo.y; v[s][k][2] = lo.z; v[s][k][3] = lo.w;
-      v[s][k][4] = hi.x; v[s][k][5] = hi.y; v[s][k][6] = hi.z; v[s][k][7] = hi.w;
-    }
-  }
-#pragma unroll
-  for (int s = 0; s < 2; ++s) {
-#pragma unroll
-    for (int k = 0; k < PER; ++k)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) ss[s] = fmaf(v[s][k][e], v[s][k][e], ss[s]);
-    ss[s] = warp_sum(ss[s]);
-  }
-  if (logits) {
-    float acc[2][kClasses];
-#pragma unroll
-    for (int s = 0; s < 2; ++s)
-#pragma unroll
-      for (int cc = 0; cc < kClasses; ++cc) acc[s][cc] = 0.f;
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-      const int it = c.lane + 32 * k;
-      if (ITEMS % 32 != 0 && it >= ITEMS) continue;
-      float t[2][8];
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) t[s][e] = v[s][k][e];
-        if (drop.thresh) {
-#pragma unroll
-          for (int e = 0; e < 8; e += 2) {
-            float m0, m1;
-            drop_pair(drop, uint32_t(b0 + 2 * c.q + s), uint32_t(cls_off + it * 8 + e), m0, m1);
-            t[s][e] *= m0; t[s][e + 1] *= m1;
-          }
-        }
-      }
-#pragma unroll
-      for (int cc = 0; cc < kClasses; ++cc) {
-        const float* wp = wf + size_t(cc) * drop.D + cls_off + it * 8;
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
-        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-        for (int s = 0; s < 2; ++s)
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[s][cc] = fmaf(t[s][e], w[e], acc[s][cc]);
-      }
-    }
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const int b = b0 + 2 * c.q + s;
-      const float inv = 1.0f / sqrtf(ss[s]);      // no epsilon, like the reference
-#pragma unroll
-      for (int cc = 0; cc < kClasses; ++cc) {
-        const float r = warp_sum(acc[s][cc]) * inv;
-        if (c.lane == 0 && b < batch) atomicAdd(logits + size_t(b) * kClasses + cc, r);
-      }
-    }
-  }
-#pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    const int g = 2 * c.q + s, b = b0 + g;
-    const float nrm = sqrtf(ss[s]);
-    const float inv = b < batch ? 1.0f / nrm : 0.f;      // no epsilon, like the reference
-    if (c.lane == 0 && b < batch && norms) norms[b] = nrm;
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-      const int it = c.lane + 32 * k;
-      if (ITEMS % 32 != 0 && it >= ITEMS) continue;
-      const int row = it / KCS, kc = it - row * KCS;
-      float o[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = v[s][k][e] * inv;
-      *reinterpret_cast<uint4*>(xop + uint32_t(kc) * kCS + row_off(g * kL + row)) = pack_bf16x8(o);
-    }
-  }
-  // the bias column: x[row][DIN] = 1, x[row][DIN+1 .. DIN+15] = 0
-  *reinterpret_cast<uint4*>(xop + uint32_t(KCS) * kCS + row_off(c.wt)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
-  *reinterpret_cast<uint4*>(xop + uint32_t(KCS + 1) * kCS + row_off(c.wt)) = make_uint4(0u, 0u, 0u, 0u);
+// TMA of the X image of (tile, role) into this warpgroup's operand buffer, completion on bar_ld
+__device__ __forceinline__ void sa_issue_x_load(const SaFwdArgs& a, int role, int tile, uint8_t* xop, uint64_t* bar_ld) {
+  const uint32_t bytes = role == 0 ? x_tile_bytes(80) : x_tile_bytes(48);
+  mbar_arrive_expect_tx(bar_ld, bytes);
+  bulk_g2s(xop, static_cast<const uint8_t*>(a.role[role].x_tiles) + size_t(tile) * bytes, bytes, bar_ld);
 }
 
 template <class C>
 __device__ __forceinline__ void sa_fwd_tile(WgCtx& c, const SaFwdArgs& a, const SaRole& R, uint8_t* wsm, uint8_t* bsm,
-                                            const float* ln_s, int tile, bool reverse_unused) {
-  (void)reverse_unused;
-  const int b0 = tile * 8;
+                                            const float* ln_s, int tile, uint64_t* bar_ld, uint32_t& ph_ld,
+                                            int next_tile, int next_role) {
   uint8_t* xop = bsm + SaFwdSmem::X;
   uint8_t* zop = bsm + SaFwdSmem::ZP;
   uint8_t* vop = bsm + SaFwdSmem::V;
-  stage_features<C::DIN>(c, xop, R.feat, R.norms, b0, a.batch, a.logits, a.wf, R.cls_off, a.drop);
-  wg_sync_for_mma(c);
+  // ---- X image of this tile (issued one tile ahead) ------------------------------------------------------------
+  mbar_wait(bar_ld, ph_ld);
+  ph_ld ^= 1;
+  tc_fence_after_sync();
   // ---- Z | V: two MMA chains over the same A operand ---------------------------------------------------------------
   if (c.wt == 0) {
     const uint64_t ax = make_smem_desc(smem_u32(xop), kCS, kRS);
@@ -491,6 +532,8 @@ __device__ __forceinline__ void sa_fwd_tile(WgCtx& c, const SaFwdArgs& a, const 
     umma_commit(c.bar);
   }
   wg_wait_mma(c);
+  // X is dead (Z, V and the scores have read it): the next tile's image lands while this one finishes
+  if (c.wt == 0 && next_tile >= 0) sa_issue_x_load(a, next_role, next_tile, xop, bar_ld);
   {
     float p[16];
     softmax16(c, C::COL_S, false, p);     // SelfAttention has no reverse weights
@@ -535,17 +578,23 @@ __device__ __forceinline__ void sa_fwd_tile(WgCtx& c, const SaFwdArgs& a, const 
 __global__ void __launch_bounds__(kCtaThreads, 1) sa_fwd_kernel(const SaFwdArgs a) {
   extern __shared__ __align__(128) uint8_t sm[];
   using L = SaFwdLayout;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::BAR);    // [0]: weights, [1], [2]: warpgroup MMA barriers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::BAR);    // [0]: weights, [1], [2]: MMA, [3], [4]: X loads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
   float* ln_s = reinterpret_cast<float*>(sm + L::LN);
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int wg = tid >> 7;
+  const int tiles = (a.batch + 7) / 8;
+  uint8_t* bsm = sm + (wg == 0 ? L::WG0 : L::WG1);
   if (tid == 0) {
-    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
     mbar_arrive_expect_tx(&bars[0], SaCfg<80>::W_BYTES + SaCfg<48>::W_BYTES);
     bulk_g2s(sm + L::W0, a.role[0].blobs, SaCfg<80>::W_BYTES, &bars[0]);
     bulk_g2s(sm + L::W1, a.role[1].blobs, SaCfg<48>::W_BYTES, &bars[0]);
   }
+  __syncthreads();
+  // the two warpgroups take the tile's two modalities, alternating: warpgroup wg starts with role wg
+  if ((tid & 127) == 0 && int(blockIdx.x) < tiles) sa_issue_x_load(a, wg, blockIdx.x, bsm + SaFwdSmem::X, &bars[3 + wg]);
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   for (int i = tid; i < 2 * 96; i += kCtaThreads) {
     const int r = i / 96, k = i - r * 96;
@@ -557,15 +606,14 @@ __global__ void __launch_bounds__(kCtaThreads, 1) sa_fwd_kernel(const SaFwdArgs 
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   mbar_wait(&bars[0], 0);
-  const int wg = tid >> 7;
   WgCtx c = make_ctx(wg * kWgThreads, tmem + uint32_t(wg) * 256u, &bars[1 + wg]);
-  uint8_t* bsm = sm + (wg == 0 ? L::WG0 : L::WG1);
-  const int tiles = (a.batch + 7) / 8;
+  uint32_t ph_ld = 0;
   int round = 0;
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++round) {
-    const int role = (wg + round) & 1;     // the two warpgroups take the tile's two modalities, alternating
-    if (role == 0) sa_fwd_tile<SaCfg<80>>(c, a, a.role[0], sm + L::W0, bsm, ln_s, tile, false);
-    else           sa_fwd_tile<SaCfg<48>>(c, a, a.role[1], sm + L::W1, bsm, ln_s + 192, tile, false);
+    const int role = (wg + round) & 1;
+    const int next = tile + int(gridDim.x) < tiles ? tile + int(gridDim.x) : -1;
+    if (role == 0) sa_fwd_tile<SaCfg<80>>(c, a, a.role[0], sm + L::W0, bsm, ln_s, tile, &bars[3 + wg], ph_ld, next, 1);
+    else           sa_fwd_tile<SaCfg<48>>(c, a, a.role[1], sm + L::W1, bsm, ln_s + 192, tile, &bars[3 + wg], ph_ld, next, 0);
   }
   tc_fence_before_sync();
   __syncthreads();

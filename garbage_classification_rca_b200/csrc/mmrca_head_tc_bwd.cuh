@@ -22,38 +22,46 @@
 namespace mmrca {
 namespace htc {
 
+__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float (&f)[8]) {
+  f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+  f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+  f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+  f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // CrossEntropyLoss(weight, label_smoothing), mean reduction (main_both.py:87-93), 4 classes, fused with the two
-// reductions over the batch that need nothing but dlogits and the raw features:
+// reductions over the batch that need nothing but dlogits and the (normalised) features:
 //   db_f[c]          += sum_b dlogits[b][c]
-//   dWf[c][off + j]  += sum_b dlogits[b][c] drop(x[b][j] / ||x_b||)      (feature sources of the concat, fp32)
-// A CTA owns a contiguous slice of samples; thread t owns 8 of the 2048 feature columns for the whole slice
-// (32 register accumulators), so HBM/L2 sees each feature row once, as coalesced 16-byte loads, and the result
-// leaves as one 16-byte atomic per class and 4 columns.  Every CTA recomputes the normaliser sum_b w[y_b] from
-// the labels, so dlogits leave normalised in one pass.  labels == null: dlogits are given (autograd backward).
+//   dWf[c][off + j]  += sum_b dlogits[b][c] drop(xn[b][j])               (feature sources of the concat, fp32 FMAs)
+// grid = (column strips, sample slices).  A strip is one 8-column group kc of one modality's X image (10 image +
+// 6 text strips): for a tile it is 2 KB of contiguous bf16, one 16-byte row per thread.  A slice is 32 tiles = 256
+// samples = one cross-entropy evaluation per thread.  Thread (row r) accumulates the 4 x 8 products of its chunk
+// r % 16 over the slice's tiles in registers; the 16 threads that share a chunk meet in shared memory and leave
+// with one 16-byte atomic per class.  Every CTA recomputes the normaliser sum_b w[y_b] from the labels, so
+// dlogits leave normalised in one pass.  labels == null: dlogits are given (autograd backward).
 // ---------------------------------------------------------------------------------------------------------------
 struct CeFeatArgs {
   const float* logits; const int64_t* labels; const float* cw; float eps; int batch;
   float* dlogits;     // [B][4]: written when labels != null, read otherwise
   float* loss;        // [1], zeroed beforehand (accumulated); CE mode only
   float* g_bf;        // [4] accumulated (null: skip)
-  const float* img; const float* txt;             // [B][1280], [B][768] raw features (null: no feature term)
-  const float* norm_img; const float* norm_txt;   // [B] L2 norms written by the forward
+  const void* x_img; const void* x_txt;           // X images written by prep_feat_kernel (null: no feature term)
   float* g_wf;        // [4][D]
   int off_img, off_txt;                           // first concat column of each feature source
   DropSpec drop;      // drop.D = D
 };
-constexpr int kCeChunk = 64;        // samples staged per pass
-constexpr int kFeatImg = 1280, kFeatTxt = 768;
-static_assert(kFeatImg + kFeatTxt == 8 * 256, "one thread per 8 feature columns");
+constexpr int kCeSliceTiles = 32;
+constexpr int kStripsImg = 80 / 8, kStripsTxt = 48 / 8;
 
 __global__ void __launch_bounds__(256) ce_feat_kernel(const CeFeatArgs a) {
   __shared__ float red[8];
   __shared__ float s_den;
-  __shared__ float4 dl_s[kCeChunk];
-  __shared__ float inv_s[2][kCeChunk];
+  __shared__ float4 dl_s[kCeSliceTiles * 8];
+  __shared__ float part[8][16][33];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool ce = a.labels != nullptr;
+  const int strip = blockIdx.x, tile0 = blockIdx.y * kCeSliceTiles, tiles = (a.batch + 7) / 8;
   float den = float(a.batch);
   if (ce && a.cw) {
     float w = 0.f;
@@ -65,36 +73,22 @@ __global__ void __launch_bounds__(256) ce_feat_kernel(const CeFeatArgs a) {
     __syncthreads();
     den = s_den;
   }
-  const float inv_den = 1.0f / den;
-  float wc[4] = {1.f, 1.f, 1.f, 1.f};
-  if (ce && a.cw) { for (int c = 0; c < 4; ++c) wc[c] = __ldg(a.cw + c); }
-  const int per = (a.batch + gridDim.x - 1) / gridDim.x;
-  const int s0 = blockIdx.x * per, s1 = min(a.batch, s0 + per);
-  // my 8 feature columns
-  const bool is_img = tid * 8 < kFeatImg;
-  const int j = is_img ? tid * 8 : tid * 8 - kFeatImg;
-  const int fw = is_img ? kFeatImg : kFeatTxt;
-  const float* feat = is_img ? a.img : a.txt;
-  const int cat0 = (is_img ? a.off_img : a.off_txt) + j;
-  float acc[4][8];
-#pragma unroll
-  for (int c = 0; c < 4; ++c)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[c][e] = 0.f;
-  float lsum = 0.f, db[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int c0 = s0; c0 < s1; c0 += kCeChunk) {
-    const int n = min(kCeChunk, s1 - c0);
-    if (tid < n) {
-      const int b = c0 + tid;
-      float d[4];
+  // ---- dlogits of my sample --------------------------------------------------------------------------------------
+  {
+    const int b = tile0 * 8 + tid;
+    float d[4] = {0.f, 0.f, 0.f, 0.f}, li = 0.f;
+    if (b < a.batch) {
       if (ce) {
+        const float inv_den = 1.0f / den;
+        float wc[4] = {1.f, 1.f, 1.f, 1.f};
+        if (a.cw) { for (int c = 0; c < 4; ++c) wc[c] = __ldg(a.cw + c); }
         const float4 zz = __ldg(reinterpret_cast<const float4*>(a.logits) + b);
         float z[4] = {zz.x, zz.y, zz.z, zz.w};
         const float m = fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3]));
         const float se = expf(z[0] - m) + expf(z[1] - m) + expf(z[2] - m) + expf(z[3] - m);
         const float lse = m + logf(se);
         const int y = int(a.labels[b]);
-        float t[4], tsum = 0.f, li = 0.f;
+        float t[4], tsum = 0.f;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           t[c] = (a.eps * 0.25f) * wc[c] + (c == y ? (1.f - a.eps) * wc[c] : 0.f);
@@ -102,69 +96,89 @@ __global__ void __launch_bounds__(256) ce_feat_kernel(const CeFeatArgs a) {
           li -= t[c] * z[c];
           tsum += t[c];
         }
-        lsum += li;
+        li *= inv_den;
 #pragma unroll
         for (int c = 0; c < 4; ++c) d[c] = (expf(z[c]) * tsum - t[c]) * inv_den;
-        if (a.dlogits) reinterpret_cast<float4*>(a.dlogits)[b] = make_float4(d[0], d[1], d[2], d[3]);
+        if (strip == 0 && a.dlogits) reinterpret_cast<float4*>(a.dlogits)[b] = make_float4(d[0], d[1], d[2], d[3]);
       } else {
         const float4 dd = __ldg(reinterpret_cast<const float4*>(a.dlogits) + b);
         d[0] = dd.x; d[1] = dd.y; d[2] = dd.z; d[3] = dd.w;
       }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) db[c] += d[c];
-      dl_s[tid] = make_float4(d[0], d[1], d[2], d[3]);
-      if (a.g_wf) { inv_s[0][tid] = 1.0f / __ldg(a.norm_img + b); inv_s[1][tid] = 1.0f / __ldg(a.norm_txt + b); }
     }
-    __syncthreads();
-    if (a.g_wf) {
-#pragma unroll 4
-      for (int i = 0; i < n; ++i) {
-        const int b = c0 + i;
-        const float4 x0 = __ldg(reinterpret_cast<const float4*>(feat + size_t(b) * fw + j));
-        const float4 x1 = __ldg(reinterpret_cast<const float4*>(feat + size_t(b) * fw + j + 4));
-        float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-        const float inv = inv_s[is_img ? 0 : 1][i];
-        if (a.drop.thresh) {
+    dl_s[tid] = make_float4(d[0], d[1], d[2], d[3]);
+    if (strip == 0) {       // the strips of a slice share its samples: one of them owns the loss and the bias gradient
+      li = warp_sum(li);
 #pragma unroll
-          for (int e = 0; e < 8; e += 2) {
-            float m0, m1;
-            drop_pair(a.drop, uint32_t(b), uint32_t(cat0 + e), m0, m1);
-            x[e] *= m0 * inv; x[e + 1] *= m1 * inv;
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) x[e] *= inv;
-        }
-        const float4 d = dl_s[i];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          acc[0][e] = fmaf(d.x, x[e], acc[0][e]); acc[1][e] = fmaf(d.y, x[e], acc[1][e]);
-          acc[2][e] = fmaf(d.z, x[e], acc[2][e]); acc[3][e] = fmaf(d.w, x[e], acc[3][e]);
-        }
-      }
-    }
-    __syncthreads();
-  }
-  if (a.g_wf && s0 < s1) {
-    const bool vec = ((reinterpret_cast<uintptr_t>(a.g_wf) | (size_t(a.drop.D) * 4) | (size_t(cat0) * 4)) & 15) == 0;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float* dst = a.g_wf + size_t(c) * a.drop.D + cat0;
-      if (vec) {
-        atomicAdd(reinterpret_cast<float4*>(dst), make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]));
-        atomicAdd(reinterpret_cast<float4*>(dst) + 1, make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]));
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) atomicAdd(dst + e, acc[c][e]);
+      for (int c = 0; c < 4; ++c) d[c] = warp_sum(d[c]);
+      if (lane == 0) {
+        if (ce && a.loss) atomicAdd(a.loss, li);
+        if (a.g_bf) { for (int c = 0; c < 4; ++c) atomicAdd(a.g_bf + c, d[c]); }
       }
     }
   }
-  lsum = warp_sum(lsum);
+  if (!a.g_wf) return;
+  __syncthreads();
+  // ---- my strip of the feature-source rows of dWf --------------------------------------------------------------------
+  const bool is_img = strip < kStripsImg;
+  const int kc = is_img ? strip : strip - kStripsImg, din = is_img ? 80 : 48;
+  const uint32_t tile_bytes = is_img ? x_tile_bytes(80) : x_tile_bytes(48);
+  const uint8_t* base = static_cast<const uint8_t*>(is_img ? a.x_img : a.x_txt) + uint32_t(kc) * kCS;
+  const int r = tid & 127, half = tid >> 7, chunk = r & 15, g = r >> 4;
+  const int col0 = (is_img ? a.off_img : a.off_txt) + chunk * din + kc * 8;      // my 8 concat columns
+  float acc[4][8];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) db[c] = warp_sum(db[c]);
-  if (lane == 0 && warp * 32 < kCeChunk) {
-    if (ce && a.loss) atomicAdd(a.loss, lsum * inv_den);
-    if (a.g_bf) { for (int c = 0; c < 4; ++c) atomicAdd(a.g_bf + c, db[c]); }
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[c][e] = 0.f;
+  uint4 raw[kCeSliceTiles / 2];
+#pragma unroll
+  for (int i = 0; i < kCeSliceTiles / 2; ++i) {       // the slice's 16 loads of this thread in flight together
+    const int t = tile0 + 2 * i + half;
+    raw[i] = t < tiles ? __ldg(reinterpret_cast<const uint4*>(base + size_t(t) * tile_bytes + row_off(r))) : make_uint4(0u, 0u, 0u, 0u);
+  }
+#pragma unroll
+  for (int i = 0; i < kCeSliceTiles / 2; ++i) {
+    const int tl = 2 * i + half, t = tile0 + tl;
+    float x[8];
+    unpack_bf16x8(raw[i], x);
+    if (a.drop.thresh) {
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) {
+        float m0, m1;
+        drop_pair(a.drop, uint32_t(t * 8 + g), uint32_t(col0 + e), m0, m1);
+        x[e] *= m0; x[e + 1] *= m1;
+      }
+    }
+    const float4 d = dl_s[tl * 8 + g];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[0][e] = fmaf(d.x, x[e], acc[0][e]); acc[1][e] = fmaf(d.y, x[e], acc[1][e]);
+      acc[2][e] = fmaf(d.z, x[e], acc[2][e]); acc[3][e] = fmaf(d.w, x[e], acc[3][e]);
+    }
+  }
+  // lanes l and l ^ 16 own the same chunk; then the 8 warps meet in shared memory
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[c][e] += __shfl_xor_sync(0xffffffffu, acc[c][e], 16);
+      if (lane < 16) part[warp][lane][c * 8 + e] = acc[c][e];
+    }
+  __syncthreads();
+  if (tid < 128) {       // thread -> (chunk, class, 4 columns)
+    const int ch = tid >> 3, c = (tid >> 1) & 3, e0 = (tid & 1) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int w = 0; w < 8; ++w)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] += part[w][ch][c * 8 + e0 + e];
+    float* dst = a.g_wf + size_t(c) * a.drop.D + (is_img ? a.off_img : a.off_txt) + ch * din + kc * 8 + e0;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      atomicAdd(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) atomicAdd(dst + e, v[e]);
+    }
   }
 }
 
@@ -196,12 +210,6 @@ __device__ __forceinline__ void cta_wait_mma(BwCtx& c) {
   mbar_wait(c.bar, c.ph);
   c.ph ^= 1;
   tc_fence_after_sync();
-}
-__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float (&f)[8]) {
-  f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
-  f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
-  f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
-  f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
 }
 __device__ __forceinline__ void ld16f(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
@@ -640,8 +648,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
 // self-attention backward (features frozen: parameter gradients only), one modality per launch
 // ---------------------------------------------------------------------------------------------------------------
 struct SaBwdArgs {
-  const float* feat;              // [B][16*DIN]
-  const void* blobs;              // bz | bv | bc
+  const void* x_tiles;            // [tiles][x_tile_bytes(DIN)]: normalised bf16 operand images (prep_feat_kernel)
+  const void* blobs;              // bz | bv
   const float* ln_g; const float* ln_b;
   const void* dout_a; const void* dout_b;   // dOut = a + b (images written by ca_bwd_kernel)
   float* gm;                      // [DIN][128]
@@ -651,10 +659,11 @@ struct SaBwdArgs {
 template <int DIN_>
 struct SaBwdSmem {
   using C = SaCfg<DIN_>;
-  static constexpr uint32_t X = 0;                                   // [128 x (DIN+16)]
-  static constexpr uint32_t ZP = X + op_bytes(C::KE);                // Z [128 x DIN]; later P
-  static constexpr uint32_t ZP_BYTES = op_bytes(DIN_) > 2 * kPHalf ? op_bytes(DIN_) : 2 * kPHalf;
-  static constexpr uint32_t V = ZP + ZP_BYTES;                       // [128 x 96]; later dV
+  // two equal buffers that swap roles every tile: X [128 x (DIN+16)] (TMA destination) and Z [128 x DIN], later P
+  static constexpr uint32_t XZ_BYTES = op_bytes(C::KE) > 2 * kPHalf ? op_bytes(C::KE) : 2 * kPHalf;
+  static constexpr uint32_t XZ0 = 0;
+  static constexpr uint32_t XZ1 = XZ0 + XZ_BYTES;
+  static constexpr uint32_t V = XZ1 + XZ_BYTES;                      // [128 x 96]; later dV
   static constexpr uint32_t DC = V + op_bytes(96);                   // [128 x 96]
   static constexpr uint32_t DYX = DC + op_bytes(96);                 // [128 x 192]: dy*xhat | dy; later dZ [128 x DIN]
   static constexpr uint32_t DLS = DYX + op_bytes(192);               // dS (2 x [64 x 64])
@@ -677,7 +686,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) sa_bwd_kernel(const SaBwdArgs 
   extern __shared__ __align__(128) uint8_t sm[];
   using S = SaBwdSmem<DIN_>; using T = SaBwdCols<DIN_>; using C = SaCfg<DIN_>;
   constexpr int DIN = DIN_, DV = C::DV;
-  // mbarriers: [0] weights, [1] MMAs read back next, [2] dOut images (TMA), [3] unused, [4] G2: dgamma|dbeta,
+  // mbarriers: [0] weights, [1] MMAs read back next, [2] dOut images (TMA), [3] X image (TMA), [4] G2: dgamma|dbeta,
   //            [5] G3: dM, dWv  (G*: persistent accumulators, waited for only before an operand buffer is reused)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
@@ -699,66 +708,24 @@ __global__ void __launch_bounds__(kCtaThreads, 1) sa_bwd_kernel(const SaBwdArgs 
   const uint32_t tmem = *tmem_slot;
   mbar_wait(&bars[0], 0);
   BwCtx c = make_bwctx(tmem, &bars[1]);
-  uint32_t ph_ld = 0, ph_g2 = 0, ph_g3 = 0;
-  uint8_t *xb = sm + S::X, *zp = sm + S::ZP, *vb = sm + S::V, *dcb = sm + S::DC, *dyx = sm + S::DYX, *dls = sm + S::DLS,
+  uint32_t ph_ld = 0, ph_x = 0, ph_g2 = 0, ph_g3 = 0;
+  uint8_t *xb = sm + S::XZ0, *zp = sm + S::XZ1, *vb = sm + S::V, *dcb = sm + S::DC, *dyx = sm + S::DYX, *dls = sm + S::DLS,
           *ones = sm + S::ONES, *wsm = sm + S::W;
   const uint8_t* bz = wsm; const uint8_t* bv = wsm + C::BZ_BYTES;
   const int tiles = (a.batch + 7) / 8;
+  constexpr uint32_t kXBytes = x_tile_bytes(DIN);
+  auto issue_x = [&](int t, uint8_t* dst) {
+    mbar_arrive_expect_tx(&bars[3], kXBytes);
+    bulk_g2s(dst, static_cast<const uint8_t*>(a.x_tiles) + size_t(t) * kXBytes, kXBytes, &bars[3]);
+  };
+  if (tid == 0 && int(blockIdx.x) < tiles) issue_x(blockIdx.x, xb);
   bool first = true;
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int b0 = tile * 8;
-    // ---- P0: features -> normalised bf16 operand (8 warps, one sample each).  The global loads are issued before
-    //      waiting for the previous tile's dM / dWv MMAs (G3), which still read the operand buffers. -----------------
-    {
-      constexpr int KCS = DIN / 8, ITEMS = kL * KCS, PER = (ITEMS + 31) / 32;
-      const int g = warp, b = b0 + g;
-      const float* base = a.feat + size_t(b) * (kL * DIN);
-      float v[PER][8];
-      float ss0 = 0.f, ss1 = 0.f;
-#pragma unroll
-      for (int k = 0; k < PER; ++k) {
-        const int it = c.lane + 32 * k;
-        float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
-        if (b < a.batch && (ITEMS % 32 == 0 || it < ITEMS)) {
-          lo = __ldg(reinterpret_cast<const float4*>(base + it * 8));
-          hi = __ldg(reinterpret_cast<const float4*>(base + it * 8 + 4));
-        }
-        v[k][0] = lo.x; v[k][1] = lo.y; v[k][2] = lo.z; v[k][3] = lo.w; v[k][4] = hi.x; v[k][5] = hi.y; v[k][6] = hi.z; v[k][7] = hi.w;
-      }
-      {   // next tile of this CTA -> L2
-        const int nb0 = (tile + int(gridDim.x)) * 8;
-        const size_t off = size_t(nb0) * (kL * DIN) + size_t(tid) * 32;
-        if (nb0 + 8 <= a.batch && tid * 32 < 8 * kL * DIN) {
-          prefetch_l2(a.feat + off);
-          if (tid * 32 + 256 * 32 < 8 * kL * DIN) prefetch_l2(a.feat + off + 256 * 32);
-        }
-      }
-      if (!first) mbar_wait_ph(&bars[5], ph_g3);
-      if (tid == 0) {     // dOut images of this tile -> the (now free) dy*xhat | dy buffer
-        mbar_arrive_expect_tx(&bars[2], 2 * kSaTileBytes);
-        bulk_g2s(dyx, static_cast<const uint8_t*>(a.dout_a) + size_t(tile) * kSaTileBytes, kSaTileBytes, &bars[2]);
-        bulk_g2s(dyx + kSaTileBytes, static_cast<const uint8_t*>(a.dout_b) + size_t(tile) * kSaTileBytes, kSaTileBytes, &bars[2]);
-      }
-#pragma unroll
-      for (int k = 0; k < PER; ++k)
-#pragma unroll
-        for (int e = 0; e < 8; e += 2) { ss0 = fmaf(v[k][e], v[k][e], ss0); ss1 = fmaf(v[k][e + 1], v[k][e + 1], ss1); }
-      const float nrm = sqrtf(warp_sum(ss0 + ss1));
-      const float inv = b < a.batch ? 1.0f / nrm : 0.f;
-#pragma unroll
-      for (int k = 0; k < PER; ++k) {
-        const int it = c.lane + 32 * k;
-        if (ITEMS % 32 != 0 && it >= ITEMS) continue;
-        const int row = it / KCS, kc = it - row * KCS;
-        float o[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = v[k][e] * inv;
-        *reinterpret_cast<uint4*>(xb + uint32_t(kc) * kCS + row_off(g * kL + row)) = pack_bf16x8(o);
-      }
-      if (tid < 128) write_bias_columns(xb, KCS, tid);
-    }
-    cta_sync_for_mma();
-    // ---- P1: Z, V ------------------------------------------------------------------------------------------------------
+    // ---- P0/P1: X image (prefetched during the previous tile) -> Z, V.  While they run: wait for the previous
+    //      tile's dM / dWv MMAs (G3), which still read the buffers about to be rewritten (the old X = this tile's
+    //      Z buffer, dV, dZ), then fetch this tile's dOut images into the dy*xhat | dy buffer. -------------------
+    mbar_wait(&bars[3], ph_x); ph_x ^= 1;
+    tc_fence_after_sync();
     if (tid == 0) {
       const uint64_t ax = make_smem_desc(smem_u32(xb), kCS, kRS);
       mma_steps(tmem + T::Z, ax, 2 * kCS, make_smem_desc(smem_u32(bz), C::BZ_LBO, 128), 2 * C::BZ_LBO,
@@ -766,6 +733,12 @@ __global__ void __launch_bounds__(kCtaThreads, 1) sa_bwd_kernel(const SaBwdArgs 
       mma_steps(tmem + T::V, ax, 2 * kCS, make_smem_desc(smem_u32(bv), C::BV_LBO, 128), 2 * C::BV_LBO,
                 make_idesc_bf16(128, DV, 0, 0), C::KE / 16, false);
       umma_commit(c.bar);
+    }
+    if (!first) mbar_wait_ph(&bars[5], ph_g3);
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&bars[2], 2 * kSaTileBytes);
+      bulk_g2s(dyx, static_cast<const uint8_t*>(a.dout_a) + size_t(tile) * kSaTileBytes, kSaTileBytes, &bars[2]);
+      bulk_g2s(dyx + kSaTileBytes, static_cast<const uint8_t*>(a.dout_b) + size_t(tile) * kSaTileBytes, kSaTileBytes, &bars[2]);
     }
     cta_wait_mma(c);
     {
@@ -880,6 +853,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) sa_bwd_kernel(const SaBwdArgs 
       umma_commit(c.bar);
     }
     cta_wait_mma(c);
+    // P is dead: the next tile's X image lands in its buffer while this tile finishes
+    if (tid == 0 && tile + int(gridDim.x) < tiles) issue_x(tile + int(gridDim.x), zp);
     mbar_wait_ph(&bars[4], ph_g2);                 // dgamma|dbeta have read dy*xhat | dy: its bytes become dZ
     if (c.w == 0) { acc_cols_to_operand(c, T::DZ, 0, DIN, dyx, c.rs); acc_cols_to_operand(c, T::DV, 0, 16, vb, c.rs); }
     else acc_cols_to_operand(c, T::DV, 16, 96, vb, c.rs);
@@ -892,6 +867,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) sa_bwd_kernel(const SaBwdArgs 
       umma_commit(&bars[5]);
     }
     first = false;
+    { uint8_t* t_ = xb; xb = zp; zp = t_; }        // the prefetched image is the next tile's X
   }
   if (!first) {
     mbar_wait_ph(&bars[5], ph_g3);
@@ -920,43 +896,56 @@ struct FinBlock {
   int din, dkq;
 };
 struct FinArgs { FinBlock blk[4]; int nblk; };
+constexpr int kFinRows = 8;                                         // rows n of W_query / W_key per CTA
+constexpr uint32_t kFinSmemBytes = (96 * 98 + 2 * kFinRows * 96 + kFinRows) * 4;
 
+// grid.x = sum over blocks of d_kq / 8.  CTA = (block, 8 rows n): dM (d_in x (d_in + 1), du in the last column) and the
+// 8 rows of W_query / W_key are staged in shared memory with every load in flight at once, then each thread owns
+// outputs (n, k): dWq[n][k] += s sum_k' dM[k][k'] Wk[n][k'],  dWk[n][k'] += s (sum_k Wq[n][k] dM[k][k'] + bq[n] du[k']),
+// dbq[n] += s sum_k' du[k'] Wk[n][k'].  Every output has exactly one owner: plain read-modify-write accumulation.
 __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
-  // blockIdx.y = block; consecutive threads own consecutive k (coalesced gm rows, broadcast weight reads)
-  const FinBlock& B = a.blk[blockIdx.y];
+  extern __shared__ __align__(16) float fsm[];
+  int b = 0, grp = blockIdx.x;
+  for (; b < a.nblk; ++b) {
+    const int g = a.blk[b].dkq / kFinRows;
+    if (grp < g) break;
+    grp -= g;
+  }
+  if (b >= a.nblk) return;
+  const FinBlock& B = a.blk[b];
+  const int din = B.din, gs = din + 1, n0 = grp * kFinRows, tid = threadIdx.x;   // odd stride: conflict-free both ways
+  float* g_s = fsm;                          // [din][gs]: g_s[k'][k] = dM[k][k'], g_s[k'][din] = du[k']
+  float* wk_s = g_s + din * gs;              // [8][din]
+  float* wq_s = wk_s + kFinRows * din;       // [8][din]
+  float* bq_s = wq_s + kFinRows * din;       // [8]
+  for (int i = tid; i < din * (din + 1); i += 256) {
+    const int kp = i / (din + 1), k = i - kp * (din + 1);
+    g_s[kp * gs + k] = __ldg(B.gm + size_t(kp) * 128 + k);
+  }
+  for (int i = tid; i < kFinRows * din; i += 256) {
+    wk_s[i] = __ldg(B.wk + size_t(n0) * din + i);
+    wq_s[i] = __ldg(B.wq + size_t(n0) * din + i);
+  }
+  if (tid < kFinRows) bq_s[tid] = __ldg(B.bq + n0 + tid);
+  __syncthreads();
   const float s = rsqrtf(float(B.dkq));
-  const int nw = B.dkq * B.din, din = B.din;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 2 * nw + B.dkq; t += gridDim.x * blockDim.x) {
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-    if (t < nw) {              // dWq[n][k] += s sum_k' dM[k][k'] Wk[n][k']
-      const int n = t / din, k = t - n * din;
-      const float* g = B.gm + k;
-      const float* w = B.wk + size_t(n) * din;
+  for (int o = tid; o < kFinRows * din; o += 256) {
+    const int nl = o / din, k = o - nl * din;
+    float q0 = 0.f, q1 = 0.f, k0 = bq_s[nl] * g_s[k * gs + din], k1 = 0.f;
 #pragma unroll 4
-      for (int kp = 0; kp < din; kp += 4) {
-        acc0 = fmaf(__ldg(g + size_t(kp) * 128), __ldg(w + kp), acc0);
-        acc1 = fmaf(__ldg(g + size_t(kp + 1) * 128), __ldg(w + kp + 1), acc1);
-        acc2 = fmaf(__ldg(g + size_t(kp + 2) * 128), __ldg(w + kp + 2), acc2);
-        acc3 = fmaf(__ldg(g + size_t(kp + 3) * 128), __ldg(w + kp + 3), acc3);
-      }
-      atomicAdd(B.g_wq + t, (acc0 + acc1 + acc2 + acc3) * s);
-    } else if (t < 2 * nw) {   // dWk[n][k'] += s (sum_k Wq[n][k] dM[k][k'] + bq[n] du[k'])
-      const int u = t - nw, n = u / din, kp = u - n * din;
-      const float* g = B.gm + size_t(kp) * 128;
-      const float* w = B.wq + size_t(n) * din;
-      acc0 = __ldg(B.bq + n) * __ldg(g + din);
-#pragma unroll 4
-      for (int k = 0; k < din; k += 4) {
-        const float4 gv = __ldg(reinterpret_cast<const float4*>(g + k));
-        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + k));
-        acc0 = fmaf(gv.x, wv.x, acc0); acc1 = fmaf(gv.y, wv.y, acc1); acc2 = fmaf(gv.z, wv.z, acc2); acc3 = fmaf(gv.w, wv.w, acc3);
-      }
-      atomicAdd(B.g_wk + u, (acc0 + acc1 + acc2 + acc3) * s);
-    } else {                   // dbq[n] += s sum_k' du[k'] Wk[n][k']
-      const int n = t - 2 * nw;
-      for (int kp = 0; kp < din; ++kp) acc0 = fmaf(__ldg(B.gm + size_t(kp) * 128 + din), __ldg(B.wk + size_t(n) * din + kp), acc0);
-      atomicAdd(B.g_bq + n, acc0 * s);
+    for (int j = 0; j < din; j += 2) {
+      q0 = fmaf(g_s[j * gs + k], wk_s[nl * din + j], q0);
+      q1 = fmaf(g_s[(j + 1) * gs + k], wk_s[nl * din + j + 1], q1);
+      k0 = fmaf(wq_s[nl * din + j], g_s[k * gs + j], k0);
+      k1 = fmaf(wq_s[nl * din + j + 1], g_s[k * gs + j + 1], k1);
     }
+    B.g_wq[size_t(n0) * din + o] += (q0 + q1) * s;
+    B.g_wk[size_t(n0) * din + o] += (k0 + k1) * s;
+  }
+  if (tid < kFinRows) {
+    float acc = 0.f;
+    for (int j = 0; j < din; ++j) acc = fmaf(g_s[j * gs + din], wk_s[tid * din + j], acc);
+    B.g_bq[n0 + tid] += acc * s;
   }
 }
 

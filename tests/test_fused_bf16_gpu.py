@@ -204,10 +204,11 @@ def test_fused_train_step_weighted_smoothed_dropout(pkg, B):
     if B >= 64:
         ours = {n: v.cpu().numpy() / 2.0 for n, v in zip(names, step.grads.views)}
         check_bf16_grads(ours, ref["grads"], f"train step B={B}")
-    # the fp32 rows of the classifier gradient (feature sources, ce_feat_kernel) are exact to fp32 rounding
+    # the feature-source rows of the classifier gradient (ce_feat_kernel): fp32 products of the bf16-rounded normalised
+    # features (2^-9 relative per element)
     gw = step.grads.views[names.index("final_with_everything.weight")].cpu().numpy() / 2.0
     rw = ref["grads"]["final_with_everything.weight"]
-    assert np.abs(gw[:, 1536:] - rw[:, 1536:]).max() <= 2e-3 * np.abs(rw[:, 1536:]).max() + 1e-7
+    assert np.abs(gw[:, 1536:] - rw[:, 1536:]).max() <= 6e-3 * np.abs(rw[:, 1536:]).max() + 1e-7
 
 
 def test_dropout_mask_is_a_pure_function_of_the_seed(pkg):

@@ -60,5 +60,33 @@ def full(path):
         print()
 
 
+LABELS = (("ca_bwd_kernel", "ca_bwd_bf16"), ("sa_bwd_kernel<80>", "sa_bwd_bf16<80>"), ("sa_bwd_kernel<48>", "sa_bwd_bf16<48>"),
+          ("sa_fwd_kernel", "sa_fwd_bf16"), ("ca_fwd_kernel", "ca_fwd_bf16"), ("ce_feat_kernel", "ce_feat"),
+          ("prep_kernel", "prep_bf16"), ("finalize_kernel", "finalize_bf16"), ("bwd_kernel", "bwd_bf16"))
+
+
+def traffic(path, batch):
+    """profiles/traffic.json: DRAM bytes (read + write) per launch of each kernel of the step, keyed by the
+    labels bench.py uses, averaged over the captured launches."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    mult = lambda u: {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+    acc = collections.OrderedDict()
+    for r in rows[2:]:
+        label = next((lab for key, lab in LABELS if key in r[ki]), None)
+        if label is None:
+            continue
+        b = float(r[ri].replace(",", "")) * mult(units[ri]) + float(r[wi].replace(",", "")) * mult(units[wi])
+        acc.setdefault(label, []).append(b)
+    print(json.dumps({"batch": int(batch), "source": path.split("/")[-1], "what": "dram__bytes_read.sum + dram__bytes_write.sum per launch",
+                      "kernels": {k: sum(v) / len(v) for k, v in acc.items()}}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else 4096)
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
