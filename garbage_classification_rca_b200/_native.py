@@ -57,7 +57,7 @@ EXPORTS = ("mmrca_query", "mmrca_last_error", "mmrca_head_workspace_bytes", "mmr
            "mmrca_head_backward", "mmrca_cross_entropy", "mmrca_head_train_step", "mmrca_attention_forward",
            "mmrca_attention_backward_scratch_bytes", "mmrca_attention_backward", "mmrca_timing_begin",
            "mmrca_timing_end", "mmrca_dev_umma_selftest", "mmrca_attention_forward_scratch_bytes",
-           "mmrca_head_workspace_offset", "mmrca_dropout_mask")
+           "mmrca_head_workspace_offset", "mmrca_dropout_mask", "mmrca_dev_set_debug")
 
 
 def _sources_newer_than_lib() -> bool:
@@ -144,6 +144,8 @@ def lib() -> C.CDLL:
         L.mmrca_dev_umma_selftest.restype = C.c_int
         L.mmrca_dropout_mask.argtypes = [C.c_uint64, C.c_float, C.c_int32, C.c_int32, _fp, _fp]
         L.mmrca_dropout_mask.restype = C.c_int
+        L.mmrca_dev_set_debug.argtypes = [_fp]
+        L.mmrca_dev_set_debug.restype = C.c_int
         if L.mmrca_query(QUERY_ABI_VERSION) != ABI_VERSION:
             raise RuntimeError("libmmrca.so ABI version mismatch: rebuild it")
         _lib = L

@@ -18,6 +18,7 @@ namespace mmrca {
 
 static thread_local char g_err[512] = "";
 static thread_local int g_launches = 0;
+static long long* g_dbg = nullptr;   // development: device buffer for per-phase clock stamps (mmrca_dev_set_debug)
 
 // ---- optional per-kernel timing (mmrca_timing_begin / _end) -------------------------------------
 struct TimingRec { const char* name; cudaEvent_t e0, e1; };
@@ -205,6 +206,8 @@ struct Workspace {
   void* t_img; void* i_img;                                         // SA output images, [tiles][kSaTileBytes]
   void* x_img; void* x_txt;                                         // normalised feature images (SA inputs)
   void* dx_img[4];                                                  // training: dXq / dXkv images of CA1, then CA2
+  void* sa_v[2]; void* sa_p[2];                                     // training: V / P images kept by the SA forward (img, txt)
+  float2* sa_stats[2];                                              // training: LayerNorm (mean, rstd) per context row
   float* gm[4]; size_t gm_floats;                                   // training: dM_ext^T per block (contiguous)
   size_t bytes;
 };
@@ -264,6 +267,10 @@ static Workspace carve(const MmrcaHeadDesc& d, bool training, void* base) {
     if (d.compute != MMRCA_COMPUTE_FP32) {
       const size_t tiles = (B + 7) / 8;
       for (int i = 0; i < 4; ++i) w.dx_img[i] = take(tiles * htc::kSaTileBytes / 4);
+      for (int i = 0; i < 2; ++i) {
+        w.sa_v[i] = take(tiles * htc::kSaTileBytes / 4); w.sa_p[i] = take(tiles * (2 * htc::kPHalf) / 4);
+        w.sa_stats[i] = reinterpret_cast<float2*>(take(tiles * 256));
+      }
       const int dins[4] = {80, 48, MMRCA_SA_DV, MMRCA_SA_DV};
       char* g0 = p + off;
       for (int i = 0; i < 4; ++i) { w.gm[i] = reinterpret_cast<float*>(p + off); off += size_t(dins[i]) * 128 * 4; }
@@ -391,9 +398,9 @@ static int head_forward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, 
     htc::SaFwdArgs a;
     memset(&a, 0, sizeof(a));
     a.role[0].x_tiles = w.x_img; a.role[0].ln_g = p.sa_img.ln_g; a.role[0].ln_b = p.sa_img.ln_b;
-    a.role[0].blobs = w.fblob[0]; a.role[0].out_tiles = w.i_img;
+    a.role[0].blobs = w.fblob[0]; a.role[0].out_tiles = w.i_img; a.role[0].v_tiles = w.sa_v[0]; a.role[0].p_tiles = w.sa_p[0]; a.role[0].ln_stats = w.sa_stats[0];
     a.role[1].x_tiles = w.x_txt; a.role[1].ln_g = p.sa_txt.ln_g; a.role[1].ln_b = p.sa_txt.ln_b;
-    a.role[1].blobs = w.fblob[1]; a.role[1].out_tiles = w.t_img;
+    a.role[1].blobs = w.fblob[1]; a.role[1].out_tiles = w.t_img; a.role[1].v_tiles = w.sa_v[1]; a.role[1].p_tiles = w.sa_p[1]; a.role[1].ln_stats = w.sa_stats[1];
     a.batch = d.batch;
     if ((rc = set_smem(htc::sa_fwd_kernel, htc::SaFwdLayout::BYTES))) return rc;
     LaunchScope ls("sa_fwd_bf16", st);
@@ -447,7 +454,8 @@ static int head_backward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p,
     // text SA output: query source of CA1, key/value source of CA2; image SA output: the other way round
     htc::SaBwdArgs a;
     memset(&a, 0, sizeof(a));
-    a.x_tiles = w.x_img; a.blobs = w.fblob[0]; a.ln_g = p.sa_img.ln_g; a.ln_b = p.sa_img.ln_b;
+    a.dbg = g_dbg;
+    a.x_tiles = w.x_img; a.v_tiles = w.sa_v[0]; a.p_tiles = w.sa_p[0]; a.ln_stats = w.sa_stats[0]; a.ln_g = p.sa_img.ln_g; a.ln_b = p.sa_img.ln_b;
     a.dout_a = w.dx_img[1]; a.dout_b = w.dx_img[2];
     a.gm = w.gm[0]; a.g_wv = g.sa_img.wv; a.g_bv = g.sa_img.bv; a.g_ln_g = g.sa_img.ln_g; a.g_ln_b = g.sa_img.ln_b;
     a.batch = d.batch;
@@ -457,7 +465,8 @@ static int head_backward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p,
       htc::sa_bwd_kernel<80><<<min(tiles, sms), htc::kCtaThreads, htc::SaBwdSmem<80>::BYTES, st>>>(a);
     }
     MMRCA_CUDA(cudaGetLastError());
-    a.x_tiles = w.x_txt; a.blobs = w.fblob[1]; a.ln_g = p.sa_txt.ln_g; a.ln_b = p.sa_txt.ln_b;
+    a.dbg = nullptr;
+    a.x_tiles = w.x_txt; a.v_tiles = w.sa_v[1]; a.p_tiles = w.sa_p[1]; a.ln_stats = w.sa_stats[1]; a.ln_g = p.sa_txt.ln_g; a.ln_b = p.sa_txt.ln_b;
     a.dout_a = w.dx_img[0]; a.dout_b = w.dx_img[3];
     a.gm = w.gm[1]; a.g_wv = g.sa_txt.wv; a.g_bv = g.sa_txt.bv; a.g_ln_g = g.sa_txt.ln_g; a.g_ln_b = g.sa_txt.ln_b;
     if ((rc = set_smem(htc::sa_bwd_kernel<48>, htc::SaBwdSmem<48>::BYTES))) return rc;
@@ -721,6 +730,10 @@ int mmrca_head_forward(const MmrcaHeadDesc* desc, const MmrcaHeadParams* params,
   if ((rc = device_info(&di))) return rc;
   Workspace w = carve(*desc, false, workspace);
   if (workspace_bytes < w.bytes) return fail(MMRCA_ERR_WORKSPACE, "workspace too small%s%s");
+  {   // a training-size workspace announces a backward: the forward then keeps what the backward reloads
+    const Workspace wt = carve(*desc, true, workspace);
+    if (workspace_bytes >= wt.bytes) w = wt;
+  }
   return head_forward_impl(*desc, *params, img_feat, txt_feat, drop_mask, drop_scale, logits, w, di.sms,
                            static_cast<cudaStream_t>(stream));
 }
@@ -845,6 +858,8 @@ int mmrca_dropout_mask(uint64_t seed, float p, int32_t batch, int32_t width, uin
   MMRCA_CUDA(cudaGetLastError());
   return MMRCA_OK;
 }
+
+int mmrca_dev_set_debug(void* device_buffer_256_int64) { g_dbg = static_cast<long long*>(device_buffer_256_int64); return MMRCA_OK; }
 
 int mmrca_dev_umma_selftest(int32_t mode, const float* a, const float* b, float* out, int32_t n, int32_t k,
                             void* stream) {

@@ -338,8 +338,10 @@ __device__ __forceinline__ void wg_wait_mma(WgCtx& c) {
 // K-major operand (rows x K cols, chunk stride cs): D (+)= A B^T over `ksteps` K=16 steps
 __device__ __forceinline__ void mma_steps(uint32_t d, uint64_t ad, uint32_t a_step, uint64_t bd, uint32_t b_step,
                                           uint32_t idesc, int ksteps, bool acc) {
-  for (int ks = 0; ks < ksteps; ++ks)
-    umma_bf16(d, desc_advance(ad, ks * a_step), desc_advance(bd, ks * b_step), idesc, (acc || ks > 0) ? 1u : 0u);
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks)        // every chain here has at most 8 K-steps: unrolled, descriptors by immediate adds
+    if (ks < ksteps)
+      umma_bf16(d, desc_advance(ad, ks * a_step), desc_advance(bd, ks * b_step), idesc, (acc || ks > 0) ? 1u : 0u);
 }
 
 // TMEM columns [c0, c0+16) of my row -> bf16 -> two 16-byte chunks of a 128-row operand
@@ -466,6 +468,9 @@ struct SaRole {
   const float* ln_g; const float* ln_b;
   const void* blobs;      // bz | bv, contiguous
   void* out_tiles;        // [tiles][kSaTileBytes]
+  void* v_tiles;          // training: V operand images [tiles][op_bytes(96)] for the backward (null: not kept)
+  void* p_tiles;          // training: attention-weight images [tiles][2 * kPHalf]
+  float2* ln_stats;       // training: (mean, rstd) of every context row, [tiles][128]
 };
 struct SaFwdArgs {
   SaRole role[2];         // 0: image (DIN 80), 1: text (DIN 48)
@@ -530,6 +535,8 @@ __device__ __forceinline__ void sa_fwd_tile(WgCtx& c, const SaFwdArgs& a, const 
                 2 * kCS, make_smem_desc(smem_u32(xop + h * 8 * kRS), kCS, kRS), 2 * kCS,
                 make_idesc_bf16(64, 64, 0, 0), C::DIN / 16, false);
     umma_commit(c.bar);
+    // training: the backward reloads V (and P, below) instead of recomputing the projections and the softmax
+    if (R.v_tiles) { bulk_s2g(static_cast<uint8_t*>(R.v_tiles) + size_t(tile) * kSaTileBytes, vop, kSaTileBytes); bulk_commit(); }
   }
   wg_wait_mma(c);
   // X is dead (Z, V and the scores have read it): the next tile's image lands while this one finishes
@@ -548,12 +555,14 @@ __device__ __forceinline__ void sa_fwd_tile(WgCtx& c, const SaFwdArgs& a, const 
                 2 * kPCS, make_smem_desc(smem_u32(vop + h * 8 * kRS), kRS, kCS), 2 * kRS,
                 make_idesc_bf16(64, C::DV, 0, 1), 4, false);
     umma_commit(c.bar);
+    if (R.p_tiles) { bulk_s2g(static_cast<uint8_t*>(R.p_tiles) + size_t(tile) * (2 * kPHalf), zop, 2 * kPHalf); bulk_commit(); }
   }
   wg_wait_mma(c);
   // ---- LayerNorm + ReLU (multimodal_model.py:65-66) -> bf16 image row ------------------------------------------
   {
     float mean, rstd;
     ln_stats_tmem<C::DV>(c, C::COL_C, mean, rstd);
+    if (R.ln_stats) R.ln_stats[size_t(tile) * 128 + c.rs] = make_float2(mean, rstd);
     uint8_t* dst = static_cast<uint8_t*>(R.out_tiles) + size_t(tile) * kSaTileBytes + row_off(c.rs);
 #pragma unroll
     for (int c0 = 0; c0 < C::DV; c0 += 16) {
@@ -570,6 +579,7 @@ __device__ __forceinline__ void sa_fwd_tile(WgCtx& c, const SaFwdArgs& a, const 
       *reinterpret_cast<uint4*>(dst + uint32_t((c0 >> 3) + 1) * kCS) = pack_bf16x8(hi);
     }
   }
+  if (c.wt == 0 && R.v_tiles) bulk_wait_read();   // the V / P stores have read their buffers
   tc_fence_before_sync();
   named_bar_sync(1 + c.wg, kWgThreads);   // TMEM columns and operand buffers are reused by the next tile
   tc_fence_after_sync();
@@ -615,6 +625,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) sa_fwd_kernel(const SaFwdArgs 
     if (role == 0) sa_fwd_tile<SaCfg<80>>(c, a, a.role[0], sm + L::W0, bsm, ln_s, tile, &bars[3 + wg], ph_ld, next, 1);
     else           sa_fwd_tile<SaCfg<48>>(c, a, a.role[1], sm + L::W1, bsm, ln_s + 192, tile, &bars[3 + wg], ph_ld, next, 0);
   }
+  if ((tid & 127) == 0) bulk_wait_all();        // this thread's V / P stores are complete before the CTA retires
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);

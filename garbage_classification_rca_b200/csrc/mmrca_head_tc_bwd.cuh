@@ -645,39 +645,47 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// self-attention backward (features frozen: parameter gradients only), one modality per launch
+// self-attention backward (features frozen: parameter gradients only), one modality per launch.
+// Nothing of the forward is recomputed except C = P V (one MMA, so that the LayerNorm backward sees exactly the
+// fp32 context the forward normalised): X comes from prep_feat_kernel's image, V and P from the images the forward
+// kept, all by TMA, one whole tile ahead into the other half of a double buffer.
 // ---------------------------------------------------------------------------------------------------------------
 struct SaBwdArgs {
   const void* x_tiles;            // [tiles][x_tile_bytes(DIN)]: normalised bf16 operand images (prep_feat_kernel)
-  const void* blobs;              // bz | bv
+  const void* v_tiles;            // [tiles][op_bytes(96)]  V operand images (sa_fwd_kernel)
+  const void* p_tiles;            // [tiles][2 * kPHalf]    attention weights (sa_fwd_kernel)
+  const float2* ln_stats;         // [tiles][128] (mean, rstd) of the forward's context rows (sa_fwd_kernel)
   const float* ln_g; const float* ln_b;
   const void* dout_a; const void* dout_b;   // dOut = a + b (images written by ca_bwd_kernel)
   float* gm;                      // [DIN][128]
   float* g_wv; float* g_bv; float* g_ln_g; float* g_ln_b;
   int batch;
+  long long* dbg;                 // development: per-phase clock64 stamps of CTA 0 (null in production)
 };
+__device__ __forceinline__ long long globaltimer_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define MMRCA_STAMP_NS(i) do { if (a.dbg && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) a.dbg[(i)] = globaltimer_ns(); } while (0)
+#define MMRCA_STAMP(i) do { if (a.dbg && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && stamp_n + (i) < 256) a.dbg[stamp_n + (i)] = clock64(); } while (0)
 template <int DIN_>
 struct SaBwdSmem {
   using C = SaCfg<DIN_>;
-  // two equal buffers that swap roles every tile: X [128 x (DIN+16)] (TMA destination) and Z [128 x DIN], later P
-  static constexpr uint32_t XZ_BYTES = op_bytes(C::KE) > 2 * kPHalf ? op_bytes(C::KE) : 2 * kPHalf;
-  static constexpr uint32_t XZ0 = 0;
-  static constexpr uint32_t XZ1 = XZ0 + XZ_BYTES;
-  static constexpr uint32_t V = XZ1 + XZ_BYTES;                      // [128 x 96]; later dV
-  static constexpr uint32_t DC = V + op_bytes(96);                   // [128 x 96]
-  static constexpr uint32_t DYX = DC + op_bytes(96);                 // [128 x 192]: dy*xhat | dy; later dZ [128 x DIN]
+  static constexpr uint32_t XB = op_bytes(C::KE), VB = op_bytes(96), PB = 2 * kPHalf;
+  static constexpr uint32_t X = 0;                                   // 2 x [128 x (DIN+16)]   (TMA, double buffer)
+  static constexpr uint32_t V = X + 2 * XB;                          // 2 x [128 x 96]         (TMA, double buffer)
+  static constexpr uint32_t P = V + 2 * VB;                          // 2 x 2 x [64 x 64]      (TMA, double buffer)
+  static constexpr uint32_t DC = P + 2 * PB;                         // [128 x 96] dC; later dV
+  static constexpr uint32_t DYX = DC + op_bytes(96);                 // [128 x 192]: dOut images (TMA), then dy*xhat | dy, then dZ
   static constexpr uint32_t DLS = DYX + op_bytes(192);               // dS (2 x [64 x 64])
   static constexpr uint32_t ONES = DLS + 2 * kPHalf;
-  static constexpr uint32_t W = al128(ONES + 4096);
-  static constexpr uint32_t LN = W + C::W_BYTES;
-  static constexpr uint32_t BAR = al128(LN + 2 * 96 * 4);
+  static constexpr uint32_t LN = al128(ONES + 4096);                 // gamma, beta [96] fp32
+  static constexpr uint32_t PART = LN + 2 * 96 * 4;                  // [2 warpgroups][128 rows] (m1, m2) partial sums
+  static constexpr uint32_t BAR = al128(PART + 2 * 128 * 8);
   static constexpr uint32_t BYTES = BAR + 128;
   static_assert(BYTES <= 232448, "SA backward does not fit shared memory");
 };
 template <int DIN_>
 struct SaBwdCols {
-  static constexpr uint32_t Z = 0, V = DIN_, S = 0, C = 64, DP = 0, DV = 0, DZ = 96;   // working: [0, 176)
-  static constexpr uint32_t G_M = 176, G_WV = G_M + DIN_, G_LN = G_WV + 96;  // G_LN: 2 x 16 columns
+  static constexpr uint32_t C = 64, DP = 0, DV = 0, DZ = 96;                        // working: [0, 176)
+  static constexpr uint32_t G_M = 176, G_WV = G_M + DIN_, G_LN = G_WV + 96;       // G_LN: 2 x 16 columns
   static_assert(G_LN + 32 <= 512, "TMEM budget");
 };
 
@@ -686,19 +694,29 @@ __global__ void __launch_bounds__(kCtaThreads, 1) sa_bwd_kernel(const SaBwdArgs 
   extern __shared__ __align__(128) uint8_t sm[];
   using S = SaBwdSmem<DIN_>; using T = SaBwdCols<DIN_>; using C = SaCfg<DIN_>;
   constexpr int DIN = DIN_, DV = C::DV;
-  // mbarriers: [0] weights, [1] MMAs read back next, [2] dOut images (TMA), [3] X image (TMA), [4] G2: dgamma|dbeta,
-  //            [5] G3: dM, dWv  (G*: persistent accumulators, waited for only before an operand buffer is reused)
+  // mbarriers: [0], [1] tile inputs X | V | P of buffer 0 / 1 (TMA), [2] MMAs read back next, [3] unused,
+  //            [4] G2: dgamma|dbeta, [5] G3: dM, dWv  (G*: persistent accumulators, waited for only before an operand
+  //            buffer is reused).  Thread 0 issues the MMAs, thread 32 (another warp) the TMA loads.
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
   float* ln_s = reinterpret_cast<float*>(sm + S::LN);
   const int tid = threadIdx.x, warp = tid >> 5;
-  if (tid == 0) {
+  if (a.dbg && tid == 0) a.dbg[300 + 2 * blockIdx.x] = globaltimer_ns();
+  const int tiles = (a.batch + 7) / 8;
+  constexpr uint32_t kXBytes = x_tile_bytes(DIN);
+  auto issue_inputs = [&](int t, int buf) {
+    mbar_arrive_expect_tx(&bars[buf], kXBytes + S::VB + S::PB);
+    bulk_g2s(sm + S::X + buf * S::XB, static_cast<const uint8_t*>(a.x_tiles) + size_t(t) * kXBytes, kXBytes, &bars[buf]);
+    bulk_g2s(sm + S::V + buf * S::VB, static_cast<const uint8_t*>(a.v_tiles) + size_t(t) * S::VB, S::VB, &bars[buf]);
+    bulk_g2s(sm + S::P + buf * S::PB, static_cast<const uint8_t*>(a.p_tiles) + size_t(t) * S::PB, S::PB, &bars[buf]);
+  };
+  if (tid == 32) {
     for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
-    mbar_arrive_expect_tx(&bars[0], C::W_BYTES);
-    bulk_g2s(sm + S::W, a.blobs, C::W_BYTES, &bars[0]);
+    if (int(blockIdx.x) < tiles) issue_inputs(blockIdx.x, 0);
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
+  float2* part = reinterpret_cast<float2*>(sm + S::PART);
   for (int i = tid; i < DV; i += kCtaThreads) { ln_s[i] = a.ln_g[i]; ln_s[DV + i] = a.ln_b[i]; }
   for (uint32_t i = tid; i < 4096 / 16; i += kCtaThreads)
     reinterpret_cast<uint4*>(sm + S::ONES)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
@@ -706,125 +724,123 @@ __global__ void __launch_bounds__(kCtaThreads, 1) sa_bwd_kernel(const SaBwdArgs 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  mbar_wait(&bars[0], 0);
-  BwCtx c = make_bwctx(tmem, &bars[1]);
-  uint32_t ph_ld = 0, ph_x = 0, ph_g2 = 0, ph_g3 = 0;
-  uint8_t *xb = sm + S::XZ0, *zp = sm + S::XZ1, *vb = sm + S::V, *dcb = sm + S::DC, *dyx = sm + S::DYX, *dls = sm + S::DLS,
-          *ones = sm + S::ONES, *wsm = sm + S::W;
-  const uint8_t* bz = wsm; const uint8_t* bv = wsm + C::BZ_BYTES;
-  const int tiles = (a.batch + 7) / 8;
-  constexpr uint32_t kXBytes = x_tile_bytes(DIN);
-  auto issue_x = [&](int t, uint8_t* dst) {
-    mbar_arrive_expect_tx(&bars[3], kXBytes);
-    bulk_g2s(dst, static_cast<const uint8_t*>(a.x_tiles) + size_t(t) * kXBytes, kXBytes, &bars[3]);
-  };
-  if (tid == 0 && int(blockIdx.x) < tiles) issue_x(blockIdx.x, xb);
+  BwCtx c = make_bwctx(tmem, &bars[2]);
+  uint32_t ph_in[2] = {0, 0}, ph_ld = 0, ph_g2 = 0, ph_g3 = 0;
+  uint8_t *dcb = sm + S::DC, *dyx = sm + S::DYX, *dls = sm + S::DLS, *ones = sm + S::ONES;
   bool first = true;
-  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    // ---- P0/P1: X image (prefetched during the previous tile) -> Z, V.  While they run: wait for the previous
-    //      tile's dM / dWv MMAs (G3), which still read the buffers about to be rewritten (the old X = this tile's
-    //      Z buffer, dV, dZ), then fetch this tile's dOut images into the dy*xhat | dy buffer. -------------------
-    mbar_wait(&bars[3], ph_x); ph_x ^= 1;
-    tc_fence_after_sync();
-    if (tid == 0) {
-      const uint64_t ax = make_smem_desc(smem_u32(xb), kCS, kRS);
-      mma_steps(tmem + T::Z, ax, 2 * kCS, make_smem_desc(smem_u32(bz), C::BZ_LBO, 128), 2 * C::BZ_LBO,
-                make_idesc_bf16(128, DIN, 0, 0), C::KE / 16, false);
-      mma_steps(tmem + T::V, ax, 2 * kCS, make_smem_desc(smem_u32(bv), C::BV_LBO, 128), 2 * C::BV_LBO,
-                make_idesc_bf16(128, DV, 0, 0), C::KE / 16, false);
-      umma_commit(c.bar);
-    }
-    if (!first) mbar_wait_ph(&bars[5], ph_g3);
-    if (tid == 0) {
-      mbar_arrive_expect_tx(&bars[2], 2 * kSaTileBytes);
-      bulk_g2s(dyx, static_cast<const uint8_t*>(a.dout_a) + size_t(tile) * kSaTileBytes, kSaTileBytes, &bars[2]);
-      bulk_g2s(dyx + kSaTileBytes, static_cast<const uint8_t*>(a.dout_b) + size_t(tile) * kSaTileBytes, kSaTileBytes, &bars[2]);
-    }
-    cta_wait_mma(c);
+  int buf = 0, stamp_n = 0;
+  MMRCA_STAMP(0); stamp_n = 1;
+  MMRCA_STAMP_NS(250);
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, buf ^= 1, stamp_n += 12) {
+    uint8_t *xb = sm + S::X + buf * S::XB, *vb = sm + S::V + buf * S::VB, *pb = sm + S::P + buf * S::PB;
+    MMRCA_STAMP(0);
+    // ---- my share of dOut = image a + image b (written by the CA backward): row rs, columns [48w, 48w + 48), straight
+    //      from L2 into registers, in flight while the inputs land and C is recomputed -----------------------------
+    uint4 ra[6], rb[6];
     {
-      constexpr int ZH = (DIN / 16 + 1) / 2 * 16;     // split Z's columns in 16-column steps
-      if (c.w == 0) { acc_cols_to_operand(c, T::Z, 0, ZH, zp, c.rp); acc_cols_to_operand(c, T::V, 0, 32, vb, c.rp); }
-      else { acc_cols_to_operand(c, T::Z, ZH, DIN, zp, c.rp); acc_cols_to_operand(c, T::V, 32, 96, vb, c.rp); }
+      const uint8_t* ga = static_cast<const uint8_t*>(a.dout_a) + size_t(tile) * kSaTileBytes + uint32_t(6 * c.w) * kCS + row_off(c.rs);
+      const uint8_t* gb = static_cast<const uint8_t*>(a.dout_b) + size_t(tile) * kSaTileBytes + uint32_t(6 * c.w) * kCS + row_off(c.rs);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        ra[j] = __ldg(reinterpret_cast<const uint4*>(ga + j * kCS));
+        rb[j] = __ldg(reinterpret_cast<const uint4*>(gb + j * kCS));
+      }
     }
-    cta_sync_for_mma();
+    const float2 st = __ldg(a.ln_stats + size_t(tile) * 128 + c.rs);
+    // ---- the previous tile's dM / dWv MMAs (G3) still read its X, dV (in dC's buffer) and dZ: once they are done,
+    //      fetch the NEXT tile's inputs into the other buffers ------------------------------------------------------
+    if (!first) mbar_wait_ph(&bars[5], ph_g3);
+    MMRCA_STAMP(1);
+    if (tid == 32 && tile + int(gridDim.x) < tiles) issue_inputs(tile + int(gridDim.x), buf ^ 1);
+    mbar_wait(&bars[buf], ph_in[buf]); ph_in[buf] ^= 1;
+    tc_fence_after_sync();
+    MMRCA_STAMP(2);
+    // ---- context C = P V (two M=64 halves), exactly the forward's MMA ----------------------------------------------
     if (tid == 0) {
       for (int h = 0; h < 2; ++h)
-        mma_steps(tmem + (uint32_t(16 * h) << 16) + T::S, make_smem_desc(smem_u32(zp + h * 8 * kRS), kCS, kRS), 2 * kCS,
-                  make_smem_desc(smem_u32(xb + h * 8 * kRS), kCS, kRS), 2 * kCS, make_idesc_bf16(64, 64, 0, 0), DIN / 16, false);
-      umma_commit(c.bar);
-    }
-    cta_wait_mma(c);
-    float p[16];
-    softmax16_bw(c, T::S, false, p);
-    store_half_row_split(c, zp, p, true);        // P reuses Z's bytes (the frozen-feature backward needs Z no more)
-    cta_sync_for_mma();
-    if (tid == 0) {
-      for (int h = 0; h < 2; ++h)
-        mma_steps(tmem + (uint32_t(16 * h) << 16) + T::C, make_smem_desc(smem_u32(zp + h * kPHalf), kPCS, kRS), 2 * kPCS,
+        mma_steps(tmem + (uint32_t(16 * h) << 16) + T::C, make_smem_desc(smem_u32(pb + h * kPHalf), kPCS, kRS), 2 * kPCS,
                   make_smem_desc(smem_u32(vb + h * 8 * kRS), kRS, kCS), 2 * kRS, make_idesc_bf16(64, DV, 0, 1), 4, false);
       umma_commit(c.bar);
     }
-    cta_wait_mma(c);
-    // ---- LayerNorm / ReLU backward.  dOut = image a + image b (written by the CA backward) sits in shared memory
-    //      where dy*xhat | dy will go: every thread first reads its whole row (statistics), then, after a CTA
-    //      barrier, rewrites its own half of the columns in place. -------------------------------------------------
+    // my row of P (the forward's bf16 weights): chunks 2q, 2q+1 of my half
+    float p[16];
     {
-      mbar_wait(&bars[2], ph_ld); ph_ld ^= 1;
-      float mean, rstd;
-      ln_stats_bw<DV>(c, T::C, mean, rstd);
-      uint8_t* ga = dyx + row_off(c.rs);
-      uint8_t* gb = dyx + kSaTileBytes + row_off(c.rs);
-      const uint32_t tc_ = c.tmem + c.lane_base + T::C;
-      float m1a = 0.f, m1b = 0.f, m2a = 0.f, m2b = 0.f;
-      for_cols16(tc_, 0, DV, [&](int c0, const float (&x)[16]) {
-        float g[16];
-        {
-          float f0[8], f1[8], f2[8], f3[8];
-          unpack_bf16x8(*reinterpret_cast<const uint4*>(ga + uint32_t(c0 >> 3) * kCS), f0);
-          unpack_bf16x8(*reinterpret_cast<const uint4*>(gb + uint32_t(c0 >> 3) * kCS), f1);
-          unpack_bf16x8(*reinterpret_cast<const uint4*>(ga + uint32_t((c0 >> 3) + 1) * kCS), f2);
-          unpack_bf16x8(*reinterpret_cast<const uint4*>(gb + uint32_t((c0 >> 3) + 1) * kCS), f3);
+      const uint8_t* pr = pb + c.h * kPHalf + row_off(16 * c.q + c.i);
+      float lo[8], hi[8];
+      unpack_bf16x8(*reinterpret_cast<const uint4*>(pr + (2 * c.q) * kPCS), lo);
+      unpack_bf16x8(*reinterpret_cast<const uint4*>(pr + (2 * c.q + 1) * kPCS), hi);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { g[e] = f0[e] + f1[e]; g[8 + e] = f2[e] + f3[e]; }
-        }
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float gam = ln_s[c0 + e];
-          const float xh = (x[e] - mean) * rstd;
-          const float y = fmaf(xh, gam, ln_s[DV + c0 + e]);
-          const float dxh = y > 0.f ? g[e] * gam : 0.f;
-          if (e & 1) { m1b += dxh; m2b = fmaf(dxh, xh, m2b); } else { m1a += dxh; m2a = fmaf(dxh, xh, m2a); }
-        }
-      });
-      __syncthreads();
-      const float m1 = (m1a + m1b) * (1.0f / float(DV)), m2 = (m2a + m2b) * (1.0f / float(DV));
-      for_cols16(tc_, 48 * c.w, 48 * c.w + 48, [&](int c0, const float (&x)[16]) {
-        float g[16], o[16], t1[16], t2[16];
-        {
-          float f0[8], f1[8], f2[8], f3[8];
-          unpack_bf16x8(*reinterpret_cast<const uint4*>(ga + uint32_t(c0 >> 3) * kCS), f0);
-          unpack_bf16x8(*reinterpret_cast<const uint4*>(gb + uint32_t(c0 >> 3) * kCS), f1);
-          unpack_bf16x8(*reinterpret_cast<const uint4*>(ga + uint32_t((c0 >> 3) + 1) * kCS), f2);
-          unpack_bf16x8(*reinterpret_cast<const uint4*>(gb + uint32_t((c0 >> 3) + 1) * kCS), f3);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) { g[e] = f0[e] + f1[e]; g[8 + e] = f2[e] + f3[e]; }
-        }
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float gam = ln_s[c0 + e];
-          const float xh = (x[e] - mean) * rstd;
-          const float y = fmaf(xh, gam, ln_s[DV + c0 + e]);
-          const float dy = y > 0.f ? g[e] : 0.f;
-          const float dxh = dy * gam;
-          o[e] = rstd * (dxh - m1 - xh * m2);
-          t1[e] = dy * xh; t2[e] = dy;
-        }
-        st_chunks16(dcb, c.rs, c0, o);
-        st_chunks16(dyx, c.rs, c0, t1);            // over image a's chunks of my row
-        st_chunks16(dyx, c.rs, DV + c0, t2);       // over image b's (DV columns = one image)
-      });
+      for (int e = 0; e < 8; ++e) { p[e] = lo[e]; p[8 + e] = hi[e]; }
     }
+    cta_wait_mma(c);
+    MMRCA_STAMP(3);
+    // ---- LayerNorm / ReLU backward.  The two warpgroups split the row's columns; the row sums m1 = mean(dxhat),
+    //      m2 = mean(dxhat xhat) meet in shared memory.  xhat and dy of my 48 columns stay in registers between the
+    //      two passes; mean / rstd are the forward's. ---------------------------------------------------------------
+    {
+      constexpr int HC = DV / 2;       // 48 columns per thread
+      const float mean = st.x, rstd = st.y;
+      float xh[HC], dy[HC];
+      MMRCA_STAMP(4);
+      {
+        uint32_t raw[HC];
+        const uint32_t tc_ = c.tmem + c.lane_base + T::C + HC * c.w;
+#pragma unroll
+        for (int j = 0; j < HC / 16; ++j) tmem_ld16_nw(tc_ + 16 * j, *reinterpret_cast<uint32_t(*)[16]>(&raw[16 * j]));
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          float fa[8], fb[8];
+          unpack_bf16x8(ra[j], fa); unpack_bf16x8(rb[j], fb);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) dy[8 * j + e] = fa[e] + fb[e];
+        }
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < HC; ++e) xh[e] = (__uint_as_float(raw[e]) - mean) * rstd;
+      }
+      float m1a = 0.f, m1b = 0.f, m2a = 0.f, m2b = 0.f;
+      const float4* g4 = reinterpret_cast<const float4*>(ln_s + HC * c.w);
+      const float4* b4 = reinterpret_cast<const float4*>(ln_s + DV + HC * c.w);
+#pragma unroll
+      for (int j = 0; j < HC / 4; ++j) {
+        const float4 gq = g4[j], bq = b4[j];
+        const float gam[4] = {gq.x, gq.y, gq.z, gq.w}, bet[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = 4 * j + e;
+          const float y = fmaf(xh[k], gam[e], bet[e]);
+          dy[k] = y > 0.f ? dy[k] : 0.f;
+          const float dxh = dy[k] * gam[e];
+          if (e & 1) { m1b += dxh; m2b = fmaf(dxh, xh[k], m2b); } else { m1a += dxh; m2a = fmaf(dxh, xh[k], m2a); }
+        }
+      }
+      part[c.w * 128 + c.rs] = make_float2(m1a + m1b, m2a + m2b);
+      __syncthreads();
+      const float2 other = part[(c.w ^ 1) * 128 + c.rs];
+      const float m1 = (m1a + m1b + other.x) * (1.0f / float(DV)), m2 = (m2a + m2b + other.y) * (1.0f / float(DV));
+#pragma unroll
+      for (int j = 0; j < HC / 16; ++j) {
+        float o[16], t1[16], t2[16];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const float4 gq = g4[4 * j + q4];
+          const float gam[4] = {gq.x, gq.y, gq.z, gq.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int k = 16 * j + 4 * q4 + e;
+            o[4 * q4 + e] = rstd * (dy[k] * gam[e] - m1 - xh[k] * m2);
+            t1[4 * q4 + e] = dy[k] * xh[k]; t2[4 * q4 + e] = dy[k];
+          }
+        }
+        const int c0 = HC * c.w + 16 * j;
+        st_chunks16(dcb, c.rs, c0, o);
+        st_chunks16(dyx, c.rs, c0, t1);
+        st_chunks16(dyx, c.rs, DV + c0, t2);
+      }
+    }
+    MMRCA_STAMP(5);
     cta_sync_for_mma();
+    MMRCA_STAMP(6);
     // ---- dP (read back next); then (G2) the LayerNorm-affine gradients: M = 192 = two M=128 MMAs ------------------
     if (tid == 0) {
       for (int h = 0; h < 2; ++h)
@@ -837,15 +853,17 @@ __global__ void __launch_bounds__(kCtaThreads, 1) sa_bwd_kernel(const SaBwdArgs 
       umma_commit(&bars[4]);
     }
     cta_wait_mma(c);
+    MMRCA_STAMP(7);
     {
       float ds[16];
       softmax_bwd16(c, T::DP, false, p, ds);
       store_half_row_split(c, dls, ds, true);
     }
     cta_sync_for_mma();
+    MMRCA_STAMP(8);
     if (tid == 0) {
       for (int h = 0; h < 2; ++h) {
-        mma_steps(tmem + (uint32_t(16 * h) << 16) + T::DV, make_smem_desc(smem_u32(zp + h * kPHalf), kRS, kPCS), 2 * kRS,
+        mma_steps(tmem + (uint32_t(16 * h) << 16) + T::DV, make_smem_desc(smem_u32(pb + h * kPHalf), kRS, kPCS), 2 * kRS,
                   make_smem_desc(smem_u32(dcb + h * 8 * kRS), kRS, kCS), 2 * kRS, make_idesc_bf16(64, DV, 1, 1), 4, false);
         mma_steps(tmem + (uint32_t(16 * h) << 16) + T::DZ, make_smem_desc(smem_u32(dls + h * kPHalf), kPCS, kRS), 2 * kPCS,
                   make_smem_desc(smem_u32(xb + h * 8 * kRS), kRS, kCS), 2 * kRS, make_idesc_bf16(64, DIN, 0, 1), 4, false);
@@ -853,22 +871,24 @@ __global__ void __launch_bounds__(kCtaThreads, 1) sa_bwd_kernel(const SaBwdArgs 
       umma_commit(c.bar);
     }
     cta_wait_mma(c);
-    // P is dead: the next tile's X image lands in its buffer while this tile finishes
-    if (tid == 0 && tile + int(gridDim.x) < tiles) issue_x(tile + int(gridDim.x), zp);
+    MMRCA_STAMP(9);
     mbar_wait_ph(&bars[4], ph_g2);                 // dgamma|dbeta have read dy*xhat | dy: its bytes become dZ
-    if (c.w == 0) { acc_cols_to_operand(c, T::DZ, 0, DIN, dyx, c.rs); acc_cols_to_operand(c, T::DV, 0, 16, vb, c.rs); }
-    else acc_cols_to_operand(c, T::DV, 16, 96, vb, c.rs);
+    // dC is dead (dP and dV have read it): its buffer takes dV
+    if (c.w == 0) { acc_cols_to_operand(c, T::DZ, 0, DIN, dyx, c.rs); acc_cols_to_operand(c, T::DV, 0, 16, dcb, c.rs); }
+    else acc_cols_to_operand(c, T::DV, 16, 96, dcb, c.rs);
+    MMRCA_STAMP(10);
     cta_sync_for_mma();
-    if (tid == 0) {       // G3: nobody waits for these before the next tile's feature loads are in flight
+    MMRCA_STAMP(11);
+    if (tid == 0) {       // G3: nobody waits for these before the next tile is under way
       mma_steps(tmem + T::G_M, make_smem_desc(smem_u32(xb), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(dyx), kRS, kCS), 2 * kRS,
                 make_idesc_bf16(128, DIN, 1, 1), 8, !first);
-      mma_steps(tmem + T::G_WV, make_smem_desc(smem_u32(xb), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(vb), kRS, kCS), 2 * kRS,
+      mma_steps(tmem + T::G_WV, make_smem_desc(smem_u32(xb), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(dcb), kRS, kCS), 2 * kRS,
                 make_idesc_bf16(128, DV, 1, 1), 8, !first);
       umma_commit(&bars[5]);
     }
     first = false;
-    { uint8_t* t_ = xb; xb = zp; zp = t_; }        // the prefetched image is the next tile's X
   }
+  MMRCA_STAMP(0);
   if (!first) {
     mbar_wait_ph(&bars[5], ph_g3);
     flush_acc(c, T::G_M, DIN, DIN + 1, [&](int m, int n) { return a.gm + size_t(n) * 128 + m; });
@@ -881,6 +901,10 @@ __global__ void __launch_bounds__(kCtaThreads, 1) sa_bwd_kernel(const SaBwdArgs 
       else if (col < 2 * DV) atomicAdd(a.g_ln_b + (col - DV), v[0]);
     }
   }
+  __syncthreads();
+  MMRCA_STAMP(1);
+  MMRCA_STAMP_NS(251);
+  if (a.dbg && tid == 0) a.dbg[301 + 2 * blockIdx.x] = globaltimer_ns();
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
@@ -896,7 +920,7 @@ struct FinBlock {
   int din, dkq;
 };
 struct FinArgs { FinBlock blk[4]; int nblk; };
-constexpr int kFinRows = 8;                                         // rows n of W_query / W_key per CTA
+constexpr int kFinRows = 2;                                         // rows n of W_query / W_key per CTA
 constexpr uint32_t kFinSmemBytes = (96 * 98 + 2 * kFinRows * 96 + kFinRows) * 4;
 
 // grid.x = sum over blocks of d_kq / 8.  CTA = (block, 8 rows n): dM (d_in x (d_in + 1), du in the last column) and the
@@ -918,9 +942,29 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
   float* wk_s = g_s + din * gs;              // [8][din]
   float* wq_s = wk_s + kFinRows * din;       // [8][din]
   float* bq_s = wq_s + kFinRows * din;       // [8]
-  for (int i = tid; i < din * (din + 1); i += 256) {
-    const int kp = i / (din + 1), k = i - kp * (din + 1);
-    g_s[kp * gs + k] = __ldg(B.gm + size_t(kp) * 128 + k);
+  {   // dM rows are 128 floats apart: din / 4 16-byte loads + du per row, at most 10 items per thread, all in flight
+    const int per_row = din / 4 + 1, items = din * per_row;
+    float4 v[10];
+#pragma unroll
+    for (int u = 0; u < 10; ++u) {
+      const int i = tid + 256 * u;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < items) {
+        const int kp = i / per_row, q = i - kp * per_row;
+        if (q < din / 4) v[u] = __ldg(reinterpret_cast<const float4*>(B.gm + size_t(kp) * 128) + q);
+        else v[u].x = __ldg(B.gm + size_t(kp) * 128 + din);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 10; ++u) {
+      const int i = tid + 256 * u;
+      if (i < items) {
+        const int kp = i / per_row, q = i - kp * per_row;
+        float* d = g_s + kp * gs + 4 * q;
+        if (q < din / 4) { d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w; }
+        else d[0] = v[u].x;
+      }
+    }
   }
   for (int i = tid; i < kFinRows * din; i += 256) {
     wk_s[i] = __ldg(B.wk + size_t(n0) * din + i);
