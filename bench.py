@@ -65,8 +65,7 @@ def kernel_flops():
     f["sa_fwd_bf16"] = sum(sa_i.values()) + sum(sa_t.values()) + 2 * 4 * 2048
     f["ca_fwd_bf16"] = 2 * sum(ca.values()) + 2 * 4 * 1536
     f["ca_bwd_bf16"] = 2 * bwd_ca(ca) + 2 * 2 * 4 * 1536
-    f["sa_bwd_bf16<80>"] = bwd_sa(sa_i)
-    f["sa_bwd_bf16<48>"] = bwd_sa(sa_t)
+    f["sa_bwd_bf16"] = bwd_sa(sa_i) + bwd_sa(sa_t)
     f["ce_feat"] = 2 * 4 * 2048                # dWf rows of the feature sources
     for k in ("prep_bf16", "finalize_bf16", "dropout_mask"):
         f[k] = 0

@@ -209,6 +209,7 @@ struct Workspace {
   void* sa_v[2]; void* sa_p[2];                                     // training: V / P images kept by the SA forward (img, txt)
   float2* sa_stats[2];                                              // training: LayerNorm (mean, rstd) per context row
   float* gm[4]; size_t gm_floats;                                   // training: dM_ext^T per block (contiguous)
+  float* step_loss = nullptr;                                       // train step: prep_feat clears gm and *step_loss (no memset nodes)
   size_t bytes;
 };
 
@@ -378,6 +379,7 @@ static int launch_prep_feat(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, co
   f.src[1].feat = txt; f.src[1].x_tiles = w.x_txt; f.src[1].norms = w.norm_txt; f.src[1].cls_off = 2 * ca + d.d_img;
   f.logits = logits; f.wf = p.wf; f.bf = p.bf; f.with_features = co ? 0 : 1;
   f.drop = make_drop(d); f.batch = d.batch;
+  if (w.step_loss) { a.zero0 = w.gm[0]; a.nzero0 = int(w.gm_floats); a.zero1 = w.step_loss; }
   const int prep_ctas = htc::kPrepCtas;
   const int feat_ctas = max(1, min((d.batch + 7) / 8, 2 * sms));
   {
@@ -429,7 +431,7 @@ static int head_backward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p,
                                cudaStream_t st) {
   const int tiles = (d.batch + 7) / 8, D = concat_width(d), ca = kL * MMRCA_CA_DV;
   int rc;
-  MMRCA_CUDA(cudaMemsetAsync(w.gm[0], 0, w.gm_floats * sizeof(float), st));
+  if (!w.step_loss) MMRCA_CUDA(cudaMemsetAsync(w.gm[0], 0, w.gm_floats * sizeof(float), st));
   {
     htc::CaBwdArgs a;
     memset(&a, 0, sizeof(a));
@@ -452,27 +454,27 @@ static int head_backward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p,
   MMRCA_CUDA(cudaGetLastError());
   {
     // text SA output: query source of CA1, key/value source of CA2; image SA output: the other way round
-    htc::SaBwdArgs a;
-    memset(&a, 0, sizeof(a));
-    a.dbg = g_dbg;
-    a.x_tiles = w.x_img; a.v_tiles = w.sa_v[0]; a.p_tiles = w.sa_p[0]; a.ln_stats = w.sa_stats[0]; a.ln_g = p.sa_img.ln_g; a.ln_b = p.sa_img.ln_b;
-    a.dout_a = w.dx_img[1]; a.dout_b = w.dx_img[2];
-    a.gm = w.gm[0]; a.g_wv = g.sa_img.wv; a.g_bv = g.sa_img.bv; a.g_ln_g = g.sa_img.ln_g; a.g_ln_b = g.sa_img.ln_b;
-    a.batch = d.batch;
-    if ((rc = set_smem(htc::sa_bwd_kernel<80>, htc::SaBwdSmem<80>::BYTES))) return rc;
+    htc::SaBwdBothArgs both;
+    memset(&both, 0, sizeof(both));
     {
-      LaunchScope ls("sa_bwd_bf16<80>", st);
-      htc::sa_bwd_kernel<80><<<min(tiles, sms), htc::kCtaThreads, htc::SaBwdSmem<80>::BYTES, st>>>(a);
+      htc::SaBwdArgs& a = both.m[0];
+      a.dbg = g_dbg;
+      a.x_tiles = w.x_img; a.v_tiles = w.sa_v[0]; a.p_tiles = w.sa_p[0]; a.ln_stats = w.sa_stats[0]; a.ln_g = p.sa_img.ln_g; a.ln_b = p.sa_img.ln_b;
+      a.dout_a = w.dx_img[1]; a.dout_b = w.dx_img[2];
+      a.gm = w.gm[0]; a.g_wv = g.sa_img.wv; a.g_bv = g.sa_img.bv; a.g_ln_g = g.sa_img.ln_g; a.g_ln_b = g.sa_img.ln_b;
+      a.batch = d.batch;
     }
-    MMRCA_CUDA(cudaGetLastError());
-    a.dbg = nullptr;
-    a.x_tiles = w.x_txt; a.v_tiles = w.sa_v[1]; a.p_tiles = w.sa_p[1]; a.ln_stats = w.sa_stats[1]; a.ln_g = p.sa_txt.ln_g; a.ln_b = p.sa_txt.ln_b;
-    a.dout_a = w.dx_img[0]; a.dout_b = w.dx_img[3];
-    a.gm = w.gm[1]; a.g_wv = g.sa_txt.wv; a.g_bv = g.sa_txt.bv; a.g_ln_g = g.sa_txt.ln_g; a.g_ln_b = g.sa_txt.ln_b;
-    if ((rc = set_smem(htc::sa_bwd_kernel<48>, htc::SaBwdSmem<48>::BYTES))) return rc;
     {
-      LaunchScope ls("sa_bwd_bf16<48>", st);
-      htc::sa_bwd_kernel<48><<<min(tiles, sms), htc::kCtaThreads, htc::SaBwdSmem<48>::BYTES, st>>>(a);
+      htc::SaBwdArgs& a = both.m[1];
+      a.x_tiles = w.x_txt; a.v_tiles = w.sa_v[1]; a.p_tiles = w.sa_p[1]; a.ln_stats = w.sa_stats[1]; a.ln_g = p.sa_txt.ln_g; a.ln_b = p.sa_txt.ln_b;
+      a.dout_a = w.dx_img[0]; a.dout_b = w.dx_img[3];
+      a.gm = w.gm[1]; a.g_wv = g.sa_txt.wv; a.g_bv = g.sa_txt.bv; a.g_ln_g = g.sa_txt.ln_g; a.g_ln_b = g.sa_txt.ln_b;
+      a.batch = d.batch;
+    }
+    if ((rc = set_smem(htc::sa_bwd_kernel, htc::kSaBwdSmemBytes))) return rc;
+    {
+      LaunchScope ls("sa_bwd_bf16", st);
+      htc::sa_bwd_kernel<<<dim3(min(tiles, max(1, sms / 2)), 2), htc::kCtaThreads, htc::kSaBwdSmemBytes, st>>>(both);
     }
     MMRCA_CUDA(cudaGetLastError());
   }
@@ -503,7 +505,7 @@ static int launch_ce_feat(const MmrcaHeadDesc& d, const float* logits, const int
                           float* loss, float* dlogits, const MmrcaHeadGrads& g, bool bias_grad, const Workspace& w,
                           cudaStream_t st) {
   const bool co = d.flags & MMRCA_FLAG_CROSS_ATTENTION_ONLY;
-  if (labels) MMRCA_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  if (labels && !w.step_loss) MMRCA_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
   htc::CeFeatArgs a;
   memset(&a, 0, sizeof(a));
   a.logits = logits; a.labels = labels; a.cw = ce ? ce->class_weight : nullptr; a.eps = ce ? ce->label_smoothing : 0.f;
@@ -777,6 +779,7 @@ int mmrca_head_train_step(const MmrcaHeadDesc* desc, const MmrcaHeadParams* para
   Workspace w = carve(*desc, true, workspace);
   if (workspace_bytes < w.bytes) return fail(MMRCA_ERR_WORKSPACE, "workspace too small (training size needed)%s%s");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (fused_ok(*desc, drop_mask)) w.step_loss = loss_out;
   if ((rc = head_forward_impl(*desc, *params, img_feat, txt_feat, drop_mask, drop_scale, logits, w, di.sms, st)))
     return rc;
   if (fused_ok(*desc, drop_mask)) {

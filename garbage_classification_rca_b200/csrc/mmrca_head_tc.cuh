@@ -79,7 +79,8 @@ struct PrepArgs {
   PrepSrc src[4];
   int nsrc;
   const float* wf; int D;                    // classifier [4][D]
-  float* zero0; int nzero0;                  // fp32 regions to clear (step accumulators)
+  float* zero0; int nzero0;                  // fp32 region to clear (step accumulators)
+  float* zero1;                              // one more float to clear (the loss accumulator), or null
 };
 
 constexpr int kPrepZTasks = (80 + 16) / 8 + (48 + 16) / 8 + 2 * (96 + 16) / 8;   // one CTA per (block, 8-column group kc)
@@ -168,6 +169,7 @@ __device__ __forceinline__ void prep_body(const PrepArgs& a, int cta, int nctas,
   }
   // (d) accumulators
   for (int i = gtid; i < a.nzero0; i += gsz) a.zero0[i] = 0.f;
+  if (gtid == 0 && a.zero1) *a.zero1 = 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

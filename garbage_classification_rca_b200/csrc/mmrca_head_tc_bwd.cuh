@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// self-attention backward (features frozen: parameter gradients only), one modality per launch.
+// self-attention backward (features frozen: parameter gradients only), one modality per blockIdx.y.
 // Nothing of the forward is recomputed except C = P V (one MMA, so that the LayerNorm backward sees exactly the
 // fp32 context the forward normalised): X comes from prep_feat_kernel's image, V and P from the images the forward
 // kept, all by TMA, one whole tile ahead into the other half of a double buffer.
@@ -690,8 +690,7 @@ struct SaBwdCols {
 };
 
 template <int DIN_>
-__global__ void __launch_bounds__(kCtaThreads, 1) sa_bwd_kernel(const SaBwdArgs a) {
-  extern __shared__ __align__(128) uint8_t sm[];
+__device__ __forceinline__ void sa_bwd_body(const SaBwdArgs& a, uint8_t* sm) {
   using S = SaBwdSmem<DIN_>; using T = SaBwdCols<DIN_>; using C = SaCfg<DIN_>;
   constexpr int DIN = DIN_, DV = C::DV;
   // mbarriers: [0], [1] tile inputs X | V | P of buffer 0 / 1 (TMA), [2] MMAs read back next, [3] unused,
@@ -908,6 +907,17 @@ __global__ void __launch_bounds__(kCtaThreads, 1) sa_bwd_kernel(const SaBwdArgs 
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// Both modalities in one launch: blockIdx.y = 0 image (DIN 80), 1 text (DIN 48), gridDim.x CTAs each.  The two
+// backward passes are independent, a tile costs about the same in both, and 2 x 512 tiles over 148 SMs is 7 rounds
+// in one launch against 2 x 4 in two (plus one prologue and one accumulator flush instead of two).
+struct SaBwdBothArgs { SaBwdArgs m[2]; };
+constexpr uint32_t kSaBwdSmemBytes = SaBwdSmem<80>::BYTES > SaBwdSmem<48>::BYTES ? SaBwdSmem<80>::BYTES : SaBwdSmem<48>::BYTES;
+__global__ void __launch_bounds__(kCtaThreads, 1) sa_bwd_kernel(const SaBwdBothArgs a) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  if (blockIdx.y == 0) sa_bwd_body<80>(a.m[0], sm);
+  else sa_bwd_body<48>(a.m[1], sm);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -60,7 +60,7 @@ def full(path):
         print()
 
 
-LABELS = (("ca_bwd_kernel", "ca_bwd_bf16"), ("sa_bwd_kernel<80>", "sa_bwd_bf16<80>"), ("sa_bwd_kernel<48>", "sa_bwd_bf16<48>"),
+LABELS = (("ca_bwd_kernel", "ca_bwd_bf16"), ("sa_bwd_kernel", "sa_bwd_bf16"),
           ("sa_fwd_kernel", "sa_fwd_bf16"), ("ca_fwd_kernel", "ca_fwd_bf16"), ("ce_feat_kernel", "ce_feat"),
           ("prep_kernel", "prep_bf16"), ("finalize_kernel", "finalize_bf16"), ("bwd_kernel", "bwd_bf16"))
 
