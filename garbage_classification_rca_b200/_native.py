@@ -144,7 +144,7 @@ def lib() -> C.CDLL:
         L.mmrca_dev_umma_selftest.restype = C.c_int
         L.mmrca_dropout_mask.argtypes = [C.c_uint64, C.c_float, C.c_int32, C.c_int32, _fp, _fp]
         L.mmrca_dropout_mask.restype = C.c_int
-        L.mmrca_dev_set_debug.argtypes = [_fp]
+        L.mmrca_dev_set_debug.argtypes = [_fp, C.c_int32]
         L.mmrca_dev_set_debug.restype = C.c_int
         if L.mmrca_query(QUERY_ABI_VERSION) != ABI_VERSION:
             raise RuntimeError("libmmrca.so ABI version mismatch: rebuild it")

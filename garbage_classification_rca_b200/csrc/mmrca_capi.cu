@@ -18,7 +18,8 @@ namespace mmrca {
 
 static thread_local char g_err[512] = "";
 static thread_local int g_launches = 0;
-static long long* g_dbg = nullptr;   // development: device buffer for per-phase clock stamps (mmrca_dev_set_debug)
+static long long* g_dbg = nullptr;
+static int g_dbg_kernel = 0;         // 0: sa_bwd, 1: ca_bwd   // development: device buffer for per-phase clock stamps (mmrca_dev_set_debug)
 
 // ---- optional per-kernel timing (mmrca_timing_begin / _end) -------------------------------------
 struct TimingRec { const char* name; cudaEvent_t e0, e1; };
@@ -447,6 +448,7 @@ static int head_backward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p,
     a.t_tiles = w.t_img; a.i_tiles = w.i_img; a.dlogits = dlogits; a.D = D;
     a.batch = d.batch; a.reverse = (d.flags & MMRCA_FLAG_REVERSE) ? 1 : 0;
     a.drop = make_drop(d);
+    a.dbg = g_dbg_kernel == 1 ? g_dbg : nullptr;
     if ((rc = set_smem(htc::ca_bwd_kernel, htc::CaBwdSmem::BYTES))) return rc;
     LaunchScope ls("ca_bwd_bf16", st);
     htc::ca_bwd_kernel<<<dim3(min(tiles, max(1, sms / 2)), 2), htc::kCtaThreads, htc::CaBwdSmem::BYTES, st>>>(a);
@@ -458,7 +460,7 @@ static int head_backward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p,
     memset(&both, 0, sizeof(both));
     {
       htc::SaBwdArgs& a = both.m[0];
-      a.dbg = g_dbg;
+      a.dbg = g_dbg_kernel == 0 ? g_dbg : nullptr;
       a.x_tiles = w.x_img; a.v_tiles = w.sa_v[0]; a.p_tiles = w.sa_p[0]; a.ln_stats = w.sa_stats[0]; a.ln_g = p.sa_img.ln_g; a.ln_b = p.sa_img.ln_b;
       a.dout_a = w.dx_img[1]; a.dout_b = w.dx_img[2];
       a.gm = w.gm[0]; a.g_wv = g.sa_img.wv; a.g_bv = g.sa_img.bv; a.g_ln_g = g.sa_img.ln_g; a.g_ln_b = g.sa_img.ln_b;
@@ -862,7 +864,10 @@ int mmrca_dropout_mask(uint64_t seed, float p, int32_t batch, int32_t width, uin
   return MMRCA_OK;
 }
 
-int mmrca_dev_set_debug(void* device_buffer_256_int64) { g_dbg = static_cast<long long*>(device_buffer_256_int64); return MMRCA_OK; }
+int mmrca_dev_set_debug(void* device_buffer_1024_int64, int32_t kernel) {
+  g_dbg = static_cast<long long*>(device_buffer_1024_int64); g_dbg_kernel = kernel;
+  return MMRCA_OK;
+}
 
 int mmrca_dev_umma_selftest(int32_t mode, const float* a, const float* b, float* out, int32_t n, int32_t k,
                             void* stream) {

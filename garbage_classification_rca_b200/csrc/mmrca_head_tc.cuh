@@ -680,7 +680,7 @@ __device__ __forceinline__ void write_bias_columns(uint8_t* op, int kc0, int row
 }
 
 __device__ __forceinline__ void ca_fwd_tile(WgCtx& c, const CaFwdArgs& a, int d, uint8_t* wsm, uint8_t* bsm,
-                                            const float* ln_s, uint64_t* bar_ld, uint32_t& ph_ld, int tile) {
+                                            const float* ln_s, uint64_t* bar_ld, uint32_t& ph_ld, int tile, int next_tile) {
   using C = CaCfg;
   const int b0 = tile * 8;
   uint8_t* xq = bsm + CaFwdSmem::XQ;
@@ -693,6 +693,10 @@ __device__ __forceinline__ void ca_fwd_tile(WgCtx& c, const CaFwdArgs& a, int d,
     mbar_arrive_expect_tx(bar_ld, 2 * kSaTileBytes);
     bulk_g2s(xq, qsrc, kSaTileBytes, bar_ld);
     bulk_g2s(xkv, ksrc, kSaTileBytes, bar_ld);
+    if (c.wg == 0 && next_tile >= 0) {      // the next tile's images (both warpgroups read both): into the L2 meanwhile
+      bulk_prefetch_l2(static_cast<const uint8_t*>(a.t_tiles) + size_t(next_tile) * kSaTileBytes, kSaTileBytes);
+      bulk_prefetch_l2(static_cast<const uint8_t*>(a.i_tiles) + size_t(next_tile) * kSaTileBytes, kSaTileBytes);
+    }
   }
   write_bias_columns(xq, C::DIN / 8, c.wt);     // (Z / P / Out reuse only the first 96 columns of xq, but the
   write_bias_columns(xkv, C::DIN / 8, c.wt);    //  image load of the next tile must not race with stale readers)
@@ -811,7 +815,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_fwd_kernel(const CaFwdArgs 
   int round = 0;
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++round) {
     const int d = (wg + round) & 1;
-    ca_fwd_tile(c, a, d, sm + (d == 0 ? L::W0 : L::W1), bsm, ln_s + d * 96, &bars[3 + wg], ph_ld, tile);
+    ca_fwd_tile(c, a, d, sm + (d == 0 ? L::W0 : L::W1), bsm, ln_s + d * 96, &bars[3 + wg], ph_ld, tile,
+                tile + int(gridDim.x) < tiles ? tile + int(gridDim.x) : -1);
   }
   tc_fence_before_sync();
   __syncthreads();

@@ -361,6 +361,10 @@ __device__ __forceinline__ void flush_acc(const BwCtx& c, uint32_t col, int ncol
   }
 }
 
+__device__ __forceinline__ long long globaltimer_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define MMRCA_STAMP_NS(i) do { if (a.dbg && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) a.dbg[(i)] = globaltimer_ns(); } while (0)
+#define MMRCA_STAMP(i) do { if (a.dbg && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && stamp_n + (i) < 256) a.dbg[stamp_n + (i)] = clock64(); } while (0)
+
 // ---------------------------------------------------------------------------------------------------------------
 // cross-attention backward, one direction per blockIdx.y
 // ---------------------------------------------------------------------------------------------------------------
@@ -380,6 +384,7 @@ struct CaBwdArgs {
   int D;                          // concat width (row stride of dWf)
   DropSpec drop;                  // concat columns of direction d: [d * 768, d * 768 + 768)
   int batch, reverse;
+  long long* dbg;                 // development: per-phase clock64 stamps of CTA (0, 0) (null in production)
 };
 struct CaBwdSmem {
   static constexpr uint32_t XQ = 0;                                  // [128 x 112]
@@ -394,7 +399,8 @@ struct CaBwdSmem {
   static constexpr uint32_t ONES = P + 2 * kPHalf;                   // [16][128] ones
   static constexpr uint32_t W = al128(ONES + 4096);
   static constexpr uint32_t LN = W + CaCfg::W_BYTES;                 // gamma, beta [48] fp32
-  static constexpr uint32_t BAR = al128(LN + 2 * 48 * 4);
+  static constexpr uint32_t PART = LN + 2 * 48 * 4;                  // [2 warpgroups][128 rows] (m1, m2) partial sums
+  static constexpr uint32_t BAR = al128(PART + 2 * 128 * 8);
   static constexpr uint32_t BYTES = BAR + 128;
   static_assert(2 * kPHalf >= op_bytes(64), "dS aliases DL");
   static_assert(BYTES <= 232448, "CA backward does not fit shared memory");
@@ -413,6 +419,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
   float* ln_s = reinterpret_cast<float*>(sm + S::LN);
+  float2* part = reinterpret_cast<float2*>(sm + S::PART);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int d = blockIdx.y;
   const CaBwdDir& D = a.dir[d];
@@ -443,8 +450,13 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
   const uint8_t* bz = wsm; const uint8_t* bv = wsm + C::BZ_BYTES; const uint8_t* bc = wsm + C::BZ_BYTES + C::BV_BYTES;
   const int tiles = (a.batch + 7) / 8;
   bool first = true;
-  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  int stamp_n = 0;
+  if (a.dbg && tid == 0) a.dbg[300 + 2 * (blockIdx.x + gridDim.x * blockIdx.y)] = globaltimer_ns();
+  MMRCA_STAMP(0); stamp_n = 1;
+  MMRCA_STAMP_NS(250);
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, stamp_n += 16) {
     const int b0 = tile * 8;
+    MMRCA_STAMP(0);
     // ---- P0: DL from dlogits; block inputs (SA images) by TMA once the previous tile's dM / dWv MMAs are done ----
     stage_dl(c, dls, a.dlogits, b0, a.batch);
     if (!first) mbar_wait_ph(&bars[4], ph_g3);
@@ -454,9 +466,14 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
       mbar_arrive_expect_tx(&bars[2], 2 * kSaTileBytes);
       bulk_g2s(xq, qsrc, kSaTileBytes, &bars[2]);
       bulk_g2s(xkv, ksrc, kSaTileBytes, &bars[2]);
+      if (tile + int(gridDim.x) < tiles) {      // the next tile's images: into the L2 while this tile is worked on
+        bulk_prefetch_l2(qsrc + size_t(gridDim.x) * kSaTileBytes, kSaTileBytes);
+        bulk_prefetch_l2(ksrc + size_t(gridDim.x) * kSaTileBytes, kSaTileBytes);
+      }
     }
     mbar_wait(&bars[2], ph_ld); ph_ld ^= 1;
     cta_sync_for_mma();
+    MMRCA_STAMP(1);
     // ---- P1: Z, V (M=128) and dOut = DL Wf_src^T (two M=64 halves, s-mapping like C) ----------------------------
     if (tid == 0) {
       mma_steps(tmem + T::Z, make_smem_desc(smem_u32(xq), kCS, kRS), 2 * kCS, make_smem_desc(smem_u32(bz), C::BZ_LBO, 128),
@@ -469,10 +486,12 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
       umma_commit(c.bar);
     }
     cta_wait_mma(c);
+    MMRCA_STAMP(2);
     // ---- P2: Z, V -> operands (columns split) ---------------------------------------------------------------------
     acc_cols_to_operand(c, T::Z, 48 * c.w, 48 * c.w + 48, zb, c.rp);
     if (c.w == 0) acc_cols_to_operand(c, T::V, 0, 32, vb, c.rp); else acc_cols_to_operand(c, T::V, 32, 48, vb, c.rp);
     cta_sync_for_mma();
+    MMRCA_STAMP(3);
     // ---- P3: scores ----------------------------------------------------------------------------------------------------
     if (tid == 0) {
       for (int h = 0; h < 2; ++h)
@@ -481,10 +500,12 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
       umma_commit(c.bar);
     }
     cta_wait_mma(c);
+    MMRCA_STAMP(4);
     float p[16];
     softmax16_bw(c, T::S, reverse, p);
     store_half_row_split(c, pb, p, false);
     cta_sync_for_mma();
+    MMRCA_STAMP(5);
     // ---- P5: context ---------------------------------------------------------------------------------------------------
     if (tid == 0) {
       for (int h = 0; h < 2; ++h)
@@ -493,54 +514,69 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
       umma_commit(c.bar);
     }
     cta_wait_mma(c);
-    // ---- P6: LayerNorm / ReLU backward on my row: warpgroup 0 emits Out and dC, warpgroup 1 dy*xhat | dy ----------
+    MMRCA_STAMP(6);
+    // ---- P6: LayerNorm / ReLU backward.  Both warpgroups own the same rows and split a row's 48 columns (24 each):
+    //      statistics over the whole row (cheap, redundant), everything else on my 24 columns, xhat and dxhat kept in
+    //      registers between the two passes; the row sums m1 = mean(dxhat), m2 = mean(dxhat xhat) meet in shared memory.
     {
+      constexpr int HC = C::DV / 2;
       float mean, rstd;
       ln_stats_bw<C::DV>(c, T::C, mean, rstd);
-      // self.drop (multimodal_model.py:719) sits between this block's output and the classifier: the keep bits of
-      // my row's 48 concat columns scale both what the classifier saw (Out, for dWf) and what it sends back (dOut)
-      const bool dropping = a.drop.thresh != 0;
-      const uint64_t keep = dropping ? drop_bits(a.drop, uint32_t(b0 + (c.rs >> 4)),
-                                                 uint32_t(d * kL * C::DV + (c.rs & 15) * C::DV), C::DV) : ~uint64_t(0);
-      const float dscale = dropping ? a.drop.scale : 1.0f;
-      float m1a = 0.f, m1b = 0.f, m2a = 0.f, m2b = 0.f;
-      const uint32_t tc_ = c.tmem + c.lane_base + T::C, tg_ = c.tmem + c.lane_base + T::DOUT;
-      for_cols16x2(tc_, tg_, 0, C::DV, [&](int c0, const float (&x)[16], const float (&g)[16]) {
-        float o[16], t1[16], t2[16];
-        const uint32_t kb = uint32_t(keep >> c0);
+      uint32_t xr[HC], gr[HC];
+      {
+        const uint32_t tc_ = c.tmem + c.lane_base + T::C + HC * c.w, tg_ = c.tmem + c.lane_base + T::DOUT + HC * c.w;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float gam = ln_s[c0 + e];
-          const float xh = (x[e] - mean) * rstd;
-          const float y = fmaf(xh, gam, ln_s[48 + c0 + e]);
-          const float mk = (kb >> e) & 1u ? dscale : 0.f;
-          const float dy = y > 0.f ? g[e] * mk : 0.f;
-          const float dxh = dy * gam;
-          if (e & 1) { m1b += dxh; m2b = fmaf(dxh, xh, m2b); } else { m1a += dxh; m2a = fmaf(dxh, xh, m2a); }
-          o[e] = fmaxf(y, 0.f) * mk; t1[e] = dy * xh; t2[e] = dy;
+        for (int j = 0; j < HC / 8; ++j) {
+          tmem_ld8_nw(tc_ + 8 * j, *reinterpret_cast<uint32_t(*)[8]>(&xr[8 * j]));
+          tmem_ld8_nw(tg_ + 8 * j, *reinterpret_cast<uint32_t(*)[8]>(&gr[8 * j]));
         }
-        if (c.w == 0) st_chunks16(ob, c.rs, c0, o);
-        else { st_chunks16(dyx, c.rs, c0, t1); st_chunks16(dyx, c.rs, C::DV + c0, t2); }
-      });
-      if (c.w == 0) {
-        const float m1 = (m1a + m1b) * (1.0f / float(C::DV)), m2 = (m2a + m2b) * (1.0f / float(C::DV));
-        for_cols16x2(tc_, tg_, 0, C::DV, [&](int c0, const float (&x)[16], const float (&g)[16]) {
-          float o[16];
-          const uint32_t kb = uint32_t(keep >> c0);
+      }
+      // self.drop (multimodal_model.py:719) sits between this block's output and the classifier: the keep bits of
+      // my concat columns scale both what the classifier saw (Out, for dWf) and what it sends back (dOut)
+      const bool dropping = a.drop.thresh != 0;
+      const uint32_t keep = dropping ? uint32_t(drop_bits(a.drop, uint32_t(b0 + (c.rs >> 4)),
+                                                          uint32_t(d * kL * C::DV + (c.rs & 15) * C::DV + HC * c.w), HC))
+                                     : 0xffffffffu;
+      const float dscale = dropping ? a.drop.scale : 1.0f;
+      tmem_wait_ld();
+      float xh[HC], dxh[HC];
+      float m1a = 0.f, m1b = 0.f, m2a = 0.f, m2b = 0.f;
+      const float* gam_s = ln_s + HC * c.w;
+      const float* bet_s = ln_s + C::DV + HC * c.w;
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float gam = ln_s[c0 + e];
-            const float xh = (x[e] - mean) * rstd;
-            const float y = fmaf(xh, gam, ln_s[48 + c0 + e]);
-            const float mk = (kb >> e) & 1u ? dscale : 0.f;
-            const float dxh = y > 0.f ? g[e] * mk * gam : 0.f;
-            o[e] = rstd * (dxh - m1 - xh * m2);
-          }
-          st_chunks16(dcb, c.rs, c0, o);
-        });
+      for (int j = 0; j < HC / 8; ++j) {
+        float o[8], t1[8], t2[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int k = 8 * j + e;
+          const float gam = gam_s[k];
+          xh[k] = (__uint_as_float(xr[k]) - mean) * rstd;
+          const float y = fmaf(xh[k], gam, bet_s[k]);
+          const float mk = (keep >> k) & 1u ? dscale : 0.f;
+          const float dy = y > 0.f ? __uint_as_float(gr[k]) * mk : 0.f;
+          dxh[k] = dy * gam;
+          if (e & 1) { m1b += dxh[k]; m2b = fmaf(dxh[k], xh[k], m2b); } else { m1a += dxh[k]; m2a = fmaf(dxh[k], xh[k], m2a); }
+          o[e] = fmaxf(y, 0.f) * mk; t1[e] = dy * xh[k]; t2[e] = dy;
+        }
+        const uint32_t kc = uint32_t(HC / 8 * c.w + j);
+        *reinterpret_cast<uint4*>(ob + kc * kCS + row_off(c.rs)) = pack_bf16x8(o);
+        *reinterpret_cast<uint4*>(dyx + kc * kCS + row_off(c.rs)) = pack_bf16x8(t1);
+        *reinterpret_cast<uint4*>(dyx + (C::DV / 8 + kc) * kCS + row_off(c.rs)) = pack_bf16x8(t2);
+      }
+      part[c.w * 128 + c.rs] = make_float2(m1a + m1b, m2a + m2b);
+      __syncthreads();
+      const float2 other = part[(c.w ^ 1) * 128 + c.rs];
+      const float m1 = (m1a + m1b + other.x) * (1.0f / float(C::DV)), m2 = (m2a + m2b + other.y) * (1.0f / float(C::DV));
+#pragma unroll
+      for (int j = 0; j < HC / 8; ++j) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = rstd * (dxh[8 * j + e] - m1 - xh[8 * j + e] * m2);
+        *reinterpret_cast<uint4*>(dcb + uint32_t(HC / 8 * c.w + j) * kCS + row_off(c.rs)) = pack_bf16x8(o);
       }
     }
     cta_sync_for_mma();
+    MMRCA_STAMP(7);
     // ---- P7: dP (read back next); classifier-weight and LayerNorm-affine gradients (persistent, group G2) ------
     if (tid == 0) {
       for (int h = 0; h < 2; ++h)
@@ -554,6 +590,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
       umma_commit(&bars[3]);
     }
     cta_wait_mma(c);
+    MMRCA_STAMP(8);
     // ---- P8: softmax backward -> dS (reuses DL's bytes once G2 has read them) ----------------------------------------
     {
       float ds[16];
@@ -562,6 +599,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
       store_half_row_split(c, dls, ds, true);
     }
     cta_sync_for_mma();
+    MMRCA_STAMP(9);
     // ---- P9: dV = P^T dC, dZ = dS Xkv ----------------------------------------------------------------------------------
     if (tid == 0) {
       for (int h = 0; h < 2; ++h) {
@@ -573,10 +611,12 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
       umma_commit(c.bar);
     }
     cta_wait_mma(c);
+    MMRCA_STAMP(10);
     // ---- P10: dV, dZ -> operands (dV over V, dZ over dy*xhat | dy) ------------------------------------------------
     if (c.w == 0) acc_cols_to_operand(c, T::DZ, 0, 80, dyx, c.rs);
     else { acc_cols_to_operand(c, T::DZ, 80, 96, dyx, c.rs); acc_cols_to_operand(c, T::DV, 0, 48, vb, c.rs); }
     cta_sync_for_mma();
+    MMRCA_STAMP(11);
     // ---- P11: gradients of the block inputs (read back next), then the parameter gradients (persistent, G3) ------
     if (tid == 0) {
       // dXq = dZ M^T  (B: the Z blob read along its other axis)
@@ -597,6 +637,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
       umma_commit(&bars[4]);
     }
     cta_wait_mma(c);
+    MMRCA_STAMP(12);
     // ---- P12: input gradients -> bf16 images for the SA backward ---------------------------------------------------
     {
       uint8_t* gq = static_cast<uint8_t*>(D.dxq_img) + size_t(tile) * kSaTileBytes;
@@ -606,10 +647,12 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
       acc_cols_to_operand(c, T::DXKV, 48 * c.w, 48 * c.w + 48, gk, c.rs);
     }
     first = false;
+    MMRCA_STAMP(13);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
   }
+  MMRCA_STAMP(0);
   // ---- flush the persistent accumulators ---------------------------------------------------------------------------
   if (!first) {
     mbar_wait_ph(&bars[4], ph_g3);
@@ -639,6 +682,10 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
       else if (c.rp < 2 * C::DV) atomicAdd(D.g_ln_b + (c.rp - C::DV), v[0]);
     }
   }
+  __syncthreads();
+  MMRCA_STAMP(1);
+  MMRCA_STAMP_NS(251);
+  if (a.dbg && tid == 0) a.dbg[301 + 2 * (blockIdx.x + gridDim.x * blockIdx.y)] = globaltimer_ns();
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
@@ -662,9 +709,6 @@ struct SaBwdArgs {
   int batch;
   long long* dbg;                 // development: per-phase clock64 stamps of CTA 0 (null in production)
 };
-__device__ __forceinline__ long long globaltimer_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#define MMRCA_STAMP_NS(i) do { if (a.dbg && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) a.dbg[(i)] = globaltimer_ns(); } while (0)
-#define MMRCA_STAMP(i) do { if (a.dbg && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && stamp_n + (i) < 256) a.dbg[stamp_n + (i)] = clock64(); } while (0)
 template <int DIN_>
 struct SaBwdSmem {
   using C = SaCfg<DIN_>;
@@ -750,7 +794,22 @@ __device__ __forceinline__ void sa_bwd_body(const SaBwdArgs& a, uint8_t* sm) {
     //      fetch the NEXT tile's inputs into the other buffers ------------------------------------------------------
     if (!first) mbar_wait_ph(&bars[5], ph_g3);
     MMRCA_STAMP(1);
-    if (tid == 32 && tile + int(gridDim.x) < tiles) issue_inputs(tile + int(gridDim.x), buf ^ 1);
+    if (tid == 32 && tile + int(gridDim.x) < tiles) {
+      issue_inputs(tile + int(gridDim.x), buf ^ 1);
+      if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && stamp_n < 200) a.dbg[600 + stamp_n / 12] = clock64();
+    }
+    if (tid == 64) {        // L2 prefetch: dOut images of the next tile (plain loads), TMA inputs of the one after
+      const int t1 = tile + int(gridDim.x), t2 = t1 + int(gridDim.x);
+      if (t1 < tiles) {
+        bulk_prefetch_l2(static_cast<const uint8_t*>(a.dout_a) + size_t(t1) * kSaTileBytes, kSaTileBytes);
+        bulk_prefetch_l2(static_cast<const uint8_t*>(a.dout_b) + size_t(t1) * kSaTileBytes, kSaTileBytes);
+      }
+      if (t2 < tiles) {
+        bulk_prefetch_l2(static_cast<const uint8_t*>(a.x_tiles) + size_t(t2) * kXBytes, kXBytes);
+        bulk_prefetch_l2(static_cast<const uint8_t*>(a.v_tiles) + size_t(t2) * S::VB, S::VB);
+        bulk_prefetch_l2(static_cast<const uint8_t*>(a.p_tiles) + size_t(t2) * S::PB, S::PB);
+      }
+    }
     mbar_wait(&bars[buf], ph_in[buf]); ph_in[buf] ^= 1;
     tc_fence_after_sync();
     MMRCA_STAMP(2);

@@ -108,6 +108,12 @@ __device__ __forceinline__ void tmem_ld16_nw(uint32_t taddr, uint32_t (&r)[16]) 
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+// 32 lanes x 8 consecutive columns, no wait
+__device__ __forceinline__ void tmem_ld8_nw(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
 // 32 lanes x 32 consecutive columns, no wait
 __device__ __forceinline__ void tmem_ld32_nw(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -127,6 +133,10 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+// bulk prefetch of [p, p + bytes) into the L2 (bytes % 16 == 0): no shared memory, no completion to wait for
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 // shared -> global bulk copy (TMA store), tracked by the bulk async-group of the issuing thread
 __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {

@@ -221,8 +221,8 @@ int mmrca_timing_begin(int32_t max_records);
 int mmrca_timing_end(MmrcaKernelTime* out, int32_t max_out);
 
 /* Development aid: a device buffer of 1024 int64 that receives per-phase clock64() stamps of CTA 0 of the profiled
- * tile kernel on its next launches (NULL switches it off; off by default). */
-int mmrca_dev_set_debug(void* device_buffer_1024_int64);
+ * tile kernel (kernel 0: SA backward, 1: CA backward) on its next launches (NULL switches it off; off by default). */
+int mmrca_dev_set_debug(void* device_buffer_1024_int64, int32_t kernel);
 
 /* Diagnostic: one 128 x N x K bf16 tcgen05 GEMM (fp32 accumulate in TMEM) through the library's operand
  * staging.  mode bit 0: b is [K][N] (MN-major) instead of [N][K]; bit 1: a is [K][128] instead of [128][K].

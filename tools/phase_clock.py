@@ -5,7 +5,9 @@ import torch
 import garbage_classification_rca_b200 as g
 from garbage_classification_rca_b200 import _native as N, functional as F
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-per = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+kern = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # 0: SA backward, 1: CA backward
+per = 16 if kern == 1 else 12
+rounds = 7
 params = F.init_head_parameters("cuda", seed=0)
 step = g.HeadTrainStep(params, B, 1280, 768, reverse=True, compute=N.COMPUTE_BF16, drop_p=0.6)
 img = torch.randn(B, 1280, device="cuda"); txt = torch.randn(B, 768, device="cuda")
@@ -13,23 +15,28 @@ lab = torch.randint(0, 4, (B,), device="cuda")
 dbg = torch.zeros(1024, dtype=torch.int64, device="cuda")
 for i in range(3):
     step.zero_grad(); step(img, txt, lab, drop_seed=i)
-N.lib().mmrca_dev_set_debug(dbg.data_ptr())
+N.lib().mmrca_dev_set_debug(dbg.data_ptr(), kern)
 step.zero_grad(); step(img, txt, lab, drop_seed=9)
 torch.cuda.synchronize()
-N.lib().mmrca_dev_set_debug(None)
+N.lib().mmrca_dev_set_debug(None, 0)
 d = dbg.cpu().tolist()
 t0 = d[0]
 print("stamps (cycles since kernel start of CTA 0):")
 vals = [v - t0 for v in d if v]
-print(vals[:1 + 4 * per + 2])
-for t in range(4):
+print(vals[:1 + rounds * per + 2])
+for t in range(rounds):
     row = d[1 + t * per: 1 + (t + 1) * per]
     if not row[0]: break
     print(f"tile {t}: start {row[0] - t0:7d}  deltas", [row[i + 1] - row[i] for i in range(per - 1) if row[i + 1]])
 ns = d[251] - d[250]
 cyc = max(v for v in d[:250]) - d[0]
+ncta = 148
 print(f"CTA 0: {cyc} cycles in {ns} ns -> SM clock {cyc / ns * 1e3:.0f} MHz")
 ent = [d[300 + 2 * i] for i in range(148)]; ex = [d[301 + 2 * i] for i in range(148)]
 t0 = min(ent)
 print("CTA entry ns (min..max):", 0, max(ent) - t0, " main-loop start of CTA 0:", d[250] - t0, " exits (min..max):", min(ex) - t0, max(ex) - t0)
 print("per-CTA duration ns: ", sorted(e - s for s, e in zip(ent, ex))[::12])
+
+if kern == 0:
+    print("TMA issue stamps (tile k issues k+1):", [v - d[0] for v in d[600:608] if v])
+    print("tile starts + wait-end (stamp 2):", [(d[1 + t * per] - d[0], d[1 + t * per + 2] - d[0]) for t in range(rounds) if d[1 + t * per]])
