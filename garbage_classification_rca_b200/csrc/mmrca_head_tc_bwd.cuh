@@ -774,30 +774,30 @@ __device__ __forceinline__ void sa_bwd_body(const SaBwdArgs& a, uint8_t* sm) {
   int buf = 0, stamp_n = 0;
   MMRCA_STAMP(0); stamp_n = 1;
   MMRCA_STAMP_NS(250);
+  // my share of dOut = image a + image b (written by the CA backward): row rs, columns [48w, 48w + 48), and the forward's
+  // LayerNorm statistics of the row, straight from L2 into registers.  They are requested most of a tile ahead (during
+  // the previous tile's dV / dZ MMAs): their latency is never waited for.
+  uint4 ra[6], rb[6];
+  float2 st;
+  auto load_dout = [&](int t) {
+    const uint8_t* ga = static_cast<const uint8_t*>(a.dout_a) + size_t(t) * kSaTileBytes + uint32_t(6 * c.w) * kCS + row_off(c.rs);
+    const uint8_t* gb = static_cast<const uint8_t*>(a.dout_b) + size_t(t) * kSaTileBytes + uint32_t(6 * c.w) * kCS + row_off(c.rs);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      ra[j] = __ldg(reinterpret_cast<const uint4*>(ga + j * kCS));
+      rb[j] = __ldg(reinterpret_cast<const uint4*>(gb + j * kCS));
+    }
+    st = __ldg(a.ln_stats + size_t(t) * 128 + c.rs);
+  };
+  if (int(blockIdx.x) < tiles) load_dout(blockIdx.x);
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, buf ^= 1, stamp_n += 12) {
     uint8_t *xb = sm + S::X + buf * S::XB, *vb = sm + S::V + buf * S::VB, *pb = sm + S::P + buf * S::PB;
     MMRCA_STAMP(0);
-    // ---- my share of dOut = image a + image b (written by the CA backward): row rs, columns [48w, 48w + 48), straight
-    //      from L2 into registers, in flight while the inputs land and C is recomputed -----------------------------
-    uint4 ra[6], rb[6];
-    {
-      const uint8_t* ga = static_cast<const uint8_t*>(a.dout_a) + size_t(tile) * kSaTileBytes + uint32_t(6 * c.w) * kCS + row_off(c.rs);
-      const uint8_t* gb = static_cast<const uint8_t*>(a.dout_b) + size_t(tile) * kSaTileBytes + uint32_t(6 * c.w) * kCS + row_off(c.rs);
-#pragma unroll
-      for (int j = 0; j < 6; ++j) {
-        ra[j] = __ldg(reinterpret_cast<const uint4*>(ga + j * kCS));
-        rb[j] = __ldg(reinterpret_cast<const uint4*>(gb + j * kCS));
-      }
-    }
-    const float2 st = __ldg(a.ln_stats + size_t(tile) * 128 + c.rs);
     // ---- the previous tile's dM / dWv MMAs (G3) still read its X, dV (in dC's buffer) and dZ: once they are done,
     //      fetch the NEXT tile's inputs into the other buffers ------------------------------------------------------
     if (!first) mbar_wait_ph(&bars[5], ph_g3);
     MMRCA_STAMP(1);
-    if (tid == 32 && tile + int(gridDim.x) < tiles) {
-      issue_inputs(tile + int(gridDim.x), buf ^ 1);
-      if (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && stamp_n < 200) a.dbg[600 + stamp_n / 12] = clock64();
-    }
+    if (tid == 32 && tile + int(gridDim.x) < tiles) issue_inputs(tile + int(gridDim.x), buf ^ 1);
     if (tid == 64) {        // L2 prefetch: dOut images of the next tile (plain loads), TMA inputs of the one after
       const int t1 = tile + int(gridDim.x), t2 = t1 + int(gridDim.x);
       if (t1 < tiles) {
@@ -928,6 +928,7 @@ __device__ __forceinline__ void sa_bwd_body(const SaBwdArgs& a, uint8_t* sm) {
       }
       umma_commit(c.bar);
     }
+    if (tile + int(gridDim.x) < tiles) load_dout(tile + int(gridDim.x));
     cta_wait_mma(c);
     MMRCA_STAMP(9);
     mbar_wait_ph(&bars[4], ph_g2);                 // dgamma|dbeta have read dy*xhat | dy: its bytes become dZ

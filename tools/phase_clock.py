@@ -37,6 +37,3 @@ t0 = min(ent)
 print("CTA entry ns (min..max):", 0, max(ent) - t0, " main-loop start of CTA 0:", d[250] - t0, " exits (min..max):", min(ex) - t0, max(ex) - t0)
 print("per-CTA duration ns: ", sorted(e - s for s, e in zip(ent, ex))[::12])
 
-if kern == 0:
-    print("TMA issue stamps (tile k issues k+1):", [v - d[0] for v in d[600:608] if v])
-    print("tile starts + wait-end (stamp 2):", [(d[1 + t * per] - d[0], d[1 + t * per + 2] - d[0]) for t in range(rounds) if d[1 + t * per]])
