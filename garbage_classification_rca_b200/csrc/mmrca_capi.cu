@@ -451,7 +451,7 @@ static int head_backward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p,
     a.dbg = g_dbg_kernel == 1 ? g_dbg : nullptr;
     if ((rc = set_smem(htc::ca_bwd_kernel, htc::CaBwdSmem::BYTES))) return rc;
     LaunchScope ls("ca_bwd_bf16", st);
-    htc::ca_bwd_kernel<<<dim3(min(tiles, max(1, sms / 2)), 2), htc::kCtaThreads, htc::CaBwdSmem::BYTES, st>>>(a);
+    htc::ca_bwd_kernel<<<dim3(min(tiles, max(1, sms / 2)), 2), htc::kCaBwdThreads, htc::CaBwdSmem::BYTES, st>>>(a);
   }
   MMRCA_CUDA(cudaGetLastError());
   {
@@ -539,7 +539,7 @@ static int head_forward_impl(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, c
     const DropSpec ds = make_drop(d);
     {
       LaunchScope ls("dropout_mask", st);
-      dropout_mask_kernel<<<min(4 * sms, max(1, int((size_t(d.batch) * ds.D / 2 + 255) / 256))), 256, 0, st>>>(ds, d.batch, w.mask);
+      dropout_mask_kernel<<<min(4 * sms, max(1, int((size_t(d.batch) * ds.D / 4 + 255) / 256))), 256, 0, st>>>(ds, d.batch, w.mask);
     }
     MMRCA_CUDA(cudaGetLastError());
     mask = w.mask; scale = ds.scale;
@@ -843,8 +843,8 @@ int mmrca_attention_backward(const MmrcaAttnParams* p, const float* x_q, const f
 }
 
 int mmrca_dropout_mask(uint64_t seed, float p, int32_t batch, int32_t width, uint8_t* mask_out, void* stream) {
-  if (!mask_out || batch < 0 || width <= 0 || (width & 1) || !(p >= 0.f && p <= 1.f))
-    return fail(MMRCA_ERR_INVALID, "dropout mask needs an even width, p in [0, 1] and an output buffer%s%s");
+  if (!mask_out || batch < 0 || width <= 0 || (width & 3) || !(p >= 0.f && p <= 1.f))
+    return fail(MMRCA_ERR_INVALID, "dropout mask needs a width that is a multiple of 4, p in [0, 1] and an output buffer%s%s");
   DeviceInfo di;
   int rc;
   if ((rc = device_info(&di))) return rc;
@@ -858,7 +858,7 @@ int mmrca_dropout_mask(uint64_t seed, float p, int32_t batch, int32_t width, uin
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   {
     LaunchScope ls("dropout_mask", st);
-    dropout_mask_kernel<<<min(4 * di.sms, max(1, int((size_t(batch) * width / 2 + 255) / 256))), 256, 0, st>>>(ds, batch, mask_out);
+    dropout_mask_kernel<<<min(4 * di.sms, max(1, int((size_t(batch) * width / 4 + 255) / 256))), 256, 0, st>>>(ds, batch, mask_out);
   }
   MMRCA_CUDA(cudaGetLastError());
   return MMRCA_OK;

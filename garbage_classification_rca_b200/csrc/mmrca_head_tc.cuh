@@ -218,7 +218,7 @@ __device__ __forceinline__ void feat_load(const FeatSrc& S, int b, bool live, in
 // ws: this source's [4][16 * DIN] slice of the classifier weight in shared memory
 template <int DIN>
 __device__ __forceinline__ void feat_emit(const FeatArgs& a, const FeatSrc& S, const float* ws, int b, bool live, int lane,
-                                          const float (&v)[(kL * DIN / 8 + 31) / 32][8], float (&cls)[kClasses]) {
+                                          const float (&v)[(kL * DIN / 8 + 31) / 32][8], float (&acc)[kClasses]) {
   constexpr int KCS = DIN / 8, ITEMS = kL * KCS, PER = (ITEMS + 31) / 32;
   float ss = 0.f;
 #pragma unroll
@@ -230,7 +230,6 @@ __device__ __forceinline__ void feat_emit(const FeatArgs& a, const FeatSrc& S, c
   if (lane == 0 && live) S.norms[b] = nrm;
   uint8_t* tile = static_cast<uint8_t*>(S.x_tiles) + size_t(b >> 3) * x_tile_bytes(DIN);
   const int r0 = (b & 7) * kL;
-  float acc[kClasses] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int k = 0; k < PER; ++k) {
     const int it = lane + 32 * k;
@@ -241,14 +240,7 @@ __device__ __forceinline__ void feat_emit(const FeatArgs& a, const FeatSrc& S, c
     for (int e = 0; e < 8; ++e) o[e] = v[k][e] * inv;
     *reinterpret_cast<uint4*>(tile + uint32_t(kc) * kCS + row_off(r0 + row)) = pack_bf16x8(o);
     if (a.with_features && live) {
-      if (a.drop.thresh) {
-#pragma unroll
-        for (int e = 0; e < 8; e += 2) {
-          float m0, m1;
-          drop_pair(a.drop, uint32_t(b), uint32_t(S.cls_off + it * 8 + e), m0, m1);
-          o[e] *= m0; o[e + 1] *= m1;
-        }
-      }
+      if (a.drop.thresh) drop_apply8(a.drop, uint32_t(b), uint32_t(S.cls_off + it * 8), o);
 #pragma unroll
       for (int cc = 0; cc < kClasses; ++cc) {
         const float4 w0 = *reinterpret_cast<const float4*>(ws + cc * (kL * DIN) + it * 8);
@@ -261,39 +253,58 @@ __device__ __forceinline__ void feat_emit(const FeatArgs& a, const FeatSrc& S, c
   // the bias column groups of my 16 rows: lanes 0-15 the ones column, lanes 16-31 the zero group
   *reinterpret_cast<uint4*>(tile + uint32_t(KCS + (lane >> 4)) * kCS + row_off(r0 + (lane & 15))) =
       make_uint4(lane < 16 ? 0x00003F80u : 0u, 0u, 0u, 0u);
-#pragma unroll
-  for (int cc = 0; cc < kClasses; ++cc) cls[cc] += warp_sum(acc[cc]);
 }
 
 __global__ void __launch_bounds__(256) prep_feat_kernel(const PrepArgs pa, const FeatArgs fa, int prep_ctas) {
   extern __shared__ __align__(16) float wsm_f[];      // [4][1280] image columns, then [4][768] text columns
   if (int(blockIdx.x) < prep_ctas) { prep_body(pa, blockIdx.x, prep_ctas, wsm_f); return; }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb = ((fa.batch + 7) / 8) * 8;      // whole tiles: the padding samples of the last tile become zero rows
+  const int stride = (int(gridDim.x) - prep_ctas) * 8;
+  int b = (int(blockIdx.x) - prep_ctas) * 8 + warp;
+  // the first sample's features are requested before anything else: they travel while the classifier slice is staged
+  float vi[5][8], vt[3][8];
+  if (b < nb) {
+    feat_load<80>(fa.src[0], b, b < fa.batch, lane, vi);
+    feat_load<48>(fa.src[1], b, b < fa.batch, lane, vt);
+  }
   if (fa.with_features) {
-    for (int i = threadIdx.x; i < kClasses * kFeatCols / 4; i += 256) {
-      const int f = 4 * i;
-      int cc, j, off;
-      if (f < kClasses * 1280) { cc = f / 1280; j = f - cc * 1280; off = fa.src[0].cls_off; }
-      else { const int g = f - kClasses * 1280; cc = g / 768; j = g - cc * 768; off = fa.src[1].cls_off; }
-      reinterpret_cast<float4*>(wsm_f)[i] = __ldg(reinterpret_cast<const float4*>(fa.wf + size_t(cc) * fa.drop.D + off + j));
+    constexpr int N4 = kClasses * kFeatCols / 4 / 256;      // 8 float4 per thread, requested four at a time
+    static_assert(N4 * 256 * 4 == kClasses * kFeatCols && N4 % 4 == 0, "classifier slice staging");
+#pragma unroll
+    for (int u0 = 0; u0 < N4; u0 += 4) {
+      float4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int f = 4 * (int(threadIdx.x) + 256 * (u0 + u));
+        int cc, j, off;
+        if (f < kClasses * 1280) { cc = f / 1280; j = f - cc * 1280; off = fa.src[0].cls_off; }
+        else { const int g = f - kClasses * 1280; cc = g / 768; j = g - cc * 768; off = fa.src[1].cls_off; }
+        t[u] = __ldg(reinterpret_cast<const float4*>(fa.wf + size_t(cc) * fa.drop.D + off + j));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) reinterpret_cast<float4*>(wsm_f)[int(threadIdx.x) + 256 * (u0 + u)] = t[u];
     }
   }
   __syncthreads();
-  const int nb = ((fa.batch + 7) / 8) * 8;      // whole tiles: the padding samples of the last tile become zero rows
-  const int stride = (int(gridDim.x) - prep_ctas) * 8;
-  for (int b = (int(blockIdx.x) - prep_ctas) * 8 + warp; b < nb; b += stride) {
+  while (b < nb) {
     const bool live = b < fa.batch;
-    float vi[5][8], vt[3][8];
-    feat_load<80>(fa.src[0], b, live, lane, vi);
-    feat_load<48>(fa.src[1], b, live, lane, vt);
-    float cls[kClasses] = {0.f, 0.f, 0.f, 0.f};
-    feat_emit<80>(fa, fa.src[0], wsm_f, b, live, lane, vi, cls);
-    feat_emit<48>(fa, fa.src[1], wsm_f + kClasses * 1280, b, live, lane, vt, cls);
+    float acc[kClasses] = {0.f, 0.f, 0.f, 0.f};
+    feat_emit<80>(fa, fa.src[0], wsm_f, b, live, lane, vi, acc);
+    feat_emit<48>(fa, fa.src[1], wsm_f + kClasses * 1280, b, live, lane, vt, acc);
+    const int bn = b + stride;
+    if (bn < nb) {      // the next sample's features travel while the classifier terms are reduced and written
+      feat_load<80>(fa.src[0], bn, bn < fa.batch, lane, vi);
+      feat_load<48>(fa.src[1], bn, bn < fa.batch, lane, vt);
+    }
+#pragma unroll
+    for (int cc = 0; cc < kClasses; ++cc) acc[cc] = warp_sum(acc[cc]);
     if (lane < kClasses && live) {
-      float r = cls[0];
-      r = lane == 1 ? cls[1] : r; r = lane == 2 ? cls[2] : r; r = lane == 3 ? cls[3] : r;
+      float r = acc[0];
+      r = lane == 1 ? acc[1] : r; r = lane == 2 ? acc[2] : r; r = lane == 3 ? acc[3] : r;
       fa.logits[size_t(b) * kClasses + lane] = __ldg(fa.bf + lane) + r;
     }
+    b = bn;
   }
 }
 
@@ -679,6 +690,18 @@ __device__ __forceinline__ void write_bias_columns(uint8_t* op, int kc0, int row
   *reinterpret_cast<uint4*>(op + uint32_t(kc0 + 1) * kCS + row_off(row)) = make_uint4(0u, 0u, 0u, 0u);
 }
 
+// Input images of (tile, direction d) through the bulk-copy engine, one mbarrier phase per tile: the key/value image is
+// requested first (it arms the barrier for both), the query image second.
+__device__ __forceinline__ void ca_issue_kv(const CaFwdArgs& a, int d, int tile, uint8_t* xkv, uint64_t* bar_ld) {
+  const uint8_t* ksrc = static_cast<const uint8_t*>(d == 0 ? a.i_tiles : a.t_tiles) + size_t(tile) * kSaTileBytes;
+  mbar_arrive_expect_tx(bar_ld, 2 * kSaTileBytes);
+  bulk_g2s(xkv, ksrc, kSaTileBytes, bar_ld);
+}
+__device__ __forceinline__ void ca_issue_q(const CaFwdArgs& a, int d, int tile, uint8_t* xq, uint64_t* bar_ld) {
+  const uint8_t* qsrc = static_cast<const uint8_t*>(d == 0 ? a.t_tiles : a.i_tiles) + size_t(tile) * kSaTileBytes;
+  bulk_g2s(xq, qsrc, kSaTileBytes, bar_ld);
+}
+
 __device__ __forceinline__ void ca_fwd_tile(WgCtx& c, const CaFwdArgs& a, int d, uint8_t* wsm, uint8_t* bsm,
                                             const float* ln_s, uint64_t* bar_ld, uint32_t& ph_ld, int tile, int next_tile) {
   using C = CaCfg;
@@ -686,18 +709,7 @@ __device__ __forceinline__ void ca_fwd_tile(WgCtx& c, const CaFwdArgs& a, int d,
   uint8_t* xq = bsm + CaFwdSmem::XQ;
   uint8_t* xkv = bsm + CaFwdSmem::XKV;
   uint8_t* vop = bsm + CaFwdSmem::V;
-  // ---- SA images of this tile through the bulk-copy engine ---------------------------------------------------
-  if (c.wt == 0) {
-    const uint8_t* qsrc = static_cast<const uint8_t*>(d == 0 ? a.t_tiles : a.i_tiles) + size_t(tile) * kSaTileBytes;
-    const uint8_t* ksrc = static_cast<const uint8_t*>(d == 0 ? a.i_tiles : a.t_tiles) + size_t(tile) * kSaTileBytes;
-    mbar_arrive_expect_tx(bar_ld, 2 * kSaTileBytes);
-    bulk_g2s(xq, qsrc, kSaTileBytes, bar_ld);
-    bulk_g2s(xkv, ksrc, kSaTileBytes, bar_ld);
-    if (c.wg == 0 && next_tile >= 0) {      // the next tile's images (both warpgroups read both): into the L2 meanwhile
-      bulk_prefetch_l2(static_cast<const uint8_t*>(a.t_tiles) + size_t(next_tile) * kSaTileBytes, kSaTileBytes);
-      bulk_prefetch_l2(static_cast<const uint8_t*>(a.i_tiles) + size_t(next_tile) * kSaTileBytes, kSaTileBytes);
-    }
-  }
+  // ---- SA images of this tile: requested during the previous tile (ca_issue_kv / ca_issue_q below) -----------------
   write_bias_columns(xq, C::DIN / 8, c.wt);     // (Z / P / Out reuse only the first 96 columns of xq, but the
   write_bias_columns(xkv, C::DIN / 8, c.wt);    //  image load of the next tile must not race with stale readers)
   mbar_wait(bar_ld, ph_ld);
@@ -725,6 +737,14 @@ __device__ __forceinline__ void ca_fwd_tile(WgCtx& c, const CaFwdArgs& a, int d,
     umma_commit(c.bar);
   }
   wg_wait_mma(c);
+  // the key/value image is dead (V and the scores have read it): the next tile's lands while this one finishes
+  if (c.wt == 0 && next_tile >= 0) {
+    ca_issue_kv(a, d ^ 1, next_tile, xkv, bar_ld);
+    if (c.wg == 0 && next_tile + int(gridDim.x) < (a.batch + 7) / 8) {      // and the tile after that: into the L2
+      bulk_prefetch_l2(static_cast<const uint8_t*>(a.t_tiles) + size_t(next_tile + gridDim.x) * kSaTileBytes, kSaTileBytes);
+      bulk_prefetch_l2(static_cast<const uint8_t*>(a.i_tiles) + size_t(next_tile + gridDim.x) * kSaTileBytes, kSaTileBytes);
+    }
+  }
   {
     float p[16];
     softmax16(c, C::COL_S, a.reverse != 0, p);
@@ -756,10 +776,10 @@ __device__ __forceinline__ void ca_fwd_tile(WgCtx& c, const CaFwdArgs& a, int d,
         o[e] = fmaxf(fmaf((__uint_as_float(r[e]) - mean) * rstd, ln_s[c0 + e], ln_s[48 + c0 + e]), 0.f);
       if (a.drop.thresh) {      // self.drop (:719) acts on the classifier's copy only
 #pragma unroll
-        for (int e = 0; e < 16; e += 2) {
-          float m0, m1;
-          drop_pair(a.drop, uint32_t(b0 + (c.rs >> 4)), cat0 + c0 + e, m0, m1);
-          o[e] *= m0; o[e + 1] *= m1;
+        for (int e = 0; e < 16; e += 4) {
+          float m[4];
+          drop_quad(a.drop, uint32_t(b0 + (c.rs >> 4)), cat0 + c0 + e, m);
+          o[e] *= m[0]; o[e + 1] *= m[1]; o[e + 2] *= m[2]; o[e + 3] *= m[3];
         }
       }
       const float lo[8] = {o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]};
@@ -776,6 +796,7 @@ __device__ __forceinline__ void ca_fwd_tile(WgCtx& c, const CaFwdArgs& a, int d,
     umma_commit(c.bar);
   }
   wg_wait_mma(c);
+  if (c.wt == 0 && next_tile >= 0) ca_issue_q(a, d ^ 1, next_tile, xq, bar_ld);      // the classifier has read Out: xq is free
   cls_readback(c, C::COL_CLS, a.logits, b0 + (c.rp >> 4), b0 + (c.rp >> 4) < a.batch);
   tc_fence_before_sync();
   named_bar_sync(1 + c.wg, kWgThreads);
@@ -813,6 +834,10 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_fwd_kernel(const CaFwdArgs 
   uint32_t ph_ld = 0;
   const int tiles = (a.batch + 7) / 8;
   int round = 0;
+  if ((tid & 127) == 0 && int(blockIdx.x) < tiles) {      // this warpgroup's first tile (direction wg)
+    ca_issue_kv(a, wg, blockIdx.x, bsm + CaFwdSmem::XKV, &bars[3 + wg]);
+    ca_issue_q(a, wg, blockIdx.x, bsm + CaFwdSmem::XQ, &bars[3 + wg]);
+  }
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++round) {
     const int d = (wg + round) & 1;
     ca_fwd_tile(c, a, d, sm + (d == 0 ? L::W0 : L::W1), bsm, ln_s + d * 96, &bars[3 + wg], ph_ld, tile,

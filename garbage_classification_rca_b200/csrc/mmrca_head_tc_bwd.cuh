@@ -141,14 +141,7 @@ __global__ void __launch_bounds__(256) ce_feat_kernel(const CeFeatArgs a) {
     const int tl = 2 * i + half, t = tile0 + tl;
     float x[8];
     unpack_bf16x8(raw[i], x);
-    if (a.drop.thresh) {
-#pragma unroll
-      for (int e = 0; e < 8; e += 2) {
-        float m0, m1;
-        drop_pair(a.drop, uint32_t(t * 8 + g), uint32_t(col0 + e), m0, m1);
-        x[e] *= m0; x[e + 1] *= m1;
-      }
-    }
+    if (a.drop.thresh) drop_apply8(a.drop, uint32_t(t * 8 + g), uint32_t(col0), x);
     const float4 d = dl_s[tl * 8 + g];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -269,10 +262,12 @@ __device__ __forceinline__ void mbar_wait_ph(uint64_t* bar, uint32_t& ph) {
 }
 
 // DL[row (b,r)][(r',c)] = dlogits[b][c] [r' == r]: warpgroup w writes column groups 4w .. 4w+3 of the row
-__device__ __forceinline__ void stage_dl(const BwCtx& c, uint8_t* dl, const float* __restrict__ dlogits, int b0, int batch) {
-  const int g = c.rp >> 4, r = c.rp & 15, b = b0 + g;
-  float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (b < batch) d = __ldg(reinterpret_cast<const float4*>(dlogits) + b);
+__device__ __forceinline__ float4 load_dl(const BwCtx& c, const float* __restrict__ dlogits, int b0, int batch) {
+  const int b = b0 + (c.rp >> 4);
+  return b < batch ? __ldg(reinterpret_cast<const float4*>(dlogits) + b) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ void stage_dl(const BwCtx& c, uint8_t* dl, const float4 d) {
+  const int r = c.rp & 15;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int kc = 4 * c.w + k;
@@ -410,7 +405,18 @@ struct CaBwdCols {   // TMEM columns
   static constexpr uint32_t G_M = 256, G_WV = 352, G_WF = 400, G_LN = 464;
 };
 
-__global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs a) {
+// 8 worker warps + 1 loader warp.  The loader waits for the previous tile's dM / dWv MMAs (the last readers of the
+// input images) and then asks the bulk-copy engine for the next tile, so the images land while the workers are still
+// writing the previous tile's input gradients; the workers synchronise among themselves on a named barrier.
+constexpr int kCaBwdThreads = kCtaThreads + 32;
+__device__ __forceinline__ void wk_sync() { named_bar_sync(1, kCtaThreads); }
+__device__ __forceinline__ void wk_sync_for_mma() {
+  fence_proxy_async();
+  tc_fence_before_sync();
+  wk_sync();
+  tc_fence_after_sync();
+}
+__global__ void __launch_bounds__(kCaBwdThreads, 1) ca_bwd_kernel(const CaBwdArgs a) {
   extern __shared__ __align__(128) uint8_t sm[];
   using S = CaBwdSmem; using T = CaBwdCols; using C = CaCfg;
   // mbarriers: [0] weights, [1] MMAs whose result is read back next, [2] tile load,
@@ -431,8 +437,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
     bulk_g2s(sm + S::W, D.blobs, C::W_BYTES, &bars[0]);
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
-  for (int i = tid; i < 48; i += kCtaThreads) { ln_s[i] = D.ln_g[i]; ln_s[48 + i] = D.ln_b[i]; }
-  for (uint32_t i = tid; i < (2 * kPHalf + 4096) / 16; i += kCtaThreads) {     // P zeros, then the ones operand
+  for (int i = tid; i < 48; i += kCaBwdThreads) { ln_s[i] = D.ln_g[i]; ln_s[48 + i] = D.ln_b[i]; }
+  for (uint32_t i = tid; i < (2 * kPHalf + 4096) / 16; i += kCaBwdThreads) {     // P zeros, then the ones operand
     const uint32_t off = i * 16;
     reinterpret_cast<uint4*>(sm + S::P)[i] =
         off < 2 * kPHalf ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
@@ -449,7 +455,28 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
           *dyx = sm + S::DYX, *dls = sm + S::DLS, *pb = sm + S::P, *ones = sm + S::ONES, *wsm = sm + S::W;
   const uint8_t* bz = wsm; const uint8_t* bv = wsm + C::BZ_BYTES; const uint8_t* bc = wsm + C::BZ_BYTES + C::BV_BYTES;
   const int tiles = (a.batch + 7) / 8;
+  if (warp == kCtaThreads / 32) {      // ---- loader warp ----------------------------------------------------------------
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x, it = 0; tile < tiles; tile += gridDim.x, ++it) {
+      if (it > 0) { mbar_wait(&bars[4], ph); ph ^= 1; }
+      if ((tid & 31) == 0) {
+        const uint8_t* qsrc = static_cast<const uint8_t*>(d == 0 ? a.t_tiles : a.i_tiles) + size_t(tile) * kSaTileBytes;
+        const uint8_t* ksrc = static_cast<const uint8_t*>(d == 0 ? a.i_tiles : a.t_tiles) + size_t(tile) * kSaTileBytes;
+        mbar_arrive_expect_tx(&bars[2], 2 * kSaTileBytes);
+        bulk_g2s(xq, qsrc, kSaTileBytes, &bars[2]);
+        bulk_g2s(xkv, ksrc, kSaTileBytes, &bars[2]);
+        if (tile + int(gridDim.x) < tiles) {      // the tile after: into the L2 meanwhile
+          bulk_prefetch_l2(qsrc + size_t(gridDim.x) * kSaTileBytes, kSaTileBytes);
+          bulk_prefetch_l2(ksrc + size_t(gridDim.x) * kSaTileBytes, kSaTileBytes);
+        }
+      }
+      __syncwarp();
+    }
+  } else {                             // ---- worker warps ---------------------------------------------------------------
   bool first = true;
+  int ntiles = 0;
+  float4 dl_next = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (int(blockIdx.x) < tiles) dl_next = load_dl(c, a.dlogits, blockIdx.x * 8, a.batch);
   int stamp_n = 0;
   if (a.dbg && tid == 0) a.dbg[300 + 2 * (blockIdx.x + gridDim.x * blockIdx.y)] = globaltimer_ns();
   MMRCA_STAMP(0); stamp_n = 1;
@@ -457,22 +484,12 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, stamp_n += 16) {
     const int b0 = tile * 8;
     MMRCA_STAMP(0);
-    // ---- P0: DL from dlogits; block inputs (SA images) by TMA once the previous tile's dM / dWv MMAs are done ----
-    stage_dl(c, dls, a.dlogits, b0, a.batch);
-    if (!first) mbar_wait_ph(&bars[4], ph_g3);
-    if (tid == 0) {
-      const uint8_t* qsrc = static_cast<const uint8_t*>(d == 0 ? a.t_tiles : a.i_tiles) + size_t(tile) * kSaTileBytes;
-      const uint8_t* ksrc = static_cast<const uint8_t*>(d == 0 ? a.i_tiles : a.t_tiles) + size_t(tile) * kSaTileBytes;
-      mbar_arrive_expect_tx(&bars[2], 2 * kSaTileBytes);
-      bulk_g2s(xq, qsrc, kSaTileBytes, &bars[2]);
-      bulk_g2s(xkv, ksrc, kSaTileBytes, &bars[2]);
-      if (tile + int(gridDim.x) < tiles) {      // the next tile's images: into the L2 while this tile is worked on
-        bulk_prefetch_l2(qsrc + size_t(gridDim.x) * kSaTileBytes, kSaTileBytes);
-        bulk_prefetch_l2(ksrc + size_t(gridDim.x) * kSaTileBytes, kSaTileBytes);
-      }
-    }
+    // ---- P0: DL from dlogits; block inputs (SA images): requested by the loader warp once the previous tile's dM / dWv
+    //      MMAs were done, which also makes their operand buffers (dZ, dV) free to overwrite below -------------------------
+    stage_dl(c, dls, dl_next);
+    if (tile + int(gridDim.x) < tiles) dl_next = load_dl(c, a.dlogits, (tile + int(gridDim.x)) * 8, a.batch);   // a tile ahead
     mbar_wait(&bars[2], ph_ld); ph_ld ^= 1;
-    cta_sync_for_mma();
+    wk_sync_for_mma();
     MMRCA_STAMP(1);
     // ---- P1: Z, V (M=128) and dOut = DL Wf_src^T (two M=64 halves, s-mapping like C) ----------------------------
     if (tid == 0) {
@@ -490,7 +507,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
     // ---- P2: Z, V -> operands (columns split) ---------------------------------------------------------------------
     acc_cols_to_operand(c, T::Z, 48 * c.w, 48 * c.w + 48, zb, c.rp);
     if (c.w == 0) acc_cols_to_operand(c, T::V, 0, 32, vb, c.rp); else acc_cols_to_operand(c, T::V, 32, 48, vb, c.rp);
-    cta_sync_for_mma();
+    wk_sync_for_mma();
     MMRCA_STAMP(3);
     // ---- P3: scores ----------------------------------------------------------------------------------------------------
     if (tid == 0) {
@@ -504,7 +521,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
     float p[16];
     softmax16_bw(c, T::S, reverse, p);
     store_half_row_split(c, pb, p, false);
-    cta_sync_for_mma();
+    wk_sync_for_mma();
     MMRCA_STAMP(5);
     // ---- P5: context ---------------------------------------------------------------------------------------------------
     if (tid == 0) {
@@ -564,7 +581,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
         *reinterpret_cast<uint4*>(dyx + (C::DV / 8 + kc) * kCS + row_off(c.rs)) = pack_bf16x8(t2);
       }
       part[c.w * 128 + c.rs] = make_float2(m1a + m1b, m2a + m2b);
-      __syncthreads();
+      wk_sync();
       const float2 other = part[(c.w ^ 1) * 128 + c.rs];
       const float m1 = (m1a + m1b + other.x) * (1.0f / float(C::DV)), m2 = (m2a + m2b + other.y) * (1.0f / float(C::DV));
 #pragma unroll
@@ -575,7 +592,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
         *reinterpret_cast<uint4*>(dcb + uint32_t(HC / 8 * c.w + j) * kCS + row_off(c.rs)) = pack_bf16x8(o);
       }
     }
-    cta_sync_for_mma();
+    wk_sync_for_mma();
     MMRCA_STAMP(7);
     // ---- P7: dP (read back next); classifier-weight and LayerNorm-affine gradients (persistent, group G2) ------
     if (tid == 0) {
@@ -598,7 +615,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
       mbar_wait_ph(&bars[3], ph_g2);
       store_half_row_split(c, dls, ds, true);
     }
-    cta_sync_for_mma();
+    wk_sync_for_mma();
     MMRCA_STAMP(9);
     // ---- P9: dV = P^T dC, dZ = dS Xkv ----------------------------------------------------------------------------------
     if (tid == 0) {
@@ -615,7 +632,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
     // ---- P10: dV, dZ -> operands (dV over V, dZ over dy*xhat | dy) ------------------------------------------------
     if (c.w == 0) acc_cols_to_operand(c, T::DZ, 0, 80, dyx, c.rs);
     else { acc_cols_to_operand(c, T::DZ, 80, 96, dyx, c.rs); acc_cols_to_operand(c, T::DV, 0, 48, vb, c.rs); }
-    cta_sync_for_mma();
+    wk_sync_for_mma();
     MMRCA_STAMP(11);
     // ---- P11: gradients of the block inputs (read back next), then the parameter gradients (persistent, G3) ------
     if (tid == 0) {
@@ -647,14 +664,16 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
       acc_cols_to_operand(c, T::DXKV, 48 * c.w, 48 * c.w + 48, gk, c.rs);
     }
     first = false;
+    ++ntiles;
     MMRCA_STAMP(13);
     tc_fence_before_sync();
-    __syncthreads();
+    wk_sync();
     tc_fence_after_sync();
   }
   MMRCA_STAMP(0);
   // ---- flush the persistent accumulators ---------------------------------------------------------------------------
   if (!first) {
+    ph_g3 = uint32_t(ntiles - 1) & 1u;
     mbar_wait_ph(&bars[4], ph_g3);
     flush_acc(c, T::G_M, C::DIN, C::DIN + 1, [&](int m, int n) { return D.gm + size_t(n) * 128 + m; });
     flush_acc(c, T::G_WV, C::DV, C::DIN + 1,
@@ -682,10 +701,11 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_bwd_kernel(const CaBwdArgs 
       else if (c.rp < 2 * C::DV) atomicAdd(D.g_ln_b + (c.rp - C::DV), v[0]);
     }
   }
-  __syncthreads();
+  wk_sync();
   MMRCA_STAMP(1);
   MMRCA_STAMP_NS(251);
   if (a.dbg && tid == 0) a.dbg[301 + 2 * (blockIdx.x + gridDim.x * blockIdx.y)] = globaltimer_ns();
+  }   // workers
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
@@ -990,8 +1010,9 @@ struct FinBlock {
   int din, dkq;
 };
 struct FinArgs { FinBlock blk[4]; int nblk; };
-constexpr int kFinRows = 2;                                         // rows n of W_query / W_key per CTA
+constexpr int kFinRows = 1;                                         // rows n of W_query / W_key per CTA
 constexpr uint32_t kFinSmemBytes = (96 * 98 + 2 * kFinRows * 96 + kFinRows) * 4;
+static_assert(kFinRows == 1, "finalize_kernel's thread mapping assumes one row per CTA");
 
 // grid.x = sum over blocks of d_kq / 8.  CTA = (block, 8 rows n): dM (d_in x (d_in + 1), du in the last column) and the
 // 8 rows of W_query / W_key are staged in shared memory with every load in flight at once, then each thread owns
@@ -1043,23 +1064,28 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
   if (tid < kFinRows) bq_s[tid] = __ldg(B.bq + n0 + tid);
   __syncthreads();
   const float s = rsqrtf(float(B.dkq));
-  for (int o = tid; o < kFinRows * din; o += 256) {
-    const int nl = o / din, k = o - nl * din;
-    float q0 = 0.f, q1 = 0.f, k0 = bq_s[nl] * g_s[k * gs + din], k1 = 0.f;
+  // two threads per output column k (each half of the contraction), the last warp takes db_query
+  if (tid < 2 * din) {
+    const int k = tid >> 1, half = tid & 1, j0 = half * (din / 2), j1 = j0 + din / 2;
+    float q0 = 0.f, q1 = 0.f, k0 = half ? 0.f : bq_s[0] * g_s[k * gs + din], k1 = 0.f;
 #pragma unroll 4
-    for (int j = 0; j < din; j += 2) {
-      q0 = fmaf(g_s[j * gs + k], wk_s[nl * din + j], q0);
-      q1 = fmaf(g_s[(j + 1) * gs + k], wk_s[nl * din + j + 1], q1);
-      k0 = fmaf(wq_s[nl * din + j], g_s[k * gs + j], k0);
-      k1 = fmaf(wq_s[nl * din + j + 1], g_s[k * gs + j + 1], k1);
+    for (int j = j0; j < j1; j += 2) {
+      q0 = fmaf(g_s[j * gs + k], wk_s[j], q0);
+      q1 = fmaf(g_s[(j + 1) * gs + k], wk_s[j + 1], q1);
+      k0 = fmaf(wq_s[j], g_s[k * gs + j], k0);
+      k1 = fmaf(wq_s[j + 1], g_s[k * gs + j + 1], k1);
     }
-    B.g_wq[size_t(n0) * din + o] += (q0 + q1) * s;
-    B.g_wk[size_t(n0) * din + o] += (k0 + k1) * s;
-  }
-  if (tid < kFinRows) {
+    float q = q0 + q1, kk = k0 + k1;
+    q += __shfl_xor_sync(0xffffffffu, q, 1);
+    kk += __shfl_xor_sync(0xffffffffu, kk, 1);
+    if (half == 0) B.g_wq[size_t(n0) * din + k] += q * s;
+    else B.g_wk[size_t(n0) * din + k] += kk * s;
+  } else if (tid >= 224) {
+    const int lane = tid & 31;
     float acc = 0.f;
-    for (int j = 0; j < din; ++j) acc = fmaf(g_s[j * gs + din], wk_s[tid * din + j], acc);
-    B.g_bq[n0 + tid] += acc * s;
+    for (int j = lane; j < din; j += 32) acc = fmaf(g_s[j * gs + din], wk_s[j], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) B.g_bq[n0] += acc * s;
   }
 }
 
