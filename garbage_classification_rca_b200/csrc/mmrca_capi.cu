@@ -19,7 +19,7 @@ namespace mmrca {
 static thread_local char g_err[512] = "";
 static thread_local int g_launches = 0;
 static long long* g_dbg = nullptr;
-static int g_dbg_kernel = 0;         // 0: sa_bwd, 1: ca_bwd   // development: device buffer for per-phase clock stamps (mmrca_dev_set_debug)
+static int g_dbg_kernel = 0;         // 0: sa_bwd, 1: ca_bwd, 2: ca_fwd   // development: device buffer for per-phase clock stamps (mmrca_dev_set_debug)
 
 // ---- optional per-kernel timing (mmrca_timing_begin / _end) -------------------------------------
 struct TimingRec { const char* name; cudaEvent_t e0, e1; };
@@ -418,6 +418,7 @@ static int head_forward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, 
     a.t_tiles = w.t_img; a.i_tiles = w.i_img;
     a.logits = logits; a.batch = d.batch; a.reverse = (d.flags & MMRCA_FLAG_REVERSE) ? 1 : 0;
     a.drop = make_drop(d);
+    a.dbg = g_dbg_kernel == 2 ? g_dbg : nullptr;
     if ((rc = set_smem(htc::ca_fwd_kernel, htc::CaFwdLayout::BYTES))) return rc;
     LaunchScope ls("ca_fwd_bf16", st);
     htc::ca_fwd_kernel<<<grid, htc::kCtaThreads, htc::CaFwdLayout::BYTES, st>>>(a);

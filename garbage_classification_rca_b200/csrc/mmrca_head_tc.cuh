@@ -387,16 +387,18 @@ __device__ __forceinline__ void cls_readback(const WgCtx& c, uint32_t col, float
 #pragma unroll
   for (int qq = 0; qq < 4; ++qq) tmem_ld16_nw(c.tmem + c.lane_base + col + 16 * qq, v[qq]);
   tmem_wait_ld();
+  // my row's four columns (r, 0..3) = column 4r + cc of the 64: picked with bit masks (a chain of ?: on lane-dependent
+  // conditions compiles to divergent branches, a thousand cycles of reconvergence per tile)
   const int r = c.rp & 15, grp = r >> 2, m = r & 3;
-  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  const uint32_t g0 = grp == 0 ? ~0u : 0u, g1 = grp == 1 ? ~0u : 0u, g2 = grp == 2 ? ~0u : 0u, g3 = grp == 3 ? ~0u : 0u;
+  const uint32_t m0 = m == 0 ? ~0u : 0u, m1 = m == 1 ? ~0u : 0u, m2 = m == 2 ? ~0u : 0u, m3 = m == 3 ? ~0u : 0u;
+  uint32_t g[16];
 #pragma unroll
-  for (int qq = 0; qq < 4; ++qq) {
+  for (int e = 0; e < 16; ++e) g[e] = (v[0][e] & g0) | (v[1][e] & g1) | (v[2][e] & g2) | (v[3][e] & g3);
+  float s[4];
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      const uint32_t x = m == 0 ? v[qq][cc] : m == 1 ? v[qq][4 + cc] : m == 2 ? v[qq][8 + cc] : v[qq][12 + cc];
-      if (grp == qq) s[cc] = __uint_as_float(x);
-    }
-  }
+  for (int cc = 0; cc < 4; ++cc)
+    s[cc] = __uint_as_float((g[cc] & m0) | (g[4 + cc] & m1) | (g[8 + cc] & m2) | (g[12 + cc] & m3));
 #pragma unroll
   for (int cc = 0; cc < 4; ++cc) {
 #pragma unroll
@@ -404,7 +406,7 @@ __device__ __forceinline__ void cls_readback(const WgCtx& c, uint32_t col, float
   }
   if (r == 0 && valid) {
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) atomicAdd(logits + size_t(b) * kClasses + cc, s[cc]);
+    for (int cc = 0; cc < 4; ++cc) red_add(logits + size_t(b) * kClasses + cc, s[cc]);
   }
 }
 
@@ -667,6 +669,7 @@ struct CaFwdArgs {
   float* logits;
   DropSpec drop;            // concat columns of direction d: [d * 768, d * 768 + 768)
   int batch, reverse;
+  long long* dbg;           // development: per-phase clock64 stamps of warpgroup 0 of CTA 0 (null in production)
 };
 struct CaFwdSmem {
   static constexpr uint32_t XQ = 0;                                   // [128 x 112]; Z, P, Out reuse its first 96 columns
@@ -703,8 +706,10 @@ __device__ __forceinline__ void ca_issue_q(const CaFwdArgs& a, int d, int tile, 
 }
 
 __device__ __forceinline__ void ca_fwd_tile(WgCtx& c, const CaFwdArgs& a, int d, uint8_t* wsm, uint8_t* bsm,
-                                            const float* ln_s, uint64_t* bar_ld, uint32_t& ph_ld, int tile, int next_tile) {
+                                            const float* ln_s, uint64_t* bar_ld, uint32_t& ph_ld, int tile, int next_tile, int stamp_n) {
   using C = CaCfg;
+#define FSTAMP(i) do { if (a.dbg && c.wt == 0 && c.wg == 0 && blockIdx.x == 0 && stamp_n + (i) < 250) a.dbg[stamp_n + (i)] = clock64(); } while (0)
+  FSTAMP(0);
   const int b0 = tile * 8;
   uint8_t* xq = bsm + CaFwdSmem::XQ;
   uint8_t* xkv = bsm + CaFwdSmem::XKV;
@@ -715,6 +720,7 @@ __device__ __forceinline__ void ca_fwd_tile(WgCtx& c, const CaFwdArgs& a, int d,
   mbar_wait(bar_ld, ph_ld);
   ph_ld ^= 1;
   wg_sync_for_mma(c);
+  FSTAMP(1);
   if (c.wt == 0) {
     mma_steps(c.tmem + C::COL_Z, make_smem_desc(smem_u32(xq), kCS, kRS), 2 * kCS,
               make_smem_desc(smem_u32(wsm), C::BZ_LBO, 128), 2 * C::BZ_LBO, make_idesc_bf16(128, C::DIN, 0, 0),
@@ -725,9 +731,11 @@ __device__ __forceinline__ void ca_fwd_tile(WgCtx& c, const CaFwdArgs& a, int d,
     umma_commit(c.bar);
   }
   wg_wait_mma(c);
+  FSTAMP(2);
   acc_to_operand<C::DIN>(c, C::COL_Z, xq);      // Z overwrites the query image (its projection is done)
   acc_to_operand<C::DV>(c, C::COL_V, vop);
   wg_sync_for_mma(c);
+  FSTAMP(3);
   if (c.wt == 0) {
 #pragma unroll
     for (int h = 0; h < 2; ++h)
@@ -737,6 +745,7 @@ __device__ __forceinline__ void ca_fwd_tile(WgCtx& c, const CaFwdArgs& a, int d,
     umma_commit(c.bar);
   }
   wg_wait_mma(c);
+  FSTAMP(4);
   // the key/value image is dead (V and the scores have read it): the next tile's lands while this one finishes
   if (c.wt == 0 && next_tile >= 0) {
     ca_issue_kv(a, d ^ 1, next_tile, xkv, bar_ld);
@@ -751,6 +760,7 @@ __device__ __forceinline__ void ca_fwd_tile(WgCtx& c, const CaFwdArgs& a, int d,
     store_p_row(c, xq, p, true);
   }
   wg_sync_for_mma(c);
+  FSTAMP(5);
   if (c.wt == 0) {
 #pragma unroll
     for (int h = 0; h < 2; ++h)
@@ -760,6 +770,7 @@ __device__ __forceinline__ void ca_fwd_tile(WgCtx& c, const CaFwdArgs& a, int d,
     umma_commit(c.bar);
   }
   wg_wait_mma(c);
+  FSTAMP(6);
   // ---- LayerNorm + ReLU (:105-106) -> classifier operand ------------------------------------------------------
   {
     float mean, rstd;
@@ -789,6 +800,7 @@ __device__ __forceinline__ void ca_fwd_tile(WgCtx& c, const CaFwdArgs& a, int d,
     }
   }
   wg_sync_for_mma(c);
+  FSTAMP(7);
   if (c.wt == 0) {
     mma_steps(c.tmem + C::COL_CLS, make_smem_desc(smem_u32(xq), kCS, kRS), 2 * kCS,
               make_smem_desc(smem_u32(wsm + C::BZ_BYTES + C::BV_BYTES), C::BC_LBO, 128), 2 * C::BC_LBO,
@@ -796,11 +808,15 @@ __device__ __forceinline__ void ca_fwd_tile(WgCtx& c, const CaFwdArgs& a, int d,
     umma_commit(c.bar);
   }
   wg_wait_mma(c);
+  FSTAMP(8);
   if (c.wt == 0 && next_tile >= 0) ca_issue_q(a, d ^ 1, next_tile, xq, bar_ld);      // the classifier has read Out: xq is free
   cls_readback(c, C::COL_CLS, a.logits, b0 + (c.rp >> 4), b0 + (c.rp >> 4) < a.batch);
+  FSTAMP(9);
   tc_fence_before_sync();
   named_bar_sync(1 + c.wg, kWgThreads);
   tc_fence_after_sync();
+  FSTAMP(10);
+#undef FSTAMP
 }
 
 __global__ void __launch_bounds__(kCtaThreads, 1) ca_fwd_kernel(const CaFwdArgs a) {
@@ -841,7 +857,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_fwd_kernel(const CaFwdArgs 
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++round) {
     const int d = (wg + round) & 1;
     ca_fwd_tile(c, a, d, sm + (d == 0 ? L::W0 : L::W1), bsm, ln_s + d * 96, &bars[3 + wg], ph_ld, tile,
-                tile + int(gridDim.x) < tiles ? tile + int(gridDim.x) : -1);
+                tile + int(gridDim.x) < tiles ? tile + int(gridDim.x) : -1, 1 + 12 * round);
   }
   tc_fence_before_sync();
   __syncthreads();

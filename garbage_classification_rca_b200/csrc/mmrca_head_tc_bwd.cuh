@@ -111,8 +111,8 @@ __global__ void __launch_bounds__(256) ce_feat_kernel(const CeFeatArgs a) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) d[c] = warp_sum(d[c]);
       if (lane == 0) {
-        if (ce && a.loss) atomicAdd(a.loss, li);
-        if (a.g_bf) { for (int c = 0; c < 4; ++c) atomicAdd(a.g_bf + c, d[c]); }
+        if (ce && a.loss) red_add(a.loss, li);
+        if (a.g_bf) { for (int c = 0; c < 4; ++c) red_add(a.g_bf + c, d[c]); }
       }
     }
   }
@@ -167,10 +167,10 @@ __global__ void __launch_bounds__(256) ce_feat_kernel(const CeFeatArgs a) {
       for (int e = 0; e < 4; ++e) v[e] += part[w][ch][c * 8 + e0 + e];
     float* dst = a.g_wf + size_t(c) * a.drop.D + (is_img ? a.off_img : a.off_txt) + ch * din + kc * 8 + e0;
     if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-      atomicAdd(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+      red_add4(dst, make_float4(v[0], v[1], v[2], v[3]));
     } else {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) atomicAdd(dst + e, v[e]);
+      for (int e = 0; e < 4; ++e) red_add(dst + e, v[e]);
     }
   }
 }
@@ -350,7 +350,7 @@ __device__ __forceinline__ void flush_acc(const BwCtx& c, uint32_t col, int ncol
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         float* p = dst(m, n0 + e);
-        if (p) atomicAdd(p, v[e]);
+        if (p) red_add(p, v[e]);
       }
     }
   }
@@ -689,7 +689,7 @@ __global__ void __launch_bounds__(kCaBwdThreads, 1) ca_bwd_kernel(const CaBwdArg
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
             const int n = n0 + e, rp = n >> 2, cls = n & 3;
-            atomicAdd(D.g_wf + size_t(cls) * a.D + rp * C::DV + j, v[e]);
+            red_add(D.g_wf + size_t(cls) * a.D + rp * C::DV + j, v[e]);
           }
         }
       }
@@ -697,8 +697,8 @@ __global__ void __launch_bounds__(kCaBwdThreads, 1) ca_bwd_kernel(const CaBwdArg
     if (c.w == 0) {
       float v[16];
       ld16f(c.tmem + c.lane_base + T::G_LN, v);
-      if (c.rp < C::DV) atomicAdd(D.g_ln_g + c.rp, v[0]);
-      else if (c.rp < 2 * C::DV) atomicAdd(D.g_ln_b + (c.rp - C::DV), v[0]);
+      if (c.rp < C::DV) red_add(D.g_ln_g + c.rp, v[0]);
+      else if (c.rp < 2 * C::DV) red_add(D.g_ln_b + (c.rp - C::DV), v[0]);
     }
   }
   wk_sync();
@@ -976,8 +976,8 @@ __device__ __forceinline__ void sa_bwd_body(const SaBwdArgs& a, uint8_t* sm) {
       float v[16];
       ld16f(c.tmem + c.lane_base + T::G_LN + 16 * c.w, v);
       const int col = 128 * c.w + c.rp;             // row of the [dy*xhat | dy]^T 1 product
-      if (col < DV) atomicAdd(a.g_ln_g + col, v[0]);
-      else if (col < 2 * DV) atomicAdd(a.g_ln_b + (col - DV), v[0]);
+      if (col < DV) red_add(a.g_ln_g + col, v[0]);
+      else if (col < 2 * DV) red_add(a.g_ln_b + (col - DV), v[0]);
     }
   }
   __syncthreads();

@@ -134,6 +134,17 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
+// fire-and-forget global reductions.  atomicAdd() on a pointer whose address space the compiler cannot prove compiles
+// to a generic ATOM with a predicate result and compare-and-swap fallbacks: the thread waits a full L2 round trip for
+// every one of them.  red.global returns nothing and is not waited for.
+__device__ __forceinline__ void red_add(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_add4(float* p16, const float4 v) {      // p16: 16-byte aligned
+  asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(__cvta_generic_to_global(p16)), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
 // bulk prefetch of [p, p + bytes) into the L2 (bytes % 16 == 0): no shared memory, no completion to wait for
 __device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
