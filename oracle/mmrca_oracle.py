@@ -381,3 +381,64 @@ def np_head_forward_backward(p, img_feat, txt_feat, reverse=True, features_only=
     out["d_img"] = (d_img_n - img_n * (img_n * d_img_n).sum(axis=1, keepdims=True)) / n_i
     out["d_txt"] = (d_txt_n - txt_n * (txt_n * d_txt_n).sum(axis=1, keepdims=True)) / n_t
     return out
+
+
+# =====================================================================================================
+# Hierarchical late-fusion head (reference multimodal_model.py:729-818, the second --late_fusion value)
+# =====================================================================================================
+HIER_IMG_SEGMENTS = (1280, 2560, 2048)     # pooled, AvgPool(7) of the 160-channel stage, AvgPool(6) of the 512-channel stage
+HIER_TXT_SEGMENTS = (768, 768, 768)        # CLS of the last layer, of hidden_states[2], of hidden_states[4]
+HIER_D_IMG, HIER_D_TXT, HIER_HIDDEN = sum(HIER_IMG_SEGMENTS), sum(HIER_TXT_SEGMENTS), 512
+HIER_PARAM_NAMES = ("final_hierarchical_image.weight", "final_hierarchical_image.bias",
+                    "final_hierarchical_text.weight", "final_hierarchical_text.bias",
+                    "final_hierarchical_all.weight", "final_hierarchical_all.bias")
+
+
+def init_hier_params(n_classes: int = 4, seed: int = 0, dtype=torch.float32) -> Dict[str, torch.Tensor]:
+    """Random parameters of the three Linear layers of the hierarchical head (multimodal_model.py:294-296),
+    torch.nn.Linear-like scale, a pure function of the seed (the 12 MB weight is never stored in a fixture)."""
+    g = torch.Generator().manual_seed(10_000 + seed)
+
+    def lin(out_f, in_f):
+        k = 1.0 / math.sqrt(in_f)
+        w = (torch.rand(out_f, in_f, generator=g, dtype=torch.float64) * 2 - 1) * k
+        b = (torch.rand(out_f, generator=g, dtype=torch.float64) * 2 - 1) * k
+        return w.to(dtype), b.to(dtype)
+
+    p: Dict[str, torch.Tensor] = {}
+    p["final_hierarchical_image.weight"], p["final_hierarchical_image.bias"] = lin(HIER_HIDDEN, HIER_D_IMG)
+    p["final_hierarchical_text.weight"], p["final_hierarchical_text.bias"] = lin(HIER_HIDDEN, HIER_D_TXT)
+    p["final_hierarchical_all.weight"], p["final_hierarchical_all.bias"] = lin(n_classes, 2 * HIER_HIDDEN)
+    return p
+
+
+def hier_forward(p: Dict[str, torch.Tensor], img_segments, txt_segments,
+                 drop_mask: Optional[torch.Tensor] = None, drop_scale: float = 1.0) -> torch.Tensor:
+    """Hierarchical.forward after the backbones and the two AvgPool2d (multimodal_model.py:777-816).
+
+    img_segments: (pooled [B,1280], stage-3 pooled+flattened [B,2560], stage-6 pooled+flattened [B,2048]);
+    txt_segments: (CLS last layer, CLS hidden_states[2], CLS hidden_states[4]), each [B,768].
+    drop_mask: keep-mask [B, 5888 + 2304] (image concat columns first) of the two self.drop calls (:805-806)."""
+    img = torch.cat([l2_normalise(s) for s in img_segments], dim=1)        # :777-782, :791-796 (order: pooled, s3, s6)
+    txt = torch.cat([l2_normalise(s) for s in txt_segments], dim=1)        # :784-789, :798-803
+    if drop_mask is not None:
+        m = drop_mask.to(img.dtype)
+        img = img * m[:, :HIER_D_IMG] * drop_scale                         # :805
+        txt = txt * m[:, HIER_D_IMG:] * drop_scale                         # :806
+    h_img = torch.relu(img @ p["final_hierarchical_image.weight"].T + p["final_hierarchical_image.bias"])   # :808, :811
+    h_txt = torch.relu(txt @ p["final_hierarchical_text.weight"].T + p["final_hierarchical_text.bias"])     # :809, :812
+    return torch.cat((h_img, h_txt), dim=1) @ p["final_hierarchical_all.weight"].T + p["final_hierarchical_all.bias"]   # :814-816
+
+
+def hier_loss_and_grads(p: Dict[str, torch.Tensor], img_segments, txt_segments, labels: torch.Tensor,
+                        class_weight: Optional[torch.Tensor] = None, label_smoothing: float = 0.0,
+                        drop_mask: Optional[torch.Tensor] = None, drop_scale: float = 1.0, dtype=torch.float64):
+    """forward + CrossEntropyLoss + backward (main_both.py:106-112) of the hierarchical head through autograd,
+    in float64 by default.  Returns (logits, loss, grads{name: tensor})."""
+    pp = {k: v.detach().to(dtype).clone().requires_grad_(True) for k, v in p.items() if k in HIER_PARAM_NAMES}
+    logits = hier_forward(pp, [s.detach().to(dtype) for s in img_segments], [s.detach().to(dtype) for s in txt_segments],
+                          drop_mask, drop_scale)
+    cw = None if class_weight is None else class_weight.to(dtype)
+    loss = cross_entropy(logits, labels, cw, label_smoothing)
+    loss.backward()
+    return logits.detach(), loss.detach(), {k: v.grad for k, v in pp.items()}
