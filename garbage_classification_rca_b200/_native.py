@@ -26,7 +26,7 @@ FLAG_FEATURE_GRADS = 256
 COMPUTE_FP32, COMPUTE_BF16, COMPUTE_BF16_FUSED = 0, 1, 2
 WS_TEXT_SA_IMAGE, WS_IMAGE_SA_IMAGE = 0, 1
 QUERY_ABI_VERSION, QUERY_DEVICE_OK, QUERY_SM_COUNT, QUERY_KERNEL_LAUNCHES, QUERY_RESET_LAUNCHES, QUERY_HAS_BF16 = range(6)
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _fp = C.c_void_p  # device pointers travel as integers
 
@@ -49,6 +49,15 @@ class KernelTime(C.Structure):
     _fields_ = [("name", C.c_char_p), ("ms", C.c_float)]
 
 
+class HierParams(C.Structure):
+    """MmrcaHierParams / MmrcaHierGrads (same layout)."""
+    _fields_ = [(n, _fp) for n in ("w_img", "b_img", "w_txt", "b_txt", "w_all", "b_all")]
+
+
+class HierDesc(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("n_classes", C.c_int32), ("drop_p", C.c_float), ("drop_seed", C.c_uint64)]
+
+
 class CeDesc(C.Structure):
     _fields_ = [("class_weight", _fp), ("label_smoothing", C.c_float)]
 
@@ -57,7 +66,8 @@ EXPORTS = ("mmrca_query", "mmrca_last_error", "mmrca_head_workspace_bytes", "mmr
            "mmrca_head_backward", "mmrca_cross_entropy", "mmrca_head_train_step", "mmrca_attention_forward",
            "mmrca_attention_backward_scratch_bytes", "mmrca_attention_backward", "mmrca_timing_begin",
            "mmrca_timing_end", "mmrca_dev_umma_selftest", "mmrca_attention_forward_scratch_bytes",
-           "mmrca_head_workspace_offset", "mmrca_dropout_mask", "mmrca_dev_set_debug")
+           "mmrca_head_workspace_offset", "mmrca_dropout_mask", "mmrca_dev_set_debug",
+           "mmrca_hier_workspace_bytes", "mmrca_hier_forward", "mmrca_hier_backward", "mmrca_hier_train_step")
 
 
 def _sources_newer_than_lib() -> bool:
@@ -146,6 +156,18 @@ def lib() -> C.CDLL:
         L.mmrca_dropout_mask.restype = C.c_int
         L.mmrca_dev_set_debug.argtypes = [_fp, C.c_int32]
         L.mmrca_dev_set_debug.restype = C.c_int
+        L.mmrca_hier_workspace_bytes.argtypes = [C.POINTER(HierDesc)]
+        L.mmrca_hier_workspace_bytes.restype = C.c_size_t
+        L.mmrca_hier_forward.argtypes = [C.POINTER(HierDesc), C.POINTER(HierParams), C.POINTER(_fp), _fp, C.c_float,
+                                         _fp, _fp, C.c_size_t, _fp]
+        L.mmrca_hier_forward.restype = C.c_int
+        L.mmrca_hier_backward.argtypes = [C.POINTER(HierDesc), C.POINTER(HierParams), _fp, C.POINTER(HierParams),
+                                          _fp, C.c_size_t, _fp]
+        L.mmrca_hier_backward.restype = C.c_int
+        L.mmrca_hier_train_step.argtypes = [C.POINTER(HierDesc), C.POINTER(HierParams), C.POINTER(_fp), _fp,
+                                            C.c_float, _fp, C.POINTER(CeDesc), _fp, _fp, C.POINTER(HierParams),
+                                            _fp, C.c_size_t, _fp]
+        L.mmrca_hier_train_step.restype = C.c_int
         if L.mmrca_query(QUERY_ABI_VERSION) != ABI_VERSION:
             raise RuntimeError("libmmrca.so ABI version mismatch: rebuild it")
         _lib = L

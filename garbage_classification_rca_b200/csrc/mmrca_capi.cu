@@ -13,6 +13,7 @@
 #include "mmrca_tc_selftest.cuh"
 #include "mmrca_head_tc.cuh"
 #include "mmrca_head_tc_bwd.cuh"
+#include "mmrca_hier.cuh"
 
 namespace mmrca {
 
@@ -654,6 +655,116 @@ static int launch_ce(const float* logits, const int64_t* labels, const MmrcaCeDe
   return MMRCA_OK;
 }
 
+// ---- hierarchical head ----------------------------------------------------------------------------------------------
+struct HierWorkspace {
+  void* x_img; void* x_txt; void* wb_img; void* wb_txt; void* h; void* dh; float* dlogits;
+  size_t bytes;
+};
+static HierWorkspace hier_carve(int batch, void* base) {
+  HierWorkspace w;
+  memset(&w, 0, sizeof(w));
+  const size_t tiles = size_t(batch + hier::kTile - 1) / hier::kTile;
+  char* p = static_cast<char*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { void* r = p ? p + off : nullptr; off += align_up_256(bytes); return r; };
+  w.x_img = take(tiles * hier::kGImg * hier::kGrpBytes);
+  w.x_txt = take(tiles * hier::kGTxt * hier::kGrpBytes);
+  w.wb_img = take(size_t(hier::kGImg) * hier::kHid * 16);
+  w.wb_txt = take(size_t(hier::kGTxt) * hier::kHid * 16);
+  w.h = take(tiles * hier::kTile * (2 * hier::kHid) * 2);
+  w.dh = take(tiles * hier::kGHid * hier::kGrpBytes);
+  w.dlogits = static_cast<float*>(take(tiles * hier::kTile * hier::kClasses * sizeof(float)));
+  w.bytes = off;
+  return w;
+}
+static int hier_check(const MmrcaHierDesc* d) {
+  if (!d) return fail(MMRCA_ERR_INVALID, "null descriptor%s%s");
+  if (d->batch < 0) return fail(MMRCA_ERR_INVALID, "batch must be >= 0%s%s");
+  if (d->n_classes != hier::kClasses) return fail(MMRCA_ERR_INVALID, "the hierarchical head is built for 4 classes%s%s");
+  if (!(d->drop_p >= 0.f && d->drop_p <= 1.f)) return fail(MMRCA_ERR_INVALID, "drop_p must be in [0, 1]%s%s");
+  return MMRCA_OK;
+}
+static DropSpec hier_drop(const MmrcaHierDesc& d) {
+  DropSpec s;
+  memset(&s, 0, sizeof(s));
+  s.D = hier::kD;
+  s.scale = 1.0f;
+  if (d.drop_p > 0.f) {
+    const float p = d.drop_p < 1.f ? d.drop_p : 1.f;
+    s.seed_lo = uint32_t(d.drop_seed & 0xffffffffu);
+    s.seed_hi = uint32_t(d.drop_seed >> 32);
+    s.thresh = uint32_t(p * 65536.0f + 0.5f);
+    s.scale = p < 1.f ? 1.0f / (1.0f - p) : 0.f;
+  }
+  return s;
+}
+static int hier_forward_impl(const MmrcaHierDesc& d, const MmrcaHierParams& p, const float* const* feats,
+                             const uint8_t* mask, float scale, float* logits, const HierWorkspace& w, cudaStream_t st) {
+  if (d.batch == 0) return MMRCA_OK;
+  int rc;
+  for (int i = 0; i < 6; ++i)
+    if (!feats[i] || (reinterpret_cast<uintptr_t>(feats[i]) & 15))
+      return fail(MMRCA_ERR_INVALID, "the six feature pointers must be non-null and 16-byte aligned%s%s");
+  const int tiles = (d.batch + hier::kTile - 1) / hier::kTile;
+  {
+    hier::PrepArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < 6; ++i) a.seg[i] = feats[i];
+    a.x_img = w.x_img; a.x_txt = w.x_txt; a.mask = mask; a.mask_scale = scale; a.drop = hier_drop(d);
+    a.logits = logits; a.b_all = p.b_all; a.batch = d.batch;
+    LaunchScope ls("hier_prep", st);
+    hier::hier_prep_kernel<<<tiles * hier::kTile, 256, 0, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  {
+    hier::WPrepArgs a;
+    a.w[0] = p.w_img; a.w[1] = p.w_txt; a.blob[0] = w.wb_img; a.blob[1] = w.wb_txt;
+    LaunchScope ls("hier_wprep", st);
+    hier::hier_wprep_kernel<<<dim3(hier::kGImg * hier::kHid / 256, 2), 256, 0, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  {
+    hier::GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x[0] = w.x_img; a.x[1] = w.x_txt; a.wb[0] = w.wb_img; a.wb[1] = w.wb_txt; a.bias[0] = p.b_img; a.bias[1] = p.b_txt;
+    a.w_all = p.w_all; a.logits = logits; a.h = w.h; a.batch = d.batch;
+    if ((rc = set_smem(hier::hier_gemm_kernel, hier::FwdSmem::BYTES))) return rc;
+    LaunchScope ls("hier_gemm", st);
+    hier::hier_gemm_kernel<<<dim3(tiles, hier::kHid / hier::kBN, 2), hier::kGemmThreads, hier::FwdSmem::BYTES, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+static int hier_backward_impl(const MmrcaHierDesc& d, const MmrcaHierParams& p, const float* dlogits,
+                              const MmrcaHierGrads& g, const HierWorkspace& w, cudaStream_t st) {
+  if (d.batch == 0) return MMRCA_OK;
+  int rc;
+  if (!g.w_img || !g.w_txt || !g.b_img || !g.b_txt)
+    return fail(MMRCA_ERR_INVALID, "the hidden-layer gradient buffers must be given%s%s");
+  if ((reinterpret_cast<uintptr_t>(g.w_img) | reinterpret_cast<uintptr_t>(g.w_txt)) & 15)
+    return fail(MMRCA_ERR_INVALID, "weight-gradient buffers must be 16-byte aligned%s%s");
+  const int tiles = (d.batch + hier::kTile - 1) / hier::kTile;
+  {
+    hier::DhArgs a;
+    memset(&a, 0, sizeof(a));
+    a.h = w.h; a.dlogits = dlogits; a.w_all = p.w_all; a.dh = w.dh; a.g_w_all = g.w_all; a.g_b_all = g.b_all;
+    a.g_b_hid[0] = g.b_img; a.g_b_hid[1] = g.b_txt; a.batch = d.batch;
+    LaunchScope ls("hier_dh", st);
+    hier::hier_dh_kernel<<<dim3(tiles, hier::kGHid / 16), 256, 0, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  {
+    hier::WgradArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dh = w.dh; a.x[0] = w.x_img; a.x[1] = w.x_txt; a.g_w[0] = g.w_img; a.g_w[1] = g.w_txt; a.tiles = tiles;
+    if ((rc = set_smem(hier::hier_wgrad_kernel, hier::WgSmem::BYTES))) return rc;
+    LaunchScope ls("hier_wgrad", st);
+    hier::hier_wgrad_kernel<<<hier::kWgCtasImg + hier::kWgCtasTxt, hier::kGemmThreads, hier::WgSmem::BYTES, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+
 }  // namespace mmrca
 
 using namespace mmrca;
@@ -794,6 +905,55 @@ int mmrca_head_train_step(const MmrcaHeadDesc* desc, const MmrcaHeadParams* para
   if ((rc = launch_ce(logits, labels, ce, desc->batch, desc->n_classes, loss_out, w.dlogits, st))) return rc;
   return head_backward_impl(*desc, *params, img_feat, txt_feat, drop_mask, drop_scale, w.dlogits, *grads, d_img_feat,
                             d_txt_feat, w, di.sms, st);
+}
+
+size_t mmrca_hier_workspace_bytes(const MmrcaHierDesc* desc) {
+  if (hier_check(desc)) return 0;
+  return hier_carve(desc->batch, nullptr).bytes;
+}
+
+int mmrca_hier_forward(const MmrcaHierDesc* desc, const MmrcaHierParams* params, const float* const* feats,
+                       const uint8_t* drop_mask, float drop_scale, float* logits, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  int rc;
+  if ((rc = hier_check(desc))) return rc;
+  if (!params || !feats || !logits || !workspace) return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
+  DeviceInfo di;
+  if ((rc = device_info(&di))) return rc;
+  const HierWorkspace w = hier_carve(desc->batch, workspace);
+  if (workspace_bytes < w.bytes) return fail(MMRCA_ERR_WORKSPACE, "workspace too small%s%s");
+  return hier_forward_impl(*desc, *params, feats, drop_mask, drop_scale, logits, w, static_cast<cudaStream_t>(stream));
+}
+
+int mmrca_hier_backward(const MmrcaHierDesc* desc, const MmrcaHierParams* params, const float* dlogits,
+                        const MmrcaHierGrads* grads, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc;
+  if ((rc = hier_check(desc))) return rc;
+  if (!params || !dlogits || !grads || !workspace) return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
+  DeviceInfo di;
+  if ((rc = device_info(&di))) return rc;
+  const HierWorkspace w = hier_carve(desc->batch, workspace);
+  if (workspace_bytes < w.bytes) return fail(MMRCA_ERR_WORKSPACE, "workspace too small%s%s");
+  return hier_backward_impl(*desc, *params, dlogits, *grads, w, static_cast<cudaStream_t>(stream));
+}
+
+int mmrca_hier_train_step(const MmrcaHierDesc* desc, const MmrcaHierParams* params, const float* const* feats,
+                          const uint8_t* drop_mask, float drop_scale, const int64_t* labels, const MmrcaCeDesc* ce,
+                          float* logits, float* loss_out, const MmrcaHierGrads* grads, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  int rc;
+  if ((rc = hier_check(desc))) return rc;
+  if (!params || !feats || !labels || !logits || !loss_out || !grads || !workspace)
+    return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
+  DeviceInfo di;
+  if ((rc = device_info(&di))) return rc;
+  const HierWorkspace w = hier_carve(desc->batch, workspace);
+  if (workspace_bytes < w.bytes) return fail(MMRCA_ERR_WORKSPACE, "workspace too small%s%s");
+  if (desc->batch == 0) return MMRCA_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((rc = hier_forward_impl(*desc, *params, feats, drop_mask, drop_scale, logits, w, st))) return rc;
+  if ((rc = launch_ce(logits, labels, ce, desc->batch, desc->n_classes, loss_out, w.dlogits, st))) return rc;
+  return hier_backward_impl(*desc, *params, w.dlogits, *grads, w, st);
 }
 
 size_t mmrca_attention_forward_scratch_bytes(int32_t, int32_t, int32_t, int32_t) { return 0; }

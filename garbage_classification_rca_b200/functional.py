@@ -375,3 +375,121 @@ def attention_block(x_q: torch.Tensor, x_kv: Optional[torch.Tensor], params: Seq
     """params: (Wq, bq, Wk, bk, Wv, bv, ln_weight, ln_bias).  x_kv=None -> self attention."""
     is_self = x_kv is None or x_kv is x_q
     return _AttentionFunction.apply(x_q, x_q if is_self else x_kv, reverse, is_self, compute, *params)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Hierarchical late-fusion head (reference multimodal_model.py:729-818)
+# ---------------------------------------------------------------------------------------------------------
+HIER_PARAM_NAMES = ("final_hierarchical_image.weight", "final_hierarchical_image.bias",
+                    "final_hierarchical_text.weight", "final_hierarchical_text.bias",
+                    "final_hierarchical_all.weight", "final_hierarchical_all.bias")
+HIER_SEGMENTS = (1280, 2560, 2048, 768, 768, 768)      # pooled, stage 3, stage 6 | CLS last, layer 2, layer 4
+HIER_CONCAT = sum(HIER_SEGMENTS)                        # 8192: [image 5888 | text 2304], the dropout mask's columns
+
+
+def _hier_feats(feats: Sequence[torch.Tensor]):
+    if len(feats) != 6:
+        raise ValueError("the hierarchical head takes six feature tensors (3 image, 3 text)")
+    feats = [_check_dev(f.float(), "hierarchical feature") for f in feats]
+    B = feats[0].shape[0]
+    for f, w in zip(feats, HIER_SEGMENTS):
+        if f.shape != (B, w):
+            raise ValueError(f"hierarchical feature of shape {tuple(f.shape)}, expected ({B}, {w})")
+    arr = (N._fp * 6)(*[f.data_ptr() for f in feats])
+    return feats, arr, B
+
+
+def _hier_struct(tensors: Sequence[Optional[torch.Tensor]]) -> N.HierParams:
+    return N.HierParams(*[t.data_ptr() if t is not None else None for t in tensors])
+
+
+class _HierFunction(torch.autograd.Function):
+    """logits = hierarchical head(six pooled feature tensors); frozen backbones (no feature gradients)."""
+
+    @staticmethod
+    def forward(ctx, drop_mask, drop_scale, drop_p, drop_seed, f0, f1, f2, f3, f4, f5, *params):
+        feats, arr, B = _hier_feats((f0, f1, f2, f3, f4, f5))
+        params = [_check_dev(p, "hierarchical parameter") for p in params]
+        if drop_mask is not None:
+            drop_mask = _check_dev(drop_mask, "dropout mask", torch.uint8)
+            if drop_mask.shape != (B, HIER_CONCAT):
+                raise ValueError("hierarchical dropout mask must be [B, 8192]")
+        dev = feats[0].device
+        desc = N.HierDesc(B, params[4].shape[0], float(drop_p), int(drop_seed) & (2 ** 64 - 1))
+        L = N.lib()
+        ws = torch.empty(max(1, L.mmrca_hier_workspace_bytes(C.byref(desc))), dtype=torch.uint8, device=dev)
+        logits = torch.empty(B, params[4].shape[0], dtype=torch.float32, device=dev)
+        ctx.save_for_backward(ws, *params)
+        ctx.desc = desc
+        if B > 0:
+            with torch.cuda.device(dev):
+                N.check(L.mmrca_hier_forward(C.byref(desc), C.byref(_hier_struct(params)), arr,
+                                             drop_mask.data_ptr() if drop_mask is not None else None,
+                                             float(drop_scale), logits.data_ptr(), ws.data_ptr(), ws.numel(),
+                                             _stream_ptr(dev)), "mmrca_hier_forward")
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        ws, *params = ctx.saved_tensors
+        if any(ctx.needs_input_grad[4:10]):
+            raise RuntimeError("the hierarchical head is built for frozen backbones: no feature gradients")
+        dlogits = _check_dev(dlogits, "dlogits")
+        fg = FlatGrads(params)
+        if ctx.desc.batch > 0:
+            with torch.cuda.device(ws.device):
+                N.check(N.lib().mmrca_hier_backward(C.byref(ctx.desc), C.byref(_hier_struct(params)), dlogits.data_ptr(),
+                                                    C.byref(_hier_struct(fg.views)), ws.data_ptr(), ws.numel(),
+                                                    _stream_ptr(ws.device)), "mmrca_hier_backward")
+        return (None,) * 10 + tuple(v if ctx.needs_input_grad[10 + i] else None for i, v in enumerate(fg.views))
+
+
+def hierarchical_head(feats: Sequence[torch.Tensor], params: Sequence[torch.Tensor], *,
+                      drop_mask: Optional[torch.Tensor] = None, drop_scale: float = 1.0, drop_p: float = 0.0,
+                      drop_seed: int = 0) -> torch.Tensor:
+    """Hierarchical.forward after the backbones and the two AvgPool2d (reference multimodal_model.py:777-816).
+
+    feats: (pooled image [B,1280], stage-3 pooled+flattened [B,2560], stage-6 pooled+flattened [B,2048],
+            text CLS last layer, hidden_states[2], hidden_states[4] — [B,768] each);
+    params: the six tensors of HIER_PARAM_NAMES.  Dropout as in mmrca_head (seeded, or a caller mask [B, 8192])."""
+    if drop_mask is not None:
+        drop_p, drop_seed = 0.0, 0
+    return _HierFunction.apply(drop_mask, float(drop_scale), float(drop_p), int(drop_seed), *feats, *params)
+
+
+class HierTrainStep:
+    """One-call training step of the hierarchical head (forward + CrossEntropyLoss + backward, reference
+    main_both.py:106-112 restricted to the head); gradients accumulate into `grads.flat`."""
+
+    def __init__(self, params: Sequence[torch.Tensor], batch: int, *, class_weight: Optional[torch.Tensor] = None,
+                 label_smoothing: float = 0.0, drop_p: float = 0.0):
+        self.params = [_check_dev(p.detach(), "hierarchical parameter") for p in params]
+        dev = self.params[0].device
+        self.desc = N.HierDesc(batch, self.params[4].shape[0], float(drop_p), 0)
+        self.grads = FlatGrads(self.params)
+        self.hp, self.hg = _hier_struct(self.params), _hier_struct(self.grads.views)
+        self.ws = torch.empty(max(1, N.lib().mmrca_hier_workspace_bytes(C.byref(self.desc))), dtype=torch.uint8, device=dev)
+        self.logits = torch.empty(batch, self.params[4].shape[0], dtype=torch.float32, device=dev)
+        self.loss = torch.empty(1, dtype=torch.float32, device=dev)
+        self.cw = _check_dev(class_weight, "class weights") if class_weight is not None else None
+        self.ce = N.CeDesc(self.cw.data_ptr() if self.cw is not None else None, float(label_smoothing))
+        self.device = dev
+
+    def zero_grad(self):
+        self.grads.zero_()
+
+    def __call__(self, feats: Sequence[torch.Tensor], labels: torch.Tensor, drop_mask: Optional[torch.Tensor] = None,
+                 drop_scale: float = 1.0, drop_seed: int = 0):
+        self.desc.drop_seed = int(drop_seed) & (2 ** 64 - 1)
+        feats, arr, B = _hier_feats(feats)
+        if B != self.desc.batch:
+            raise ValueError("feature batch does not match the batch this step was built for")
+        labels = _check_dev(labels, "labels", torch.int64)
+        if drop_mask is not None:
+            drop_mask = _check_dev(drop_mask, "dropout mask", torch.uint8)
+        with torch.cuda.device(self.device):
+            N.check(N.lib().mmrca_hier_train_step(
+                C.byref(self.desc), C.byref(self.hp), arr, drop_mask.data_ptr() if drop_mask is not None else None,
+                float(drop_scale), labels.data_ptr(), C.byref(self.ce), self.logits.data_ptr(), self.loss.data_ptr(),
+                C.byref(self.hg), self.ws.data_ptr(), self.ws.numel(), _stream_ptr(self.device)), "mmrca_hier_train_step")
+        return self.loss, self.logits

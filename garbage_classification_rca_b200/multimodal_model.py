@@ -360,6 +360,45 @@ class MM_RCA(EffV2MediumAndDistilbertGated):
         return self.forward_features(image_features, text_features)
 
 
+class Hierarchical(EffV2MediumAndDistilbertGated):
+    """Hierarchical late fusion (reference :729-818, `--late_fusion=hierarchical`): multi-scale image features (pooled
+    vector + average-pooled 160- and 512-channel stage maps) and the CLS embeddings of three text layers, six L2
+    normalisations, two concats, dropout, Linear(5888 -> 512) / Linear(2304 -> 512) with ReLU, Linear(1024 -> n_classes).
+    The backbones and the two AvgPool2d stay stock torch; everything after them is one call into libmmrca.so
+    (bf16 tcgen05 GEMMs, frozen backbones).  Like the reference it assumes EfficientNetV2-M at 480 x 480."""
+
+    def hier_parameters(self) -> List[torch.Tensor]:
+        sd = dict(self.named_parameters())
+        return [sd[n] for n in F.HIER_PARAM_NAMES]
+
+    def forward_features(self, feats, drop_mask: Optional[torch.Tensor] = None, drop_scale: Optional[float] = None):
+        """The head on the six pooled feature tensors (reference :777-816)."""
+        drop_p, drop_seed = 0.0, 0
+        if drop_mask is None:
+            p = float(self.drop.p)
+            if self.training and p > 0.0:
+                drop_p = min(p, 1.0)
+                drop_seed = int(torch.randint(0, 2 ** 62, (1,), generator=self.dropout_generator).item())
+                self.last_dropout_seed = drop_seed
+            drop_scale = 1.0
+        elif drop_scale is None:
+            drop_scale = 1.0 / (1.0 - float(self.drop.p))
+        return F.hierarchical_head(feats, self.hier_parameters(), drop_mask=drop_mask, drop_scale=drop_scale,
+                                   drop_p=drop_p, drop_seed=drop_seed)
+
+    def forward(self, _input_ids, _attention_mask, _images, eval=False, remove_image=False, remove_text=False):
+        self._images = _images
+        self._input_ids = _input_ids
+        self._attention_mask = _attention_mask
+        self.drop_modalities(eval, remove_image, remove_text)
+        text_output, text_features, (out_stage_3, out_stage_6, image_features) = self._backbone_features(True)
+        hidden_states = text_output.hidden_states
+        layer_2, layer_4 = hidden_states[2][:, 0, :], hidden_states[4][:, 0, :]                    # reference :756-757
+        s3 = torch.nn.functional.avg_pool2d(out_stage_3, kernel_size=7, stride=7).flatten(1)       # :761-762, :769
+        s6 = torch.nn.functional.avg_pool2d(out_stage_6, kernel_size=6, stride=6).flatten(1)       # :765-766, :772
+        return self.forward_features((image_features, s3, s6, text_features, layer_2, layer_4))
+
+
 def load_reference_state_dict(model: nn.Module, state_dict, strict: bool = True):
     """load_state_dict that also accepts checkpoints saved from an nn.DataParallel wrapper
     (`module.` prefix)."""

@@ -47,7 +47,7 @@ class CrossEntropyLoss(nn.Module):
 
 # ---- model dispatch -------------------------------------------------------------------------------------
 def build_model(args, n_classes: int = 4, pretrained: bool = True):
-    """--late_fusion dispatch (reference main_both.py:272-343).  Only the MM-RCA path is rebuilt here."""
+    """--late_fusion dispatch (reference main_both.py:272-343): MM_RCA and hierarchical are rebuilt here."""
     from . import multimodal_model as mm
     compute = N.COMPUTE_BF16 if getattr(args, "compute", "fp32") == "bf16" else N.COMPUTE_FP32
     common = (n_classes, args.model_dropout, args.image_text_dropout, args.image_prob_dropout,
@@ -55,8 +55,10 @@ def build_model(args, n_classes: int = 4, pretrained: bool = True):
     if args.late_fusion == "MM_RCA":
         return mm.MM_RCA(*common, args.features_only, args.cross_attention_only, pretrained=pretrained,
                          compute=compute)
+    if args.late_fusion == "hierarchical":      # reference main_both.py:318-330
+        return mm.Hierarchical(*common, args.features_only, args.cross_attention_only, pretrained=pretrained)
     raise SystemExit(f"late fusion strategy {args.late_fusion!r} is outside the B200-native hot path "
-                     "(MM_RCA is; see SURVEY.md §8)")
+                     "(MM_RCA and hierarchical are; see SURVEY.md §8)")
 
 
 # ---- data-parallel plumbing -----------------------------------------------------------------------------

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MMRCA_ABI_VERSION 2
+#define MMRCA_ABI_VERSION 3
 
 #define MMRCA_NUM_PATCHES 16 /* multimodal_model.py:249 */
 #define MMRCA_SA_DKQ 128     /* :251 */
@@ -208,6 +208,40 @@ int mmrca_attention_backward(const MmrcaAttnParams* p, const float* x_q, const f
                              int32_t d_v, int32_t reverse, const MmrcaAttnGrads* grads,
                              float* d_x_q, float* d_x_kv, void* scratch, size_t scratch_bytes,
                              int32_t compute, void* stream);
+
+/* ---- Hierarchical late-fusion head: Hierarchical.forward after the backbones and the two AvgPool2d
+ * (multimodal_model.py:777-816) + CrossEntropyLoss + backward with frozen backbones.  bf16 tcgen05 GEMMs, fp32
+ * accumulate: the 2e-2-absolute logits contract.  Fixed by the reference: 4 classes, hidden width 512, image
+ * concat 1280 + 2560 + 2048, text concat 3 x 768 (:294-296). ---- */
+typedef struct MmrcaHierParams {
+  const float* w_img; const float* b_img; /* final_hierarchical_image  [512, 5888], [512]  (:294) */
+  const float* w_txt; const float* b_txt; /* final_hierarchical_text   [512, 2304], [512]  (:295) */
+  const float* w_all; const float* b_all; /* final_hierarchical_all    [4, 1024],  [4]     (:296) */
+} MmrcaHierParams;
+typedef struct MmrcaHierGrads { /* accumulated into (+=), 16-byte aligned; w_all / b_all may be NULL */
+  float* w_img; float* b_img; float* w_txt; float* b_txt; float* w_all; float* b_all;
+} MmrcaHierGrads;
+typedef struct MmrcaHierDesc {
+  int32_t batch;
+  int32_t n_classes;  /* 4 */
+  float drop_p;       /* self.drop on both concats (:805-806): seeded mask over the virtual concat [image 5888 | text 2304] */
+  uint64_t drop_seed;
+} MmrcaHierDesc;
+size_t mmrca_hier_workspace_bytes(const MmrcaHierDesc* desc);
+/* feats[6]: pooled image [B,1280], AvgPool(7)+flatten of the 160-channel stage [B,2560], AvgPool(6)+flatten of the
+ * 512-channel stage [B,2048], text CLS of the last layer / hidden_states[2] / hidden_states[4] [B,768] each (fp32,
+ * 16-byte aligned).  drop_mask: caller-drawn uint8 keep mask [B, 8192] (image concat columns first), kept values
+ * scaled by drop_scale; NULL: eval (drop_p == 0) or the seeded mask (mmrca_dropout_mask(seed, p, B, 8192)). */
+int mmrca_hier_forward(const MmrcaHierDesc* desc, const MmrcaHierParams* params, const float* const* feats,
+                       const uint8_t* drop_mask, float drop_scale, float* logits, void* workspace,
+                       size_t workspace_bytes, void* stream);
+/* needs the unmodified workspace of the forward */
+int mmrca_hier_backward(const MmrcaHierDesc* desc, const MmrcaHierParams* params, const float* dlogits,
+                        const MmrcaHierGrads* grads, void* workspace, size_t workspace_bytes, void* stream);
+int mmrca_hier_train_step(const MmrcaHierDesc* desc, const MmrcaHierParams* params, const float* const* feats,
+                          const uint8_t* drop_mask, float drop_scale, const int64_t* labels, const MmrcaCeDesc* ce,
+                          float* logits, float* loss_out, const MmrcaHierGrads* grads, void* workspace,
+                          size_t workspace_bytes, void* stream);
 
 /* Per-kernel timing for roofline reports: between begin and end every kernel this library launches on
  * the calling thread is bracketed by a pair of CUDA events on ITS launch stream (up to max_records

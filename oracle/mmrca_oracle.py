@@ -394,9 +394,14 @@ HIER_PARAM_NAMES = ("final_hierarchical_image.weight", "final_hierarchical_image
                     "final_hierarchical_all.weight", "final_hierarchical_all.bias")
 
 
-def init_hier_params(n_classes: int = 4, seed: int = 0, dtype=torch.float32) -> Dict[str, torch.Tensor]:
+def init_hier_params(n_classes: int = 4, seed: int = 0, dtype=torch.float32, bias_gap: float = 0.0) -> Dict[str, torch.Tensor]:
     """Random parameters of the three Linear layers of the hierarchical head (multimodal_model.py:294-296),
-    torch.nn.Linear-like scale, a pure function of the seed (the 12 MB weight is never stored in a fixture)."""
+    torch.nn.Linear-like scale, a pure function of the seed (the 12 MB weight is never stored in a fixture).
+
+    bias_gap pushes the two hidden-layer biases away from zero (b += sign(b) * bias_gap).  At init scale the hidden
+    pre-activations are ~N(0, 0.013): a bf16 GEMM flips the ReLU of the few units that sit within its rounding error of
+    zero, which changes whole rows of the weight gradient.  With a gap of a few sigma the ReLU pattern is decided by the
+    bias and element-wise gradient parity is meaningful (the analogue of qk_gain for the attention head)."""
     g = torch.Generator().manual_seed(10_000 + seed)
 
     def lin(out_f, in_f):
@@ -409,6 +414,9 @@ def init_hier_params(n_classes: int = 4, seed: int = 0, dtype=torch.float32) -> 
     p["final_hierarchical_image.weight"], p["final_hierarchical_image.bias"] = lin(HIER_HIDDEN, HIER_D_IMG)
     p["final_hierarchical_text.weight"], p["final_hierarchical_text.bias"] = lin(HIER_HIDDEN, HIER_D_TXT)
     p["final_hierarchical_all.weight"], p["final_hierarchical_all.bias"] = lin(n_classes, 2 * HIER_HIDDEN)
+    if bias_gap:
+        for k in ("final_hierarchical_image.bias", "final_hierarchical_text.bias"):
+            p[k] = p[k] + torch.sign(p[k]) * bias_gap
     return p
 
 

@@ -61,14 +61,14 @@ class StubImage(torch.nn.Module):
         return self.maps
 
 
-def run_case(name, B, seed, class_weight=None, label_smoothing=0.0, p_drop=0.0):
+def run_case(name, B, seed, class_weight=None, label_smoothing=0.0, p_drop=0.0, bias_gap=0.05):
     torch.manual_seed(seed)
     mm.distilbert = lambda: StubText()
     mm.bert = lambda: StubText()
     mm.eff_net_v2 = lambda: StubImage()
     with redirect_stdout(io.StringIO()):
         m = mm.Hierarchical(4, p_drop, 0.0, 0.7, 256, "distilbert", 16, True, False, False)
-    params = orc.init_hier_params(seed=seed)
+    params = orc.init_hier_params(seed=seed, bias_gap=bias_gap)
     missing, unexpected = m.load_state_dict(params, strict=False)
     assert not unexpected, unexpected
     g = torch.Generator().manual_seed(2000 + seed)
@@ -101,7 +101,7 @@ def run_case(name, B, seed, class_weight=None, label_smoothing=0.0, p_drop=0.0):
                txt_last=cls[0].numpy(), txt_l2=cls[1].numpy(), txt_l4=cls[2].numpy(), labels=labels.numpy(),
                logits=logits.detach().numpy(), loss=np.float32(loss.item()), seed=np.int64(seed),
                label_smoothing=np.float32(label_smoothing), drop_scale=np.float32(drop_scale),
-               sample_steps=np.array([ROW_STEP, COL_STEP]))
+               sample_steps=np.array([ROW_STEP, COL_STEP]), bias_gap=np.float32(bias_gap))
     if cw is not None:
         out["class_weight"] = cw.numpy()
     if drop_mask is not None:
@@ -122,3 +122,4 @@ if __name__ == "__main__":
     run_case("plain", B=5, seed=0)
     run_case("weighted_smooth", B=6, seed=1, class_weight=[0.6, 1.7, 0.9, 1.2], label_smoothing=0.1)
     run_case("dropout", B=4, seed=2, p_drop=0.6)
+    run_case("init_scale", B=6, seed=3, bias_gap=0.0)      # default-init biases: ReLU units near zero exist
