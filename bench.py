@@ -277,7 +277,10 @@ def run_b200(args, rank, world, local_rank):
     B, K, W = args.batch, args.steps, args.warmup
     compute = N.COMPUTE_BF16 if args.compute == "bf16" else N.COMPUTE_FP32
     params = g.functional.init_head_parameters(dev, seed=0)
-    step = g.HeadTrainStep(params, B, D_IMG, D_TXT, reverse=True, compute=compute, drop_p=args.dropout)
+    co = args.variant == "cross_only"
+    params = g.functional.init_head_parameters(dev, seed=0, cross_attention_only=co) if co else params
+    step = g.HeadTrainStep(params, B, D_IMG, D_TXT, reverse=args.variant != "ca", cross_attention_only=co, compute=compute,
+                           drop_p=args.dropout)
     dp = HeadDataParallel(step)
     # inputs larger than L2: rotate over NB distinct batches
     per_batch = B * (D_IMG + D_TXT) * 4
@@ -396,7 +399,7 @@ def run_b200(args, rank, world, local_rank):
         "metric": "mmrca_head_fwd_bwd_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if compute == N.COMPUTE_FP32 else "bf16", "data": "synthetic",
-        "config": {"workload": f"MM_RCA --reverse fusion head fwd+CE+bwd, batch {B}/GPU, features 1280+768, "
+        "config": {"workload": f"MM_RCA {'--reverse' if args.variant == 'rca' else 'plain cross-attention' if args.variant == 'ca' else '--reverse --cross_attention_only'} fusion head fwd+CE+bwd, batch {B}/GPU, features 1280+768, "
                                f"4 classes, train mode with dropout p={args.dropout} (in-kernel seeded mask, new seed "
                                "every step), backbones frozen (BASELINE.json configs[1])",
                    "parallelism": f"dp{world}", "global_batch": world * B,
@@ -422,6 +425,69 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         dist.destroy_process_group()
 
+# ------------------------------------------------------------------------------------------------------
+def run_hier(args):
+    """Secondary workload (not the BASELINE line): the hierarchical late-fusion head (--late_fusion=hierarchical,
+    reference multimodal_model.py:729-818) fwd + CrossEntropyLoss + bwd at batch `--batch` on one B200, inputs resident
+    in HBM (six pooled feature tensors, 32 KB / sample fp32), seeded dropout.  FLOPs: 2 * B * 8192 * 512 for the two
+    hidden GEMMs forward, the same again for their weight gradients, + the 1024 -> 4 classifier."""
+    import torch
+    import garbage_classification_rca_b200 as g
+    from garbage_classification_rca_b200 import _native as N
+    from oracle import mmrca_oracle as orc      # parameter initialisation only (bench.py may use oracle/)
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    p = orc.init_hier_params(seed=0)
+    params = [p[n].to(dev) for n in g.functional.HIER_PARAM_NAMES]
+    step = g.HierTrainStep(params, B, drop_p=args.dropout)
+    gen = torch.Generator().manual_seed(5)
+    NB = 2                                       # 2 x 134 MB of features > 126 MB L2
+    feats = [[torch.randn(B, w, generator=gen).to(dev) for w in g.functional.HIER_SEGMENTS] for _ in range(NB)]
+    labels = torch.randint(0, 4, (B,), generator=gen).to(dev)
+
+    def one(i):
+        step.zero_grad()
+        step(feats[i % NB], labels, drop_seed=100 + i)
+
+    for i in range(W):
+        one(i)
+    torch.cuda.synchronize()
+    N.kernel_launches(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        one(W + i)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = N.kernel_launches()
+    ms = e0.elapsed_time(e1)
+    per_kernel = {}
+    N.timing_begin(launches + 64)
+    for i in range(K):
+        one(W + i)
+    for name, t in N.timing_end(launches + 64):
+        per_kernel.setdefault(name, []).append(t)
+    peaks = load_peaks()
+    flops = {"hier_gemm": 2 * 8192 * 512 + 2 * 1024 * 4, "hier_wgrad": 2 * 8192 * 512, "hier_dh": 2 * 2 * 1024 * 4}
+    share = {k: sum(v) / K for k, v in per_kernel.items()}
+    dom = max(share, key=share.get)
+    dom_ms = statistics.mean(per_kernel[dom])
+    achieved = flops.get(dom, 0) * B / (dom_ms * 1e-3) / 1e12
+    total = sum(flops.values())
+    print(json.dumps({
+        "metric": "hierarchical_head_fwd_bwd_samples_per_s", "value": B * K / (ms * 1e-3), "unit": "samples/s", "n_gpus": 1,
+        "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"Hierarchical fusion head fwd+CE+bwd, batch {B}, features 5888+2304, hidden 512+512, 4 classes, "
+                               f"dropout p={args.dropout}, backbones frozen (SURVEY.md §8 a11 / f-1; secondary workload)",
+                   "l2": "inputs rotate over 2 batches (268 MB > 126 MB L2)", "loss": float(step.loss.item())},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["bf16_sustained"], "kernel_ms": dom_ms, "traffic": None},
+        "roofline_step": {"bound": "tensor", "achieved": B * K / (ms * 1e-3) * total / 1e12, "peak": peaks["bf16_sustained"],
+                          "frac": B * K / (ms * 1e-3) * total / 1e12 / peaks["bf16_sustained"], "flops_per_sample": total},
+        "kernels_ms_per_step": {k: round(v, 4) for k, v in sorted(share.items(), key=lambda kv: -kv[1])}}))
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -433,12 +499,20 @@ def main():
     ap.add_argument("--compute", default="bf16", choices=("fp32", "bf16"))
     ap.add_argument("--dropout", type=float, default=0.6, help="model_dropout (reference options.py:25 default 0.6)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="mmrca", choices=("mmrca", "hierarchical"),
+                    help="mmrca: the BASELINE.json line (default); hierarchical: the second --late_fusion head (1 GPU)")
+    ap.add_argument("--variant", default="rca", choices=("rca", "ca", "cross_only"),
+                    help="late-fusion ablation of the mmrca workload (BASELINE.json configs[3]): --reverse (default), plain "
+                         "cross-attention, --cross_attention_only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
+    if args.workload == "hierarchical":
+        if rank == 0:
+            run_hier(args)
+    elif args.impl == "reference":
         run_reference(args, rank, world)
     else:
         run_b200(args, rank, world, local_rank)
