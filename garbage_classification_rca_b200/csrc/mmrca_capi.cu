@@ -952,7 +952,17 @@ int mmrca_hier_train_step(const MmrcaHierDesc* desc, const MmrcaHierParams* para
   if (desc->batch == 0) return MMRCA_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if ((rc = hier_forward_impl(*desc, *params, feats, drop_mask, drop_scale, logits, w, st))) return rc;
-  if ((rc = launch_ce(logits, labels, ce, desc->batch, desc->n_classes, loss_out, w.dlogits, st))) return rc;
+  {   // CrossEntropyLoss + dlogits: the multi-CTA kernel of the bf16 pipeline in its cross-entropy-only mode
+    MMRCA_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+    htc::CeFeatArgs a;
+    memset(&a, 0, sizeof(a));
+    a.logits = logits; a.labels = labels; a.cw = ce ? ce->class_weight : nullptr; a.eps = ce ? ce->label_smoothing : 0.f;
+    a.batch = desc->batch; a.dlogits = w.dlogits; a.loss = loss_out;
+    const int tiles8 = (desc->batch + 7) / 8;
+    LaunchScope ls("ce_feat", st);
+    htc::ce_feat_kernel<<<dim3(1, (tiles8 + htc::kCeSliceTiles - 1) / htc::kCeSliceTiles), 256, 0, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
   return hier_backward_impl(*desc, *params, w.dlogits, *grads, w, st);
 }
 
