@@ -488,6 +488,85 @@ def run_hier(args):
                           "frac": B * K / (ms * 1e-3) * total / 1e12 / peaks["bf16_sustained"], "flops_per_sample": total},
         "kernels_ms_per_step": {k: round(v, 4) for k, v in sorted(share.items(), key=lambda kv: -kv[1])}}))
 
+# ------------------------------------------------------------------------------------------------------
+def run_full(args, rank, world, local_rank):
+    """Secondary workload (BASELINE.json configs[2]): one full MM_RCA training step in the reference's transfer-learning
+    phase — stock EfficientNetV2-M (480 x 480) + BERT-base (512 tokens) under bf16 autocast with frozen, random-init
+    weights (no network for checkpoints), the B200 fusion head (bf16 pipeline) with CrossEntropyLoss, backward, one
+    all-reduce of the head gradients, SGD step — at `--batch` samples per GPU (256 in BASELINE.json).  > 99.99 % of the
+    FLOPs are the stock backbones; the line shows the drop-in module inside a real step."""
+    import io
+    from contextlib import redirect_stdout
+    import torch
+    import torch.distributed as dist
+    from garbage_classification_rca_b200 import _native as N, multimodal_model as M
+    from garbage_classification_rca_b200.training import CrossEntropyLoss, allreduce_mean_
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    torch.manual_seed(1 + rank)
+    with redirect_stdout(io.StringIO()):
+        m = M.MM_RCA(4, args.dropout, 0.0, 0.7, 256, "bert", B, True, False, False, pretrained=False, compute=N.COMPUTE_BF16)
+    m = m.to(dev).train()
+    head = [p for n, p in m.named_parameters() if not n.startswith(("image_model.", "text_model.")) and p.requires_grad]
+    opt = torch.optim.SGD(head, lr=1e-3)
+    crit = CrossEntropyLoss()
+    T = m.get_max_token_size()
+    H, Wd = m.get_image_size()
+    images = torch.randn(B, 3, H, Wd, device=dev)
+    ids = torch.randint(0, 30522, (B, T), device=dev)
+    mask = torch.ones_like(ids)
+    labels = torch.randint(0, 4, (B,), device=dev)
+
+    def one():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = m(ids, mask, images)
+        loss = crit(logits.float(), labels)
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in head if p.grad is not None])
+            allreduce_mean_(flat)
+            o = 0
+            for p in head:
+                if p.grad is not None:
+                    p.grad.copy_(flat[o:o + p.numel()].view_as(p)); o += p.numel()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    for _ in range(W):
+        one()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    N.kernel_launches(reset=True)
+    e0.record()
+    for _ in range(K):
+        loss = one()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    if rank == 0:
+        print(json.dumps({
+            "metric": "mmrca_full_step_samples_per_s", "value": world * B * K / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"full MM_RCA --reverse step, EfficientNetV2-M {H}x{Wd} + BERT-base {T} tokens (stock torch, bf16 "
+                                   f"autocast, frozen random-init), B200 fusion head, batch {B}/GPU (BASELINE.json configs[2]; "
+                                   "secondary workload)", "parallelism": f"dp{world}", "loss": float(loss.item())},
+            "gpu_launches": N.kernel_launches()}))
+    if world > 1:
+        dist.destroy_process_group()
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -499,8 +578,9 @@ def main():
     ap.add_argument("--compute", default="bf16", choices=("fp32", "bf16"))
     ap.add_argument("--dropout", type=float, default=0.6, help="model_dropout (reference options.py:25 default 0.6)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="mmrca", choices=("mmrca", "hierarchical"),
-                    help="mmrca: the BASELINE.json line (default); hierarchical: the second --late_fusion head (1 GPU)")
+    ap.add_argument("--workload", default="mmrca", choices=("mmrca", "hierarchical", "full"),
+                    help="mmrca: the BASELINE.json line (default); hierarchical: the second --late_fusion head (1 GPU); full: a whole "
+                         "training step with the stock backbones (BASELINE.json configs[2], use --batch 256)")
     ap.add_argument("--variant", default="rca", choices=("rca", "ca", "cross_only"),
                     help="late-fusion ablation of the mmrca workload (BASELINE.json configs[3]): --reverse (default), plain "
                          "cross-attention, --cross_attention_only")
@@ -512,6 +592,8 @@ def main():
     if args.workload == "hierarchical":
         if rank == 0:
             run_hier(args)
+    elif args.workload == "full":
+        run_full(args, rank, world, local_rank)
     elif args.impl == "reference":
         run_reference(args, rank, world)
     else:
