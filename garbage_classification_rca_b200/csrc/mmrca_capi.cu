@@ -210,6 +210,7 @@ struct Workspace {
   void* dx_img[4];                                                  // training: dXq / dXkv images of CA1, then CA2
   void* sa_v[2]; void* sa_p[2];                                     // training: V / P images kept by the SA forward (img, txt)
   float2* sa_stats[2];                                              // training: LayerNorm (mean, rstd) per context row
+  uint4* ca_row[2];                                                 // training: CA rows {keep bits, mean, rstd} per direction
   float* gm[4]; size_t gm_floats;                                   // training: dM_ext^T per block (contiguous)
   float* step_loss = nullptr;                                       // train step: prep_feat clears gm and *step_loss (no memset nodes)
   size_t bytes;
@@ -270,6 +271,7 @@ static Workspace carve(const MmrcaHeadDesc& d, bool training, void* base) {
     if (d.compute != MMRCA_COMPUTE_FP32) {
       const size_t tiles = (B + 7) / 8;
       for (int i = 0; i < 4; ++i) w.dx_img[i] = take(tiles * htc::kSaTileBytes / 4);
+      for (int i = 0; i < 2; ++i) w.ca_row[i] = reinterpret_cast<uint4*>(take(tiles * (128 * 16 / 4)));
       for (int i = 0; i < 2; ++i) {
         w.sa_v[i] = take(tiles * htc::kSaTileBytes / 4); w.sa_p[i] = take(tiles * (2 * htc::kPHalf) / 4);
         w.sa_stats[i] = reinterpret_cast<float2*>(take(tiles * 256));
@@ -419,6 +421,7 @@ static int head_forward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, 
     a.t_tiles = w.t_img; a.i_tiles = w.i_img;
     a.logits = logits; a.batch = d.batch; a.reverse = (d.flags & MMRCA_FLAG_REVERSE) ? 1 : 0;
     a.drop = make_drop(d);
+    a.row_out[0] = w.ca_row[0]; a.row_out[1] = w.ca_row[1];
     a.dbg = g_dbg_kernel == 2 ? g_dbg : nullptr;
     if ((rc = set_smem(htc::ca_fwd_kernel, htc::CaFwdLayout::BYTES))) return rc;
     LaunchScope ls("ca_fwd_bf16", st);
@@ -446,6 +449,7 @@ static int head_backward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p,
       a.dir[i].g_ln_g = ag[i]->ln_g; a.dir[i].g_ln_b = ag[i]->ln_b;
       a.dir[i].g_wf = g.wf + i * ca;
       a.dir[i].dxq_img = w.dx_img[2 * i]; a.dir[i].dxkv_img = w.dx_img[2 * i + 1];
+      a.dir[i].row_in = w.ca_row[i];
     }
     a.t_tiles = w.t_img; a.i_tiles = w.i_img; a.dlogits = dlogits; a.D = D;
     a.batch = d.batch; a.reverse = (d.flags & MMRCA_FLAG_REVERSE) ? 1 : 0;

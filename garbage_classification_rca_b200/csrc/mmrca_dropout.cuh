@@ -47,19 +47,22 @@ __device__ __forceinline__ void drop_apply8(const DropSpec& s, uint32_t b, uint3
   x[4] *= m[0]; x[5] *= m[1]; x[6] *= m[2]; x[7] *= m[3];
 }
 
-// keep-bits of `n` (multiple of 4, <= 64) consecutive concat columns starting at column col0 (col0 % 4 == 0)
-__device__ __forceinline__ uint64_t drop_bits(const DropSpec& s, uint32_t b, uint32_t col0, int n) {
-  uint64_t bits = 0;
+// keep-bits of N (multiple of 4, <= 64) consecutive concat columns starting at column col0 (col0 % 4 == 0); fully
+// unrolled so that the N / 4 hashes are independent instruction streams (a rolled loop serialises their multiply chains)
+template <int N>
+__device__ __forceinline__ uint64_t drop_bits(const DropSpec& s, uint32_t b, uint32_t col0) {
+  static_assert(N % 4 == 0 && N <= 64, "quads");
+  uint32_t lo = 0, hi = 0;
   const uint32_t q0 = b * uint32_t(s.D >> 2) + (col0 >> 2);
-#pragma unroll 4
-  for (int j = 0; j < n; j += 4) {
+#pragma unroll
+  for (int j = 0; j < N; j += 4) {
     uint32_t w0, w1;
     drop_hash(s, q0 + uint32_t(j >> 2), w0, w1);
     const uint32_t k = ((w0 & 0xffffu) >= s.thresh ? 1u : 0u) | ((w0 >> 16) >= s.thresh ? 2u : 0u) |
                        ((w1 & 0xffffu) >= s.thresh ? 4u : 0u) | ((w1 >> 16) >= s.thresh ? 8u : 0u);
-    bits |= uint64_t(k) << j;
+    if (j < 32) lo |= k << j; else hi |= k << (j - 32);
   }
-  return bits;
+  return uint64_t(lo) | (uint64_t(hi) << 32);
 }
 
 // uint8 keep-mask [B][D] of the same draws (1 = kept)

@@ -669,6 +669,8 @@ struct CaFwdArgs {
   float* logits;
   DropSpec drop;            // concat columns of direction d: [d * 768, d * 768 + 768)
   int batch, reverse;
+  uint4* row_out[2];        // training: per direction [tiles][128] {keep bits lo, hi, mean, rstd} of every context row
+                            // for the backward (dropout draws and LayerNorm statistics are not redone there); null: not kept
   long long* dbg;           // development: per-phase clock64 stamps of warpgroup 0 of CTA 0 (null in production)
 };
 struct CaFwdSmem {
@@ -776,23 +778,21 @@ __device__ __forceinline__ void ca_fwd_tile(WgCtx& c, const CaFwdArgs& a, int d,
     float mean, rstd;
     ln_stats_tmem<C::DV>(c, C::COL_C, mean, rstd);
     const uint32_t cat0 = uint32_t(d * kL * C::DV + (c.rs & 15) * C::DV);   // my row's first concat column (:689-716)
+    // self.drop (:719) acts on the classifier's copy only: the keep bits of my 48 concat columns, drawn once
+    const uint64_t keep = a.drop.thresh ? drop_bits<C::DV>(a.drop, uint32_t(b0 + (c.rs >> 4)), cat0) : ~uint64_t(0);
+    const float dscale = a.drop.thresh ? a.drop.scale : 1.0f;
+    if (a.row_out[d])
+      a.row_out[d][size_t(tile) * 128 + c.rs] = make_uint4(uint32_t(keep), uint32_t(keep >> 32), __float_as_uint(mean), __float_as_uint(rstd));
 #pragma unroll
     for (int c0 = 0; c0 < C::DV; c0 += 16) {
       uint32_t r[16];
       tmem_ld16_nw(c.tmem + c.lane_base + C::COL_C + c0, r);
       tmem_wait_ld();
+      const uint32_t kb = uint32_t(keep >> c0);
       float o[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e)
-        o[e] = fmaxf(fmaf((__uint_as_float(r[e]) - mean) * rstd, ln_s[c0 + e], ln_s[48 + c0 + e]), 0.f);
-      if (a.drop.thresh) {      // self.drop (:719) acts on the classifier's copy only
-#pragma unroll
-        for (int e = 0; e < 16; e += 4) {
-          float m[4];
-          drop_quad(a.drop, uint32_t(b0 + (c.rs >> 4)), cat0 + c0 + e, m);
-          o[e] *= m[0]; o[e + 1] *= m[1]; o[e + 2] *= m[2]; o[e + 3] *= m[3];
-        }
-      }
+        o[e] = fmaxf(fmaf((__uint_as_float(r[e]) - mean) * rstd, ln_s[c0 + e], ln_s[48 + c0 + e]), 0.f) * ((kb >> e) & 1u ? dscale : 0.f);
       const float lo[8] = {o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]};
       const float hi[8] = {o[8], o[9], o[10], o[11], o[12], o[13], o[14], o[15]};
       *reinterpret_cast<uint4*>(xq + uint32_t(c0 >> 3) * kCS + row_off(c.rs)) = pack_bf16x8(lo);

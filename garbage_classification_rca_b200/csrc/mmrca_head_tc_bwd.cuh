@@ -371,6 +371,7 @@ struct CaBwdDir {
   float* g_ln_g; float* g_ln_b;   // [48]
   float* g_wf;                    // classifier rows of this source: &dWf[0][off], row stride D
   void* dxq_img; void* dxkv_img;  // [tiles][kSaTileBytes] out
+  const uint4* row_in;            // [tiles][128] {keep bits lo, hi, mean, rstd} kept by the forward (ca_fwd_kernel)
 };
 struct CaBwdArgs {
   CaBwdDir dir[2];
@@ -476,7 +477,11 @@ __global__ void __launch_bounds__(kCaBwdThreads, 1) ca_bwd_kernel(const CaBwdArg
   bool first = true;
   int ntiles = 0;
   float4 dl_next = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (int(blockIdx.x) < tiles) dl_next = load_dl(c, a.dlogits, blockIdx.x * 8, a.batch);
+  uint4 row_next = make_uint4(0u, 0u, 0u, 0u);
+  if (int(blockIdx.x) < tiles) {
+    dl_next = load_dl(c, a.dlogits, blockIdx.x * 8, a.batch);
+    row_next = __ldg(D.row_in + size_t(blockIdx.x) * 128 + c.rs);
+  }
   int stamp_n = 0;
   if (a.dbg && tid == 0) a.dbg[300 + 2 * (blockIdx.x + gridDim.x * blockIdx.y)] = globaltimer_ns();
   MMRCA_STAMP(0); stamp_n = 1;
@@ -487,7 +492,11 @@ __global__ void __launch_bounds__(kCaBwdThreads, 1) ca_bwd_kernel(const CaBwdArg
     // ---- P0: DL from dlogits; block inputs (SA images): requested by the loader warp once the previous tile's dM / dWv
     //      MMAs were done, which also makes their operand buffers (dZ, dV) free to overwrite below -------------------------
     stage_dl(c, dls, dl_next);
-    if (tile + int(gridDim.x) < tiles) dl_next = load_dl(c, a.dlogits, (tile + int(gridDim.x)) * 8, a.batch);   // a tile ahead
+    const uint4 row_cur = row_next;      // my row's dropout keep bits and LayerNorm statistics from the forward
+    if (tile + int(gridDim.x) < tiles) {      // a tile ahead
+      dl_next = load_dl(c, a.dlogits, (tile + int(gridDim.x)) * 8, a.batch);
+      row_next = __ldg(D.row_in + size_t(tile + int(gridDim.x)) * 128 + c.rs);
+    }
     mbar_wait(&bars[2], ph_ld); ph_ld ^= 1;
     wk_sync_for_mma();
     MMRCA_STAMP(1);
@@ -533,12 +542,11 @@ __global__ void __launch_bounds__(kCaBwdThreads, 1) ca_bwd_kernel(const CaBwdArg
     cta_wait_mma(c);
     MMRCA_STAMP(6);
     // ---- P6: LayerNorm / ReLU backward.  Both warpgroups own the same rows and split a row's 48 columns (24 each):
-    //      statistics over the whole row (cheap, redundant), everything else on my 24 columns, xhat and dxhat kept in
+    //      mean / rstd and the dropout keep bits are the forward's, everything else on my 24 columns, xhat and dxhat kept in
     //      registers between the two passes; the row sums m1 = mean(dxhat), m2 = mean(dxhat xhat) meet in shared memory.
     {
       constexpr int HC = C::DV / 2;
-      float mean, rstd;
-      ln_stats_bw<C::DV>(c, T::C, mean, rstd);
+      const float mean = __uint_as_float(row_cur.z), rstd = __uint_as_float(row_cur.w);
       uint32_t xr[HC], gr[HC];
       {
         const uint32_t tc_ = c.tmem + c.lane_base + T::C + HC * c.w, tg_ = c.tmem + c.lane_base + T::DOUT + HC * c.w;
@@ -551,9 +559,7 @@ __global__ void __launch_bounds__(kCaBwdThreads, 1) ca_bwd_kernel(const CaBwdArg
       // self.drop (multimodal_model.py:719) sits between this block's output and the classifier: the keep bits of
       // my concat columns scale both what the classifier saw (Out, for dWf) and what it sends back (dOut)
       const bool dropping = a.drop.thresh != 0;
-      const uint32_t keep = dropping ? uint32_t(drop_bits(a.drop, uint32_t(b0 + (c.rs >> 4)),
-                                                          uint32_t(d * kL * C::DV + (c.rs & 15) * C::DV + HC * c.w), HC))
-                                     : 0xffffffffu;
+      const uint32_t keep = uint32_t((uint64_t(row_cur.x) | (uint64_t(row_cur.y) << 32)) >> (HC * c.w));
       const float dscale = dropping ? a.drop.scale : 1.0f;
       tmem_wait_ld();
       float xh[HC], dxh[HC];

@@ -9,7 +9,7 @@ kern = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # 0: SA backward, 1: CA
 per = 16 if kern == 1 else 12
 rounds = 4 if kern == 2 else 7
 params = F.init_head_parameters("cuda", seed=0)
-step = g.HeadTrainStep(params, B, 1280, 768, reverse=True, compute=N.COMPUTE_BF16, drop_p=0.6)
+step = g.HeadTrainStep(params, B, 1280, 768, reverse=True, compute=N.COMPUTE_BF16, drop_p=float(os.environ.get("DROP_P", "0.6")))
 img = torch.randn(B, 1280, device="cuda"); txt = torch.randn(B, 768, device="cuda")
 lab = torch.randint(0, 4, (B,), device="cuda")
 dbg = torch.zeros(1024, dtype=torch.int64, device="cuda")
