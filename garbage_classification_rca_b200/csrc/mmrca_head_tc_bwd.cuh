@@ -422,9 +422,10 @@ __global__ void __launch_bounds__(kCaBwdThreads, 1) ca_bwd_kernel(const CaBwdArg
   using S = CaBwdSmem; using T = CaBwdCols; using C = CaCfg;
   // mbarriers: [0] weights, [1] MMAs whose result is read back next, [2] tile load,
   //            [3] dWf / dgamma|dbeta MMAs (G2), [4] dM / dWv MMAs (G3): nobody reads those results until the flush,
-  //            they are only waited for before one of their operand buffers is overwritten
+  //            they are only waited for before one of their operand buffers is overwritten,
+  //            [5] the second half of a split MMA phase: its read-back overlaps the first half's
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::BAR);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
   float* ln_s = reinterpret_cast<float*>(sm + S::LN);
   float2* part = reinterpret_cast<float2*>(sm + S::PART);
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(kCaBwdThreads, 1) ca_bwd_kernel(const CaBwdArg
   const CaBwdDir& D = a.dir[d];
   const bool reverse = a.reverse != 0;
   if (tid == 0) {
-    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
     mbar_arrive_expect_tx(&bars[0], C::W_BYTES);
     bulk_g2s(sm + S::W, D.blobs, C::W_BYTES, &bars[0]);
@@ -451,13 +452,13 @@ __global__ void __launch_bounds__(kCaBwdThreads, 1) ca_bwd_kernel(const CaBwdArg
   const uint32_t tmem = *tmem_slot;
   mbar_wait(&bars[0], 0);
   BwCtx c = make_bwctx(tmem, &bars[1]);
-  uint32_t ph_ld = 0, ph_g2 = 0, ph_g3 = 0;
+  uint32_t ph_ld = 0, ph_g2 = 0, ph_g3 = 0, ph_b = 0;
   uint8_t *xq = sm + S::XQ, *xkv = sm + S::XKV, *zb = sm + S::Z, *vb = sm + S::V, *ob = sm + S::OUT, *dcb = sm + S::DC,
           *dyx = sm + S::DYX, *dls = sm + S::DLS, *pb = sm + S::P, *ones = sm + S::ONES, *wsm = sm + S::W;
   const uint8_t* bz = wsm; const uint8_t* bv = wsm + C::BZ_BYTES; const uint8_t* bc = wsm + C::BZ_BYTES + C::BV_BYTES;
   const int tiles = (a.batch + 7) / 8;
   if (warp == kCtaThreads / 32) {      // ---- loader warp ----------------------------------------------------------------
-    uint32_t ph = 0;
+    uint32_t ph = 0, phb = 0;
     for (int tile = blockIdx.x, it = 0; tile < tiles; tile += gridDim.x, ++it) {
       if (it > 0) { mbar_wait(&bars[4], ph); ph ^= 1; }
       if ((tid & 31) == 0) {
@@ -470,6 +471,19 @@ __global__ void __launch_bounds__(kCaBwdThreads, 1) ca_bwd_kernel(const CaBwdArg
           bulk_prefetch_l2(qsrc + size_t(gridDim.x) * kSaTileBytes, kSaTileBytes);
           bulk_prefetch_l2(ksrc + size_t(gridDim.x) * kSaTileBytes, kSaTileBytes);
         }
+      }
+      __syncwarp();
+      // The persistent dM / dWv MMAs (G3) are issued from here, once the tile's last read-back MMAs (dXkv, third
+      // completion of bars[5] in a tile) are done: tcgen05.mma issue blocks while the tensor pipe's queue is full, so
+      // issued by the workers' thread 0 they held its warp - and with it the end-of-tile barrier - for their whole run.
+      for (int k = 0; k < 3; ++k) { mbar_wait(&bars[5], phb); phb ^= 1; }
+      tc_fence_after_sync();
+      if ((tid & 31) == 0) {
+        mma_steps(tmem + T::G_M, make_smem_desc(smem_u32(xq), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(dyx), kRS, kCS), 2 * kRS,
+                  make_idesc_bf16(128, C::DIN, 1, 1), 8, it > 0);
+        mma_steps(tmem + T::G_WV, make_smem_desc(smem_u32(xkv), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(vb), kRS, kCS), 2 * kRS,
+                  make_idesc_bf16(128, C::DV, 1, 1), 8, it > 0);
+        umma_commit(&bars[4]);
       }
       __syncwarp();
     }
@@ -504,17 +518,19 @@ __global__ void __launch_bounds__(kCaBwdThreads, 1) ca_bwd_kernel(const CaBwdArg
     if (tid == 0) {
       mma_steps(tmem + T::Z, make_smem_desc(smem_u32(xq), kCS, kRS), 2 * kCS, make_smem_desc(smem_u32(bz), C::BZ_LBO, 128),
                 2 * C::BZ_LBO, make_idesc_bf16(128, C::DIN, 0, 0), C::KE / 16, false);
+      umma_commit(c.bar);
       mma_steps(tmem + T::V, make_smem_desc(smem_u32(xkv), kCS, kRS), 2 * kCS, make_smem_desc(smem_u32(bv), C::BV_LBO, 128),
                 2 * C::BV_LBO, make_idesc_bf16(128, C::DV, 0, 0), C::KE / 16, false);
       for (int h = 0; h < 2; ++h)
         mma_steps(tmem + (uint32_t(16 * h) << 16) + T::DOUT, make_smem_desc(smem_u32(dls + h * 8 * kRS), kCS, kRS), 2 * kCS,
                   make_smem_desc(smem_u32(bc), 128, C::BC_LBO), 2 * 128, make_idesc_bf16(64, C::DV, 0, 1), kNCls / 16, false);
-      umma_commit(c.bar);
+      umma_commit(&bars[5]);
     }
     cta_wait_mma(c);
     MMRCA_STAMP(2);
-    // ---- P2: Z, V -> operands (columns split) ---------------------------------------------------------------------
+    // ---- P2: Z, V -> operands (columns split); Z is converted while the V / dOut MMAs run --------------------------
     acc_cols_to_operand(c, T::Z, 48 * c.w, 48 * c.w + 48, zb, c.rp);
+    mbar_wait_ph(&bars[5], ph_b);
     if (c.w == 0) acc_cols_to_operand(c, T::V, 0, 32, vb, c.rp); else acc_cols_to_operand(c, T::V, 32, 48, vb, c.rp);
     wk_sync_for_mma();
     MMRCA_STAMP(3);
@@ -623,21 +639,23 @@ __global__ void __launch_bounds__(kCaBwdThreads, 1) ca_bwd_kernel(const CaBwdArg
     }
     wk_sync_for_mma();
     MMRCA_STAMP(9);
-    // ---- P9: dV = P^T dC, dZ = dS Xkv ----------------------------------------------------------------------------------
+    // ---- P9: dZ = dS Xkv (converted while the next MMAs run), dV = P^T dC ---------------------------------------------
     if (tid == 0) {
-      for (int h = 0; h < 2; ++h) {
-        mma_steps(tmem + (uint32_t(16 * h) << 16) + T::DV, make_smem_desc(smem_u32(pb + h * kPHalf), kRS, kPCS), 2 * kRS,
-                  make_smem_desc(smem_u32(dcb + h * 8 * kRS), kRS, kCS), 2 * kRS, make_idesc_bf16(64, C::DV, 1, 1), 4, false);
+      for (int h = 0; h < 2; ++h)
         mma_steps(tmem + (uint32_t(16 * h) << 16) + T::DZ, make_smem_desc(smem_u32(dls + h * kPHalf), kPCS, kRS), 2 * kPCS,
                   make_smem_desc(smem_u32(xkv + h * 8 * kRS), kRS, kCS), 2 * kRS, make_idesc_bf16(64, C::DIN, 0, 1), 4, false);
-      }
       umma_commit(c.bar);
+      for (int h = 0; h < 2; ++h)
+        mma_steps(tmem + (uint32_t(16 * h) << 16) + T::DV, make_smem_desc(smem_u32(pb + h * kPHalf), kRS, kPCS), 2 * kRS,
+                  make_smem_desc(smem_u32(dcb + h * 8 * kRS), kRS, kCS), 2 * kRS, make_idesc_bf16(64, C::DV, 1, 1), 4, false);
+      umma_commit(&bars[5]);
     }
     cta_wait_mma(c);
     MMRCA_STAMP(10);
-    // ---- P10: dV, dZ -> operands (dV over V, dZ over dy*xhat | dy) ------------------------------------------------
-    if (c.w == 0) acc_cols_to_operand(c, T::DZ, 0, 80, dyx, c.rs);
-    else { acc_cols_to_operand(c, T::DZ, 80, 96, dyx, c.rs); acc_cols_to_operand(c, T::DV, 0, 48, vb, c.rs); }
+    // ---- P10: dZ, dV -> operands (dZ over dy*xhat | dy, dV over V) ------------------------------------------------
+    acc_cols_to_operand(c, T::DZ, 48 * c.w, 48 * c.w + 48, dyx, c.rs);
+    mbar_wait_ph(&bars[5], ph_b);
+    if (c.w == 0) acc_cols_to_operand(c, T::DV, 0, 32, vb, c.rs); else acc_cols_to_operand(c, T::DV, 32, 48, vb, c.rs);
     wk_sync_for_mma();
     MMRCA_STAMP(11);
     // ---- P11: gradients of the block inputs (read back next), then the parameter gradients (persistent, G3) ------
@@ -645,19 +663,15 @@ __global__ void __launch_bounds__(kCaBwdThreads, 1) ca_bwd_kernel(const CaBwdArg
       // dXq = dZ M^T  (B: the Z blob read along its other axis)
       mma_steps(tmem + T::DXQ, make_smem_desc(smem_u32(dyx), kCS, kRS), 2 * kCS, make_smem_desc(smem_u32(bz), 128, C::BZ_LBO), 2 * 128,
                 make_idesc_bf16(128, C::DIN, 0, 1), C::DIN / 16, false);
-      // dXkv = dS^T Z + dV Wv
+      umma_commit(c.bar);
+      // dXkv = dS^T Z + dV Wv  (runs while dXq is read back)
       for (int h = 0; h < 2; ++h) {
         mma_steps(tmem + (uint32_t(16 * h) << 16) + T::DXKV, make_smem_desc(smem_u32(dls + h * kPHalf), kRS, kPCS), 2 * kRS,
                   make_smem_desc(smem_u32(zb + h * 8 * kRS), kRS, kCS), 2 * kRS, make_idesc_bf16(64, C::DIN, 1, 1), 4, false);
         mma_steps(tmem + (uint32_t(16 * h) << 16) + T::DXKV, make_smem_desc(smem_u32(vb + h * 8 * kRS), kCS, kRS), 2 * kCS,
                   make_smem_desc(smem_u32(bv), 128, C::BV_LBO), 2 * 128, make_idesc_bf16(64, C::DIN, 0, 1), C::DV / 16, true);
       }
-      umma_commit(c.bar);
-      mma_steps(tmem + T::G_M, make_smem_desc(smem_u32(xq), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(dyx), kRS, kCS), 2 * kRS,
-                make_idesc_bf16(128, C::DIN, 1, 1), 8, !first);
-      mma_steps(tmem + T::G_WV, make_smem_desc(smem_u32(xkv), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(vb), kRS, kCS), 2 * kRS,
-                make_idesc_bf16(128, C::DV, 1, 1), 8, !first);
-      umma_commit(&bars[4]);
+      umma_commit(&bars[5]);
     }
     cta_wait_mma(c);
     MMRCA_STAMP(12);
@@ -667,6 +681,7 @@ __global__ void __launch_bounds__(kCaBwdThreads, 1) ca_bwd_kernel(const CaBwdArg
       uint8_t* gk = static_cast<uint8_t*>(D.dxkv_img) + size_t(tile) * kSaTileBytes;
       // (global images use the same [column group][row] geometry as the shared-memory operands)
       acc_cols_to_operand(c, T::DXQ, 48 * c.w, 48 * c.w + 48, gq, c.rp);
+      mbar_wait_ph(&bars[5], ph_b);
       acc_cols_to_operand(c, T::DXKV, 48 * c.w, 48 * c.w + 48, gk, c.rs);
     }
     first = false;
