@@ -223,7 +223,7 @@ def run_reference(args, rank, world):
         step(i)
     dt = time.perf_counter() - t0
     val = args.steps * args.batch / dt
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "mmrca_head_fwd_bwd_samples_per_s", "value": val, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -421,7 +421,7 @@ def run_b200(args, rank, world, local_rank):
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(B, args.dropout)
-    print(json.dumps(out))
+    emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -475,7 +475,7 @@ def run_hier(args):
     dom_ms = statistics.mean(per_kernel[dom])
     achieved = flops.get(dom, 0) * B / (dom_ms * 1e-3) / 1e12
     total = sum(flops.values())
-    print(json.dumps({
+    emit(json.dumps({
         "metric": "hierarchical_head_fwd_bwd_samples_per_s", "value": B * K / (ms * 1e-3), "unit": "samples/s", "n_gpus": 1,
         "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"Hierarchical fusion head fwd+CE+bwd, batch {B}, features 5888+2304, hidden 512+512, 4 classes, "
@@ -556,7 +556,7 @@ def run_full(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
     if rank == 0:
-        print(json.dumps({
+        emit(json.dumps({
             "metric": "mmrca_full_step_samples_per_s", "value": world * B * K / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "dtype": "bf16",
             "data": "synthetic",
@@ -568,7 +568,23 @@ def run_full(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's ORIGINAL stdout; fd 1 itself is pointed at stderr for the rest of the run
+    so that native libraries (NCCL prints its version banner to stdout) cannot put other lines next to it."""
+    if _JSON_FD is None:
+        print(line, flush=True)
+    else:
+        os.write(_JSON_FD, (line + "\n").encode())
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
