@@ -281,7 +281,7 @@ def run_b200(args, rank, world, local_rank):
     params = g.functional.init_head_parameters(dev, seed=0, cross_attention_only=co) if co else params
     step = g.HeadTrainStep(params, B, D_IMG, D_TXT, reverse=args.variant != "ca", cross_attention_only=co, compute=compute,
                            drop_p=args.dropout)
-    dp = HeadDataParallel(step)
+    dp = HeadDataParallel(step, peer=not args.nccl)
     # inputs larger than L2: rotate over NB distinct batches
     per_batch = B * (D_IMG + D_TXT) * 4
     NB = max(2, -(-2 * L2_BYTES // per_batch))
@@ -403,6 +403,7 @@ def run_b200(args, rank, world, local_rank):
                                f"4 classes, train mode with dropout p={args.dropout} (in-kernel seeded mask, new seed "
                                "every step), backbones frozen (BASELINE.json configs[1])",
                    "parallelism": f"dp{world}", "global_batch": world * B,
+                   "collective": dp.collective if world > 1 else "none (1 GPU)",
                    "l2": f"inputs rotate over {NB} distinct batches ({NB * per_batch >> 20} MiB > 126 MiB L2)",
                    "compute": args.compute, "loss": loss_val},
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": B * (D_IMG + D_TXT) * 4 + B * 8,
@@ -594,6 +595,8 @@ def main():
     ap.add_argument("--compute", default="bf16", choices=("fp32", "bf16"))
     ap.add_argument("--dropout", type=float, default=0.6, help="model_dropout (reference options.py:25 default 0.6)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl", action="store_true", help="N > 1: all-reduce the gradient bucket with NCCL instead of the "
+                                                        "one-shot peer-memory kernel")
     ap.add_argument("--workload", default="mmrca", choices=("mmrca", "hierarchical", "full"),
                     help="mmrca: the BASELINE.json line (default); hierarchical: the second --late_fusion head (1 GPU); full: a whole "
                          "training step with the stock backbones (BASELINE.json configs[2], use --batch 256)")

@@ -67,7 +67,8 @@ EXPORTS = ("mmrca_query", "mmrca_last_error", "mmrca_head_workspace_bytes", "mmr
            "mmrca_attention_backward_scratch_bytes", "mmrca_attention_backward", "mmrca_timing_begin",
            "mmrca_timing_end", "mmrca_dev_umma_selftest", "mmrca_attention_forward_scratch_bytes",
            "mmrca_head_workspace_offset", "mmrca_dropout_mask", "mmrca_dev_set_debug",
-           "mmrca_hier_workspace_bytes", "mmrca_hier_forward", "mmrca_hier_backward", "mmrca_hier_train_step")
+           "mmrca_hier_workspace_bytes", "mmrca_hier_forward", "mmrca_hier_backward", "mmrca_hier_train_step",
+           "mmrca_peer_allreduce_mean", "mmrca_peer_allreduce_pad_bytes")
 
 
 def _sources_newer_than_lib() -> bool:
@@ -168,6 +169,11 @@ def lib() -> C.CDLL:
                                             C.c_float, _fp, C.POINTER(CeDesc), _fp, _fp, C.POINTER(HierParams),
                                             _fp, C.c_size_t, _fp]
         L.mmrca_hier_train_step.restype = C.c_int
+        L.mmrca_peer_allreduce_mean.argtypes = [_fp, C.c_int32, C.c_int32, C.POINTER(_fp), C.POINTER(_fp), C.c_int32,
+                                                C.c_int32, C.c_uint32, _fp]
+        L.mmrca_peer_allreduce_mean.restype = C.c_int
+        L.mmrca_peer_allreduce_pad_bytes.argtypes = [C.c_int32]
+        L.mmrca_peer_allreduce_pad_bytes.restype = C.c_int
         if L.mmrca_query(QUERY_ABI_VERSION) != ABI_VERSION:
             raise RuntimeError("libmmrca.so ABI version mismatch: rebuild it")
         _lib = L

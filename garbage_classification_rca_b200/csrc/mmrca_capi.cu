@@ -14,6 +14,7 @@
 #include "mmrca_head_tc.cuh"
 #include "mmrca_head_tc_bwd.cuh"
 #include "mmrca_hier.cuh"
+#include "mmrca_peer.cuh"
 
 namespace mmrca {
 
@@ -969,6 +970,34 @@ int mmrca_hier_train_step(const MmrcaHierDesc* desc, const MmrcaHierParams* para
   MMRCA_CUDA(cudaGetLastError());
   return hier_backward_impl(*desc, *params, w.dlogits, *grads, w, st);
 }
+
+int mmrca_peer_allreduce_mean(float* flat, int32_t n, int32_t n_pad, const void* const* staging, void* const* pads,
+                              int32_t rank, int32_t world, uint32_t step, void* stream) {
+  if (!flat || !staging || !pads) return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
+  if (n <= 0 || (n & 3) || n_pad < n || (n_pad & 3) || (reinterpret_cast<uintptr_t>(flat) & 15))
+    return fail(MMRCA_ERR_INVALID, "bucket must be 16-byte aligned with a multiple of 4 floats, n_pad >= n%s%s");
+  if (world < 1 || world > peer::kMaxWorld || rank < 0 || rank >= world || step == 0)
+    return fail(MMRCA_ERR_INVALID, "world must be in [1, 16], rank in [0, world), step >= 1%s%s");
+  DeviceInfo di;
+  int rc;
+  if ((rc = device_info(&di))) return rc;
+  if (di.sms < peer::kCtas) return fail(MMRCA_ERR_INVALID, "the peer all-reduce needs its CTAs co-resident%s%s");
+  peer::Args a;
+  memset(&a, 0, sizeof(a));
+  a.flat = flat; a.n = n; a.n_pad = n_pad; a.rank = rank; a.world = world; a.step = step;
+  for (int i = 0; i < world; ++i) {
+    if (!staging[i] || !pads[i]) return fail(MMRCA_ERR_INVALID, "null peer buffer%s%s");
+    a.staging[i] = static_cast<const float*>(staging[i]); a.pads[i] = static_cast<uint32_t*>(pads[i]);
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    LaunchScope ls("peer_allreduce", st);
+    peer::allreduce_mean_kernel<<<peer::kCtas, peer::kThreads, 0, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+int mmrca_peer_allreduce_pad_bytes(int32_t world) { return 2 * world * peer::kCtas * int(sizeof(uint32_t)); }
 
 size_t mmrca_attention_forward_scratch_bytes(int32_t, int32_t, int32_t, int32_t) { return 0; }
 

@@ -81,18 +81,73 @@ def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
     return flat
 
 
+class PeerAllReduce:
+    """The step's one collective as a one-shot all-reduce over NVLink peer memory (csrc/mmrca_peer.cuh): every rank
+    reads the W staged copies of the 379 KB bucket itself.  torch's symmetric memory does the plumbing (allocation, IPC
+    exchange, mapping); the reduction is libmmrca.so's kernel.  Construction is a collective over `group`; it raises
+    if symmetric memory is unavailable (the caller then keeps NCCL)."""
+
+    def __init__(self, numel: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.n = numel
+        self.n_pad = (numel + 63) // 64 * 64
+        pad_words = N.lib().mmrca_peer_allreduce_pad_bytes(self.world) // 4
+        self.pad_off = 2 * self.n_pad                                   # [staging half 0 | half 1 | flag pad] in one buffer
+        self.buf = symm_mem.empty(self.pad_off + pad_words, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.staging = (N._fp * self.world)(*ptrs)
+        self.pads = (N._fp * self.world)(*[p + 4 * self.pad_off for p in ptrs])
+        self.step = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                                             # every pad is zero before anyone publishes a flag
+
+    def __call__(self, flat: torch.Tensor) -> torch.Tensor:
+        if flat.numel() != self.n or flat.dtype != torch.float32 or not flat.is_contiguous():
+            raise ValueError("bucket does not match the one this all-reduce was built for")
+        self.step += 1
+        with torch.cuda.device(flat.device):
+            N.check(N.lib().mmrca_peer_allreduce_mean(flat.data_ptr(), self.n, self.n_pad, self.staging, self.pads,
+                                                      self.rank, self.world, self.step,
+                                                      torch.cuda.current_stream(flat.device).cuda_stream),
+                    "mmrca_peer_allreduce_mean")
+        return flat
+
+
 class HeadDataParallel:
     """Batch-sharded training of the fusion head on precomputed features: each rank runs the one-call
-    train step on its shard, then ONE all-reduce of `step.grads.flat` (94 820 floats, 379 KB)."""
+    train step on its shard, then ONE all-reduce of `step.grads.flat` (94 820 floats, 379 KB): over NVLink peer
+    memory (PeerAllReduce) when `peer=True` and symmetric memory is available, through NCCL / gloo otherwise."""
 
-    def __init__(self, step: F.HeadTrainStep, group=None):
+    def __init__(self, step, group=None, peer: bool = False):
         self.step = step
         self.group = group
+        self.peer = None
+        self.collective = "torch.distributed all_reduce"
+        if peer and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1 \
+                and step.grads.flat.is_cuda:
+            ok = torch.zeros(1, device=step.grads.flat.device)
+            try:
+                self.peer = PeerAllReduce(step.grads.flat.numel(), step.grads.flat.device, group)
+                ok += 1
+            except Exception as e:      # noqa: BLE001  (no symmetric memory on this box: NCCL does the job)
+                self.peer_error = repr(e)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)     # all ranks or none
+            if ok.item() < 1:
+                self.peer = None
+            else:
+                self.collective = "one-shot all-reduce over NVLink peer memory (mmrca_peer_allreduce_mean)"
 
     def __call__(self, img, txt, labels, drop_mask=None, drop_scale=1.0, sync: bool = True, drop_seed: int = 0):
         loss, logits = self.step(img, txt, labels, drop_mask, drop_scale, drop_seed)
         if sync:   # sync=False == DDP.no_sync() while accumulating (reference steps every acc_steps batches)
-            allreduce_mean_(self.step.grads.flat, self.group)
+            if self.peer is not None:
+                self.peer(self.step.grads.flat)
+            else:
+                allreduce_mean_(self.step.grads.flat, self.group)
         return loss, logits
 
 

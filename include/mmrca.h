@@ -243,6 +243,16 @@ int mmrca_hier_train_step(const MmrcaHierDesc* desc, const MmrcaHierParams* para
                           float* logits, float* loss_out, const MmrcaHierGrads* grads, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* One-shot all-reduce (mean over `world` ranks) of the flat head-gradient bucket over NVLink peer memory: the single
+ * collective of a data-parallel step (SURVEY.md §8 e; the reference never ran multi-GPU, stock DDP would call NCCL
+ * here).  staging[i] / pads[i]: rank i's symmetric staging buffer (2 * n_pad floats) and flag pad
+ * (mmrca_peer_allreduce_pad_bytes(world) bytes, zeroed once), mapped into this process (torch symmetric memory or CUDA
+ * IPC; host arrays of device pointers).  step = 1, 2, 3, ...: the same sequence on every rank.  Every rank calls it once
+ * per step on its stream; flat is reduced in place, bit-identical on all ranks. */
+int mmrca_peer_allreduce_mean(float* flat, int32_t n, int32_t n_pad, const void* const* staging, void* const* pads,
+                              int32_t rank, int32_t world, uint32_t step, void* stream);
+int mmrca_peer_allreduce_pad_bytes(int32_t world);
+
 /* Per-kernel timing for roofline reports: between begin and end every kernel this library launches on
  * the calling thread is bracketed by a pair of CUDA events on ITS launch stream (up to max_records
  * launches).  mmrca_timing_end synchronises those events (the only call here that blocks), writes up to
