@@ -977,7 +977,7 @@ int mmrca_peer_allreduce_mean(float* flat, int32_t n, int32_t n_pad, const void*
   if (n <= 0 || (n & 3) || n_pad < n || (n_pad & 3) || (reinterpret_cast<uintptr_t>(flat) & 15))
     return fail(MMRCA_ERR_INVALID, "bucket must be 16-byte aligned with a multiple of 4 floats, n_pad >= n%s%s");
   if (world < 1 || world > peer::kMaxWorld || rank < 0 || rank >= world || step == 0)
-    return fail(MMRCA_ERR_INVALID, "world must be in [1, 16], rank in [0, world), step >= 1%s%s");
+    return fail(MMRCA_ERR_INVALID, "world must be in [1, 8], rank in [0, world), step >= 1%s%s");
   DeviceInfo di;
   int rc;
   if ((rc = device_info(&di))) return rc;

@@ -23,7 +23,7 @@
 namespace mmrca {
 namespace peer {
 
-constexpr int kMaxWorld = 16;
+constexpr int kMaxWorld = 8;
 constexpr int kCtas = 48, kThreads = 256;
 
 struct Args {
@@ -63,15 +63,31 @@ __global__ void __launch_bounds__(kThreads) allreduce_mean_kernel(const Args a) 
     while (int32_t(ld_acquire_sys(f) - a.step) < 0) { }
   }
   __syncthreads();
+  // all W remote loads of an element group are in flight before the first one is consumed (a load-add-load-add loop
+  // would pay one NVLink round trip per rank), two groups per thread interleaved
   const float inv = 1.0f / float(a.world);
   float4* dst = reinterpret_cast<float4*>(a.flat);
-  for (int i = lo + tid; i < hi; i += kThreads) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = 0; p < a.world; ++p) {
-      const float4 v = ld_peer(reinterpret_cast<const float4*>(a.staging[p]) + size_t(par) * (a.n_pad / 4) + i);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  const size_t half = size_t(par) * (a.n_pad / 4);
+  for (int i0 = lo + tid; i0 < hi; i0 += 2 * kThreads) {
+    const int i1 = i0 + kThreads;
+    float4 v0[kMaxWorld], v1[kMaxWorld];
+#pragma unroll
+    for (int p = 0; p < kMaxWorld; ++p) {
+      if (p < a.world) {
+        v0[p] = ld_peer(reinterpret_cast<const float4*>(a.staging[p]) + half + i0);
+        if (i1 < hi) v1[p] = ld_peer(reinterpret_cast<const float4*>(a.staging[p]) + half + i1);
+      }
     }
-    dst[i] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+#pragma unroll
+    for (int p = 0; p < kMaxWorld; ++p) {
+      if (p < a.world) {
+        s0.x += v0[p].x; s0.y += v0[p].y; s0.z += v0[p].z; s0.w += v0[p].w;
+        if (i1 < hi) { s1.x += v1[p].x; s1.y += v1[p].y; s1.z += v1[p].z; s1.w += v1[p].w; }
+      }
+    }
+    dst[i0] = make_float4(s0.x * inv, s0.y * inv, s0.z * inv, s0.w * inv);
+    if (i1 < hi) dst[i1] = make_float4(s1.x * inv, s1.y * inv, s1.z * inv, s1.w * inv);
   }
 }
 
