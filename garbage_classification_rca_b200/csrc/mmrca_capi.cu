@@ -725,7 +725,7 @@ static int hier_forward_impl(const MmrcaHierDesc& d, const MmrcaHierParams& p, c
     hier::WPrepArgs a;
     a.w[0] = p.w_img; a.w[1] = p.w_txt; a.blob[0] = w.wb_img; a.blob[1] = w.wb_txt;
     LaunchScope ls("hier_wprep", st);
-    hier::hier_wprep_kernel<<<dim3(hier::kGImg * hier::kHid / 256, 2), 256, 0, st>>>(a);
+    hier::hier_wprep_kernel<<<dim3(hier::kHid / 32, hier::kGImg / 32 + hier::kGTxt / 32), 256, 0, st>>>(a);
   }
   MMRCA_CUDA(cudaGetLastError());
   {

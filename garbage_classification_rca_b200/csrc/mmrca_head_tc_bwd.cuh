@@ -1038,7 +1038,7 @@ static_assert(kFinRows == 1, "finalize_kernel's thread mapping assumes one row p
 // grid.x = sum over blocks of d_kq / 8.  CTA = (block, 8 rows n): dM (d_in x (d_in + 1), du in the last column) and the
 // 8 rows of W_query / W_key are staged in shared memory with every load in flight at once, then each thread owns
 // outputs (n, k): dWq[n][k] += s sum_k' dM[k][k'] Wk[n][k'],  dWk[n][k'] += s (sum_k Wq[n][k] dM[k][k'] + bq[n] du[k']),
-// dbq[n] += s sum_k' du[k'] Wk[n][k'].  Every output has exactly one owner: plain read-modify-write accumulation.
+// dbq[n] += s sum_k' du[k'] Wk[n][k'].  Every output has exactly one owner.
 __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
   extern __shared__ __align__(16) float fsm[];
   int b = 0, grp = blockIdx.x;
@@ -1054,27 +1054,25 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
   float* wk_s = g_s + din * gs;              // [8][din]
   float* wq_s = wk_s + kFinRows * din;       // [8][din]
   float* bq_s = wq_s + kFinRows * din;       // [8]
-  {   // dM rows are 128 floats apart: din / 4 16-byte loads + du per row, at most 10 items per thread, all in flight
-    const int per_row = din / 4 + 1, items = din * per_row;
-    float4 v[10];
+  {   // dM rows are 128 floats apart: warp w takes rows w, w + 8, ... whole (one 16-byte load per lane, no index
+      // arithmetic), every load of the thread in flight before the first shared-memory store
+    const int warp = tid >> 5, lane = tid & 31;
+    float4 v[12];
 #pragma unroll
-    for (int u = 0; u < 10; ++u) {
-      const int i = tid + 256 * u;
+    for (int u = 0; u < 12; ++u) {
+      const int kp = warp + 8 * u;
       v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < items) {
-        const int kp = i / per_row, q = i - kp * per_row;
-        if (q < din / 4) v[u] = __ldg(reinterpret_cast<const float4*>(B.gm + size_t(kp) * 128) + q);
-        else v[u].x = __ldg(B.gm + size_t(kp) * 128 + din);
-      }
+      if (kp < din && 4 * lane <= din) v[u] = __ldg(reinterpret_cast<const float4*>(B.gm + size_t(kp) * 128) + lane);
     }
 #pragma unroll
-    for (int u = 0; u < 10; ++u) {
-      const int i = tid + 256 * u;
-      if (i < items) {
-        const int kp = i / per_row, q = i - kp * per_row;
-        float* d = g_s + kp * gs + 4 * q;
-        if (q < din / 4) { d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w; }
-        else d[0] = v[u].x;
+    for (int u = 0; u < 12; ++u) {
+      const int kp = warp + 8 * u;
+      if (kp < din && 4 * lane <= din) {
+        float* d = g_s + kp * gs + 4 * lane;
+        const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (4 * lane + j <= din) d[j] = e[j];
       }
     }
   }
@@ -1099,14 +1097,14 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinArgs a) {
     float q = q0 + q1, kk = k0 + k1;
     q += __shfl_xor_sync(0xffffffffu, q, 1);
     kk += __shfl_xor_sync(0xffffffffu, kk, 1);
-    if (half == 0) B.g_wq[size_t(n0) * din + k] += q * s;
-    else B.g_wk[size_t(n0) * din + k] += kk * s;
+    if (half == 0) red_add(B.g_wq + size_t(n0) * din + k, q * s);      // accumulate (+=), not waited for
+    else red_add(B.g_wk + size_t(n0) * din + k, kk * s);
   } else if (tid >= 224) {
     const int lane = tid & 31;
     float acc = 0.f;
     for (int j = lane; j < din; j += 32) acc = fmaf(g_s[j * gs + din], wk_s[j], acc);
     acc = warp_sum(acc);
-    if (lane == 0) B.g_bq[n0] += acc * s;
+    if (lane == 0) red_add(B.g_bq + n0, acc * s);
   }
 }
 

@@ -118,16 +118,31 @@ __global__ void __launch_bounds__(256) hier_prep_kernel(const PrepArgs a) {
   if (tid < kClasses && live) a.logits[size_t(b) * kClasses + tid] = __ldg(a.b_all + tid);
 }
 
-// W [512][K] fp32 -> blob [K/8][512][8] bf16 (the K-major B operand of the forward GEMM); blockIdx.y = modality
+// W [512][K] fp32 -> blob [K/8][512][8] bf16 (the K-major B operand of the forward GEMM).  CTA = 32 rows n x 32 column
+// groups: a warp reads 1 KB of one weight row per instruction, the tile is transposed through shared memory and a warp
+// writes the 32 consecutive 16-byte entries of one column group (reads and writes both coalesced).
+// grid = (16 row blocks, 23 + 9 group blocks: image then text)
 struct WPrepArgs { const float* w[2]; void* blob[2]; };
 __global__ void __launch_bounds__(256) hier_wprep_kernel(const WPrepArgs a) {
-  const int mod = blockIdx.y, K = mod == 0 ? kDImg : kDTxt;
-  const int idx = blockIdx.x * 256 + threadIdx.x, n = idx & (kHid - 1), kg = idx >> 9;
-  if (kg >= K / 8) return;
-  const float* p = a.w[mod] + size_t(n) * K + kg * 8;
-  const float4 lo = __ldg(reinterpret_cast<const float4*>(p)), hi = __ldg(reinterpret_cast<const float4*>(p + 4));
-  const float o[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-  *reinterpret_cast<uint4*>(static_cast<uint8_t*>(a.blob[mod]) + (size_t(kg) * kHid + n) * 16) = pack_bf16x8(o);
+  __shared__ uint4 t[32][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int gb = blockIdx.y, mod = 0;
+  if (gb >= kGImg / 32) { gb -= kGImg / 32; mod = 1; }
+  const int K = mod == 0 ? kDImg : kDTxt, n0 = blockIdx.x * 32, kg0 = gb * 32;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int nl = warp + 8 * j;
+    const float* p = a.w[mod] + size_t(n0 + nl) * K + (kg0 + lane) * 8;
+    const float4 lo = __ldg(reinterpret_cast<const float4*>(p)), hi = __ldg(reinterpret_cast<const float4*>(p + 4));
+    const float o[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    t[lane][nl] = pack_bf16x8(o);      // [column group][row]
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int kl = warp + 8 * j;
+    *reinterpret_cast<uint4*>(static_cast<uint8_t*>(a.blob[mod]) + (size_t(kg0 + kl) * kHid + n0 + lane) * 16) = t[kl][lane];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
