@@ -21,7 +21,7 @@ namespace mmrca {
 static thread_local char g_err[512] = "";
 static thread_local int g_launches = 0;
 static long long* g_dbg = nullptr;
-static int g_dbg_kernel = 0;         // 0: sa_bwd, 1: ca_bwd, 2: ca_fwd   // development: device buffer for per-phase clock stamps (mmrca_dev_set_debug)
+static int g_dbg_kernel = 0;         // 0: sa_bwd, 1: ca_bwd, 2: ca_fwd, 3: sa_fwd   // development: device buffer for per-phase clock stamps (mmrca_dev_set_debug)
 
 // ---- optional per-kernel timing (mmrca_timing_begin / _end) -------------------------------------
 struct TimingRec { const char* name; cudaEvent_t e0, e1; };
@@ -409,6 +409,7 @@ static int head_forward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, 
     a.role[1].x_tiles = w.x_txt; a.role[1].ln_g = p.sa_txt.ln_g; a.role[1].ln_b = p.sa_txt.ln_b;
     a.role[1].blobs = w.fblob[1]; a.role[1].out_tiles = w.t_img; a.role[1].v_tiles = w.sa_v[1]; a.role[1].p_tiles = w.sa_p[1]; a.role[1].ln_stats = w.sa_stats[1];
     a.batch = d.batch;
+    a.dbg = g_dbg_kernel == 3 ? g_dbg : nullptr;
     if ((rc = set_smem(htc::sa_fwd_kernel, htc::SaFwdLayout::BYTES))) return rc;
     LaunchScope ls("sa_fwd_bf16", st);
     htc::sa_fwd_kernel<<<grid, htc::kCtaThreads, htc::SaFwdLayout::BYTES, st>>>(a);

@@ -490,6 +490,7 @@ struct SaRole {
 struct SaFwdArgs {
   SaRole role[2];         // 0: image (DIN 80), 1: text (DIN 48)
   int batch;
+  long long* dbg;         // development: per-phase clock64 stamps of warpgroup 0 of CTA 0 (null in production)
 };
 
 // warpgroup buffers of the SA forward (sized for the wider role)
@@ -521,7 +522,9 @@ __device__ __forceinline__ void sa_issue_x_load(const SaFwdArgs& a, int role, in
 template <class C>
 __device__ __forceinline__ void sa_fwd_tile(WgCtx& c, const SaFwdArgs& a, const SaRole& R, uint8_t* wsm, uint8_t* bsm,
                                             const float* ln_s, int tile, uint64_t* bar_ld, uint32_t& ph_ld,
-                                            int next_tile, int next_role) {
+                                            int next_tile, int next_role, int stamp_n) {
+#define FSTAMP(i) do { if (a.dbg && c.wt == 0 && c.wg == 0 && blockIdx.x == 0 && stamp_n + (i) < 250) a.dbg[stamp_n + (i)] = clock64(); } while (0)
+  FSTAMP(0);
   uint8_t* xop = bsm + SaFwdSmem::X;
   uint8_t* zop = bsm + SaFwdSmem::ZP;
   uint8_t* vop = bsm + SaFwdSmem::V;
@@ -529,6 +532,7 @@ __device__ __forceinline__ void sa_fwd_tile(WgCtx& c, const SaFwdArgs& a, const 
   mbar_wait(bar_ld, ph_ld);
   ph_ld ^= 1;
   tc_fence_after_sync();
+  FSTAMP(1);
   // ---- Z | V: two MMA chains over the same A operand ---------------------------------------------------------------
   if (c.wt == 0) {
     const uint64_t ax = make_smem_desc(smem_u32(xop), kCS, kRS);
@@ -539,9 +543,11 @@ __device__ __forceinline__ void sa_fwd_tile(WgCtx& c, const SaFwdArgs& a, const 
     umma_commit(c.bar);
   }
   wg_wait_mma(c);
+  FSTAMP(2);
   acc_to_operand<C::DIN>(c, C::COL_Z, zop);
   acc_to_operand<C::DV>(c, C::COL_V, vop);
   wg_sync_for_mma(c);
+  FSTAMP(3);
   // ---- scores: two M=64 halves, S_h = Z_h X_h^T --------------------------------------------------------------
   if (c.wt == 0) {
 #pragma unroll
@@ -554,6 +560,7 @@ __device__ __forceinline__ void sa_fwd_tile(WgCtx& c, const SaFwdArgs& a, const 
     if (R.v_tiles) { bulk_s2g(static_cast<uint8_t*>(R.v_tiles) + size_t(tile) * kSaTileBytes, vop, kSaTileBytes); bulk_commit(); }
   }
   wg_wait_mma(c);
+  FSTAMP(4);
   // X is dead (Z, V and the scores have read it): the next tile's image lands while this one finishes
   if (c.wt == 0 && next_tile >= 0) sa_issue_x_load(a, next_role, next_tile, xop, bar_ld);
   {
@@ -562,6 +569,7 @@ __device__ __forceinline__ void sa_fwd_tile(WgCtx& c, const SaFwdArgs& a, const 
     store_p_row(c, zop, p, true);         // P reuses Z's bytes: every chunk of my row is rewritten
   }
   wg_sync_for_mma(c);
+  FSTAMP(5);
   // ---- context: C_h = P_h V_h -----------------------------------------------------------------------------------
   if (c.wt == 0) {
 #pragma unroll
@@ -573,12 +581,14 @@ __device__ __forceinline__ void sa_fwd_tile(WgCtx& c, const SaFwdArgs& a, const 
     if (R.p_tiles) { bulk_s2g(static_cast<uint8_t*>(R.p_tiles) + size_t(tile) * (2 * kPHalf), zop, 2 * kPHalf); bulk_commit(); }
   }
   wg_wait_mma(c);
+  FSTAMP(6);
   // ---- LayerNorm + ReLU (multimodal_model.py:65-66) -> bf16 image row ------------------------------------------
   {
     float mean, rstd;
     ln_stats_tmem<C::DV>(c, C::COL_C, mean, rstd);
     if (R.ln_stats) R.ln_stats[size_t(tile) * 128 + c.rs] = make_float2(mean, rstd);
     uint8_t* dst = static_cast<uint8_t*>(R.out_tiles) + size_t(tile) * kSaTileBytes + row_off(c.rs);
+    const float nmr = -mean * rstd;      // xhat = x rstd - mean rstd: one FMA per element
 #pragma unroll
     for (int c0 = 0; c0 < C::DV; c0 += 16) {
       uint32_t r[16];
@@ -587,17 +597,21 @@ __device__ __forceinline__ void sa_fwd_tile(WgCtx& c, const SaFwdArgs& a, const 
       float o[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e)
-        o[e] = fmaxf(fmaf((__uint_as_float(r[e]) - mean) * rstd, ln_s[c0 + e], ln_s[96 + c0 + e]), 0.f);
+        o[e] = fmaxf(fmaf(fmaf(__uint_as_float(r[e]), rstd, nmr), ln_s[c0 + e], ln_s[96 + c0 + e]), 0.f);
       const float lo[8] = {o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]};
       const float hi[8] = {o[8], o[9], o[10], o[11], o[12], o[13], o[14], o[15]};
       *reinterpret_cast<uint4*>(dst + uint32_t(c0 >> 3) * kCS) = pack_bf16x8(lo);
       *reinterpret_cast<uint4*>(dst + uint32_t((c0 >> 3) + 1) * kCS) = pack_bf16x8(hi);
     }
   }
+  FSTAMP(7);
   if (c.wt == 0 && R.v_tiles) bulk_wait_read();   // the V / P stores have read their buffers
+  FSTAMP(8);
   tc_fence_before_sync();
   named_bar_sync(1 + c.wg, kWgThreads);   // TMEM columns and operand buffers are reused by the next tile
   tc_fence_after_sync();
+  FSTAMP(9);
+#undef FSTAMP
 }
 
 __global__ void __launch_bounds__(kCtaThreads, 1) sa_fwd_kernel(const SaFwdArgs a) {
@@ -637,8 +651,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) sa_fwd_kernel(const SaFwdArgs 
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++round) {
     const int role = (wg + round) & 1;
     const int next = tile + int(gridDim.x) < tiles ? tile + int(gridDim.x) : -1;
-    if (role == 0) sa_fwd_tile<SaCfg<80>>(c, a, a.role[0], sm + L::W0, bsm, ln_s, tile, &bars[3 + wg], ph_ld, next, 1);
-    else           sa_fwd_tile<SaCfg<48>>(c, a, a.role[1], sm + L::W1, bsm, ln_s + 192, tile, &bars[3 + wg], ph_ld, next, 0);
+    if (role == 0) sa_fwd_tile<SaCfg<80>>(c, a, a.role[0], sm + L::W0, bsm, ln_s, tile, &bars[3 + wg], ph_ld, next, 1, 1 + 12 * round);
+    else           sa_fwd_tile<SaCfg<48>>(c, a, a.role[1], sm + L::W1, bsm, ln_s + 192, tile, &bars[3 + wg], ph_ld, next, 0, 1 + 12 * round);
   }
   if ((tid & 127) == 0) bulk_wait_all();        // this thread's V / P stores are complete before the CTA retires
   tc_fence_before_sync();
@@ -781,6 +795,7 @@ __device__ __forceinline__ void ca_fwd_tile(WgCtx& c, const CaFwdArgs& a, int d,
     // self.drop (:719) acts on the classifier's copy only: the keep bits of my 48 concat columns, drawn once
     const uint64_t keep = a.drop.thresh ? drop_bits<C::DV>(a.drop, uint32_t(b0 + (c.rs >> 4)), cat0) : ~uint64_t(0);
     const float dscale = a.drop.thresh ? a.drop.scale : 1.0f;
+    const float nmr = -mean * rstd;
     if (a.row_out[d])
       a.row_out[d][size_t(tile) * 128 + c.rs] = make_uint4(uint32_t(keep), uint32_t(keep >> 32), __float_as_uint(mean), __float_as_uint(rstd));
 #pragma unroll
@@ -792,7 +807,7 @@ __device__ __forceinline__ void ca_fwd_tile(WgCtx& c, const CaFwdArgs& a, int d,
       float o[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e)
-        o[e] = fmaxf(fmaf((__uint_as_float(r[e]) - mean) * rstd, ln_s[c0 + e], ln_s[48 + c0 + e]), 0.f) * ((kb >> e) & 1u ? dscale : 0.f);
+        o[e] = fmaxf(fmaf(fmaf(__uint_as_float(r[e]), rstd, nmr), ln_s[c0 + e], ln_s[48 + c0 + e]), 0.f) * ((kb >> e) & 1u ? dscale : 0.f);
       const float lo[8] = {o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]};
       const float hi[8] = {o[8], o[9], o[10], o[11], o[12], o[13], o[14], o[15]};
       *reinterpret_cast<uint4*>(xq + uint32_t(c0 >> 3) * kCS + row_off(c.rs)) = pack_bf16x8(lo);

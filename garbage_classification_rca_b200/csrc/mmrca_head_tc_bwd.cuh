@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(kCaBwdThreads, 1) ca_bwd_kernel(const CaBwdArg
     //      registers between the two passes; the row sums m1 = mean(dxhat), m2 = mean(dxhat xhat) meet in shared memory.
     {
       constexpr int HC = C::DV / 2;
-      const float mean = __uint_as_float(row_cur.z), rstd = __uint_as_float(row_cur.w);
+      const float mean = __uint_as_float(row_cur.z), rstd = __uint_as_float(row_cur.w), nmr = -mean * rstd;
       uint32_t xr[HC], gr[HC];
       {
         const uint32_t tc_ = c.tmem + c.lane_base + T::C + HC * c.w, tg_ = c.tmem + c.lane_base + T::DOUT + HC * c.w;
@@ -589,7 +589,7 @@ __global__ void __launch_bounds__(kCaBwdThreads, 1) ca_bwd_kernel(const CaBwdArg
         for (int e = 0; e < 8; ++e) {
           const int k = 8 * j + e;
           const float gam = gam_s[k];
-          xh[k] = (__uint_as_float(xr[k]) - mean) * rstd;
+          xh[k] = fmaf(__uint_as_float(xr[k]), rstd, nmr);
           const float y = fmaf(xh[k], gam, bet_s[k]);
           const float mk = (keep >> k) & 1u ? dscale : 0.f;
           const float dy = y > 0.f ? __uint_as_float(gr[k]) * mk : 0.f;
@@ -878,7 +878,7 @@ __device__ __forceinline__ void sa_bwd_body(const SaBwdArgs& a, uint8_t* sm) {
     //      two passes; mean / rstd are the forward's. ---------------------------------------------------------------
     {
       constexpr int HC = DV / 2;       // 48 columns per thread
-      const float mean = st.x, rstd = st.y;
+      const float mean = st.x, rstd = st.y, nmr = -mean * rstd;
       float xh[HC], dy[HC];
       MMRCA_STAMP(4);
       {
@@ -895,7 +895,7 @@ __device__ __forceinline__ void sa_bwd_body(const SaBwdArgs& a, uint8_t* sm) {
         }
         tmem_wait_ld();
 #pragma unroll
-        for (int e = 0; e < HC; ++e) xh[e] = (__uint_as_float(raw[e]) - mean) * rstd;
+        for (int e = 0; e < HC; ++e) xh[e] = fmaf(__uint_as_float(raw[e]), rstd, nmr);
       }
       float m1a = 0.f, m1b = 0.f, m2a = 0.f, m2b = 0.f;
       const float4* g4 = reinterpret_cast<const float4*>(ln_s + HC * c.w);

@@ -7,7 +7,7 @@ from garbage_classification_rca_b200 import _native as N, functional as F
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 kern = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # 0: SA backward, 1: CA backward
 per = 16 if kern == 1 else 12
-rounds = 4 if kern == 2 else 7
+rounds = 4 if kern >= 2 else 7
 params = F.init_head_parameters("cuda", seed=0)
 step = g.HeadTrainStep(params, B, 1280, 768, reverse=True, compute=N.COMPUTE_BF16, drop_p=float(os.environ.get("DROP_P", "0.6")))
 img = torch.randn(B, 1280, device="cuda"); txt = torch.randn(B, 768, device="cuda")
@@ -20,7 +20,7 @@ step.zero_grad(); step(img, txt, lab, drop_seed=9)
 torch.cuda.synchronize()
 N.lib().mmrca_dev_set_debug(None, 0)
 d = dbg.cpu().tolist()
-t0 = d[0] if kern != 2 else d[1]
+t0 = d[0] if kern < 2 else d[1]
 print("stamps (cycles since kernel start of CTA 0):")
 vals = [v - t0 for v in d if v]
 print(vals[:1 + rounds * per + 2])
