@@ -277,10 +277,11 @@ def run_b200(args, rank, world, local_rank):
     B, K, W = args.batch, args.steps, args.warmup
     compute = N.COMPUTE_BF16 if args.compute == "bf16" else N.COMPUTE_FP32
     params = g.functional.init_head_parameters(dev, seed=0)
-    co = args.variant == "cross_only"
-    params = g.functional.init_head_parameters(dev, seed=0, cross_attention_only=co) if co else params
-    step = g.HeadTrainStep(params, B, D_IMG, D_TXT, reverse=args.variant != "ca", cross_attention_only=co, compute=compute,
-                           drop_p=args.dropout)
+    co, fo = args.variant == "cross_only", args.variant == "features_only"
+    if co or fo:
+        params = g.functional.init_head_parameters(dev, seed=0, cross_attention_only=co, features_only=fo)
+    step = g.HeadTrainStep(params, B, D_IMG, D_TXT, reverse=args.variant != "ca", cross_attention_only=co, features_only=fo,
+                           compute=compute, drop_p=args.dropout)
     dp = HeadDataParallel(step, peer=not args.nccl)
     # inputs larger than L2: rotate over NB distinct batches
     per_batch = B * (D_IMG + D_TXT) * 4
@@ -399,7 +400,7 @@ def run_b200(args, rank, world, local_rank):
         "metric": "mmrca_head_fwd_bwd_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if compute == N.COMPUTE_FP32 else "bf16", "data": "synthetic",
-        "config": {"workload": f"MM_RCA {'--reverse' if args.variant == 'rca' else 'plain cross-attention' if args.variant == 'ca' else '--reverse --cross_attention_only'} fusion head fwd+CE+bwd, batch {B}/GPU, features 1280+768, "
+        "config": {"workload": f"MM_RCA {'--reverse' if args.variant == 'rca' else 'plain cross-attention' if args.variant == 'ca' else '--reverse --cross_attention_only' if args.variant == 'cross_only' else '--features_only (fp32 kernels)'} fusion head fwd+CE+bwd, batch {B}/GPU, features 1280+768, "
                                f"4 classes, train mode with dropout p={args.dropout} (in-kernel seeded mask, new seed "
                                "every step), backbones frozen (BASELINE.json configs[1])",
                    "parallelism": f"dp{world}", "global_batch": world * B,
@@ -420,6 +421,12 @@ def run_b200(args, rank, world, local_rank):
                                        "peak_gbs": peaks["hbm_gbs"]}},
         "kernels_ms_per_step": {k: round(v, 4) for k, v in sorted(share.items(), key=lambda kv: -kv[1])},
     }
+    # the streaming kernels of the step against the HBM roof: algorithmic bytes per sample (DESIGN.md kernel table)
+    hbm_bytes = {"prep_feat": 8192 + 4608, "ce_feat": 4608}
+    out["roofline_hbm_kernels"] = {
+        k: {"achieved_gbs": hbm_bytes[k] * B / (share[k] * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
+            "frac": hbm_bytes[k] * B / (share[k] * 1e-3) / 1e9 / peaks["hbm_gbs"], "bytes_per_sample": hbm_bytes[k]}
+        for k in hbm_bytes if k in share}
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(B, args.dropout)
     emit(json.dumps(out))
@@ -600,7 +607,7 @@ def main():
     ap.add_argument("--workload", default="mmrca", choices=("mmrca", "hierarchical", "full"),
                     help="mmrca: the BASELINE.json line (default); hierarchical: the second --late_fusion head (1 GPU); full: a whole "
                          "training step with the stock backbones (BASELINE.json configs[2], use --batch 256)")
-    ap.add_argument("--variant", default="rca", choices=("rca", "ca", "cross_only"),
+    ap.add_argument("--variant", default="rca", choices=("rca", "ca", "cross_only", "features_only"),
                     help="late-fusion ablation of the mmrca workload (BASELINE.json configs[3]): --reverse (default), plain "
                          "cross-attention, --cross_attention_only")
     args = ap.parse_args()

@@ -308,7 +308,7 @@ static int check_desc(const MmrcaHeadDesc* d) {
 // features, 4 classes) without a materialised dropout mask; everything else runs on the fp32 kernels.
 static bool fused_ok(const MmrcaHeadDesc& d, const uint8_t* mask) {
   return d.compute != MMRCA_COMPUTE_FP32 && d.d_img == 1280 && d.d_txt == 768 && d.n_classes == 4 &&
-         !(d.flags & (MMRCA_FLAG_FEATURES_ONLY | MMRCA_FLAG_FEATURE_GRADS)) && mask == nullptr;
+         !(d.flags & MMRCA_FLAG_FEATURE_GRADS) && mask == nullptr;
 }
 
 // concat order: multimodal_model.py:694-716
@@ -364,9 +364,12 @@ static htc::PrepBlock make_prep_block(const MmrcaAttnParams& p, void* blob, int 
 // weights -> bf16 blobs; features -> normalised bf16 images, norms, logits = bias + fp32 feature terms
 static int launch_prep_feat(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, const float* img, const float* txt,
                             float* logits, const Workspace& w, int sms, cudaStream_t st) {
-  const bool co = d.flags & MMRCA_FLAG_CROSS_ATTENTION_ONLY;
+  const bool fo = d.flags & MMRCA_FLAG_FEATURES_ONLY, co = !fo && (d.flags & MMRCA_FLAG_CROSS_ATTENTION_ONLY);
   htc::PrepArgs a;
   memset(&a, 0, sizeof(a));
+  // --features_only (multimodal_model.py:694-699, :721-722): the attention blocks do not reach the logits; only the
+  // feature half of this kernel runs (no weight blobs), then ce_feat: two streaming kernels for forward + backward
+  if (!fo) {
   a.blk[0] = make_prep_block(p.sa_img, w.fblob[0], 80, MMRCA_SA_DKQ, MMRCA_SA_DV);
   a.blk[1] = make_prep_block(p.sa_txt, w.fblob[1], 48, MMRCA_SA_DKQ, MMRCA_SA_DV);
   a.blk[2] = make_prep_block(p.ca1, w.fblob[2], MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV);
@@ -377,11 +380,13 @@ static int launch_prep_feat(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, co
   a.src[1].bc = static_cast<uint8_t*>(w.fblob[3]) + htc::CaCfg::BZ_BYTES + htc::CaCfg::BV_BYTES;
   a.src[1].off = ca; a.src[1].w = MMRCA_CA_DV;
   a.nsrc = 2;      // (the feature sources of the classifier run in fp32: prep_feat_kernel / ce_feat_kernel)
+  }
   a.wf = p.wf; a.D = concat_width(d);
   htc::FeatArgs f;
   memset(&f, 0, sizeof(f));
-  f.src[0].feat = img; f.src[0].x_tiles = w.x_img; f.src[0].norms = w.norm_img; f.src[0].cls_off = 2 * ca;
-  f.src[1].feat = txt; f.src[1].x_tiles = w.x_txt; f.src[1].norms = w.norm_txt; f.src[1].cls_off = 2 * ca + d.d_img;
+  const int feat0 = fo ? 0 : 2 * kL * MMRCA_CA_DV;      // first concat column of the image features (:694-716)
+  f.src[0].feat = img; f.src[0].x_tiles = w.x_img; f.src[0].norms = w.norm_img; f.src[0].cls_off = feat0;
+  f.src[1].feat = txt; f.src[1].x_tiles = w.x_txt; f.src[1].norms = w.norm_txt; f.src[1].cls_off = feat0 + d.d_img;
   f.logits = logits; f.wf = p.wf; f.bf = p.bf; f.with_features = co ? 0 : 1;
   f.drop = make_drop(d); f.batch = d.batch;
   if (w.step_loss) { a.zero0 = w.gm[0]; a.nzero0 = int(w.gm_floats); a.zero1 = w.step_loss; }
@@ -399,6 +404,7 @@ static int head_forward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, 
                               float* logits, const Workspace& w, int sms, cudaStream_t st) {
   int rc;
   if ((rc = launch_prep_feat(d, p, img, txt, logits, w, sms, st))) return rc;
+  if (d.flags & MMRCA_FLAG_FEATURES_ONLY) return MMRCA_OK;
   const int tiles = (d.batch + 7) / 8;
   const int grid = min(tiles, sms);
   {
@@ -439,6 +445,7 @@ static int head_backward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p,
                                cudaStream_t st) {
   const int tiles = (d.batch + 7) / 8, D = concat_width(d), ca = kL * MMRCA_CA_DV;
   int rc;
+  if (d.flags & MMRCA_FLAG_FEATURES_ONLY) return MMRCA_OK;      // ce_feat has done everything there is to do
   if (!w.step_loss) MMRCA_CUDA(cudaMemsetAsync(w.gm[0], 0, w.gm_floats * sizeof(float), st));
   {
     htc::CaBwdArgs a;
@@ -523,7 +530,7 @@ static int launch_ce_feat(const MmrcaHeadDesc& d, const float* logits, const int
   a.drop = make_drop(d);
   if (!co && g.wf) {
     a.x_img = w.x_img; a.x_txt = w.x_txt; a.g_wf = g.wf;
-    a.off_img = 2 * kL * MMRCA_CA_DV; a.off_txt = a.off_img + d.d_img;
+    a.off_img = (d.flags & MMRCA_FLAG_FEATURES_ONLY) ? 0 : 2 * kL * MMRCA_CA_DV; a.off_txt = a.off_img + d.d_img;
   }
   {
     const int tiles = (d.batch + 7) / 8;

@@ -58,7 +58,8 @@ extern "C" {
 #define MMRCA_COMPUTE_BF16 1 /* bf16 tcgen05 tensor-core pipeline, fp32 accumulate: the 2e-2-absolute contract.
                                 Covers the reference's literal shapes (1280 / 768 features, 4 classes) with frozen
                                 features and seeded dropout (MmrcaHeadDesc.drop_p / drop_seed); a caller-supplied
-                                drop_mask, feature gradients, other widths and features_only run the fp32 kernels. */
+                                drop_mask, feature gradients and other widths run the fp32 kernels; features_only is two
+                                streaming kernels (normalise + fp32 classifier, then cross-entropy + dWf). */
 #define MMRCA_COMPUTE_BF16_FUSED 2 /* alias of MMRCA_COMPUTE_BF16 (kept for ABI v1 callers) */
 
 /* mmrca_query() selectors */

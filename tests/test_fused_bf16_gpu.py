@@ -89,7 +89,8 @@ def test_fused_sa_images_and_logits(pkg, B, qk_gain):
 
 
 @pytest.mark.parametrize("flags", [(True, False, False), (False, False, False), (True, False, True),
-                                   (False, False, True)], ids=["rca", "ca", "rca_cross_only", "ca_cross_only"])
+                                   (False, False, True), (True, True, False)],
+                         ids=["rca", "ca", "rca_cross_only", "ca_cross_only", "features_only"])
 def test_fused_logits_switches(pkg, flags):
     rev, fo, co = flags
     B = 333
@@ -245,3 +246,40 @@ def test_seeded_dropout_fp32_kernels_match_oracle(pkg):
     scale = max(np.abs(v).max() for v in ref["grads"].values())
     for n, t in zip(names, params):
         assert_grad_close(n, t.grad.cpu().numpy(), ref["grads"][n], GRAD_REL_FP32_TIGHT, scale)
+
+
+@pytest.mark.parametrize("B,drop_p", [(1, 0.0), (61, 0.6), (4096, 0.6)])
+def test_fused_features_only_train_step(pkg, B, drop_p):
+    """--features_only through the bf16 build: two streaming kernels (prep_feat: normalise + fp32 classifier terms;
+    ce_feat: cross-entropy + dWf from the bf16 feature images).  Logits are fp32 arithmetic: the 1e-4-relative contract;
+    dWf sees bf16-rounded features: 1e-2 of its largest entry.  The attention blocks stay outside the graph (reference
+    multimodal_model.py:694-699): their gradients are untouched."""
+    from garbage_classification_rca_b200 import _native as N
+    from garbage_classification_rca_b200 import functional as F
+    p = orc.init_head_params(features_only=True, seed=9)
+    img, txt, labels = make_inputs(B, 9)
+    names = pkg.head_param_names(True, False)
+    cw = torch.tensor([0.8, 1.3, 1.0, 0.9])
+    step = pkg.HeadTrainStep([p[n].cuda() for n in names], B, 1280, 768, reverse=True, features_only=True,
+                             class_weight=cw.cuda(), label_smoothing=0.1, compute=N.COMPUTE_BF16, drop_p=drop_p)
+    step.zero_grad()
+    N.kernel_launches(reset=True)
+    loss, logits = step(img.cuda(), txt.cuda(), labels.cuda(), drop_seed=5)
+    torch.cuda.synchronize()
+    assert N.kernel_launches() == 2
+    mask, scale = None, 1.0
+    if drop_p > 0:
+        mask = F.dropout_mask(5, drop_p, B, 2048, "cuda").cpu().numpy()
+        scale = 1.0 / (1.0 - drop_p)
+    ref = orc.np_head_forward_backward(p, img.numpy(), txt.numpy(), True, True, False, labels=labels.numpy(),
+                                       class_weight=cw.numpy(), label_smoothing=0.1, drop_mask=mask, drop_scale=scale)
+    lg = logits.cpu().numpy()
+    assert np.abs(lg - ref["logits"]).max() <= 1e-4 * np.abs(ref["logits"]).max()
+    assert abs(loss.item() - ref["loss"]) < 1e-4
+    for n, v in zip(names, step.grads.views):
+        g = v.cpu().numpy()
+        if n.startswith("final_features_only_linear"):
+            r = ref["grads"][n]
+            assert np.abs(g - r).max() <= 1e-2 * np.abs(r).max() + 1e-9, n
+        else:
+            assert np.abs(g).max() == 0.0, n
