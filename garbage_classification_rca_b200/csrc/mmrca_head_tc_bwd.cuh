@@ -2,7 +2,9 @@
 //
 // Backward of CVPR_code/multimodal_model.py:661-728 + CrossEntropyLoss (main_both.py:87-93,110-112), in the
 // algebra of mmrca_head_tc.cuh (Z = Xq M + u replaces Q and K).  Per attention block and 128-row tile:
-//   recompute   Z, V, S, P, C                    (nothing but the block inputs is read back from HBM)
+//   forward     CA: Z, V, S, P, C are recomputed on chip (only the block inputs, the dropout keep bits and the LayerNorm
+//               statistics are read back; reloading Z / V / P was measured slower);
+//               SA: V, P and the LayerNorm statistics are the forward's (TMA, a tile ahead), C = P V is one MMA
 //   LayerNorm   dy = dOut [y > 0],  dC = rstd (dy g - mean(dy g) - xhat mean(dy g xhat))
 //   attention   dP = dC V^T,  dV = P^T dC,  dS = softmax'(dP),  dZ = dS Xkv
 //   inputs      dXq = dZ M^T,  dXkv = dS^T Z + dV Wv            (CA blocks: they feed the SA backward)
@@ -11,11 +13,11 @@
 //                                        chunk diagonal.  The rows of the feature sources: ce_feat_kernel, fp32)
 //               [dgamma | dbeta] += [dy xhat | dy]^T 1
 // Every contraction, including the reductions over the batch, is a tcgen05.mma.  The parameter gradients stay in
-// TMEM for the whole persistent CTA and are flushed once at the end with lane-coalesced atomics; dW_query,
-// dW_key, db_query follow from dM, du in finalize_kernel (dM = Wq^T dWk-ish products of size d_in^2, once per step).
+// TMEM for the whole persistent CTA and are flushed once at the end with lane-coalesced red.global; dW_query,
+// dW_key, db_query follow from dM, du in finalize_kernel (products of size d_in^2, once per step).
 // A CTA owns one tile at a time; its two warpgroups own the same rows and split the columns / the kinds of
-// operand they emit, so the per-row scalars (softmax, LayerNorm statistics) are computed redundantly instead of
-// being exchanged.
+// operand they emit.  The CA backward has a ninth warp that requests the next tile's images and issues the
+// persistent dM / dWv MMAs (tcgen05.mma issue blocks while the tensor queue is full).
 #pragma once
 #include "mmrca_head_tc.cuh"
 

@@ -294,3 +294,40 @@ def test_module_drop_in_with_stub_backbones(pkg):
     loss.backward()
     assert m.final_with_everything.weight.grad is not None and m.cross_attention_1.W_value.weight.grad is not None
     assert m.image_to_hidden_size.weight.grad is None   # dead parameters stay outside the graph
+
+
+def _peer_allreduce_worker(rank, world, port, out):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", device_id=dev)
+    from garbage_classification_rca_b200.training import PeerAllReduce, allreduce_mean_
+    n = 94824
+    ar = PeerAllReduce(n, dev)
+    worst = 0.0
+    for it in range(6):
+        g = torch.Generator(device=dev).manual_seed(100 * it + rank)
+        x = torch.randn(n, device=dev, generator=g)
+        ref = allreduce_mean_(x.clone())
+        got = ar(x.clone())
+        worst = max(worst, (got - ref).abs().max().item())
+        chk = got.clone()
+        dist.broadcast(chk, 0)
+        assert torch.equal(chk, got)          # bit-identical on every rank
+    out[rank] = worst
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs with NVLink peer access")
+def test_peer_memory_allreduce_matches_nccl(pkg):
+    """The one collective of a data-parallel step as the one-shot NVLink peer-memory kernel
+    (mmrca_peer_allreduce_mean) against NCCL; skipped on a single-GPU box (tools/check_peer_allreduce.py
+    runs the same check under torchrun at 2 and 8 GPUs)."""
+    import torch.multiprocessing as mp
+    world = 2
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_peer_allreduce_worker, args=(world, 29631, out), nprocs=world, join=True)
+        assert len(out) == world and max(out.values()) <= 1e-6
