@@ -37,8 +37,8 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float (&f)[8]) {
 //   db_f[c]          += sum_b dlogits[b][c]
 //   dWf[c][off + j]  += sum_b dlogits[b][c] drop(xn[b][j])               (feature sources of the concat, fp32 FMAs)
 // grid = (column strips, sample slices).  A strip is one 8-column group kc of one modality's X image (10 image +
-// 6 text strips): for a tile it is 2 KB of contiguous bf16, one 16-byte row per thread.  A slice is 32 tiles = 256
-// samples = one cross-entropy evaluation per thread.  Thread (row r) accumulates the 4 x 8 products of its chunk
+// 6 text strips): for a tile it is 2 KB of contiguous bf16, one 16-byte row per thread.  A slice is 16 tiles = 128
+// samples = one cross-entropy evaluation per thread of the first four warps.  Thread (row r) accumulates the 4 x 8 products of its chunk
 // r % 16 over the slice's tiles in registers; the 16 threads that share a chunk meet in shared memory and leave
 // with one 16-byte atomic per class.  Every CTA recomputes the normaliser sum_b w[y_b] from the labels, so
 // dlogits leave normalised in one pass.  labels == null: dlogits are given (autograd backward).
@@ -53,7 +53,7 @@ struct CeFeatArgs {
   int off_img, off_txt;                           // first concat column of each feature source
   DropSpec drop;      // drop.D = D
 };
-constexpr int kCeSliceTiles = 32;
+constexpr int kCeSliceTiles = 16;      // 128 samples per slice: 10 + 6 strips x 32 slices = 512 CTAs at batch 4096
 constexpr int kStripsImg = 80 / 8, kStripsTxt = 48 / 8;
 
 __global__ void __launch_bounds__(256) ce_feat_kernel(const CeFeatArgs a) {
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) ce_feat_kernel(const CeFeatArgs a) {
   {
     const int b = tile0 * 8 + tid;
     float d[4] = {0.f, 0.f, 0.f, 0.f}, li = 0.f;
-    if (b < a.batch) {
+    if (tid < kCeSliceTiles * 8 && b < a.batch) {      // the slice's samples: one per thread of the first warps
       if (ce) {
         const float inv_den = 1.0f / den;
         float wc[4] = {1.f, 1.f, 1.f, 1.f};
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) ce_feat_kernel(const CeFeatArgs a) {
         d[0] = dd.x; d[1] = dd.y; d[2] = dd.z; d[3] = dd.w;
       }
     }
-    dl_s[tid] = make_float4(d[0], d[1], d[2], d[3]);
+    if (tid < kCeSliceTiles * 8) dl_s[tid] = make_float4(d[0], d[1], d[2], d[3]);
     if (strip == 0) {       // the strips of a slice share its samples: one of them owns the loss and the bias gradient
       li = warp_sum(li);
 #pragma unroll
