@@ -331,3 +331,28 @@ def test_peer_memory_allreduce_matches_nccl(pkg):
         out = m.dict()
         mp.spawn(_peer_allreduce_worker, args=(world, 29631, out), nprocs=world, join=True)
         assert len(out) == world and max(out.values()) <= 1e-6
+
+
+def test_module_with_stock_backbones_cfg1(pkg):
+    """BASELINE.json configs[0] through the drop-in module with the real (random-init, no network) stock backbones:
+    EfficientNetV2-M feature extractor + DistilBERT, batch 8, 3x384x384 images, 128-token text, eval forward.  The
+    head's logits are checked against the oracle on the features the module's own backbones produced."""
+    import io
+    from contextlib import redirect_stdout
+    from garbage_classification_rca_b200 import multimodal_model as M
+    torch.manual_seed(0)
+    with redirect_stdout(io.StringIO()):
+        m = M.MM_RCA(4, 0.6, 0.0, 0.7, 256, "distilbert", 8, True, False, False, pretrained=False)
+    m = m.cuda().eval()
+    images = torch.randn(8, 3, 384, 384, device="cuda")
+    ids = torch.randint(0, 30522, (8, 128), device="cuda")
+    mask = torch.ones_like(ids)
+    with torch.no_grad():
+        out = m(ids, mask, images, eval=True)
+        m._images, m._input_ids, m._attention_mask = images, ids, mask
+        _, txt, (_, _, img) = m._backbone_features()
+    assert out.shape == (8, 4) and torch.isfinite(out).all()
+    assert img.shape == (8, 1280) and txt.shape == (8, 768)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items() if not k.startswith(("image_model.", "text_model."))}
+    ref = orc.head_forward(sd, img.float().cpu(), txt.float().cpu(), True)
+    assert rel_err(out.cpu().numpy(), ref.numpy()) < LOGITS_REL_FP32
