@@ -175,3 +175,30 @@ def test_hier_init_scale_relu_boundary(pkg):
         a, r = t.grad.cpu().double().numpy().ravel(), rg[n].numpy().ravel()
         assert np.corrcoef(a, r)[0, 1] >= 0.995, n
         assert np.linalg.norm(a - r) <= 0.10 * np.linalg.norm(r), n
+
+
+def test_hier_module_with_stock_backbones(pkg):
+    """Hierarchical through the real (random-init) EfficientNetV2-M at 480 x 480 (30 x 30 and 15 x 15 stage maps, the
+    pool sizes the reference assumes) and DistilBERT with hidden states: eval forward against the oracle on the
+    features the module's own backbones produced."""
+    import io
+    from contextlib import redirect_stdout
+    from garbage_classification_rca_b200 import multimodal_model as M
+    torch.manual_seed(0)
+    with redirect_stdout(io.StringIO()):
+        m = M.Hierarchical(4, 0.6, 0.0, 0.7, 256, "distilbert", 2, True, False, False, pretrained=False)
+    m = m.cuda().eval()
+    images = torch.randn(2, 3, 480, 480, device="cuda")
+    ids = torch.randint(0, 30522, (2, 64), device="cuda")
+    mask = torch.ones_like(ids)
+    with torch.no_grad():
+        out = m(ids, mask, images, eval=True)
+        m._images, m._input_ids, m._attention_mask = images, ids, mask
+        text_output, txt, (s3, s6, img) = m._backbone_features(True)
+        hs = text_output.hidden_states
+        feats = (img, torch.nn.functional.avg_pool2d(s3, 7, 7).flatten(1), torch.nn.functional.avg_pool2d(s6, 6, 6).flatten(1),
+                 txt, hs[2][:, 0, :], hs[4][:, 0, :])
+    assert [tuple(f.shape) for f in feats] == [(2, w) for w in pkg.functional.HIER_SEGMENTS]
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items() if k.startswith("final_hierarchical")}
+    ref = orc.hier_forward(sd, [f.float().cpu() for f in feats[:3]], [f.float().cpu() for f in feats[3:]])
+    assert (out.cpu() - ref).abs().max().item() <= LOGITS_ABS_BF16
