@@ -263,6 +263,66 @@ def cpu_baseline(batch, dropout, budget_s=12.0, max_steps=400):
             "sample": f"{n} fwd+CE+bwd steps of batch {batch} ({dt:.1f} s) of the torch-CPU oracle port"}
 
 
+def gpu_eager_baseline(batch, dropout, steps, warmup, dev):
+    """The "existing Blackwell path" (SURVEY.md §2.2 / §8 d): the reference's own torch ops for this path - the oracle
+    restatement, op for op what MM_RCA.forward + CrossEntropyLoss + backward() launch - run by PyTorch eager on the same
+    B200, fp32 and under bf16 autocast, same batch / steps / warm-up, CUDA-event timed, inputs resident in HBM."""
+    import torch
+    from oracle import mmrca_oracle as orc
+    p = {k: v.to(dev) for k, v in orc.init_head_params(seed=0).items()}
+    img, txt, lab = synth_batches(2, batch, 0)
+    img, txt, lab = img.to(dev), txt.to(dev), lab.to(dev)
+    dm, ds = cpu_drop_mask(batch, dropout)
+    dm = dm.to(dev) if dm is not None else None
+    out = {}
+    for name, ctx in (("fp32", None), ("bf16_autocast", torch.bfloat16)):
+        def step(i):
+            pp = {k: v.detach().requires_grad_(True) for k, v in p.items()}
+            with torch.autocast("cuda", dtype=ctx, enabled=ctx is not None):
+                logits = orc.head_forward(pp, img[i % 2], txt[i % 2], True, False, False, dm, ds)
+            orc.cross_entropy(logits.float(), lab[i % 2]).backward()
+        for i in range(max(warmup, 3)):
+            step(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[name] = {"value": batch / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms}
+    out["what"] = ("PyTorch eager (torch %s) running the reference's op sequence for this path on the same GPU; fixed dropout "
+                   "mask; %d steps after warm-up, CUDA events" % (torch.__version__, steps))
+    return out
+
+
+def collective_check(dp, step, dev, world):
+    """N > 1, untimed: the same gradient bucket reduced through NCCL and through the one-shot peer-memory kernel
+    (mmrca_peer_allreduce_mean): largest difference, and whether every rank ends with bit-identical bytes."""
+    import torch
+    import torch.distributed as dist
+    if dp.peer is None:
+        return {"skipped": "peer all-reduce not in use (%s)" % dp.collective}
+    src = step.grads.flat.clone()
+    src.add_(torch.arange(src.numel(), device=dev, dtype=torch.float32).mul_(1e-7 * (1 + dist.get_rank())))
+    a, b = src.clone(), src.clone()
+    dist.all_reduce(a, op=dist.ReduceOp.SUM)
+    a.div_(world)
+    dp.peer(b)
+    torch.cuda.synchronize()
+    err = (a - b).abs().max()
+    ref = a.abs().max()
+    bits = b.view(torch.int32).to(torch.int64)
+    h = torch.stack([bits.sum(), (bits * torch.arange(1, bits.numel() + 1, device=dev)).sum()])
+    hmax, hmin = h.clone(), h.clone()
+    dist.all_reduce(hmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(hmin, op=dist.ReduceOp.MIN)
+    dist.all_reduce(err, op=dist.ReduceOp.MAX)
+    return {"max_abs_err": float(err), "max_abs_ref": float(ref), "bit_identical_across_ranks": bool((hmax == hmin).all()),
+            "bucket_floats": int(src.numel()), "against": "NCCL all_reduce(sum) / world"}
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -301,6 +361,7 @@ def run_b200(args, rank, world, local_rank):
     # ---- value: device-resident inputs -------------------------------------------------------------
     for i in range(W):
         device_step(i)
+    coll = collective_check(dp, step, dev, world) if world > 1 else None
     sampler = make_clock_sampler(local_rank) if rank == 0 else None
     if rank == 0:
         sampler.start()
@@ -427,7 +488,10 @@ def run_b200(args, rank, world, local_rank):
         k: {"achieved_gbs": hbm_bytes[k] * B / (share[k] * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
             "frac": hbm_bytes[k] * B / (share[k] * 1e-3) / 1e9 / peaks["hbm_gbs"], "bytes_per_sample": hbm_bytes[k]}
         for k in hbm_bytes if k in share}
+    if coll is not None:
+        out["collective_check"] = coll
     if world == 1 and not args.no_cpu_baseline:
+        out["gpu_eager_baseline"] = gpu_eager_baseline(B, args.dropout, K, W, dev)
         out["cpu_baseline"] = cpu_baseline(B, args.dropout)
     emit(json.dumps(out))
     if world > 1:

@@ -16,17 +16,20 @@ CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libmmrca.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
 
+# -cudart shared: the library uses the process's libcudart.so.12 (the one torch has loaded) instead of embedding a
+# second, static CUDA runtime with its whole symbol table
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-shared", "-Xcompiler", "-fPIC", "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
 SOURCES = ["mmrca_capi.cu"]
 
 # mmrca.h constants
 FLAG_REVERSE, FLAG_FEATURES_ONLY, FLAG_CROSS_ATTENTION_ONLY = 1, 2, 4
 FLAG_FEATURE_GRADS = 256
+FLAG_TRAINING = 512
 COMPUTE_FP32, COMPUTE_BF16, COMPUTE_BF16_FUSED = 0, 1, 2
 WS_TEXT_SA_IMAGE, WS_IMAGE_SA_IMAGE = 0, 1
 QUERY_ABI_VERSION, QUERY_DEVICE_OK, QUERY_SM_COUNT, QUERY_KERNEL_LAUNCHES, QUERY_RESET_LAUNCHES, QUERY_HAS_BF16 = range(6)
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _fp = C.c_void_p  # device pointers travel as integers
 

@@ -4,6 +4,7 @@
 #include "../../include/mmrca.h"
 
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdio.h>
 #include <string.h>
 
@@ -20,8 +21,8 @@ namespace mmrca {
 
 static thread_local char g_err[512] = "";
 static thread_local int g_launches = 0;
-static long long* g_dbg = nullptr;
-static int g_dbg_kernel = 0;         // 0: sa_bwd, 1: ca_bwd, 2: ca_fwd, 3: sa_fwd   // development: device buffer for per-phase clock stamps (mmrca_dev_set_debug)
+static thread_local long long* g_dbg = nullptr;   // development aid, per calling thread (mmrca_dev_set_debug)
+static thread_local int g_dbg_kernel = 0;         // 0: sa_bwd, 1: ca_bwd, 2: ca_fwd, 3: sa_fwd   // development: device buffer for per-phase clock stamps (mmrca_dev_set_debug)
 
 // ---- optional per-kernel timing (mmrca_timing_begin / _end) -------------------------------------
 struct TimingRec { const char* name; cudaEvent_t e0, e1; };
@@ -57,22 +58,24 @@ static size_t align_up_256(size_t v) { return (v + 255) & ~size_t(255); }
 struct DeviceInfo { int ok; int sms; };
 
 static int device_info(DeviceInfo* out) {
-  static DeviceInfo cache[64];
-  static bool have[64];
+  // one packed word per device, published with release / read with acquire: concurrent first calls from several
+  // threads (nn.DataParallel) compute the same value and store it atomically
+  static std::atomic<uint32_t> cache[64];       // bit 31: valid, bit 30: ok, low bits: SM count
   int dev = -1;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
     cudaGetLastError();
     return fail(MMRCA_ERR_NO_DEVICE, "no CUDA device: the MM-RCA head has no CPU fallback%s%s");
   }
-  if (!have[dev]) {
+  uint32_t word = cache[dev].load(std::memory_order_acquire);
+  if (!(word & 0x80000000u)) {
     int major = 0, sms = 0;
     cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cache[dev].ok = (major == 10);
-    cache[dev].sms = sms;
-    have[dev] = true;
+    word = 0x80000000u | (major == 10 ? 0x40000000u : 0u) | (uint32_t(sms) & 0xffffu);
+    cache[dev].store(word, std::memory_order_release);
   }
-  *out = cache[dev];
+  out->ok = (word & 0x40000000u) ? 1 : 0;
+  out->sms = int(word & 0xffffu);
   if (!out->ok) return fail(MMRCA_ERR_NO_DEVICE, "device is not compute capability 10.x (sm_100a kernels only)%s%s");
   return MMRCA_OK;
 }
@@ -242,18 +245,28 @@ static DropSpec make_drop(const MmrcaHeadDesc& d) {
   return s;
 }
 
+// The bf16 tensor-core pipeline covers the reference's literal dimensions (multimodal_model.py:249-258: 1280 / 768
+// features, 4 classes) with frozen features; every other desc runs on the fp32 kernels (never on the CPU).  A pure
+// function of the desc: it also decides which buffers the workspace holds.
+static bool desc_is_tc(const MmrcaHeadDesc& d) {
+  return d.compute != MMRCA_COMPUTE_FP32 && d.d_img == 1280 && d.d_txt == 768 && d.n_classes == 4 &&
+         !(d.flags & MMRCA_FLAG_FEATURE_GRADS);
+}
+
 static Workspace carve(const MmrcaHeadDesc& d, bool training, void* base) {
   Workspace w;
   memset(&w, 0, sizeof(w));
   char* p = static_cast<char*>(base);
   size_t off = 0;
   const size_t B = size_t(d.batch > 0 ? d.batch : 0);
+  const bool tc = desc_is_tc(d);
   auto take = [&](size_t floats) { float* r = reinterpret_cast<float*>(p + off); off += align_up(floats * 4); return r; };
   w.norm_img = take(B); w.norm_txt = take(B);
-  w.t_sa = take(B * kL * MMRCA_SA_DV); w.i_sa = take(B * kL * MMRCA_SA_DV);
-  w.t_i = take(B * kL * MMRCA_CA_DV); w.i_t = take(B * kL * MMRCA_CA_DV);
-  if (d.drop_p > 0.f) w.mask = reinterpret_cast<uint8_t*>(take((B * size_t(concat_width(d)) + 3) / 4));
-  if (d.compute != MMRCA_COMPUTE_FP32) {
+  if (!tc) {      // fp32 SIMT kernels: block outputs in fp32 rows, a materialised dropout mask
+    w.t_sa = take(B * kL * MMRCA_SA_DV); w.i_sa = take(B * kL * MMRCA_SA_DV);
+    w.t_i = take(B * kL * MMRCA_CA_DV); w.i_t = take(B * kL * MMRCA_CA_DV);
+    if (d.drop_p > 0.f) w.mask = reinterpret_cast<uint8_t*>(take((B * size_t(concat_width(d)) + 3) / 4));
+  } else {        // bf16 pipeline: weight blobs and operand images
     const size_t tiles = (B + 7) / 8;
     w.fblob[0] = take(htc::SaCfg<80>::W_BYTES / 4);
     w.fblob[1] = take(htc::SaCfg<48>::W_BYTES / 4);
@@ -265,11 +278,12 @@ static Workspace carve(const MmrcaHeadDesc& d, bool training, void* base) {
     w.x_txt = take(tiles * htc::x_tile_bytes(48) / 4);
   }
   if (training) {
-    w.d_t_sa = take(B * kL * MMRCA_SA_DV); w.d_i_sa = take(B * kL * MMRCA_SA_DV);
-    w.d_t_i = take(B * kL * MMRCA_CA_DV); w.d_i_t = take(B * kL * MMRCA_CA_DV);
-    w.dy = take(B * kL * (2 * MMRCA_SA_DKQ + MMRCA_SA_DV));
     w.dlogits = take(B * size_t(d.n_classes > 0 ? d.n_classes : 0));
-    if (d.compute != MMRCA_COMPUTE_FP32) {
+    if (!tc) {
+      w.d_t_sa = take(B * kL * MMRCA_SA_DV); w.d_i_sa = take(B * kL * MMRCA_SA_DV);
+      w.d_t_i = take(B * kL * MMRCA_CA_DV); w.d_i_t = take(B * kL * MMRCA_CA_DV);
+      w.dy = take(B * kL * (2 * MMRCA_SA_DKQ + MMRCA_SA_DV));
+    } else {
       const size_t tiles = (B + 7) / 8;
       for (int i = 0; i < 4; ++i) w.dx_img[i] = take(tiles * htc::kSaTileBytes / 4);
       for (int i = 0; i < 2; ++i) w.ca_row[i] = reinterpret_cast<uint4*>(take(tiles * (128 * 16 / 4)));
@@ -304,11 +318,12 @@ static int check_desc(const MmrcaHeadDesc* d) {
   return MMRCA_OK;
 }
 
-// The fused bf16 pipeline covers the reference's literal dimensions (multimodal_model.py:249-258: 1280 / 768
-// features, 4 classes) without a materialised dropout mask; everything else runs on the fp32 kernels.
-static bool fused_ok(const MmrcaHeadDesc& d, const uint8_t* mask) {
-  return d.compute != MMRCA_COMPUTE_FP32 && d.d_img == 1280 && d.d_txt == 768 && d.n_classes == 4 &&
-         !(d.flags & MMRCA_FLAG_FEATURE_GRADS) && mask == nullptr;
+// a caller-drawn dropout mask exists for parity with torch's Philox stream: fp32 kernels only
+static int check_mask(const MmrcaHeadDesc& d, const uint8_t* mask) {
+  if (mask && desc_is_tc(d))
+    return fail(MMRCA_ERR_INVALID, "a caller-supplied drop_mask needs compute = MMRCA_COMPUTE_FP32 (the bf16 pipeline draws "
+                                   "its seeded mask on chip: desc.drop_p / drop_seed)%s%s");
+  return MMRCA_OK;
 }
 
 // concat order: multimodal_model.py:694-716
@@ -521,7 +536,8 @@ static int head_backward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p,
 static int launch_ce_feat(const MmrcaHeadDesc& d, const float* logits, const int64_t* labels, const MmrcaCeDesc* ce,
                           float* loss, float* dlogits, const MmrcaHeadGrads& g, bool bias_grad, const Workspace& w,
                           cudaStream_t st) {
-  const bool co = d.flags & MMRCA_FLAG_CROSS_ATTENTION_ONLY;
+  // the reference's if / elif gives features_only precedence over cross_attention_only (multimodal_model.py:694-726)
+  const bool fo = d.flags & MMRCA_FLAG_FEATURES_ONLY, co = !fo && (d.flags & MMRCA_FLAG_CROSS_ATTENTION_ONLY);
   if (labels && !w.step_loss) MMRCA_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
   htc::CeFeatArgs a;
   memset(&a, 0, sizeof(a));
@@ -530,7 +546,7 @@ static int launch_ce_feat(const MmrcaHeadDesc& d, const float* logits, const int
   a.drop = make_drop(d);
   if (!co && g.wf) {
     a.x_img = w.x_img; a.x_txt = w.x_txt; a.g_wf = g.wf;
-    a.off_img = (d.flags & MMRCA_FLAG_FEATURES_ONLY) ? 0 : 2 * kL * MMRCA_CA_DV; a.off_txt = a.off_img + d.d_img;
+    a.off_img = fo ? 0 : 2 * kL * MMRCA_CA_DV; a.off_txt = a.off_img + d.d_img;
   }
   {
     const int tiles = (d.batch + 7) / 8;
@@ -549,7 +565,8 @@ static int head_forward_impl(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, c
   const int rev = (d.flags & MMRCA_FLAG_REVERSE) ? 1 : 0;
   int rc;
   if (d.batch == 0) return MMRCA_OK;
-  if (fused_ok(d, mask)) return head_forward_fused(d, p, img, txt, logits, w, sms, st);
+  if ((rc = check_mask(d, mask))) return rc;
+  if (desc_is_tc(d)) return head_forward_fused(d, p, img, txt, logits, w, sms, st);
   if (!mask && d.drop_p > 0.f) {      // seeded dropout: the fp32 kernels read the materialised mask
     const DropSpec ds = make_drop(d);
     {
@@ -594,7 +611,8 @@ static int head_backward_impl(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, 
   if (d.batch == 0) return MMRCA_OK;
   if (want_feat && !(d_img && d_txt))
     return fail(MMRCA_ERR_INVALID, "d_img_feat and d_txt_feat must both be given or both be NULL%s%s");
-  if (fused_ok(d, mask)) {
+  if ((rc = check_mask(d, mask))) return rc;
+  if (desc_is_tc(d)) {
     if (want_feat)
       return fail(MMRCA_ERR_INVALID, "feature gradients need MMRCA_FLAG_FEATURE_GRADS in the desc of the forward AND "
                                      "the backward (the bf16 pipeline keeps parameter gradients only)%s%s");
@@ -857,12 +875,12 @@ int mmrca_head_forward(const MmrcaHeadDesc* desc, const MmrcaHeadParams* params,
     return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
   DeviceInfo di;
   if ((rc = device_info(&di))) return rc;
-  Workspace w = carve(*desc, false, workspace);
-  if (workspace_bytes < w.bytes) return fail(MMRCA_ERR_WORKSPACE, "workspace too small%s%s");
-  {   // a training-size workspace announces a backward: the forward then keeps what the backward reloads
-    const Workspace wt = carve(*desc, true, workspace);
-    if (workspace_bytes >= wt.bytes) w = wt;
-  }
+  // MMRCA_FLAG_TRAINING: a backward will follow, the forward keeps what it reloads (training-size workspace)
+  const bool training = (desc->flags & MMRCA_FLAG_TRAINING) != 0;
+  Workspace w = carve(*desc, training, workspace);
+  if (workspace_bytes < w.bytes)
+    return fail(MMRCA_ERR_WORKSPACE, training ? "workspace too small (MMRCA_FLAG_TRAINING needs the training size)%s%s"
+                                              : "workspace too small%s%s");
   return head_forward_impl(*desc, *params, img_feat, txt_feat, drop_mask, drop_scale, logits, w, di.sms,
                            static_cast<cudaStream_t>(stream));
 }
@@ -906,10 +924,10 @@ int mmrca_head_train_step(const MmrcaHeadDesc* desc, const MmrcaHeadParams* para
   Workspace w = carve(*desc, true, workspace);
   if (workspace_bytes < w.bytes) return fail(MMRCA_ERR_WORKSPACE, "workspace too small (training size needed)%s%s");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (fused_ok(*desc, drop_mask)) w.step_loss = loss_out;
+  if (desc_is_tc(*desc) && !drop_mask) w.step_loss = loss_out;
   if ((rc = head_forward_impl(*desc, *params, img_feat, txt_feat, drop_mask, drop_scale, logits, w, di.sms, st)))
     return rc;
-  if (fused_ok(*desc, drop_mask)) {
+  if (desc_is_tc(*desc)) {
     if ((rc = launch_ce_feat(*desc, logits, labels, ce, loss_out, w.dlogits, *grads, grads->bf != nullptr, w, st)))
       return rc;
     return head_backward_impl(*desc, *params, img_feat, txt_feat, drop_mask, drop_scale, w.dlogits, *grads, d_img_feat,

@@ -142,6 +142,39 @@ def workspace_bytes(batch: int, d_img: int, d_txt: int, n_classes: int, flags: i
     return int(N.lib().mmrca_head_workspace_bytes(C.byref(d), 1 if training else 0))
 
 
+class _WorkspacePool:
+    """Device scratch of the autograd paths, recycled instead of allocated on every forward.  A forward checks a buffer
+    out, its backward hands it back (a forward whose backward never runs simply drops its buffer)."""
+
+    def __init__(self):
+        self._free: Dict[Tuple[int, int], List[torch.Tensor]] = {}
+
+    def take(self, nbytes: int, device) -> torch.Tensor:
+        key = (torch.device(device).index or 0, int(nbytes))
+        lst = self._free.get(key)
+        if lst:
+            return lst.pop()
+        return torch.empty(max(1, nbytes), dtype=torch.uint8, device=device)
+
+    def give(self, t: torch.Tensor) -> None:
+        lst = self._free.setdefault((t.device.index or 0, t.numel()), [])
+        if len(lst) < 2:
+            lst.append(t)
+
+
+_pool = _WorkspacePool()
+
+
+def _check_mask(drop_mask: Optional[torch.Tensor], batch: int, width: int, what: str) -> Optional[torch.Tensor]:
+    if drop_mask is None:
+        return None
+    drop_mask = _check_dev(drop_mask, "dropout mask", torch.uint8)
+    if tuple(drop_mask.shape) != (batch, width):
+        raise ValueError(f"{what} dropout mask has shape {tuple(drop_mask.shape)}, expected ({batch}, {width}): "
+                         "[batch, concat width of the selected late-fusion variant]")
+    return drop_mask
+
+
 class FlatGrads:
     """One contiguous fp32 buffer holding the gradients of all head tensors (the single NCCL
     all-reduce bucket, SURVEY.md §8 e) plus per-tensor views in head_param_names order."""
@@ -153,6 +186,8 @@ class FlatGrads:
         for p in params:
             self.offsets.append(off)
             off += (p.numel() + 3) // 4 * 4
+        self.n = off            # gradient entries; flat[n : n + 4] is a spare slot (the loss denominator of a
+        off += 4                # data-parallel step rides there, training.allreduce_global_mean_)
         self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
         self.views = [self.flat[o:o + p.numel()].view(p.shape) for o, p in zip(self.offsets, params)]
 
@@ -169,18 +204,21 @@ class _HeadFunction(torch.autograd.Function):
         img = _check_dev(img, "image features")
         txt = _check_dev(txt, "text features")
         params = [_check_dev(p, "head parameter") for p in params]
-        if drop_mask is not None:
-            drop_mask = _check_dev(drop_mask, "dropout mask", torch.uint8)
         B, d_img, d_txt = img.shape[0], img.shape[1], txt.shape[1]
         if txt.shape[0] != B:
             raise ValueError("image and text feature batches differ")
+        drop_mask = _check_mask(drop_mask, B, concat_width(d_img, d_txt, bool(flags & N.FLAG_FEATURES_ONLY),
+                                                           bool(flags & N.FLAG_CROSS_ATTENTION_ONLY)), "head")
+        if drop_mask is not None:
+            compute = N.COMPUTE_FP32           # a caller-drawn mask (parity with torch's Philox stream): fp32 kernels
         needs_bwd = any(ctx.needs_input_grad)
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             flags |= N.FLAG_FEATURE_GRADS      # fine-tune phase: the backward must return feature gradients
+        if needs_bwd:
+            flags |= N.FLAG_TRAINING           # the forward keeps what the backward reloads
         desc = _desc(B, d_img, d_txt, n_classes, flags, compute, drop_p, drop_seed)
         L = N.lib()
-        ws = torch.empty(max(1, L.mmrca_head_workspace_bytes(C.byref(desc), 1 if needs_bwd else 0)),
-                         dtype=torch.uint8, device=img.device)
+        ws = _pool.take(L.mmrca_head_workspace_bytes(C.byref(desc), 1 if needs_bwd else 0), img.device)
         logits = torch.empty(B, n_classes, dtype=torch.float32, device=img.device)
         hp = _head_struct(params)
         ctx.save_for_backward(img, txt, drop_mask, ws, *params)
@@ -214,6 +252,7 @@ class _HeadFunction(torch.autograd.Function):
                     dlogits.data_ptr(), C.byref(hg), d_img.data_ptr() if want_feat else None,
                     d_txt.data_ptr() if want_feat else None, ws.data_ptr(), ws.numel(),
                     _stream_ptr(img.device)), "mmrca_head_backward")
+        _pool.give(ws)
         features_only = bool(flags & N.FLAG_FEATURES_ONLY)
         pg = []
         for i, v in enumerate(fg.views):
@@ -277,6 +316,7 @@ class HeadTrainStep:
         dev = self.params[0].device
         self.flags = make_flags(reverse, features_only, cross_attention_only) | (N.FLAG_FEATURE_GRADS if feature_grads else 0)
         self.desc = _desc(batch, d_img, d_txt, n_classes, self.flags, compute, drop_p, 0)
+        self.concat_width = concat_width(d_img, d_txt, features_only, cross_attention_only)
         self.grads = FlatGrads(self.params)
         self.hp, self.hg = _head_struct(self.params), _head_struct(self.grads.views)
         L = N.lib()
@@ -301,8 +341,10 @@ class HeadTrainStep:
         labels = _check_dev(labels, "labels", torch.int64)
         if img.shape != (self.desc.batch, self.desc.d_img) or txt.shape != (self.desc.batch, self.desc.d_txt):
             raise ValueError("feature shapes do not match the shapes this step was built for")
-        if drop_mask is not None:
-            drop_mask = _check_dev(drop_mask, "dropout mask", torch.uint8)
+        drop_mask = _check_mask(drop_mask, self.desc.batch, self.concat_width, "head")
+        if drop_mask is not None and self.desc.compute != N.COMPUTE_FP32:
+            raise ValueError("a caller-drawn dropout mask needs a step built with compute=COMPUTE_FP32 (the bf16 pipeline "
+                             "draws its seeded mask on chip: drop_p / drop_seed)")
         with torch.cuda.device(self.device):
             N.check(N.lib().mmrca_head_train_step(
                 C.byref(self.desc), C.byref(self.hp), img.data_ptr(), txt.data_ptr(),
@@ -485,8 +527,7 @@ class HierTrainStep:
         if B != self.desc.batch:
             raise ValueError("feature batch does not match the batch this step was built for")
         labels = _check_dev(labels, "labels", torch.int64)
-        if drop_mask is not None:
-            drop_mask = _check_dev(drop_mask, "dropout mask", torch.uint8)
+        drop_mask = _check_mask(drop_mask, B, HIER_CONCAT, "hierarchical")
         with torch.cuda.device(self.device):
             N.check(N.lib().mmrca_hier_train_step(
                 C.byref(self.desc), C.byref(self.hp), arr, drop_mask.data_ptr() if drop_mask is not None else None,

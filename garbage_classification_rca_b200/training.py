@@ -81,6 +81,25 @@ def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
     return flat
 
 
+def allreduce_global_mean_(flat: torch.Tensor, n: int, local_den, group=None, reduce=None) -> torch.Tensor:
+    """Exact global-mean gradient when the per-rank normalisers differ (class-weighted CrossEntropyLoss: each rank divided
+    by its own sum of w[y_b]; or unequal shards: by its own batch).  flat[:n] holds this rank's gradient normalised by
+    `local_den`; flat[n] is a spare slot.  The bucket is rescaled to the un-normalised sum, the denominator rides in the
+    spare slot through the SAME single collective, and the result is sum_r den_r g_r / sum_r den_r = the gradient a single
+    process gets on the concatenated batch (reference main_both.py:87-93 on the global batch).
+    `reduce`: callable(flat) doing the collective (sum or mean over ranks: the ratio is the same); default all-reduce."""
+    if flat.numel() <= n:
+        raise ValueError("the bucket needs one spare float after its n gradient entries")
+    flat[:n].mul_(local_den)
+    flat[n] = local_den
+    if reduce is not None:
+        reduce(flat)
+    elif dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat[:n].div_(flat[n])
+    return flat
+
+
 class PeerAllReduce:
     """The step's one collective as a one-shot all-reduce over NVLink peer memory (csrc/mmrca_peer.cuh): every rank
     reads the W staged copies of the 379 KB bucket itself.  torch's symmetric memory does the plumbing (allocation, IPC
@@ -127,6 +146,14 @@ class HeadDataParallel:
         self.group = group
         self.peer = None
         self.collective = "torch.distributed all_reduce"
+        # Averaging per-rank gradients by 1/world is the global mean only when every rank normalised by the same
+        # denominator.  With class weights (sum of w[y_b] differs per rank) or unequal shards the denominators ride along
+        # in the bucket's spare slot (allreduce_global_mean_): still ONE collective per step.
+        self.exact_mean = getattr(step, "cw", None) is not None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            sizes = [None] * dist.get_world_size(group)
+            dist.all_gather_object(sizes, int(step.desc.batch), group=group)
+            self.exact_mean = self.exact_mean or len(set(sizes)) > 1
         if peer and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1 \
                 and step.grads.flat.is_cuda:
             ok = torch.zeros(1, device=step.grads.flat.device)
@@ -144,10 +171,15 @@ class HeadDataParallel:
     def __call__(self, img, txt, labels, drop_mask=None, drop_scale=1.0, sync: bool = True, drop_seed: int = 0):
         loss, logits = self.step(img, txt, labels, drop_mask, drop_scale, drop_seed)
         if sync:   # sync=False == DDP.no_sync() while accumulating (reference steps every acc_steps batches)
-            if self.peer is not None:
-                self.peer(self.step.grads.flat)
+            flat = self.step.grads.flat
+            if self.exact_mean:
+                cw = self.step.cw
+                den = cw[labels].sum() if cw is not None else float(labels.shape[0])
+                allreduce_global_mean_(flat, self.step.grads.n, den, self.group, reduce=self.peer)
+            elif self.peer is not None:
+                self.peer(flat)
             else:
-                allreduce_mean_(self.step.grads.flat, self.group)
+                allreduce_mean_(flat, self.group)
         return loss, logits
 
 

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MMRCA_ABI_VERSION 3
+#define MMRCA_ABI_VERSION 4
 
 #define MMRCA_NUM_PATCHES 16 /* multimodal_model.py:249 */
 #define MMRCA_SA_DKQ 128     /* :251 */
@@ -52,14 +52,21 @@ extern "C" {
 #define MMRCA_FLAG_CROSS_ATTENTION_ONLY 4u /* --cross_attention_only: concat = [T_I, I_T], :701-706 */
 #define MMRCA_FLAG_FEATURE_GRADS 256u      /* the backward will be asked for d_img_feat / d_txt_feat (fine-tune phase,
                                               main_both.py:687-694): set it for the forward too */
+#define MMRCA_FLAG_TRAINING 512u           /* mmrca_head_forward only: a mmrca_head_backward on the same workspace follows
+                                              (autograd), so the forward keeps what the backward reloads and needs the
+                                              training-size workspace.  Without it the forward is inference: nothing is
+                                              kept, whatever the size of the workspace.  (ABI v4; v3 inferred this from
+                                              the workspace size.) */
 
 /* MmrcaHeadDesc.compute */
 #define MMRCA_COMPUTE_FP32 0 /* fp32 SIMT kernels: the 1e-4-relative contract */
 #define MMRCA_COMPUTE_BF16 1 /* bf16 tcgen05 tensor-core pipeline, fp32 accumulate: the 2e-2-absolute contract.
                                 Covers the reference's literal shapes (1280 / 768 features, 4 classes) with frozen
-                                features and seeded dropout (MmrcaHeadDesc.drop_p / drop_seed); a caller-supplied
-                                drop_mask, feature gradients and other widths run the fp32 kernels; features_only is two
-                                streaming kernels (normalise + fp32 classifier, then cross-entropy + dWf). */
+                                features and seeded dropout (MmrcaHeadDesc.drop_p / drop_seed); feature gradients and
+                                other widths run the fp32 kernels (the workspace is laid out accordingly: it is a
+                                function of the desc alone); a caller-supplied drop_mask is an error in this mode
+                                (pass MMRCA_COMPUTE_FP32); features_only is two streaming kernels (normalise + fp32
+                                classifier, then cross-entropy + dWf). */
 #define MMRCA_COMPUTE_BF16_FUSED 2 /* alias of MMRCA_COMPUTE_BF16 (kept for ABI v1 callers) */
 
 /* mmrca_query() selectors */

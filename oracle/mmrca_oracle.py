@@ -199,9 +199,9 @@ def cross_entropy(logits: torch.Tensor, labels: torch.Tensor,
     """
     logp = torch.log_softmax(logits, dim=1)
     n, c = logits.shape
-    w = torch.ones(c, dtype=logits.dtype) if weight is None else weight.to(logits.dtype)
+    w = torch.ones(c, dtype=logits.dtype, device=logits.device) if weight is None else weight.to(logits.dtype)
     wy = w[labels]
-    nll = -(logp[torch.arange(n), labels]) * wy
+    nll = -(logp[torch.arange(n, device=logits.device), labels]) * wy
     smooth = -(logp * w[None, :]).sum(dim=1)
     li = (1.0 - label_smoothing) * nll + (label_smoothing / c) * smooth
     return li.sum() / wy.sum()

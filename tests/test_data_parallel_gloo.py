@@ -60,6 +60,50 @@ def test_sharded_flat_allreduce_equals_full_batch_gradient():
     assert np.abs(flat - ref).max() / np.abs(ref).max() < 1e-5
 
 
+def _worker_weighted(rank, world, port, B, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from garbage_classification_rca_b200.training import allreduce_global_mean_, shard_range
+    torch.set_num_threads(2)
+    p = orc.init_head_params(seed=4, qk_gain=40.0)
+    img, txt, labels = make_inputs(B, 4)
+    cw = torch.tensor([0.5, 2.0, 1.0, 0.7])
+    lo, hi = shard_range(B, rank, world)          # B = 13, world 2: shards of 7 and 6 samples
+    _, _, grads, _, _ = orc.head_loss_and_grads(p, img[lo:hi], txt[lo:hi], labels[lo:hi], True, False, False,
+                                                class_weight=cw, label_smoothing=0.1)
+    names = orc.head_param_names()
+    g = torch.cat([grads[n].reshape(-1) for n in names])
+    flat = torch.cat([g, torch.zeros(4)])
+    allreduce_global_mean_(flat, g.numel(), cw[labels[lo:hi]].sum())
+    if rank == 0:
+        q.put(flat[:g.numel()].numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_class_weighted_uneven_shards_give_the_global_weighted_mean_gradient():
+    """Per-rank CrossEntropyLoss(weight=) normalises by the rank's own sum of w[y]; with unequal shards on top, a plain
+    1/world average is not the single-process gradient.  The denominators ride in the bucket's spare slot."""
+    B, world = 13, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_weighted, args=(r, world, port, B, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    flat = q.get(timeout=240)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    p = orc.init_head_params(seed=4, qk_gain=40.0)
+    img, txt, labels = make_inputs(B, 4)
+    cw = torch.tensor([0.5, 2.0, 1.0, 0.7])
+    _, _, grads, _, _ = orc.head_loss_and_grads(p, img, txt, labels, True, False, False, class_weight=cw,
+                                                label_smoothing=0.1)
+    ref = torch.cat([grads[n].reshape(-1) for n in orc.head_param_names()]).numpy()
+    assert np.abs(flat - ref).max() / np.abs(ref).max() < 1e-5
+
+
 def test_shard_range_covers_batch_without_overlap():
     from garbage_classification_rca_b200.training import shard_range
     for n in (0, 1, 7, 16, 4096, 4099):

@@ -53,7 +53,8 @@ def run_fused_forward(g, p, img, txt, flags, training=False):
     names = g.head_param_names(fo, co)
     params = [p[n].cuda().contiguous() for n in names]
     B = img.shape[0]
-    desc = N.HeadDesc(B, 1280, 768, 4, F.make_flags(rev, fo, co), N.COMPUTE_BF16_FUSED)
+    desc = N.HeadDesc(B, 1280, 768, 4, F.make_flags(rev, fo, co) | (N.FLAG_TRAINING if training else 0),
+                      N.COMPUTE_BF16_FUSED)
     L = N.lib()
     nbytes = int(L.mmrca_head_workspace_bytes(C.byref(desc), 1 if training else 0))
     ws = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
@@ -248,20 +249,23 @@ def test_seeded_dropout_fp32_kernels_match_oracle(pkg):
         assert_grad_close(n, t.grad.cpu().numpy(), ref["grads"][n], GRAD_REL_FP32_TIGHT, scale)
 
 
+@pytest.mark.parametrize("co", [False, True], ids=["features_only", "features_only+cross_only"])
 @pytest.mark.parametrize("B,drop_p", [(1, 0.0), (61, 0.6), (4096, 0.6)])
-def test_fused_features_only_train_step(pkg, B, drop_p):
+def test_fused_features_only_train_step(pkg, B, drop_p, co):
     """--features_only through the bf16 build: two streaming kernels (prep_feat: normalise + fp32 classifier terms;
     ce_feat: cross-entropy + dWf from the bf16 feature images).  Logits are fp32 arithmetic: the 1e-4-relative contract;
     dWf sees bf16-rounded features: 1e-2 of its largest entry.  The attention blocks stay outside the graph (reference
     multimodal_model.py:694-699): their gradients are untouched."""
     from garbage_classification_rca_b200 import _native as N
     from garbage_classification_rca_b200 import functional as F
-    p = orc.init_head_params(features_only=True, seed=9)
+    # with both switches set the reference's if / elif gives features_only precedence (multimodal_model.py:694-726)
+    p = orc.init_head_params(features_only=True, cross_attention_only=co, seed=9)
     img, txt, labels = make_inputs(B, 9)
-    names = pkg.head_param_names(True, False)
+    names = pkg.head_param_names(True, co)
     cw = torch.tensor([0.8, 1.3, 1.0, 0.9])
     step = pkg.HeadTrainStep([p[n].cuda() for n in names], B, 1280, 768, reverse=True, features_only=True,
-                             class_weight=cw.cuda(), label_smoothing=0.1, compute=N.COMPUTE_BF16, drop_p=drop_p)
+                             cross_attention_only=co, class_weight=cw.cuda(), label_smoothing=0.1,
+                             compute=N.COMPUTE_BF16, drop_p=drop_p)
     step.zero_grad()
     N.kernel_launches(reset=True)
     loss, logits = step(img.cuda(), txt.cuda(), labels.cuda(), drop_seed=5)
@@ -271,7 +275,7 @@ def test_fused_features_only_train_step(pkg, B, drop_p):
     if drop_p > 0:
         mask = F.dropout_mask(5, drop_p, B, 2048, "cuda").cpu().numpy()
         scale = 1.0 / (1.0 - drop_p)
-    ref = orc.np_head_forward_backward(p, img.numpy(), txt.numpy(), True, True, False, labels=labels.numpy(),
+    ref = orc.np_head_forward_backward(p, img.numpy(), txt.numpy(), True, True, co, labels=labels.numpy(),
                                        class_weight=cw.numpy(), label_smoothing=0.1, drop_mask=mask, drop_scale=scale)
     lg = logits.cpu().numpy()
     assert np.abs(lg - ref["logits"]).max() <= 1e-4 * np.abs(ref["logits"]).max()

@@ -69,7 +69,8 @@ def test_head_matches_reference_golden(pkg, case):
 
 
 @pytest.mark.parametrize("flags", [(True, False, False), (False, False, False), (True, True, False),
-                                   (True, False, True)], ids=["rca", "ca", "features_only", "cross_only"])
+                                   (True, False, True), (True, True, True)],
+                         ids=["rca", "ca", "features_only", "cross_only", "features_only+cross_only"])
 @pytest.mark.parametrize("B", [1, 3, 8, 17, 64])
 def test_head_matches_oracle_seeded(pkg, flags, B):
     """Ragged batch sizes (not a multiple of the 2/4-sample tiles), all four switch combinations,
