@@ -26,6 +26,7 @@ SOURCES = ["mmrca_capi.cu"]
 FLAG_REVERSE, FLAG_FEATURES_ONLY, FLAG_CROSS_ATTENTION_ONLY = 1, 2, 4
 FLAG_FEATURE_GRADS = 256
 FLAG_TRAINING = 512
+FLAG_FEATURES_BF16 = 1024
 COMPUTE_FP32, COMPUTE_BF16, COMPUTE_BF16_FUSED = 0, 1, 2
 WS_TEXT_SA_IMAGE, WS_IMAGE_SA_IMAGE = 0, 1
 QUERY_ABI_VERSION, QUERY_DEVICE_OK, QUERY_SM_COUNT, QUERY_KERNEL_LAUNCHES, QUERY_RESET_LAUNCHES, QUERY_HAS_BF16 = range(6)
@@ -71,7 +72,7 @@ EXPORTS = ("mmrca_query", "mmrca_last_error", "mmrca_head_workspace_bytes", "mmr
            "mmrca_timing_end", "mmrca_dev_umma_selftest", "mmrca_attention_forward_scratch_bytes",
            "mmrca_head_workspace_offset", "mmrca_dropout_mask", "mmrca_dev_set_debug",
            "mmrca_hier_workspace_bytes", "mmrca_hier_forward", "mmrca_hier_backward", "mmrca_hier_train_step",
-           "mmrca_peer_allreduce_mean", "mmrca_peer_allreduce_pad_bytes")
+           "mmrca_peer_allreduce_mean", "mmrca_peer_allreduce_pad_bytes", "mmrca_peer_allreduce_status")
 
 
 def _sources_newer_than_lib() -> bool:
@@ -177,6 +178,8 @@ def lib() -> C.CDLL:
         L.mmrca_peer_allreduce_mean.restype = C.c_int
         L.mmrca_peer_allreduce_pad_bytes.argtypes = [C.c_int32]
         L.mmrca_peer_allreduce_pad_bytes.restype = C.c_int
+        L.mmrca_peer_allreduce_status.argtypes = [_fp, C.c_int32, _fp]
+        L.mmrca_peer_allreduce_status.restype = C.c_int
         if L.mmrca_query(QUERY_ABI_VERSION) != ABI_VERSION:
             raise RuntimeError("libmmrca.so ABI version mismatch: rebuild it")
         _lib = L

@@ -315,6 +315,9 @@ static int check_desc(const MmrcaHeadDesc* d) {
   if (d->compute != MMRCA_COMPUTE_FP32 && d->compute != MMRCA_COMPUTE_BF16 && d->compute != MMRCA_COMPUTE_BF16_FUSED)
     return fail(MMRCA_ERR_INVALID, "unknown compute mode%s%s");
   if (!(d->drop_p >= 0.f && d->drop_p <= 1.f)) return fail(MMRCA_ERR_INVALID, "drop_p must be in [0, 1]%s%s");
+  if ((d->flags & MMRCA_FLAG_FEATURES_BF16) && !desc_is_tc(*d))
+    return fail(MMRCA_ERR_INVALID, "MMRCA_FLAG_FEATURES_BF16 needs the bf16 pipeline (compute = MMRCA_COMPUTE_BF16, 1280 / 768 "
+                                   "features, 4 classes, no feature gradients)%s%s");
   return MMRCA_OK;
 }
 
@@ -367,11 +370,13 @@ __global__ void __launch_bounds__(kThreads) l2norm_kernel(const float* __restric
 }
 
 // ---- fused bf16 pipeline: forward -----------------------------------------------------------------------------
-static htc::PrepBlock make_prep_block(const MmrcaAttnParams& p, void* blob, int din, int dkq, int dv) {
+// blob of a self-attention block: bz | bv | bv (lo); of a cross-attention direction: bz | bv | bc | bv (lo) | bc (lo)
+static htc::PrepBlock make_prep_block(const MmrcaAttnParams& p, void* blob, int din, int dkq, int dv, bool cross) {
   htc::PrepBlock b;
   b.wq = p.wq; b.bq = p.bq; b.wk = p.wk; b.wv = p.wv; b.bv = p.bv;
   b.bz = blob;
   b.bvb = static_cast<uint8_t*>(blob) + htc::blob_bytes(din, din + 16);
+  b.bvb_lo = static_cast<uint8_t*>(blob) + (cross ? htc::CaCfg::OFF_BV_LO : htc::blob_bytes(din, din + 16) + htc::blob_bytes(dv, din + 16));
   b.din = din; b.dkq = dkq; b.dv = dv;
   return b;
 }
@@ -385,14 +390,16 @@ static int launch_prep_feat(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, co
   // --features_only (multimodal_model.py:694-699, :721-722): the attention blocks do not reach the logits; only the
   // feature half of this kernel runs (no weight blobs), then ce_feat: two streaming kernels for forward + backward
   if (!fo) {
-  a.blk[0] = make_prep_block(p.sa_img, w.fblob[0], 80, MMRCA_SA_DKQ, MMRCA_SA_DV);
-  a.blk[1] = make_prep_block(p.sa_txt, w.fblob[1], 48, MMRCA_SA_DKQ, MMRCA_SA_DV);
-  a.blk[2] = make_prep_block(p.ca1, w.fblob[2], MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV);
-  a.blk[3] = make_prep_block(p.ca2, w.fblob[3], MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV);
+  a.blk[0] = make_prep_block(p.sa_img, w.fblob[0], 80, MMRCA_SA_DKQ, MMRCA_SA_DV, false);
+  a.blk[1] = make_prep_block(p.sa_txt, w.fblob[1], 48, MMRCA_SA_DKQ, MMRCA_SA_DV, false);
+  a.blk[2] = make_prep_block(p.ca1, w.fblob[2], MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV, true);
+  a.blk[3] = make_prep_block(p.ca2, w.fblob[3], MMRCA_SA_DV, MMRCA_CA_DKQ, MMRCA_CA_DV, true);
   const int ca = kL * MMRCA_CA_DV;   // 768: width of T_I / I_T in the concat (multimodal_model.py:708-716)
-  a.src[0].bc = static_cast<uint8_t*>(w.fblob[2]) + htc::CaCfg::BZ_BYTES + htc::CaCfg::BV_BYTES;
+  a.src[0].bc = static_cast<uint8_t*>(w.fblob[2]) + htc::CaCfg::OFF_BC;
+  a.src[0].bc_lo = static_cast<uint8_t*>(w.fblob[2]) + htc::CaCfg::OFF_BC_LO;
   a.src[0].off = 0; a.src[0].w = MMRCA_CA_DV;
-  a.src[1].bc = static_cast<uint8_t*>(w.fblob[3]) + htc::CaCfg::BZ_BYTES + htc::CaCfg::BV_BYTES;
+  a.src[1].bc = static_cast<uint8_t*>(w.fblob[3]) + htc::CaCfg::OFF_BC;
+  a.src[1].bc_lo = static_cast<uint8_t*>(w.fblob[3]) + htc::CaCfg::OFF_BC_LO;
   a.src[1].off = ca; a.src[1].w = MMRCA_CA_DV;
   a.nsrc = 2;      // (the feature sources of the classifier run in fp32: prep_feat_kernel / ce_feat_kernel)
   }
@@ -404,6 +411,7 @@ static int launch_prep_feat(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, co
   f.src[1].feat = txt; f.src[1].x_tiles = w.x_txt; f.src[1].norms = w.norm_txt; f.src[1].cls_off = feat0 + d.d_img;
   f.logits = logits; f.wf = p.wf; f.bf = p.bf; f.with_features = co ? 0 : 1;
   f.drop = make_drop(d); f.batch = d.batch;
+  f.feat_bf16 = (d.flags & MMRCA_FLAG_FEATURES_BF16) ? 1 : 0;
   if (w.step_loss) { a.zero0 = w.gm[0]; a.nzero0 = int(w.gm_floats); a.zero1 = w.step_loss; }
   const int prep_ctas = htc::kPrepCtas;
   const int feat_ctas = max(1, min((d.batch + 7) / 8, 2 * sms));
@@ -448,7 +456,7 @@ static int head_forward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, 
     a.dbg = g_dbg_kernel == 2 ? g_dbg : nullptr;
     if ((rc = set_smem(htc::ca_fwd_kernel, htc::CaFwdLayout::BYTES))) return rc;
     LaunchScope ls("ca_fwd_bf16", st);
-    htc::ca_fwd_kernel<<<grid, htc::kCtaThreads, htc::CaFwdLayout::BYTES, st>>>(a);
+    htc::ca_fwd_kernel<<<dim3(min((tiles + 1) / 2, max(1, sms / 2)), 2), htc::kCtaThreads, htc::CaFwdLayout::BYTES, st>>>(a);
   }
   MMRCA_CUDA(cudaGetLastError());
   return MMRCA_OK;
@@ -1023,7 +1031,18 @@ int mmrca_peer_allreduce_mean(float* flat, int32_t n, int32_t n_pad, const void*
   MMRCA_CUDA(cudaGetLastError());
   return MMRCA_OK;
 }
-int mmrca_peer_allreduce_pad_bytes(int32_t world) { return 2 * world * peer::kCtas * int(sizeof(uint32_t)); }
+int mmrca_peer_allreduce_pad_bytes(int32_t world) {
+  return (2 * world * peer::kCtas + peer::kStatusWords) * int(sizeof(uint32_t));
+}
+int mmrca_peer_allreduce_status(const void* own_pad, int32_t world, void* stream) {
+  if (!own_pad || world < 1 || world > peer::kMaxWorld) return -fail(MMRCA_ERR_INVALID, "bad pad / world%s%s");
+  uint32_t word = 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (cudaMemcpyAsync(&word, static_cast<const uint32_t*>(own_pad) + size_t(2) * world * peer::kCtas, sizeof(word),
+                      cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+    return -fail(MMRCA_ERR_CUDA, "reading the peer all-reduce status word failed%s%s");
+  return int(word);
+}
 
 size_t mmrca_attention_forward_scratch_bytes(int32_t, int32_t, int32_t, int32_t) { return 0; }
 
@@ -1102,8 +1121,8 @@ int mmrca_dev_set_debug(void* device_buffer_1024_int64, int32_t kernel) {
 int mmrca_dev_umma_selftest(int32_t mode, const float* a, const float* b, float* out, int32_t n, int32_t k,
                             void* stream) {
   if (!a || !b || !out) return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
-  if (n < 16 || n > 256 || n % 16 || k < 16 || k % 16 || mode < 0 || mode > 7)
-    return fail(MMRCA_ERR_INVALID, "selftest needs 16 <= n <= 256, n % 16 == 0, k % 16 == 0, mode in [0,7]%s%s");
+  if (n < 16 || n > 256 || n % 16 || k < 16 || k % 16 || mode < 0 || mode > 15)
+    return fail(MMRCA_ERR_INVALID, "selftest needs 16 <= n <= 256, n % 16 == 0, k % 16 == 0, mode in [0,15]%s%s");
   DeviceInfo di;
   int rc;
   if ((rc = device_info(&di))) return rc;

@@ -70,10 +70,14 @@ __device__ __forceinline__ uint32_t row_off(int r) { return uint32_t(r >> 3) * k
 struct PrepBlock {
   const float* wq; const float* bq; const float* wk; const float* wv; const float* bv;
   void* bz;      // [n = d_in][k = d_in + 16]:  M^T, row k = d_in holds u
-  void* bvb;     // [n = d_v ][k = d_in + 16]:  W_value, row k = d_in holds b_value
+  void* bvb;     // [n = d_v ][k = d_in + 16]:  W_value, row k = d_in holds b_value  (bf16 "hi" part)
+  void* bvb_lo;  // same shape: bf16(W_value - hi).  hi + lo carries 16 mantissa bits: the rounding of W_value to ONE
+                 // bf16 is a systematic (sample-independent) perturbation that does not average out over the batch and
+                 // dominated the gradient error of this pipeline (tools/emulate_bf16.py)
   int din, dkq, dv;
 };
-struct PrepSrc { void* bc; int off, w; };   // classifier source: columns [off, off + 16*w) of the concat
+// classifier source: columns [off, off + 16*w) of the concat; bc / bc_lo: hi / lo bf16 parts of the weight slice
+struct PrepSrc { void* bc; void* bc_lo; int off, w; };
 struct PrepArgs {
   PrepBlock blk[4];
   PrepSrc src[4];
@@ -151,7 +155,10 @@ __device__ __forceinline__ void prep_body(const PrepArgs& a, int cta, int nctas,
       } else if (kc * 8 == B.din) {
         v[0] = __ldg(B.bv + n);
       }
-      *reinterpret_cast<uint4*>(static_cast<uint8_t*>(B.bvb) + size_t(kc) * (B.dv * 16) + n * 16) = pack_bf16x8(v);
+      float lo[8];
+      const uint4 hi = pack_bf16x8_hilo(v, lo);
+      *reinterpret_cast<uint4*>(static_cast<uint8_t*>(B.bvb) + size_t(kc) * (B.dv * 16) + n * 16) = hi;
+      *reinterpret_cast<uint4*>(static_cast<uint8_t*>(B.bvb_lo) + size_t(kc) * (B.dv * 16) + n * 16) = pack_bf16x8(lo);
     }
   }
   // (c) classifier blobs: Bc[n = r'*4 + c][k = j] = Wf[c][off + r'*w + j]
@@ -164,7 +171,10 @@ __device__ __forceinline__ void prep_body(const PrepArgs& a, int cta, int nctas,
       float v[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] = __ldg(p + e);
-      *reinterpret_cast<uint4*>(static_cast<uint8_t*>(S.bc) + size_t(kc) * (kNCls * 16) + n * 16) = pack_bf16x8(v);
+      float lo[8];
+      const uint4 hi = pack_bf16x8_hilo(v, lo);
+      *reinterpret_cast<uint4*>(static_cast<uint8_t*>(S.bc) + size_t(kc) * (kNCls * 16) + n * 16) = hi;
+      *reinterpret_cast<uint4*>(static_cast<uint8_t*>(S.bc_lo) + size_t(kc) * (kNCls * 16) + n * 16) = pack_bf16x8(lo);
     }
   }
   // (d) accumulators
@@ -182,7 +192,7 @@ __device__ __forceinline__ void prep_body(const PrepArgs& a, int cta, int nctas,
 // group KCS holds the constant-one column that carries the projection biases, group KCS + 1 zeros.
 // ---------------------------------------------------------------------------------------------------------------
 struct FeatSrc {
-  const float* feat;      // [B][16 * din] fp32
+  const void* feat;       // [B][16 * din] fp32, or bf16 when FeatArgs::feat_bf16 (MMRCA_FLAG_FEATURES_BF16)
   void* x_tiles;          // [tiles][x_tile_bytes(din)] out
   float* norms;           // [B] out
   int cls_off;            // first concat column of this source
@@ -194,15 +204,30 @@ struct FeatArgs {
   int with_features;      // the classifier sees the features (not cross_attention_only)
   DropSpec drop;          // drop.D = concat width
   int batch;
+  int feat_bf16;          // the features arrive as bf16 (half the HBM / PCIe bytes); norms and classifier terms stay fp32
 };
 __host__ __device__ constexpr uint32_t x_tile_bytes(int din) { return op_bytes(din + 16); }
 constexpr int kFeatCols = 16 * 80 + 16 * 48;                 // 2048 feature columns of the concat
 constexpr uint32_t kFeatSmemBytes = kClasses * kFeatCols * 4 > kPrepSmemBytes ? kClasses * kFeatCols * 4 : kPrepSmemBytes;
 
 template <int DIN>
-__device__ __forceinline__ void feat_load(const FeatSrc& S, int b, bool live, int lane, float (&v)[(kL * DIN / 8 + 31) / 32][8]) {
+__device__ __forceinline__ void feat_load(const FeatSrc& S, bool bf16, int b, bool live, int lane, float (&v)[(kL * DIN / 8 + 31) / 32][8]) {
   constexpr int ITEMS = kL * DIN / 8, PER = (ITEMS + 31) / 32;
-  const float* base = S.feat + size_t(b) * (kL * DIN);
+  if (bf16) {      // one 16-byte load per item
+    const uint4* base = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(S.feat) + size_t(b) * (kL * DIN));
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int it = lane + 32 * k;
+      uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+      if (live && (ITEMS % 32 == 0 || it < ITEMS)) raw = __ldg(base + it);
+      v[k][0] = __uint_as_float(raw.x << 16); v[k][1] = __uint_as_float(raw.x & 0xffff0000u);
+      v[k][2] = __uint_as_float(raw.y << 16); v[k][3] = __uint_as_float(raw.y & 0xffff0000u);
+      v[k][4] = __uint_as_float(raw.z << 16); v[k][5] = __uint_as_float(raw.z & 0xffff0000u);
+      v[k][6] = __uint_as_float(raw.w << 16); v[k][7] = __uint_as_float(raw.w & 0xffff0000u);
+    }
+    return;
+  }
+  const float* base = static_cast<const float*>(S.feat) + size_t(b) * (kL * DIN);
 #pragma unroll
   for (int k = 0; k < PER; ++k) {
     const int it = lane + 32 * k;
@@ -265,8 +290,8 @@ __global__ void __launch_bounds__(256) prep_feat_kernel(const PrepArgs pa, const
   // the first sample's features are requested before anything else: they travel while the classifier slice is staged
   float vi[5][8], vt[3][8];
   if (b < nb) {
-    feat_load<80>(fa.src[0], b, b < fa.batch, lane, vi);
-    feat_load<48>(fa.src[1], b, b < fa.batch, lane, vt);
+    feat_load<80>(fa.src[0], fa.feat_bf16 != 0, b, b < fa.batch, lane, vi);
+    feat_load<48>(fa.src[1], fa.feat_bf16 != 0, b, b < fa.batch, lane, vt);
   }
   if (fa.with_features) {
     constexpr int N4 = kClasses * kFeatCols / 4 / 256;      // 8 float4 per thread, requested four at a time
@@ -294,8 +319,8 @@ __global__ void __launch_bounds__(256) prep_feat_kernel(const PrepArgs pa, const
     feat_emit<48>(fa, fa.src[1], wsm_f + kClasses * 1280, b, live, lane, vt, acc);
     const int bn = b + stride;
     if (bn < nb) {      // the next sample's features travel while the classifier terms are reduced and written
-      feat_load<80>(fa.src[0], bn, bn < fa.batch, lane, vi);
-      feat_load<48>(fa.src[1], bn, bn < fa.batch, lane, vt);
+      feat_load<80>(fa.src[0], fa.feat_bf16 != 0, bn, bn < fa.batch, lane, vi);
+      feat_load<48>(fa.src[1], fa.feat_bf16 != 0, bn, bn < fa.batch, lane, vt);
     }
 #pragma unroll
     for (int cc = 0; cc < kClasses; ++cc) acc[cc] = warp_sum(acc[cc]);
@@ -470,7 +495,7 @@ struct SaCfg {
   static constexpr int DIN = DIN_, KE = DIN_ + 16, DV = kDV_SA;
   static constexpr uint32_t BZ_LBO = DIN * 16, BZ_BYTES = blob_bytes(DIN, KE);
   static constexpr uint32_t BV_LBO = DV * 16, BV_BYTES = blob_bytes(DV, KE);
-  static constexpr uint32_t W_BYTES = BZ_BYTES + BV_BYTES;
+  static constexpr uint32_t W_BYTES = BZ_BYTES + 2 * BV_BYTES;      // bz | bv (hi) | bv (lo)
   // TMEM columns (relative to the warpgroup base)
   static constexpr uint32_t COL_Z = 0, COL_V = DIN, COL_S = 0, COL_C = 64;
   static_assert(DIN + DV <= 256, "warpgroup TMEM budget");
@@ -540,6 +565,9 @@ __device__ __forceinline__ void sa_fwd_tile(WgCtx& c, const SaFwdArgs& a, const 
               make_idesc_bf16(128, C::DIN, 0, 0), C::KE / 16, false);
     mma_steps(c.tmem + C::COL_V, ax, 2 * kCS, make_smem_desc(smem_u32(wsm + C::BZ_BYTES), C::BV_LBO, 128),
               2 * C::BV_LBO, make_idesc_bf16(128, C::DV, 0, 0), C::KE / 16, false);
+    // V += X (W_value - hi)^T: the value projection sees W_value to 16 mantissa bits
+    mma_steps(c.tmem + C::COL_V, ax, 2 * kCS, make_smem_desc(smem_u32(wsm + C::BZ_BYTES + C::BV_BYTES), C::BV_LBO, 128),
+              2 * C::BV_LBO, make_idesc_bf16(128, C::DV, 0, 0), C::KE / 16, true);
     umma_commit(c.bar);
   }
   wg_wait_mma(c);
@@ -668,7 +696,10 @@ struct CaCfg {
   static constexpr uint32_t BZ_LBO = DIN * 16, BZ_BYTES = blob_bytes(DIN, KE);
   static constexpr uint32_t BV_LBO = DV * 16, BV_BYTES = blob_bytes(DV, KE);
   static constexpr uint32_t BC_LBO = kNCls * 16, BC_BYTES = blob_bytes(kNCls, DV);
-  static constexpr uint32_t W_BYTES = BZ_BYTES + BV_BYTES + BC_BYTES;
+  // blob of a direction: bz | bv | bc | bv (lo) | bc (lo).  The backward recomputes V with hi + lo but reads the classifier
+  // slice (dOut = DL Wf^T) and W_value (dXkv) in one bf16: it loads the first W_BYTES_BWD bytes only.
+  static constexpr uint32_t OFF_BV = BZ_BYTES, OFF_BC = OFF_BV + BV_BYTES, OFF_BV_LO = OFF_BC + BC_BYTES, OFF_BC_LO = OFF_BV_LO + BV_BYTES;
+  static constexpr uint32_t W_BYTES = OFF_BC_LO + BC_BYTES, W_BYTES_BWD = OFF_BC_LO;
   static constexpr uint32_t COL_Z = 0, COL_V = DIN, COL_S = 0, COL_C = 64, COL_CLS = 112;
 };
 
@@ -693,13 +724,12 @@ struct CaFwdSmem {
   static constexpr uint32_t V = al128(XKV + op_bytes(112));           // [128 x 48]
   static constexpr uint32_t BYTES = al128(V + op_bytes(48));
 };
-struct CaFwdLayout {
+struct CaFwdLayout {      // a CTA works on ONE direction (blockIdx.y): its blob (hi + lo parts) + two warpgroup pipelines
   static constexpr uint32_t W0 = 0;
-  static constexpr uint32_t W1 = al128(W0 + CaCfg::W_BYTES);
-  static constexpr uint32_t WG0 = al128(W1 + CaCfg::W_BYTES);
+  static constexpr uint32_t WG0 = al128(W0 + CaCfg::W_BYTES);
   static constexpr uint32_t WG1 = WG0 + CaFwdSmem::BYTES;
-  static constexpr uint32_t LN = WG1 + CaFwdSmem::BYTES;              // 2 dirs x (gamma, beta) x 48
-  static constexpr uint32_t BAR = al128(LN + 2 * 2 * 48 * 4);         // weights, 2 x MMA, 2 x tile-load barriers, tmem slot
+  static constexpr uint32_t LN = WG1 + CaFwdSmem::BYTES;              // (gamma, beta) x 48
+  static constexpr uint32_t BAR = al128(LN + 2 * 48 * 4);             // weights, 2 x MMA, 2 x tile-load barriers, tmem slot
   static constexpr uint32_t BYTES = BAR + 64;
   static_assert(BYTES <= 232448, "CA forward does not fit shared memory");
 };
@@ -742,8 +772,11 @@ __device__ __forceinline__ void ca_fwd_tile(WgCtx& c, const CaFwdArgs& a, int d,
               make_smem_desc(smem_u32(wsm), C::BZ_LBO, 128), 2 * C::BZ_LBO, make_idesc_bf16(128, C::DIN, 0, 0),
               C::KE / 16, false);
     mma_steps(c.tmem + C::COL_V, make_smem_desc(smem_u32(xkv), kCS, kRS), 2 * kCS,
-              make_smem_desc(smem_u32(wsm + C::BZ_BYTES), C::BV_LBO, 128), 2 * C::BV_LBO,
+              make_smem_desc(smem_u32(wsm + C::OFF_BV), C::BV_LBO, 128), 2 * C::BV_LBO,
               make_idesc_bf16(128, C::DV, 0, 0), C::KE / 16, false);
+    mma_steps(c.tmem + C::COL_V, make_smem_desc(smem_u32(xkv), kCS, kRS), 2 * kCS,      // += Xkv (W_value - hi)^T
+              make_smem_desc(smem_u32(wsm + C::OFF_BV_LO), C::BV_LBO, 128), 2 * C::BV_LBO,
+              make_idesc_bf16(128, C::DV, 0, 0), C::KE / 16, true);
     umma_commit(c.bar);
   }
   wg_wait_mma(c);
@@ -764,10 +797,10 @@ __device__ __forceinline__ void ca_fwd_tile(WgCtx& c, const CaFwdArgs& a, int d,
   FSTAMP(4);
   // the key/value image is dead (V and the scores have read it): the next tile's lands while this one finishes
   if (c.wt == 0 && next_tile >= 0) {
-    ca_issue_kv(a, d ^ 1, next_tile, xkv, bar_ld);
-    if (c.wg == 0 && next_tile + int(gridDim.x) < (a.batch + 7) / 8) {      // and the tile after that: into the L2
-      bulk_prefetch_l2(static_cast<const uint8_t*>(a.t_tiles) + size_t(next_tile + gridDim.x) * kSaTileBytes, kSaTileBytes);
-      bulk_prefetch_l2(static_cast<const uint8_t*>(a.i_tiles) + size_t(next_tile + gridDim.x) * kSaTileBytes, kSaTileBytes);
+    ca_issue_kv(a, d, next_tile, xkv, bar_ld);
+    if (next_tile + 2 * int(gridDim.x) < (a.batch + 7) / 8) {      // and this warpgroup's tile after that: into the L2
+      bulk_prefetch_l2(static_cast<const uint8_t*>(a.t_tiles) + size_t(next_tile + 2 * gridDim.x) * kSaTileBytes, kSaTileBytes);
+      bulk_prefetch_l2(static_cast<const uint8_t*>(a.i_tiles) + size_t(next_tile + 2 * gridDim.x) * kSaTileBytes, kSaTileBytes);
     }
   }
   {
@@ -818,13 +851,16 @@ __device__ __forceinline__ void ca_fwd_tile(WgCtx& c, const CaFwdArgs& a, int d,
   FSTAMP(7);
   if (c.wt == 0) {
     mma_steps(c.tmem + C::COL_CLS, make_smem_desc(smem_u32(xq), kCS, kRS), 2 * kCS,
-              make_smem_desc(smem_u32(wsm + C::BZ_BYTES + C::BV_BYTES), C::BC_LBO, 128), 2 * C::BC_LBO,
+              make_smem_desc(smem_u32(wsm + C::OFF_BC), C::BC_LBO, 128), 2 * C::BC_LBO,
               make_idesc_bf16(128, kNCls, 0, 0), C::DV / 16, false);
+    mma_steps(c.tmem + C::COL_CLS, make_smem_desc(smem_u32(xq), kCS, kRS), 2 * kCS,      // += F (Wf - hi)^T
+              make_smem_desc(smem_u32(wsm + C::OFF_BC_LO), C::BC_LBO, 128), 2 * C::BC_LBO,
+              make_idesc_bf16(128, kNCls, 0, 0), C::DV / 16, true);
     umma_commit(c.bar);
   }
   wg_wait_mma(c);
   FSTAMP(8);
-  if (c.wt == 0 && next_tile >= 0) ca_issue_q(a, d ^ 1, next_tile, xq, bar_ld);      // the classifier has read Out: xq is free
+  if (c.wt == 0 && next_tile >= 0) ca_issue_q(a, d, next_tile, xq, bar_ld);      // the classifier has read Out: xq is free
   cls_readback(c, C::COL_CLS, a.logits, b0 + (c.rp >> 4), b0 + (c.rp >> 4) < a.batch);
   FSTAMP(9);
   tc_fence_before_sync();
@@ -841,18 +877,17 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_fwd_kernel(const CaFwdArgs 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
   float* ln_s = reinterpret_cast<float*>(sm + L::LN);
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int d = blockIdx.y;       // direction: 0 = cross_attention_1, 1 = cross_attention_2
   if (tid == 0) {
     for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
-    mbar_arrive_expect_tx(&bars[0], 2 * CaCfg::W_BYTES);
-    bulk_g2s(sm + L::W0, a.dir[0].blobs, CaCfg::W_BYTES, &bars[0]);
-    bulk_g2s(sm + L::W1, a.dir[1].blobs, CaCfg::W_BYTES, &bars[0]);
+    mbar_arrive_expect_tx(&bars[0], CaCfg::W_BYTES);
+    bulk_g2s(sm + L::W0, a.dir[d].blobs, CaCfg::W_BYTES, &bars[0]);
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
-  for (int i = tid; i < 2 * 48; i += kCtaThreads) {
-    const int d = i / 48, k = i - d * 48;
-    ln_s[d * 96 + k] = a.dir[d].ln_g[k];
-    ln_s[d * 96 + 48 + k] = a.dir[d].ln_b[k];
+  for (int i = tid; i < 48; i += kCtaThreads) {
+    ln_s[i] = a.dir[d].ln_g[i];
+    ln_s[48 + i] = a.dir[d].ln_b[i];
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -864,16 +899,16 @@ __global__ void __launch_bounds__(kCtaThreads, 1) ca_fwd_kernel(const CaFwdArgs 
   uint8_t* bsm = sm + (wg == 0 ? L::WG0 : L::WG1);
   uint32_t ph_ld = 0;
   const int tiles = (a.batch + 7) / 8;
+  // the CTA's two warpgroups are independent pipelines on their own tiles of this direction
+  const int first = 2 * int(blockIdx.x) + wg, stride = 2 * int(gridDim.x);
   int round = 0;
-  if ((tid & 127) == 0 && int(blockIdx.x) < tiles) {      // this warpgroup's first tile (direction wg)
-    ca_issue_kv(a, wg, blockIdx.x, bsm + CaFwdSmem::XKV, &bars[3 + wg]);
-    ca_issue_q(a, wg, blockIdx.x, bsm + CaFwdSmem::XQ, &bars[3 + wg]);
+  if ((tid & 127) == 0 && first < tiles) {
+    ca_issue_kv(a, d, first, bsm + CaFwdSmem::XKV, &bars[3 + wg]);
+    ca_issue_q(a, d, first, bsm + CaFwdSmem::XQ, &bars[3 + wg]);
   }
-  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++round) {
-    const int d = (wg + round) & 1;
-    ca_fwd_tile(c, a, d, sm + (d == 0 ? L::W0 : L::W1), bsm, ln_s + d * 96, &bars[3 + wg], ph_ld, tile,
-                tile + int(gridDim.x) < tiles ? tile + int(gridDim.x) : -1, 1 + 12 * round);
-  }
+  for (int tile = first; tile < tiles; tile += stride, ++round)
+    ca_fwd_tile(c, a, d, sm + L::W0, bsm, ln_s, &bars[3 + wg], ph_ld, tile, tile + stride < tiles ? tile + stride : -1,
+                1 + 12 * round);
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);

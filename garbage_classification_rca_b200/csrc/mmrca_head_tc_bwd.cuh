@@ -394,9 +394,10 @@ struct CaBwdSmem {
   static constexpr uint32_t DYX = DC + op_bytes(48);                 // [128 x 96]: dy*xhat | dy; later dZ
   static constexpr uint32_t DLS = DYX + op_bytes(96);                // DL [128 x 64]; later dS (2 x [64 x 64])
   static constexpr uint32_t P = DLS + 2 * kPHalf;                    // 2 x [64 x 64]
-  static constexpr uint32_t ONES = P + 2 * kPHalf;                   // [16][128] ones
-  static constexpr uint32_t W = al128(ONES + 4096);
-  static constexpr uint32_t LN = W + CaCfg::W_BYTES;                 // gamma, beta [48] fp32
+  static constexpr uint32_t ONES = P + 2 * kPHalf;                   // [16 rows][8] ones: the B operand of the column-sum MMAs, read
+                                                                     // with a ZERO K-stride descriptor (every k-group = these 256 B)
+  static constexpr uint32_t W = al128(ONES + 256);                   // bz | bv | bc | bv (lo)
+  static constexpr uint32_t LN = W + CaCfg::W_BYTES_BWD;             // gamma, beta [48] fp32
   static constexpr uint32_t PART = LN + 2 * 48 * 4;                  // [2 warpgroups][128 rows] (m1, m2) partial sums
   static constexpr uint32_t BAR = al128(PART + 2 * 128 * 8);
   static constexpr uint32_t BYTES = BAR + 128;
@@ -437,12 +438,12 @@ __global__ void __launch_bounds__(kCaBwdThreads, 1) ca_bwd_kernel(const CaBwdArg
   if (tid == 0) {
     for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
-    mbar_arrive_expect_tx(&bars[0], C::W_BYTES);
-    bulk_g2s(sm + S::W, D.blobs, C::W_BYTES, &bars[0]);
+    mbar_arrive_expect_tx(&bars[0], C::W_BYTES_BWD);
+    bulk_g2s(sm + S::W, D.blobs, C::W_BYTES_BWD, &bars[0]);
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   for (int i = tid; i < 48; i += kCaBwdThreads) { ln_s[i] = D.ln_g[i]; ln_s[48 + i] = D.ln_b[i]; }
-  for (uint32_t i = tid; i < (2 * kPHalf + 4096) / 16; i += kCaBwdThreads) {     // P zeros, then the ones operand
+  for (uint32_t i = tid; i < (2 * kPHalf + 256) / 16; i += kCaBwdThreads) {      // P zeros, then the ones operand
     const uint32_t off = i * 16;
     reinterpret_cast<uint4*>(sm + S::P)[i] =
         off < 2 * kPHalf ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
@@ -457,7 +458,8 @@ __global__ void __launch_bounds__(kCaBwdThreads, 1) ca_bwd_kernel(const CaBwdArg
   uint32_t ph_ld = 0, ph_g2 = 0, ph_g3 = 0, ph_b = 0;
   uint8_t *xq = sm + S::XQ, *xkv = sm + S::XKV, *zb = sm + S::Z, *vb = sm + S::V, *ob = sm + S::OUT, *dcb = sm + S::DC,
           *dyx = sm + S::DYX, *dls = sm + S::DLS, *pb = sm + S::P, *ones = sm + S::ONES, *wsm = sm + S::W;
-  const uint8_t* bz = wsm; const uint8_t* bv = wsm + C::BZ_BYTES; const uint8_t* bc = wsm + C::BZ_BYTES + C::BV_BYTES;
+  const uint8_t* bz = wsm; const uint8_t* bv = wsm + C::OFF_BV; const uint8_t* bc = wsm + C::OFF_BC;
+  const uint8_t* bv_lo = wsm + C::OFF_BV_LO;
   const int tiles = (a.batch + 7) / 8;
   if (warp == kCtaThreads / 32) {      // ---- loader warp ----------------------------------------------------------------
     uint32_t ph = 0, phb = 0;
@@ -523,6 +525,8 @@ __global__ void __launch_bounds__(kCaBwdThreads, 1) ca_bwd_kernel(const CaBwdArg
       umma_commit(c.bar);
       mma_steps(tmem + T::V, make_smem_desc(smem_u32(xkv), kCS, kRS), 2 * kCS, make_smem_desc(smem_u32(bv), C::BV_LBO, 128),
                 2 * C::BV_LBO, make_idesc_bf16(128, C::DV, 0, 0), C::KE / 16, false);
+      mma_steps(tmem + T::V, make_smem_desc(smem_u32(xkv), kCS, kRS), 2 * kCS, make_smem_desc(smem_u32(bv_lo), C::BV_LBO, 128),
+                2 * C::BV_LBO, make_idesc_bf16(128, C::DV, 0, 0), C::KE / 16, true);      // the forward's hi + lo W_value
       for (int h = 0; h < 2; ++h)
         mma_steps(tmem + (uint32_t(16 * h) << 16) + T::DOUT, make_smem_desc(smem_u32(dls + h * 8 * kRS), kCS, kRS), 2 * kCS,
                   make_smem_desc(smem_u32(bc), 128, C::BC_LBO), 2 * 128, make_idesc_bf16(64, C::DV, 0, 1), kNCls / 16, false);
@@ -626,7 +630,7 @@ __global__ void __launch_bounds__(kCaBwdThreads, 1) ca_bwd_kernel(const CaBwdArg
       umma_commit(c.bar);
       mma_steps(tmem + T::G_WF, make_smem_desc(smem_u32(ob), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(dls), kRS, kCS), 2 * kRS,
                 make_idesc_bf16(64, kNCls, 1, 1), 8, !first);
-      mma_steps(tmem + T::G_LN, make_smem_desc(smem_u32(dyx), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(ones), 256, 128), 512,
+      mma_steps(tmem + T::G_LN, make_smem_desc(smem_u32(dyx), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(ones), 0, 128), 0,
                 make_idesc_bf16(128, 16, 1, 0), 8, !first);
       umma_commit(&bars[3]);
     }

@@ -16,6 +16,9 @@
 // step k is not written again before step k + 2, and a rank can only reach step k + 2 after every peer has published
 // its step k + 1 flags, i.e. finished reading step k: no trailing barrier either.  All CTAs must be co-resident
 // (grid <= number of SMs).
+// A peer that never publishes (crashed rank, torn-down mapping) must not hang the GPU: the wait is bounded
+// (kSpinTimeoutNs of %globaltimer, ~2 s); on expiry the CTA records the missing peer in the status word that follows
+// the flags in its own pad (mmrca_peer_allreduce_status reads it) and leaves its slice of the bucket untouched.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -25,6 +28,8 @@ namespace peer {
 
 constexpr int kMaxWorld = 8;
 constexpr int kCtas = 48, kThreads = 256;
+constexpr long long kSpinTimeoutNs = 2000000000LL;
+constexpr int kStatusWords = 4;      // after the flags: [0] = 1 + rank of a peer that timed out (0: healthy), rest reserved
 
 struct Args {
   float* flat;                       // local bucket, n floats (n % 4 == 0, 16-byte aligned): in/out
@@ -48,8 +53,12 @@ __device__ __forceinline__ float4 ld_peer(const float4* p) {      // not through
   return v;
 }
 
+__device__ __forceinline__ long long globaltimer_ns_peer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
 __global__ void __launch_bounds__(kThreads) allreduce_mean_kernel(const Args a) {
+  __shared__ int s_dead;
   const int tid = threadIdx.x, cta = blockIdx.x;
+  if (tid == 0) s_dead = 0;
   const int par = int(a.step & 1u);
   const int n4 = a.n / 4, per = (n4 + kCtas - 1) / kCtas, lo = cta * per, hi = min(n4, lo + per);
   float4* mine = reinterpret_cast<float4*>(const_cast<float*>(a.staging[a.rank])) + size_t(par) * (a.n_pad / 4);
@@ -60,9 +69,18 @@ __global__ void __launch_bounds__(kThreads) allreduce_mean_kernel(const Args a) 
     __threadfence_system();
     st_release_sys(a.pads[tid] + (size_t(par) * a.world + a.rank) * kCtas + cta, a.step);      // tell rank `tid`
     const uint32_t* f = a.pads[a.rank] + (size_t(par) * a.world + tid) * kCtas + cta;            // hear from rank `tid`
-    while (int32_t(ld_acquire_sys(f) - a.step) < 0) { }
+    const long long t0 = globaltimer_ns_peer();
+    uint32_t spins = 0;
+    while (int32_t(ld_acquire_sys(f) - a.step) < 0) {
+      if ((++spins & 1023u) == 0 && globaltimer_ns_peer() - t0 > kSpinTimeoutNs) {
+        a.pads[a.rank][size_t(2) * a.world * kCtas] = uint32_t(1 + tid);      // status word: peer `tid` never arrived
+        s_dead = 1;
+        break;
+      }
+    }
   }
   __syncthreads();
+  if (s_dead) return;
   // all W remote loads of an element group are in flight before the first one is consumed (a load-add-load-add loop
   // would pay one NVLink round trip per rank), two groups per thread interleaved
   const float inv = 1.0f / float(a.world);

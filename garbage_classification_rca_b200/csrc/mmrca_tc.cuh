@@ -206,6 +206,16 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float (&v)[8]) {
   return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
 }
 
+// hi = bf16(v) packed, lo[] = v - float(hi) (to be packed as the second half of a hi + lo pair)
+__device__ __forceinline__ uint4 pack_bf16x8_hilo(const float (&v)[8], float (&lo)[8]) {
+  const uint4 h = pack_bf16x8(v);
+  const uint32_t w[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+    lo[e] = v[e] - __uint_as_float((e & 1) ? (w[e >> 1] & 0xffff0000u) : (w[e >> 1] << 16));
+  return h;
+}
+
 // byte offset of the 16-byte chunk (row r, 8-column group kc) inside a canonical no-swizzle operand
 __device__ __forceinline__ uint32_t core_off(int r, int kc, uint32_t lbo, uint32_t sbo) {
   return uint32_t(kc) * lbo + uint32_t(r >> 3) * sbo + uint32_t(r & 7) * 16u;

@@ -11,6 +11,9 @@ namespace tc {
 // mode bit 1: A is MN-major (source a[K][128]) instead of K-major (source a[128][K])
 // mode bit 2: two M=64 MMAs (rows 0-63 and 64-127) instead of one M=128; the second accumulator sits 16 TMEM
 //             lanes up, i.e. a warp's lanes 0-15 hold rows 16q.. of the first half and lanes 16-31 rows 64+16q..
+// mode bit 3: the B descriptor has a ZERO leading-dimension stride and is not advanced along K: every 8-column group of
+//             B reads the bytes of group 0, i.e. B_eff[n][k] = b[n][k % 8] (K-major B only).  This is how a constant
+//             operand (the all-ones operand of the column-sum MMAs) can live in 16 bytes per row.
 // out[128][N] = A * B^T (logical A[128][K], B[N][K]).  N % 16 == 0, N <= 256, K % 16 == 0.
 __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(int mode, const float* __restrict__ a,
                                                               const float* __restrict__ b, float* __restrict__ out,
@@ -79,8 +82,10 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(int mode, const f
   const uint32_t taddr = tmem_base;
   const bool halves = mode & 4;
   if (tid == 0) {
+    const bool bzero = (mode & 8) && !b_mn;
     const uint64_t ad = make_smem_desc(smem_u32(sa), a_lbo, a_sbo);
-    const uint64_t bd = make_smem_desc(smem_u32(sb), b_lbo, b_sbo);
+    const uint64_t bd = make_smem_desc(smem_u32(sb), bzero ? 0u : b_lbo, b_sbo);
+    const uint32_t b_lbo = bzero ? 0u : (uint32_t(N) / 8) * 128 + 16;      // shadows: K-advance of the B descriptor
     if (!halves) {
       const uint32_t idesc = make_idesc_bf16(M, N, a_mn ? 1 : 0, b_mn ? 1 : 0);
       for (int ks = 0; ks < K / 16; ++ks)

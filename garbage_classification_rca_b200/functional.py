@@ -337,7 +337,12 @@ class HeadTrainStep:
                  drop_mask: Optional[torch.Tensor] = None, drop_scale: float = 1.0, drop_seed: int = 0):
         """drop_seed: seed of this step's dropout mask when the step was built with drop_p > 0."""
         self.desc.drop_seed = int(drop_seed) & (2 ** 64 - 1)
-        img, txt = _check_dev(img, "image features"), _check_dev(txt, "text features")
+        # bf16 features (a backbone under bf16 autocast, or a host hand-off that ships half the bytes): bf16 pipeline only
+        fdt = torch.bfloat16 if (img.dtype == torch.bfloat16 and txt.dtype == torch.bfloat16) else torch.float32
+        if fdt == torch.bfloat16 and self.desc.compute == N.COMPUTE_FP32:
+            raise TypeError("bf16 features need a step built with compute=COMPUTE_BF16")
+        self.desc.flags = (self.flags | N.FLAG_FEATURES_BF16) if fdt == torch.bfloat16 else self.flags
+        img, txt = _check_dev(img, "image features", fdt), _check_dev(txt, "text features", fdt)
         labels = _check_dev(labels, "labels", torch.int64)
         if img.shape != (self.desc.batch, self.desc.d_img) or txt.shape != (self.desc.batch, self.desc.d_txt):
             raise ValueError("feature shapes do not match the shapes this step was built for")

@@ -135,6 +135,17 @@ class PeerAllReduce:
                     "mmrca_peer_allreduce_mean")
         return flat
 
+    def status(self) -> int:
+        """0 = every peer arrived so far; 1 + r = rank r never published its flags within the kernel's bounded wait (the
+        bucket was left unreduced); synchronises the current stream."""
+        dev = self.buf.device
+        with torch.cuda.device(dev):
+            rc = N.lib().mmrca_peer_allreduce_status(self.pads[self.rank], self.world,
+                                                     torch.cuda.current_stream(dev).cuda_stream)
+        if rc < 0:
+            N.check(-rc, "mmrca_peer_allreduce_status")
+        return rc
+
 
 class HeadDataParallel:
     """Batch-sharded training of the fusion head on precomputed features: each rank runs the one-call

@@ -52,6 +52,10 @@ extern "C" {
 #define MMRCA_FLAG_CROSS_ATTENTION_ONLY 4u /* --cross_attention_only: concat = [T_I, I_T], :701-706 */
 #define MMRCA_FLAG_FEATURE_GRADS 256u      /* the backward will be asked for d_img_feat / d_txt_feat (fine-tune phase,
                                               main_both.py:687-694): set it for the forward too */
+#define MMRCA_FLAG_FEATURES_BF16 1024u     /* img_feat / txt_feat point to bf16 (not fp32) arrays of the same shape: cast the
+                                              pointers.  What a backbone under bf16 autocast hands over; halves the bytes a
+                                              host -> device hand-off ships.  Norms, the fp32 classifier terms and everything
+                                              downstream are computed from the bf16 values in fp32.  bf16 pipeline only. */
 #define MMRCA_FLAG_TRAINING 512u           /* mmrca_head_forward only: a mmrca_head_backward on the same workspace follows
                                               (autograd), so the forward keeps what the backward reloads and needs the
                                               training-size workspace.  Without it the forward is inference: nothing is
@@ -260,6 +264,10 @@ int mmrca_hier_train_step(const MmrcaHierDesc* desc, const MmrcaHierParams* para
 int mmrca_peer_allreduce_mean(float* flat, int32_t n, int32_t n_pad, const void* const* staging, void* const* pads,
                               int32_t rank, int32_t world, uint32_t step, void* stream);
 int mmrca_peer_allreduce_pad_bytes(int32_t world);
+/* The wait for a peer's flag is bounded (~2 s): a rank that never arrives does not hang the GPU; the kernel then leaves the
+ * bucket unreduced and records the peer in the status word behind the flags of this rank's own pad.  This call reads it
+ * (the one peer function that synchronises `stream`): 0 = healthy, 1 + r = rank r timed out, < 0 = -MMRCA_ERR_*. */
+int mmrca_peer_allreduce_status(const void* own_pad, int32_t world, void* stream);
 
 /* Per-kernel timing for roofline reports: between begin and end every kernel this library launches on
  * the calling thread is bracketed by a pair of CUDA events on ITS launch stream (up to max_records

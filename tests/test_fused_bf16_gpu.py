@@ -129,8 +129,16 @@ def test_fused_argmax_agreement(pkg):
 
 
 # ---- backward ------------------------------------------------------------------------------------------------------
-BF16_GRAD = {False: dict(cos=0.9995, flat_l2_rel=1e-2, worst_l2_rel=0.10, max_err_over_global=2.5e-2),   # full concat
-             True: dict(cos=0.998, flat_l2_rel=7e-2, worst_l2_rel=0.35, max_err_over_global=0.15)}       # cross-only
+# north_star: "fusion-head gradients within 1e-2 relative".  The bf16 pipeline is held to it NORM-WISE on the whole head
+# gradient (||g - g_ref||_2 / ||g_ref||_2 over the flat 94 820-entry bucket: what an optimizer step sees) on every
+# variant of configs[3]; measured 2.4e-3 (full concat) / 8.9e-3 (cross-only) at batch 200 and 0.9e-3 / 2.8e-3 at batch
+# 2048 (gpurun_out/r2_diag_*.log).  Per tensor the worst L2 error is 1 - 2.3 % (full) and up to 4.6 % (cross-only, on
+# 48- / 96-entry LayerNorm / bias tensors whose batch sum cancels): that residue is the bf16 rounding of the FORWARD
+# activations (X, V, SA output), each worth 0.5 - 2 % on those tensors (tools/emulate_bf16.py reproduces the GPU's
+# figures to 4 digits and attributes them site by site); only hi + lo pairs of every forward operand would remove it
+# (DESIGN.md §2).  The fp32 kernels meet 1e-2 per tensor with two orders of magnitude to spare (test_parity_gpu.py).
+BF16_GRAD = {False: dict(cos=0.99999, flat_l2_rel=5e-3, worst_l2_rel=3e-2, max_err_over_global=1e-2),    # full concat
+             True: dict(cos=0.9999, flat_l2_rel=1e-2, worst_l2_rel=6e-2, max_err_over_global=2.5e-2)}    # cross-only
 
 
 def check_bf16_grads(ours, ref, what, cross_only=False):
@@ -154,7 +162,7 @@ def test_fused_logits_loss_and_gradients(pkg, flags, qk_gain, drop_p):
     from garbage_classification_rca_b200 import functional as F
     from garbage_classification_rca_b200.training import CrossEntropyLoss
     rev, fo, co = flags
-    B, seed = 200, 77
+    B, seed = 512, 77
     p = orc.init_head_params(features_only=fo, cross_attention_only=co, seed=31, qk_gain=qk_gain)
     img, txt, labels = make_inputs(B, 31)
     mask, scale = None, 1.0
@@ -205,7 +213,7 @@ def test_fused_train_step_weighted_smoothed_dropout(pkg, B):
     assert abs(loss.item() - ref["loss"]) < 5e-3
     if B >= 64:
         ours = {n: v.cpu().numpy() / 2.0 for n, v in zip(names, step.grads.views)}
-        check_bf16_grads(ours, ref["grads"], f"train step B={B}")
+        check_bf16_grads(ours, ref["grads"], f"train step B={B}", cross_only=B < 200)   # 64 samples: the looser row
     # the feature-source rows of the classifier gradient (ce_feat_kernel): fp32 products of the bf16-rounded normalised
     # features (2^-9 relative per element)
     gw = step.grads.views[names.index("final_with_everything.weight")].cpu().numpy() / 2.0
@@ -287,3 +295,55 @@ def test_fused_features_only_train_step(pkg, B, drop_p, co):
             assert np.abs(g - r).max() <= 1e-2 * np.abs(r).max() + 1e-9, n
         else:
             assert np.abs(g).max() == 0.0, n
+
+
+def test_fused_gradients_at_benchmark_batch(pkg):
+    """BASELINE.json configs[1] itself: batch 4096, --reverse, dropout 0.6 - the whole head gradient against the float64
+    oracle (same keep mask).  The norm-wise error shrinks with the batch (the systematic weight-rounding term is gone
+    since the hi + lo W_value / classifier blobs): held to 3e-3, a third of north_star's 1e-2."""
+    from garbage_classification_rca_b200 import _native as N
+    from garbage_classification_rca_b200 import functional as F
+    B, seed, drop_p = 4096, 4242, 0.6
+    p = orc.init_head_params(seed=12, qk_gain=40.0)
+    img, txt, labels = make_inputs(B, 12)
+    mask = F.dropout_mask(seed, drop_p, B, 3584, "cuda").cpu().numpy()
+    ref = orc.np_head_forward_backward(p, img.numpy(), txt.numpy(), True, False, False, labels=labels.numpy(),
+                                       drop_mask=mask, drop_scale=1.0 / (1.0 - drop_p))
+    names = pkg.head_param_names()
+    step = pkg.HeadTrainStep([p[n].cuda() for n in names], B, 1280, 768, reverse=True, compute=N.COMPUTE_BF16, drop_p=drop_p)
+    step.zero_grad()
+    loss, logits = step(img.cuda(), txt.cuda(), labels.cuda(), drop_seed=seed)
+    torch.cuda.synchronize()
+    assert np.abs(logits.cpu().numpy() - ref["logits"]).max() < LOGITS_ABS_BF16 * 2.5
+    s = grad_summary({n: v.cpu().numpy() for n, v in zip(names, step.grads.views)}, ref["grads"])
+    assert s["flat_l2_rel"] <= 3e-3 and s["cos"] >= 0.99999, s
+    assert s["worst_l2_rel"] <= 3e-2 and s["max_err_over_global"] <= 5e-3, s
+
+
+@pytest.mark.parametrize("B", [8, 333])
+def test_fused_train_step_bf16_features(pkg, B):
+    """MMRCA_FLAG_FEATURES_BF16: the features arrive as bf16 (a backbone under bf16 autocast / a host hand-off shipping
+    half the bytes).  Against the oracle on the SAME (bf16-rounded) features the usual limits hold; against the oracle on
+    the original fp32 features the logits stay within north_star's 2e-2 absolute."""
+    from garbage_classification_rca_b200 import _native as N
+    p = orc.init_head_params(seed=21, qk_gain=40.0)
+    img, txt, labels = make_inputs(B, 600 + B)
+    img16, txt16 = img.bfloat16(), txt.bfloat16()
+    ref32 = orc.np_head_forward_backward(p, img.numpy(), txt.numpy(), True, False, False, labels=labels.numpy())
+    ref16 = orc.np_head_forward_backward(p, img16.float().numpy(), txt16.float().numpy(), True, False, False,
+                                         labels=labels.numpy())
+    names = pkg.head_param_names()
+    step = pkg.HeadTrainStep([p[n].cuda() for n in names], B, 1280, 768, reverse=True, compute=N.COMPUTE_BF16)
+    step.zero_grad()
+    loss, logits = step(img16.cuda(), txt16.cuda(), labels.cuda())
+    torch.cuda.synchronize()
+    lg = logits.cpu().numpy()
+    assert np.abs(lg - ref32["logits"]).max() < LOGITS_ABS_BF16
+    assert np.abs(lg - ref16["logits"]).max() < LOGITS_ABS_BF16
+    assert abs(loss.item() - ref16["loss"]) < 5e-3
+    if B >= 200:
+        check_bf16_grads({n: v.cpu().numpy() for n, v in zip(names, step.grads.views)}, ref16["grads"], "bf16 features")
+    # the same step object takes fp32 features again (the flag is per call)
+    step.zero_grad()
+    _, logits32 = step(img.cuda(), txt.cuda(), labels.cuda())
+    assert np.abs(logits32.cpu().numpy() - ref32["logits"]).max() < LOGITS_ABS_BF16
