@@ -604,7 +604,7 @@ def run_full(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from garbage_classification_rca_b200 import _native as N, multimodal_model as M
-    from garbage_classification_rca_b200.training import CrossEntropyLoss, allreduce_mean_
+    from garbage_classification_rca_b200.training import CrossEntropyLoss, FusedSGD, PeerAllReduce, allreduce_mean_
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -614,8 +614,22 @@ def run_full(args, rank, world, local_rank):
     with redirect_stdout(io.StringIO()):
         m = M.MM_RCA(4, args.dropout, 0.0, 0.7, 256, "bert", B, True, False, False, pretrained=False, compute=N.COMPUTE_BF16)
     m = m.to(dev).train()
-    head = [p for n, p in m.named_parameters() if not n.startswith(("image_model.", "text_model.")) and p.requires_grad]
-    opt = torch.optim.SGD(head, lr=1e-3)
+    # module path with ONE persistent gradient bucket (the backward kernels accumulate into it, p.grad are views), ONE
+    # collective on it, ONE fused SGD launch over the flat parameter bucket (reference: torch.optim.SGD, main_both.py:548)
+    fg = m.attach_flat_grads(flat_params=True)
+    opt = FusedSGD(m._flat_params, fg, lr=1e-3, weight_decay=0.03)
+    peer, collective = None, "none (1 GPU)"
+    if world > 1:
+        ok = torch.zeros(1, device=dev)
+        try:
+            peer = PeerAllReduce(fg.flat.numel(), dev)
+            ok += 1
+        except Exception:      # noqa: BLE001
+            peer = None
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() < 1:
+            peer = None
+        collective = "mmrca_peer_allreduce_mean (NVLink peer memory)" if peer is not None else "NCCL all_reduce"
     crit = CrossEntropyLoss()
     T = m.get_max_token_size()
     H, Wd = m.get_image_size()
@@ -623,51 +637,78 @@ def run_full(args, rank, world, local_rank):
     ids = torch.randint(0, 30522, (B, T), device=dev)
     mask = torch.ones_like(ids)
     labels = torch.randint(0, 4, (B,), device=dev)
+    sample_ids = torch.arange(B)
 
-    def one():
+    def one(cached=False):
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            logits = m(ids, mask, images)
+            logits = m(ids, mask, images, sample_ids=sample_ids if cached else None)
         loss = crit(logits.float(), labels)
         loss.backward()
         if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in head if p.grad is not None])
-            allreduce_mean_(flat)
-            o = 0
-            for p in head:
-                if p.grad is not None:
-                    p.grad.copy_(flat[o:o + p.numel()].view_as(p)); o += p.numel()
+            peer(fg.flat) if peer is not None else allreduce_mean_(fg.flat)
         opt.step()
-        opt.zero_grad(set_to_none=True)
+        opt.zero_grad()
         return loss
+
+    def timed(fn, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            out = fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms, out
 
     for _ in range(W):
         one()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     N.kernel_launches(reset=True)
-    e0.record()
-    for _ in range(K):
-        loss = one()
-    e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t[0])
+    ms, loss = timed(one, K)
+    launches = N.kernel_launches()
+    # the head's share of that step: the same head work (hand-off output -> logits -> loss -> backward -> fused SGD) alone
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        m._images, m._input_ids, m._attention_mask = images, ids, mask
+        feats = m.backbone_features()
+
+    def head_only():
+        l = crit(m.forward_features(*feats).float(), labels)
+        l.backward()
+        opt.step()
+        opt.zero_grad()
+        return l
+
+    for _ in range(3):
+        head_only()
+    ms_head, _ = timed(head_only, 4 * K)
+    # epochs >= 2 of the frozen phase with the feature cache (training.FeatureCache): the backbones are skipped
+    m.enable_feature_cache(B)
+    for _ in range(3):
+        one(cached=True)
+    ms_cached, _ = timed(lambda: one(cached=True), 4 * K)
     if rank == 0:
         emit(json.dumps({
             "metric": "mmrca_full_step_samples_per_s", "value": world * B * K / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": f"full MM_RCA --reverse step, EfficientNetV2-M {H}x{Wd} + BERT-base {T} tokens (stock torch, bf16 "
-                                   f"autocast, frozen random-init), B200 fusion head, batch {B}/GPU (BASELINE.json configs[2]; "
-                                   "secondary workload)", "parallelism": f"dp{world}", "loss": float(loss.item())},
-            "gpu_launches": N.kernel_launches()}))
+                                   f"autocast, frozen random-init), fused feature hand-off, B200 fusion head (bf16 pipeline, bf16 features), "
+                                   f"flat gradient bucket + fused SGD, batch {B}/GPU (BASELINE.json configs[2]; secondary workload)",
+                       "parallelism": f"dp{world}", "collective": collective, "loss": float(loss.item())},
+            "head": {"ms_per_step": ms_head / (4 * K), "share_of_step": (ms_head / (4 * K)) / (ms / K),
+                     "what": "logits + CrossEntropyLoss + backward + fused SGD on the hand-off's features, module path"},
+            "cached_features": {"value": world * B * 4 * K / (ms_cached * 1e-3), "unit": "samples/s",
+                                "ms_per_step": ms_cached / (4 * K),
+                                "what": "the same step with training.FeatureCache (frozen phase, epochs >= 2: backbones skipped)"},
+            "gpu_launches": launches}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -4,8 +4,9 @@ Host side: Python/PyTorch mirror of the reference model API (multimodal_model.py
 Device side: hand-written sm_100a CUDA kernels behind a C ABI (include/mmrca.h, libmmrca.so).
 """
 from . import _native, functional
-from .functional import (HeadTrainStep, HierTrainStep, attention_block, concat_width, cross_entropy,
-                         final_linear_name, head_param_names, hierarchical_head, mmrca_head)
+from .functional import (FusionTrainStep, HeadTrainStep, HierTrainStep, attention_block, concat_width, cross_entropy,
+                         feature_handoff, final_linear_name, fusion_head, head_param_names, hierarchical_head, mmrca_head)
 
-__all__ = ["_native", "functional", "HeadTrainStep", "HierTrainStep", "attention_block", "concat_width", "cross_entropy",
-           "final_linear_name", "head_param_names", "hierarchical_head", "mmrca_head"]
+__all__ = ["_native", "functional", "FusionTrainStep", "HeadTrainStep", "HierTrainStep", "attention_block", "concat_width",
+           "cross_entropy", "feature_handoff", "final_linear_name", "fusion_head", "head_param_names", "hierarchical_head",
+           "mmrca_head"]

@@ -62,6 +62,19 @@ class HierDesc(C.Structure):
     _fields_ = [("batch", C.c_int32), ("n_classes", C.c_int32), ("drop_p", C.c_float), ("drop_seed", C.c_uint64)]
 
 
+class FusionParams(C.Structure):
+    """MmrcaFusionParams / MmrcaFusionGrads (same layout)."""
+    _fields_ = [(n, _fp) for n in ("w_img", "b_img", "w_txt", "b_txt", "w_cat", "b_cat", "w_fc", "b_fc")]
+
+
+class FusionDesc(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("d_img", C.c_int32), ("d_txt", C.c_int32), ("hidden", C.c_int32),
+                ("n_classes", C.c_int32), ("flags", C.c_uint32), ("drop_p", C.c_float), ("drop_seed", C.c_uint64)]
+
+
+FUSION_NORMALIZED = 1
+
+
 class CeDesc(C.Structure):
     _fields_ = [("class_weight", _fp), ("label_smoothing", C.c_float)]
 
@@ -72,7 +85,9 @@ EXPORTS = ("mmrca_query", "mmrca_last_error", "mmrca_head_workspace_bytes", "mmr
            "mmrca_timing_end", "mmrca_dev_umma_selftest", "mmrca_attention_forward_scratch_bytes",
            "mmrca_head_workspace_offset", "mmrca_dropout_mask", "mmrca_dev_set_debug",
            "mmrca_hier_workspace_bytes", "mmrca_hier_forward", "mmrca_hier_backward", "mmrca_hier_train_step",
-           "mmrca_peer_allreduce_mean", "mmrca_peer_allreduce_pad_bytes", "mmrca_peer_allreduce_status")
+           "mmrca_peer_allreduce_mean", "mmrca_peer_allreduce_pad_bytes", "mmrca_peer_allreduce_status",
+           "mmrca_feature_handoff", "mmrca_sgd_step", "mmrca_adamw_step",
+           "mmrca_fusion_workspace_bytes", "mmrca_fusion_forward", "mmrca_fusion_backward", "mmrca_fusion_train_step")
 
 
 def _sources_newer_than_lib() -> bool:
@@ -180,6 +195,25 @@ def lib() -> C.CDLL:
         L.mmrca_peer_allreduce_pad_bytes.restype = C.c_int
         L.mmrca_peer_allreduce_status.argtypes = [_fp, C.c_int32, _fp]
         L.mmrca_peer_allreduce_status.restype = C.c_int
+        L.mmrca_fusion_workspace_bytes.argtypes = [C.c_void_p]
+        L.mmrca_fusion_workspace_bytes.restype = C.c_size_t
+        L.mmrca_fusion_forward.argtypes = [C.c_void_p, C.c_void_p, _fp, _fp, _fp, C.c_float, _fp, _fp, C.c_size_t, _fp]
+        L.mmrca_fusion_forward.restype = C.c_int
+        L.mmrca_fusion_backward.argtypes = [C.c_void_p, C.c_void_p, _fp, _fp, _fp, C.c_float, _fp, C.c_void_p, _fp, _fp,
+                                            _fp, C.c_size_t, _fp]
+        L.mmrca_fusion_backward.restype = C.c_int
+        L.mmrca_fusion_train_step.argtypes = [C.c_void_p, C.c_void_p, _fp, _fp, _fp, C.c_float, _fp, C.c_void_p, _fp, _fp,
+                                              C.c_void_p, _fp, _fp, _fp, C.c_size_t, _fp]
+        L.mmrca_fusion_train_step.restype = C.c_int
+        L.mmrca_feature_handoff.argtypes = [_fp, C.c_int32, C.c_int64, C.c_int32, _fp, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_int32, C.c_int32, _fp, _fp, C.c_int32, _fp]
+        L.mmrca_feature_handoff.restype = C.c_int
+        L.mmrca_sgd_step.argtypes = [_fp, _fp, _fp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
+                                     C.c_int32, _fp]
+        L.mmrca_sgd_step.restype = C.c_int
+        L.mmrca_adamw_step.argtypes = [_fp, _fp, _fp, _fp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
+                                       C.c_float, C.c_int32, _fp]
+        L.mmrca_adamw_step.restype = C.c_int
         if L.mmrca_query(QUERY_ABI_VERSION) != ABI_VERSION:
             raise RuntimeError("libmmrca.so ABI version mismatch: rebuild it")
         _lib = L

@@ -4,7 +4,9 @@
 #include "../../include/mmrca.h"
 
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <atomic>
+#include <math.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -16,6 +18,8 @@
 #include "mmrca_head_tc_bwd.cuh"
 #include "mmrca_hier.cuh"
 #include "mmrca_peer.cuh"
+#include "mmrca_train_aux.cuh"
+#include "mmrca_fusion_fp32.cuh"
 
 namespace mmrca {
 
@@ -804,6 +808,158 @@ static int hier_backward_impl(const MmrcaHierDesc& d, const MmrcaHierParams& p, 
   return MMRCA_OK;
 }
 
+// ---- classic / normalized fusion heads (mmrca_fusion_fp32.cuh) ---------------------------------------------------------
+struct FusionWorkspace {
+  float *h_img, *h_txt, *n_img, *n_txt, *c, *d_c, *d_h_img, *d_h_txt, *dlogits;
+  uint8_t* mask;
+  size_t bytes;
+};
+static FusionWorkspace fusion_carve(const MmrcaFusionDesc& d, void* base) {
+  FusionWorkspace w;
+  memset(&w, 0, sizeof(w));
+  char* p = static_cast<char*>(base);
+  size_t off = 0;
+  const size_t B = size_t(d.batch > 0 ? d.batch : 0), H = size_t(d.hidden > 0 ? d.hidden : 0);
+  auto take = [&](size_t floats) { float* r = reinterpret_cast<float*>(p + off); off += align_up_256(floats * 4); return r; };
+  w.h_img = take(B * H); w.h_txt = take(B * H); w.n_img = take(B); w.n_txt = take(B); w.c = take(B * H);
+  w.mask = reinterpret_cast<uint8_t*>(take((B * H + 3) / 4));
+  w.d_c = take(B * H); w.d_h_img = take(B * H); w.d_h_txt = take(B * H);
+  w.dlogits = take(B * size_t(d.n_classes > 0 ? d.n_classes : 0));
+  w.bytes = off;
+  return w;
+}
+static int fusion_check(const MmrcaFusionDesc* d) {
+  if (!d) return fail(MMRCA_ERR_INVALID, "null descriptor%s%s");
+  if (d->batch < 0 || d->d_img <= 0 || d->d_txt <= 0 || d->hidden <= 0 || (d->hidden & 3))
+    return fail(MMRCA_ERR_INVALID, "fusion head: batch >= 0, positive widths, hidden a multiple of 4%s%s");
+  if (d->n_classes < 1 || d->n_classes > 8) return fail(MMRCA_ERR_INVALID, "n_classes must be in [1, 8]%s%s");
+  if (!(d->drop_p >= 0.f && d->drop_p <= 1.f)) return fail(MMRCA_ERR_INVALID, "drop_p must be in [0, 1]%s%s");
+  return MMRCA_OK;
+}
+static int launch_sgemm(const fus::GemmArgs& g, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return MMRCA_OK;
+  {
+    LaunchScope ls("fusion_sgemm", st);
+    fus::sgemm_kernel<<<dim3((g.N + fus::kTN - 1) / fus::kTN, (g.M + fus::kTM - 1) / fus::kTM), 256, 0, st>>>(g);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+static fus::GemmArgs gemm_args(const float* a, long long sa_m, long long sa_k, const float* b, long long sb_k, long long sb_n,
+                               float* c, long long ldc, int M, int N, int K, const float* bias, bool acc) {
+  fus::GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.a = a; g.sa_m = sa_m; g.sa_k = sa_k; g.b = b; g.sb_k = sb_k; g.sb_n = sb_n; g.c = c; g.ldc = ldc;
+  g.M = M; g.N = N; g.K = K; g.bias = bias; g.accumulate = acc ? 1 : 0;
+  return g;
+}
+static int launch_colsum(const float* x, int ld, int rows, int n, float* out, int sms, cudaStream_t st) {
+  if (!out || rows <= 0) return MMRCA_OK;
+  {
+    LaunchScope ls("fusion_colsum", st);
+    fus::colsum_kernel<<<dim3((n + 31) / 32, max(1, min((rows + 63) / 64, 2 * sms))), 256, 0, st>>>(x, ld, rows, n, out);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+static DropSpec fusion_drop(const MmrcaFusionDesc& d) {
+  MmrcaHeadDesc h;
+  memset(&h, 0, sizeof(h));
+  h.drop_p = d.drop_p; h.drop_seed = d.drop_seed;
+  DropSpec s = make_drop(h);
+  s.D = d.hidden;
+  if (d.drop_p <= 0.f) s.thresh = 0;
+  return s;
+}
+static CatArgs fusion_cat(const MmrcaFusionDesc& d, const MmrcaFusionParams& p, const FusionWorkspace& w,
+                          const uint8_t* mask, float scale) {
+  CatArgs c;
+  memset(&c, 0, sizeof(c));
+  c.seg[0].src = w.c; c.seg[0].width = d.hidden; c.nseg = 1; c.D = d.hidden; c.batch = d.batch;
+  c.mask = mask; c.scale = scale; c.wf = p.w_fc; c.bf = p.b_fc;
+  return c;
+}
+static int fusion_forward_impl(const MmrcaFusionDesc& d, const MmrcaFusionParams& p, const float* img, const float* txt,
+                               const uint8_t*& mask, float& scale, float* logits, const FusionWorkspace& w, int sms,
+                               cudaStream_t st) {
+  const int B = d.batch, H = d.hidden;
+  const bool nrm = (d.flags & MMRCA_FUSION_NORMALIZED) != 0;
+  int rc;
+  if (B == 0) return MMRCA_OK;
+  // image_to_hidden_size / text_to_hidden_size (multimodal_model.py:521-522, :566-567)
+  if ((rc = launch_sgemm(gemm_args(img, d.d_img, 1, p.w_img, 1, d.d_img, w.h_img, H, B, H, d.d_img, p.b_img, false), st))) return rc;
+  if ((rc = launch_sgemm(gemm_args(txt, d.d_txt, 1, p.w_txt, 1, d.d_txt, w.h_txt, H, B, H, d.d_txt, p.b_txt, false), st))) return rc;
+  if (nrm) {      // :569-570, no epsilon
+    const int grid = min((B + kWarps - 1) / kWarps, 8 * sms);
+    { LaunchScope ls("l2norm", st); l2norm_kernel<<<grid, kThreads, 0, st>>>(w.h_img, w.n_img, B, H); }
+    { LaunchScope ls("l2norm", st); l2norm_kernel<<<grid, kThreads, 0, st>>>(w.h_txt, w.n_txt, B, H); }
+    MMRCA_CUDA(cudaGetLastError());
+  }
+  // concat + concat_layer (:524-527, :572-575): two accumulating GEMMs over the halves of W_cat
+  fus::GemmArgs g = gemm_args(w.h_img, H, 1, p.w_cat, 1, 2 * H, w.c, H, B, H, H, p.b_cat, false);
+  g.inv_m = nrm ? w.n_img : nullptr;
+  if ((rc = launch_sgemm(g, st))) return rc;
+  g = gemm_args(w.h_txt, H, 1, p.w_cat + H, 1, 2 * H, w.c, H, B, H, H, nullptr, true);
+  g.inv_m = nrm ? w.n_txt : nullptr;
+  if ((rc = launch_sgemm(g, st))) return rc;
+  // self.drop + fc_layer (:528-529, :576-577)
+  if (!mask && d.drop_p > 0.f) {
+    const DropSpec ds = fusion_drop(d);
+    {
+      LaunchScope ls("dropout_mask", st);
+      dropout_mask_kernel<<<min(4 * sms, max(1, int((size_t(B) * H / 4 + 255) / 256))), 256, 0, st>>>(ds, B, w.mask);
+    }
+    MMRCA_CUDA(cudaGetLastError());
+    mask = w.mask; scale = ds.scale;
+  }
+  CatArgs c = fusion_cat(d, p, w, mask, scale);
+  c.logits = logits;
+  return classifier_dispatch(false, d.n_classes, c, sms, st);
+}
+static int fusion_backward_impl(const MmrcaFusionDesc& d, const MmrcaFusionParams& p, const float* img, const float* txt,
+                                const uint8_t* mask, float scale, const float* dlogits, const MmrcaFusionGrads& g,
+                                float* d_img, float* d_txt, const FusionWorkspace& w, int sms, cudaStream_t st) {
+  const int B = d.batch, H = d.hidden;
+  const bool nrm = (d.flags & MMRCA_FUSION_NORMALIZED) != 0;
+  int rc;
+  if (B == 0) return MMRCA_OK;
+  if (!mask && d.drop_p > 0.f) { mask = w.mask; scale = fusion_drop(d).scale; }      // materialised by the forward
+  // fc_layer + dropout backward: dW_fc, db_fc, d_c
+  CatArgs c = fusion_cat(d, p, w, mask, scale);
+  c.dlogits = dlogits; c.g_wf = g.w_fc; c.g_bf = g.b_fc; c.seg[0].dst = w.d_c;
+  if ((rc = classifier_dispatch(true, d.n_classes, c, sms, st))) return rc;
+  // concat_layer: db, dW (two halves), d(hidden halves)
+  if ((rc = launch_colsum(w.d_c, H, B, H, g.b_cat, sms, st))) return rc;
+  const float* hs[2] = {w.h_img, w.h_txt};
+  const float* ns[2] = {w.n_img, w.n_txt};
+  float* dhs[2] = {w.d_h_img, w.d_h_txt};
+  for (int m = 0; m < 2; ++m) {
+    fus::GemmArgs a = gemm_args(w.d_c, 1, H, hs[m], H, 1, g.w_cat + m * H, 2 * H, H, H, B, nullptr, true);
+    a.inv_k = nrm ? ns[m] : nullptr;
+    if ((rc = launch_sgemm(a, st))) return rc;
+    if ((rc = launch_sgemm(gemm_args(w.d_c, H, 1, p.w_cat + m * H, 2 * H, 1, dhs[m], H, B, H, H, nullptr, false), st))) return rc;
+    if (nrm) {      // through h / ||h||
+      const int grid = min((B + kWarps - 1) / kWarps, 8 * sms);
+      { LaunchScope ls("l2norm_bwd", st); l2norm_bwd_kernel<<<grid, kThreads, 0, st>>>(hs[m], ns[m], dhs[m], B, H); }
+      MMRCA_CUDA(cudaGetLastError());
+    }
+  }
+  // the two projections: db, dW, optionally d(features)
+  const float* xs[2] = {img, txt};
+  const int dins[2] = {d.d_img, d.d_txt};
+  float* gws[2] = {g.w_img, g.w_txt};
+  float* gbs[2] = {g.b_img, g.b_txt};
+  const float* ws[2] = {p.w_img, p.w_txt};
+  float* dxs[2] = {d_img, d_txt};
+  for (int m = 0; m < 2; ++m) {
+    if ((rc = launch_colsum(dhs[m], H, B, H, gbs[m], sms, st))) return rc;
+    if ((rc = launch_sgemm(gemm_args(dhs[m], 1, H, xs[m], dins[m], 1, gws[m], dins[m], H, dins[m], B, nullptr, true), st))) return rc;
+    if (dxs[m] && (rc = launch_sgemm(gemm_args(dhs[m], H, 1, ws[m], dins[m], 1, dxs[m], dins[m], B, dins[m], H, nullptr, false), st)))
+      return rc;
+  }
+  return MMRCA_OK;
+}
+
 }  // namespace mmrca
 
 using namespace mmrca;
@@ -946,6 +1102,60 @@ int mmrca_head_train_step(const MmrcaHeadDesc* desc, const MmrcaHeadParams* para
                             d_txt_feat, w, di.sms, st);
 }
 
+size_t mmrca_fusion_workspace_bytes(const MmrcaFusionDesc* desc) {
+  if (fusion_check(desc)) return 0;
+  return fusion_carve(*desc, nullptr).bytes;
+}
+
+static int fusion_common(const MmrcaFusionDesc* desc, const void* a, const void* b, const void* c, const void* e, void* ws,
+                         size_t ws_bytes, FusionWorkspace* w, DeviceInfo* di) {
+  int rc;
+  if ((rc = fusion_check(desc))) return rc;
+  if (!a || !b || !c || !e || !ws) return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
+  if ((rc = device_info(di))) return rc;
+  *w = fusion_carve(*desc, ws);
+  if (ws_bytes < w->bytes) return fail(MMRCA_ERR_WORKSPACE, "workspace too small%s%s");
+  return MMRCA_OK;
+}
+
+int mmrca_fusion_forward(const MmrcaFusionDesc* desc, const MmrcaFusionParams* params, const float* img_feat,
+                         const float* txt_feat, const uint8_t* drop_mask, float drop_scale, float* logits, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  FusionWorkspace w; DeviceInfo di;
+  int rc;
+  if ((rc = fusion_common(desc, params, img_feat, txt_feat, logits, workspace, workspace_bytes, &w, &di))) return rc;
+  return fusion_forward_impl(*desc, *params, img_feat, txt_feat, drop_mask, drop_scale, logits, w, di.sms,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int mmrca_fusion_backward(const MmrcaFusionDesc* desc, const MmrcaFusionParams* params, const float* img_feat,
+                          const float* txt_feat, const uint8_t* drop_mask, float drop_scale, const float* dlogits,
+                          const MmrcaFusionGrads* grads, float* d_img_feat, float* d_txt_feat, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  FusionWorkspace w; DeviceInfo di;
+  int rc;
+  if ((rc = fusion_common(desc, params, img_feat, txt_feat, dlogits, workspace, workspace_bytes, &w, &di))) return rc;
+  if (!grads) return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
+  return fusion_backward_impl(*desc, *params, img_feat, txt_feat, drop_mask, drop_scale, dlogits, *grads, d_img_feat,
+                              d_txt_feat, w, di.sms, static_cast<cudaStream_t>(stream));
+}
+
+int mmrca_fusion_train_step(const MmrcaFusionDesc* desc, const MmrcaFusionParams* params, const float* img_feat,
+                            const float* txt_feat, const uint8_t* drop_mask, float drop_scale, const int64_t* labels,
+                            const MmrcaCeDesc* ce, float* logits, float* loss_out, const MmrcaFusionGrads* grads,
+                            float* d_img_feat, float* d_txt_feat, void* workspace, size_t workspace_bytes, void* stream) {
+  FusionWorkspace w; DeviceInfo di;
+  int rc;
+  if ((rc = fusion_common(desc, params, img_feat, txt_feat, logits, workspace, workspace_bytes, &w, &di))) return rc;
+  if (!grads || !labels || !loss_out) return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
+  if (desc->batch == 0) return MMRCA_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((rc = fusion_forward_impl(*desc, *params, img_feat, txt_feat, drop_mask, drop_scale, logits, w, di.sms, st))) return rc;
+  if ((rc = launch_ce(logits, labels, ce, desc->batch, desc->n_classes, loss_out, w.dlogits, st))) return rc;
+  return fusion_backward_impl(*desc, *params, img_feat, txt_feat, drop_mask, drop_scale, w.dlogits, *grads, d_img_feat,
+                              d_txt_feat, w, di.sms, st);
+}
+
 size_t mmrca_hier_workspace_bytes(const MmrcaHierDesc* desc) {
   if (hier_check(desc)) return 0;
   return hier_carve(desc->batch, nullptr).bytes;
@@ -1042,6 +1252,79 @@ int mmrca_peer_allreduce_status(const void* own_pad, int32_t world, void* stream
                       cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
     return -fail(MMRCA_ERR_CUDA, "reading the peer all-reduce status word failed%s%s");
   return int(word);
+}
+
+int mmrca_feature_handoff(const void* hidden, int32_t hidden_bf16, int64_t hidden_batch_stride, int32_t d_txt,
+                          const void* fmap, int32_t fmap_bf16, int32_t channels, int32_t hw, int32_t channels_last,
+                          int32_t batch, void* txt_out, void* img_out, int32_t out_bf16, void* stream) {
+  if (!hidden || !fmap || !txt_out || !img_out) return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
+  if (batch < 0 || d_txt <= 0 || channels <= 0 || hw <= 0 || hidden_batch_stride < d_txt)
+    return fail(MMRCA_ERR_INVALID, "bad hand-off shape%s%s");
+  DeviceInfo di;
+  int rc;
+  if ((rc = device_info(&di))) return rc;
+  if (batch == 0) return MMRCA_OK;
+  if (batch > 65535) return fail(MMRCA_ERR_INVALID, "hand-off batch must be <= 65535%s%s");
+  aux::HandoffArgs a;
+  memset(&a, 0, sizeof(a));
+  a.hidden = hidden; a.hidden_bstride = hidden_batch_stride; a.hidden_bf16 = hidden_bf16 ? 1 : 0; a.d_txt = d_txt;
+  a.fmap = fmap; a.fmap_bf16 = fmap_bf16 ? 1 : 0; a.channels = channels; a.hw = hw; a.channels_last = channels_last ? 1 : 0;
+  a.txt_out = txt_out; a.img_out = img_out; a.out_bf16 = out_bf16 ? 1 : 0; a.batch = batch;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    LaunchScope ls("feature_handoff", st);
+    aux::feature_handoff_kernel<<<dim3((channels + 31) / 32 + 1, batch), 256, 0, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+
+static int check_bucket(const void* p, int64_t n) {
+  if (!p || n <= 0 || (n & 3) || (reinterpret_cast<uintptr_t>(p) & 15))
+    return fail(MMRCA_ERR_INVALID, "optimizer buckets must be non-null, 16-byte aligned, with a multiple of 4 floats%s%s");
+  return MMRCA_OK;
+}
+
+int mmrca_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n, float lr, float momentum,
+                   float dampening, float weight_decay, int32_t nesterov, int32_t first_step, void* stream) {
+  int rc;
+  if ((rc = check_bucket(params, n)) || (rc = check_bucket(grads, n))) return rc;
+  if (momentum != 0.f && (rc = check_bucket(momentum_buf, n))) return rc;
+  DeviceInfo di;
+  if ((rc = device_info(&di))) return rc;
+  aux::SgdArgs a;
+  a.p = params; a.g = grads; a.buf = momentum != 0.f ? momentum_buf : nullptr; a.n4 = n / 4;
+  a.lr = lr; a.momentum = momentum; a.dampening = dampening; a.weight_decay = weight_decay;
+  a.nesterov = nesterov ? 1 : 0; a.first_step = first_step ? 1 : 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    LaunchScope ls("sgd_step", st);
+    aux::sgd_step_kernel<<<int(std::min<long long>((a.n4 + 255) / 256, 2LL * di.sms)), 256, 0, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+
+int mmrca_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, int32_t step, void* stream) {
+  int rc;
+  if ((rc = check_bucket(params, n)) || (rc = check_bucket(grads, n)) || (rc = check_bucket(exp_avg, n)) ||
+      (rc = check_bucket(exp_avg_sq, n))) return rc;
+  if (step < 1) return fail(MMRCA_ERR_INVALID, "AdamW step counts from 1%s%s");
+  DeviceInfo di;
+  if ((rc = device_info(&di))) return rc;
+  aux::AdamwArgs a;
+  a.p = params; a.g = grads; a.m = exp_avg; a.v = exp_avg_sq; a.n4 = n / 4;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
+  a.bias1 = float(1.0 - pow(double(beta1), double(step)));
+  a.bias2_sqrt = float(sqrt(1.0 - pow(double(beta2), double(step))));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    LaunchScope ls("adamw_step", st);
+    aux::adamw_step_kernel<<<int(std::min<long long>((a.n4 + 255) / 256, 2LL * di.sms)), 256, 0, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
 }
 
 size_t mmrca_attention_forward_scratch_bytes(int32_t, int32_t, int32_t, int32_t) { return 0; }

@@ -200,10 +200,18 @@ class _HeadFunction(torch.autograd.Function):
     """logits = MM_RCA head(img_feat, txt_feat); backward recomputes attention internals on chip."""
 
     @staticmethod
-    def forward(ctx, img, txt, drop_mask, drop_scale, flags, n_classes, compute, drop_p, drop_seed, *params):
-        img = _check_dev(img, "image features")
-        txt = _check_dev(txt, "text features")
+    def forward(ctx, img, txt, drop_mask, drop_scale, flags, n_classes, compute, drop_p, drop_seed, grad_sink, *params):
+        fdt = torch.float32
+        if img.dtype == torch.bfloat16 and txt.dtype == torch.bfloat16:      # MMRCA_FLAG_FEATURES_BF16
+            if compute == N.COMPUTE_FP32 or ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or drop_mask is not None:
+                raise TypeError("bf16 features are taken by the bf16 pipeline with frozen backbones and seeded dropout only; "
+                                "pass fp32 features otherwise")
+            fdt = torch.bfloat16
+            flags |= N.FLAG_FEATURES_BF16
+        img = _check_dev(img, "image features", fdt)
+        txt = _check_dev(txt, "text features", fdt)
         params = [_check_dev(p, "head parameter") for p in params]
+        ctx.grad_sink = grad_sink
         B, d_img, d_txt = img.shape[0], img.shape[1], txt.shape[1]
         if txt.shape[0] != B:
             raise ValueError("image and text feature batches differ")
@@ -239,7 +247,10 @@ class _HeadFunction(torch.autograd.Function):
         dlogits = _check_dev(dlogits, "dlogits")
         B = img.shape[0]
         desc = _desc(B, img.shape[1], txt.shape[1], n_classes, flags, compute, drop_p, drop_seed)
-        fg = FlatGrads(params)
+        # gradients accumulate (+=) straight into the module's persistent bucket when one is attached
+        # (MM_RCA.attach_flat_grads: p.grad IS a view of it), else into a fresh bucket returned to autograd
+        sink = ctx.grad_sink
+        fg = sink if sink is not None else FlatGrads(params)
         want_feat = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         d_img = torch.empty_like(img) if want_feat else None
         d_txt = torch.empty_like(txt) if want_feat else None
@@ -256,19 +267,23 @@ class _HeadFunction(torch.autograd.Function):
         features_only = bool(flags & N.FLAG_FEATURES_ONLY)
         pg = []
         for i, v in enumerate(fg.views):
-            need = ctx.needs_input_grad[9 + i]
+            need = ctx.needs_input_grad[10 + i] and sink is None
             # features_only: the attention blocks are outside the graph in the reference (their result is
             # discarded, multimodal_model.py:676-699) -> grad None, like autograd there.
             pg.append(v if need and not (features_only and i < 32) else None)
         return (d_img if ctx.needs_input_grad[0] else None, d_txt if ctx.needs_input_grad[1] else None,
-                None, None, None, None, None, None, None, *pg)
+                None, None, None, None, None, None, None, None, *pg)
 
 
 def mmrca_head(img_feat: torch.Tensor, txt_feat: torch.Tensor, params: Sequence[torch.Tensor], *,
                reverse: bool, features_only: bool = False, cross_attention_only: bool = False,
                n_classes: int = 4, drop_mask: Optional[torch.Tensor] = None, drop_scale: float = 1.0,
-               drop_p: float = 0.0, drop_seed: int = 0, compute: int = N.COMPUTE_FP32) -> torch.Tensor:
+               drop_p: float = 0.0, drop_seed: int = 0, compute: int = N.COMPUTE_FP32,
+               grad_sink: Optional["FlatGrads"] = None) -> torch.Tensor:
     """Fusion head of MM_RCA.forward (reference multimodal_model.py:661-728) on pooled features.
+
+    grad_sink: a persistent FlatGrads over `params` (same order): the backward accumulates into it and returns no
+    parameter gradients to autograd (the caller has pointed every p.grad at its view, training.attach_flat_grads).
 
     params: the 34 tensors in head_param_names(features_only, cross_attention_only) order.
     self.drop (:719), two ways:
@@ -279,7 +294,7 @@ def mmrca_head(img_feat: torch.Tensor, txt_feat: torch.Tensor, params: Sequence[
     if drop_mask is not None:
         drop_p, drop_seed = 0.0, 0
     return _HeadFunction.apply(img_feat, txt_feat, drop_mask, drop_scale, flags, n_classes, compute,
-                               float(drop_p), int(drop_seed), *params)
+                               float(drop_p), int(drop_seed), grad_sink, *params)
 
 
 def cross_entropy(logits: torch.Tensor, labels: torch.Tensor, class_weight: Optional[torch.Tensor] = None,
@@ -299,6 +314,42 @@ def cross_entropy(logits: torch.Tensor, labels: torch.Tensor, class_weight: Opti
                                             loss.data_ptr(), dl.data_ptr() if dl is not None else None,
                                             _stream_ptr(logits.device)), "mmrca_cross_entropy")
     return loss, dl
+
+
+def feature_handoff(hidden: torch.Tensor, fmap: torch.Tensor, out_dtype: torch.dtype = torch.bfloat16
+                    ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(image features [B, C], text features [B, H]) from the stock backbones' raw outputs in ONE kernel: the CLS row of
+    the text backbone's last hidden state `hidden` [B, T, H] (reference multimodal_model.py:651-658) and the global average
+    pool + flatten of the image backbone's final feature map `fmap` [B, C, h, w] (:25-36), cast to `out_dtype` (bf16: what
+    the head takes with MMRCA_FLAG_FEATURES_BF16).  fp32 or bf16 inputs, NCHW or channels_last maps."""
+    for t, what in ((hidden, "hidden state"), (fmap, "feature map")):
+        if not t.is_cuda:
+            raise RuntimeError(f"{what} must be a CUDA tensor: the hand-off has no CPU fallback")
+        if t.dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError(f"{what} must be fp32 or bf16, got {t.dtype}")
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("out_dtype must be fp32 or bf16")
+    B, T, H = hidden.shape
+    if hidden.stride(2) != 1 or hidden.stride(1) != H:
+        hidden = hidden.contiguous()
+    Bf, Cc, h, w = fmap.shape
+    if Bf != B:
+        raise ValueError("hidden state and feature map batches differ")
+    if fmap.is_contiguous():
+        channels_last = 0
+    elif fmap.is_contiguous(memory_format=torch.channels_last):
+        channels_last = 1
+    else:
+        fmap, channels_last = fmap.contiguous(), 0
+    txt = torch.empty(B, H, dtype=out_dtype, device=hidden.device)
+    img = torch.empty(B, Cc, dtype=out_dtype, device=hidden.device)
+    if B > 0:
+        with torch.cuda.device(hidden.device):
+            N.check(N.lib().mmrca_feature_handoff(
+                hidden.data_ptr(), int(hidden.dtype == torch.bfloat16), hidden.stride(0), H, fmap.data_ptr(),
+                int(fmap.dtype == torch.bfloat16), Cc, h * w, channels_last, B, txt.data_ptr(), img.data_ptr(),
+                int(out_dtype == torch.bfloat16), _stream_ptr(hidden.device)), "mmrca_feature_handoff")
+    return img, txt
 
 
 class HeadTrainStep:
@@ -538,4 +589,129 @@ class HierTrainStep:
                 C.byref(self.desc), C.byref(self.hp), arr, drop_mask.data_ptr() if drop_mask is not None else None,
                 float(drop_scale), labels.data_ptr(), C.byref(self.ce), self.logits.data_ptr(), self.loss.data_ptr(),
                 C.byref(self.hg), self.ws.data_ptr(), self.ws.numel(), _stream_ptr(self.device)), "mmrca_hier_train_step")
+        return self.loss, self.logits
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Classic / Normalized late-fusion heads (reference multimodal_model.py:489-579)
+# ---------------------------------------------------------------------------------------------------------
+FUSION_PARAM_NAMES = ("image_to_hidden_size.weight", "image_to_hidden_size.bias", "text_to_hidden_size.weight",
+                      "text_to_hidden_size.bias", "concat_layer.weight", "concat_layer.bias", "fc_layer.weight",
+                      "fc_layer.bias")
+
+
+def _fusion_struct(tensors: Sequence[Optional[torch.Tensor]]) -> N.FusionParams:
+    return N.FusionParams(*[t.data_ptr() if t is not None else None for t in tensors])
+
+
+def _fusion_desc(B, params, normalized, drop_p, drop_seed) -> N.FusionDesc:
+    H, d_img = params[0].shape
+    d_txt = params[2].shape[1]
+    if tuple(params[4].shape) != (H, 2 * H) or params[6].shape[1] != H:
+        raise ValueError("fusion head: concat_layer must be [H, 2H] and fc_layer [n_classes, H]")
+    return N.FusionDesc(B, d_img, d_txt, H, params[6].shape[0], N.FUSION_NORMALIZED if normalized else 0,
+                        float(drop_p), int(drop_seed) & (2 ** 64 - 1))
+
+
+class _FusionFunction(torch.autograd.Function):
+    """logits = classic / normalized fusion head(pooled image features, text CLS features)."""
+
+    @staticmethod
+    def forward(ctx, img, txt, drop_mask, drop_scale, normalized, drop_p, drop_seed, *params):
+        img, txt = _check_dev(img, "image features"), _check_dev(txt, "text features")
+        params = [_check_dev(p, "fusion parameter") for p in params]
+        B = img.shape[0]
+        desc = _fusion_desc(B, params, normalized, drop_p, drop_seed)
+        if img.shape[1] != desc.d_img or txt.shape != (B, desc.d_txt):
+            raise ValueError("feature shapes do not match the projection weights")
+        drop_mask = _check_mask(drop_mask, B, desc.hidden, "fusion head")
+        L = N.lib()
+        ws = _pool.take(L.mmrca_fusion_workspace_bytes(C.byref(desc)), img.device)
+        logits = torch.empty(B, desc.n_classes, dtype=torch.float32, device=img.device)
+        ctx.save_for_backward(img, txt, drop_mask, ws, *params)
+        ctx.cfg = (desc, float(drop_scale))
+        if B > 0:
+            with torch.cuda.device(img.device):
+                N.check(L.mmrca_fusion_forward(C.byref(desc), C.byref(_fusion_struct(params)), img.data_ptr(), txt.data_ptr(),
+                                               drop_mask.data_ptr() if drop_mask is not None else None, float(drop_scale),
+                                               logits.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(img.device)),
+                        "mmrca_fusion_forward")
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        img, txt, drop_mask, ws, *params = ctx.saved_tensors
+        desc, drop_scale = ctx.cfg
+        dlogits = _check_dev(dlogits, "dlogits")
+        fg = FlatGrads(params)
+        want_feat = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        d_img = torch.empty_like(img) if want_feat else None
+        d_txt = torch.empty_like(txt) if want_feat else None
+        if desc.batch > 0:
+            with torch.cuda.device(img.device):
+                N.check(N.lib().mmrca_fusion_backward(
+                    C.byref(desc), C.byref(_fusion_struct(params)), img.data_ptr(), txt.data_ptr(),
+                    drop_mask.data_ptr() if drop_mask is not None else None, drop_scale, dlogits.data_ptr(),
+                    C.byref(_fusion_struct(fg.views)), d_img.data_ptr() if want_feat else None,
+                    d_txt.data_ptr() if want_feat else None, ws.data_ptr(), ws.numel(), _stream_ptr(img.device)),
+                    "mmrca_fusion_backward")
+        elif want_feat:
+            d_img.zero_(); d_txt.zero_()
+        _pool.give(ws)
+        return (d_img if ctx.needs_input_grad[0] else None, d_txt if ctx.needs_input_grad[1] else None, None, None, None,
+                None, None, *[v if ctx.needs_input_grad[7 + i] else None for i, v in enumerate(fg.views)])
+
+
+def fusion_head(img_feat: torch.Tensor, txt_feat: torch.Tensor, params: Sequence[torch.Tensor], *, normalized: bool,
+                drop_mask: Optional[torch.Tensor] = None, drop_scale: float = 1.0, drop_p: float = 0.0,
+                drop_seed: int = 0) -> torch.Tensor:
+    """Classic (`normalized=False`) / Normalized late-fusion head after the backbones (reference
+    multimodal_model.py:521-529 / :566-577).  params: the eight tensors of FUSION_PARAM_NAMES.  Dropout on the
+    concat_layer output [B, H]: seeded (drop_p, drop_seed; dropout_mask(seed, p, B, H) returns the mask) or caller-drawn."""
+    if drop_mask is not None:
+        drop_p, drop_seed = 0.0, 0
+    return _FusionFunction.apply(img_feat, txt_feat, drop_mask, float(drop_scale), bool(normalized), float(drop_p),
+                                 int(drop_seed), *params)
+
+
+class FusionTrainStep:
+    """One-call training step of the classic / normalized head (forward + CrossEntropyLoss + backward, reference
+    main_both.py:106-112 restricted to the head); gradients accumulate into `grads.flat`."""
+
+    def __init__(self, params: Sequence[torch.Tensor], batch: int, *, normalized: bool,
+                 class_weight: Optional[torch.Tensor] = None, label_smoothing: float = 0.0, drop_p: float = 0.0,
+                 feature_grads: bool = False):
+        self.params = [_check_dev(p.detach(), "fusion parameter") for p in params]
+        dev = self.params[0].device
+        self.desc = _fusion_desc(batch, self.params, normalized, drop_p, 0)
+        self.grads = FlatGrads(self.params)
+        self.hp, self.hg = _fusion_struct(self.params), _fusion_struct(self.grads.views)
+        self.ws = torch.empty(max(1, N.lib().mmrca_fusion_workspace_bytes(C.byref(self.desc))), dtype=torch.uint8, device=dev)
+        self.logits = torch.empty(batch, self.desc.n_classes, dtype=torch.float32, device=dev)
+        self.loss = torch.empty(1, dtype=torch.float32, device=dev)
+        self.cw = _check_dev(class_weight, "class weights") if class_weight is not None else None
+        self.ce = N.CeDesc(self.cw.data_ptr() if self.cw is not None else None, float(label_smoothing))
+        self.d_img = torch.empty(batch, self.desc.d_img, dtype=torch.float32, device=dev) if feature_grads else None
+        self.d_txt = torch.empty(batch, self.desc.d_txt, dtype=torch.float32, device=dev) if feature_grads else None
+        self.device = dev
+
+    def zero_grad(self):
+        self.grads.zero_()
+
+    def __call__(self, img: torch.Tensor, txt: torch.Tensor, labels: torch.Tensor, drop_mask: Optional[torch.Tensor] = None,
+                 drop_scale: float = 1.0, drop_seed: int = 0):
+        self.desc.drop_seed = int(drop_seed) & (2 ** 64 - 1)
+        img, txt = _check_dev(img, "image features"), _check_dev(txt, "text features")
+        labels = _check_dev(labels, "labels", torch.int64)
+        if img.shape != (self.desc.batch, self.desc.d_img) or txt.shape != (self.desc.batch, self.desc.d_txt):
+            raise ValueError("feature shapes do not match the shapes this step was built for")
+        drop_mask = _check_mask(drop_mask, self.desc.batch, self.desc.hidden, "fusion head")
+        with torch.cuda.device(self.device):
+            N.check(N.lib().mmrca_fusion_train_step(
+                C.byref(self.desc), C.byref(self.hp), img.data_ptr(), txt.data_ptr(),
+                drop_mask.data_ptr() if drop_mask is not None else None, float(drop_scale), labels.data_ptr(),
+                C.byref(self.ce), self.logits.data_ptr(), self.loss.data_ptr(), C.byref(self.hg),
+                self.d_img.data_ptr() if self.d_img is not None else None,
+                self.d_txt.data_ptr() if self.d_txt is not None else None, self.ws.data_ptr(), self.ws.numel(),
+                _stream_ptr(self.device)), "mmrca_fusion_train_step")
         return self.loss, self.logits

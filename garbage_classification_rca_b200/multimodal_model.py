@@ -49,14 +49,19 @@ class EfficientNetV2MFullFeatureExtractor(nn.Module):
         self.avgpool = model.avgpool
         self.classifier = model.classifier   # registered but never applied (reference :23)
 
-    def forward(self, x):
+    def forward_maps(self, x):
+        """(stage-3 map, stage-6 map, final_conv map): forward() without the avgpool + flatten, for the fused feature
+        hand-off (functional.feature_handoff pools, gathers the CLS row and casts in one kernel)."""
         x = self.stem(x)
         taps = {}
         for name in self.STAGES:
             x = getattr(self, name)(x)
             taps[name] = x
-        pooled = torch.flatten(self.avgpool(self.final_conv(x)), 1)
-        return taps["stage3"], taps["stage6"], pooled
+        return taps["stage3"], taps["stage6"], self.final_conv(x)
+
+    def forward(self, x):
+        s3, s6, fmap = self.forward_maps(x)
+        return s3, s6, torch.flatten(self.avgpool(fmap), 1)
 
 
 def _freeze(m: nn.Module) -> nn.Module:
@@ -306,10 +311,35 @@ class EffV2MediumAndDistilbertGated(nn.Module):
         sd = dict(self.named_parameters())
         return [sd[n] for n in self._head_names]
 
+    def attach_flat_grads(self, flat_params: bool = False):
+        """Give the head a persistent flat gradient bucket: every head parameter's .grad becomes a view of ONE fp32
+        buffer that the backward kernels accumulate into directly (no per-backward allocation, no copies) and that a
+        data-parallel step all-reduces as a single collective (training.HeadDataParallel semantics for the module path).
+        flat_params=True also moves the parameters themselves into one buffer (training.FlatParams) so that
+        training.FusedSGD / FusedAdamW update all of them with one kernel.  Returns the FlatGrads (``.flat`` is the
+        bucket).  Call after .to(device); optimizer.zero_grad(set_to_none=False) / flat.zero_() keeps the views alive."""
+        from . import training as T
+        params = self.head_parameters()
+        self._flat_grads = F.FlatGrads([p.detach() for p in params])
+        T.attach_flat_grads(params, self._flat_grads)
+        self._flat_params = T.FlatParams(params, self._flat_grads) if flat_params else None
+        return self._flat_grads
+
     def forward(self, _input_ids, _attention_mask, _images, eval=False, remove_image=False, remove_text=False):
         raise NotImplementedError(
-            "only the MM_RCA late-fusion path is rebuilt B200-native in this package; the gated / classic / "
-            "normalized / CLIP variants keep their parameters (state_dict parity) but have no forward here")
+            "the gated fusion (reference :330-396) is outside the B200-native hot path: MM_RCA, Hierarchical, "
+            "EffV2MediumAndDistilbertClassic and EffV2MediumAndDistilbertNormalized are rebuilt here; the gated / CLIP / "
+            "bimodal variants keep their parameters (state_dict parity) but have no forward")
+
+    def _seeded_dropout(self) -> Tuple[float, int]:
+        """(p, seed) of this forward's self.drop: the seed comes from torch's CPU generator (or `dropout_generator`),
+        the keep mask itself is drawn inside the kernels (F.dropout_mask(seed, p, ...) returns it)."""
+        p = float(self.drop.p)
+        if not self.training or p <= 0.0:
+            return 0.0, 0
+        seed = int(torch.randint(0, 2 ** 62, (1,), generator=self.dropout_generator).item())
+        self.last_dropout_seed = seed
+        return min(p, 1.0), seed
 
 
 def _quiet_gru(inp, hid):
@@ -337,8 +367,12 @@ class MM_RCA(EffV2MediumAndDistilbertGated):
                          drop_mask: Optional[torch.Tensor] = None, drop_scale: Optional[float] = None):
         """Fusion head on pooled features [B,1280] / [B,768] (reference :661-728).  `drop_mask` overrides
         the internally drawn dropout mask (parity tests pass the mask torch.nn.Dropout drew)."""
-        image_features = image_features.float()
-        text_features = text_features.float()
+        bf16_ok = (self.compute != N.COMPUTE_FP32 and drop_mask is None and image_features.dtype == torch.bfloat16
+                   and text_features.dtype == torch.bfloat16
+                   and not (image_features.requires_grad or text_features.requires_grad))
+        if not bf16_ok:      # bf16 features of frozen backbones go to the bf16 pipeline as they are (MMRCA_FLAG_FEATURES_BF16)
+            image_features = image_features.float()
+            text_features = text_features.float()
         drop_p, drop_seed = 0.0, 0
         if drop_mask is None:
             drop_p, drop_seed = self._dropout_seed()
@@ -349,15 +383,58 @@ class MM_RCA(EffV2MediumAndDistilbertGated):
                             features_only=bool(self.features_only),
                             cross_attention_only=bool(self.cross_attention_only), n_classes=self.n_classes,
                             drop_mask=drop_mask, drop_scale=drop_scale, drop_p=drop_p, drop_seed=drop_seed,
-                            compute=self.compute)
+                            compute=self.compute, grad_sink=getattr(self, "_flat_grads", None))
 
-    def forward(self, _input_ids, _attention_mask, _images, eval=False, remove_image=False, remove_text=False):
+    def enable_feature_cache(self, n_samples: int, dtype: torch.dtype = torch.bfloat16):
+        """Frozen-backbone phase only: keep every sample's pooled features on the device (training.FeatureCache) and skip
+        both backbones when forward() is given `sample_ids` that are all cached.  The reference recomputes the frozen
+        backbones every step (main_both.py:562-577)."""
+        from .training import FeatureCache
+        dev = next(self.parameters()).device
+        self.feature_cache = FeatureCache(n_samples, IMAGE_FEATURES, 768, dev, dtype)
+        return self.feature_cache
+
+    def _frozen(self) -> bool:
+        """Transfer-learning phase: the reference freezes / unfreezes each backbone as a whole (:113-153,
+        main_both.py:687-694), so one parameter per backbone tells."""
+        for m in (self.text_model, self.image_model):
+            p = next(iter(m.parameters()), None)
+            if p is not None and p.requires_grad:
+                return False
+        return True
+
+    def backbone_features(self):
+        """Pooled image / text features of the current inputs.  Frozen backbones on a GPU hand their raw outputs (last
+        hidden state, final feature map) to ONE hand-off kernel (functional.feature_handoff: CLS gather + average pool +
+        cast, bf16 out for the bf16 pipeline); otherwise the stock path of the reference (:651-659)."""
+        fused = self._images.is_cuda and self._frozen() and isinstance(self.image_model, EfficientNetV2MFullFeatureExtractor)
+        if not fused:
+            _, text_features, (_, _, image_features) = self._backbone_features()
+            return image_features, text_features
+        with torch.no_grad():
+            hidden = self.text_model(input_ids=self._input_ids, attention_mask=self._attention_mask)[0]
+            _, _, fmap = self.image_model.forward_maps(self._images)
+            if hidden.dtype not in (torch.float32, torch.bfloat16):
+                hidden = hidden.float()
+            if fmap.dtype not in (torch.float32, torch.bfloat16):
+                fmap = fmap.float()
+            out_dtype = torch.bfloat16 if self.compute != N.COMPUTE_FP32 else torch.float32
+            return F.feature_handoff(hidden, fmap, out_dtype)
+
+    def forward(self, _input_ids, _attention_mask, _images, eval=False, remove_image=False, remove_text=False,
+                sample_ids: Optional[torch.Tensor] = None):
         self._images = _images
         self._input_ids = _input_ids
         self._attention_mask = _attention_mask
         self.drop_modalities(eval, remove_image, remove_text)
-        _, text_features, (_, _, image_features) = self._backbone_features()
-        return self.forward_features(image_features, text_features)
+        cache = getattr(self, "feature_cache", None)
+        use_cache = cache is not None and sample_ids is not None and self._frozen() and not (remove_image or remove_text)
+        feats = cache.lookup(sample_ids) if use_cache else None
+        if feats is None:
+            feats = self.backbone_features()
+            if use_cache:
+                cache.store(sample_ids, *feats)
+        return self.forward_features(*feats)
 
 
 class Hierarchical(EffV2MediumAndDistilbertGated):
@@ -397,6 +474,47 @@ class Hierarchical(EffV2MediumAndDistilbertGated):
         s3 = torch.nn.functional.avg_pool2d(out_stage_3, kernel_size=7, stride=7).flatten(1)       # :761-762, :769
         s6 = torch.nn.functional.avg_pool2d(out_stage_6, kernel_size=6, stride=6).flatten(1)       # :765-766, :772
         return self.forward_features((image_features, s3, s6, text_features, layer_2, layer_4))
+
+
+class EffV2MediumAndDistilbertClassic(EffV2MediumAndDistilbertGated):
+    """Classic late fusion (reference :489-534, `--late_fusion=classic`): Linear(1280 -> H) and Linear(768 -> H) projections
+    into the shared fusion dimension H = num_neurons_FC, concat, Linear(2H -> H), dropout, Linear(H -> n_classes); the
+    Normalized subclass L2-normalises the two projections first.  Everything after the backbones is libmmrca.so
+    (mmrca_fusion_*).  The reference passes the image extractor's whole (stage3, stage6, pooled) tuple to
+    image_to_hidden_size (:519-521), which raises a TypeError as shipped; the pooled vector is what is fed here."""
+
+    NORMALIZED = False
+
+    def fusion_parameters(self) -> List[torch.Tensor]:
+        sd = dict(self.named_parameters())
+        return [sd[n] for n in F.FUSION_PARAM_NAMES]
+
+    def forward_features(self, image_features: torch.Tensor, text_features: torch.Tensor,
+                         drop_mask: Optional[torch.Tensor] = None, drop_scale: Optional[float] = None):
+        drop_p, drop_seed = 0.0, 0
+        if drop_mask is None:
+            drop_p, drop_seed = self._seeded_dropout()
+            drop_scale = 1.0
+        elif drop_scale is None:
+            drop_scale = 1.0 / (1.0 - float(self.drop.p))
+        return F.fusion_head(image_features.float(), text_features.float(), self.fusion_parameters(),
+                             normalized=self.NORMALIZED, drop_mask=drop_mask, drop_scale=drop_scale, drop_p=drop_p,
+                             drop_seed=drop_seed)
+
+    def forward(self, _input_ids, _attention_mask, _images, eval=False, remove_image=False, remove_text=False):
+        print("Normalized forward" if self.NORMALIZED else "Classic forward")       # reference :500, :545
+        self._images = _images
+        self._input_ids = _input_ids
+        self._attention_mask = _attention_mask
+        self.drop_modalities(eval, remove_image, remove_text)
+        _, text_features, (_, _, image_features) = self._backbone_features()
+        return self.forward_features(image_features, text_features)
+
+
+class EffV2MediumAndDistilbertNormalized(EffV2MediumAndDistilbertClassic):
+    """Normalized late fusion (reference :536-579, `--late_fusion=normalized`)."""
+
+    NORMALIZED = True
 
 
 def load_reference_state_dict(model: nn.Module, state_dict, strict: bool = True):

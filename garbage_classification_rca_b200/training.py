@@ -57,8 +57,12 @@ def build_model(args, n_classes: int = 4, pretrained: bool = True):
                          compute=compute)
     if args.late_fusion == "hierarchical":      # reference main_both.py:318-330
         return mm.Hierarchical(*common, args.features_only, args.cross_attention_only, pretrained=pretrained)
+    if args.late_fusion == "classic":           # reference main_both.py:284-292
+        return mm.EffV2MediumAndDistilbertClassic(*common, pretrained=pretrained)
+    if args.late_fusion == "normalized":        # reference main_both.py:294-302
+        return mm.EffV2MediumAndDistilbertNormalized(*common, pretrained=pretrained)
     raise SystemExit(f"late fusion strategy {args.late_fusion!r} is outside the B200-native hot path "
-                     "(MM_RCA and hierarchical are; see SURVEY.md §8)")
+                     "(MM_RCA, hierarchical, classic and normalized are; see SURVEY.md §8)")
 
 
 # ---- data-parallel plumbing -----------------------------------------------------------------------------
@@ -199,6 +203,161 @@ def attach_flat_grads(params: Sequence[nn.Parameter], grads: F.FlatGrads) -> Non
     consumes the kernels' output without copies."""
     for p, v in zip(params, grads.views):
         p.grad = v
+
+
+class FlatParams:
+    """One contiguous fp32 buffer holding the head parameters themselves, laid out exactly like FlatGrads lays out their
+    gradients; every nn.Parameter's .data becomes a view of it (state_dict, .to(), strict loading are unaffected: a view
+    serialises as its own tensor).  Together with FlatGrads it lets ONE kernel update all 34 tensors (FusedSGD /
+    FusedAdamW) and one collective reduce all their gradients."""
+
+    def __init__(self, params: Sequence[nn.Parameter], layout: F.FlatGrads):
+        self.flat = torch.zeros_like(layout.flat)
+        self.views = []
+        for p, off in zip(params, layout.offsets):
+            v = self.flat[off:off + p.numel()].view(p.shape)
+            v.copy_(p.detach())
+            p.data = v
+            self.views.append(v)
+        self.n = layout.n
+
+
+class _FusedOptimizer:
+    """Base of the fused optimizers over (FlatParams, FlatGrads).  param_groups / zero_grad mirror what the reference's
+    loop touches (main_both.py:113-121 step + zero_grad, :700-703 lr rescale, ReduceLROnPlateau writes group['lr'])."""
+
+    def __init__(self, flat_params: FlatParams, flat_grads: F.FlatGrads, **defaults):
+        if flat_params.flat.numel() != flat_grads.flat.numel():
+            raise ValueError("parameter and gradient buckets differ in layout")
+        self.p, self.g = flat_params, flat_grads
+        self.param_groups = [dict(defaults, params=[])]
+        self.defaults = dict(defaults)
+        self.state: dict = {}
+        self.steps = 0
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.g.zero_()
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.p.flat.device).cuda_stream
+
+
+class FusedSGD(_FusedOptimizer):
+    """torch.optim.SGD(lr, momentum, dampening, weight_decay, nesterov) on the flat head bucket: one launch."""
+
+    def __init__(self, flat_params, flat_grads, lr, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False):
+        super().__init__(flat_params, flat_grads, lr=lr, momentum=momentum, dampening=dampening,
+                         weight_decay=weight_decay, nesterov=nesterov)
+        self.buf = torch.zeros_like(flat_params.flat) if momentum != 0.0 else None
+
+    @torch.no_grad()
+    def step(self):
+        g = self.param_groups[0]
+        with torch.cuda.device(self.p.flat.device):
+            N.check(N.lib().mmrca_sgd_step(self.p.flat.data_ptr(), self.g.flat.data_ptr(),
+                                           self.buf.data_ptr() if self.buf is not None else None, self.p.flat.numel(),
+                                           float(g["lr"]), float(g["momentum"]), float(g["dampening"]),
+                                           float(g["weight_decay"]), int(bool(g["nesterov"])), int(self.steps == 0),
+                                           self._stream()), "mmrca_sgd_step")
+        self.steps += 1
+
+
+class FusedAdamW(_FusedOptimizer):
+    """torch.optim.AdamW(lr, betas, eps, weight_decay) on the flat head bucket: one launch."""
+
+    def __init__(self, flat_params, flat_grads, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        super().__init__(flat_params, flat_grads, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        self.m = torch.zeros_like(flat_params.flat)
+        self.v = torch.zeros_like(flat_params.flat)
+
+    @torch.no_grad()
+    def step(self):
+        g = self.param_groups[0]
+        self.steps += 1
+        with torch.cuda.device(self.p.flat.device):
+            N.check(N.lib().mmrca_adamw_step(self.p.flat.data_ptr(), self.g.flat.data_ptr(), self.m.data_ptr(),
+                                             self.v.data_ptr(), self.p.flat.numel(), float(g["lr"]), float(g["betas"][0]),
+                                             float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), self.steps,
+                                             self._stream()), "mmrca_adamw_step")
+
+
+class FeatureCache:
+    """Pooled backbone features of the frozen (transfer-learning) phase, kept on the device by dataset index, so that
+    epochs after the first skip the two backbones (> 99.99 % of a step's FLOPs).  The reference recomputes them every
+    step (main_both.py:562-577).  Only valid while the backbones are frozen AND the inputs of a sample do not change
+    between epochs (no random augmentation / modality dropout): opt-in, off by default.  bf16 storage is what the bf16
+    head takes directly (MMRCA_FLAG_FEATURES_BF16); 4 KB per sample."""
+
+    def __init__(self, n_samples: int, d_img: int, d_txt: int, device, dtype: torch.dtype = torch.bfloat16):
+        self.img = torch.empty(n_samples, d_img, dtype=dtype, device=device)
+        self.txt = torch.empty(n_samples, d_txt, dtype=dtype, device=device)
+        self.valid = torch.zeros(n_samples, dtype=torch.bool, device=device)
+        self.hits = self.misses = 0
+
+    def lookup(self, ids: torch.Tensor):
+        """(img, txt) for `ids` if every one of them is cached, else None (one host sync on the validity bits)."""
+        ids = ids.to(self.valid.device)
+        if bool(self.valid[ids].all()):
+            self.hits += int(ids.numel())
+            return self.img[ids], self.txt[ids]
+        self.misses += int(ids.numel())
+        return None
+
+    def store(self, ids: torch.Tensor, img: torch.Tensor, txt: torch.Tensor) -> None:
+        ids = ids.to(self.valid.device)
+        self.img[ids] = img.detach().to(self.img.dtype)
+        self.txt[ids] = txt.detach().to(self.txt.dtype)
+        self.valid[ids] = True
+
+    def invalidate(self) -> None:
+        self.valid.zero_()
+
+
+# ---- evaluation, reference semantics --------------------------------------------------------------------
+# main_both.py:43-47: the three evaluation modes of calculate_set_accuracy
+mode_config_dict = {
+    "image_only": {"remove_text": True, "remove_image": False},
+    "text_only": {"remove_text": False, "remove_image": True},
+    "both": {"remove_text": False, "remove_image": False},
+}
+
+
+def calculate_set_accuracy(model, data_loader, len_data, device, batch_size, mode, eval_mode, verbose: bool = False):
+    """Mirror of calculate_set_accuracy (reference main_both.py:141-198): accuracy of `model` over a loader in one of the
+    modes of mode_config_dict (`mode` is the dict, like in the reference's calls :596-652), predictions by argmax.  Returns
+    (accuracy in percent, per-class report dict).  The report is computed here (precision / recall / f1 / support per
+    class + accuracy) instead of importing sklearn."""
+    n_batches = math.ceil(len_data / batch_size)
+    all_labels, all_predictions = [], []
+    correct = 0
+    with torch.no_grad():
+        for batch_idx, (data, labels) in enumerate(data_loader):
+            ids = data["text"]["tokens"].to(device)
+            mask = data["text"]["attention_mask"].to(device)
+            images = data["image"]["raw_image"].to(device)
+            labels = labels.to(device)
+            outputs = model(_input_ids=ids, _attention_mask=mask, _images=images, eval=eval_mode,
+                            remove_text=mode["remove_text"], remove_image=mode["remove_image"])
+            pred = torch.max(outputs, 1)[1].view(-1)
+            correct += torch.sum(torch.eq(pred, labels)).item()
+            if verbose:
+                print("Batches {}/{} ".format(batch_idx, n_batches))
+            all_labels.append(labels.cpu())
+            all_predictions.append(pred.cpu())
+    y = torch.cat(all_labels) if all_labels else torch.zeros(0, dtype=torch.long)
+    yhat = torch.cat(all_predictions) if all_predictions else torch.zeros(0, dtype=torch.long)
+    report = {}
+    for c, name in enumerate(["black", "blue", "green", "ttr"]):
+        tp = int(((yhat == c) & (y == c)).sum())
+        fp = int(((yhat == c) & (y != c)).sum())
+        fn = int(((yhat != c) & (y == c)).sum())
+        prec = tp / (tp + fp) if tp + fp else 0.0
+        rec = tp / (tp + fn) if tp + fn else 0.0
+        report[name] = {"precision": prec, "recall": rec,
+                        "f1-score": 2 * prec * rec / (prec + rec) if prec + rec else 0.0, "support": tp + fn}
+    report["accuracy"] = correct / max(1, int(y.numel()))
+    acc = 100 * (correct / len_data)
+    return acc, report
 
 
 # ---- one epoch, reference semantics ---------------------------------------------------------------------

@@ -255,6 +255,43 @@ int mmrca_hier_train_step(const MmrcaHierDesc* desc, const MmrcaHierParams* para
                           float* logits, float* loss_out, const MmrcaHierGrads* grads, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* ---- Classic / Normalized late-fusion heads (--late_fusion=classic | normalized): everything after the backbones in
+ * EffV2MediumAndDistilbertClassic / ...Normalized.forward (multimodal_model.py:489-579) - the image and text projections
+ * into the shared fusion dimension H = num_neurons_FC (:521-522, :566-567), for "normalized" their row L2 normalisation
+ * (:569-570, no epsilon), concat + concat_layer (:524-527), self.drop (:528), fc_layer (:529) - plus CrossEntropyLoss and the
+ * backward, fp32 (the 1e-4 contract).  (The reference hands image_to_hidden_size the extractor's TUPLE, which raises a
+ * TypeError; the pooled vector, its third element, is what is meant and what img_feat is.) ---- */
+#define MMRCA_FUSION_NORMALIZED 1u
+typedef struct MmrcaFusionParams {
+  const float* w_img; const float* b_img; /* image_to_hidden_size [H, d_img], [H]   (:199-201) */
+  const float* w_txt; const float* b_txt; /* text_to_hidden_size  [H, d_txt], [H]   (:203-206) */
+  const float* w_cat; const float* b_cat; /* concat_layer         [H, 2H],    [H]   (:208-210) */
+  const float* w_fc;  const float* b_fc;  /* fc_layer             [n_classes, H], [n_classes] (:212) */
+} MmrcaFusionParams;
+typedef struct MmrcaFusionGrads { /* accumulated into (+=) */
+  float* w_img; float* b_img; float* w_txt; float* b_txt; float* w_cat; float* b_cat; float* w_fc; float* b_fc;
+} MmrcaFusionGrads;
+typedef struct MmrcaFusionDesc {
+  int32_t batch, d_img, d_txt, hidden, n_classes;
+  uint32_t flags;     /* MMRCA_FUSION_NORMALIZED */
+  float drop_p;       /* self.drop on the concat_layer output [B, H]: seeded mask = mmrca_dropout_mask(seed, p, B, H) */
+  uint64_t drop_seed;
+} MmrcaFusionDesc;
+size_t mmrca_fusion_workspace_bytes(const MmrcaFusionDesc* desc);
+/* drop_mask: caller-drawn uint8 keep mask [B, H] (kept values scaled by drop_scale) or NULL (eval / seeded) */
+int mmrca_fusion_forward(const MmrcaFusionDesc* desc, const MmrcaFusionParams* params, const float* img_feat,
+                         const float* txt_feat, const uint8_t* drop_mask, float drop_scale, float* logits,
+                         void* workspace, size_t workspace_bytes, void* stream);
+/* needs the unmodified workspace of the forward; d_img_feat / d_txt_feat: written if non-NULL (fine-tune phase) */
+int mmrca_fusion_backward(const MmrcaFusionDesc* desc, const MmrcaFusionParams* params, const float* img_feat,
+                          const float* txt_feat, const uint8_t* drop_mask, float drop_scale, const float* dlogits,
+                          const MmrcaFusionGrads* grads, float* d_img_feat, float* d_txt_feat, void* workspace,
+                          size_t workspace_bytes, void* stream);
+int mmrca_fusion_train_step(const MmrcaFusionDesc* desc, const MmrcaFusionParams* params, const float* img_feat,
+                            const float* txt_feat, const uint8_t* drop_mask, float drop_scale, const int64_t* labels,
+                            const MmrcaCeDesc* ce, float* logits, float* loss_out, const MmrcaFusionGrads* grads,
+                            float* d_img_feat, float* d_txt_feat, void* workspace, size_t workspace_bytes, void* stream);
+
 /* One-shot all-reduce (mean over `world` ranks) of the flat head-gradient bucket over NVLink peer memory: the single
  * collective of a data-parallel step (SURVEY.md §8 e; the reference never ran multi-GPU, stock DDP would call NCCL
  * here).  staging[i] / pads[i]: rank i's symmetric staging buffer (2 * n_pad floats) and flag pad
@@ -268,6 +305,24 @@ int mmrca_peer_allreduce_pad_bytes(int32_t world);
  * bucket unreduced and records the peer in the status word behind the flags of this rank's own pad.  This call reads it
  * (the one peer function that synchronises `stream`): 0 = healthy, 1 + r = rank r timed out, < 0 = -MMRCA_ERR_*. */
 int mmrca_peer_allreduce_status(const void* own_pad, int32_t world, void* stream);
+
+/* ---- around the head ---- */
+/* Feature hand-off from the stock backbones, one launch: txt_out[b][:] = hidden[b][0][:] (the CLS row of the text
+ * backbone's last hidden state, multimodal_model.py:651-658) and img_out[b][c] = mean over the hw positions of the image
+ * backbone's final feature map (avgpool + flatten, :25-36).  hidden: [B][T][d_txt] with row b at b * hidden_batch_stride
+ * elements; fmap: contiguous [B][channels][hw] (channels_last = 0) or [B][hw][channels] (channels_last = 1); *_bf16: the
+ * array holds bf16 instead of fp32.  bf16 outputs are what MMRCA_FLAG_FEATURES_BF16 takes. */
+int mmrca_feature_handoff(const void* hidden, int32_t hidden_bf16, int64_t hidden_batch_stride, int32_t d_txt,
+                          const void* fmap, int32_t fmap_bf16, int32_t channels, int32_t hw, int32_t channels_last,
+                          int32_t batch, void* txt_out, void* img_out, int32_t out_bf16, void* stream);
+/* Optimizer step over ONE contiguous fp32 parameter bucket and its gradient bucket (n floats, n % 4 == 0, 16-byte
+ * aligned): torch.optim.SGD / torch.optim.AdamW semantics (main_both.py:544-552: lr, weight_decay = --reg).
+ * sgd: momentum_buf may be NULL when momentum == 0; first_step != 0: the momentum buffer is initialised with the
+ * gradient (torch's first step).  adamw: step = 1, 2, ... (bias correction). */
+int mmrca_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n, float lr, float momentum,
+                   float dampening, float weight_decay, int32_t nesterov, int32_t first_step, void* stream);
+int mmrca_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, int32_t step, void* stream);
 
 /* Per-kernel timing for roofline reports: between begin and end every kernel this library launches on
  * the calling thread is bracketed by a pair of CUDA events on ITS launch stream (up to max_records

@@ -450,3 +450,62 @@ def hier_loss_and_grads(p: Dict[str, torch.Tensor], img_segments, txt_segments, 
     loss = cross_entropy(logits, labels, cw, label_smoothing)
     loss.backward()
     return logits.detach(), loss.detach(), {k: v.grad for k, v in pp.items()}
+
+
+# =====================================================================================================
+# Classic / Normalized late-fusion heads (reference multimodal_model.py:489-579)
+# =====================================================================================================
+FUSION_PARAM_NAMES = ("image_to_hidden_size.weight", "image_to_hidden_size.bias", "text_to_hidden_size.weight",
+                      "text_to_hidden_size.bias", "concat_layer.weight", "concat_layer.bias", "fc_layer.weight",
+                      "fc_layer.bias")
+
+
+def init_fusion_params(d_img: int = 1280, d_txt: int = 768, hidden: int = 256, n_classes: int = 4, seed: int = 0,
+                       dtype=torch.float32) -> Dict[str, torch.Tensor]:
+    """Random parameters of the four Linear layers (multimodal_model.py:199-212), torch.nn.Linear-like scale, a pure
+    function of the seed."""
+    g = torch.Generator().manual_seed(20_000 + seed)
+
+    def lin(out_f, in_f):
+        k = 1.0 / math.sqrt(in_f)
+        w = (torch.rand(out_f, in_f, generator=g, dtype=torch.float64) * 2 - 1) * k
+        b = (torch.rand(out_f, generator=g, dtype=torch.float64) * 2 - 1) * k
+        return w.to(dtype), b.to(dtype)
+
+    p: Dict[str, torch.Tensor] = {}
+    p["image_to_hidden_size.weight"], p["image_to_hidden_size.bias"] = lin(hidden, d_img)
+    p["text_to_hidden_size.weight"], p["text_to_hidden_size.bias"] = lin(hidden, d_txt)
+    p["concat_layer.weight"], p["concat_layer.bias"] = lin(hidden, 2 * hidden)
+    p["fc_layer.weight"], p["fc_layer.bias"] = lin(n_classes, hidden)
+    return p
+
+
+def fusion_forward(p: Dict[str, torch.Tensor], img_feat: torch.Tensor, txt_feat: torch.Tensor, normalized: bool,
+                   drop_mask: Optional[torch.Tensor] = None, drop_scale: float = 1.0) -> torch.Tensor:
+    """EffV2MediumAndDistilbertClassic.forward (:521-531) / ...Normalized.forward (:566-579) after the backbones.
+    img_feat is the POOLED image vector (the reference hands the extractor's tuple to the Linear, a TypeError as shipped)."""
+    h_i = torch.nn.functional.linear(img_feat, p["image_to_hidden_size.weight"], p["image_to_hidden_size.bias"])   # :521 / :566
+    h_t = torch.nn.functional.linear(txt_feat, p["text_to_hidden_size.weight"], p["text_to_hidden_size.bias"])     # :522 / :567
+    if normalized:
+        h_i = h_i / h_i.norm(dim=1, keepdim=True)                                                                # :569
+        h_t = h_t / h_t.norm(dim=1, keepdim=True)                                                                # :570
+    cat = torch.cat((h_i, h_t), dim=1)                                                                           # :524-525 / :572-573
+    c = torch.nn.functional.linear(cat, p["concat_layer.weight"], p["concat_layer.bias"])                        # :527 / :575
+    if drop_mask is not None:
+        c = c * drop_mask.to(c.dtype) * drop_scale                                                               # :528 / :576
+    return torch.nn.functional.linear(c, p["fc_layer.weight"], p["fc_layer.bias"])                               # :529 / :577
+
+
+def fusion_loss_and_grads(p: Dict[str, torch.Tensor], img_feat: torch.Tensor, txt_feat: torch.Tensor, labels: torch.Tensor,
+                          normalized: bool, class_weight: Optional[torch.Tensor] = None, label_smoothing: float = 0.0,
+                          drop_mask: Optional[torch.Tensor] = None, drop_scale: float = 1.0, dtype=torch.float64):
+    """forward + CrossEntropyLoss + backward (main_both.py:106-112) through autograd, float64 by default.
+    Returns (logits, loss, grads{name: tensor}, d_img, d_txt)."""
+    pp = {k: v.detach().to(dtype).clone().requires_grad_(True) for k, v in p.items() if k in FUSION_PARAM_NAMES}
+    img = img_feat.detach().to(dtype).clone().requires_grad_(True)
+    txt = txt_feat.detach().to(dtype).clone().requires_grad_(True)
+    logits = fusion_forward(pp, img, txt, normalized, drop_mask, drop_scale)
+    cw = None if class_weight is None else class_weight.to(dtype)
+    loss = cross_entropy(logits, labels, cw, label_smoothing)
+    loss.backward()
+    return logits.detach(), loss.detach(), {k: v.grad for k, v in pp.items()}, img.grad, txt.grad

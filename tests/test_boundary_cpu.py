@@ -127,3 +127,102 @@ def test_drop_modalities_matches_reference_semantics():
         assert m._images.sum() == 0 and torch.equal(m._input_ids, ids)
         m.drop_modalities(True, False, True)
         assert m._input_ids.sum() == 0 and m._attention_mask.sum() == 0
+
+
+REFERENCE = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference checkout only exists in the build container")
+@pytest.mark.parametrize("flags", [(True, False, False), (True, True, False), (False, False, True)])
+def test_pth_round_trip_with_the_reference_class(tmp_path, flags):
+    """save_model_weights (ours) -> torch.load -> STRICT load_state_dict into the unmodified reference MM_RCA, and a
+    reference-saved .pth strict-loaded into ours (main_both.py:201-226, calculate_test_accuracy_both.py:187), with the
+    backbones stubbed out on both sides (their key names are pinned by test_state_dict_layout_matches_reference)."""
+    import sys
+    sys.path.insert(0, REFERENCE)
+    import CVPR_code.multimodal_model as mm
+    from garbage_classification_rca_b200 import multimodal_model as M
+    from garbage_classification_rca_b200.training import save_model_weights
+    rev, fo, co = flags
+
+    class _Cfg:
+        hidden_size = 768
+
+    class Stub(torch.nn.Module):
+        config = _Cfg()
+
+    saved = mm.distilbert, mm.eff_net_v2
+    mm.distilbert, mm.eff_net_v2 = (lambda: Stub()), (lambda: Stub())
+    try:
+        with redirect_stdout(io.StringIO()):
+            torch.manual_seed(1)
+            ref = mm.MM_RCA(4, 0.6, 0.0, 0.7, 256, "distilbert", 16, rev, fo, co)
+            torch.manual_seed(2)
+            ours = M.MM_RCA(4, 0.6, 0.0, 0.7, 256, "distilbert", 16, rev, fo, co, pretrained=False)
+    finally:
+        mm.distilbert, mm.eff_net_v2 = saved
+    ours.text_model, ours.image_model = Stub(), Stub()
+    path = save_model_weights(ours, str(tmp_path / "ours.pth"), "cpu")
+    ref.load_state_dict(torch.load(path), strict=True)                       # calculate_test_accuracy_both.py:187
+    for (k, a), (k2, b) in zip(ours.state_dict().items(), ref.state_dict().items()):
+        assert k == k2 and torch.equal(a, b)
+    torch.manual_seed(3)
+    for p in ref.parameters():
+        p.data.normal_()
+    torch.save(ref.state_dict(), str(tmp_path / "ref.pth"))                  # main_both.py:223-224
+    M.load_reference_state_dict(ours, torch.load(str(tmp_path / "ref.pth")), strict=True)
+    assert all(torch.equal(a, b) for a, b in zip(ours.state_dict().values(), ref.state_dict().values()))
+    # a checkpoint written from an nn.DataParallel wrapper carries a "module." prefix (SURVEY.md §5)
+    M.load_reference_state_dict(ours, {"module." + k: v for k, v in ref.state_dict().items()}, strict=True)
+
+
+def test_run_one_epoch_reference_semantics():
+    """run_one_epoch mirror (main_both.py:81-134) on a CPU stand-in model: the optimizer steps every acc_steps batches
+    and on the last one, gradients are NOT scaled by 1/acc_steps (the division happens after backward, :112-114), the
+    returned losses are the divided ones."""
+    from garbage_classification_rca_b200 import training as T
+
+    class Toy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(6, 4)
+
+        def forward(self, _input_ids, _attention_mask, _images):
+            return self.lin(_images.flatten(1))
+
+    class CE(torch.nn.Module):          # the kernels need a GPU; the loop's semantics do not
+        def __init__(self, weight=None, label_smoothing=0.0):
+            super().__init__()
+            self.f = torch.nn.CrossEntropyLoss(weight=weight, label_smoothing=label_smoothing)
+
+        def forward(self, a, b):
+            return self.f(a, b)
+
+    g = torch.Generator().manual_seed(0)
+    batches = [({"text": {"tokens": torch.zeros(3, 2, dtype=torch.long), "attention_mask": torch.ones(3, 2, dtype=torch.long)},
+                 "image": {"raw_image": torch.randn(3, 6, generator=g)}}, torch.randint(0, 4, (3,), generator=g))
+               for _ in range(5)]
+    saved, T.CrossEntropyLoss = T.CrossEntropyLoss, CE
+    try:
+        torch.manual_seed(0)
+        m = Toy()
+        ref = Toy()
+        ref.load_state_dict(m.state_dict())
+        opt = torch.optim.SGD(m.parameters(), lr=0.1)
+        n_batches, losses = T.run_one_epoch(0, m, batches, 15, "cpu", 3, opt, [1.0, 2.0, 0.5, 1.0], True, 2, 0.1)
+    finally:
+        T.CrossEntropyLoss = saved
+    # restatement of the reference loop
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.1)
+    crit = torch.nn.CrossEntropyLoss(weight=torch.tensor([1.0, 2.0, 0.5, 1.0]), label_smoothing=0.1)
+    rl = []
+    for i, (d, y) in enumerate(batches):
+        loss = crit(ref(None, None, d["image"]["raw_image"]), y)
+        loss.backward()
+        rl.append(loss.detach() / 2)
+        if (i + 1) % 2 == 0 or i + 1 == len(batches):
+            ropt.step()
+            ropt.zero_grad()
+    assert n_batches == 5 and len(losses) == 5
+    assert all(abs(float(a) - float(b)) < 1e-6 for a, b in zip(losses, rl))
+    assert all(torch.allclose(a, b, atol=1e-7) for a, b in zip(m.state_dict().values(), ref.state_dict().values()))

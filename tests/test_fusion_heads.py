@@ -1,0 +1,162 @@
+"""Classic / Normalized late-fusion heads (reference multimodal_model.py:489-579, `--late_fusion=classic|normalized`).
+
+CPU: the oracle restatement against fixtures generated from the UNMODIFIED reference classes
+(tests/golden/make_golden_fusion.py).  GPU (-m gpu): the CUDA path through the C ABI (mmrca_fusion_*) against those
+fixtures and against the oracle at ragged / larger batches; fp32: logits 1e-4 relative, gradients 1e-2 relative
+(north_star), held to 2e-4."""
+import glob
+import io
+import os
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mmrca_oracle as orc
+from tests._util import GOLDEN, rel_err
+
+CASES = sorted(os.path.basename(f)[7:-4] for f in glob.glob(os.path.join(GOLDEN, "fusion_*.npz")))
+TIGHT = 2e-4
+
+
+def _sample_index(size):
+    return np.random.default_rng(12345).choice(size, 256, replace=False)
+
+
+def _load(name):
+    d = np.load(os.path.join(GOLDEN, f"fusion_{name}.npz"))
+    p = orc.init_fusion_params(seed=int(d["seed"]))
+    cw = torch.tensor(d["class_weight"]) if d["class_weight"].size else None
+    mask = torch.tensor(d["mask"]) if d["mask"].size else None
+    scale = 1.0 / (1.0 - float(d["drop"])) if mask is not None else 1.0
+    return d, p, cw, mask, scale
+
+
+def _check_grads(d, grads, d_img, d_txt, tol):
+    for n in orc.FUSION_PARAM_NAMES:
+        g = np.asarray(grads[n], dtype=np.float64)
+        if "grad." + n in d.files:
+            assert rel_err(g, d["grad." + n]) < tol, n
+        else:
+            assert rel_err(g.sum(axis=1), d["gradrow." + n]) < tol, n
+            assert rel_err(g.sum(axis=0), d["gradcol." + n]) < tol, n
+            ref = d["gradsample." + n]
+            assert np.abs(g.ravel()[_sample_index(g.size)] - ref).max() < tol * np.abs(d["gradrow." + n]).max(), n
+    assert rel_err(d_img, d["d_img"]) < tol and rel_err(d_txt, d["d_txt"]) < tol
+
+
+def test_fixture_set_is_complete():
+    assert CASES == ["classic", "classic_weighted_smooth_dropout", "normalized", "normalized_weighted_smooth_dropout"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_matches_reference_golden(case):
+    d, p, cw, mask, scale = _load(case)
+    logits, loss, grads, d_img, d_txt = orc.fusion_loss_and_grads(
+        p, torch.tensor(d["img"]), torch.tensor(d["txt"]), torch.tensor(d["labels"]), bool(d["normalized"]),
+        class_weight=cw, label_smoothing=float(d["label_smoothing"]), drop_mask=mask, drop_scale=scale)
+    assert rel_err(logits.numpy(), d["logits"]) < 1e-5
+    assert abs(float(loss) - float(d["loss"])) < 1e-5
+    _check_grads(d, {k: v.numpy() for k, v in grads.items()}, d_img.numpy(), d_txt.numpy(), 1e-4)
+
+
+# ---- GPU -------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def pkg(native_lib):
+    import garbage_classification_rca_b200 as g
+    return g
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES)
+def test_cuda_head_matches_reference_golden(pkg, case):
+    """autograd path (mmrca_fusion_forward + mmrca_cross_entropy + mmrca_fusion_backward) with the reference's own dropout
+    mask, directly against the reference's outputs."""
+    from garbage_classification_rca_b200.training import CrossEntropyLoss
+    d, p, cw, mask, scale = _load(case)
+    names = pkg.functional.FUSION_PARAM_NAMES
+    params = [p[n].cuda().requires_grad_(True) for n in names]
+    img = torch.tensor(d["img"]).cuda().requires_grad_(True)
+    txt = torch.tensor(d["txt"]).cuda().requires_grad_(True)
+    logits = pkg.fusion_head(img, txt, params, normalized=bool(d["normalized"]),
+                             drop_mask=mask.cuda() if mask is not None else None, drop_scale=scale)
+    loss = CrossEntropyLoss(weight=cw.cuda() if cw is not None else None, label_smoothing=float(d["label_smoothing"]))(
+        logits, torch.tensor(d["labels"]).cuda())
+    loss.backward()
+    assert rel_err(logits.detach().cpu().numpy(), d["logits"]) < 1e-4
+    assert abs(loss.item() - float(d["loss"])) < 1e-5
+    _check_grads(d, {n: t.grad.cpu().numpy() for n, t in zip(names, params)}, img.grad.cpu().numpy(),
+                 txt.grad.cpu().numpy(), TIGHT)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("normalized", [False, True], ids=["classic", "normalized"])
+@pytest.mark.parametrize("B", [1, 7, 64, 333])
+def test_cuda_train_step_matches_oracle(pkg, normalized, B):
+    """One-call step (mmrca_fusion_train_step) with seeded dropout, class weights and label smoothing, ragged batches,
+    gradients accumulated over two calls; feature gradients included."""
+    from garbage_classification_rca_b200 import functional as F
+    p = orc.init_fusion_params(seed=40 + B)
+    g = torch.Generator().manual_seed(B)
+    img = torch.randn(B, 1280, generator=g) * 0.7 + 0.1
+    txt = torch.randn(B, 768, generator=g) * 1.3 - 0.05
+    labels = torch.randint(0, 4, (B,), generator=g)
+    cw = torch.tensor([0.6, 1.7, 1.0, 0.9])
+    seed, drop_p = 11, 0.6
+    mask = F.dropout_mask(seed, drop_p, B, 256, "cuda").cpu()
+    rl, rloss, rg, rdi, rdt = orc.fusion_loss_and_grads(p, img, txt, labels, normalized, class_weight=cw, label_smoothing=0.1,
+                                                        drop_mask=mask, drop_scale=1.0 / (1.0 - drop_p))
+    names = F.FUSION_PARAM_NAMES
+    step = pkg.FusionTrainStep([p[n].cuda() for n in names], B, normalized=normalized, class_weight=cw.cuda(),
+                               label_smoothing=0.1, drop_p=drop_p, feature_grads=True)
+    step.zero_grad()
+    for _ in range(2):
+        loss, logits = step(img.cuda(), txt.cuda(), labels.cuda(), drop_seed=seed)
+    torch.cuda.synchronize()
+    assert rel_err(logits.cpu().numpy(), rl.numpy()) < 1e-4
+    assert abs(loss.item() - float(rloss)) < 1e-5
+    for n, v in zip(names, step.grads.views):
+        assert rel_err(v.cpu().numpy() / 2.0, rg[n].numpy()) < TIGHT, n
+    assert rel_err(step.d_img.cpu().numpy(), rdi.numpy()) < TIGHT and rel_err(step.d_txt.cpu().numpy(), rdt.numpy()) < TIGHT
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cls_name", ["EffV2MediumAndDistilbertClassic", "EffV2MediumAndDistilbertNormalized"])
+def test_module_drop_in(pkg, cls_name):
+    """The nn.Module mirrors (reference ctor, forward(_input_ids, _attention_mask, _images, ...), shared state_dict) with
+    stub backbones, eval and train mode, against the oracle on the module's own state_dict."""
+    from garbage_classification_rca_b200 import multimodal_model as M
+
+    class StubText(torch.nn.Module):
+        def forward(self, input_ids=None, attention_mask=None, **kw):
+            return (self.feat.unsqueeze(1),)
+
+    class StubImage(torch.nn.Module):
+        def forward(self, x):
+            return None, None, self.feat
+
+    torch.manual_seed(0)
+    with redirect_stdout(io.StringIO()):
+        m = getattr(M, cls_name)(4, 0.6, 0.0, 0.7, 256, "distilbert", pretrained=False)      # the reference's 6-argument call
+    m.text_model, m.image_model = StubText(), StubImage()
+    m = m.cuda()
+    B = 10
+    g = torch.Generator().manual_seed(5)
+    img, txt, labels = torch.randn(B, 1280, generator=g), torch.randn(B, 768, generator=g), torch.randint(0, 4, (B,), generator=g)
+    m.text_model.feat, m.image_model.feat = txt.cuda(), img.cuda()
+    ids = torch.zeros(B, 8, dtype=torch.long).cuda()
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    normalized = cls_name.endswith("Normalized")
+    m.eval()
+    with torch.no_grad(), redirect_stdout(io.StringIO()) as out:
+        y = m(_input_ids=ids, _attention_mask=torch.ones_like(ids), _images=torch.zeros(B, 3, 8, 8).cuda(), eval=True)
+    assert ("Normalized forward" if normalized else "Classic forward") in out.getvalue()
+    assert rel_err(y.cpu().numpy(), orc.fusion_forward(sd, img, txt, normalized).numpy()) < 1e-4
+    m.train()
+    y = m.forward_features(img.cuda(), txt.cuda())
+    mask = pkg.functional.dropout_mask(m.last_dropout_seed, 0.6, B, 256, "cuda").cpu()
+    assert rel_err(y.detach().cpu().numpy(), orc.fusion_forward(sd, img, txt, normalized, mask, 2.5).numpy()) < 1e-4
+    torch.nn.functional.cross_entropy(y, labels.cuda()).backward()
+    assert m.concat_layer.weight.grad is not None and m.image_to_hidden_size.bias.grad is not None
+    assert m.final_with_everything.weight.grad is None      # the other variants' parameters stay outside the graph
