@@ -394,9 +394,9 @@ struct CaBwdSmem {
   static constexpr uint32_t DYX = DC + op_bytes(48);                 // [128 x 96]: dy*xhat | dy; later dZ
   static constexpr uint32_t DLS = DYX + op_bytes(96);                // DL [128 x 64]; later dS (2 x [64 x 64])
   static constexpr uint32_t P = DLS + 2 * kPHalf;                    // 2 x [64 x 64]
-  static constexpr uint32_t ONES = P + 2 * kPHalf;                   // [16 rows][8] ones: the B operand of the column-sum MMAs, read
-                                                                     // with a ZERO K-stride descriptor (every k-group = these 256 B)
-  static constexpr uint32_t W = al128(ONES + 256);                   // bz | bv | bc | bv (lo)
+  static constexpr uint32_t ONES = P + 2 * kPHalf;                   // 512 B of ones: one K = 16 slice [2 k-groups][16 rows][8] of the all-ones
+                                                                     // B operand of the column-sum MMAs; every K-step re-reads it
+  static constexpr uint32_t W = al128(ONES + 512);                   // bz | bv | bc | bv (lo)
   static constexpr uint32_t LN = W + CaCfg::W_BYTES_BWD;             // gamma, beta [48] fp32
   static constexpr uint32_t PART = LN + 2 * 48 * 4;                  // [2 warpgroups][128 rows] (m1, m2) partial sums
   static constexpr uint32_t BAR = al128(PART + 2 * 128 * 8);
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(kCaBwdThreads, 1) ca_bwd_kernel(const CaBwdArg
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   for (int i = tid; i < 48; i += kCaBwdThreads) { ln_s[i] = D.ln_g[i]; ln_s[48 + i] = D.ln_b[i]; }
-  for (uint32_t i = tid; i < (2 * kPHalf + 256) / 16; i += kCaBwdThreads) {      // P zeros, then the ones operand
+  for (uint32_t i = tid; i < (2 * kPHalf + 512) / 16; i += kCaBwdThreads) {      // P zeros, then the ones operand
     const uint32_t off = i * 16;
     reinterpret_cast<uint4*>(sm + S::P)[i] =
         off < 2 * kPHalf ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
@@ -630,7 +630,7 @@ __global__ void __launch_bounds__(kCaBwdThreads, 1) ca_bwd_kernel(const CaBwdArg
       umma_commit(c.bar);
       mma_steps(tmem + T::G_WF, make_smem_desc(smem_u32(ob), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(dls), kRS, kCS), 2 * kRS,
                 make_idesc_bf16(64, kNCls, 1, 1), 8, !first);
-      mma_steps(tmem + T::G_LN, make_smem_desc(smem_u32(dyx), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(ones), 0, 128), 0,
+      mma_steps(tmem + T::G_LN, make_smem_desc(smem_u32(dyx), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(ones), 256, 128), 0,
                 make_idesc_bf16(128, 16, 1, 0), 8, !first);
       umma_commit(&bars[3]);
     }

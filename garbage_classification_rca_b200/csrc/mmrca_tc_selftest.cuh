@@ -11,9 +11,9 @@ namespace tc {
 // mode bit 1: A is MN-major (source a[K][128]) instead of K-major (source a[128][K])
 // mode bit 2: two M=64 MMAs (rows 0-63 and 64-127) instead of one M=128; the second accumulator sits 16 TMEM
 //             lanes up, i.e. a warp's lanes 0-15 hold rows 16q.. of the first half and lanes 16-31 rows 64+16q..
-// mode bit 3: the B descriptor has a ZERO leading-dimension stride and is not advanced along K: every 8-column group of
-//             B reads the bytes of group 0, i.e. B_eff[n][k] = b[n][k % 8] (K-major B only).  This is how a constant
-//             operand (the all-ones operand of the column-sum MMAs) can live in 16 bytes per row.
+// mode bit 3: B is the constant all-ones operand of the column-sum MMAs (N = 16): ONE K = 16 slice of it (512 bytes of
+//             0x3F80, ordinary descriptor) that every K-step re-reads - the B descriptor is simply not advanced along K:
+//             out[m][n] = sum_k A[m][k].  b is ignored.
 // out[128][N] = A * B^T (logical A[128][K], B[N][K]).  N % 16 == 0, N <= 256, K % 16 == 0.
 __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(int mode, const float* __restrict__ a,
                                                               const float* __restrict__ b, float* __restrict__ out,
@@ -57,7 +57,10 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(int mode, const f
     }
   }
   // ---- stage B ----
-  if (!b_mn) {   // source b[N][K]
+  if (mode & 8) {
+    for (int i = tid; i < 512 / 16; i += 128)
+      reinterpret_cast<uint4*>(sb)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  } else if (!b_mn) {   // source b[N][K]
     for (int i = tid; i < N * (K / 8); i += 128) {
       const int n = i / (K / 8), kc = i % (K / 8);
       float v[8];
@@ -82,10 +85,10 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(int mode, const f
   const uint32_t taddr = tmem_base;
   const bool halves = mode & 4;
   if (tid == 0) {
-    const bool bzero = (mode & 8) && !b_mn;
+    const bool bones = (mode & 8) != 0;
     const uint64_t ad = make_smem_desc(smem_u32(sa), a_lbo, a_sbo);
-    const uint64_t bd = make_smem_desc(smem_u32(sb), bzero ? 0u : b_lbo, b_sbo);
-    const uint32_t b_lbo = bzero ? 0u : (uint32_t(N) / 8) * 128 + 16;      // shadows: K-advance of the B descriptor
+    const uint64_t bd = make_smem_desc(smem_u32(sb), bones ? 256u : b_lbo, b_sbo);
+    const uint32_t b_lbo = bones ? 0u : (uint32_t(N) / 8) * 128 + 16;      // shadows: K-advance of the B descriptor (none for ones)
     if (!halves) {
       const uint32_t idesc = make_idesc_bf16(M, N, a_mn ? 1 : 0, b_mn ? 1 : 0);
       for (int ks = 0; ks < K / 16; ++ks)

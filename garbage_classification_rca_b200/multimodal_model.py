@@ -307,9 +307,14 @@ class EffV2MediumAndDistilbertGated(nn.Module):
         return text_output, text_features, image_out
 
     def head_parameters(self) -> List[torch.Tensor]:
-        """The tensors MM_RCA.forward reads, in MmrcaHeadParams order."""
-        sd = dict(self.named_parameters())
-        return [sd[n] for n in self._head_names]
+        """The tensors MM_RCA.forward reads, in MmrcaHeadParams order (looked up once: walking the 1 300 named parameters
+        of the module on every forward costs more host time than the head's kernels take on the GPU)."""
+        cache = self.__dict__.get("_head_param_cache")
+        if cache is None:
+            sd = dict(self.named_parameters())
+            cache = [sd[n] for n in self._head_names]
+            self.__dict__["_head_param_cache"] = cache
+        return cache
 
     def attach_flat_grads(self, flat_params: bool = False):
         """Give the head a persistent flat gradient bucket: every head parameter's .grad becomes a view of ONE fp32
@@ -445,8 +450,12 @@ class Hierarchical(EffV2MediumAndDistilbertGated):
     (bf16 tcgen05 GEMMs, frozen backbones).  Like the reference it assumes EfficientNetV2-M at 480 x 480."""
 
     def hier_parameters(self) -> List[torch.Tensor]:
-        sd = dict(self.named_parameters())
-        return [sd[n] for n in F.HIER_PARAM_NAMES]
+        cache = self.__dict__.get("_hier_param_cache")
+        if cache is None:
+            sd = dict(self.named_parameters())
+            cache = [sd[n] for n in F.HIER_PARAM_NAMES]
+            self.__dict__["_hier_param_cache"] = cache
+        return cache
 
     def forward_features(self, feats, drop_mask: Optional[torch.Tensor] = None, drop_scale: Optional[float] = None):
         """The head on the six pooled feature tensors (reference :777-816)."""
@@ -486,8 +495,12 @@ class EffV2MediumAndDistilbertClassic(EffV2MediumAndDistilbertGated):
     NORMALIZED = False
 
     def fusion_parameters(self) -> List[torch.Tensor]:
-        sd = dict(self.named_parameters())
-        return [sd[n] for n in F.FUSION_PARAM_NAMES]
+        cache = self.__dict__.get("_fusion_param_cache")
+        if cache is None:
+            sd = dict(self.named_parameters())
+            cache = [sd[n] for n in F.FUSION_PARAM_NAMES]
+            self.__dict__["_fusion_param_cache"] = cache
+        return cache
 
     def forward_features(self, image_features: torch.Tensor, text_features: torch.Tensor,
                          drop_mask: Optional[torch.Tensor] = None, drop_scale: Optional[float] = None):
