@@ -75,6 +75,10 @@ class FusionDesc(C.Structure):
 FUSION_NORMALIZED = 1
 
 
+class TokenDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("batch", "seq_len", "d_in_q", "d_in_kv", "d_kq", "d_v", "reverse")]
+
+
 class CeDesc(C.Structure):
     _fields_ = [("class_weight", _fp), ("label_smoothing", C.c_float)]
 
@@ -87,6 +91,7 @@ EXPORTS = ("mmrca_query", "mmrca_last_error", "mmrca_head_workspace_bytes", "mmr
            "mmrca_hier_workspace_bytes", "mmrca_hier_forward", "mmrca_hier_backward", "mmrca_hier_train_step",
            "mmrca_peer_allreduce_mean", "mmrca_peer_allreduce_pad_bytes", "mmrca_peer_allreduce_status",
            "mmrca_feature_handoff", "mmrca_sgd_step", "mmrca_adamw_step",
+           "mmrca_token_attention_workspace_bytes", "mmrca_token_attention_forward",
            "mmrca_fusion_workspace_bytes", "mmrca_fusion_forward", "mmrca_fusion_backward", "mmrca_fusion_train_step")
 
 
@@ -195,6 +200,10 @@ def lib() -> C.CDLL:
         L.mmrca_peer_allreduce_pad_bytes.restype = C.c_int
         L.mmrca_peer_allreduce_status.argtypes = [_fp, C.c_int32, _fp]
         L.mmrca_peer_allreduce_status.restype = C.c_int
+        L.mmrca_token_attention_workspace_bytes.argtypes = [C.c_void_p]
+        L.mmrca_token_attention_workspace_bytes.restype = C.c_size_t
+        L.mmrca_token_attention_forward.argtypes = [C.c_void_p, C.c_void_p, _fp, _fp, _fp, _fp, C.c_size_t, _fp]
+        L.mmrca_token_attention_forward.restype = C.c_int
         L.mmrca_fusion_workspace_bytes.argtypes = [C.c_void_p]
         L.mmrca_fusion_workspace_bytes.restype = C.c_size_t
         L.mmrca_fusion_forward.argtypes = [C.c_void_p, C.c_void_p, _fp, _fp, _fp, C.c_float, _fp, _fp, C.c_size_t, _fp]
@@ -224,6 +233,10 @@ def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = lib().mmrca_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def last_error() -> str:
+    return lib().mmrca_last_error().decode("utf-8", "replace")
 
 
 def kernel_launches(reset: bool = False) -> int:

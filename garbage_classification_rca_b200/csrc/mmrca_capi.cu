@@ -20,6 +20,7 @@
 #include "mmrca_peer.cuh"
 #include "mmrca_train_aux.cuh"
 #include "mmrca_fusion_fp32.cuh"
+#include "mmrca_token.cuh"
 
 namespace mmrca {
 
@@ -808,6 +809,112 @@ static int hier_backward_impl(const MmrcaHierDesc& d, const MmrcaHierParams& p, 
   return MMRCA_OK;
 }
 
+// ---- token-level attention blocks (mmrca_token.cuh) ------------------------------------------------------------------------
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+  // the driver entry point through the runtime: libmmrca.so does not link libcuda
+  static std::atomic<void*> cached{nullptr};
+  void* f = cached.load(std::memory_order_acquire);
+  if (!f) {
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    cached.store(f, std::memory_order_release);
+  }
+  return reinterpret_cast<TensorMapEncodeFn>(f);
+}
+// bf16 [d2][d1][d0] (d0 contiguous), box {64, box1, 1}, 128-byte swizzle, out-of-range elements read as zero
+static int make_tensor_map(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box1, int rank) {
+  TensorMapEncodeFn enc = tensor_map_encoder();
+  if (!enc) return fail(MMRCA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver%s%s");
+  const cuuint64_t dims[3] = {d0, d1, d2};
+  const cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+  const cuuint32_t box[3] = {uint32_t(tok::kBK), box1, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, cuuint32_t(rank), const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MMRCA_ERR_CUDA, "cuTensorMapEncodeTiled failed (activations must be 16-byte aligned bf16, "
+                                                     "d_in a multiple of 8)%s%s");
+  return MMRCA_OK;
+}
+struct TokenWorkspace {
+  __nv_bfloat16* w;       // stacked bf16 weights: self [2 d_kq + d_v][d_in]; cross [d_kq][d_in_q] then [d_kq + d_v][d_in_kv]
+  float* bias;            // stacked [2 d_kq + d_v]
+  void *q_img, *k_img, *v_img;
+  size_t bytes;
+};
+static TokenWorkspace token_carve(const MmrcaTokenDesc& d, void* base) {
+  TokenWorkspace w;
+  memset(&w, 0, sizeof(w));
+  char* p = static_cast<char*>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { void* r = p ? p + off : nullptr; off += align_up_256(bytes); return r; };
+  const size_t B = size_t(d.batch > 0 ? d.batch : 0), tps = size_t(d.seq_len + tok::kTile - 1) / tok::kTile;
+  w.w = static_cast<__nv_bfloat16*>(take((size_t(d.d_kq) * d.d_in_q + size_t(d.d_kq + d.d_v) * d.d_in_kv) * 2));
+  w.bias = static_cast<float*>(take(size_t(2 * d.d_kq + d.d_v) * 4));
+  w.q_img = take(B * tps * htc::op_bytes(d.d_kq));
+  w.k_img = take(B * tps * htc::op_bytes(d.d_kq));
+  w.v_img = take(B * tps * htc::op_bytes(d.d_v));
+  w.bytes = off;
+  return w;
+}
+static int token_check(const MmrcaTokenDesc* d) {
+  if (!d) return fail(MMRCA_ERR_INVALID, "null descriptor%s%s");
+  if (d->batch < 0 || d->seq_len < 2 || d->seq_len > tok::kTile * tok::kMaxTiles)
+    return fail(MMRCA_ERR_INVALID, "token attention: batch >= 0 and 2 <= seq_len <= 256%s%s");
+  if (!((d->d_kq == 128 && d->d_v == 96) || (d->d_kq == 64 && d->d_v == 48)))
+    return fail(MMRCA_ERR_INVALID, "token attention: (d_kq, d_v) must be (128, 96) or (64, 48) (multimodal_model.py:251-255)%s%s");
+  if (d->d_in_q < 16 || (d->d_in_q & 7) || d->d_in_kv < 16 || (d->d_in_kv & 7))
+    return fail(MMRCA_ERR_INVALID, "token attention: d_in must be a multiple of 8, >= 16%s%s");
+  return MMRCA_OK;
+}
+static int launch_cast(const float* src, __nv_bfloat16* dst, long long n, int sms, cudaStream_t st) {
+  {
+    LaunchScope ls("cast_bf16", st);
+    tok::cast_bf16_kernel<<<int(std::min<long long>((n / 4 + 255) / 256 + 1, 4LL * sms)), 256, 0, st>>>(src, dst, n);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+// one projection GEMM: x [B][L][K] bf16, w [N][K] bf16 (rows: the segments back to back), bias [N]
+static int launch_tok_proj(const MmrcaTokenDesc& d, const void* x, int K, const __nv_bfloat16* w, const float* bias, int N,
+                           const tok::ProjSeg (&segs)[3], cudaStream_t st) {
+  int rc;
+  tok::ProjArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int i = 0; i < 3; ++i) a.seg[i] = segs[i];
+  a.bias = bias; a.N = N; a.K = K;
+  a.nacc = N > 256 ? 2 : 1; a.bn = N / a.nacc;
+  if (a.bn % 16 || a.bn * a.nacc != N) return fail(MMRCA_ERR_INVALID, "projection width must split into 16-column multiples%s%s");
+  a.tiles_per_sample = (d.seq_len + tok::kTile - 1) / tok::kTile;
+  CUtensorMap tx, tw;
+  if ((rc = make_tensor_map(&tx, x, uint64_t(K), uint64_t(d.seq_len), uint64_t(d.batch), tok::kTile, 3))) return rc;
+  if ((rc = make_tensor_map(&tw, w, uint64_t(K), uint64_t(N), 1, uint32_t(a.bn), 2))) return rc;
+  const size_t smem = tok::kStages * size_t(tok::proj_stage_bytes(N)) + 128 + 1024;
+  if ((rc = set_smem(tok::tok_proj_kernel, smem))) return rc;
+  {
+    LaunchScope ls("tok_proj", st);
+    tok::tok_proj_kernel<<<d.batch * a.tiles_per_sample, tok::kProjThreads, smem, st>>>(tx, tw, a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+template <int DKQ, int DV>
+static int launch_tok_attn(const MmrcaTokenDesc& d, const tok::AttnArgs& a, cudaStream_t st) {
+  int rc;
+  using S = tok::AttnSmem<DKQ, DV>;
+  if ((rc = set_smem(tok::tok_attn_kernel<DKQ, DV>, S::BYTES))) return rc;
+  {
+    LaunchScope ls(DKQ == 128 ? "tok_attn<128,96>" : "tok_attn<64,48>", st);
+    tok::tok_attn_kernel<DKQ, DV><<<d.batch * a.tiles_per_sample, 128, S::BYTES, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+
 // ---- classic / normalized fusion heads (mmrca_fusion_fp32.cuh) ---------------------------------------------------------
 struct FusionWorkspace {
   float *h_img, *h_txt, *n_img, *n_txt, *c, *d_c, *d_h_img, *d_h_txt, *dlogits;
@@ -1100,6 +1207,54 @@ int mmrca_head_train_step(const MmrcaHeadDesc* desc, const MmrcaHeadParams* para
   if ((rc = launch_ce(logits, labels, ce, desc->batch, desc->n_classes, loss_out, w.dlogits, st))) return rc;
   return head_backward_impl(*desc, *params, img_feat, txt_feat, drop_mask, drop_scale, w.dlogits, *grads, d_img_feat,
                             d_txt_feat, w, di.sms, st);
+}
+
+size_t mmrca_token_attention_workspace_bytes(const MmrcaTokenDesc* desc) {
+  if (token_check(desc)) return 0;
+  return token_carve(*desc, nullptr).bytes;
+}
+
+int mmrca_token_attention_forward(const MmrcaTokenDesc* desc, const MmrcaAttnParams* p, const void* x_q, const void* x_kv,
+                                  float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc;
+  if ((rc = token_check(desc))) return rc;
+  if (!p || !x_q || !out || !workspace) return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
+  const bool self = x_kv == nullptr || x_kv == x_q;
+  if (self && desc->d_in_q != desc->d_in_kv) return fail(MMRCA_ERR_INVALID, "self attention: d_in_q must equal d_in_kv%s%s");
+  if ((reinterpret_cast<uintptr_t>(x_q) & 15) || (!self && (reinterpret_cast<uintptr_t>(x_kv) & 15)))
+    return fail(MMRCA_ERR_INVALID, "token activations must be 16-byte aligned%s%s");
+  DeviceInfo di;
+  if ((rc = device_info(&di))) return rc;
+  const TokenWorkspace w = token_carve(*desc, workspace);
+  if (workspace_bytes < w.bytes) return fail(MMRCA_ERR_WORKSPACE, "workspace too small%s%s");
+  if (desc->batch == 0) return MMRCA_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int dkq = desc->d_kq, dv = desc->d_v, kq = desc->d_in_q, kkv = desc->d_in_kv;
+  // stacked bf16 weights and fp32 biases: [W_query ; W_key ; W_value]
+  __nv_bfloat16* wq = w.w;
+  __nv_bfloat16* wk = wq + size_t(dkq) * kq;
+  __nv_bfloat16* wv = wk + size_t(dkq) * kkv;
+  if ((rc = launch_cast(p->wq, wq, (long long)dkq * kq, di.sms, st))) return rc;
+  if ((rc = launch_cast(p->wk, wk, (long long)dkq * kkv, di.sms, st))) return rc;
+  if ((rc = launch_cast(p->wv, wv, (long long)dv * kkv, di.sms, st))) return rc;
+  MMRCA_CUDA(cudaMemcpyAsync(w.bias, p->bq, size_t(dkq) * 4, cudaMemcpyDeviceToDevice, st));
+  MMRCA_CUDA(cudaMemcpyAsync(w.bias + dkq, p->bk, size_t(dkq) * 4, cudaMemcpyDeviceToDevice, st));
+  MMRCA_CUDA(cudaMemcpyAsync(w.bias + 2 * dkq, p->bv, size_t(dv) * 4, cudaMemcpyDeviceToDevice, st));
+  const float qscale = 1.0f / sqrtf(float(dkq));      // scores / sqrt(d_kq) (:58-60, :89-91) folded into Q
+  if (self) {
+    const tok::ProjSeg segs[3] = {{w.q_img, dkq, qscale}, {w.k_img, dkq, 1.0f}, {w.v_img, dv, 1.0f}};
+    if ((rc = launch_tok_proj(*desc, x_q, kq, wq, w.bias, 2 * dkq + dv, segs, st))) return rc;
+  } else {
+    const tok::ProjSeg sq[3] = {{w.q_img, dkq, qscale}, {nullptr, 0, 1.0f}, {nullptr, 0, 1.0f}};
+    if ((rc = launch_tok_proj(*desc, x_q, kq, wq, w.bias, dkq, sq, st))) return rc;
+    const tok::ProjSeg skv[3] = {{w.k_img, dkq, 1.0f}, {w.v_img, dv, 1.0f}, {nullptr, 0, 1.0f}};
+    if ((rc = launch_tok_proj(*desc, x_kv, kkv, wk, w.bias + dkq, dkq + dv, skv, st))) return rc;
+  }
+  tok::AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.q_img = w.q_img; a.k_img = w.k_img; a.v_img = w.v_img; a.ln_g = p->ln_g; a.ln_b = p->ln_b; a.out = out;
+  a.L = desc->seq_len; a.tiles_per_sample = (desc->seq_len + tok::kTile - 1) / tok::kTile; a.reverse = desc->reverse ? 1 : 0;
+  return dkq == 128 ? launch_tok_attn<128, 96>(*desc, a, st) : launch_tok_attn<64, 48>(*desc, a, st);
 }
 
 size_t mmrca_fusion_workspace_bytes(const MmrcaFusionDesc* desc) {

@@ -1,0 +1,309 @@
+// Token-level attention blocks (BASELINE.json configs[4]: ViT-L/16's 197 patch tokens x 1024, RoBERTa's 256 tokens x 768):
+// SelfAttention (CVPR_code/multimodal_model.py:39-68) and ReverseCrossAttention (:71-108) for square L <= 256 on real
+// token sequences [B, L, K] instead of the 16 pseudo-tokens of the pooled vector.  The reference classes are shape-generic
+// (Linear on the last dimension, batched matmul, square-attention assert :93), so they are the oracle for these shapes.
+//
+//   tok_proj   Q | K | V = X [W_query | W_key | W_value]^T + b : the one place on this path where the projection is a real
+//              GEMM (K = 1024 / 768, N = 352).  Warp-specialised tcgen05 pipeline: one TMA producer thread
+//              (cp.async.bulk.tensor through tensor maps, 128-byte swizzle: X is read as it lies in HBM, [B, L, K] bf16,
+//              out-of-range token rows of a 128-row tile are zero-filled by the TMA unit), one MMA thread, four epilogue
+//              warps; one CTA owns a 128-token tile and ALL N columns (two accumulators in TMEM), so X is read once.
+//              Epilogue: + bias, Q pre-scaled by 1/sqrt(d_kq), bf16, written as operand IMAGES (canonical no-swizzle
+//              core-matrix layout, one image per (sample, tile, Q|K|V)) that the attention kernel loads with one bulk copy.
+//   tok_attn   per (sample, 128-query tile): S = Q K^T over the sample's <= 256 keys (accumulator [128 x 256] in TMEM),
+//              softmax over the L valid keys (optionally the reverse weights (1 - A) / (L - 1)), C = P V, LayerNorm + ReLU.
+//              One thread per query row for the softmax / LayerNorm; K / V tiles arrive by bulk copy (TMA engine).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mmrca_head_tc_bwd.cuh"
+
+namespace mmrca {
+namespace tok {
+
+using namespace tc;
+using htc::kCS;
+using htc::kRS;
+using htc::row_off;
+
+constexpr int kTile = 128;            // tokens per tile
+constexpr int kMaxTiles = 2;          // L <= 256
+constexpr int kBK = 64;               // K per pipeline stage: one 128-byte swizzle span of bf16
+constexpr int kStages = 3;
+constexpr int kProjThreads = 192;
+
+// ---- TMA tensor-map loads, 128B-swizzled shared-memory descriptors ------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+// K-major operand whose rows are 128-byte swizzle spans (what a {64 bf16, rows} TMA box with SWIZZLE_128B lands):
+// 8-row groups 1024 bytes apart, layout type 2 (SWIZZLE_128B); the leading-dimension offset is unused for this layout.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr >> 4) & 0x3FFF);
+  d |= uint64_t(1) << 16;
+  d |= uint64_t((1024u >> 4) & 0x3FFF) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(2) << 61;
+  return d;
+}
+
+// ---- projection GEMM -------------------------------------------------------------------------------------------------------
+struct ProjSeg { void* img; int cols; float scale; };     // output columns [start, start + cols) -> image; values * scale
+struct ProjArgs {
+  ProjSeg seg[3];           // Q | K | V (cols == 0: absent)
+  const float* bias;        // [N]
+  int N, bn, nacc;          // N = bn * nacc total columns, bn <= 256 per accumulator
+  int K, tiles_per_sample;
+};
+
+__host__ __device__ constexpr uint32_t proj_stage_bytes(int n) { return uint32_t(kTile * kBK * 2 + n * kBK * 2); }
+
+__global__ void __launch_bounds__(kProjThreads, 1) tok_proj_kernel(const __grid_constant__ CUtensorMap tm_x,
+                                                                   const __grid_constant__ CUtensorMap tm_w, const ProjArgs a) {
+  extern __shared__ __align__(1024) uint8_t sm_raw[];
+  // 1024-byte alignment of every operand buffer (SWIZZLE_128B)
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_bytes = kTile * kBK * 2, b_bytes = uint32_t(a.N) * kBK * 2, stage = a_bytes + b_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + kStages * stage);
+  uint64_t* empty = full + kStages;
+  uint64_t* accb = empty + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accb + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x / a.tiles_per_sample, mt = blockIdx.x - b * a.tiles_per_sample;
+  const int n_it = (a.K + kBK - 1) / kBK;
+  if (tid == 0) {
+    for (int i = 0; i < 2 * kStages + 1; ++i) mbar_init(&full[i], 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_w);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % kStages;
+        if (it >= kStages) mbar_wait(&empty[s], uint32_t(it / kStages - 1) & 1u);
+        mbar_arrive_expect_tx(&full[s], stage);
+        uint8_t* sa = sm + s * stage;
+        tma_load_3d(sa, &tm_x, it * kBK, mt * kTile, b, &full[s]);
+        for (int j = 0; j < a.nacc; ++j)
+          tma_load_2d(sa + a_bytes + uint32_t(j) * uint32_t(a.bn) * kBK * 2, &tm_w, it * kBK, j * a.bn, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kTile, a.bn, 0, 0);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % kStages;
+        mbar_wait(&full[s], uint32_t(it / kStages) & 1u);
+        tc_fence_after_sync();
+        const uint32_t sa = smem_u32(sm + s * stage);
+        const uint64_t ad = make_smem_desc_sw128(sa);
+#pragma unroll
+        for (int ks = 0; ks < kBK / 16; ++ks) {
+          for (int j = 0; j < a.nacc; ++j) {
+            const uint64_t bd = make_smem_desc_sw128(sa + a_bytes + uint32_t(j) * uint32_t(a.bn) * kBK * 2);
+            umma_bf16(tmem + uint32_t(j * a.bn), desc_advance(ad, ks * 32), desc_advance(bd, ks * 32), idesc, (it | ks) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(accb);
+    }
+  } else {
+    const int q = warp & 3, row = 32 * q + lane;
+    mbar_wait(accb, 0);
+    tc_fence_after_sync();
+    int seg = 0, seg0 = 0;
+#pragma unroll 1
+    for (int n0 = 0; n0 < a.N; n0 += 16) {
+      while (n0 >= seg0 + a.seg[seg].cols) { seg0 += a.seg[seg].cols; ++seg; }
+      uint32_t r[16];
+      tmem_ld16_nw(tmem + (uint32_t(32 * q) << 16) + uint32_t(n0), r);
+      tmem_wait_ld();
+      const float sc = a.seg[seg].scale;
+      float v[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] = (__uint_as_float(r[e]) + __ldg(a.bias + n0 + e)) * sc;
+      const int c = n0 - seg0, groups = a.seg[seg].cols / 8;
+      uint8_t* tile = static_cast<uint8_t*>(a.seg[seg].img) + (size_t(b) * a.tiles_per_sample + mt) * (size_t(groups) * kCS);
+      const float lo[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
+      const float hi[8] = {v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]};
+      *reinterpret_cast<uint4*>(tile + uint32_t(c >> 3) * kCS + row_off(row)) = pack_bf16x8(lo);
+      *reinterpret_cast<uint4*>(tile + uint32_t((c >> 3) + 1) * kCS + row_off(row)) = pack_bf16x8(hi);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// fp32 -> bf16 (activations that arrive in fp32; weights [W_query | W_key | W_value] stacked row-wise)
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  for (long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * 1024) {
+    if (i + 3 < n) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
+      *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    } else {
+      for (long long j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+    }
+  }
+}
+
+// ---- attention ---------------------------------------------------------------------------------------------------------------
+struct AttnArgs {
+  const void* q_img; const void* k_img; const void* v_img;     // [B][tiles][cols/8 * kCS] operand images (tok_proj)
+  const float* ln_g; const float* ln_b;
+  float* out;               // [B][L][DV] fp32
+  int L, tiles_per_sample, reverse;
+};
+
+template <int DKQ, int DV>
+struct AttnSmem {
+  static constexpr uint32_t QB = htc::op_bytes(DKQ), VB = htc::op_bytes(DV), PB = htc::op_bytes(kMaxTiles * kTile);
+  static constexpr uint32_t Q = 0;
+  static constexpr uint32_t K = htc::al128(Q + QB);                     // kMaxTiles key tiles
+  static constexpr uint32_t V = htc::al128(K + kMaxTiles * QB);         // kMaxTiles value tiles
+  static constexpr uint32_t P = htc::al128(V + kMaxTiles * VB);         // [128 x 256] attention weights
+  static constexpr uint32_t LN = htc::al128(P + PB);
+  static constexpr uint32_t BAR = htc::al128(LN + 2 * DV * 4);
+  static constexpr uint32_t BYTES = BAR + 64;
+  static_assert(BYTES <= 232448, "token attention does not fit shared memory");
+};
+
+template <int DKQ, int DV>
+__global__ void __launch_bounds__(128, 1) tok_attn_kernel(const AttnArgs a) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  using S = AttnSmem<DKQ, DV>;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::BAR);      // [0] loads, [1] MMAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  float* ln_s = reinterpret_cast<float*>(sm + S::LN);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tps = a.tiles_per_sample;
+  const int b = blockIdx.x / tps, mt = blockIdx.x - b * tps;
+  uint8_t *sq = sm + S::Q, *sk = sm + S::K, *sv = sm + S::V, *sp = sm + S::P;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(&bars[0], S::QB + uint32_t(tps) * (S::QB + S::VB));
+    bulk_g2s(sq, static_cast<const uint8_t*>(a.q_img) + (size_t(b) * tps + mt) * S::QB, S::QB, &bars[0]);
+    for (int j = 0; j < tps; ++j) {
+      bulk_g2s(sk + j * S::QB, static_cast<const uint8_t*>(a.k_img) + (size_t(b) * tps + j) * S::QB, S::QB, &bars[0]);
+      bulk_g2s(sv + j * S::VB, static_cast<const uint8_t*>(a.v_img) + (size_t(b) * tps + j) * S::VB, S::VB, &bars[0]);
+    }
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  for (int i = tid; i < DV; i += 128) { ln_s[i] = a.ln_g[i]; ln_s[DV + i] = a.ln_b[i]; }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_base = uint32_t(32 * warp) << 16;
+  constexpr uint32_t COL_S = 0, COL_C = 256;
+  mbar_wait(&bars[0], 0);
+  tc_fence_after_sync();
+  // ---- S = Q K^T (Q carries the 1/sqrt(d_kq) factor): one N = 128 chain per key tile ------------------------------------
+  if (tid == 0) {
+    for (int j = 0; j < tps; ++j)
+      htc::mma_steps(tmem + COL_S + 128 * j, make_smem_desc(smem_u32(sq), kCS, kRS), 2 * kCS,
+                     make_smem_desc(smem_u32(sk + j * S::QB), kCS, kRS), 2 * kCS, make_idesc_bf16(128, 128, 0, 0), DKQ / 16, false);
+    umma_commit(&bars[1]);
+  }
+  mbar_wait(&bars[1], 0);
+  tc_fence_after_sync();
+  // ---- softmax over the L valid keys of my query row (multimodal_model.py:58-60, :89-98) ----------------------------------
+  const int row = tid, ncols = tps * kTile;
+  const int L = a.L;
+  float m = -INFINITY;
+  for (int c0 = 0; c0 < ncols; c0 += 16) {
+    float s[16];
+    htc::ld16f(tmem + lane_base + COL_S + c0, s);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) if (c0 + e < L) m = fmaxf(m, s[e]);
+  }
+  float sum = 0.f;
+  for (int c0 = 0; c0 < ncols; c0 += 16) {
+    float s[16];
+    htc::ld16f(tmem + lane_base + COL_S + c0, s);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) if (c0 + e < L) sum += __expf(s[e] - m);
+  }
+  const float inv = 1.0f / sum, rinv = 1.0f / float(L - 1);
+  for (int c0 = 0; c0 < ncols; c0 += 16) {
+    float s[16], p[16];
+    htc::ld16f(tmem + lane_base + COL_S + c0, s);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const float w = __expf(s[e] - m) * inv;
+      p[e] = c0 + e < L ? (a.reverse ? (1.0f - w) * rinv : w) : 0.f;
+    }
+    htc::st_chunks16(sp, row, c0, p);
+  }
+  fence_proxy_async();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  // ---- C = P V: A = P (K-major over the keys), B = V tiles read MN-major -----------------------------------------------------
+  if (tid == 0) {
+    for (int j = 0; j < tps; ++j)
+      htc::mma_steps(tmem + COL_C, make_smem_desc(smem_u32(sp + uint32_t(16 * j) * kCS), kCS, kRS), 2 * kCS,
+                     make_smem_desc(smem_u32(sv + j * S::VB), kRS, kCS), 2 * kRS, make_idesc_bf16(128, DV, 0, 1), 8, j > 0);
+    umma_commit(&bars[1]);
+  }
+  mbar_wait(&bars[1], 1);
+  tc_fence_after_sync();
+  // ---- LayerNorm + ReLU (:65-66, :105-106) ------------------------------------------------------------------------------------
+  {
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c0 = 0; c0 < DV; c0 += 16) {
+      float x[16];
+      htc::ld16f(tmem + lane_base + COL_C + c0, x);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) { s1 += x[e]; s2 = fmaf(x[e], x[e], s2); }
+    }
+    const float mean = s1 * (1.0f / float(DV));
+    const float rstd = rsqrtf(fmaxf(s2 * (1.0f / float(DV)) - mean * mean, 0.f) + kLnEps);
+    const int t = mt * kTile + row;
+    float* dst = a.out + (size_t(b) * L + t) * DV;
+#pragma unroll
+    for (int c0 = 0; c0 < DV; c0 += 16) {
+      float x[16];
+      htc::ld16f(tmem + lane_base + COL_C + c0, x);
+      if (t < L) {
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          float4 o;
+          o.x = fmaxf(fmaf((x[e] - mean) * rstd, ln_s[c0 + e], ln_s[DV + c0 + e]), 0.f);
+          o.y = fmaxf(fmaf((x[e + 1] - mean) * rstd, ln_s[c0 + e + 1], ln_s[DV + c0 + e + 1]), 0.f);
+          o.z = fmaxf(fmaf((x[e + 2] - mean) * rstd, ln_s[c0 + e + 2], ln_s[DV + c0 + e + 2]), 0.f);
+          o.w = fmaxf(fmaf((x[e + 3] - mean) * rstd, ln_s[c0 + e + 3], ln_s[DV + c0 + e + 3]), 0.f);
+          *reinterpret_cast<float4*>(dst + c0 + e) = o;
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace tok
+}  // namespace mmrca

@@ -715,3 +715,53 @@ class FusionTrainStep:
                 self.d_txt.data_ptr() if self.d_txt is not None else None, self.ws.data_ptr(), self.ws.numel(),
                 _stream_ptr(self.device)), "mmrca_fusion_train_step")
         return self.loss, self.logits
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Token-level attention blocks (BASELINE.json configs[4]): SelfAttention / ReverseCrossAttention on [B, L, d_in], L <= 256
+# ---------------------------------------------------------------------------------------------------------
+class TokenAttention:
+    """SelfAttention.forward (reference multimodal_model.py:51-68) / ReverseCrossAttention.forward (:82-108) on real token
+    sequences (ViT-L/16: [B, 197, 1024]; RoBERTa: [B, 256, 768]; the blocks' own outputs [B, L, 96]) through the bf16
+    tensor-core path: a TMA-fed tcgen05 projection GEMM + one attention kernel per (sample, 128-query tile).  Forward
+    only.  Activations are bf16 (fp32 inputs are cast at the hand-off); parameters fp32 (W_query.weight, W_query.bias,
+    W_key.weight, W_key.bias, W_value.weight, W_value.bias, norm.weight, norm.bias); output fp32 [B, L, d_v].
+    Persistent workspace: build once per (batch, L, widths), call many times."""
+
+    def __init__(self, params: Sequence[torch.Tensor], batch: int, seq_len: int, *, d_in_kv: Optional[int] = None,
+                 reverse: bool = False):
+        self.params = [_check_dev(p.detach(), "attention parameter") for p in params]
+        dev = self.params[0].device
+        d_kq, d_in_q = self.params[0].shape
+        d_v = self.params[4].shape[0]
+        kkv = self.params[2].shape[1]
+        if d_in_kv is not None and d_in_kv != kkv:
+            raise ValueError("d_in_kv does not match W_key")
+        self.desc = N.TokenDesc(batch, seq_len, d_in_q, kkv, d_kq, d_v, 1 if reverse else 0)
+        self.ap = _attn_struct(self.params)
+        nbytes = N.lib().mmrca_token_attention_workspace_bytes(C.byref(self.desc))
+        if nbytes == 0:
+            raise ValueError("unsupported token attention shape: " + N.last_error())
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.out = torch.empty(batch, seq_len, d_v, dtype=torch.float32, device=dev)
+        self.device = dev
+
+    def __call__(self, x_q: torch.Tensor, x_kv: Optional[torch.Tensor] = None) -> torch.Tensor:
+        d = self.desc
+        xs = []
+        for x, k, what in ((x_q, d.d_in_q, "x_q"), (x_kv, d.d_in_kv, "x_kv")):
+            if x is None:
+                xs.append(None)
+                continue
+            if not x.is_cuda:
+                raise RuntimeError(f"{what} must be a CUDA tensor: the token attention has no CPU fallback")
+            if tuple(x.shape) != (d.batch, d.seq_len, k):
+                raise ValueError(f"{what} has shape {tuple(x.shape)}, expected {(d.batch, d.seq_len, k)} "
+                                 "(square attention, reference multimodal_model.py:93)")
+            xs.append((x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)).contiguous())
+        with torch.cuda.device(self.device):
+            N.check(N.lib().mmrca_token_attention_forward(
+                C.byref(self.desc), C.byref(self.ap), xs[0].data_ptr(), xs[1].data_ptr() if xs[1] is not None else None,
+                self.out.data_ptr(), self.ws.data_ptr(), self.ws.numel(), _stream_ptr(self.device)),
+                "mmrca_token_attention_forward")
+        return self.out

@@ -255,6 +255,21 @@ int mmrca_hier_train_step(const MmrcaHierDesc* desc, const MmrcaHierParams* para
                           float* logits, float* loss_out, const MmrcaHierGrads* grads, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* ---- Token-level attention blocks (BASELINE.json configs[4]): SelfAttention.forward (multimodal_model.py:51-68) and
+ * ReverseCrossAttention.forward (:82-108) on real token sequences x [B, L, d_in] with 2 <= L <= 256 (ViT-L/16: 197 x 1024,
+ * RoBERTa: 256 x 768) instead of the head's 16 pseudo-tokens.  Square attention like the reference (:93): x_q and x_kv share L.
+ * bf16 tensor-core path (2e-2 absolute contract): the Q | K | V projection is a TMA-fed tcgen05 GEMM over the tokens, the
+ * attention core one kernel per (sample, 128-query tile).  Forward only (inference / frozen blocks).
+ *   x_q, x_kv: bf16 [B, L, d_in_q] / [B, L, d_in_kv], 16-byte aligned; x_kv == NULL or == x_q: self attention.
+ *   (d_kq, d_v) in {(128, 96), (64, 48)}; p: fp32 parameters in torch.nn.Linear layout; out: fp32 [B, L, d_v]. ---- */
+typedef struct MmrcaTokenDesc {
+  int32_t batch, seq_len, d_in_q, d_in_kv, d_kq, d_v;
+  int32_t reverse;    /* (1 - A) / (L - 1) weights (:95-99) */
+} MmrcaTokenDesc;
+size_t mmrca_token_attention_workspace_bytes(const MmrcaTokenDesc* desc);
+int mmrca_token_attention_forward(const MmrcaTokenDesc* desc, const MmrcaAttnParams* p, const void* x_q, const void* x_kv,
+                                  float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- Classic / Normalized late-fusion heads (--late_fusion=classic | normalized): everything after the backbones in
  * EffV2MediumAndDistilbertClassic / ...Normalized.forward (multimodal_model.py:489-579) - the image and text projections
  * into the shared fusion dimension H = num_neurons_FC (:521-522, :566-567), for "normalized" their row L2 normalisation
