@@ -713,6 +713,110 @@ def run_full(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_token(args, rank, world, local_rank):
+    """Secondary workload (BASELINE.json configs[4] / SURVEY.md §8 d cfg 5): the attention blocks on real token sequences,
+    forward, `--batch` samples per GPU (replicas: inference shards by batch, no collective):
+      SelfAttention(1024 -> 128 / 96) on ViT-L/16 tokens [B, 197, 1024], SelfAttention(768 -> 128 / 96) on RoBERTa tokens
+      [B, 256, 768], and a ReverseCrossAttention(96 -> 64 / 48) on each sequence length (the reference asserts square
+      attention, multimodal_model.py:93: the partner sequence is the block output of the neighbouring sample).
+    The projection GEMM (K = 1024 / 768) is where this path meets the tensor roof: its achieved TFLOP/s is reported against
+    the measured bf16 peak; FLOPs count the L valid tokens only (tiles are padded to 128 rows)."""
+    import torch
+    import torch.distributed as dist
+    from garbage_classification_rca_b200 import _native as N, functional as F
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    g = torch.Generator().manual_seed(7 + rank)
+
+    def block(d_q, d_kv, d_kq, d_v):
+        def lin(o, i):
+            k = 1.0 / i ** 0.5
+            return [((torch.rand(o, i, generator=g) * 2 - 1) * k).to(dev), ((torch.rand(o, generator=g) * 2 - 1) * k).to(dev)]
+        return lin(d_kq, d_q) + lin(d_kq, d_kv) + lin(d_v, d_kv) + [torch.ones(d_v, device=dev), torch.zeros(d_v, device=dev)]
+
+    NB = 2      # 2 x (B x 197 x 1024 + B x 256 x 768) bf16: rotates over more than the L2 for B >= 128
+    x_img = [torch.randn(B, 197, 1024, generator=g).bfloat16().to(dev) for _ in range(NB)]
+    x_txt = [torch.randn(B, 256, 768, generator=g).bfloat16().to(dev) for _ in range(NB)]
+    sa_i = F.TokenAttention(block(1024, 1024, 128, 96), B, 197)
+    sa_t = F.TokenAttention(block(768, 768, 128, 96), B, 256)
+    ca_i = F.TokenAttention(block(96, 96, 64, 48), B, 197, reverse=True)
+    ca_t = F.TokenAttention(block(96, 96, 64, 48), B, 256, reverse=True)
+
+    def one(i):
+        i_sa = sa_i(x_img[i % NB])
+        t_sa = sa_t(x_txt[i % NB])
+        i_16, t_16 = i_sa.to(torch.bfloat16), t_sa.to(torch.bfloat16)
+        ca_i(i_16, torch.roll(i_16, 1, 0))
+        ca_t(t_16, torch.roll(t_16, 1, 0))
+
+    for i in range(W):
+        one(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    N.kernel_launches(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        one(W + i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = N.kernel_launches()
+    ms = e0.elapsed_time(e1)
+    per_kernel = {}
+    N.timing_begin(launches + 64)
+    for i in range(K):
+        one(W + i)
+    recs = N.timing_end(launches + 64)
+    torch.cuda.synchronize()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    if rank == 0:
+        # per step the projection launches come in a fixed order: SA image (N 352, K 1024), SA text (352, 768), then per
+        # cross block Q (64, 96) and K|V (112, 96)
+        proj = [r for r in recs if r[0] == "tok_proj"]
+        shapes = [(197, 1024, 352), (256, 768, 352), (197, 96, 64), (197, 96, 112), (256, 96, 64), (256, 96, 112)]
+        per_shape = {}
+        for j, (name, t_ms) in enumerate(proj):
+            per_shape.setdefault(shapes[j % 6], []).append(t_ms)
+        for name, t_ms in recs:
+            per_kernel.setdefault(name, []).append(t_ms)
+        peaks = load_peaks()
+        big = (197, 1024, 352)
+        big_ms = statistics.mean(per_shape[big])
+        big_flops = 2.0 * B * big[0] * big[1] * big[2]
+        ach = big_flops / (big_ms * 1e-3) / 1e12
+        flops_sample = sum(2.0 * L * Kd * Nn for (L, Kd, Nn) in shapes) + \
+            2 * 2.0 * (197 * 197 + 256 * 256) * (128 + 96) / 2 + 2 * 2.0 * (197 * 197 + 256 * 256) * (64 + 48) / 2
+        emit(json.dumps({
+            "metric": "token_level_rca_blocks_fwd_samples_per_s", "value": world * B * K / (ms * 1e-3), "unit": "samples/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"token-level attention blocks forward (BASELINE.json configs[4]): SelfAttention on ViT-L/16 tokens "
+                                   f"[{B},197,1024] and RoBERTa tokens [{B},256,768], ReverseCrossAttention 96->64/48 at L=197 and L=256; "
+                                   f"batch {B}/GPU, replicas (no collective); secondary workload",
+                       "parallelism": f"replicas x{world}", "l2": f"inputs rotate over {NB} batches"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "tok_proj [B*197 x 1024] x [1024 x 352]", "achieved": ach,
+                         "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
+                         "kernel_ms": big_ms, "traffic": None,
+                         "flops": "2 * B * 197 * 1024 * 352 (valid tokens; tiles are padded to 2 x 128 rows per sample)"},
+            "roofline_step": {"bound": "tensor", "achieved": B * K / (ms * 1e-3) * flops_sample / 1e12,
+                              "peak": peaks["bf16_sustained"], "frac": B * K / (ms * 1e-3) * flops_sample / 1e12 / peaks["bf16_sustained"],
+                              "flops_per_sample": flops_sample},
+            "proj_ms_by_shape": {f"L{L}_K{Kd}_N{Nn}": round(statistics.mean(v), 4) for (L, Kd, Nn), v in per_shape.items()},
+            "kernels_ms_per_step": {k: round(sum(v) / K, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -sum(kv[1]))}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 _JSON_FD = None
 
 
@@ -741,7 +845,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl", action="store_true", help="N > 1: all-reduce the gradient bucket with NCCL instead of the "
                                                         "one-shot peer-memory kernel")
-    ap.add_argument("--workload", default="mmrca", choices=("mmrca", "hierarchical", "full"),
+    ap.add_argument("--workload", default="mmrca", choices=("mmrca", "hierarchical", "full", "token"),
                     help="mmrca: the BASELINE.json line (default); hierarchical: the second --late_fusion head (1 GPU); full: a whole "
                          "training step with the stock backbones (BASELINE.json configs[2], use --batch 256)")
     ap.add_argument("--variant", default="rca", choices=("rca", "ca", "cross_only", "features_only"),
@@ -757,6 +861,8 @@ def main():
             run_hier(args)
     elif args.workload == "full":
         run_full(args, rank, world, local_rank)
+    elif args.workload == "token":
+        run_token(args, rank, world, local_rank)
     elif args.impl == "reference":
         run_reference(args, rank, world)
     else:

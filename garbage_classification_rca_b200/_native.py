@@ -76,7 +76,11 @@ FUSION_NORMALIZED = 1
 
 
 class TokenDesc(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("batch", "seq_len", "d_in_q", "d_in_kv", "d_kq", "d_v", "reverse")]
+    _fields_ = [(n, C.c_int32) for n in ("batch", "seq_len", "d_in_q", "d_in_kv", "d_kq", "d_v", "reverse")] + \
+               [("flags", C.c_uint32)]
+
+
+TOKEN_WEIGHTS_READY = 1
 
 
 class CeDesc(C.Structure):

@@ -881,7 +881,7 @@ static int launch_cast(const float* src, __nv_bfloat16* dst, long long n, int sm
 }
 // one projection GEMM: x [B][L][K] bf16, w [N][K] bf16 (rows: the segments back to back), bias [N]
 static int launch_tok_proj(const MmrcaTokenDesc& d, const void* x, int K, const __nv_bfloat16* w, const float* bias, int N,
-                           const tok::ProjSeg (&segs)[3], cudaStream_t st) {
+                           const tok::ProjSeg (&segs)[3], int sms, cudaStream_t st) {
   int rc;
   tok::ProjArgs a;
   memset(&a, 0, sizeof(a));
@@ -890,14 +890,15 @@ static int launch_tok_proj(const MmrcaTokenDesc& d, const void* x, int K, const 
   a.nacc = N > 256 ? 2 : 1; a.bn = N / a.nacc;
   if (a.bn % 16 || a.bn * a.nacc != N) return fail(MMRCA_ERR_INVALID, "projection width must split into 16-column multiples%s%s");
   a.tiles_per_sample = (d.seq_len + tok::kTile - 1) / tok::kTile;
+  a.L = d.seq_len; a.rows = d.batch * d.seq_len;
   CUtensorMap tx, tw;
-  if ((rc = make_tensor_map(&tx, x, uint64_t(K), uint64_t(d.seq_len), uint64_t(d.batch), tok::kTile, 3))) return rc;
+  if ((rc = make_tensor_map(&tx, x, uint64_t(K), uint64_t(a.rows), 1, tok::kTile, 2))) return rc;
   if ((rc = make_tensor_map(&tw, w, uint64_t(K), uint64_t(N), 1, uint32_t(a.bn), 2))) return rc;
-  const size_t smem = tok::kStages * size_t(tok::proj_stage_bytes(N)) + 128 + 1024;
+  const size_t smem = tok::kStages * size_t(tok::proj_stage_bytes(N)) + 128 + size_t(N) * 4 + 1024;
   if ((rc = set_smem(tok::tok_proj_kernel, smem))) return rc;
   {
     LaunchScope ls("tok_proj", st);
-    tok::tok_proj_kernel<<<d.batch * a.tiles_per_sample, tok::kProjThreads, smem, st>>>(tx, tw, a);
+    tok::tok_proj_kernel<<<min((a.rows + tok::kTile - 1) / tok::kTile, sms), tok::kProjThreads, smem, st>>>(tx, tw, a);
   }
   MMRCA_CUDA(cudaGetLastError());
   return MMRCA_OK;
@@ -1234,21 +1235,23 @@ int mmrca_token_attention_forward(const MmrcaTokenDesc* desc, const MmrcaAttnPar
   __nv_bfloat16* wq = w.w;
   __nv_bfloat16* wk = wq + size_t(dkq) * kq;
   __nv_bfloat16* wv = wk + size_t(dkq) * kkv;
-  if ((rc = launch_cast(p->wq, wq, (long long)dkq * kq, di.sms, st))) return rc;
-  if ((rc = launch_cast(p->wk, wk, (long long)dkq * kkv, di.sms, st))) return rc;
-  if ((rc = launch_cast(p->wv, wv, (long long)dv * kkv, di.sms, st))) return rc;
-  MMRCA_CUDA(cudaMemcpyAsync(w.bias, p->bq, size_t(dkq) * 4, cudaMemcpyDeviceToDevice, st));
-  MMRCA_CUDA(cudaMemcpyAsync(w.bias + dkq, p->bk, size_t(dkq) * 4, cudaMemcpyDeviceToDevice, st));
-  MMRCA_CUDA(cudaMemcpyAsync(w.bias + 2 * dkq, p->bv, size_t(dv) * 4, cudaMemcpyDeviceToDevice, st));
+  if (!(desc->flags & MMRCA_TOKEN_WEIGHTS_READY)) {
+    if ((rc = launch_cast(p->wq, wq, (long long)dkq * kq, di.sms, st))) return rc;
+    if ((rc = launch_cast(p->wk, wk, (long long)dkq * kkv, di.sms, st))) return rc;
+    if ((rc = launch_cast(p->wv, wv, (long long)dv * kkv, di.sms, st))) return rc;
+    MMRCA_CUDA(cudaMemcpyAsync(w.bias, p->bq, size_t(dkq) * 4, cudaMemcpyDeviceToDevice, st));
+    MMRCA_CUDA(cudaMemcpyAsync(w.bias + dkq, p->bk, size_t(dkq) * 4, cudaMemcpyDeviceToDevice, st));
+    MMRCA_CUDA(cudaMemcpyAsync(w.bias + 2 * dkq, p->bv, size_t(dv) * 4, cudaMemcpyDeviceToDevice, st));
+  }
   const float qscale = 1.0f / sqrtf(float(dkq));      // scores / sqrt(d_kq) (:58-60, :89-91) folded into Q
   if (self) {
     const tok::ProjSeg segs[3] = {{w.q_img, dkq, qscale}, {w.k_img, dkq, 1.0f}, {w.v_img, dv, 1.0f}};
-    if ((rc = launch_tok_proj(*desc, x_q, kq, wq, w.bias, 2 * dkq + dv, segs, st))) return rc;
+    if ((rc = launch_tok_proj(*desc, x_q, kq, wq, w.bias, 2 * dkq + dv, segs, di.sms, st))) return rc;
   } else {
     const tok::ProjSeg sq[3] = {{w.q_img, dkq, qscale}, {nullptr, 0, 1.0f}, {nullptr, 0, 1.0f}};
-    if ((rc = launch_tok_proj(*desc, x_q, kq, wq, w.bias, dkq, sq, st))) return rc;
+    if ((rc = launch_tok_proj(*desc, x_q, kq, wq, w.bias, dkq, sq, di.sms, st))) return rc;
     const tok::ProjSeg skv[3] = {{w.k_img, dkq, 1.0f}, {w.v_img, dv, 1.0f}, {nullptr, 0, 1.0f}};
-    if ((rc = launch_tok_proj(*desc, x_kv, kkv, wk, w.bias + dkq, dkq + dv, skv, st))) return rc;
+    if ((rc = launch_tok_proj(*desc, x_kv, kkv, wk, w.bias + dkq, dkq + dv, skv, di.sms, st))) return rc;
   }
   tok::AttnArgs a;
   memset(&a, 0, sizeof(a));

@@ -44,6 +44,10 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// L2 prefetch of a box (no shared memory, nothing to wait for)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
@@ -66,10 +70,15 @@ struct ProjArgs {
   const float* bias;        // [N]
   int N, bn, nacc;          // N = bn * nacc total columns, bn <= 256 per accumulator
   int K, tiles_per_sample;
+  int L, rows;              // tokens per sample, B * L: the GEMM's M dimension is the FLAT token index (no per-sample padding
+                            // of the MMA work); the epilogue scatters row r to image (r / L, (r % L) / 128), row (r % L) % 128
 };
 
 __host__ __device__ constexpr uint32_t proj_stage_bytes(int n) { return uint32_t(kTile * kBK * 2 + n * kBK * 2); }
 
+// Persistent: grid = min(tiles, SMs); a CTA walks the 128-row tiles blockIdx.x, + gridDim.x, ...  The producer's stage ring
+// runs across tile boundaries, so the next tile's first stages land while the epilogue warps drain the accumulators; the
+// MMA thread waits for the drain (tmem_empty) before it overwrites them.
 __global__ void __launch_bounds__(kProjThreads, 1) tok_proj_kernel(const __grid_constant__ CUtensorMap tm_x,
                                                                    const __grid_constant__ CUtensorMap tm_w, const ProjArgs a) {
   extern __shared__ __align__(1024) uint8_t sm_raw[];
@@ -78,75 +87,106 @@ __global__ void __launch_bounds__(kProjThreads, 1) tok_proj_kernel(const __grid_
   const uint32_t a_bytes = kTile * kBK * 2, b_bytes = uint32_t(a.N) * kBK * 2, stage = a_bytes + b_bytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(sm + kStages * stage);
   uint64_t* empty = full + kStages;
-  uint64_t* accb = empty + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accb + 1);
+  uint64_t* accb = empty + kStages;          // accumulators complete (MMA -> epilogue)
+  uint64_t* tmem_empty = accb + 1;           // accumulators drained (epilogue -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  float* bias_s = reinterpret_cast<float*>(tmem_slot + 2);      // [N]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.x / a.tiles_per_sample, mt = blockIdx.x - b * a.tiles_per_sample;
+  const int tiles = (a.rows + kTile - 1) / kTile;
   const int n_it = (a.K + kBK - 1) / kBK;
   if (tid == 0) {
-    for (int i = 0; i < 2 * kStages + 1; ++i) mbar_init(&full[i], 1);
+    for (int i = 0; i < 2 * kStages + 2; ++i) mbar_init(&full[i], 1);
     mbar_fence_init();
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w);
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  for (int i = tid; i < a.N; i += kProjThreads) bias_s[i] = __ldg(a.bias + i);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < n_it; ++it) {
-        const int s = it % kStages;
-        if (it >= kStages) mbar_wait(&empty[s], uint32_t(it / kStages - 1) & 1u);
-        mbar_arrive_expect_tx(&full[s], stage);
-        uint8_t* sa = sm + s * stage;
-        tma_load_3d(sa, &tm_x, it * kBK, mt * kTile, b, &full[s]);
-        for (int j = 0; j < a.nacc; ++j)
-          tma_load_2d(sa + a_bytes + uint32_t(j) * uint32_t(a.bn) * kBK * 2, &tm_w, it * kBK, j * a.bn, &full[s]);
+      // (measured and dropped: L2 prefetch of the X boxes 8 k-blocks ahead, and a per-CTA rotation of the K order against
+      //  hot L2 slices - neither moved the kernel: it runs at the L2 -> SM rate this tile shape needs)
+      int git = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int it = 0; it < n_it; ++it, ++git) {
+          const int s = git % kStages;
+          if (git >= kStages) mbar_wait(&empty[s], uint32_t(git / kStages - 1) & 1u);
+          mbar_arrive_expect_tx(&full[s], stage);
+          uint8_t* sa = sm + s * stage;
+          tma_load_2d(sa, &tm_x, it * kBK, tile * kTile, &full[s]);
+          for (int j = 0; j < a.nacc; ++j)
+            tma_load_2d(sa + a_bytes + uint32_t(j) * uint32_t(a.bn) * kBK * 2, &tm_w, it * kBK, j * a.bn, &full[s]);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(kTile, a.bn, 0, 0);
-      for (int it = 0; it < n_it; ++it) {
-        const int s = it % kStages;
-        mbar_wait(&full[s], uint32_t(it / kStages) & 1u);
-        tc_fence_after_sync();
-        const uint32_t sa = smem_u32(sm + s * stage);
-        const uint64_t ad = make_smem_desc_sw128(sa);
+      int git = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++ti) {
+        if (ti > 0) { mbar_wait(tmem_empty, uint32_t(ti - 1) & 1u); tc_fence_after_sync(); }
+        for (int it = 0; it < n_it; ++it, ++git) {
+          const int s = git % kStages;
+          mbar_wait(&full[s], uint32_t(git / kStages) & 1u);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(sm + s * stage);
+          const uint64_t ad = make_smem_desc_sw128(sa);
 #pragma unroll
-        for (int ks = 0; ks < kBK / 16; ++ks) {
-          for (int j = 0; j < a.nacc; ++j) {
-            const uint64_t bd = make_smem_desc_sw128(sa + a_bytes + uint32_t(j) * uint32_t(a.bn) * kBK * 2);
-            umma_bf16(tmem + uint32_t(j * a.bn), desc_advance(ad, ks * 32), desc_advance(bd, ks * 32), idesc, (it | ks) ? 1u : 0u);
+          for (int ks = 0; ks < kBK / 16; ++ks) {
+            for (int j = 0; j < a.nacc; ++j) {
+              const uint64_t bd = make_smem_desc_sw128(sa + a_bytes + uint32_t(j) * uint32_t(a.bn) * kBK * 2);
+              umma_bf16(tmem + uint32_t(j * a.bn), desc_advance(ad, ks * 32), desc_advance(bd, ks * 32), idesc, (it | ks) ? 1u : 0u);
+            }
           }
+          umma_commit(&empty[s]);
         }
-        umma_commit(&empty[s]);
+        umma_commit(accb);
       }
-      umma_commit(accb);
     }
   } else {
-    const int q = warp & 3, row = 32 * q + lane;
-    mbar_wait(accb, 0);
-    tc_fence_after_sync();
-    int seg = 0, seg0 = 0;
+    const int q = warp & 3;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++ti) {
+      const int r_flat = tile * kTile + 32 * q + lane;
+      const bool live = r_flat < a.rows;
+      const int b = live ? r_flat / a.L : 0, t = r_flat - b * a.L, mt = t >> 7, row = t & 127;
+      mbar_wait(accb, uint32_t(ti) & 1u);
+      tc_fence_after_sync();
+      int seg = 0, seg0 = 0;
 #pragma unroll 1
-    for (int n0 = 0; n0 < a.N; n0 += 16) {
-      while (n0 >= seg0 + a.seg[seg].cols) { seg0 += a.seg[seg].cols; ++seg; }
-      uint32_t r[16];
-      tmem_ld16_nw(tmem + (uint32_t(32 * q) << 16) + uint32_t(n0), r);
-      tmem_wait_ld();
-      const float sc = a.seg[seg].scale;
-      float v[16];
+      for (int n0 = 0; n0 < a.N; n0 += 32) {
+        uint32_t r0[16], r1[16];
+        const bool two = n0 + 16 < a.N;
+        tmem_ld16_nw(tmem + (uint32_t(32 * q) << 16) + uint32_t(n0), r0);
+        if (two) tmem_ld16_nw(tmem + (uint32_t(32 * q) << 16) + uint32_t(n0 + 16), r1);
+        tmem_wait_ld();
 #pragma unroll
-      for (int e = 0; e < 16; ++e) v[e] = (__uint_as_float(r[e]) + __ldg(a.bias + n0 + e)) * sc;
-      const int c = n0 - seg0, groups = a.seg[seg].cols / 8;
-      uint8_t* tile = static_cast<uint8_t*>(a.seg[seg].img) + (size_t(b) * a.tiles_per_sample + mt) * (size_t(groups) * kCS);
-      const float lo[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
-      const float hi[8] = {v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]};
-      *reinterpret_cast<uint4*>(tile + uint32_t(c >> 3) * kCS + row_off(row)) = pack_bf16x8(lo);
-      *reinterpret_cast<uint4*>(tile + uint32_t((c >> 3) + 1) * kCS + row_off(row)) = pack_bf16x8(hi);
+        for (int h = 0; h < 2; ++h) {
+          if (h == 1 && !two) break;
+          const int nn = n0 + 16 * h;
+          while (nn >= seg0 + a.seg[seg].cols) { seg0 += a.seg[seg].cols; ++seg; }
+          const float sc = a.seg[seg].scale;
+          float v[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = (__uint_as_float(h ? r1[e] : r0[e]) + bias_s[nn + e]) * sc;
+          const int c = nn - seg0, groups = a.seg[seg].cols / 8;
+          uint8_t* img = static_cast<uint8_t*>(a.seg[seg].img) + (size_t(b) * a.tiles_per_sample + mt) * (size_t(groups) * kCS);
+          const float lo[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
+          const float hi[8] = {v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]};
+          if (live) {
+            *reinterpret_cast<uint4*>(img + uint32_t(c >> 3) * kCS + row_off(row)) = pack_bf16x8(lo);
+            *reinterpret_cast<uint4*>(img + uint32_t((c >> 3) + 1) * kCS + row_off(row)) = pack_bf16x8(hi);
+          }
+        }
+      }
+      // the accumulators are drained: hand TMEM back to the MMA thread
+      tc_fence_before_sync();
+      named_bar_sync(1, 128);
+      if (tid == 64) mbar_arrive(tmem_empty);
     }
   }
   tc_fence_before_sync();
@@ -219,6 +259,17 @@ __global__ void __launch_bounds__(128, 1) tok_attn_kernel(const AttnArgs a) {
   constexpr uint32_t COL_S = 0, COL_C = 256;
   mbar_wait(&bars[0], 0);
   tc_fence_after_sync();
+  // The images' rows beyond the sample's L tokens were never written by the projection: key rows there only feed masked
+  // score columns, query rows only feed output rows that are not stored, but VALUE rows meet P = 0 in the P V product
+  // and must be finite: zero them here (made visible to the tensor core by the fence that follows the softmax).
+  {
+    const int pad0 = a.L - (tps - 1) * kTile;           // first pad row of the last value tile
+    uint8_t* vlast = sv + (tps - 1) * S::VB;
+    for (int i = tid; i < (kTile - pad0) * (DV / 8); i += 128) {
+      const int r = pad0 + i / (DV / 8), g = i % (DV / 8);
+      *reinterpret_cast<uint4*>(vlast + uint32_t(g) * kCS + row_off(r)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
   // ---- S = Q K^T (Q carries the 1/sqrt(d_kq) factor): one N = 128 chain per key tile ------------------------------------
   if (tid == 0) {
     for (int j = 0; j < tps; ++j)

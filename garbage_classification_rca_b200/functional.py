@@ -737,7 +737,7 @@ class TokenAttention:
         kkv = self.params[2].shape[1]
         if d_in_kv is not None and d_in_kv != kkv:
             raise ValueError("d_in_kv does not match W_key")
-        self.desc = N.TokenDesc(batch, seq_len, d_in_q, kkv, d_kq, d_v, 1 if reverse else 0)
+        self.desc = N.TokenDesc(batch, seq_len, d_in_q, kkv, d_kq, d_v, 1 if reverse else 0, 0)
         self.ap = _attn_struct(self.params)
         nbytes = N.lib().mmrca_token_attention_workspace_bytes(C.byref(self.desc))
         if nbytes == 0:
@@ -764,4 +764,9 @@ class TokenAttention:
                 C.byref(self.desc), C.byref(self.ap), xs[0].data_ptr(), xs[1].data_ptr() if xs[1] is not None else None,
                 self.out.data_ptr(), self.ws.data_ptr(), self.ws.numel(), _stream_ptr(self.device)),
                 "mmrca_token_attention_forward")
+        self.desc.flags |= N.TOKEN_WEIGHTS_READY      # the bf16 weights now sit in the workspace
         return self.out
+
+    def refresh_weights(self) -> None:
+        """Call after the parameters changed (optimizer step, load_state_dict): the next call converts them again."""
+        self.desc.flags &= ~N.TOKEN_WEIGHTS_READY

@@ -262,9 +262,12 @@ int mmrca_hier_train_step(const MmrcaHierDesc* desc, const MmrcaHierParams* para
  * attention core one kernel per (sample, 128-query tile).  Forward only (inference / frozen blocks).
  *   x_q, x_kv: bf16 [B, L, d_in_q] / [B, L, d_in_kv], 16-byte aligned; x_kv == NULL or == x_q: self attention.
  *   (d_kq, d_v) in {(128, 96), (64, 48)}; p: fp32 parameters in torch.nn.Linear layout; out: fp32 [B, L, d_v]. ---- */
+#define MMRCA_TOKEN_WEIGHTS_READY 1u /* the workspace already holds this block's bf16 weights (an earlier call with the same,
+                                       unchanged parameters on the same workspace): skip their conversion */
 typedef struct MmrcaTokenDesc {
   int32_t batch, seq_len, d_in_q, d_in_kv, d_kq, d_v;
   int32_t reverse;    /* (1 - A) / (L - 1) weights (:95-99) */
+  uint32_t flags;     /* MMRCA_TOKEN_* */
 } MmrcaTokenDesc;
 size_t mmrca_token_attention_workspace_bytes(const MmrcaTokenDesc* desc);
 int mmrca_token_attention_forward(const MmrcaTokenDesc* desc, const MmrcaAttnParams* p, const void* x_q, const void* x_kv,
