@@ -12,7 +12,11 @@ batch and the flat head-gradient bucket is all-reduced once per step (plain data
 One JSON line on stdout (rank 0):
   value        samples/s with inputs already resident in HBM (device-timed, max over ranks)
   e2e          the same metric through the public host API with HOST buffers: pinned H2D of the features and
-               labels and D2H of loss + logits inside the timed region (double-buffered on a copy stream)
+               labels (one staged record per batch, three slots deep on a copy stream; bf16 features when
+               compute=bf16, MMRCA_FLAG_FEATURES_BF16) and D2H of loss + logits inside the timed region;
+               e2e_fp32_features: the same with fp32 features
+  gpu_eager_baseline   the reference's op sequence under PyTorch eager on the same GPU (fp32 and bf16 autocast)
+  collective_check     N > 1: the peer-memory all-reduce against NCCL on the same bucket (untimed)
   roofline     dominant kernel: algorithmic FLOPs per launch / its CUDA-event duration, vs the measured
                bf16 tensor peak (MEASURED_PEAKS.json) — the roof SURVEY.md §8(d) assigns to the fused head
   cpu_baseline the oracle port of the reference timed on this box's host cores (N = 1 only)
@@ -188,6 +192,19 @@ def ncu_traffic(kernel, batch):
         if int(d.get("batch", -1)) != batch:
             return None
         return d["kernels"].get(kernel)
+    except (OSError, ValueError, KeyError):
+        return None
+
+
+def ncu_step_traffic(batch):
+    """Sum of the per-launch DRAM bytes of every kernel of the step (profiles/traffic.json), if taken at this batch."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as fh:
+            d = json.load(fh)
+        if int(d.get("batch", -1)) != batch:
+            return None
+        return float(sum(d["kernels"].values()))
     except (OSError, ValueError, KeyError):
         return None
 
@@ -509,7 +526,8 @@ def run_b200(args, rank, world, local_rank):
                      "kernel_ms": dom_ms, "kernel_share_of_step": share[dom] / total_k,
                      "timing": f"second pass of {K} steps with per-kernel CUDA events on the launch stream"},
         "roofline_step": {"bound": "tensor", "achieved": step_tflops, "peak": peak, "unit": "TFLOP/s",
-                          "frac": step_tflops / peak, "flops_per_sample": FLOPS_FWD_BWD,
+                          "frac": step_tflops / peak, "flops_per_sample": FLOPS_FWD_BWD, "traffic": ncu_step_traffic(B),
+                          "algorithmic_bytes": BYTES_PER_SAMPLE * B,
                           "hbm_view": {"achieved_gbs": value / world * BYTES_PER_SAMPLE / 1e9,
                                        "peak_gbs": peaks["hbm_gbs"]}},
         "kernels_ms_per_step": {k: round(v, 4) for k, v in sorted(share.items(), key=lambda kv: -kv[1])},

@@ -62,7 +62,8 @@ def full(path):
 
 LABELS = (("ca_bwd_kernel", "ca_bwd_bf16"), ("sa_bwd_kernel", "sa_bwd_bf16"),
           ("sa_fwd_kernel", "sa_fwd_bf16"), ("ca_fwd_kernel", "ca_fwd_bf16"), ("ce_feat_kernel", "ce_feat"),
-          ("prep_kernel", "prep_bf16"), ("finalize_kernel", "finalize_bf16"), ("bwd_kernel", "bwd_bf16"))
+          ("prep_feat_kernel", "prep_feat"), ("prep_kernel", "prep_bf16"), ("finalize_kernel", "finalize_bf16"),
+          ("bwd_kernel", "bwd_bf16"))
 
 
 def traffic(path, batch):
