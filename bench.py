@@ -372,9 +372,8 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def device_step(i):
-        step.zero_grad()
-        dp(img_d[i % NB], txt_d[i % NB], lab_d[i % NB], drop_seed=1000 + i)     # a fresh dropout mask every step
+    def device_step(i):      # zero_grad() is folded into the step's first kernel (MMRCA_FLAG_ZERO_GRADS)
+        dp(img_d[i % NB], txt_d[i % NB], lab_d[i % NB], drop_seed=1000 + i, zero_grad=True)     # a fresh dropout mask every step
 
     # ---- value: device-resident inputs -------------------------------------------------------------
     for i in range(W):
@@ -453,8 +452,7 @@ def run_b200(args, rank, world, local_rank):
                 sl = i % NSLOT
                 main.wait_event(ready[sl])
                 main.wait_event(done)            # the previous step's loss / logits have left the device
-                step.zero_grad()
-                dp(*slots[sl], drop_seed=5000 + i)
+                dp(*slots[sl], drop_seed=5000 + i, zero_grad=True)
                 consumed[sl].record(main)
                 with torch.cuda.stream(d2h_stream):      # results go back on their own stream, under the next step
                     d2h_stream.wait_event(consumed[sl])

@@ -27,6 +27,7 @@ FLAG_REVERSE, FLAG_FEATURES_ONLY, FLAG_CROSS_ATTENTION_ONLY = 1, 2, 4
 FLAG_FEATURE_GRADS = 256
 FLAG_TRAINING = 512
 FLAG_FEATURES_BF16 = 1024
+FLAG_ZERO_GRADS = 2048
 COMPUTE_FP32, COMPUTE_BF16, COMPUTE_BF16_FUSED = 0, 1, 2
 WS_TEXT_SA_IMAGE, WS_IMAGE_SA_IMAGE = 0, 1
 QUERY_ABI_VERSION, QUERY_DEVICE_OK, QUERY_SM_COUNT, QUERY_KERNEL_LAUNCHES, QUERY_RESET_LAUNCHES, QUERY_HAS_BF16 = range(6)

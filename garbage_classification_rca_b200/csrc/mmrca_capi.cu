@@ -222,6 +222,7 @@ struct Workspace {
   uint4* ca_row[2];                                                 // training: CA rows {keep bits, mean, rstd} per direction
   float* gm[4]; size_t gm_floats;                                   // training: dM_ext^T per block (contiguous)
   float* step_loss = nullptr;                                       // train step: prep_feat clears gm and *step_loss (no memset nodes)
+  float* zero_grads = nullptr; int zero_grads_n = 0;               // train step + MMRCA_FLAG_ZERO_GRADS: the gradient bucket to clear
   size_t bytes;
 };
 
@@ -418,6 +419,7 @@ static int launch_prep_feat(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, co
   f.drop = make_drop(d); f.batch = d.batch;
   f.feat_bf16 = (d.flags & MMRCA_FLAG_FEATURES_BF16) ? 1 : 0;
   if (w.step_loss) { a.zero0 = w.gm[0]; a.nzero0 = int(w.gm_floats); a.zero1 = w.step_loss; }
+  a.zero2 = w.zero_grads; a.nzero2 = w.zero_grads_n;
   const int prep_ctas = htc::kPrepCtas;
   const int feat_ctas = max(1, min((d.batch + 7) / 8, 2 * sms));
   {
@@ -1197,6 +1199,18 @@ int mmrca_head_train_step(const MmrcaHeadDesc* desc, const MmrcaHeadParams* para
   if (workspace_bytes < w.bytes) return fail(MMRCA_ERR_WORKSPACE, "workspace too small (training size needed)%s%s");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (desc_is_tc(*desc) && !drop_mask) w.step_loss = loss_out;
+  if (desc->flags & MMRCA_FLAG_ZERO_GRADS) {
+    // the gradient tensors are one contiguous bucket in MmrcaHeadGrads order (functional.FlatGrads): [sa_img.wq, bf + C)
+    float* lo = grads->sa_img.wq;
+    float* hi = grads->bf ? grads->bf + desc->n_classes : nullptr;
+    const long long n = lo && hi ? (long long)(hi - lo) : -1;
+    if (n <= 0 || n > (1 << 24) || (reinterpret_cast<uintptr_t>(lo) & 15))
+      return fail(MMRCA_ERR_INVALID, "MMRCA_FLAG_ZERO_GRADS needs the gradients in one contiguous, 16-byte aligned bucket in "
+                                     "MmrcaHeadGrads order (sa_img.wq first, bf last)%s%s");
+    const long long n4 = (n + 3) & ~3LL;      // the bucket is padded to 4 floats per tensor
+    if (w.step_loss) { w.zero_grads = lo; w.zero_grads_n = int(n4); }
+    else MMRCA_CUDA(cudaMemsetAsync(lo, 0, size_t(n4) * sizeof(float), st));
+  }
   if ((rc = head_forward_impl(*desc, *params, img_feat, txt_feat, drop_mask, drop_scale, logits, w, di.sms, st)))
     return rc;
   if (desc_is_tc(*desc)) {

@@ -85,6 +85,7 @@ struct PrepArgs {
   const float* wf; int D;                    // classifier [4][D]
   float* zero0; int nzero0;                  // fp32 region to clear (step accumulators)
   float* zero1;                              // one more float to clear (the loss accumulator), or null
+  float* zero2; int nzero2;                  // MMRCA_FLAG_ZERO_GRADS: the caller's contiguous gradient bucket (16-byte aligned)
 };
 
 constexpr int kPrepZTasks = (80 + 16) / 8 + (48 + 16) / 8 + 2 * (96 + 16) / 8;   // one CTA per (block, 8-column group kc)
@@ -180,6 +181,7 @@ __device__ __forceinline__ void prep_body(const PrepArgs& a, int cta, int nctas,
   // (d) accumulators
   for (int i = gtid; i < a.nzero0; i += gsz) a.zero0[i] = 0.f;
   if (gtid == 0 && a.zero1) *a.zero1 = 0.f;
+  for (int i = gtid; i < a.nzero2 / 4; i += gsz) reinterpret_cast<float4*>(a.zero2)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -385,14 +385,18 @@ class HeadTrainStep:
         self.grads.zero_()
 
     def __call__(self, img: torch.Tensor, txt: torch.Tensor, labels: torch.Tensor,
-                 drop_mask: Optional[torch.Tensor] = None, drop_scale: float = 1.0, drop_seed: int = 0):
-        """drop_seed: seed of this step's dropout mask when the step was built with drop_p > 0."""
+                 drop_mask: Optional[torch.Tensor] = None, drop_scale: float = 1.0, drop_seed: int = 0,
+                 zero_grad: bool = False):
+        """drop_seed: seed of this step's dropout mask when the step was built with drop_p > 0.
+        zero_grad: clear the gradient bucket inside the step's first kernel (== zero_grad() right before the call,
+        without the extra fill launch)."""
         self.desc.drop_seed = int(drop_seed) & (2 ** 64 - 1)
         # bf16 features (a backbone under bf16 autocast, or a host hand-off that ships half the bytes): bf16 pipeline only
         fdt = torch.bfloat16 if (img.dtype == torch.bfloat16 and txt.dtype == torch.bfloat16) else torch.float32
         if fdt == torch.bfloat16 and self.desc.compute == N.COMPUTE_FP32:
             raise TypeError("bf16 features need a step built with compute=COMPUTE_BF16")
-        self.desc.flags = (self.flags | N.FLAG_FEATURES_BF16) if fdt == torch.bfloat16 else self.flags
+        self.desc.flags = ((self.flags | N.FLAG_FEATURES_BF16) if fdt == torch.bfloat16 else self.flags) | \
+            (N.FLAG_ZERO_GRADS if zero_grad else 0)
         img, txt = _check_dev(img, "image features", fdt), _check_dev(txt, "text features", fdt)
         labels = _check_dev(labels, "labels", torch.int64)
         if img.shape != (self.desc.batch, self.desc.d_img) or txt.shape != (self.desc.batch, self.desc.d_txt):

@@ -183,8 +183,9 @@ class HeadDataParallel:
             else:
                 self.collective = "one-shot all-reduce over NVLink peer memory (mmrca_peer_allreduce_mean)"
 
-    def __call__(self, img, txt, labels, drop_mask=None, drop_scale=1.0, sync: bool = True, drop_seed: int = 0):
-        loss, logits = self.step(img, txt, labels, drop_mask, drop_scale, drop_seed)
+    def __call__(self, img, txt, labels, drop_mask=None, drop_scale=1.0, sync: bool = True, drop_seed: int = 0,
+                 zero_grad: bool = False):
+        loss, logits = self.step(img, txt, labels, drop_mask, drop_scale, drop_seed, zero_grad=zero_grad)
         if sync:   # sync=False == DDP.no_sync() while accumulating (reference steps every acc_steps batches)
             flat = self.step.grads.flat
             if self.exact_mean:

@@ -56,6 +56,10 @@ extern "C" {
                                               pointers.  What a backbone under bf16 autocast hands over; halves the bytes a
                                               host -> device hand-off ships.  Norms, the fp32 classifier terms and everything
                                               downstream are computed from the bf16 values in fp32.  bf16 pipeline only. */
+#define MMRCA_FLAG_ZERO_GRADS 2048u        /* mmrca_head_train_step only: clear the gradients first (optimizer.zero_grad() folded
+                                              into the step's first kernel).  The gradient tensors must form ONE contiguous,
+                                              16-byte aligned bucket in MmrcaHeadGrads order, sa_img.wq first, bf last, each
+                                              tensor padded to a multiple of 4 floats (what the Python layer's FlatGrads is). */
 #define MMRCA_FLAG_TRAINING 512u           /* mmrca_head_forward only: a mmrca_head_backward on the same workspace follows
                                               (autograd), so the forward keeps what the backward reloads and needs the
                                               training-size workspace.  Without it the forward is inference: nothing is

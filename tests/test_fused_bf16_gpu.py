@@ -347,3 +347,31 @@ def test_fused_train_step_bf16_features(pkg, B):
     step.zero_grad()
     _, logits32 = step(img.cuda(), txt.cuda(), labels.cuda())
     assert np.abs(logits32.cpu().numpy() - ref32["logits"]).max() < LOGITS_ABS_BF16
+
+
+def test_zero_grad_folded_into_the_step(pkg):
+    """MMRCA_FLAG_ZERO_GRADS: the step clears the contiguous gradient bucket in its first kernel - the same gradients as
+    zero_grad() followed by the step, and no accumulation across calls."""
+    from garbage_classification_rca_b200 import _native as N
+    B = 40
+    p = orc.init_head_params(seed=3, qk_gain=40.0)
+    img, txt, labels = make_inputs(B, 3)
+    names = pkg.head_param_names()
+    step = pkg.HeadTrainStep([p[n].cuda() for n in names], B, 1280, 768, reverse=True, compute=N.COMPUTE_BF16, drop_p=0.6)
+    step.zero_grad()
+    step(img.cuda(), txt.cuda(), labels.cuda(), drop_seed=4)
+    ref = step.grads.flat.clone()
+    step.grads.flat.fill_(123.0)
+    for _ in range(2):
+        step(img.cuda(), txt.cuda(), labels.cuda(), drop_seed=4, zero_grad=True)
+    torch.cuda.synchronize()
+    n = step.grads.n
+    assert (step.grads.flat[:n] - ref[:n]).abs().max().item() <= 1e-6 * max(1.0, ref[:n].abs().max().item())
+    # the fp32 kernels take the flag too (a memset node instead of the fused clear)
+    step32 = pkg.HeadTrainStep([p[n].cuda() for n in names], B, 1280, 768, reverse=True, compute=N.COMPUTE_FP32)
+    step32.zero_grad()
+    step32(img.cuda(), txt.cuda(), labels.cuda())
+    ref32 = step32.grads.flat.clone()
+    step32.grads.flat.fill_(-7.0)
+    step32(img.cuda(), txt.cuda(), labels.cuda(), zero_grad=True)
+    assert (step32.grads.flat[:n] - ref32[:n]).abs().max().item() <= 1e-6 * max(1.0, ref32[:n].abs().max().item())
