@@ -16,6 +16,7 @@
 #include "mmrca_tc_selftest.cuh"
 #include "mmrca_head_tc.cuh"
 #include "mmrca_head_tc_bwd.cuh"
+#include "mmrca_head_tc_dx.cuh"
 #include "mmrca_hier.cuh"
 #include "mmrca_peer.cuh"
 #include "mmrca_train_aux.cuh"
@@ -221,6 +222,7 @@ struct Workspace {
   float2* sa_stats[2];                                              // training: LayerNorm (mean, rstd) per context row
   uint4* ca_row[2];                                                 // training: CA rows {keep bits, mean, rstd} per direction
   float* gm[4]; size_t gm_floats;                                   // training: dM_ext^T per block (contiguous)
+  void* sa_dz[2]; void* sa_ds[2]; void* sa_dv[2];                   // training + feature gradients: dZ / dS / dV images of the SA backward
   float* step_loss = nullptr;                                       // train step: prep_feat clears gm and *step_loss (no memset nodes)
   float* zero_grads = nullptr; int zero_grads_n = 0;               // train step + MMRCA_FLAG_ZERO_GRADS: the gradient bucket to clear
   size_t bytes;
@@ -255,8 +257,9 @@ static DropSpec make_drop(const MmrcaHeadDesc& d) {
 // features, 4 classes) with frozen features; every other desc runs on the fp32 kernels (never on the CPU).  A pure
 // function of the desc: it also decides which buffers the workspace holds.
 static bool desc_is_tc(const MmrcaHeadDesc& d) {
+  // (features_only with feature gradients is two streaming kernels' worth of work: it stays on the fp32 kernels)
   return d.compute != MMRCA_COMPUTE_FP32 && d.d_img == 1280 && d.d_txt == 768 && d.n_classes == 4 &&
-         !(d.flags & MMRCA_FLAG_FEATURE_GRADS);
+         !((d.flags & MMRCA_FLAG_FEATURE_GRADS) && (d.flags & MMRCA_FLAG_FEATURES_ONLY));
 }
 
 static Workspace carve(const MmrcaHeadDesc& d, bool training, void* base) {
@@ -296,6 +299,13 @@ static Workspace carve(const MmrcaHeadDesc& d, bool training, void* base) {
       for (int i = 0; i < 2; ++i) {
         w.sa_v[i] = take(tiles * htc::kSaTileBytes / 4); w.sa_p[i] = take(tiles * (2 * htc::kPHalf) / 4);
         w.sa_stats[i] = reinterpret_cast<float2*>(take(tiles * 256));
+      }
+      if (d.flags & MMRCA_FLAG_FEATURE_GRADS) {
+        const int sdin[2] = {80, 48};
+        for (int i = 0; i < 2; ++i) {
+          w.sa_dz[i] = take(tiles * htc::op_bytes(sdin[i]) / 4); w.sa_ds[i] = take(tiles * (2 * htc::kPHalf) / 4);
+          w.sa_dv[i] = take(tiles * htc::kSaTileBytes / 4);
+        }
       }
       const int dins[4] = {80, 48, MMRCA_SA_DV, MMRCA_SA_DV};
       char* g0 = p + off;
@@ -471,8 +481,8 @@ static int head_forward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, 
 
 // ---- fused bf16 pipeline: backward --------------------------------------------------------------------------
 static int head_backward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, const float* img, const float* txt,
-                               const float* dlogits, const MmrcaHeadGrads& g, const Workspace& w, int sms,
-                               cudaStream_t st) {
+                               const float* dlogits, const MmrcaHeadGrads& g, float* d_img, float* d_txt,
+                               const Workspace& w, int sms, cudaStream_t st) {
   const int tiles = (d.batch + 7) / 8, D = concat_width(d), ca = kL * MMRCA_CA_DV;
   int rc;
   if (d.flags & MMRCA_FLAG_FEATURES_ONLY) return MMRCA_OK;      // ce_feat has done everything there is to do
@@ -510,6 +520,7 @@ static int head_backward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p,
       a.dout_a = w.dx_img[1]; a.dout_b = w.dx_img[2];
       a.gm = w.gm[0]; a.g_wv = g.sa_img.wv; a.g_bv = g.sa_img.bv; a.g_ln_g = g.sa_img.ln_g; a.g_ln_b = g.sa_img.ln_b;
       a.batch = d.batch;
+      if (d_img) { a.dz_tiles = w.sa_dz[0]; a.ds_tiles = w.sa_ds[0]; a.dv_tiles = w.sa_dv[0]; }
     }
     {
       htc::SaBwdArgs& a = both.m[1];
@@ -517,11 +528,34 @@ static int head_backward_fused(const MmrcaHeadDesc& d, const MmrcaHeadParams& p,
       a.dout_a = w.dx_img[0]; a.dout_b = w.dx_img[3];
       a.gm = w.gm[1]; a.g_wv = g.sa_txt.wv; a.g_bv = g.sa_txt.bv; a.g_ln_g = g.sa_txt.ln_g; a.g_ln_b = g.sa_txt.ln_b;
       a.batch = d.batch;
+      if (d_txt) { a.dz_tiles = w.sa_dz[1]; a.ds_tiles = w.sa_ds[1]; a.dv_tiles = w.sa_dv[1]; }
     }
     if ((rc = set_smem(htc::sa_bwd_kernel, htc::kSaBwdSmemBytes))) return rc;
     {
       LaunchScope ls("sa_bwd_bf16", st);
       htc::sa_bwd_kernel<<<dim3(min(tiles, max(1, sms / 2)), 2), htc::kCtaThreads, htc::kSaBwdSmemBytes, st>>>(both);
+    }
+    MMRCA_CUDA(cudaGetLastError());
+  }
+  if (d_img && d_txt) {      // fine-tune phase: feature gradients from the images sa_bwd just left
+    const bool co = (d.flags & MMRCA_FLAG_CROSS_ATTENTION_ONLY) != 0;
+    htc::SaDxBothArgs both;
+    memset(&both, 0, sizeof(both));
+    const float* feats[2] = {img, txt};
+    const float* norms[2] = {w.norm_img, w.norm_txt};
+    const void* xt[2] = {w.x_img, w.x_txt};
+    float* outs[2] = {d_img, d_txt};
+    const int offs[2] = {2 * kL * MMRCA_CA_DV, 2 * kL * MMRCA_CA_DV + d.d_img};
+    for (int i = 0; i < 2; ++i) {
+      htc::SaDxArgs& a = both.m[i];
+      a.x_tiles = xt[i]; a.dz_tiles = w.sa_dz[i]; a.ds_tiles = w.sa_ds[i]; a.dv_tiles = w.sa_dv[i]; a.blobs = w.fblob[i];
+      a.feat = feats[i]; a.norms = norms[i]; a.dlogits = dlogits; a.wf = co ? nullptr : p.wf; a.cls_off = offs[i]; a.D = D;
+      a.drop = make_drop(d); a.d_feat = outs[i]; a.batch = d.batch;
+    }
+    if ((rc = set_smem(htc::sa_dx_kernel, htc::kSaDxSmemBytes))) return rc;
+    {
+      LaunchScope ls("sa_dx_bf16", st);
+      htc::sa_dx_kernel<<<dim3(min(tiles, max(1, sms / 2)), 2), htc::kWgThreads, htc::kSaDxSmemBytes, st>>>(both);
     }
     MMRCA_CUDA(cudaGetLastError());
   }
@@ -628,14 +662,17 @@ static int head_backward_impl(const MmrcaHeadDesc& d, const MmrcaHeadParams& p, 
     return fail(MMRCA_ERR_INVALID, "d_img_feat and d_txt_feat must both be given or both be NULL%s%s");
   if ((rc = check_mask(d, mask))) return rc;
   if (desc_is_tc(d)) {
-    if (want_feat)
+    if (want_feat && !(d.flags & MMRCA_FLAG_FEATURE_GRADS))
       return fail(MMRCA_ERR_INVALID, "feature gradients need MMRCA_FLAG_FEATURE_GRADS in the desc of the forward AND "
-                                     "the backward (the bf16 pipeline keeps parameter gradients only)%s%s");
+                                     "the backward (it sizes the workspace)%s%s");
+    if (want_feat && (d.flags & MMRCA_FLAG_FEATURES_BF16))
+      return fail(MMRCA_ERR_INVALID, "feature gradients are taken with respect to fp32 features (MMRCA_FLAG_FEATURES_BF16 is "
+                                     "for frozen backbones)%s%s");
     // classifier bias gradient and the feature-source rows of dWf from the given dlogits (train_step has done
     // both inside its cross-entropy kernel)
     if (!ce_done && (rc = launch_ce_feat(d, nullptr, nullptr, nullptr, nullptr, const_cast<float*>(dlogits), g, g.bf != nullptr,
                                          w, st))) return rc;
-    return head_backward_fused(d, p, img, txt, dlogits, g, w, sms, st);
+    return head_backward_fused(d, p, img, txt, dlogits, g, want_feat ? d_img : nullptr, want_feat ? d_txt : nullptr, w, sms, st);
   }
   if (!mask && d.drop_p > 0.f) { mask = w.mask; scale = make_drop(d).scale; }   // materialised by the forward
   // 1. classifier: dWf, dbf, d(T_I), d(I_T) and the direct feature terms d(img_n), d(txt_n)

@@ -755,6 +755,9 @@ struct SaBwdArgs {
   float* g_wv; float* g_bv; float* g_ln_g; float* g_ln_b;
   int batch;
   long long* dbg;                 // development: per-phase clock64 stamps of CTA 0 (null in production)
+  // MMRCA_FLAG_FEATURE_GRADS (fine-tune phase): the tile's dZ, dS, dV operands are also left in HBM for sa_dx_kernel
+  // (mmrca_head_tc_dx.cuh), which turns them into feature gradients; null: not kept
+  void* dz_tiles; void* ds_tiles; void* dv_tiles;
 };
 template <int DIN_>
 struct SaBwdSmem {
@@ -920,7 +923,8 @@ __device__ __forceinline__ void sa_bwd_body(const SaBwdArgs& a, uint8_t* sm) {
         }
       }
       part[c.w * 128 + c.rs] = make_float2(m1a + m1b, m2a + m2b);
-      __syncthreads();
+      if (tid == 96 && a.dz_tiles) bulk_wait_read();      // the previous tile's exported dZ / dS / dV have left shared memory
+      __syncthreads();                                    // (every write to their buffers comes after this barrier)
       const float2 other = part[(c.w ^ 1) * 128 + c.rs];
       const float m1 = (m1a + m1b + other.x) * (1.0f / float(DV)), m2 = (m2a + m2b + other.y) * (1.0f / float(DV));
 #pragma unroll
@@ -985,6 +989,12 @@ __device__ __forceinline__ void sa_bwd_body(const SaBwdArgs& a, uint8_t* sm) {
     MMRCA_STAMP(10);
     cta_sync_for_mma();
     MMRCA_STAMP(11);
+    if (tid == 96 && a.dz_tiles) {      // fine-tune phase: dZ, dS, dV also go to HBM (bulk stores, read asynchronously)
+      bulk_s2g(static_cast<uint8_t*>(a.dz_tiles) + size_t(tile) * op_bytes(DIN), dyx, op_bytes(DIN));
+      bulk_s2g(static_cast<uint8_t*>(a.ds_tiles) + size_t(tile) * (2 * kPHalf), dls, 2 * kPHalf);
+      bulk_s2g(static_cast<uint8_t*>(a.dv_tiles) + size_t(tile) * op_bytes(96), dcb, op_bytes(96));
+      bulk_commit();
+    }
     if (tid == 0) {       // G3: nobody waits for these before the next tile is under way
       mma_steps(tmem + T::G_M, make_smem_desc(smem_u32(xb), kRS, kCS), 2 * kRS, make_smem_desc(smem_u32(dyx), kRS, kCS), 2 * kRS,
                 make_idesc_bf16(128, DIN, 1, 1), 8, !first);
@@ -995,6 +1005,7 @@ __device__ __forceinline__ void sa_bwd_body(const SaBwdArgs& a, uint8_t* sm) {
     first = false;
   }
   MMRCA_STAMP(0);
+  if (tid == 96 && a.dz_tiles) bulk_wait_all();      // the exported images are complete before the CTA retires
   if (!first) {
     mbar_wait_ph(&bars[5], ph_g3);
     flush_acc(c, T::G_M, DIN, DIN + 1, [&](int m, int n) { return a.gm + size_t(n) * 128 + m; });
