@@ -69,12 +69,13 @@ extern "C" {
 /* MmrcaHeadDesc.compute */
 #define MMRCA_COMPUTE_FP32 0 /* fp32 SIMT kernels: the 1e-4-relative contract */
 #define MMRCA_COMPUTE_BF16 1 /* bf16 tcgen05 tensor-core pipeline, fp32 accumulate: the 2e-2-absolute contract.
-                                Covers the reference's literal shapes (1280 / 768 features, 4 classes) with frozen
-                                features and seeded dropout (MmrcaHeadDesc.drop_p / drop_seed); feature gradients and
-                                other widths run the fp32 kernels (the workspace is laid out accordingly: it is a
-                                function of the desc alone); a caller-supplied drop_mask is an error in this mode
-                                (pass MMRCA_COMPUTE_FP32); features_only is two streaming kernels (normalise + fp32
-                                classifier, then cross-entropy + dWf). */
+                                Covers the reference's literal shapes (1280 / 768 features, 4 classes) with seeded
+                                dropout (MmrcaHeadDesc.drop_p / drop_seed), frozen features or feature gradients
+                                (MMRCA_FLAG_FEATURE_GRADS); other widths (and features_only with feature gradients) run
+                                the fp32 kernels (the workspace is laid out accordingly: it is a function of the desc
+                                alone); a caller-supplied drop_mask is an error in this mode (pass MMRCA_COMPUTE_FP32);
+                                features_only is two streaming kernels (normalise + fp32 classifier, then
+                                cross-entropy + dWf). */
 #define MMRCA_COMPUTE_BF16_FUSED 2 /* alias of MMRCA_COMPUTE_BF16 (kept for ABI v1 callers) */
 
 /* mmrca_query() selectors */
