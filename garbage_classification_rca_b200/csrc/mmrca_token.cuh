@@ -1,7 +1,7 @@
 // Token-level attention blocks (BASELINE.json configs[4]: ViT-L/16's 197 patch tokens x 1024, RoBERTa's 256 tokens x 768):
 // SelfAttention (CVPR_code/multimodal_model.py:39-68) and ReverseCrossAttention (:71-108) for square L <= 256 on real
 // token sequences [B, L, K] instead of the 16 pseudo-tokens of the pooled vector.  The reference classes are shape-generic
-// (Linear on the last dimension, batched matmul, square-attention assert :93), so they are the oracle for these shapes.
+// (Linear on the last dimension, batched matmul, square-attention assert :93), so they define these shapes too (the parity tests check against them).
 //
 //   tok_proj   Q | K | V = X [W_query | W_key | W_value]^T + b : the one place on this path where the projection is a real
 //              GEMM (K = 1024 / 768, N = 352).  Warp-specialised tcgen05 pipeline: one TMA producer thread
