@@ -538,6 +538,21 @@ def run_b200(args, rank, world, local_rank):
         for k in hbm_bytes if k in share}
     if coll is not None:
         out["collective_check"] = coll
+    if world == 1 and compute == N.COMPUTE_BF16 and args.variant == "rca":
+        # the fp32 SIMT kernels (the 1e-4 / per-tensor 1e-2 contract; feature gradients at fp32 accuracy) on the same
+        # workload, a few steps: they are the other product path, and nobody should have to guess their speed
+        step32 = g.HeadTrainStep(params, B, D_IMG, D_TXT, reverse=True, compute=N.COMPUTE_FP32, drop_p=args.dropout)
+        for i in range(2):
+            step32(img_d[i % NB], txt_d[i % NB], lab_d[i % NB], drop_seed=i, zero_grad=True)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(5):
+            step32(img_d[i % NB], txt_d[i % NB], lab_d[i % NB], drop_seed=10 + i, zero_grad=True)
+        f1.record()
+        torch.cuda.synchronize()
+        out["fp32_kernels"] = {"value": 5 * B / (f0.elapsed_time(f1) * 1e-3), "unit": "samples/s",
+                               "ms_per_step": f0.elapsed_time(f1) / 5, "what": "MMRCA_COMPUTE_FP32 (SIMT) train step, same workload, 5 steps"}
     if world == 1 and not args.no_cpu_baseline:
         out["gpu_eager_baseline"] = gpu_eager_baseline(B, args.dropout, K, W, dev)
         out["cpu_baseline"] = cpu_baseline(B, args.dropout)

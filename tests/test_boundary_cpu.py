@@ -226,3 +226,21 @@ def test_run_one_epoch_reference_semantics():
     assert n_batches == 5 and len(losses) == 5
     assert all(abs(float(a) - float(b)) < 1e-6 for a, b in zip(losses, rl))
     assert all(torch.allclose(a, b, atol=1e-7) for a, b in zip(m.state_dict().values(), ref.state_dict().values()))
+
+
+def test_build_model_dispatches_the_rebuilt_late_fusion_variants():
+    """--late_fusion dispatch (reference main_both.py:272-343): MM_RCA, hierarchical, classic, normalized are rebuilt;
+    the others exit like an unknown strategy would."""
+    from garbage_classification_rca_b200 import multimodal_model as M
+    from garbage_classification_rca_b200.options import args_parser
+    from garbage_classification_rca_b200.training import build_model
+    want = {"MM_RCA": M.MM_RCA, "hierarchical": M.Hierarchical, "classic": M.EffV2MediumAndDistilbertClassic,
+            "normalized": M.EffV2MediumAndDistilbertNormalized}
+    for name, cls in want.items():
+        a = args_parser([f"--late_fusion={name}", "--text_model=distilbert"])
+        with redirect_stdout(io.StringIO()):
+            m = build_model(a, pretrained=False)
+        assert type(m) is cls
+        assert len(m.state_dict()) > 1000        # the shared base's full state_dict, whatever the variant
+    with pytest.raises(SystemExit):
+        build_model(args_parser(["--late_fusion=clip"]), pretrained=False)
