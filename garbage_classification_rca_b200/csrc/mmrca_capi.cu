@@ -892,7 +892,8 @@ static TokenWorkspace token_carve(const MmrcaTokenDesc& d, void* base) {
   size_t off = 0;
   auto take = [&](size_t bytes) { void* r = p ? p + off : nullptr; off += align_up_256(bytes); return r; };
   const size_t B = size_t(d.batch > 0 ? d.batch : 0), tps = size_t(d.seq_len + tok::kTile - 1) / tok::kTile;
-  w.w = static_cast<__nv_bfloat16*>(take((size_t(d.d_kq) * d.d_in_q + size_t(d.d_kq + d.d_v) * d.d_in_kv) * 2));
+  const size_t kq_pad = size_t(d.d_in_q + tok::kBK - 1) / tok::kBK * tok::kBK, kkv_pad = size_t(d.d_in_kv + tok::kBK - 1) / tok::kBK * tok::kBK;
+  w.w = static_cast<__nv_bfloat16*>(take((size_t(d.d_kq) * kq_pad + size_t(d.d_kq + d.d_v) * kkv_pad) * 2));
   w.bias = static_cast<float*>(take(size_t(2 * d.d_kq + d.d_v) * 4));
   w.q_img = take(B * tps * htc::op_bytes(d.d_kq));
   w.k_img = take(B * tps * htc::op_bytes(d.d_kq));
@@ -919,11 +920,22 @@ static int launch_cast(const float* src, __nv_bfloat16* dst, long long n, int sm
   return MMRCA_OK;
 }
 // one projection GEMM: x [B][L][K] bf16, w [N][K] bf16 (rows: the segments back to back), bias [N]
+static int launch_tok_wprep(const float* w, int n_rows, int K, int N, int n0, void* blob, int sms, cudaStream_t st) {
+  const long long chunks = (long long)((K + tok::kBK - 1) / tok::kBK) * n_rows * 8;
+  {
+    LaunchScope ls("tok_wprep", st);
+    tok::tok_wprep_kernel<<<int(std::min<long long>((chunks + 255) / 256, 4LL * sms)), 256, 0, st>>>(w, n_rows, K, N, n0,
+                                                                                                       static_cast<uint8_t*>(blob));
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
 static int launch_tok_proj(const MmrcaTokenDesc& d, const void* x, int K, const __nv_bfloat16* w, const float* bias, int N,
                            const tok::ProjSeg (&segs)[3], int sms, cudaStream_t st) {
   int rc;
   tok::ProjArgs a;
   memset(&a, 0, sizeof(a));
+  a.wblob = reinterpret_cast<const uint8_t*>(w);
   for (int i = 0; i < 3; ++i) a.seg[i] = segs[i];
   a.bias = bias; a.N = N; a.K = K;
   a.nacc = N > 256 ? 2 : 1; a.bn = N / a.nacc;
@@ -932,7 +944,7 @@ static int launch_tok_proj(const MmrcaTokenDesc& d, const void* x, int K, const 
   a.L = d.seq_len; a.rows = d.batch * d.seq_len;
   CUtensorMap tx, tw;
   if ((rc = make_tensor_map(&tx, x, uint64_t(K), uint64_t(a.rows), 1, tok::kTile, 2))) return rc;
-  if ((rc = make_tensor_map(&tw, w, uint64_t(K), uint64_t(N), 1, uint32_t(a.bn), 2))) return rc;
+  tw = tx;      // (the weights arrive as pre-swizzled images through the bulk-copy engine: no second tensor map)
   const size_t smem = tok::kStages * size_t(tok::proj_stage_bytes(N)) + 128 + size_t(N) * 4 + 1024;
   if ((rc = set_smem(tok::tok_proj_kernel, smem))) return rc;
   {
@@ -1282,14 +1294,23 @@ int mmrca_token_attention_forward(const MmrcaTokenDesc* desc, const MmrcaAttnPar
   if (desc->batch == 0) return MMRCA_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int dkq = desc->d_kq, dv = desc->d_v, kq = desc->d_in_q, kkv = desc->d_in_kv;
-  // stacked bf16 weights and fp32 biases: [W_query ; W_key ; W_value]
+  // bf16 weight images ([k-block][N][128 B swizzled], tok_wprep_kernel) and stacked fp32 biases.  Self attention: one
+  // image of the stacked [W_query; W_key; W_value] (N = 2 d_kq + d_v); cross: one of W_query (x_q's width), one of
+  // [W_key; W_value] (x_kv's width).
+  const size_t kq_pad = size_t(kq + tok::kBK - 1) / tok::kBK * tok::kBK;
   __nv_bfloat16* wq = w.w;
-  __nv_bfloat16* wk = wq + size_t(dkq) * kq;
-  __nv_bfloat16* wv = wk + size_t(dkq) * kkv;
+  __nv_bfloat16* wk = wq + size_t(dkq) * kq_pad;      // cross: the second image starts here
   if (!(desc->flags & MMRCA_TOKEN_WEIGHTS_READY)) {
-    if ((rc = launch_cast(p->wq, wq, (long long)dkq * kq, di.sms, st))) return rc;
-    if ((rc = launch_cast(p->wk, wk, (long long)dkq * kkv, di.sms, st))) return rc;
-    if ((rc = launch_cast(p->wv, wv, (long long)dv * kkv, di.sms, st))) return rc;
+    if (self) {
+      const int N = 2 * dkq + dv;
+      if ((rc = launch_tok_wprep(p->wq, dkq, kq, N, 0, wq, di.sms, st))) return rc;
+      if ((rc = launch_tok_wprep(p->wk, dkq, kq, N, dkq, wq, di.sms, st))) return rc;
+      if ((rc = launch_tok_wprep(p->wv, dv, kq, N, 2 * dkq, wq, di.sms, st))) return rc;
+    } else {
+      if ((rc = launch_tok_wprep(p->wq, dkq, kq, dkq, 0, wq, di.sms, st))) return rc;
+      if ((rc = launch_tok_wprep(p->wk, dkq, kkv, dkq + dv, 0, wk, di.sms, st))) return rc;
+      if ((rc = launch_tok_wprep(p->wv, dv, kkv, dkq + dv, dkq, wk, di.sms, st))) return rc;
+    }
     MMRCA_CUDA(cudaMemcpyAsync(w.bias, p->bq, size_t(dkq) * 4, cudaMemcpyDeviceToDevice, st));
     MMRCA_CUDA(cudaMemcpyAsync(w.bias + dkq, p->bk, size_t(dkq) * 4, cudaMemcpyDeviceToDevice, st));
     MMRCA_CUDA(cudaMemcpyAsync(w.bias + 2 * dkq, p->bv, size_t(dv) * 4, cudaMemcpyDeviceToDevice, st));

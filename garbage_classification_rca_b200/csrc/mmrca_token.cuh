@@ -33,7 +33,7 @@ constexpr int kTile = 128;            // tokens per tile
 constexpr int kMaxTiles = 2;          // L <= 256
 constexpr int kBK = 64;               // K per pipeline stage: one 128-byte swizzle span of bf16
 constexpr int kStages = 3;
-constexpr int kProjThreads = 192;
+constexpr int kProjThreads = 64 + 256;      // producer warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
 
 // ---- TMA tensor-map loads, 128B-swizzled shared-memory descriptors ------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
@@ -66,6 +66,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
 // ---- projection GEMM -------------------------------------------------------------------------------------------------------
 struct ProjSeg { void* img; int cols; float scale; };     // output columns [start, start + cols) -> image; values * scale
 struct ProjArgs {
+  const uint8_t* wblob;     // pre-swizzled weight images [k-block][N][128 B] (tok_wprep_kernel)
   ProjSeg seg[3];           // Q | K | V (cols == 0: absent)
   const float* bias;        // [N]
   int N, bn, nacc;          // N = bn * nacc total columns, bn <= 256 per accumulator
@@ -118,8 +119,7 @@ __global__ void __launch_bounds__(kProjThreads, 1) tok_proj_kernel(const __grid_
           mbar_arrive_expect_tx(&full[s], stage);
           uint8_t* sa = sm + s * stage;
           tma_load_2d(sa, &tm_x, it * kBK, tile * kTile, &full[s]);
-          for (int j = 0; j < a.nacc; ++j)
-            tma_load_2d(sa + a_bytes + uint32_t(j) * uint32_t(a.bn) * kBK * 2, &tm_w, it * kBK, j * a.bn, &full[s]);
+          bulk_g2s(sa + a_bytes, a.wblob + size_t(it) * b_bytes, b_bytes, &full[s]);      // the whole [N x 64] weight slab
         }
       }
     }
@@ -148,44 +148,61 @@ __global__ void __launch_bounds__(kProjThreads, 1) tok_proj_kernel(const __grid_
       }
     }
   } else {
-    const int q = warp & 3;
+    // ---- epilogue: 8 warps; warp w reads TMEM lanes 32 (w % 4) .. + 31 (its row of the tile) and every other 32-column
+    //      chunk (half = (w - 2) / 4).  Measured on the first version (4 warps, per-chunk address arithmetic, segment
+    //      table indexed dynamically): 9.5 us of fixed cost per 128-row tile against 13.7 us of main loop at K = 1024.
+    const int q = warp & 3, half = (warp - 2) >> 2;
     int ti = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++ti) {
       const int r_flat = tile * kTile + 32 * q + lane;
       const bool live = r_flat < a.rows;
       const int b = live ? r_flat / a.L : 0, t = r_flat - b * a.L, mt = t >> 7, row = t & 127;
+      const size_t tile_idx = size_t(b) * a.tiles_per_sample + mt;
+      const uint32_t roff = row_off(row);
       mbar_wait(accb, uint32_t(ti) & 1u);
       tc_fence_after_sync();
-      int seg = 0, seg0 = 0;
-#pragma unroll 1
-      for (int n0 = 0; n0 < a.N; n0 += 32) {
-        uint32_t r0[16], r1[16];
-        const bool two = n0 + 16 < a.N;
-        tmem_ld16_nw(tmem + (uint32_t(32 * q) << 16) + uint32_t(n0), r0);
-        if (two) tmem_ld16_nw(tmem + (uint32_t(32 * q) << 16) + uint32_t(n0 + 16), r1);
-        tmem_wait_ld();
+      int n0 = 0, chunk = 0;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (h == 1 && !two) break;
-          const int nn = n0 + 16 * h;
-          while (nn >= seg0 + a.seg[seg].cols) { seg0 += a.seg[seg].cols; ++seg; }
-          const float sc = a.seg[seg].scale;
+      for (int sgi = 0; sgi < 3; ++sgi) {
+        const ProjSeg sg = a.seg[sgi];                       // static index: stays in registers / constant bank
+        if (sg.cols == 0) continue;
+        uint8_t* img = static_cast<uint8_t*>(sg.img) + tile_idx * (size_t(sg.cols >> 3) * kCS) + roff;
+        const float sc = sg.scale;
+#pragma unroll 1
+        for (int c = 0; c < sg.cols; c += 32, ++chunk) {
+          if ((chunk & 1) != half) continue;
+          const bool two = c + 16 < sg.cols;
+          uint32_t r0[16], r1[16];
+          tmem_ld16_nw(tmem + (uint32_t(32 * q) << 16) + uint32_t(n0 + c), r0);
+          if (two) tmem_ld16_nw(tmem + (uint32_t(32 * q) << 16) + uint32_t(n0 + c + 16), r1);
+          tmem_wait_ld();
+          const float* bs = bias_s + n0 + c;
           float v[16];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = (__uint_as_float(h ? r1[e] : r0[e]) + bias_s[nn + e]) * sc;
-          const int c = nn - seg0, groups = a.seg[seg].cols / 8;
-          uint8_t* img = static_cast<uint8_t*>(a.seg[seg].img) + (size_t(b) * a.tiles_per_sample + mt) * (size_t(groups) * kCS);
+          for (int e = 0; e < 16; ++e) v[e] = (__uint_as_float(r0[e]) + bs[e]) * sc;
           const float lo[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
           const float hi[8] = {v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]};
+          uint8_t* dst = img + uint32_t(c >> 3) * kCS;
           if (live) {
-            *reinterpret_cast<uint4*>(img + uint32_t(c >> 3) * kCS + row_off(row)) = pack_bf16x8(lo);
-            *reinterpret_cast<uint4*>(img + uint32_t((c >> 3) + 1) * kCS + row_off(row)) = pack_bf16x8(hi);
+            *reinterpret_cast<uint4*>(dst) = pack_bf16x8(lo);
+            *reinterpret_cast<uint4*>(dst + kCS) = pack_bf16x8(hi);
+          }
+          if (two) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = (__uint_as_float(r1[e]) + bs[16 + e]) * sc;
+            const float lo2[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
+            const float hi2[8] = {v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]};
+            if (live) {
+              *reinterpret_cast<uint4*>(dst + 2 * kCS) = pack_bf16x8(lo2);
+              *reinterpret_cast<uint4*>(dst + 3 * kCS) = pack_bf16x8(hi2);
+            }
           }
         }
+        n0 += sg.cols;
       }
       // the accumulators are drained: hand TMEM back to the MMA thread
       tc_fence_before_sync();
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       if (tid == 64) mbar_arrive(tmem_empty);
     }
   }
@@ -203,6 +220,27 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
     } else {
       for (long long j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
     }
+  }
+}
+
+// W [n_rows][K] fp32 (rows n0 .. n0 + n_rows of the stacked [W_query; W_key; W_value]) -> bf16 blob laid out as the
+// shared-memory IMAGE the projection's B operand wants: [k-block of 64][N rows][128 bytes, 16-byte chunks XOR-swizzled
+// by (row % 8)] - what a {64, N} SWIZZLE_128B tensor-map box would land - so that a stage's whole weight slab is ONE
+// contiguous bulk copy instead of N row requests through the tiled-TMA path.  Columns beyond K are zero.
+__global__ void __launch_bounds__(256) tok_wprep_kernel(const float* __restrict__ w, int n_rows, int K, int N, int n0,
+                                                        uint8_t* __restrict__ blob) {
+  const int kblocks = (K + kBK - 1) / kBK;
+  const long long chunks = (long long)kblocks * n_rows * 8;      // 16-byte chunks
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < chunks; i += (long long)gridDim.x * 256) {
+    const int ch = int(i & 7);
+    const long long t = i >> 3;
+    const int n = int(t % n_rows), kb = int(t / n_rows);
+    const int k0 = kb * kBK + ch * 8;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = k0 + e < K ? __ldg(w + (size_t)n * K + k0 + e) : 0.f;
+    const int row = n0 + n;
+    *reinterpret_cast<uint4*>(blob + ((size_t)kb * N + row) * 128 + uint32_t((ch ^ (row & 7)) * 16)) = pack_bf16x8(v);
   }
 }
 
