@@ -961,7 +961,7 @@ static int launch_tok_attn(const MmrcaTokenDesc& d, const tok::AttnArgs& a, cuda
   if ((rc = set_smem(tok::tok_attn_kernel<DKQ, DV>, S::BYTES))) return rc;
   {
     LaunchScope ls(DKQ == 128 ? "tok_attn<128,96>" : "tok_attn<64,48>", st);
-    tok::tok_attn_kernel<DKQ, DV><<<d.batch * a.tiles_per_sample, 128, S::BYTES, st>>>(a);
+    tok::tok_attn_kernel<DKQ, DV><<<d.batch * a.tiles_per_sample, 256, S::BYTES, st>>>(a);
   }
   MMRCA_CUDA(cudaGetLastError());
   return MMRCA_OK;

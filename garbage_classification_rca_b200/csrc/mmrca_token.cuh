@@ -258,21 +258,33 @@ struct AttnSmem {
   static constexpr uint32_t Q = 0;
   static constexpr uint32_t K = htc::al128(Q + QB);                     // kMaxTiles key tiles
   static constexpr uint32_t V = htc::al128(K + kMaxTiles * QB);         // kMaxTiles value tiles
-  static constexpr uint32_t P = htc::al128(V + kMaxTiles * VB);         // [128 x 256] attention weights
-  static constexpr uint32_t LN = htc::al128(P + PB);
-  static constexpr uint32_t BAR = htc::al128(LN + 2 * DV * 4);
+  static constexpr uint32_t P = htc::al128(V + kMaxTiles * VB);         // [128 x 256] unnormalised attention weights
+  static constexpr uint32_t LN = htc::al128(P + PB);                    // gamma, beta
+  static constexpr uint32_t VSUM = LN + 2 * DV * 4;                     // column sums of V over the valid keys (reverse weights)
+  static constexpr uint32_t PART = VSUM + DV * 4;                       // [2 halves][128 rows] float2 exchange
+  static constexpr uint32_t BAR = htc::al128(PART + 2 * kTile * 8);
   static constexpr uint32_t BYTES = BAR + 64;
   static_assert(BYTES <= 232448, "token attention does not fit shared memory");
 };
 
+// 256 threads: two threads per query row (warp w reads TMEM lanes 32 (w % 4) .., half = w / 4 takes every other 16-column
+// chunk).  Per-thread TMEM reads are software-pipelined (the next chunk is in flight while the current one is used): with
+// one thread per row and a wait after every load the kernel spent most of its time on TMEM-load latency.
+// Two passes over the scores: (1) row maximum, (2) p = exp(s - max) written UNNORMALISED as the bf16 P operand while its row
+// sum accumulates; the 1 / sum lands on the context row after P V.  The reverse weights (1 - A) / (L - 1) (:95-99) follow
+// from the same unnormalised product: ((1 - A) V)[c] = colsum(V)[c] - (P_un V)[c] / sum, with colsum(V) over the sample's
+// L valid keys computed once per CTA.
 template <int DKQ, int DV>
-__global__ void __launch_bounds__(128, 1) tok_attn_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(256, 1) tok_attn_kernel(const AttnArgs a) {
   extern __shared__ __align__(128) uint8_t sm[];
   using S = AttnSmem<DKQ, DV>;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::BAR);      // [0] loads, [1] MMAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
   float* ln_s = reinterpret_cast<float*>(sm + S::LN);
+  float* vsum = reinterpret_cast<float*>(sm + S::VSUM);
+  float2* part = reinterpret_cast<float2*>(sm + S::PART);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, half = warp >> 2, row = 32 * q + lane;
   const int tps = a.tiles_per_sample;
   const int b = blockIdx.x / tps, mt = blockIdx.x - b * tps;
   uint8_t *sq = sm + S::Q, *sk = sm + S::K, *sv = sm + S::V, *sp = sm + S::P;
@@ -288,26 +300,16 @@ __global__ void __launch_bounds__(128, 1) tok_attn_kernel(const AttnArgs a) {
     }
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
-  for (int i = tid; i < DV; i += 128) { ln_s[i] = a.ln_g[i]; ln_s[DV + i] = a.ln_b[i]; }
+  for (int i = tid; i < DV; i += 256) { ln_s[i] = a.ln_g[i]; ln_s[DV + i] = a.ln_b[i]; }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_base = uint32_t(32 * warp) << 16;
+  const uint32_t lane_base = uint32_t(32 * q) << 16;
   constexpr uint32_t COL_S = 0, COL_C = 256;
+  const int L = a.L, ncols = tps * kTile;
   mbar_wait(&bars[0], 0);
   tc_fence_after_sync();
-  // The images' rows beyond the sample's L tokens were never written by the projection: key rows there only feed masked
-  // score columns, query rows only feed output rows that are not stored, but VALUE rows meet P = 0 in the P V product
-  // and must be finite: zero them here (made visible to the tensor core by the fence that follows the softmax).
-  {
-    const int pad0 = a.L - (tps - 1) * kTile;           // first pad row of the last value tile
-    uint8_t* vlast = sv + (tps - 1) * S::VB;
-    for (int i = tid; i < (kTile - pad0) * (DV / 8); i += 128) {
-      const int r = pad0 + i / (DV / 8), g = i % (DV / 8);
-      *reinterpret_cast<uint4*>(vlast + uint32_t(g) * kCS + row_off(r)) = make_uint4(0u, 0u, 0u, 0u);
-    }
-  }
   // ---- S = Q K^T (Q carries the 1/sqrt(d_kq) factor): one N = 128 chain per key tile ------------------------------------
   if (tid == 0) {
     for (int j = 0; j < tps; ++j)
@@ -315,40 +317,78 @@ __global__ void __launch_bounds__(128, 1) tok_attn_kernel(const AttnArgs a) {
                      make_smem_desc(smem_u32(sk + j * S::QB), kCS, kRS), 2 * kCS, make_idesc_bf16(128, 128, 0, 0), DKQ / 16, false);
     umma_commit(&bars[1]);
   }
+  // while the scores are computed: the value rows beyond the sample's L tokens were never written by the projection
+  // and meet P = 0 in the P V product, so they must be finite: zero them; and colsum(V) over the valid keys
+  {
+    const int pad0 = L - (tps - 1) * kTile;           // first pad row of the last value tile
+    uint8_t* vlast = sv + (tps - 1) * S::VB;
+    for (int i = tid; i < (kTile - pad0) * (DV / 8); i += 256) {
+      const int r = pad0 + i / (DV / 8), g = i % (DV / 8);
+      *reinterpret_cast<uint4*>(vlast + uint32_t(g) * kCS + row_off(r)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (a.reverse && tid < DV) {
+      float acc0 = 0.f, acc1 = 0.f;
+      for (int j = 0; j < L; j += 2) {
+        const uint8_t* v0 = sv + (j >> 7) * S::VB + uint32_t(tid >> 3) * kCS + row_off(j & 127) + (tid & 7) * 2;
+        acc0 += __uint_as_float(uint32_t(*reinterpret_cast<const uint16_t*>(v0)) << 16);
+        if (j + 1 < L) {
+          const uint8_t* v1 = sv + ((j + 1) >> 7) * S::VB + uint32_t(tid >> 3) * kCS + row_off((j + 1) & 127) + (tid & 7) * 2;
+          acc1 += __uint_as_float(uint32_t(*reinterpret_cast<const uint16_t*>(v1)) << 16);
+        }
+      }
+      vsum[tid] = acc0 + acc1;
+    }
+  }
   mbar_wait(&bars[1], 0);
   tc_fence_after_sync();
-  // ---- softmax over the L valid keys of my query row (multimodal_model.py:58-60, :89-98) ----------------------------------
-  const int row = tid, ncols = tps * kTile;
-  const int L = a.L;
+  // ---- softmax statistics of my query row (multimodal_model.py:58-60, :89-91); my chunks: 16-column chunks of parity `half`
+  const uint32_t ts = tmem + lane_base + COL_S;
+  const int nchunks = ncols / 16;
   float m = -INFINITY;
-  for (int c0 = 0; c0 < ncols; c0 += 16) {
-    float s[16];
-    htc::ld16f(tmem + lane_base + COL_S + c0, s);
+  {
+    uint32_t nx[16];
+    tmem_ld16_nw(ts + 16 * half, nx);
+#pragma unroll 1
+    for (int ch = half; ch < nchunks; ch += 2) {
+      tmem_wait_ld();
+      float s[16];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) if (c0 + e < L) m = fmaxf(m, s[e]);
-  }
-  float sum = 0.f;
-  for (int c0 = 0; c0 < ncols; c0 += 16) {
-    float s[16];
-    htc::ld16f(tmem + lane_base + COL_S + c0, s);
+      for (int e = 0; e < 16; ++e) s[e] = __uint_as_float(nx[e]);
+      if (ch + 2 < nchunks) tmem_ld16_nw(ts + 16 * (ch + 2), nx);
+      const int c0 = 16 * ch;
 #pragma unroll
-    for (int e = 0; e < 16; ++e) if (c0 + e < L) sum += __expf(s[e] - m);
-  }
-  const float inv = 1.0f / sum, rinv = 1.0f / float(L - 1);
-  for (int c0 = 0; c0 < ncols; c0 += 16) {
-    float s[16], p[16];
-    htc::ld16f(tmem + lane_base + COL_S + c0, s);
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      const float w = __expf(s[e] - m) * inv;
-      p[e] = c0 + e < L ? (a.reverse ? (1.0f - w) * rinv : w) : 0.f;
+      for (int e = 0; e < 16; ++e) if (c0 + e < L) m = fmaxf(m, s[e]);
     }
-    htc::st_chunks16(sp, row, c0, p);
   }
+  part[half * kTile + row].x = m;
+  __syncthreads();
+  m = fmaxf(m, part[(half ^ 1) * kTile + row].x);
+  float sum = 0.f;
+  {
+    uint32_t nx[16];
+    tmem_ld16_nw(ts + 16 * half, nx);
+#pragma unroll 1
+    for (int ch = half; ch < nchunks; ch += 2) {
+      tmem_wait_ld();
+      float p[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) p[e] = __uint_as_float(nx[e]);
+      if (ch + 2 < nchunks) tmem_ld16_nw(ts + 16 * (ch + 2), nx);
+      const int c0 = 16 * ch;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        p[e] = c0 + e < L ? __expf(p[e] - m) : 0.f;
+        sum += p[e];
+      }
+      htc::st_chunks16(sp, row, c0, p);
+    }
+  }
+  part[half * kTile + row].y = sum;
   fence_proxy_async();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
+  sum += part[(half ^ 1) * kTile + row].y;
   // ---- C = P V: A = P (K-major over the keys), B = V tiles read MN-major -----------------------------------------------------
   if (tid == 0) {
     for (int j = 0; j < tps; ++j)
@@ -358,34 +398,45 @@ __global__ void __launch_bounds__(128, 1) tok_attn_kernel(const AttnArgs a) {
   }
   mbar_wait(&bars[1], 1);
   tc_fence_after_sync();
-  // ---- LayerNorm + ReLU (:65-66, :105-106) ------------------------------------------------------------------------------------
+  // ---- context row -> LayerNorm + ReLU (:65-66, :105-106); my columns: [half * DV / 2, + DV / 2) -----------------------------
   {
+    constexpr int HC = DV / 2;                       // 48 or 24
+    const float inv = 1.0f / sum, rinv = 1.0f / float(L - 1);
+    float x[HC];
+    {
+      uint32_t raw[HC];
+      const uint32_t tc_ = tmem + lane_base + COL_C + HC * half;
+#pragma unroll
+      for (int j = 0; j < HC / 8; ++j) tmem_ld8_nw(tc_ + 8 * j, *reinterpret_cast<uint32_t(*)[8]>(&raw[8 * j]));
+      tmem_wait_ld();
+#pragma unroll
+      for (int e = 0; e < HC; ++e) {
+        const float cun = __uint_as_float(raw[e]) * inv;
+        x[e] = a.reverse ? (vsum[HC * half + e] - cun) * rinv : cun;
+      }
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int c0 = 0; c0 < DV; c0 += 16) {
-      float x[16];
-      htc::ld16f(tmem + lane_base + COL_C + c0, x);
-#pragma unroll
-      for (int e = 0; e < 16; ++e) { s1 += x[e]; s2 = fmaf(x[e], x[e], s2); }
-    }
-    const float mean = s1 * (1.0f / float(DV));
-    const float rstd = rsqrtf(fmaxf(s2 * (1.0f / float(DV)) - mean * mean, 0.f) + kLnEps);
+    for (int e = 0; e < HC; ++e) { s1 += x[e]; s2 = fmaf(x[e], x[e], s2); }
+    __syncthreads();                                  // (the softmax exchange above has been read by everyone)
+    part[half * kTile + row] = make_float2(s1, s2);
+    __syncthreads();
+    const float2 o = part[(half ^ 1) * kTile + row];
+    const float mean = (s1 + o.x) * (1.0f / float(DV));
+    const float rstd = rsqrtf(fmaxf((s2 + o.y) * (1.0f / float(DV)) - mean * mean, 0.f) + kLnEps);
     const int t = mt * kTile + row;
-    float* dst = a.out + (size_t(b) * L + t) * DV;
+    if (t < L) {
+      float* dst = a.out + (size_t(b) * L + t) * DV + HC * half;
+      const float* gam = ln_s + HC * half;
+      const float* bet = ln_s + DV + HC * half;
 #pragma unroll
-    for (int c0 = 0; c0 < DV; c0 += 16) {
-      float x[16];
-      htc::ld16f(tmem + lane_base + COL_C + c0, x);
-      if (t < L) {
-#pragma unroll
-        for (int e = 0; e < 16; e += 4) {
-          float4 o;
-          o.x = fmaxf(fmaf((x[e] - mean) * rstd, ln_s[c0 + e], ln_s[DV + c0 + e]), 0.f);
-          o.y = fmaxf(fmaf((x[e + 1] - mean) * rstd, ln_s[c0 + e + 1], ln_s[DV + c0 + e + 1]), 0.f);
-          o.z = fmaxf(fmaf((x[e + 2] - mean) * rstd, ln_s[c0 + e + 2], ln_s[DV + c0 + e + 2]), 0.f);
-          o.w = fmaxf(fmaf((x[e + 3] - mean) * rstd, ln_s[c0 + e + 3], ln_s[DV + c0 + e + 3]), 0.f);
-          *reinterpret_cast<float4*>(dst + c0 + e) = o;
-        }
+      for (int e = 0; e < HC; e += 4) {
+        float4 v;
+        v.x = fmaxf(fmaf((x[e] - mean) * rstd, gam[e], bet[e]), 0.f);
+        v.y = fmaxf(fmaf((x[e + 1] - mean) * rstd, gam[e + 1], bet[e + 1]), 0.f);
+        v.z = fmaxf(fmaf((x[e + 2] - mean) * rstd, gam[e + 2], bet[e + 2]), 0.f);
+        v.w = fmaxf(fmaf((x[e + 3] - mean) * rstd, gam[e + 3], bet[e + 3]), 0.f);
+        *reinterpret_cast<float4*>(dst + e) = v;
       }
     }
   }
