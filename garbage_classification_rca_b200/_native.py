@@ -60,7 +60,11 @@ class HierParams(C.Structure):
 
 
 class HierDesc(C.Structure):
-    _fields_ = [("batch", C.c_int32), ("n_classes", C.c_int32), ("drop_p", C.c_float), ("drop_seed", C.c_uint64)]
+    _fields_ = [("batch", C.c_int32), ("n_classes", C.c_int32), ("drop_p", C.c_float), ("flags", C.c_uint32),
+                ("drop_seed", C.c_uint64)]
+
+
+HIER_FEATURE_GRADS = 1
 
 
 class FusionParams(C.Structure):
@@ -94,6 +98,7 @@ EXPORTS = ("mmrca_query", "mmrca_last_error", "mmrca_head_workspace_bytes", "mmr
            "mmrca_timing_end", "mmrca_dev_umma_selftest", "mmrca_attention_forward_scratch_bytes",
            "mmrca_head_workspace_offset", "mmrca_dropout_mask", "mmrca_dev_set_debug",
            "mmrca_hier_workspace_bytes", "mmrca_hier_forward", "mmrca_hier_backward", "mmrca_hier_train_step",
+           "mmrca_hier_backward_features",
            "mmrca_peer_allreduce_mean", "mmrca_peer_allreduce_pad_bytes", "mmrca_peer_allreduce_status",
            "mmrca_feature_handoff", "mmrca_sgd_step", "mmrca_adamw_step",
            "mmrca_token_attention_workspace_bytes", "mmrca_token_attention_forward",
@@ -194,6 +199,9 @@ def lib() -> C.CDLL:
         L.mmrca_hier_backward.argtypes = [C.POINTER(HierDesc), C.POINTER(HierParams), _fp, C.POINTER(HierParams),
                                           _fp, C.c_size_t, _fp]
         L.mmrca_hier_backward.restype = C.c_int
+        L.mmrca_hier_backward_features.argtypes = [C.POINTER(HierDesc), C.POINTER(HierParams), C.POINTER(_fp), _fp, C.c_float,
+                                                   C.POINTER(_fp), _fp, C.c_size_t, _fp]
+        L.mmrca_hier_backward_features.restype = C.c_int
         L.mmrca_hier_train_step.argtypes = [C.POINTER(HierDesc), C.POINTER(HierParams), C.POINTER(_fp), _fp,
                                             C.c_float, _fp, C.POINTER(CeDesc), _fp, _fp, C.POINTER(HierParams),
                                             _fp, C.c_size_t, _fp]

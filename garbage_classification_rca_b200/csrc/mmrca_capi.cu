@@ -741,9 +741,10 @@ static int launch_ce(const float* logits, const int64_t* labels, const MmrcaCeDe
 // ---- hierarchical head ----------------------------------------------------------------------------------------------
 struct HierWorkspace {
   void* x_img; void* x_txt; void* wb_img; void* wb_txt; void* h; void* dh; float* dlogits;
+  float* dcat;      // MMRCA_HIER_FEATURE_GRADS: d(dropped concat) fp32 [tiles * 128][8192]
   size_t bytes;
 };
-static HierWorkspace hier_carve(int batch, void* base) {
+static HierWorkspace hier_carve(int batch, void* base, uint32_t flags = 0) {
   HierWorkspace w;
   memset(&w, 0, sizeof(w));
   const size_t tiles = size_t(batch + hier::kTile - 1) / hier::kTile;
@@ -757,6 +758,7 @@ static HierWorkspace hier_carve(int batch, void* base) {
   w.h = take(tiles * hier::kTile * (2 * hier::kHid) * 2);
   w.dh = take(tiles * hier::kGHid * hier::kGrpBytes);
   w.dlogits = static_cast<float*>(take(tiles * hier::kTile * hier::kClasses * sizeof(float)));
+  if (flags & MMRCA_HIER_FEATURE_GRADS) w.dcat = static_cast<float*>(take(tiles * hier::kTile * size_t(hier::kD) * sizeof(float)));
   w.bytes = off;
   return w;
 }
@@ -1388,7 +1390,7 @@ int mmrca_fusion_train_step(const MmrcaFusionDesc* desc, const MmrcaFusionParams
 
 size_t mmrca_hier_workspace_bytes(const MmrcaHierDesc* desc) {
   if (hier_check(desc)) return 0;
-  return hier_carve(desc->batch, nullptr).bytes;
+  return hier_carve(desc->batch, nullptr, desc->flags).bytes;
 }
 
 int mmrca_hier_forward(const MmrcaHierDesc* desc, const MmrcaHierParams* params, const float* const* feats,
@@ -1399,7 +1401,7 @@ int mmrca_hier_forward(const MmrcaHierDesc* desc, const MmrcaHierParams* params,
   if (!params || !feats || !logits || !workspace) return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
   DeviceInfo di;
   if ((rc = device_info(&di))) return rc;
-  const HierWorkspace w = hier_carve(desc->batch, workspace);
+  const HierWorkspace w = hier_carve(desc->batch, workspace, desc->flags);
   if (workspace_bytes < w.bytes) return fail(MMRCA_ERR_WORKSPACE, "workspace too small%s%s");
   return hier_forward_impl(*desc, *params, feats, drop_mask, drop_scale, logits, w, static_cast<cudaStream_t>(stream));
 }
@@ -1411,9 +1413,47 @@ int mmrca_hier_backward(const MmrcaHierDesc* desc, const MmrcaHierParams* params
   if (!params || !dlogits || !grads || !workspace) return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
   DeviceInfo di;
   if ((rc = device_info(&di))) return rc;
-  const HierWorkspace w = hier_carve(desc->batch, workspace);
+  const HierWorkspace w = hier_carve(desc->batch, workspace, desc->flags);
   if (workspace_bytes < w.bytes) return fail(MMRCA_ERR_WORKSPACE, "workspace too small%s%s");
   return hier_backward_impl(*desc, *params, dlogits, *grads, w, static_cast<cudaStream_t>(stream));
+}
+
+int mmrca_hier_backward_features(const MmrcaHierDesc* desc, const MmrcaHierParams* params, const float* const* feats,
+                                 const uint8_t* drop_mask, float drop_scale, float* const* d_feats, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  int rc;
+  if ((rc = hier_check(desc))) return rc;
+  if (!params || !feats || !d_feats || !workspace) return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
+  if (!(desc->flags & MMRCA_HIER_FEATURE_GRADS))
+    return fail(MMRCA_ERR_INVALID, "feature gradients need MMRCA_HIER_FEATURE_GRADS in the desc of the forward and the backward%s%s");
+  for (int i = 0; i < 6; ++i)
+    if (!feats[i] || !d_feats[i] || ((reinterpret_cast<uintptr_t>(feats[i]) | reinterpret_cast<uintptr_t>(d_feats[i])) & 15))
+      return fail(MMRCA_ERR_INVALID, "the six feature / gradient pointers must be non-null and 16-byte aligned%s%s");
+  DeviceInfo di;
+  if ((rc = device_info(&di))) return rc;
+  const HierWorkspace w = hier_carve(desc->batch, workspace, desc->flags);
+  if (workspace_bytes < w.bytes) return fail(MMRCA_ERR_WORKSPACE, "workspace too small%s%s");
+  if (desc->batch == 0) return MMRCA_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int tiles = (desc->batch + hier::kTile - 1) / hier::kTile;
+  {   // d(dropped concat) = dH W: the dH image of mmrca_hier_backward and the forward's weight blobs
+    hier::DxArgs a;
+    a.dh = w.dh; a.wb[0] = w.wb_img; a.wb[1] = w.wb_txt; a.dcat = w.dcat;
+    if ((rc = set_smem(hier::hier_dx_kernel, hier::DxSmem::BYTES))) return rc;
+    LaunchScope ls("hier_dx", st);
+    hier::hier_dx_kernel<<<dim3(tiles, hier::kD / hier::kBN), hier::kGemmThreads, hier::DxSmem::BYTES, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  {
+    hier::DxFinishArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < 6; ++i) { a.seg[i] = feats[i]; a.out[i] = d_feats[i]; }
+    a.dcat = w.dcat; a.mask = drop_mask; a.mask_scale = drop_scale; a.drop = hier_drop(*desc); a.batch = desc->batch;
+    LaunchScope ls("hier_dx_finish", st);
+    hier::hier_dx_finish_kernel<<<desc->batch, 256, 0, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
 }
 
 int mmrca_hier_train_step(const MmrcaHierDesc* desc, const MmrcaHierParams* params, const float* const* feats,
@@ -1426,7 +1466,7 @@ int mmrca_hier_train_step(const MmrcaHierDesc* desc, const MmrcaHierParams* para
     return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
   DeviceInfo di;
   if ((rc = device_info(&di))) return rc;
-  const HierWorkspace w = hier_carve(desc->batch, workspace);
+  const HierWorkspace w = hier_carve(desc->batch, workspace, desc->flags);
   if (workspace_bytes < w.bytes) return fail(MMRCA_ERR_WORKSPACE, "workspace too small%s%s");
   if (desc->batch == 0) return MMRCA_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

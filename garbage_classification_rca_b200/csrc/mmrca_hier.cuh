@@ -445,5 +445,159 @@ __global__ void __launch_bounds__(kGemmThreads, 1) hier_wgrad_kernel(const Wgrad
   if (warp == 1) tmem_dealloc(tmem, kBN);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// feature gradients (fine-tune phase, main_both.py:687-694): d(dropped concat) = dH W, a GEMM with the SAME operand bytes
+// as the forward - A = the dH image (K-major over the 512 hidden units of the modality), B = the forward's weight blob
+// [k/8][512][8] read MN-major (n = concat column contiguous, K = hidden unit) - then, per sample, the dropout mask and the
+// six L2-norm backwards (hier_dx_finish_kernel).  CTA = (sample tile, 256 concat columns); grid.y walks the image columns
+// (23 blocks) then the text columns (9 blocks).
+// ---------------------------------------------------------------------------------------------------------------
+struct DxArgs {
+  const void* dh;            // dH image [tiles][128 groups][128][8]
+  const void* wb[2];         // weight blobs [K/8][512][8]
+  float* dcat;               // out: d(dropped concat) fp32 [tiles * 128][8192] (image columns first)
+};
+constexpr int kDxStages = 2, kDxKG = 16;                                    // 16 hidden groups = K 128 per stage
+constexpr uint32_t kDxABytes = kDxKG * kGrpBytes;                           // 32 KB
+constexpr uint32_t kDxBBytes = (kBN / 8) * (kDxKG * 8) * 16;                // 32 column groups x 128 hidden x 16 B = 64 KB
+struct DxSmem {
+  static constexpr uint32_t A = 0, B = A + kDxStages * kDxABytes, BAR = B + kDxStages * kDxBBytes, BYTES = BAR + 128;
+  static_assert(BYTES <= 232448, "hierarchical feature-gradient GEMM does not fit shared memory");
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1) hier_dx_kernel(const DxArgs a) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  using S = DxSmem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + S::BAR);
+  uint64_t* empty = full + kDxStages;
+  uint64_t* accb = empty + kDxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accb + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x;
+  int cb = blockIdx.y, mod = 0;
+  if (cb >= kDImg / kBN) { cb -= kDImg / kBN; mod = 1; }
+  constexpr int n_it = kHid / (kDxKG * 8);                                  // 4 K-stages
+  if (tid == 0) {
+    for (int i = 0; i < 2 * kDxStages + 1; ++i) mbar_init(&full[i], 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kBN);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint8_t* pa = static_cast<const uint8_t*>(a.dh) + (size_t(tile) * kGHid + size_t(mod) * (kHid / 8)) * kGrpBytes;
+      const uint8_t* pb = static_cast<const uint8_t*>(a.wb[mod]) + size_t(cb) * (kBN / 8) * (kHid * 16);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % kDxStages;
+        if (it >= kDxStages) mbar_wait(&empty[s], uint32_t(it / kDxStages - 1) & 1u);
+        mbar_arrive_expect_tx(&full[s], kDxABytes + kDxBBytes);
+        bulk_g2s(sm + S::A + s * kDxABytes, pa + size_t(it) * kDxABytes, kDxABytes, &full[s]);
+#pragma unroll 1
+        for (int g = 0; g < kBN / 8; ++g)      // column group g: hidden units [128 it, 128 it + 128) are 2 KB contiguous
+          bulk_g2s(sm + S::B + s * kDxBBytes + g * (kDxKG * 8 * 16), pb + (size_t(g) * kHid + size_t(it) * kDxKG * 8) * 16,
+                   kDxKG * 8 * 16, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, kBN, 0, 1);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % kDxStages;
+        mbar_wait(&full[s], uint32_t(it / kDxStages) & 1u);
+        tc_fence_after_sync();
+        const uint64_t ad = make_smem_desc(smem_u32(sm + S::A + s * kDxABytes), kGrpBytes, 128);
+        const uint64_t bd = make_smem_desc(smem_u32(sm + S::B + s * kDxBBytes), 128, kDxKG * 8 * 16);
+#pragma unroll
+        for (int ks = 0; ks < kDxKG / 2; ++ks)
+          umma_bf16(tmem, desc_advance(ad, ks * 2 * kGrpBytes), desc_advance(bd, ks * 256), idesc, (it | ks) ? 1u : 0u);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(accb);
+    }
+  } else {
+    const int q = warp & 3, row = 32 * q + lane;
+    float* dst = a.dcat + size_t(tile * kTile + row) * kD + (mod ? kDImg : 0) + cb * kBN;
+    mbar_wait(accb, 0);
+    tc_fence_after_sync();
+#pragma unroll 1
+    for (int c0 = 0; c0 < kBN; c0 += 32) {
+      uint32_t r0[16], r1[16];
+      tmem_ld16_nw(tmem + (uint32_t(32 * q) << 16) + c0, r0);
+      tmem_ld16_nw(tmem + (uint32_t(32 * q) << 16) + c0 + 16, r1);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        *reinterpret_cast<uint4*>(dst + c0 + 4 * j) = make_uint4(r0[4 * j], r0[4 * j + 1], r0[4 * j + 2], r0[4 * j + 3]);
+        *reinterpret_cast<uint4*>(dst + c0 + 16 + 4 * j) = make_uint4(r1[4 * j], r1[4 * j + 1], r1[4 * j + 2], r1[4 * j + 3]);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, kBN);
+}
+
+// per sample: d(x_seg) = (m . d - xn (xn . (m . d))) / ||x_seg|| for the six segments (m: the dropout multipliers of the forward).
+// One CTA per sample, the thread / item / segment mapping of hier_prep_kernel.
+struct DxFinishArgs {
+  const float* seg[6];       // the forward's raw features
+  const float* dcat;         // [tiles * 128][8192]
+  const uint8_t* mask; float mask_scale; DropSpec drop;
+  float* out[6];             // feature gradients, same shapes as seg
+  int batch;
+};
+__global__ void __launch_bounds__(256) hier_dx_finish_kernel(const DxFinishArgs a) {
+  __shared__ float s_ss[6], s_dot[6];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  if (tid < 6) { s_ss[tid] = 0.f; s_dot[tid] = 0.f; }
+  __syncthreads();
+  float v[4][8], d[4][8];
+  int seg[4], first[4], len[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int item = tid + 256 * k;
+    if (item < 160) { seg[k] = 0; first[k] = 0; len[k] = 1280; }
+    else if (item < 480) { seg[k] = 1; first[k] = 160; len[k] = 2560; }
+    else if (item < 736) { seg[k] = 2; first[k] = 480; len[k] = 2048; }
+    else if (item < 832) { seg[k] = 3; first[k] = 736; len[k] = 768; }
+    else if (item < 928) { seg[k] = 4; first[k] = 832; len[k] = 768; }
+    else { seg[k] = 5; first[k] = 928; len[k] = 768; }
+    const float* p = a.seg[seg[k]] + size_t(b) * len[k] + (item - first[k]) * 8;
+    const float4 lo = __ldg(reinterpret_cast<const float4*>(p)), hi = __ldg(reinterpret_cast<const float4*>(p + 4));
+    v[k][0] = lo.x; v[k][1] = lo.y; v[k][2] = lo.z; v[k][3] = lo.w; v[k][4] = hi.x; v[k][5] = hi.y; v[k][6] = hi.z; v[k][7] = hi.w;
+    const float* q = a.dcat + size_t(b) * kD + item * 8;
+    const float4 dlo = __ldg(reinterpret_cast<const float4*>(q)), dhi = __ldg(reinterpret_cast<const float4*>(q + 4));
+    d[k][0] = dlo.x; d[k][1] = dlo.y; d[k][2] = dlo.z; d[k][3] = dlo.w; d[k][4] = dhi.x; d[k][5] = dhi.y; d[k][6] = dhi.z; d[k][7] = dhi.w;
+    if (a.mask) {
+      const uint2 m = __ldg(reinterpret_cast<const uint2*>(a.mask + size_t(b) * kD + item * 8));
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d[k][e] *= (((e < 4 ? m.x : m.y) >> (8 * (e & 3))) & 0xffu) ? a.mask_scale : 0.f;
+    } else if (a.drop.thresh) {
+      drop_apply8(a.drop, uint32_t(b), uint32_t(item * 8), d[k]);
+    }
+    float ss = 0.f, dot = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { ss = fmaf(v[k][e], v[k][e], ss); dot = fmaf(v[k][e], d[k][e], dot); }
+    ss = warp_sum(ss); dot = warp_sum(dot);
+    if (lane == 0) { atomicAdd(&s_ss[seg[k]], ss); atomicAdd(&s_dot[seg[k]], dot); }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int item = tid + 256 * k;
+    const float n2 = s_ss[seg[k]], inv = 1.0f / sqrtf(n2);
+    const float proj = s_dot[seg[k]] / n2;          // (x . d) / ||x||^2: xn (xn . d) = x proj
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = (d[k][e] - v[k][e] * proj) * inv;
+    float* p = a.out[seg[k]] + size_t(b) * len[k] + (item - first[k]) * 8;
+    *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(o[4], o[5], o[6], o[7]);
+  }
+}
+
 }  // namespace hier
 }  // namespace mmrca

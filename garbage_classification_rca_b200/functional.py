@@ -517,12 +517,15 @@ class _HierFunction(torch.autograd.Function):
             if drop_mask.shape != (B, HIER_CONCAT):
                 raise ValueError("hierarchical dropout mask must be [B, 8192]")
         dev = feats[0].device
-        desc = N.HierDesc(B, params[4].shape[0], float(drop_p), int(drop_seed) & (2 ** 64 - 1))
+        want_feat = any(ctx.needs_input_grad[4:10])
+        desc = N.HierDesc(B, params[4].shape[0], float(drop_p), N.HIER_FEATURE_GRADS if want_feat else 0,
+                          int(drop_seed) & (2 ** 64 - 1))
         L = N.lib()
         ws = torch.empty(max(1, L.mmrca_hier_workspace_bytes(C.byref(desc))), dtype=torch.uint8, device=dev)
         logits = torch.empty(B, params[4].shape[0], dtype=torch.float32, device=dev)
         ctx.save_for_backward(ws, *params)
         ctx.desc = desc
+        ctx.feat_state = (feats, drop_mask, float(drop_scale)) if want_feat else None
         if B > 0:
             with torch.cuda.device(dev):
                 N.check(L.mmrca_hier_forward(C.byref(desc), C.byref(_hier_struct(params)), arr,
@@ -534,16 +537,24 @@ class _HierFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits):
         ws, *params = ctx.saved_tensors
-        if any(ctx.needs_input_grad[4:10]):
-            raise RuntimeError("the hierarchical head is built for frozen backbones: no feature gradients")
         dlogits = _check_dev(dlogits, "dlogits")
         fg = FlatGrads(params)
+        dfe = [None] * 6
         if ctx.desc.batch > 0:
             with torch.cuda.device(ws.device):
                 N.check(N.lib().mmrca_hier_backward(C.byref(ctx.desc), C.byref(_hier_struct(params)), dlogits.data_ptr(),
                                                     C.byref(_hier_struct(fg.views)), ws.data_ptr(), ws.numel(),
                                                     _stream_ptr(ws.device)), "mmrca_hier_backward")
-        return (None,) * 10 + tuple(v if ctx.needs_input_grad[10 + i] else None for i, v in enumerate(fg.views))
+                if ctx.feat_state is not None:      # fine-tune phase (reference main_both.py:687-694)
+                    feats, drop_mask, drop_scale = ctx.feat_state
+                    dfe = [torch.empty_like(f) for f in feats]
+                    N.check(N.lib().mmrca_hier_backward_features(
+                        C.byref(ctx.desc), C.byref(_hier_struct(params)), (N._fp * 6)(*[f.data_ptr() for f in feats]),
+                        drop_mask.data_ptr() if drop_mask is not None else None, drop_scale,
+                        (N._fp * 6)(*[t.data_ptr() for t in dfe]), ws.data_ptr(), ws.numel(), _stream_ptr(ws.device)),
+                        "mmrca_hier_backward_features")
+        return (None,) * 4 + tuple(g if ctx.needs_input_grad[4 + i] else None for i, g in enumerate(dfe)) + \
+            tuple(v if ctx.needs_input_grad[10 + i] else None for i, v in enumerate(fg.views))
 
 
 def hierarchical_head(feats: Sequence[torch.Tensor], params: Sequence[torch.Tensor], *,
@@ -567,7 +578,7 @@ class HierTrainStep:
                  label_smoothing: float = 0.0, drop_p: float = 0.0):
         self.params = [_check_dev(p.detach(), "hierarchical parameter") for p in params]
         dev = self.params[0].device
-        self.desc = N.HierDesc(batch, self.params[4].shape[0], float(drop_p), 0)
+        self.desc = N.HierDesc(batch, self.params[4].shape[0], float(drop_p), 0, 0)
         self.grads = FlatGrads(self.params)
         self.hp, self.hg = _hier_struct(self.params), _hier_struct(self.grads.views)
         self.ws = torch.empty(max(1, N.lib().mmrca_hier_workspace_bytes(C.byref(self.desc))), dtype=torch.uint8, device=dev)

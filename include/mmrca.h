@@ -238,10 +238,12 @@ typedef struct MmrcaHierParams {
 typedef struct MmrcaHierGrads { /* accumulated into (+=), 16-byte aligned; w_all / b_all may be NULL */
   float* w_img; float* b_img; float* w_txt; float* b_txt; float* w_all; float* b_all;
 } MmrcaHierGrads;
+#define MMRCA_HIER_FEATURE_GRADS 1u /* the backward will be asked for the six feature gradients (fine-tune phase): sizes the workspace */
 typedef struct MmrcaHierDesc {
   int32_t batch;
   int32_t n_classes;  /* 4 */
   float drop_p;       /* self.drop on both concats (:805-806): seeded mask over the virtual concat [image 5888 | text 2304] */
+  uint32_t flags;     /* MMRCA_HIER_* */
   uint64_t drop_seed;
 } MmrcaHierDesc;
 size_t mmrca_hier_workspace_bytes(const MmrcaHierDesc* desc);
@@ -252,9 +254,14 @@ size_t mmrca_hier_workspace_bytes(const MmrcaHierDesc* desc);
 int mmrca_hier_forward(const MmrcaHierDesc* desc, const MmrcaHierParams* params, const float* const* feats,
                        const uint8_t* drop_mask, float drop_scale, float* logits, void* workspace,
                        size_t workspace_bytes, void* stream);
-/* needs the unmodified workspace of the forward */
+/* needs the unmodified workspace of the forward.  d_feats: NULL (frozen backbones) or six output pointers shaped like
+ * feats (fine-tune phase, main_both.py:687-694; needs MMRCA_HIER_FEATURE_GRADS in desc->flags of forward and backward and the
+ * forward's feats / drop_mask / drop_scale again): d(loss)/d(feature) through the dropout, the concat and the six L2 norms. */
 int mmrca_hier_backward(const MmrcaHierDesc* desc, const MmrcaHierParams* params, const float* dlogits,
                         const MmrcaHierGrads* grads, void* workspace, size_t workspace_bytes, void* stream);
+int mmrca_hier_backward_features(const MmrcaHierDesc* desc, const MmrcaHierParams* params, const float* const* feats,
+                                 const uint8_t* drop_mask, float drop_scale, float* const* d_feats, void* workspace,
+                                 size_t workspace_bytes, void* stream);
 int mmrca_hier_train_step(const MmrcaHierDesc* desc, const MmrcaHierParams* params, const float* const* feats,
                           const uint8_t* drop_mask, float drop_scale, const int64_t* labels, const MmrcaCeDesc* ce,
                           float* logits, float* loss_out, const MmrcaHierGrads* grads, void* workspace,

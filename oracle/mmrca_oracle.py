@@ -440,15 +440,19 @@ def hier_forward(p: Dict[str, torch.Tensor], img_segments, txt_segments,
 
 def hier_loss_and_grads(p: Dict[str, torch.Tensor], img_segments, txt_segments, labels: torch.Tensor,
                         class_weight: Optional[torch.Tensor] = None, label_smoothing: float = 0.0,
-                        drop_mask: Optional[torch.Tensor] = None, drop_scale: float = 1.0, dtype=torch.float64):
+                        drop_mask: Optional[torch.Tensor] = None, drop_scale: float = 1.0, dtype=torch.float64,
+                        feature_grads: bool = False):
     """forward + CrossEntropyLoss + backward (main_both.py:106-112) of the hierarchical head through autograd,
-    in float64 by default.  Returns (logits, loss, grads{name: tensor})."""
+    in float64 by default.  Returns (logits, loss, grads{name: tensor}) (+ the six feature gradients on request)."""
     pp = {k: v.detach().to(dtype).clone().requires_grad_(True) for k, v in p.items() if k in HIER_PARAM_NAMES}
-    logits = hier_forward(pp, [s.detach().to(dtype) for s in img_segments], [s.detach().to(dtype) for s in txt_segments],
-                          drop_mask, drop_scale)
+    xi = [s.detach().to(dtype).clone().requires_grad_(feature_grads) for s in img_segments]
+    xt = [s.detach().to(dtype).clone().requires_grad_(feature_grads) for s in txt_segments]
+    logits = hier_forward(pp, xi, xt, drop_mask, drop_scale)
     cw = None if class_weight is None else class_weight.to(dtype)
     loss = cross_entropy(logits, labels, cw, label_smoothing)
     loss.backward()
+    if feature_grads:      # fine-tune phase: d(loss)/d(each of the six pooled feature tensors), image segments first
+        return logits.detach(), loss.detach(), {k: v.grad for k, v in pp.items()}, [t.grad for t in xi + xt]
     return logits.detach(), loss.detach(), {k: v.grad for k, v in pp.items()}
 
 

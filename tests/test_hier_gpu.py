@@ -202,3 +202,33 @@ def test_hier_module_with_stock_backbones(pkg):
     sd = {k: v.detach().cpu() for k, v in m.state_dict().items() if k.startswith("final_hierarchical")}
     ref = orc.hier_forward(sd, [f.float().cpu() for f in feats[:3]], [f.float().cpu() for f in feats[3:]])
     assert (out.cpu() - ref).abs().max().item() <= LOGITS_ABS_BF16
+
+
+@pytest.mark.parametrize("B,drop_p", [(5, 0.0), (200, 0.6)])
+def test_hier_feature_gradients(pkg, B, drop_p):
+    """Fine-tune phase (reference main_both.py:687-694): d(loss)/d(each of the six pooled feature tensors) - dH W as a
+    tcgen05 GEMM over the forward's operand bytes, then the dropout mask and the six L2-norm backwards - against the float64
+    oracle (same seeded mask): relative L2 error per tensor <= 2e-2 (bf16 dH and weights)."""
+    from garbage_classification_rca_b200 import functional as F
+    from garbage_classification_rca_b200.training import CrossEntropyLoss
+    p = orc.init_hier_params(seed=6, bias_gap=0.1)
+    g = torch.Generator().manual_seed(60 + B)
+    feats = [torch.randn(B, w, generator=g) * 0.8 + 0.1 for w in F.HIER_SEGMENTS]
+    labels = torch.randint(0, 4, (B,), generator=g)
+    seed = 21
+    mask = F.dropout_mask(seed, drop_p, B, F.HIER_CONCAT, "cuda").cpu() if drop_p > 0 else None
+    scale = 1.0 / (1.0 - drop_p) if drop_p > 0 else 1.0
+    _, rloss, rg, rfe = orc.hier_loss_and_grads(p, feats[:3], feats[3:], labels, drop_mask=mask, drop_scale=scale,
+                                                feature_grads=True)
+    params = [p[n].cuda().requires_grad_(True) for n in F.HIER_PARAM_NAMES]
+    xs = [f.cuda().requires_grad_(True) for f in feats]
+    logits = pkg.hierarchical_head(xs, params, drop_p=drop_p, drop_seed=seed)
+    loss = CrossEntropyLoss()(logits, labels.cuda())
+    loss.backward()
+    assert abs(loss.item() - float(rloss)) <= 2e-2
+    for i, (x, r) in enumerate(zip(xs, rfe)):
+        got, ref = x.grad.cpu().double().numpy(), r.numpy()
+        err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+        assert err <= 2e-2, f"feature {i}: relative L2 error {err:.3e}"
+    for n, t in zip(F.HIER_PARAM_NAMES, params):      # the parameter gradients are unaffected by the extra outputs
+        _grad_check(t.grad.cpu().numpy(), rg[n].numpy(), n)
