@@ -165,6 +165,20 @@ class _WorkspacePool:
 _pool = _WorkspacePool()
 
 
+class _Lease:
+    """Hands a pooled workspace back when the autograd node that owns it dies (after backward, or when the graph is
+    dropped) - never earlier, so backward(retain_graph=True) can run again on intact saved buffers."""
+
+    def __init__(self, buf: torch.Tensor):
+        self.buf = buf
+
+    def __del__(self):
+        try:
+            _pool.give(self.buf)
+        except Exception:      # noqa: BLE001  (interpreter shutdown)
+            pass
+
+
 def _check_mask(drop_mask: Optional[torch.Tensor], batch: int, width: int, what: str) -> Optional[torch.Tensor]:
     if drop_mask is None:
         return None
@@ -227,6 +241,7 @@ class _HeadFunction(torch.autograd.Function):
         desc = _desc(B, d_img, d_txt, n_classes, flags, compute, drop_p, drop_seed)
         L = N.lib()
         ws = _pool.take(L.mmrca_head_workspace_bytes(C.byref(desc), 1 if needs_bwd else 0), img.device)
+        ctx.lease = _Lease(ws)
         logits = torch.empty(B, n_classes, dtype=torch.float32, device=img.device)
         hp = _head_struct(params)
         ctx.save_for_backward(img, txt, drop_mask, ws, *params)
@@ -263,7 +278,6 @@ class _HeadFunction(torch.autograd.Function):
                     dlogits.data_ptr(), C.byref(hg), d_img.data_ptr() if want_feat else None,
                     d_txt.data_ptr() if want_feat else None, ws.data_ptr(), ws.numel(),
                     _stream_ptr(img.device)), "mmrca_head_backward")
-        _pool.give(ws)
         features_only = bool(flags & N.FLAG_FEATURES_ONLY)
         pg = []
         for i, v in enumerate(fg.views):
@@ -642,6 +656,7 @@ class _FusionFunction(torch.autograd.Function):
         drop_mask = _check_mask(drop_mask, B, desc.hidden, "fusion head")
         L = N.lib()
         ws = _pool.take(L.mmrca_fusion_workspace_bytes(C.byref(desc)), img.device)
+        ctx.lease = _Lease(ws)
         logits = torch.empty(B, desc.n_classes, dtype=torch.float32, device=img.device)
         ctx.save_for_backward(img, txt, drop_mask, ws, *params)
         ctx.cfg = (desc, float(drop_scale))
@@ -672,7 +687,6 @@ class _FusionFunction(torch.autograd.Function):
                     "mmrca_fusion_backward")
         elif want_feat:
             d_img.zero_(); d_txt.zero_()
-        _pool.give(ws)
         return (d_img if ctx.needs_input_grad[0] else None, d_txt if ctx.needs_input_grad[1] else None, None, None, None,
                 None, None, *[v if ctx.needs_input_grad[7 + i] else None for i, v in enumerate(fg.views)])
 

@@ -433,7 +433,10 @@ class MM_RCA(EffV2MediumAndDistilbertGated):
         self._attention_mask = _attention_mask
         self.drop_modalities(eval, remove_image, remove_text)
         cache = getattr(self, "feature_cache", None)
-        use_cache = cache is not None and sample_ids is not None and self._frozen() and not (remove_image or remove_text)
+        # the cache holds the features of the UNMODIFIED inputs: not when a modality is removed (eval flags) or may be
+        # dropped at random (training with image_or_text_dropout_chance > 0, reference :444-452)
+        use_cache = (cache is not None and sample_ids is not None and self._frozen() and not (remove_image or remove_text)
+                     and (eval or self.image_or_text_dropout_chance == 0))
         feats = cache.lookup(sample_ids) if use_cache else None
         if feats is None:
             feats = self.backbone_features()

@@ -244,3 +244,18 @@ def test_build_model_dispatches_the_rebuilt_late_fusion_variants():
         assert len(m.state_dict()) > 1000        # the shared base's full state_dict, whatever the variant
     with pytest.raises(SystemExit):
         build_model(args_parser(["--late_fusion=clip"]), pretrained=False)
+
+
+def test_feature_cache_logic_on_cpu():
+    """training.FeatureCache: all-or-nothing lookup by dataset index, store, invalidate (device-agnostic plumbing)."""
+    from garbage_classification_rca_b200.training import FeatureCache
+    c = FeatureCache(10, 4, 3, "cpu", dtype=torch.float32)
+    ids = torch.tensor([7, 2, 9])
+    assert c.lookup(ids) is None and c.misses == 3
+    img, txt = torch.arange(12.0).view(3, 4), torch.arange(9.0).view(3, 3)
+    c.store(ids, img, txt)
+    got = c.lookup(torch.tensor([9, 7]))
+    assert torch.equal(got[0], img[[2, 0]]) and torch.equal(got[1], txt[[2, 0]]) and c.hits == 2
+    assert c.lookup(torch.tensor([9, 1])) is None          # one uncached id: the whole batch goes through the backbones
+    c.invalidate()
+    assert c.lookup(ids) is None
