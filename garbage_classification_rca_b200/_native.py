@@ -86,6 +86,7 @@ class TokenDesc(C.Structure):
 
 
 TOKEN_WEIGHTS_READY = 1
+TOKEN_TRAINING = 2
 
 
 class CeDesc(C.Structure):
@@ -101,7 +102,7 @@ EXPORTS = ("mmrca_query", "mmrca_last_error", "mmrca_head_workspace_bytes", "mmr
            "mmrca_hier_backward_features",
            "mmrca_peer_allreduce_mean", "mmrca_peer_allreduce_pad_bytes", "mmrca_peer_allreduce_status",
            "mmrca_feature_handoff", "mmrca_sgd_step", "mmrca_adamw_step",
-           "mmrca_token_attention_workspace_bytes", "mmrca_token_attention_forward",
+           "mmrca_token_attention_workspace_bytes", "mmrca_token_attention_forward", "mmrca_token_attention_backward",
            "mmrca_fusion_workspace_bytes", "mmrca_fusion_forward", "mmrca_fusion_backward", "mmrca_fusion_train_step")
 
 
@@ -217,6 +218,9 @@ def lib() -> C.CDLL:
         L.mmrca_token_attention_workspace_bytes.restype = C.c_size_t
         L.mmrca_token_attention_forward.argtypes = [C.c_void_p, C.c_void_p, _fp, _fp, _fp, _fp, C.c_size_t, _fp]
         L.mmrca_token_attention_forward.restype = C.c_int
+        L.mmrca_token_attention_backward.argtypes = [C.c_void_p, C.c_void_p, _fp, _fp, _fp, C.c_void_p, _fp, _fp, _fp,
+                                                     C.c_size_t, _fp]
+        L.mmrca_token_attention_backward.restype = C.c_int
         L.mmrca_fusion_workspace_bytes.argtypes = [C.c_void_p]
         L.mmrca_fusion_workspace_bytes.restype = C.c_size_t
         L.mmrca_fusion_forward.argtypes = [C.c_void_p, C.c_void_p, _fp, _fp, _fp, C.c_float, _fp, _fp, C.c_size_t, _fp]

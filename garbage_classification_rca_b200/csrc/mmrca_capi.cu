@@ -22,6 +22,7 @@
 #include "mmrca_train_aux.cuh"
 #include "mmrca_fusion_fp32.cuh"
 #include "mmrca_token.cuh"
+#include "mmrca_token_bwd.cuh"
 
 namespace mmrca {
 
@@ -885,6 +886,10 @@ struct TokenWorkspace {
   __nv_bfloat16* w;       // stacked bf16 weights: self [2 d_kq + d_v][d_in]; cross [d_kq][d_in_q] then [d_kq + d_v][d_in_kv]
   float* bias;            // stacked [2 d_kq + d_v]
   void *q_img, *k_img, *v_img;
+  // MMRCA_TOKEN_TRAINING: kept by the forward for the backward, and the backward's own buffers
+  void* p_img; float* sum;
+  float *dq, *dk_part, *dv_part;
+  void *dq_img, *dk_img, *dv_img, *xq_img, *xkv_img, *wmn_q, *wmn_kv;
   size_t bytes;
 };
 static TokenWorkspace token_carve(const MmrcaTokenDesc& d, void* base) {
@@ -900,6 +905,21 @@ static TokenWorkspace token_carve(const MmrcaTokenDesc& d, void* base) {
   w.q_img = take(B * tps * htc::op_bytes(d.d_kq));
   w.k_img = take(B * tps * htc::op_bytes(d.d_kq));
   w.v_img = take(B * tps * htc::op_bytes(d.d_v));
+  if (d.flags & MMRCA_TOKEN_TRAINING) {
+    const size_t ncols = tps * tok::kTile;
+    w.p_img = take(B * tps * htc::op_bytes(tok::kMaxTiles * tok::kTile));
+    w.sum = static_cast<float*>(take(B * tps * tok::kTile * 4));
+    w.dq = static_cast<float*>(take(B * ncols * d.d_kq * 4));
+    w.dk_part = static_cast<float*>(take(B * tps * ncols * d.d_kq * 4));
+    w.dv_part = static_cast<float*>(take(B * tps * ncols * d.d_v * 4));
+    w.dq_img = take(B * tps * htc::op_bytes(d.d_kq));
+    w.dk_img = take(B * tps * htc::op_bytes(d.d_kq));
+    w.dv_img = take(B * tps * htc::op_bytes(d.d_v));
+    w.xq_img = take(B * tps * size_t(d.d_in_q / 8) * tok::kXGrp);
+    w.xkv_img = take(B * tps * size_t(d.d_in_kv / 8) * tok::kXGrp);
+    w.wmn_q = take(size_t(d.d_in_q / 8) * size_t(2 * d.d_kq + d.d_v) * 16);
+    w.wmn_kv = take(size_t(d.d_in_kv / 8) * size_t(d.d_kq + d.d_v) * 16);
+  }
   w.bytes = off;
   return w;
 }
@@ -964,6 +984,51 @@ static int launch_tok_attn(const MmrcaTokenDesc& d, const tok::AttnArgs& a, cuda
   {
     LaunchScope ls(DKQ == 128 ? "tok_attn<128,96>" : "tok_attn<64,48>", st);
     tok::tok_attn_kernel<DKQ, DV><<<d.batch * a.tiles_per_sample, 256, S::BYTES, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+
+template <int DKQ, int DV>
+static int launch_tok_attn_bwd(const MmrcaTokenDesc& d, const tok::AttnBwdArgs& a, cudaStream_t st) {
+  int rc;
+  using S = tok::AttnBwdSmem<DKQ, DV>;
+  if ((rc = set_smem(tok::tok_attn_bwd_kernel<DKQ, DV>, S::BYTES))) return rc;
+  {
+    LaunchScope ls(DKQ == 128 ? "tok_attn_bwd<128,96>" : "tok_attn_bwd<64,48>", st);
+    tok::tok_attn_bwd_kernel<DKQ, DV><<<d.batch * a.tiles_per_sample, 256, S::BYTES, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+static int launch_tok_wgrad(const tok::WgradArgs& a, int nseg, int sms, cudaStream_t st) {
+  int rc;
+  if ((rc = set_smem(tok::tok_wgrad_kernel, tok::GradSmem::BYTES))) return rc;
+  const int nts = (a.K + 255) / 256;
+  const int splits = std::max(1, std::min(a.tiles, sms / (nts * nseg)));
+  {
+    LaunchScope ls("tok_wgrad", st);
+    tok::tok_wgrad_kernel<<<dim3(nts, nseg, splits), tok::kGradThreads, tok::GradSmem::BYTES, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+static int launch_tok_dgrad(const tok::DgradArgs& a, int tiles, cudaStream_t st) {
+  int rc;
+  if ((rc = set_smem(tok::tok_dgrad_kernel, tok::GradSmem::BYTES))) return rc;
+  {
+    LaunchScope ls("tok_dgrad", st);
+    tok::tok_dgrad_kernel<<<dim3(tiles, (a.K + 255) / 256), tok::kGradThreads, tok::GradSmem::BYTES, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+static int launch_tok_wprep_mn(const float* w, int n_rows, int K, int N, int n0, void* blob, int sms, cudaStream_t st) {
+  const long long items = (long long)n_rows * (K / 8);
+  {
+    LaunchScope ls("tok_wprep_mn", st);
+    tok::tok_wprep_mn_kernel<<<int(std::min<long long>((items + 255) / 256, 4LL * sms)), 256, 0, st>>>(w, n_rows, K, N, n0,
+                                                                                                         static_cast<uint8_t*>(blob));
   }
   MMRCA_CUDA(cudaGetLastError());
   return MMRCA_OK;
@@ -1331,7 +1396,110 @@ int mmrca_token_attention_forward(const MmrcaTokenDesc* desc, const MmrcaAttnPar
   memset(&a, 0, sizeof(a));
   a.q_img = w.q_img; a.k_img = w.k_img; a.v_img = w.v_img; a.ln_g = p->ln_g; a.ln_b = p->ln_b; a.out = out;
   a.L = desc->seq_len; a.tiles_per_sample = (desc->seq_len + tok::kTile - 1) / tok::kTile; a.reverse = desc->reverse ? 1 : 0;
+  a.p_out = w.p_img; a.sum_out = w.sum;      // null unless MMRCA_TOKEN_TRAINING
   return dkq == 128 ? launch_tok_attn<128, 96>(*desc, a, st) : launch_tok_attn<64, 48>(*desc, a, st);
+}
+
+int mmrca_token_attention_backward(const MmrcaTokenDesc* desc, const MmrcaAttnParams* p, const void* x_q, const void* x_kv,
+                                   const float* d_out, const MmrcaAttnGrads* grads, float* d_x_q, float* d_x_kv,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+  int rc;
+  if ((rc = token_check(desc))) return rc;
+  if (!(desc->flags & MMRCA_TOKEN_TRAINING))
+    return fail(MMRCA_ERR_INVALID, "token attention backward needs MMRCA_TOKEN_TRAINING on the descriptor of forward and backward%s%s");
+  if (!p || !x_q || !d_out || !grads || !workspace) return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
+  const bool self = x_kv == nullptr || x_kv == x_q;
+  if (self && desc->d_in_q != desc->d_in_kv) return fail(MMRCA_ERR_INVALID, "self attention: d_in_q must equal d_in_kv%s%s");
+  if ((desc->d_in_q & 15) || (desc->d_in_kv & 15))
+    return fail(MMRCA_ERR_INVALID, "token attention backward: d_in must be a multiple of 16%s%s");
+  if ((reinterpret_cast<uintptr_t>(x_q) & 15) || (!self && (reinterpret_cast<uintptr_t>(x_kv) & 15)) ||
+      (reinterpret_cast<uintptr_t>(d_out) & 15) || (reinterpret_cast<uintptr_t>(d_x_q) & 15) || (reinterpret_cast<uintptr_t>(d_x_kv) & 15))
+    return fail(MMRCA_ERR_INVALID, "token activations and gradients must be 16-byte aligned%s%s");
+  DeviceInfo di;
+  if ((rc = device_info(&di))) return rc;
+  const TokenWorkspace w = token_carve(*desc, workspace);
+  if (workspace_bytes < w.bytes) return fail(MMRCA_ERR_WORKSPACE, "workspace too small%s%s");
+  if (desc->batch == 0) return MMRCA_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int dkq = desc->d_kq, dv = desc->d_v, kq = desc->d_in_q, kkv = desc->d_in_kv, L = desc->seq_len;
+  const int tps = (L + tok::kTile - 1) / tok::kTile, tiles = desc->batch * tps;
+  {
+    tok::AttnBwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.q_img = w.q_img; a.k_img = w.k_img; a.v_img = w.v_img; a.p_img = w.p_img; a.sum = w.sum;
+    a.ln_g = p->ln_g; a.ln_b = p->ln_b; a.d_out = d_out;
+    a.dq = w.dq; a.dk_part = w.dk_part; a.dv_part = w.dv_part; a.g_ln_g = grads->ln_g; a.g_ln_b = grads->ln_b;
+    a.L = L; a.tiles_per_sample = tps; a.reverse = desc->reverse ? 1 : 0;
+    if ((rc = dkq == 128 ? launch_tok_attn_bwd<128, 96>(*desc, a, st) : launch_tok_attn_bwd<64, 48>(*desc, a, st))) return rc;
+  }
+  {
+    tok::GradFinishArgs a;
+    memset(&a, 0, sizeof(a));
+    a.dq = w.dq; a.dk_part = w.dk_part; a.dv_part = w.dv_part; a.dq_img = w.dq_img; a.dk_img = w.dk_img; a.dv_img = w.dv_img;
+    a.g_bq = grads->bq; a.g_bk = grads->bk; a.g_bv = grads->bv;
+    a.qscale = 1.0f / sqrtf(float(dkq)); a.L = L; a.tiles_per_sample = tps; a.dkq = dkq; a.dv = dv;
+    {
+      LaunchScope ls("tok_grad_finish", st);
+      tok::tok_grad_finish_kernel<<<tiles, 256, 0, st>>>(a);
+    }
+    MMRCA_CUDA(cudaGetLastError());
+  }
+  {
+    LaunchScope ls("tok_x_image", st);
+    tok::tok_x_image_kernel<<<tiles, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x_q), L, tps, kq, static_cast<uint8_t*>(w.xq_img));
+    if (!self)
+      tok::tok_x_image_kernel<<<tiles, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x_kv), L, tps, kkv, static_cast<uint8_t*>(w.xkv_img));
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  // weight gradients
+  {
+    tok::WgradArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tiles = tiles;
+    if (self) {
+      a.seg[0] = {w.dq_img, grads->wq, dkq}; a.seg[1] = {w.dk_img, grads->wk, dkq}; a.seg[2] = {w.dv_img, grads->wv, dv};
+      a.x_img = w.xq_img; a.K = kq;
+      if ((rc = launch_tok_wgrad(a, 3, di.sms, st))) return rc;
+    } else {
+      a.seg[0] = {w.dq_img, grads->wq, dkq};
+      a.x_img = w.xq_img; a.K = kq;
+      if ((rc = launch_tok_wgrad(a, 1, di.sms, st))) return rc;
+      a.seg[0] = {w.dk_img, grads->wk, dkq}; a.seg[1] = {w.dv_img, grads->wv, dv};
+      a.x_img = w.xkv_img; a.K = kkv;
+      if ((rc = launch_tok_wgrad(a, 2, di.sms, st))) return rc;
+    }
+  }
+  // input gradients
+  if (d_x_q || d_x_kv) {
+    tok::DgradArgs a;
+    memset(&a, 0, sizeof(a));
+    a.L = L; a.tiles_per_sample = tps;
+    if (self) {
+      if (!d_x_q) return fail(MMRCA_ERR_INVALID, "self attention: the input gradient goes to d_x_q%s%s");
+      const int N = 2 * dkq + dv;
+      if ((rc = launch_tok_wprep_mn(p->wq, dkq, kq, N, 0, w.wmn_q, di.sms, st))) return rc;
+      if ((rc = launch_tok_wprep_mn(p->wk, dkq, kq, N, dkq, w.wmn_q, di.sms, st))) return rc;
+      if ((rc = launch_tok_wprep_mn(p->wv, dv, kq, N, 2 * dkq, w.wmn_q, di.sms, st))) return rc;
+      a.seg[0] = {w.dq_img, dkq, 0}; a.seg[1] = {w.dk_img, dkq, dkq}; a.seg[2] = {w.dv_img, dv, 2 * dkq}; a.nseg = 3;
+      a.wmn = w.wmn_q; a.Ntot = N; a.dx = d_x_q; a.K = kq;
+      if ((rc = launch_tok_dgrad(a, tiles, st))) return rc;
+    } else {
+      if (d_x_q) {
+        if ((rc = launch_tok_wprep_mn(p->wq, dkq, kq, dkq, 0, w.wmn_q, di.sms, st))) return rc;
+        a.seg[0] = {w.dq_img, dkq, 0}; a.nseg = 1;
+        a.wmn = w.wmn_q; a.Ntot = dkq; a.dx = d_x_q; a.K = kq;
+        if ((rc = launch_tok_dgrad(a, tiles, st))) return rc;
+      }
+      if (d_x_kv) {
+        if ((rc = launch_tok_wprep_mn(p->wk, dkq, kkv, dkq + dv, 0, w.wmn_kv, di.sms, st))) return rc;
+        if ((rc = launch_tok_wprep_mn(p->wv, dv, kkv, dkq + dv, dkq, w.wmn_kv, di.sms, st))) return rc;
+        a.seg[0] = {w.dk_img, dkq, 0}; a.seg[1] = {w.dv_img, dv, dkq}; a.nseg = 2;
+        a.wmn = w.wmn_kv; a.Ntot = dkq + dv; a.dx = d_x_kv; a.K = kkv;
+        if ((rc = launch_tok_dgrad(a, tiles, st))) return rc;
+      }
+    }
+  }
+  return MMRCA_OK;
 }
 
 size_t mmrca_fusion_workspace_bytes(const MmrcaFusionDesc* desc) {

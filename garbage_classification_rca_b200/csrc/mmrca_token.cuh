@@ -249,6 +249,8 @@ struct AttnArgs {
   const void* q_img; const void* k_img; const void* v_img;     // [B][tiles][cols/8 * kCS] operand images (tok_proj)
   const float* ln_g; const float* ln_b;
   float* out;               // [B][L][DV] fp32
+  void* p_out;              // training: the unnormalised attention weights, [B * tiles][op_bytes(256)] bf16 images (null: not kept)
+  float* sum_out;           // training: their row sums [B * tiles][128]
   int L, tiles_per_sample, reverse;
 };
 
@@ -389,6 +391,13 @@ __global__ void __launch_bounds__(256, 1) tok_attn_kernel(const AttnArgs a) {
   __syncthreads();
   tc_fence_after_sync();
   sum += part[(half ^ 1) * kTile + row].y;
+  if (a.p_out) {      // the backward's inputs (mmrca_token_bwd.cuh): P as it feeds the tensor core, and the row sums
+    if (tid == 32) {
+      bulk_s2g(static_cast<uint8_t*>(a.p_out) + (size_t(b) * tps + mt) * S::PB, sp, uint32_t(tps) * 16 * kCS);
+      bulk_commit();
+    }
+    if (half == 0) a.sum_out[(size_t(b) * tps + mt) * kTile + row] = sum;
+  }
   // ---- C = P V: A = P (K-major over the keys), B = V tiles read MN-major -----------------------------------------------------
   if (tid == 0) {
     for (int j = 0; j < tps; ++j)
@@ -440,6 +449,7 @@ __global__ void __launch_bounds__(256, 1) tok_attn_kernel(const AttnArgs a) {
       }
     }
   }
+  if (a.p_out && tid == 32) bulk_wait_all();
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);

@@ -1,0 +1,601 @@
+// Backward of the token-level attention blocks (mmrca_token.cuh): what loss.backward() does to SelfAttention.forward
+// (CVPR_code/multimodal_model.py:51-68) / ReverseCrossAttention.forward (:82-108) on [B, L, K] token sequences.
+//
+//   tok_attn_bwd     per (sample, 128-query tile), from the forward's operand images (Q, K, V), its unnormalised attention
+//                    weights P (bf16 image) and row sums: C = P V again (tensor core), LayerNorm + ReLU backward per row,
+//                    d(weights) = E V^T, softmax backward in place (P -> dS), dV = P^T E, dQ = dS K, dK = dS^T Q - five
+//                    tcgen05 chains, accumulators in TMEM.  dQ rows are the tile's own; dK / dV are per-query-tile partials.
+//   tok_grad_finish  sums the partials, applies 1/sqrt(d_kq) to dQ, emits the bf16 gradient IMAGES the two GEMMs below read
+//                    and the bias gradients (column sums).
+//   tok_x_image      token activations [B, L, K] bf16 -> per-(sample, tile) images (tokens contiguous per 8-column group)
+//   tok_wgrad        dW[N][K] += dQKV^T X: both operands MN-major over the token dimension, split-K over the token tiles
+//   tok_dgrad        dX[B, L, K] = dQKV [W_query; W_key; W_value]: A = the gradient images (K-major), B = the bf16 weights
+//                    in [K/8][N][8] order read MN-major
+#pragma once
+#include "mmrca_token.cuh"
+
+namespace mmrca {
+namespace tok {
+
+constexpr uint32_t kXGrp = kTile * 16;            // one 8-column group of an X image tile: 128 tokens x 16 bytes
+
+struct AttnBwdArgs {
+  const void* q_img; const void* k_img; const void* v_img;     // the forward's operand images
+  const void* p_img;        // [B * tiles][op_bytes(256)] unnormalised attention weights (forward, training)
+  const float* sum;         // [B * tiles][128] softmax row sums
+  const float* ln_g; const float* ln_b;
+  const float* d_out;       // [B][L][DV]
+  float* dq;                // [B][tiles * 128][DKQ]: d(loss)/d(scaled query image)
+  float* dk_part;           // [B][tiles (query tile)][tiles * 128][DKQ]
+  float* dv_part;           // [B][tiles (query tile)][tiles * 128][DV]
+  float* g_ln_g; float* g_ln_b;     // += (atomics)
+  int L, tiles_per_sample, reverse;
+};
+
+template <int DKQ, int DV>
+struct AttnBwdSmem {
+  static constexpr uint32_t QB = htc::op_bytes(DKQ), VB = htc::op_bytes(DV), PB = htc::op_bytes(kMaxTiles * kTile);
+  static constexpr uint32_t K = 0;                                           // kMaxTiles key tiles
+  static constexpr uint32_t VQ = htc::al128(K + kMaxTiles * QB);             // value tiles; later the query tile
+  static constexpr uint32_t VQ_BYTES = kMaxTiles * VB > QB ? kMaxTiles * VB : QB;
+  static constexpr uint32_t P = htc::al128(VQ + VQ_BYTES);                   // P, overwritten by dS
+  static constexpr uint32_t E = htc::al128(P + PB);                          // [128 x DV]: d(P_un V) rows, bf16
+  static constexpr uint32_t LN = htc::al128(E + VB);                         // gamma, beta
+  static constexpr uint32_t VSUM = LN + 2 * DV * 4;
+  static constexpr uint32_t ACC = VSUM + DV * 4;                             // d(gamma), d(beta), d(colsum V)
+  static constexpr uint32_t PART = ACC + 3 * DV * 4;
+  static constexpr uint32_t BAR = htc::al128(PART + 2 * kTile * 8);
+  static constexpr uint32_t BYTES = BAR + 64;
+  static_assert(BYTES <= 232448, "token attention backward does not fit shared memory");
+};
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4 u, float* v) {
+  v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+  v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+  v[4] = __uint_as_float(u.z << 16); v[5] = __uint_as_float(u.z & 0xffff0000u);
+  v[6] = __uint_as_float(u.w << 16); v[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+__device__ __forceinline__ void ld_chunks16(const uint8_t* op, int row, int col0, float (&v)[16]) {
+  unpack_bf16x8(*reinterpret_cast<const uint4*>(op + uint32_t(col0 >> 3) * kCS + row_off(row)), v);
+  unpack_bf16x8(*reinterpret_cast<const uint4*>(op + uint32_t((col0 >> 3) + 1) * kCS + row_off(row)), v + 8);
+}
+__device__ __forceinline__ float warp_sum32(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// 256 threads; thread (q = warp % 4, half = warp / 4, lane) owns row 32 q + lane of whatever the phase's rows are (queries
+// for the row phases, keys when the dK / dV accumulators are drained) and the column half `half`.
+template <int DKQ, int DV>
+__global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs a) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  using S = AttnBwdSmem<DKQ, DV>;
+  constexpr int HC = DV / 2, HQ = DKQ / 2;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::BAR);      // [0] loads, [1] MMAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  float* ln_s = reinterpret_cast<float*>(sm + S::LN);
+  float* vsum = reinterpret_cast<float*>(sm + S::VSUM);
+  float* acc_s = reinterpret_cast<float*>(sm + S::ACC);
+  float2* part = reinterpret_cast<float2*>(sm + S::PART);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, half = warp >> 2, row = 32 * q + lane;
+  const int tps = a.tiles_per_sample, L = a.L, ncols = tps * kTile;
+  const int b = blockIdx.x / tps, mt = blockIdx.x - b * tps;
+  const size_t tile_idx = size_t(b) * tps + mt;
+  uint8_t *sk = sm + S::K, *sv = sm + S::VQ, *sq = sm + S::VQ, *sp = sm + S::P, *se = sm + S::E;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(&bars[0], uint32_t(tps) * (S::QB + S::VB + 16 * kCS));
+    for (int j = 0; j < tps; ++j) {
+      bulk_g2s(sk + j * S::QB, static_cast<const uint8_t*>(a.k_img) + (size_t(b) * tps + j) * S::QB, S::QB, &bars[0]);
+      bulk_g2s(sv + j * S::VB, static_cast<const uint8_t*>(a.v_img) + (size_t(b) * tps + j) * S::VB, S::VB, &bars[0]);
+    }
+    bulk_g2s(sp, static_cast<const uint8_t*>(a.p_img) + tile_idx * S::PB, uint32_t(tps) * 16 * kCS, &bars[0]);
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  for (int i = tid; i < DV; i += 256) { ln_s[i] = a.ln_g[i]; ln_s[DV + i] = a.ln_b[i]; }
+  for (int i = tid; i < 3 * DV; i += 256) acc_s[i] = 0.f;
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_base = uint32_t(32 * q) << 16;
+  constexpr uint32_t COL_C = 0, COL_DV = 0, COL_DA = 192, COL_DQ = 0, COL_DK = 192;
+  const int t = mt * kTile + row;                 // my query token
+  const bool valid = t < L;
+  const int kpad0 = L - (tps - 1) * kTile;        // first pad row of the last key tile
+  const int qpad0 = min(kTile, L - mt * kTile);   // first pad row of my query tile
+  mbar_wait(&bars[0], 0);
+  tc_fence_after_sync();
+  // rows beyond the sample's L tokens were never written by the forward: they meet zero weights in the products below
+  // and must be finite
+  {
+    uint8_t* vlast = sv + (tps - 1) * S::VB;
+    for (int i = tid; i < (kTile - kpad0) * (DV / 8); i += 256) {
+      const int r = kpad0 + i / (DV / 8), g = i % (DV / 8);
+      *reinterpret_cast<uint4*>(vlast + uint32_t(g) * kCS + row_off(r)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    uint8_t* klast = sk + (tps - 1) * S::QB;
+    for (int i = tid; i < (kTile - kpad0) * (DKQ / 8); i += 256) {
+      const int r = kpad0 + i / (DKQ / 8), g = i % (DKQ / 8);
+      *reinterpret_cast<uint4*>(klast + uint32_t(g) * kCS + row_off(r)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    const int pg = ncols / 8;
+    for (int i = tid; i < (kTile - qpad0) * pg; i += 256) {
+      const int r = qpad0 + i / pg, g = i % pg;
+      *reinterpret_cast<uint4*>(sp + uint32_t(g) * kCS + row_off(r)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (a.reverse && tid < DV) {
+      float acc0 = 0.f, acc1 = 0.f;
+      for (int j = 0; j < L; j += 2) {
+        const uint8_t* v0 = sv + (j >> 7) * S::VB + uint32_t(tid >> 3) * kCS + row_off(j & 127) + (tid & 7) * 2;
+        acc0 += __uint_as_float(uint32_t(*reinterpret_cast<const uint16_t*>(v0)) << 16);
+        if (j + 1 < L) {
+          const uint8_t* v1 = sv + ((j + 1) >> 7) * S::VB + uint32_t(tid >> 3) * kCS + row_off((j + 1) & 127) + (tid & 7) * 2;
+          acc1 += __uint_as_float(uint32_t(*reinterpret_cast<const uint16_t*>(v1)) << 16);
+        }
+      }
+      vsum[tid] = acc0 + acc1;
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  // ---- C = P V, as the forward did -----------------------------------------------------------------------------------------
+  if (tid == 0) {
+    for (int j = 0; j < tps; ++j)
+      htc::mma_steps(tmem + COL_C, make_smem_desc(smem_u32(sp + uint32_t(16 * j) * kCS), kCS, kRS), 2 * kCS,
+                     make_smem_desc(smem_u32(sv + j * S::VB), kRS, kCS), 2 * kRS, make_idesc_bf16(128, DV, 0, 1), 8, j > 0);
+    umma_commit(&bars[1]);
+  }
+  const float sum = valid ? a.sum[tile_idx * kTile + row] : 1.0f;
+  const float inv = valid ? 1.0f / sum : 0.f, rinv = 1.0f / float(L - 1);
+  float dy[HC];                                      // d(out) of my columns, then d(pre-LayerNorm context)
+  if (valid) {
+    const float* src = a.d_out + (size_t(b) * L + t) * DV + HC * half;
+#pragma unroll
+    for (int e = 0; e < HC; e += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + e));
+      dy[e] = v.x; dy[e + 1] = v.y; dy[e + 2] = v.z; dy[e + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < HC; ++e) dy[e] = 0.f;
+  }
+  mbar_wait(&bars[1], 0);
+  tc_fence_after_sync();
+  // ---- LayerNorm + ReLU backward of my row (:65-66, :105-106) -> E = d(P_un V) = d(context) / sum (reverse: * -1/(L-1)) ------
+  {
+    float x[HC];
+    {
+      uint32_t raw[HC];
+      const uint32_t tc_ = tmem + lane_base + COL_C + HC * half;
+#pragma unroll
+      for (int j = 0; j < HC / 8; ++j) tmem_ld8_nw(tc_ + 8 * j, *reinterpret_cast<uint32_t(*)[8]>(&raw[8 * j]));
+      tmem_wait_ld();
+#pragma unroll
+      for (int e = 0; e < HC; ++e) {
+        const float cun = __uint_as_float(raw[e]) * inv;
+        x[e] = a.reverse ? (vsum[HC * half + e] - cun) * rinv : cun;
+      }
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < HC; ++e) { s1 += x[e]; s2 = fmaf(x[e], x[e], s2); }
+    part[half * kTile + row] = make_float2(s1, s2);
+    __syncthreads();
+    const float2 o = part[(half ^ 1) * kTile + row];
+    const float mean = (s1 + o.x) * (1.0f / float(DV));
+    const float rstd = rsqrtf(fmaxf((s2 + o.y) * (1.0f / float(DV)) - mean * mean, 0.f) + kLnEps);
+    const float* gam = ln_s + HC * half;
+    const float* bet = ln_s + DV + HC * half;
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < HC; ++e) {
+      const float xh = (x[e] - mean) * rstd;
+      const float g = fmaf(xh, gam[e], bet[e]) > 0.f ? dy[e] : 0.f;      // ReLU gate
+      // column sums over the tile's rows: d(gamma), d(beta)
+      const float cg = warp_sum32(g * xh), cb = warp_sum32(g);
+      if (lane == 0) { atomicAdd(&acc_s[HC * half + e], cg); atomicAdd(&acc_s[DV + HC * half + e], cb); }
+      const float dxh = g * gam[e];
+      t1 += dxh;
+      t2 = fmaf(dxh, xh, t2);
+      x[e] = xh;
+      dy[e] = dxh;
+    }
+    __syncthreads();
+    part[half * kTile + row] = make_float2(t1, t2);
+    __syncthreads();
+    const float2 o2 = part[(half ^ 1) * kTile + row];
+    const float m1 = (t1 + o2.x) * (1.0f / float(DV)), m2 = (t2 + o2.y) * (1.0f / float(DV));
+    const float esc = a.reverse ? -inv * rinv : inv;
+#pragma unroll
+    for (int g8 = 0; g8 < HC / 8; ++g8) {
+      float ev[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = 8 * g8 + e;
+        const float dx = valid ? rstd * (dy[c] - m1 - x[c] * m2) : 0.f;      // d(loss)/d(context row before the LayerNorm)
+        if (a.reverse) {
+          const float cs = warp_sum32(dx * rinv);                            // d(colsum V)
+          if (lane == 0) atomicAdd(&acc_s[2 * DV + HC * half + c], cs);
+        }
+        ev[e] = dx * esc;
+      }
+      *reinterpret_cast<uint4*>(se + uint32_t((HC / 8) * half + g8) * kCS + row_off(row)) = pack_bf16x8(ev);
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  // ---- d(weights) = E V^T (per key tile, N = 128) and dV = P^T E (per key tile, M = 128 keys) ------------------------------------
+  if (tid == 0) {
+    for (int j = 0; j < tps; ++j)
+      htc::mma_steps(tmem + COL_DA + 128 * j, make_smem_desc(smem_u32(se), kCS, kRS), 2 * kCS,
+                     make_smem_desc(smem_u32(sv + j * S::VB), kCS, kRS), 2 * kCS, make_idesc_bf16(128, 128, 0, 0), DV / 16, false);
+    for (int j = 0; j < tps; ++j)
+      htc::mma_steps(tmem + COL_DV + DV * j, make_smem_desc(smem_u32(sp + uint32_t(16 * j) * kCS), kRS, kCS), 2 * kRS,
+                     make_smem_desc(smem_u32(se), kRS, kCS), 2 * kRS, make_idesc_bf16(128, DV, 1, 1), 8, false);
+    umma_commit(&bars[1]);
+  }
+  mbar_wait(&bars[1], 1);
+  tc_fence_after_sync();
+  // the value tiles are dead: the query tile takes their place
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bars[0], S::QB);
+    bulk_g2s(sq, static_cast<const uint8_t*>(a.q_img) + tile_idx * S::QB, S::QB, &bars[0]);
+  }
+  // ---- softmax backward in place: dS = P_un (dA' - dot / sum), dot = sum_j dA'_j P_un_j (dA' = dA / sum: E carries 1/sum) -----
+  {
+    const uint32_t ta = tmem + lane_base + COL_DA;
+    const int nchunks = ncols / 16;
+    float dot = 0.f;
+    {
+      uint32_t nx[16];
+      tmem_ld16_nw(ta + 16 * half, nx);
+#pragma unroll 1
+      for (int ch = half; ch < nchunks; ch += 2) {
+        float p[16];
+        ld_chunks16(sp, row, 16 * ch, p);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) dot = fmaf(__uint_as_float(nx[e]), p[e], dot);
+        if (ch + 2 < nchunks) tmem_ld16_nw(ta + 16 * (ch + 2), nx);
+      }
+    }
+    part[half * kTile + row].x = dot;
+    __syncthreads();
+    dot = (dot + part[(half ^ 1) * kTile + row].x) * inv;
+    {
+      uint32_t nx[16];
+      tmem_ld16_nw(ta + 16 * half, nx);
+#pragma unroll 1
+      for (int ch = half; ch < nchunks; ch += 2) {
+        float p[16];
+        ld_chunks16(sp, row, 16 * ch, p);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) p[e] *= __uint_as_float(nx[e]) - dot;
+        if (ch + 2 < nchunks) tmem_ld16_nw(ta + 16 * (ch + 2), nx);
+        htc::st_chunks16(sp, row, 16 * ch, p);
+      }
+    }
+  }
+  // ---- drain dV: my row is KEY 128 j + row of key tile j ------------------------------------------------------------------------
+  for (int j = 0; j < tps; ++j) {
+    uint32_t raw[HC];
+    const uint32_t tv = tmem + lane_base + COL_DV + DV * j + HC * half;
+#pragma unroll
+    for (int g = 0; g < HC / 8; ++g) tmem_ld8_nw(tv + 8 * g, *reinterpret_cast<uint32_t(*)[8]>(&raw[8 * g]));
+    tmem_wait_ld();
+    const int key = j * kTile + row;
+    const bool add_t = a.reverse && key < L;        // every valid key's value row feeds colsum(V)
+    float* dst = a.dv_part + ((size_t(b) * tps + mt) * ncols + key) * DV + HC * half;
+#pragma unroll
+    for (int e = 0; e < HC; e += 4) {
+      float4 v = make_float4(__uint_as_float(raw[e]), __uint_as_float(raw[e + 1]), __uint_as_float(raw[e + 2]), __uint_as_float(raw[e + 3]));
+      if (add_t) {
+        const float* tv_ = acc_s + 2 * DV + HC * half + e;
+        v.x += tv_[0]; v.y += tv_[1]; v.z += tv_[2]; v.w += tv_[3];
+      }
+      *reinterpret_cast<float4*>(dst + e) = v;
+    }
+  }
+  mbar_wait(&bars[0], 1);                           // the query tile has landed
+  for (int i = tid; i < (kTile - qpad0) * (DKQ / 8); i += 256) {
+    const int r = qpad0 + i / (DKQ / 8), g = i % (DKQ / 8);
+    *reinterpret_cast<uint4*>(sq + uint32_t(g) * kCS + row_off(r)) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  fence_proxy_async();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  // ---- dQ = dS K (accumulated over the key tiles), dK = dS^T Q (per key tile) ------------------------------------------------------
+  if (tid == 0) {
+    for (int j = 0; j < tps; ++j)
+      htc::mma_steps(tmem + COL_DQ, make_smem_desc(smem_u32(sp + uint32_t(16 * j) * kCS), kCS, kRS), 2 * kCS,
+                     make_smem_desc(smem_u32(sk + j * S::QB), kRS, kCS), 2 * kRS, make_idesc_bf16(128, DKQ, 0, 1), 8, j > 0);
+    for (int j = 0; j < tps; ++j)
+      htc::mma_steps(tmem + COL_DK + DKQ * j, make_smem_desc(smem_u32(sp + uint32_t(16 * j) * kCS), kRS, kCS), 2 * kRS,
+                     make_smem_desc(smem_u32(sq), kRS, kCS), 2 * kRS, make_idesc_bf16(128, DKQ, 1, 1), 8, false);
+    umma_commit(&bars[1]);
+  }
+  // LayerNorm-affine gradients of this tile
+  if (tid < DV) {
+    atomicAdd(a.g_ln_g + tid, acc_s[tid]);
+    atomicAdd(a.g_ln_b + tid, acc_s[DV + tid]);
+  }
+  mbar_wait(&bars[1], 0);
+  tc_fence_after_sync();
+  {
+    float* dst = a.dq + (size_t(b) * ncols + t) * DKQ + HQ * half;
+    const uint32_t tq = tmem + lane_base + COL_DQ + HQ * half;
+#pragma unroll 1
+    for (int c0 = 0; c0 < HQ; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16_nw(tq + c0, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) *reinterpret_cast<uint4*>(dst + c0 + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+    }
+  }
+  for (int j = 0; j < tps; ++j) {
+    float* dst = a.dk_part + ((size_t(b) * tps + mt) * ncols + j * kTile + row) * DKQ + HQ * half;
+    const uint32_t tk = tmem + lane_base + COL_DK + DKQ * j + HQ * half;
+#pragma unroll 1
+    for (int c0 = 0; c0 < HQ; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16_nw(tk + c0, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) *reinterpret_cast<uint4*>(dst + c0 + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---- partial sums -> bf16 gradient images + bias gradients ---------------------------------------------------------------------
+struct GradFinishArgs {
+  const float* dq; const float* dk_part; const float* dv_part;
+  void* dq_img; void* dk_img; void* dv_img;        // [B * tiles][op_bytes(cols)], rows beyond L zero
+  float* g_bq; float* g_bk; float* g_bv;           // += column sums
+  float qscale;
+  int L, tiles_per_sample, dkq, dv;
+};
+__global__ void __launch_bounds__(256) tok_grad_finish_kernel(const GradFinishArgs a) {
+  __shared__ float cs[2 * 128 + 96];
+  const int tid = threadIdx.x, tps = a.tiles_per_sample, ncols = tps * kTile;
+  const int b = blockIdx.x / tps, j = blockIdx.x - b * tps;
+  const int ntot = 2 * a.dkq + a.dv;
+  for (int i = tid; i < ntot; i += 256) cs[i] = 0.f;
+  __syncthreads();
+  for (int seg = 0; seg < 3; ++seg) {
+    const int cols = seg == 2 ? a.dv : a.dkq, G = cols / 8, off = seg == 0 ? 0 : (seg == 1 ? a.dkq : 2 * a.dkq);
+    const float* src = seg == 0 ? a.dq : (seg == 1 ? a.dk_part : a.dv_part);
+    uint8_t* img = static_cast<uint8_t*>(seg == 0 ? a.dq_img : (seg == 1 ? a.dk_img : a.dv_img)) + size_t(blockIdx.x) * (size_t(G) * kCS);
+    const int nparts = seg == 0 ? 1 : tps;
+    const float sc = seg == 0 ? a.qscale : 1.0f;
+    for (int idx = tid; idx < kTile * G; idx += 256) {
+      const int r = idx / G, g = idx - r * G, t = j * kTile + r;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      if (t < a.L) {
+        for (int m = 0; m < nparts; ++m) {
+          const float* p = src + ((size_t(b) * nparts + m) * ncols + t) * cols + 8 * g;
+          const float4 v0 = __ldg(reinterpret_cast<const float4*>(p)), v1 = __ldg(reinterpret_cast<const float4*>(p + 4));
+          v[0] += v0.x; v[1] += v0.y; v[2] += v0.z; v[3] += v0.w; v[4] += v1.x; v[5] += v1.y; v[6] += v1.z; v[7] += v1.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { v[e] *= sc; atomicAdd(&cs[off + 8 * g + e], v[e]); }
+      }
+      *reinterpret_cast<uint4*>(img + uint32_t(g) * kCS + row_off(r)) = pack_bf16x8(v);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < ntot; i += 256) {
+    float* dst = i < a.dkq ? a.g_bq + i : (i < 2 * a.dkq ? a.g_bk + (i - a.dkq) : a.g_bv + (i - 2 * a.dkq));
+    atomicAdd(dst, cs[i]);
+  }
+}
+
+// x [B][L][K] bf16 -> [B * tiles][K / 8][128 tokens][8], rows beyond L zero
+__global__ void __launch_bounds__(256) tok_x_image_kernel(const __nv_bfloat16* __restrict__ x, int L, int tps, int K,
+                                                          uint8_t* __restrict__ img) {
+  const int b = blockIdx.x / tps, j = blockIdx.x - b * tps, G = K / 8;
+  for (int idx = threadIdx.x; idx < kTile * G; idx += 256) {
+    const int r = idx / G, g = idx - r * G, t = j * kTile + r;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (t < L) v = __ldg(reinterpret_cast<const uint4*>(x + (size_t(b) * L + t) * K + 8 * g));
+    *reinterpret_cast<uint4*>(img + (size_t(blockIdx.x) * G + g) * kXGrp + uint32_t(r) * 16) = v;
+  }
+}
+
+// W [n_rows][K] fp32 (rows n0 .. of the stacked [W_query; W_key; W_value]) -> bf16 [K / 8][N][8]: the dgrad GEMM's B operand
+__global__ void __launch_bounds__(256) tok_wprep_mn_kernel(const float* __restrict__ w, int n_rows, int K, int N, int n0,
+                                                           uint8_t* __restrict__ blob) {
+  const int G = K / 8;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < (long long)n_rows * G; i += (long long)gridDim.x * 256) {
+    const int n = int(i / G), g = int(i - (long long)n * G);
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(w + (size_t)n * K + 8 * g));
+    const float4 v1 = __ldg(reinterpret_cast<const float4*>(w + (size_t)n * K + 8 * g + 4));
+    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    *reinterpret_cast<uint4*>(blob + ((size_t)g * N + n0 + n) * 16) = pack_bf16x8(v);
+  }
+}
+
+// ---- weight gradients ---------------------------------------------------------------------------------------------------------------
+constexpr int kGradThreads = 192;                 // producer warp, MMA warp, 4 epilogue warps
+constexpr int kGradStages = 2;
+constexpr uint32_t kGradABytes = htc::op_bytes(128);      // 33 024
+constexpr uint32_t kGradBBytes = 32 * kXGrp;              // 256 columns x 128 tokens: 64 KB
+struct GradSmem {
+  static constexpr uint32_t A = 0, B = htc::al128(A + kGradStages * kGradABytes), BAR = B + kGradStages * kGradBBytes, BYTES = BAR + 128;
+  static_assert(BYTES <= 232448, "token gradient GEMMs do not fit shared memory");
+};
+struct WgradSeg { const void* img; float* g_w; int cols; };      // gradient image [tiles][op_bytes(cols)]; dW [cols][K] +=
+struct WgradArgs { WgradSeg seg[3]; const void* x_img; int K, tiles; };
+
+// grid = (ceil(K / 256), segments, splits of the token tiles); D[m = gradient column][n = X column] over k = token
+__global__ void __launch_bounds__(kGradThreads, 1) tok_wgrad_kernel(const WgradArgs a) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  using S = GradSmem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + S::BAR);
+  uint64_t* empty = full + kGradStages;
+  uint64_t* accb = empty + kGradStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accb + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const WgradSeg sg = a.seg[blockIdx.y];
+  const int nt = blockIdx.x, G = a.K / 8, gb = min(32, G - nt * 32), bn = gb * 8;
+  const int t0 = int((long long)a.tiles * blockIdx.z / gridDim.z), t1 = int((long long)a.tiles * (blockIdx.z + 1) / gridDim.z);
+  const int n_it = t1 - t0;
+  if (n_it <= 0) return;
+  const uint32_t a_bytes = htc::op_bytes(sg.cols), b_bytes = uint32_t(gb) * kXGrp;
+  if (tid == 0) {
+    for (int i = 0; i < 2 * kGradStages + 1; ++i) mbar_init(&full[i], 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint8_t* pa = static_cast<const uint8_t*>(sg.img);
+      const uint8_t* pb = static_cast<const uint8_t*>(a.x_img) + size_t(nt) * 32 * kXGrp;
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % kGradStages;
+        if (it >= kGradStages) mbar_wait(&empty[s], uint32_t(it / kGradStages - 1) & 1u);
+        mbar_arrive_expect_tx(&full[s], a_bytes + b_bytes);
+        bulk_g2s(sm + S::A + s * kGradABytes, pa + size_t(t0 + it) * a_bytes, a_bytes, &full[s]);
+        bulk_g2s(sm + S::B + s * kGradBBytes, pb + size_t(t0 + it) * G * kXGrp, b_bytes, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, bn, 1, 1);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % kGradStages;
+        mbar_wait(&full[s], uint32_t(it / kGradStages) & 1u);
+        tc_fence_after_sync();
+        const uint64_t ad = make_smem_desc(smem_u32(sm + S::A + s * kGradABytes), kRS, kCS);
+        const uint64_t bd = make_smem_desc(smem_u32(sm + S::B + s * kGradBBytes), 128, kXGrp);
+#pragma unroll
+        for (int ks = 0; ks < kTile / 16; ++ks)
+          umma_bf16(tmem, desc_advance(ad, ks * 2 * kRS), desc_advance(bd, ks * 256), idesc, (it | ks) ? 1u : 0u);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(accb);
+    }
+  } else {
+    const int q = warp & 3, row = 32 * q + lane;
+    float* dst = sg.g_w + size_t(row) * a.K + nt * 256;
+    mbar_wait(accb, 0);
+    tc_fence_after_sync();
+#pragma unroll 1
+    for (int c0 = 0; c0 < bn; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16_nw(tmem + (uint32_t(32 * q) << 16) + c0, r);
+      tmem_wait_ld();
+      if (row < sg.cols) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) atomicAdd(dst + c0 + e, __uint_as_float(r[e]));
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+// ---- input gradients ------------------------------------------------------------------------------------------------------------------
+struct DgradSeg { const void* img; int cols; int woff; };      // gradient image; rows [woff, woff + cols) of the stacked weight
+struct DgradArgs {
+  DgradSeg seg[3]; int nseg;
+  const void* wmn;          // bf16 [K / 8][Ntot][8] (tok_wprep_mn_kernel)
+  int Ntot;
+  float* dx;                // [B][L][K]
+  int L, tiles_per_sample, K;
+};
+// grid = (B * tiles, ceil(K / 256)); one pipeline stage per segment (K dimension = the segment's gradient columns)
+__global__ void __launch_bounds__(kGradThreads, 1) tok_dgrad_kernel(const DgradArgs a) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  using S = GradSmem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + S::BAR);
+  uint64_t* empty = full + kGradStages;
+  uint64_t* accb = empty + kGradStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accb + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x, nt = blockIdx.y, G = a.K / 8, gb = min(32, G - nt * 32), bn = gb * 8;
+  if (tid == 0) {
+    for (int i = 0; i < 2 * kGradStages + 1; ++i) mbar_init(&full[i], 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < a.nseg; ++it) {
+        const DgradSeg sg = a.seg[it];
+        const int s = it % kGradStages;
+        if (it >= kGradStages) mbar_wait(&empty[s], uint32_t(it / kGradStages - 1) & 1u);
+        const uint32_t a_bytes = htc::op_bytes(sg.cols), col_bytes = uint32_t(sg.cols) * 16;
+        mbar_arrive_expect_tx(&full[s], a_bytes + uint32_t(gb) * col_bytes);
+        bulk_g2s(sm + S::A + s * kGradABytes, static_cast<const uint8_t*>(sg.img) + size_t(tile) * a_bytes, a_bytes, &full[s]);
+        const uint8_t* pb = static_cast<const uint8_t*>(a.wmn) + (size_t(nt) * 32 * a.Ntot + sg.woff) * 16;
+#pragma unroll 1
+        for (int g = 0; g < gb; ++g)
+          bulk_g2s(sm + S::B + s * kGradBBytes + uint32_t(g) * col_bytes, pb + size_t(g) * a.Ntot * 16, col_bytes, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, bn, 0, 1);
+      for (int it = 0; it < a.nseg; ++it) {
+        const DgradSeg sg = a.seg[it];
+        const int s = it % kGradStages;
+        mbar_wait(&full[s], uint32_t(it / kGradStages) & 1u);
+        tc_fence_after_sync();
+        const uint64_t ad = make_smem_desc(smem_u32(sm + S::A + s * kGradABytes), kCS, kRS);
+        const uint64_t bd = make_smem_desc(smem_u32(sm + S::B + s * kGradBBytes), 128, uint32_t(sg.cols) * 16);
+        for (int ks = 0; ks < sg.cols / 16; ++ks)
+          umma_bf16(tmem, desc_advance(ad, ks * 2 * kCS), desc_advance(bd, ks * 256), idesc, (it | ks) ? 1u : 0u);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(accb);
+    }
+  } else {
+    const int q = warp & 3, row = 32 * q + lane;
+    const int b = tile / a.tiles_per_sample, t = (tile - b * a.tiles_per_sample) * kTile + row;
+    float* dst = a.dx + (size_t(b) * a.L + t) * a.K + nt * 256;
+    mbar_wait(accb, 0);
+    tc_fence_after_sync();
+#pragma unroll 1
+    for (int c0 = 0; c0 < bn; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16_nw(tmem + (uint32_t(32 * q) << 16) + c0, r);
+      tmem_wait_ld();
+      if (t < a.L) {
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) *reinterpret_cast<uint4*>(dst + c0 + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace tok
+}  // namespace mmrca

@@ -749,16 +749,48 @@ class FusionTrainStep:
 # ---------------------------------------------------------------------------------------------------------
 # Token-level attention blocks (BASELINE.json configs[4]): SelfAttention / ReverseCrossAttention on [B, L, d_in], L <= 256
 # ---------------------------------------------------------------------------------------------------------
+class _TokenFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, block, x_q, x_kv, *params):
+        ctx.block = block
+        ctx.dtypes = (x_q.dtype, x_kv.dtype if x_kv is not None else None)
+        out = block(x_q, x_kv)
+        ctx.serial = block._serial = getattr(block, "_serial", 0) + 1
+        return out.clone()
+
+    @staticmethod
+    def backward(ctx, d_out):
+        block = ctx.block
+        if block._serial != ctx.serial:
+            raise RuntimeError("TokenAttention: the workspace was reused by a later forward before this backward ran")
+        grads = [torch.zeros_like(p) for p in block.params]
+        need_q, need_kv = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        dxq, dxkv = block.backward(d_out, grads, need_q, need_kv)
+        if dxq is not None and not need_q:
+            dxq = None
+        if dxq is not None and ctx.dtypes[0] != torch.float32:
+            dxq = dxq.to(ctx.dtypes[0])
+        if dxkv is not None and ctx.dtypes[1] != torch.float32:
+            dxkv = dxkv.to(ctx.dtypes[1])
+        pg = [g if ctx.needs_input_grad[3 + i] else None for i, g in enumerate(grads)]
+        return (None, dxq, dxkv, *pg)
+
+
 class TokenAttention:
     """SelfAttention.forward (reference multimodal_model.py:51-68) / ReverseCrossAttention.forward (:82-108) on real token
     sequences (ViT-L/16: [B, 197, 1024]; RoBERTa: [B, 256, 768]; the blocks' own outputs [B, L, 96]) through the bf16
-    tensor-core path: a TMA-fed tcgen05 projection GEMM + one attention kernel per (sample, 128-query tile).  Forward
-    only.  Activations are bf16 (fp32 inputs are cast at the hand-off); parameters fp32 (W_query.weight, W_query.bias,
+    tensor-core path: a TMA-fed tcgen05 projection GEMM + one attention kernel per (sample, 128-query tile).
+    Activations are bf16 (fp32 inputs are cast at the hand-off); parameters fp32 (W_query.weight, W_query.bias,
     W_key.weight, W_key.bias, W_value.weight, W_value.bias, norm.weight, norm.bias); output fp32 [B, L, d_v].
-    Persistent workspace: build once per (batch, L, widths), call many times."""
+    Persistent workspace: build once per (batch, L, widths), call many times.  training=True keeps the attention weights
+    for backward() (the five-GEMM attention backward + weight / input gradient GEMMs, all tcgen05), and apply() runs the
+    block under torch.autograd."""
 
     def __init__(self, params: Sequence[torch.Tensor], batch: int, seq_len: int, *, d_in_kv: Optional[int] = None,
-                 reverse: bool = False):
+                 reverse: bool = False, training: bool = False):
+        self.param_tensors = list(params)
+        self.training = training
+        self._saved = None
         self.params = [_check_dev(p.detach(), "attention parameter") for p in params]
         dev = self.params[0].device
         d_kq, d_in_q = self.params[0].shape
@@ -766,7 +798,7 @@ class TokenAttention:
         kkv = self.params[2].shape[1]
         if d_in_kv is not None and d_in_kv != kkv:
             raise ValueError("d_in_kv does not match W_key")
-        self.desc = N.TokenDesc(batch, seq_len, d_in_q, kkv, d_kq, d_v, 1 if reverse else 0, 0)
+        self.desc = N.TokenDesc(batch, seq_len, d_in_q, kkv, d_kq, d_v, 1 if reverse else 0, N.TOKEN_TRAINING if training else 0)
         self.ap = _attn_struct(self.params)
         nbytes = N.lib().mmrca_token_attention_workspace_bytes(C.byref(self.desc))
         if nbytes == 0:
@@ -794,7 +826,42 @@ class TokenAttention:
                 self.out.data_ptr(), self.ws.data_ptr(), self.ws.numel(), _stream_ptr(self.device)),
                 "mmrca_token_attention_forward")
         self.desc.flags |= N.TOKEN_WEIGHTS_READY      # the bf16 weights now sit in the workspace
+        self._saved = (xs[0], xs[1])
         return self.out
+
+    def backward(self, d_out: torch.Tensor, grads: Sequence[torch.Tensor], need_dx_q: bool = False,
+                 need_dx_kv: bool = False) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+        """Accumulates the parameter gradients into `grads` (eight fp32 tensors shaped like the parameters) and returns
+        (d_x_q, d_x_kv) (fp32, None where not asked for; self attention: d_x_q is the whole input gradient).  Must
+        follow the forward call it differentiates: it reads the workspace that call left."""
+        if not self.training or self._saved is None:
+            raise RuntimeError("TokenAttention.backward needs training=True and a preceding forward call")
+        d = self.desc
+        xq, xkv = self._saved
+        self_attn = xkv is None
+        d_out = _check_dev(d_out, "d_out").to(torch.float32).contiguous()
+        if tuple(d_out.shape) != (d.batch, d.seq_len, d.d_v):
+            raise ValueError(f"d_out has shape {tuple(d_out.shape)}, expected {(d.batch, d.seq_len, d.d_v)}")
+        for g, p_ in zip(grads, self.params):
+            if g.dtype != torch.float32 or g.shape != p_.shape or not g.is_contiguous() or g.device != self.device:
+                raise ValueError("gradient buffers must be contiguous fp32 tensors shaped like the parameters")
+        ag = _attn_struct(list(grads))
+        dxq = torch.empty(d.batch, d.seq_len, d.d_in_q, dtype=torch.float32, device=self.device) \
+            if (need_dx_q or (self_attn and need_dx_kv)) else None
+        dxkv = torch.empty(d.batch, d.seq_len, d.d_in_kv, dtype=torch.float32, device=self.device) \
+            if (need_dx_kv and not self_attn) else None
+        with torch.cuda.device(self.device):
+            N.check(N.lib().mmrca_token_attention_backward(
+                C.byref(self.desc), C.byref(self.ap), xq.data_ptr(), xkv.data_ptr() if xkv is not None else None,
+                d_out.data_ptr(), C.byref(ag), dxq.data_ptr() if dxq is not None else None,
+                dxkv.data_ptr() if dxkv is not None else None, self.ws.data_ptr(), self.ws.numel(),
+                _stream_ptr(self.device)), "mmrca_token_attention_backward")
+        return dxq, dxkv
+
+    def apply(self, x_q: torch.Tensor, x_kv: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The block under torch.autograd: gradients flow to the parameter tensors this object was built from and to
+        x_q / x_kv.  (One live graph per object: the backward reads the workspace of the latest forward.)"""
+        return _TokenFunction.apply(self, x_q, x_kv, *self.param_tensors)
 
     def refresh_weights(self) -> None:
         """Call after the parameters changed (optimizer step, load_state_dict): the next call converts them again."""

@@ -271,11 +271,13 @@ int mmrca_hier_train_step(const MmrcaHierDesc* desc, const MmrcaHierParams* para
  * ReverseCrossAttention.forward (:82-108) on real token sequences x [B, L, d_in] with 2 <= L <= 256 (ViT-L/16: 197 x 1024,
  * RoBERTa: 256 x 768) instead of the head's 16 pseudo-tokens.  Square attention like the reference (:93): x_q and x_kv share L.
  * bf16 tensor-core path (2e-2 absolute contract): the Q | K | V projection is a TMA-fed tcgen05 GEMM over the tokens, the
- * attention core one kernel per (sample, 128-query tile).  Forward only (inference / frozen blocks).
+ * attention core one kernel per (sample, 128-query tile).
  *   x_q, x_kv: bf16 [B, L, d_in_q] / [B, L, d_in_kv], 16-byte aligned; x_kv == NULL or == x_q: self attention.
  *   (d_kq, d_v) in {(128, 96), (64, 48)}; p: fp32 parameters in torch.nn.Linear layout; out: fp32 [B, L, d_v]. ---- */
 #define MMRCA_TOKEN_WEIGHTS_READY 1u /* the workspace already holds this block's bf16 weights (an earlier call with the same,
                                        unchanged parameters on the same workspace): skip their conversion */
+#define MMRCA_TOKEN_TRAINING 2u      /* the forward keeps the attention weights for mmrca_token_attention_backward (larger
+                                       workspace; set on the descriptor of the workspace query, forward and backward) */
 typedef struct MmrcaTokenDesc {
   int32_t batch, seq_len, d_in_q, d_in_kv, d_kq, d_v;
   int32_t reverse;    /* (1 - A) / (L - 1) weights (:95-99) */
@@ -284,6 +286,14 @@ typedef struct MmrcaTokenDesc {
 size_t mmrca_token_attention_workspace_bytes(const MmrcaTokenDesc* desc);
 int mmrca_token_attention_forward(const MmrcaTokenDesc* desc, const MmrcaAttnParams* p, const void* x_q, const void* x_kv,
                                   float* out, void* workspace, size_t workspace_bytes, void* stream);
+/* Backward of the block (what loss.backward() does to SelfAttention.forward / ReverseCrossAttention.forward, multimodal_model.py:51-68,
+ * :82-108): needs the unmodified workspace of the MMRCA_TOKEN_TRAINING forward and the same x_q / x_kv.
+ *   d_out: fp32 [B, L, d_v];  grads: accumulated into (+=, device atomics);  d_x_q / d_x_kv: fp32 [B, L, d_in], WRITTEN
+ *   (NULL to skip; self attention: d_x_q receives the sum over the three projections, d_x_kv must be NULL).
+ *   d_in a multiple of 16.  bf16 operands, fp32 accumulation. */
+int mmrca_token_attention_backward(const MmrcaTokenDesc* desc, const MmrcaAttnParams* p, const void* x_q, const void* x_kv,
+                                   const float* d_out, const MmrcaAttnGrads* grads, float* d_x_q, float* d_x_kv,
+                                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- Classic / Normalized late-fusion heads (--late_fusion=classic | normalized): everything after the backbones in
  * EffV2MediumAndDistilbertClassic / ...Normalized.forward (multimodal_model.py:489-579) - the image and text projections

@@ -87,3 +87,110 @@ def test_token_attention_rejects_what_it_does_not_cover(pkg):
         blk(torch.zeros(2, 33, 64).cuda())                                       # shape mismatch
     with pytest.raises(RuntimeError):
         blk(torch.zeros(2, 32, 64))                                              # no CPU fallback
+
+
+# ---- backward (mmrca_token_attention_backward) ---------------------------------------------------------------------------
+def _oracle_grads(fn, xs, p, prefix, d_out):
+    """float64 autograd through the oracle restatement: gradients of sum(out * d_out) w.r.t. the parameters and inputs."""
+    p64 = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    xs64 = [x.double().requires_grad_(True) for x in xs]
+    out = fn(*xs64, p64, prefix)
+    (out * d_out.double()).sum().backward()
+    return {k: v.grad for k, v in p64.items()}, [x.grad for x in xs64], out.detach()
+
+
+def _rel(a, ref):
+    return ((a.double().cpu() - ref).norm() / ref.norm().clamp_min(1e-30)).item()
+
+
+# bf16 operands, fp32 accumulation, float64 oracle: per-tensor relative L2 error of the gradients (measured 4e-4 .. 1e-2,
+# tools/diag_token_bwd.py).  The blocks end in a ReLU: an output within the bf16 forward error of zero can sit on the other
+# side of the kink in the product than in the float64 oracle, and each such element moves a whole d_out entry in or out
+# of the gradient (5e-2 .. 2e-1 relative on these small random problems - a property of comparing across precisions at
+# a kink, not of the backward).  The tests therefore zero d_out where EITHER forward has the gate closed, so both
+# backward passes run with the same gates - closed gates are still exercised, the coin flips at the kink are not.
+TOK_GRAD_LIMIT = 2e-2
+
+
+def _gate_mask(out_product, out_oracle):
+    return ((out_product.cpu() > 0) & (out_oracle > 0)).float()
+
+
+@pytest.mark.parametrize("B,L,K", [(3, 197, 1024), (2, 256, 768), (4, 16, 96), (1, 77, 208), (2, 129, 1024)],
+                         ids=["vit_l16", "roberta", "pseudo_tokens", "ragged", "two_tiles_ragged"])
+def test_token_self_attention_backward_matches_oracle(pkg, B, L, K):
+    from garbage_classification_rca_b200 import functional as F
+    p = _block_params("sa", K, K, 128, 96, seed=L + K, gain=2.0)
+    g = torch.Generator().manual_seed(B + L)
+    x = torch.randn(B, L, K, generator=g).bfloat16()
+    d_out = torch.randn(B, L, 96, generator=g) / (B * L)
+    params = [p[f"sa.{l}"].cuda() for l in LEAVES]
+    blk = F.TokenAttention(params, B, L, training=True)
+    out = blk(x.cuda())
+    d_out = d_out * _gate_mask(out, orc.self_attention(x.float(), p, "sa"))
+    grads = [torch.zeros_like(t) for t in params]
+    dx, _ = blk.backward(d_out.cuda(), grads, need_dx_q=True)
+    torch.cuda.synchronize()
+    ref_g, ref_dx, ref_out = _oracle_grads(lambda x_, p_, pre: orc.self_attention(x_, p_, pre), [x.float()], p, "sa", d_out)
+    _check(out, ref_out.float(), "SA training forward")
+    for l, gt in zip(LEAVES, grads):
+        r = ref_g[f"sa.{l}"]
+        if l == "W_key.bias":       # analytically zero (softmax is shift-invariant): absolute check against the scale of d(b_q)
+            assert gt.abs().max().item() < 1e-2 * ref_g["sa.W_query.bias"].abs().max().item() + 1e-7
+            continue
+        assert _rel(gt, r) < TOK_GRAD_LIMIT, f"SA d({l}) B={B} L={L} K={K}: rel {_rel(gt, r):.3e}"
+    assert _rel(dx, ref_dx[0]) < TOK_GRAD_LIMIT, f"SA d(x): rel {_rel(dx, ref_dx[0]):.3e}"
+    # the backward accumulates into the parameter gradients
+    blk(x.cuda())
+    blk.backward(d_out.cuda(), grads)
+    torch.cuda.synchronize()
+    assert _rel(grads[0], 2 * ref_g["sa.W_query.weight"]) < TOK_GRAD_LIMIT
+
+
+@pytest.mark.parametrize("reverse", [True, False], ids=["rca", "ca"])
+@pytest.mark.parametrize("B,L", [(3, 197), (2, 256), (4, 16), (1, 100)])
+def test_token_cross_attention_backward_matches_oracle(pkg, B, L, reverse):
+    from garbage_classification_rca_b200 import functional as F
+    p = _block_params("ca", 96, 96, 64, 48, seed=7 * L + int(reverse), gain=2.0)
+    g = torch.Generator().manual_seed(L)
+    x1 = torch.relu(torch.randn(B, L, 96, generator=g)).bfloat16()
+    x2 = torch.relu(torch.randn(B, L, 96, generator=g)).bfloat16()
+    d_out = torch.randn(B, L, 48, generator=g) / (B * L)
+    params = [p[f"ca.{l}"].cuda() for l in LEAVES]
+    blk = F.TokenAttention(params, B, L, reverse=reverse, training=True)
+    out = blk(x1.cuda(), x2.cuda())
+    d_out = d_out * _gate_mask(out, orc.reverse_cross_attention(x1.float(), x2.float(), p, "ca", reverse))
+    grads = [torch.zeros_like(t) for t in params]
+    dx1, dx2 = blk.backward(d_out.cuda(), grads, need_dx_q=True, need_dx_kv=True)
+    torch.cuda.synchronize()
+    ref_g, ref_dx, _ = _oracle_grads(lambda a, b, p_, pre: orc.reverse_cross_attention(a, b, p_, pre, reverse),
+                                     [x1.float(), x2.float()], p, "ca", d_out)
+    for l, gt in zip(LEAVES, grads):
+        r = ref_g[f"ca.{l}"]
+        if l == "W_key.bias":
+            assert gt.abs().max().item() < 1e-2 * ref_g["ca.W_query.bias"].abs().max().item() + 1e-7
+            continue
+        assert _rel(gt, r) < TOK_GRAD_LIMIT, f"CA d({l}) reverse={reverse} B={B} L={L}: rel {_rel(gt, r):.3e}"
+    assert _rel(dx1, ref_dx[0]) < TOK_GRAD_LIMIT, f"CA d(x_q): rel {_rel(dx1, ref_dx[0]):.3e}"
+    assert _rel(dx2, ref_dx[1]) < TOK_GRAD_LIMIT, f"CA d(x_kv): rel {_rel(dx2, ref_dx[1]):.3e}"
+
+
+def test_token_attention_under_autograd(pkg):
+    """apply(): gradients reach the parameter tensors and the inputs like loss.backward() through the reference modules."""
+    from garbage_classification_rca_b200 import functional as F
+    B, L, K = 2, 50, 128
+    p = _block_params("sa", K, K, 128, 96, seed=3)
+    params = [p[f"sa.{l}"].cuda().requires_grad_(True) for l in LEAVES]
+    x = torch.randn(B, L, K, generator=torch.Generator().manual_seed(1)).bfloat16().float()
+    xg = x.cuda().requires_grad_(True)
+    blk = F.TokenAttention(params, B, L, training=True)
+    out = blk.apply(xg)
+    out.square().sum().backward()
+    p64 = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    x64 = x.double().requires_grad_(True)
+    orc.self_attention(x64, p64, "sa").square().sum().backward()
+    assert _rel(params[0].grad, p64["sa.W_query.weight"].grad) < TOK_GRAD_LIMIT
+    assert _rel(params[4].grad, p64["sa.W_value.weight"].grad) < TOK_GRAD_LIMIT
+    assert _rel(xg.grad, x64.grad) < TOK_GRAD_LIMIT
+    with pytest.raises(RuntimeError):
+        F.TokenAttention([t.detach() for t in params], B, L).backward(out.detach(), [torch.zeros_like(t) for t in params])
