@@ -799,10 +799,24 @@ def run_token(args, rank, world, local_rank):
     NB = 2      # 2 x (B x 197 x 1024 + B x 256 x 768) bf16: rotates over more than the L2 for B >= 128
     x_img = [torch.randn(B, 197, 1024, generator=g).bfloat16().to(dev) for _ in range(NB)]
     x_txt = [torch.randn(B, 256, 768, generator=g).bfloat16().to(dev) for _ in range(NB)]
-    sa_i = F.TokenAttention(block(1024, 1024, 128, 96), B, 197)
-    sa_t = F.TokenAttention(block(768, 768, 128, 96), B, 256)
-    ca_i = F.TokenAttention(block(96, 96, 64, 48), B, 197, reverse=True)
-    ca_t = F.TokenAttention(block(96, 96, 64, 48), B, 256, reverse=True)
+    train = not args.token_forward_only
+    blocks = [block(1024, 1024, 128, 96), block(768, 768, 128, 96), block(96, 96, 64, 48), block(96, 96, 64, 48)]
+    sa_i = F.TokenAttention(blocks[0], B, 197, training=train)
+    sa_t = F.TokenAttention(blocks[1], B, 256, training=train)
+    ca_i = F.TokenAttention(blocks[2], B, 197, reverse=True, training=train)
+    ca_t = F.TokenAttention(blocks[3], B, 256, reverse=True, training=train)
+    # gradient bucket: one flat fp32 buffer, the per-tensor views go to the backward calls; zeroed once per step
+    n_par = sum(t.numel() for blk in blocks for t in blk)
+    flat_g = torch.zeros(n_par, device=dev)
+    views, off = [], 0
+    for blk in blocks:
+        vs = []
+        for t in blk:
+            vs.append(flat_g[off:off + t.numel()].view_as(t))
+            off += t.numel()
+        views.append(vs)
+    d_ca_i = (torch.randn(B, 197, 48, generator=g) / (B * 197)).to(dev)
+    d_ca_t = (torch.randn(B, 256, 48, generator=g) / (B * 256)).to(dev)
 
     def one(i):
         i_sa = sa_i(x_img[i % NB])
@@ -810,6 +824,15 @@ def run_token(args, rank, world, local_rank):
         i_16, t_16 = i_sa.to(torch.bfloat16), t_sa.to(torch.bfloat16)
         ca_i(i_16, torch.roll(i_16, 1, 0))
         ca_t(t_16, torch.roll(t_16, 1, 0))
+        if not train:
+            return
+        # backward of the four blocks: the cross blocks hand d(SA output) back (query side + the rolled key/value side),
+        # the self blocks stop at the frozen backbone's tokens (no input gradient)
+        flat_g.zero_()
+        dq_i, dkv_i = ca_i.backward(d_ca_i, views[2], True, True)
+        dq_t, dkv_t = ca_t.backward(d_ca_t, views[3], True, True)
+        sa_i.backward(dq_i + torch.roll(dkv_i, -1, 0), views[0])
+        sa_t.backward(dq_t + torch.roll(dkv_t, -1, 0), views[1])
 
     for i in range(W):
         one(i)
@@ -852,13 +875,18 @@ def run_token(args, rank, world, local_rank):
         big_ms = statistics.mean(per_shape[big])
         big_flops = 2.0 * B * big[0] * big[1] * big[2]
         ach = big_flops / (big_ms * 1e-3) / 1e12
-        flops_sample = sum(2.0 * L * Kd * Nn for (L, Kd, Nn) in shapes) + \
-            2 * 2.0 * (197 * 197 + 256 * 256) * (128 + 96) / 2 + 2 * 2.0 * (197 * 197 + 256 * 256) * (64 + 48) / 2
+        ll = 197 * 197 + 256 * 256
+        flops_sample = sum(2.0 * L * Kd * Nn for (L, Kd, Nn) in shapes) + 2.0 * ll * (128 + 96) + 2.0 * ll * (64 + 48)
+        if train:
+            # backward: weight gradients of every projection, input gradients of the cross blocks' projections, and per block
+            # C, d(weights), dV (d_v wide) + dQ, dK (d_kq wide)
+            flops_sample += sum(2.0 * L * Kd * Nn for (L, Kd, Nn) in shapes) + sum(2.0 * L * Kd * Nn for (L, Kd, Nn) in shapes[2:]) + \
+                2.0 * ll * (3 * 96 + 2 * 128) + 2.0 * ll * (3 * 48 + 2 * 64)
         emit(json.dumps({
-            "metric": "token_level_rca_blocks_fwd_samples_per_s", "value": world * B * K / (ms * 1e-3), "unit": "samples/s",
+            "metric": "token_level_rca_blocks_fwd_bwd_samples_per_s" if train else "token_level_rca_blocks_fwd_samples_per_s", "value": world * B * K / (ms * 1e-3), "unit": "samples/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"token-level attention blocks forward (BASELINE.json configs[4]): SelfAttention on ViT-L/16 tokens "
+            "config": {"workload": f"token-level attention blocks {'forward + backward' if train else 'forward'} (BASELINE.json configs[4]): SelfAttention on ViT-L/16 tokens "
                                    f"[{B},197,1024] and RoBERTa tokens [{B},256,768], ReverseCrossAttention 96->64/48 at L=197 and L=256; "
                                    f"batch {B}/GPU, replicas (no collective); secondary workload",
                        "parallelism": f"replicas x{world}", "l2": f"inputs rotate over {NB} batches"},
@@ -902,6 +930,7 @@ def main():
     ap.add_argument("--compute", default="bf16", choices=("fp32", "bf16"))
     ap.add_argument("--dropout", type=float, default=0.6, help="model_dropout (reference options.py:25 default 0.6)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--token-forward-only", action="store_true", help="--workload token: forward only (inference)")
     ap.add_argument("--nccl", action="store_true", help="N > 1: all-reduce the gradient bucket with NCCL instead of the "
                                                         "one-shot peer-memory kernel")
     ap.add_argument("--workload", default="mmrca", choices=("mmrca", "hierarchical", "full", "token"),

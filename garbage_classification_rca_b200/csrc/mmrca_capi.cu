@@ -888,7 +888,7 @@ struct TokenWorkspace {
   void *q_img, *k_img, *v_img;
   // MMRCA_TOKEN_TRAINING: kept by the forward for the backward, and the backward's own buffers
   void* p_img; float* sum;
-  float *dq, *dk_part, *dv_part;
+  void *dk_part, *dv_part;
   void *dq_img, *dk_img, *dv_img, *xq_img, *xkv_img, *wmn_q, *wmn_kv;
   size_t bytes;
 };
@@ -906,12 +906,10 @@ static TokenWorkspace token_carve(const MmrcaTokenDesc& d, void* base) {
   w.k_img = take(B * tps * htc::op_bytes(d.d_kq));
   w.v_img = take(B * tps * htc::op_bytes(d.d_v));
   if (d.flags & MMRCA_TOKEN_TRAINING) {
-    const size_t ncols = tps * tok::kTile;
     w.p_img = take(B * tps * htc::op_bytes(tok::kMaxTiles * tok::kTile));
     w.sum = static_cast<float*>(take(B * tps * tok::kTile * 4));
-    w.dq = static_cast<float*>(take(B * ncols * d.d_kq * 4));
-    w.dk_part = static_cast<float*>(take(B * tps * ncols * d.d_kq * 4));
-    w.dv_part = static_cast<float*>(take(B * tps * ncols * d.d_v * 4));
+    w.dk_part = tps > 1 ? take(B * tps * tps * htc::op_bytes(d.d_kq)) : nullptr;
+    w.dv_part = tps > 1 ? take(B * tps * tps * htc::op_bytes(d.d_v)) : nullptr;
     w.dq_img = take(B * tps * htc::op_bytes(d.d_kq));
     w.dk_img = take(B * tps * htc::op_bytes(d.d_kq));
     w.dv_img = take(B * tps * htc::op_bytes(d.d_v));
@@ -1428,19 +1426,30 @@ int mmrca_token_attention_backward(const MmrcaTokenDesc* desc, const MmrcaAttnPa
     memset(&a, 0, sizeof(a));
     a.q_img = w.q_img; a.k_img = w.k_img; a.v_img = w.v_img; a.p_img = w.p_img; a.sum = w.sum;
     a.ln_g = p->ln_g; a.ln_b = p->ln_b; a.d_out = d_out;
-    a.dq = w.dq; a.dk_part = w.dk_part; a.dv_part = w.dv_part; a.g_ln_g = grads->ln_g; a.g_ln_b = grads->ln_b;
+    a.dq_img = w.dq_img; a.dk_out = tps > 1 ? w.dk_part : w.dk_img; a.dv_out = tps > 1 ? w.dv_part : w.dv_img;
+    a.g_bq = grads->bq; a.g_bk = grads->bk; a.g_bv = grads->bv; a.qscale = 1.0f / sqrtf(float(dkq));
+    a.g_ln_g = grads->ln_g; a.g_ln_b = grads->ln_b;
     a.L = L; a.tiles_per_sample = tps; a.reverse = desc->reverse ? 1 : 0;
+    static long long* dbgbuf = nullptr;
+    if (getenv("MMRCA_TOK_DBG")) { if (!dbgbuf) cudaMalloc(&dbgbuf, 64 * 8); a.dbg = dbgbuf; }
     if ((rc = dkq == 128 ? launch_tok_attn_bwd<128, 96>(*desc, a, st) : launch_tok_attn_bwd<64, 48>(*desc, a, st))) return rc;
+    if (a.dbg) {
+      long long h[16];
+      cudaStreamSynchronize(st);
+      cudaMemcpy(h, dbgbuf, sizeof(h), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "tok_attn_bwd dkq=%d phases (cycles):", dkq);
+      for (int i = 1; i <= 14; ++i) fprintf(stderr, " %d:%lld", i, h[i] - h[i - 1]);
+      fprintf(stderr, "\n");
+    }
   }
-  {
-    tok::GradFinishArgs a;
+  if (tps > 1) {
+    tok::GradSumArgs a;
     memset(&a, 0, sizeof(a));
-    a.dq = w.dq; a.dk_part = w.dk_part; a.dv_part = w.dv_part; a.dq_img = w.dq_img; a.dk_img = w.dk_img; a.dv_img = w.dv_img;
-    a.g_bq = grads->bq; a.g_bk = grads->bk; a.g_bv = grads->bv;
-    a.qscale = 1.0f / sqrtf(float(dkq)); a.L = L; a.tiles_per_sample = tps; a.dkq = dkq; a.dv = dv;
+    a.dk_part = w.dk_part; a.dv_part = w.dv_part; a.dk_img = w.dk_img; a.dv_img = w.dv_img;
+    a.tiles_per_sample = tps; a.dkq = dkq; a.dv = dv;
     {
-      LaunchScope ls("tok_grad_finish", st);
-      tok::tok_grad_finish_kernel<<<tiles, 256, 0, st>>>(a);
+      LaunchScope ls("tok_grad_sum", st);
+      tok::tok_grad_sum_kernel<<<tiles, 256, 0, st>>>(a);
     }
     MMRCA_CUDA(cudaGetLastError());
   }
@@ -1842,11 +1851,23 @@ int mmrca_dev_set_debug(void* device_buffer_1024_int64, int32_t kernel) {
 int mmrca_dev_umma_selftest(int32_t mode, const float* a, const float* b, float* out, int32_t n, int32_t k,
                             void* stream) {
   if (!a || !b || !out) return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
-  if (n < 16 || n > 256 || n % 16 || k < 16 || k % 16 || mode < 0 || mode > 15)
-    return fail(MMRCA_ERR_INVALID, "selftest needs 16 <= n <= 256, n % 16 == 0, k % 16 == 0, mode in [0,15]%s%s");
+  if (n < 16 || n > 256 || n % 16 || k < 16 || k % 16 || mode < 0 || mode > 16)
+    return fail(MMRCA_ERR_INVALID, "selftest needs 16 <= n <= 256, n % 16 == 0, k % 16 == 0, mode in [0,16]%s%s");
   DeviceInfo di;
   int rc;
   if ((rc = device_info(&di))) return rc;
+  if (mode == 16) {
+    const size_t smem16 = size_t(2 + (n + 63) / 64) * k * 128 + 1024;
+    if (smem16 > 200 * 1024) return fail(MMRCA_ERR_INVALID, "selftest operands do not fit shared memory%s%s");
+    if ((rc = set_smem(tc::umma_mn128_selftest_kernel, smem16))) return rc;
+    cudaStream_t st16 = static_cast<cudaStream_t>(stream);
+    {
+      LaunchScope ls("umma_mn128_selftest", st16);
+      tc::umma_mn128_selftest_kernel<<<1, 128, smem16, st16>>>(a, b, out, n, k);
+    }
+    MMRCA_CUDA(cudaGetLastError());
+    return MMRCA_OK;
+  }
   const size_t smem = tc::umma_selftest_smem_bytes(n, k);
   if (smem > 200 * 1024) return fail(MMRCA_ERR_INVALID, "selftest operands do not fit shared memory%s%s");
   if ((rc = set_smem(tc::umma_selftest_kernel, smem))) return rc;

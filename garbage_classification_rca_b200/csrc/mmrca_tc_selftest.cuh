@@ -120,6 +120,79 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(int mode, const f
   }
 }
 
+// mode 16: both operands MN-major in the 128-byte-swizzled layout a {64 columns, K rows} SWIZZLE_128B tensor-map box lands
+// from a row-major [K][columns] source: per 64-column block, K rows of 128 bytes whose 16-byte chunks are XOR-swizzled by
+// (row % 8); blocks K * 128 bytes apart (the descriptor's leading-dimension offset), 8-row groups 1024 bytes apart (stride
+// offset), one K = 16 step = two row groups = 2048 bytes.  a: [K][128], b: [K][N]; out[128][N] = A^T B.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr >> 4) & 0x3FFF);
+  d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= uint64_t((1024u >> 4) & 0x3FFF) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(2) << 61;
+  return d;
+}
+__global__ void __launch_bounds__(128, 1) umma_mn128_selftest_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                                    float* __restrict__ out, int N, int K) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nblk = (N + 63) / 64;
+  const uint32_t blk = uint32_t(K) * 128;
+  uint8_t* sa = smem;
+  uint8_t* sb = smem + 2 * blk;
+  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  if (warp == 0) {
+    uint32_t cols = 32;
+    while (cols < uint32_t(N)) cols <<= 1;
+    tmem_alloc(&tmem_base, cols);
+  }
+  for (int i = tid; i < K * 16; i += 128) {          // A: 16 chunks of 8 columns per row
+    const int k = i / 16, c = i % 16;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = a[k * 128 + c * 8 + e];
+    *reinterpret_cast<uint4*>(sa + uint32_t(c >> 3) * blk + uint32_t(k) * 128 + uint32_t(((c & 7) ^ (k & 7)) * 16)) = pack_bf16x8(v);
+  }
+  for (int i = tid; i < K * nblk * 8; i += 128) {
+    const int k = i / (nblk * 8), c = i % (nblk * 8);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = c * 8 + e < N ? b[k * N + c * 8 + e] : 0.f;
+    *reinterpret_cast<uint4*>(sb + uint32_t(c >> 3) * blk + uint32_t(k) * 128 + uint32_t(((c & 7) ^ (k & 7)) * 16)) = pack_bf16x8(v);
+  }
+  fence_proxy_async();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t taddr = tmem_base;
+  if (tid == 0) {
+    const uint64_t ad = make_smem_desc_sw128_mn(smem_u32(sa), blk), bd = make_smem_desc_sw128_mn(smem_u32(sb), blk);
+    const uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
+    for (int ks = 0; ks < K / 16; ++ks) umma_bf16(taddr, desc_advance(ad, ks * 2048), desc_advance(bd, ks * 2048), idesc, ks > 0);
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after_sync();
+  const int r = warp * 32 + lane;
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    tmem_ld16(taddr + (uint32_t(warp * 32) << 16) + uint32_t(c0), v);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) out[r * N + c0 + e] = v[e];
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t cols = 32;
+    while (cols < uint32_t(N)) cols <<= 1;
+    tmem_dealloc(taddr, cols);
+  }
+}
+
 inline size_t umma_selftest_smem_bytes(int N, int K) {
   const size_t a_lbo = (128 / 8) * 128 + 16, b_lbo = (size_t(N) / 8) * 128 + 16;
   return (((K / 8) * a_lbo + 127) & ~size_t(127)) + (K / 8) * b_lbo + 128;

@@ -5,8 +5,9 @@
 //                    weights P (bf16 image) and row sums: C = P V again (tensor core), LayerNorm + ReLU backward per row,
 //                    d(weights) = E V^T, softmax backward in place (P -> dS), dV = P^T E, dQ = dS K, dK = dS^T Q - five
 //                    tcgen05 chains, accumulators in TMEM.  dQ rows are the tile's own; dK / dV are per-query-tile partials.
-//   tok_grad_finish  sums the partials, applies 1/sqrt(d_kq) to dQ, emits the bf16 gradient IMAGES the two GEMMs below read
-//                    and the bias gradients (column sums).
+//                    All three leave the kernel as bf16 gradient IMAGES (what the two GEMMs below load) together with the
+//                    bias gradients (column sums, from the fp32 accumulators).
+//   tok_grad_sum     two-tile samples only: adds the two query tiles' dK / dV partial images
 //   tok_x_image      token activations [B, L, K] bf16 -> per-(sample, tile) images (tokens contiguous per 8-column group)
 //   tok_wgrad        dW[N][K] += dQKV^T X: both operands MN-major over the token dimension, split-K over the token tiles
 //   tok_dgrad        dX[B, L, K] = dQKV [W_query; W_key; W_value]: A = the gradient images (K-major), B = the bf16 weights
@@ -25,12 +26,19 @@ struct AttnBwdArgs {
   const float* sum;         // [B * tiles][128] softmax row sums
   const float* ln_g; const float* ln_b;
   const float* d_out;       // [B][L][DV]
-  float* dq;                // [B][tiles * 128][DKQ]: d(loss)/d(scaled query image)
-  float* dk_part;           // [B][tiles (query tile)][tiles * 128][DKQ]
-  float* dv_part;           // [B][tiles (query tile)][tiles * 128][DV]
+  // bf16 gradient IMAGES (the layout of the forward's Q / K / V images: what tok_wgrad / tok_dgrad load), rows beyond L zero.
+  // dQ (times 1/sqrt(d_kq)) is final; dK / dV are final for one-tile samples, else per-query-tile partials that
+  // tok_grad_sum adds up.
+  void* dq_img;             // [B * tiles][op_bytes(DKQ)]
+  void* dk_out;             // one tile per sample: [B][op_bytes(DKQ)]; else [B * tiles (query tile)][tiles (key tile)][op_bytes(DKQ)]
+  void* dv_out;             // likewise, op_bytes(DV)
+  float* g_bq; float* g_bk; float* g_bv;     // += column sums (atomics)
+  float qscale;
   float* g_ln_g; float* g_ln_b;     // += (atomics)
   int L, tiles_per_sample, reverse;
+  long long* dbg;
 };
+#define TOK_STAMP(i) do { if (a.dbg && tid == 0 && blockIdx.x == 0) a.dbg[(i)] = clock64(); } while (0)
 
 template <int DKQ, int DV>
 struct AttnBwdSmem {
@@ -42,8 +50,9 @@ struct AttnBwdSmem {
   static constexpr uint32_t E = htc::al128(P + PB);                          // [128 x DV]: d(P_un V) rows, bf16
   static constexpr uint32_t LN = htc::al128(E + VB);                         // gamma, beta
   static constexpr uint32_t VSUM = LN + 2 * DV * 4;
-  static constexpr uint32_t ACC = VSUM + DV * 4;                             // d(gamma), d(beta), d(colsum V)
-  static constexpr uint32_t PART = ACC + 3 * DV * 4;
+  static constexpr uint32_t NS = 3 * DV + 2 * DKQ + DV;                      // column sums of a 32-row slab: d(gamma), d(beta),
+  static constexpr uint32_t ACC = VSUM + DV * 4;                             // d(colsum V), d(b_query), d(b_key), d(b_value); x 4 slabs
+  static constexpr uint32_t PART = ACC + 4 * NS * 4;
   static constexpr uint32_t BAR = htc::al128(PART + 2 * kTile * 8);
   static constexpr uint32_t BYTES = BAR + 64;
   static_assert(BYTES <= 232448, "token attention backward does not fit shared memory");
@@ -65,6 +74,37 @@ __device__ __forceinline__ float warp_sum32(float v) {
   return v;
 }
 
+// Column sums over the 32 rows a warp holds (lane = row, v[0 .. N) = the row's values of N columns), WRITTEN to dst[0 .. N)
+// (a per-warp slot: shared-memory float atomics are compare-and-swap loops, four warps on the same words crawl):
+// instead of N butterflies of 5 shuffles, every step with an even count EXCHANGES halves - the lane with the step's bit set
+// keeps the upper half of the columns, its partner the lower - so the count halves with the lane distance (48 -> 24 -> 12 ->
+// 6 -> 3: 45 shuffles, then 3 for the last bit instead of 240).  Destroys v.
+template <int N, int M, int F>
+struct WarpColSum {
+  static __device__ __forceinline__ void run(float* v, int lane, float* dst) {
+    if constexpr (M == 0) {
+      if ((lane & F) == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) dst[i] = v[i];
+      }
+    } else if constexpr (N % 2 == 0) {
+      const bool up = (lane & M) != 0;
+#pragma unroll
+      for (int i = 0; i < N / 2; ++i) {
+        const float send = up ? v[i] : v[i + N / 2], keep = up ? v[i + N / 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, M);
+      }
+      WarpColSum<N / 2, M / 2, F>::run(v, lane, dst + (up ? N / 2 : 0));
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], M);
+      WarpColSum<N, M / 2, F | M>::run(v, lane, dst);
+    }
+  }
+};
+template <int N>
+__device__ __forceinline__ void warp_col_sums(float (&v)[N], int lane, float* dst) { WarpColSum<N, 16, 0>::run(v, lane, dst); }
+
 // 256 threads; thread (q = warp % 4, half = warp / 4, lane) owns row 32 q + lane of whatever the phase's rows are (queries
 // for the row phases, keys when the dK / dV accumulators are drained) and the column half `half`.
 template <int DKQ, int DV>
@@ -76,10 +116,12 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
   float* ln_s = reinterpret_cast<float*>(sm + S::LN);
   float* vsum = reinterpret_cast<float*>(sm + S::VSUM);
-  float* acc_s = reinterpret_cast<float*>(sm + S::ACC);
+  float* slots = reinterpret_cast<float*>(sm + S::ACC);
   float2* part = reinterpret_cast<float2*>(sm + S::PART);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, half = warp >> 2, row = 32 * q + lane;
+  float* myslot = slots + q * S::NS;
+  constexpr int SLOT_B = 3 * DV;                   // bias sums start here
   const int tps = a.tiles_per_sample, L = a.L, ncols = tps * kTile;
   const int b = blockIdx.x / tps, mt = blockIdx.x - b * tps;
   const size_t tile_idx = size_t(b) * tps + mt;
@@ -97,7 +139,6 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   for (int i = tid; i < DV; i += 256) { ln_s[i] = a.ln_g[i]; ln_s[DV + i] = a.ln_b[i]; }
-  for (int i = tid; i < 3 * DV; i += 256) acc_s[i] = 0.f;
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -108,6 +149,22 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
   const bool valid = t < L;
   const int kpad0 = L - (tps - 1) * kTile;        // first pad row of the last key tile
   const int qpad0 = min(kTile, L - mt * kTile);   // first pad row of my query tile
+  // (global loads of my row issued before the wait for the operand tiles)
+  const float sum = valid ? a.sum[tile_idx * kTile + row] : 1.0f;
+  const float inv = valid ? 1.0f / sum : 0.f, rinv = 1.0f / float(L - 1);
+  float dy[HC];                                      // d(out) of my columns, then d(pre-LayerNorm context)
+  if (valid) {
+    const float* src = a.d_out + (size_t(b) * L + t) * DV + HC * half;
+#pragma unroll
+    for (int e = 0; e < HC; e += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + e));
+      dy[e] = v.x; dy[e + 1] = v.y; dy[e + 2] = v.z; dy[e + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < HC; ++e) dy[e] = 0.f;
+  }
+  TOK_STAMP(0);
   mbar_wait(&bars[0], 0);
   tc_fence_after_sync();
   // rows beyond the sample's L tokens were never written by the forward: they meet zero weights in the products below
@@ -145,6 +202,7 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
+  TOK_STAMP(1);
   // ---- C = P V, as the forward did -----------------------------------------------------------------------------------------
   if (tid == 0) {
     for (int j = 0; j < tps; ++j)
@@ -152,22 +210,9 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
                      make_smem_desc(smem_u32(sv + j * S::VB), kRS, kCS), 2 * kRS, make_idesc_bf16(128, DV, 0, 1), 8, j > 0);
     umma_commit(&bars[1]);
   }
-  const float sum = valid ? a.sum[tile_idx * kTile + row] : 1.0f;
-  const float inv = valid ? 1.0f / sum : 0.f, rinv = 1.0f / float(L - 1);
-  float dy[HC];                                      // d(out) of my columns, then d(pre-LayerNorm context)
-  if (valid) {
-    const float* src = a.d_out + (size_t(b) * L + t) * DV + HC * half;
-#pragma unroll
-    for (int e = 0; e < HC; e += 4) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(src + e));
-      dy[e] = v.x; dy[e + 1] = v.y; dy[e + 2] = v.z; dy[e + 3] = v.w;
-    }
-  } else {
-#pragma unroll
-    for (int e = 0; e < HC; ++e) dy[e] = 0.f;
-  }
   mbar_wait(&bars[1], 0);
   tc_fence_after_sync();
+  TOK_STAMP(2);
   // ---- LayerNorm + ReLU backward of my row (:65-66, :105-106) -> E = d(P_un V) = d(context) / sum (reverse: * -1/(L-1)) ------
   {
     float x[HC];
@@ -194,19 +239,23 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
     const float* gam = ln_s + HC * half;
     const float* bet = ln_s + DV + HC * half;
     float t1 = 0.f, t2 = 0.f;
+    float tmp[HC];
 #pragma unroll
     for (int e = 0; e < HC; ++e) {
       const float xh = (x[e] - mean) * rstd;
       const float g = fmaf(xh, gam[e], bet[e]) > 0.f ? dy[e] : 0.f;      // ReLU gate
-      // column sums over the tile's rows: d(gamma), d(beta)
-      const float cg = warp_sum32(g * xh), cb = warp_sum32(g);
-      if (lane == 0) { atomicAdd(&acc_s[HC * half + e], cg); atomicAdd(&acc_s[DV + HC * half + e], cb); }
       const float dxh = g * gam[e];
       t1 += dxh;
       t2 = fmaf(dxh, xh, t2);
       x[e] = xh;
-      dy[e] = dxh;
+      dy[e] = g;
+      tmp[e] = g * xh;
     }
+    // column sums over the tile's rows: d(gamma), d(beta)
+    warp_col_sums(tmp, lane, myslot + HC * half);
+#pragma unroll
+    for (int e = 0; e < HC; ++e) tmp[e] = dy[e];
+    warp_col_sums(tmp, lane, myslot + DV + HC * half);
     __syncthreads();
     part[half * kTile + row] = make_float2(t1, t2);
     __syncthreads();
@@ -214,25 +263,28 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
     const float m1 = (t1 + o2.x) * (1.0f / float(DV)), m2 = (t2 + o2.y) * (1.0f / float(DV));
     const float esc = a.reverse ? -inv * rinv : inv;
 #pragma unroll
+    for (int e = 0; e < HC; ++e)      // d(loss)/d(context row before the LayerNorm)
+      dy[e] = valid ? rstd * (dy[e] * gam[e] - m1 - x[e] * m2) : 0.f;
+#pragma unroll
     for (int g8 = 0; g8 < HC / 8; ++g8) {
       float ev[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int c = 8 * g8 + e;
-        const float dx = valid ? rstd * (dy[c] - m1 - x[c] * m2) : 0.f;      // d(loss)/d(context row before the LayerNorm)
-        if (a.reverse) {
-          const float cs = warp_sum32(dx * rinv);                            // d(colsum V)
-          if (lane == 0) atomicAdd(&acc_s[2 * DV + HC * half + c], cs);
-        }
-        ev[e] = dx * esc;
-      }
+      for (int e = 0; e < 8; ++e) ev[e] = dy[8 * g8 + e] * esc;
       *reinterpret_cast<uint4*>(se + uint32_t((HC / 8) * half + g8) * kCS + row_off(row)) = pack_bf16x8(ev);
+    }
+    if (a.reverse) {                  // d(colsum V)
+#pragma unroll
+      for (int e = 0; e < HC; ++e) dy[e] *= rinv;
+      warp_col_sums(dy, lane, myslot + 2 * DV + HC * half);
     }
   }
   fence_proxy_async();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
+  if (a.reverse && tid < DV)      // d(colsum V) of the tile (vsum is dead: reuse); read after the softmax phase's barrier
+    vsum[tid] = slots[2 * DV + tid] + slots[S::NS + 2 * DV + tid] + slots[2 * S::NS + 2 * DV + tid] + slots[3 * S::NS + 2 * DV + tid];
+  TOK_STAMP(3);
   // ---- d(weights) = E V^T (per key tile, N = 128) and dV = P^T E (per key tile, M = 128 keys) ------------------------------------
   if (tid == 0) {
     for (int j = 0; j < tps; ++j)
@@ -245,6 +297,7 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
   }
   mbar_wait(&bars[1], 1);
   tc_fence_after_sync();
+  TOK_STAMP(4);
   // the value tiles are dead: the query tile takes their place
   if (tid == 0) {
     mbar_arrive_expect_tx(&bars[0], S::QB);
@@ -286,26 +339,34 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
       }
     }
   }
+  TOK_STAMP(5);
   // ---- drain dV: my row is KEY 128 j + row of key tile j ------------------------------------------------------------------------
-  for (int j = 0; j < tps; ++j) {
-    uint32_t raw[HC];
-    const uint32_t tv = tmem + lane_base + COL_DV + DV * j + HC * half;
+  {
+    float vtot[HC];
 #pragma unroll
-    for (int g = 0; g < HC / 8; ++g) tmem_ld8_nw(tv + 8 * g, *reinterpret_cast<uint32_t(*)[8]>(&raw[8 * g]));
-    tmem_wait_ld();
-    const int key = j * kTile + row;
-    const bool add_t = a.reverse && key < L;        // every valid key's value row feeds colsum(V)
-    float* dst = a.dv_part + ((size_t(b) * tps + mt) * ncols + key) * DV + HC * half;
+    for (int e = 0; e < HC; ++e) vtot[e] = 0.f;
+    for (int j = 0; j < tps; ++j) {
+      uint32_t raw[HC];
+      const uint32_t tv = tmem + lane_base + COL_DV + DV * j + HC * half;
 #pragma unroll
-    for (int e = 0; e < HC; e += 4) {
-      float4 v = make_float4(__uint_as_float(raw[e]), __uint_as_float(raw[e + 1]), __uint_as_float(raw[e + 2]), __uint_as_float(raw[e + 3]));
-      if (add_t) {
-        const float* tv_ = acc_s + 2 * DV + HC * half + e;
-        v.x += tv_[0]; v.y += tv_[1]; v.z += tv_[2]; v.w += tv_[3];
+      for (int g = 0; g < HC / 8; ++g) tmem_ld8_nw(tv + 8 * g, *reinterpret_cast<uint32_t(*)[8]>(&raw[8 * g]));
+      tmem_wait_ld();
+      const int key = j * kTile + row;
+      const bool add_t = a.reverse && key < L;        // every valid key's value row feeds colsum(V)
+      uint8_t* dst = static_cast<uint8_t*>(a.dv_out) + (tps == 1 ? size_t(b) : tile_idx * tps + j) * S::VB + row_off(row);
+      float v[HC];
+#pragma unroll
+      for (int e = 0; e < HC; ++e) {
+        v[e] = __uint_as_float(raw[e]) + (add_t ? vsum[HC * half + e] : 0.f);
+        vtot[e] += v[e];
       }
-      *reinterpret_cast<float4*>(dst + e) = v;
+#pragma unroll
+      for (int g8 = 0; g8 < HC / 8; ++g8)
+        *reinterpret_cast<uint4*>(dst + uint32_t((HC / 8) * half + g8) * kCS) = pack_bf16x8(*reinterpret_cast<const float(*)[8]>(&v[8 * g8]));
     }
+    warp_col_sums(vtot, lane, myslot + SLOT_B + 2 * DKQ + HC * half);
   }
+  TOK_STAMP(6);
   mbar_wait(&bars[0], 1);                           // the query tile has landed
   for (int i = tid; i < (kTile - qpad0) * (DKQ / 8); i += 256) {
     const int r = qpad0 + i / (DKQ / 8), g = i % (DKQ / 8);
@@ -315,6 +376,7 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
+  TOK_STAMP(7);
   // ---- dQ = dS K (accumulated over the key tiles), dK = dS^T Q (per key tile) ------------------------------------------------------
   if (tid == 0) {
     for (int j = 0; j < tps; ++j)
@@ -325,96 +387,109 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
                      make_smem_desc(smem_u32(sq), kRS, kCS), 2 * kRS, make_idesc_bf16(128, DKQ, 1, 1), 8, false);
     umma_commit(&bars[1]);
   }
+  TOK_STAMP(8);
   // LayerNorm-affine gradients of this tile
   if (tid < DV) {
-    atomicAdd(a.g_ln_g + tid, acc_s[tid]);
-    atomicAdd(a.g_ln_b + tid, acc_s[DV + tid]);
+    atomicAdd(a.g_ln_g + tid, slots[tid] + slots[S::NS + tid] + slots[2 * S::NS + tid] + slots[3 * S::NS + tid]);
+    atomicAdd(a.g_ln_b + tid, slots[DV + tid] + slots[S::NS + DV + tid] + slots[2 * S::NS + DV + tid] + slots[3 * S::NS + DV + tid]);
   }
   mbar_wait(&bars[1], 0);
   tc_fence_after_sync();
+  TOK_STAMP(9);
   {
-    float* dst = a.dq + (size_t(b) * ncols + t) * DKQ + HQ * half;
+    uint8_t* dst = static_cast<uint8_t*>(a.dq_img) + tile_idx * S::QB + row_off(row);
     const uint32_t tq = tmem + lane_base + COL_DQ + HQ * half;
-#pragma unroll 1
-    for (int c0 = 0; c0 < HQ; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld16_nw(tq + c0, r);
-      tmem_wait_ld();
+    uint32_t r[HQ];
 #pragma unroll
-      for (int e = 0; e < 16; e += 4) *reinterpret_cast<uint4*>(dst + c0 + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
-    }
+    for (int c0 = 0; c0 < HQ; c0 += 16) tmem_ld16_nw(tq + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[c0]));
+    tmem_wait_ld();
+    float v[HQ];
+#pragma unroll
+    for (int e = 0; e < HQ; ++e) v[e] = __uint_as_float(r[e]) * a.qscale;      // scores = (q / sqrt(d_kq)) . k
+#pragma unroll
+    for (int g8 = 0; g8 < HQ / 8; ++g8)
+      *reinterpret_cast<uint4*>(dst + uint32_t((HQ / 8) * half + g8) * kCS) = pack_bf16x8(*reinterpret_cast<const float(*)[8]>(&v[8 * g8]));
+    TOK_STAMP(10);
+    warp_col_sums(v, lane, myslot + SLOT_B + HQ * half);
   }
+  TOK_STAMP(11);
+  {
+  float ktot[HQ];
+#pragma unroll
+  for (int e = 0; e < HQ; ++e) ktot[e] = 0.f;
   for (int j = 0; j < tps; ++j) {
-    float* dst = a.dk_part + ((size_t(b) * tps + mt) * ncols + j * kTile + row) * DKQ + HQ * half;
+    uint8_t* dst = static_cast<uint8_t*>(a.dk_out) + (tps == 1 ? size_t(b) : tile_idx * tps + j) * S::QB + row_off(row);
     const uint32_t tk = tmem + lane_base + COL_DK + DKQ * j + HQ * half;
-#pragma unroll 1
-    for (int c0 = 0; c0 < HQ; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld16_nw(tk + c0, r);
-      tmem_wait_ld();
+    uint32_t r[HQ];
 #pragma unroll
-      for (int e = 0; e < 16; e += 4) *reinterpret_cast<uint4*>(dst + c0 + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
-    }
+    for (int c0 = 0; c0 < HQ; c0 += 16) tmem_ld16_nw(tk + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[c0]));
+    tmem_wait_ld();
+    float v[HQ];
+#pragma unroll
+    for (int e = 0; e < HQ; ++e) { v[e] = __uint_as_float(r[e]); ktot[e] += v[e]; }
+#pragma unroll
+    for (int g8 = 0; g8 < HQ / 8; ++g8)
+      *reinterpret_cast<uint4*>(dst + uint32_t((HQ / 8) * half + g8) * kCS) = pack_bf16x8(*reinterpret_cast<const float(*)[8]>(&v[8 * g8]));
   }
+  TOK_STAMP(12);
+  warp_col_sums(ktot, lane, myslot + SLOT_B + DKQ + HQ * half);
+  }
+  TOK_STAMP(13);
+  __syncthreads();
+  for (int i = tid; i < 2 * DKQ + DV; i += 256) {
+    const float* sl = slots + SLOT_B + i;
+    atomicAdd(i < DKQ ? a.g_bq + i : (i < 2 * DKQ ? a.g_bk + (i - DKQ) : a.g_bv + (i - 2 * DKQ)),
+              sl[0] + sl[S::NS] + sl[2 * S::NS] + sl[3 * S::NS]);
+  }
+  TOK_STAMP(14);
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-// ---- partial sums -> bf16 gradient images + bias gradients ---------------------------------------------------------------------
-struct GradFinishArgs {
-  const float* dq; const float* dk_part; const float* dv_part;
-  void* dq_img; void* dk_img; void* dv_img;        // [B * tiles][op_bytes(cols)], rows beyond L zero
-  float* g_bq; float* g_bk; float* g_bv;           // += column sums
-  float qscale;
-  int L, tiles_per_sample, dkq, dv;
-};
-__global__ void __launch_bounds__(256) tok_grad_finish_kernel(const GradFinishArgs a) {
-  __shared__ float cs[2 * 128 + 96];
-  const int tid = threadIdx.x, tps = a.tiles_per_sample, ncols = tps * kTile;
-  const int b = blockIdx.x / tps, j = blockIdx.x - b * tps;
-  const int ntot = 2 * a.dkq + a.dv;
-  for (int i = tid; i < ntot; i += 256) cs[i] = 0.f;
-  __syncthreads();
-  for (int seg = 0; seg < 3; ++seg) {
-    const int cols = seg == 2 ? a.dv : a.dkq, G = cols / 8, off = seg == 0 ? 0 : (seg == 1 ? a.dkq : 2 * a.dkq);
-    const float* src = seg == 0 ? a.dq : (seg == 1 ? a.dk_part : a.dv_part);
-    uint8_t* img = static_cast<uint8_t*>(seg == 0 ? a.dq_img : (seg == 1 ? a.dk_img : a.dv_img)) + size_t(blockIdx.x) * (size_t(G) * kCS);
-    const int nparts = seg == 0 ? 1 : tps;
-    const float sc = seg == 0 ? a.qscale : 1.0f;
-    for (int idx = tid; idx < kTile * G; idx += 256) {
-      const int r = idx / G, g = idx - r * G, t = j * kTile + r;
-      float v[8];
+// ---- two-tile samples: dK / dV image of key tile (b, j) = sum over the query tiles m of the partial images ((b, m), j) ----------
+struct GradSumArgs { const void* dk_part; const void* dv_part; void* dk_img; void* dv_img; int tiles_per_sample, dkq, dv; };
+__global__ void __launch_bounds__(256) tok_grad_sum_kernel(const GradSumArgs a) {
+  const int tps = a.tiles_per_sample, b = blockIdx.x / tps, j = blockIdx.x - b * tps;
+  for (int seg = 0; seg < 2; ++seg) {
+    const uint32_t n16 = htc::op_bytes(seg ? a.dv : a.dkq) / 16;
+    const uint4* src = static_cast<const uint4*>(seg ? a.dv_part : a.dk_part);
+    uint4* dst = static_cast<uint4*>(seg ? a.dv_img : a.dk_img) + size_t(blockIdx.x) * n16;
+    for (uint32_t i = threadIdx.x; i < n16; i += 256) {
+      float acc[8], v[8];
+      unpack_bf16x8(__ldg(src + ((size_t(b) * tps) * tps + j) * n16 + i), acc);
+      for (int m = 1; m < tps; ++m) {
+        unpack_bf16x8(__ldg(src + ((size_t(b) * tps + m) * tps + j) * n16 + i), v);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = 0.f;
-      if (t < a.L) {
-        for (int m = 0; m < nparts; ++m) {
-          const float* p = src + ((size_t(b) * nparts + m) * ncols + t) * cols + 8 * g;
-          const float4 v0 = __ldg(reinterpret_cast<const float4*>(p)), v1 = __ldg(reinterpret_cast<const float4*>(p + 4));
-          v[0] += v0.x; v[1] += v0.y; v[2] += v0.z; v[3] += v0.w; v[4] += v1.x; v[5] += v1.y; v[6] += v1.z; v[7] += v1.w;
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { v[e] *= sc; atomicAdd(&cs[off + 8 * g + e], v[e]); }
+        for (int e = 0; e < 8; ++e) acc[e] += v[e];
       }
-      *reinterpret_cast<uint4*>(img + uint32_t(g) * kCS + row_off(r)) = pack_bf16x8(v);
+      dst[i] = pack_bf16x8(acc);
     }
-  }
-  __syncthreads();
-  for (int i = tid; i < ntot; i += 256) {
-    float* dst = i < a.dkq ? a.g_bq + i : (i < 2 * a.dkq ? a.g_bk + (i - a.dkq) : a.g_bv + (i - 2 * a.dkq));
-    atomicAdd(dst, cs[i]);
   }
 }
 
-// x [B][L][K] bf16 -> [B * tiles][K / 8][128 tokens][8], rows beyond L zero
+// x [B][L][K] bf16 -> [B * tiles][K / 8][128 tokens][8], rows beyond L zero.  Eight column groups at a time through shared
+// memory: 128-byte row pieces in (one sector-complete read per 8 lanes), 512-byte runs of one group out.
 __global__ void __launch_bounds__(256) tok_x_image_kernel(const __nv_bfloat16* __restrict__ x, int L, int tps, int K,
                                                           uint8_t* __restrict__ img) {
-  const int b = blockIdx.x / tps, j = blockIdx.x - b * tps, G = K / 8;
-  for (int idx = threadIdx.x; idx < kTile * G; idx += 256) {
-    const int r = idx / G, g = idx - r * G, t = j * kTile + r;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (t < L) v = __ldg(reinterpret_cast<const uint4*>(x + (size_t(b) * L + t) * K + 8 * g));
-    *reinterpret_cast<uint4*>(img + (size_t(blockIdx.x) * G + g) * kXGrp + uint32_t(r) * 16) = v;
+  __shared__ uint4 st[8 * 129];
+  const int b = blockIdx.x / tps, j = blockIdx.x - b * tps, G = K / 8, tid = threadIdx.x;
+  for (int g0 = 0; g0 < G; g0 += 8) {
+    const int ng = min(8, G - g0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + 256 * i, r = idx >> 3, g = idx & 7, t = j * kTile + r;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (t < L && g < ng) v = __ldg(reinterpret_cast<const uint4*>(x + (size_t(b) * L + t) * K + 8 * (g0 + g)));
+      st[g * 129 + r] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + 256 * i, g = idx >> 7, r = idx & 127;
+      if (g < ng) *reinterpret_cast<uint4*>(img + (size_t(blockIdx.x) * G + g0 + g) * kXGrp + uint32_t(r) * 16) = st[g * 129 + r];
+    }
+    __syncthreads();
   }
 }
 

@@ -381,6 +381,7 @@ int mmrca_dev_set_debug(void* device_buffer_1024_int64, int32_t kernel);
 
 /* Diagnostic: one 128 x N x K bf16 tcgen05 GEMM (fp32 accumulate in TMEM) through the library's operand
  * staging.  mode bit 0: b is [K][N] (MN-major) instead of [N][K]; bit 1: a is [K][128] instead of [128][K].
+ * mode 16: a is [K][128], b is [K][N], both staged as the 128-byte-swizzled MN-major layout a SWIZZLE_128B tensor-map box lands.
  * out[128][N] = A B^T.  N % 16 == 0, 16 <= N <= 256, K % 16 == 0, operands must fit shared memory. */
 int mmrca_dev_umma_selftest(int32_t mode, const float* a, const float* b, float* out, int32_t n, int32_t k,
                             void* stream);

@@ -42,3 +42,22 @@ def test_umma_constant_ones_operand(native_lib, k):
         ref = A.bfloat16().float().sum(dim=1, keepdim=True).expand(128, n)
         err = (out.cpu() - ref).abs().max().item()
         assert err < 1e-3 * max(1.0, ref.abs().max().item()), f"k {k}: max err {err}"
+
+
+@pytest.mark.parametrize("shape", [(64, 16), (128, 64), (192, 64), (160, 128), (176, 32), (256, 64)])
+def test_umma_swizzled_mn_major_operands(native_lib, shape):
+    """mode 16: both operands MN-major in the SWIZZLE_128B layout a tensor-map box lands from row-major [K][columns]
+    memory (the token-level weight-gradient GEMM reads X and the gradients this way)."""
+    from garbage_classification_rca_b200 import _native as N
+    n, k = shape
+    g = torch.Generator().manual_seed(n + k)
+    A = torch.randn(128, k, generator=g)
+    B = torch.randn(n, k, generator=g)
+    a_dev, b_dev = A.t().contiguous().cuda(), B.t().contiguous().cuda()
+    out = torch.full((128, n), float("nan"), device="cuda")
+    N.check(native_lib.mmrca_dev_umma_selftest(16, a_dev.data_ptr(), b_dev.data_ptr(), out.data_ptr(), n, k,
+                                               torch.cuda.current_stream().cuda_stream), "selftest")
+    torch.cuda.synchronize()
+    ref = A.bfloat16().float() @ B.bfloat16().float().t()
+    err = (out.cpu() - ref).abs().max().item()
+    assert err < 1e-3 * max(1.0, ref.abs().max().item()), f"n {n} k {k}: max err {err}"
