@@ -819,6 +819,9 @@ def run_token(args, rank, world, local_rank):
     d_ca_t = (torch.randn(B, 256, 48, generator=g) / (B * 256)).to(dev)
 
     def one(i):
+        if train:       # a training step follows an optimizer step: the bf16 weight images are rebuilt from the fp32 parameters
+            for blk in (sa_i, sa_t, ca_i, ca_t):
+                blk.refresh_weights()
         i_sa = sa_i(x_img[i % NB])
         t_sa = sa_t(x_txt[i % NB])
         i_16, t_16 = i_sa.to(torch.bfloat16), t_sa.to(torch.bfloat16)

@@ -867,15 +867,16 @@ static TensorMapEncodeFn tensor_map_encoder() {
   }
   return reinterpret_cast<TensorMapEncodeFn>(f);
 }
-// bf16 [d2][d1][d0] (d0 contiguous), box {64, box1, 1}, 128-byte swizzle, out-of-range elements read as zero
-static int make_tensor_map(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box1, int rank) {
+// bf16 [rows][cols] with a row pitch of ld elements (cols contiguous), box {64, box_rows}, 128-byte swizzle, out-of-range
+// elements read as zero
+static int make_tensor_map(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows) {
   TensorMapEncodeFn enc = tensor_map_encoder();
   if (!enc) return fail(MMRCA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver%s%s");
-  const cuuint64_t dims[3] = {d0, d1, d2};
-  const cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
-  const cuuint32_t box[3] = {uint32_t(tok::kBK), box1, 1};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, cuuint32_t(rank), const_cast<void*>(base), dims, strides, box, estr,
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {ld * 2};
+  const cuuint32_t box[2] = {uint32_t(tok::kBK), box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(MMRCA_ERR_CUDA, "cuTensorMapEncodeTiled failed (activations must be 16-byte aligned bf16, "
@@ -888,8 +889,9 @@ struct TokenWorkspace {
   void *q_img, *k_img, *v_img;
   // MMRCA_TOKEN_TRAINING: kept by the forward for the backward, and the backward's own buffers
   void* p_img; float* sum;
-  void *dk_part, *dv_part;
-  void *dq_img, *dk_img, *dv_img, *xq_img, *xkv_img, *wmn_q, *wmn_kv;
+  __nv_bfloat16* g;             // gradient rows: self [rows][2 d_kq + d_v]; cross [rows][d_kq] then [rows][d_kq + d_v]
+  __nv_bfloat16* part[2];       // two-tile samples: per-query-tile dK | dV partial rows [rows][d_kq + d_v]
+  __nv_bfloat16* wbf;           // bf16 weights as they lie: self [2 d_kq + d_v][d_in]; cross [d_kq][d_in_q] then [d_kq + d_v][d_in_kv]
   size_t bytes;
 };
 static TokenWorkspace token_carve(const MmrcaTokenDesc& d, void* base) {
@@ -908,15 +910,11 @@ static TokenWorkspace token_carve(const MmrcaTokenDesc& d, void* base) {
   if (d.flags & MMRCA_TOKEN_TRAINING) {
     w.p_img = take(B * tps * htc::op_bytes(tok::kMaxTiles * tok::kTile));
     w.sum = static_cast<float*>(take(B * tps * tok::kTile * 4));
-    w.dk_part = tps > 1 ? take(B * tps * tps * htc::op_bytes(d.d_kq)) : nullptr;
-    w.dv_part = tps > 1 ? take(B * tps * tps * htc::op_bytes(d.d_v)) : nullptr;
-    w.dq_img = take(B * tps * htc::op_bytes(d.d_kq));
-    w.dk_img = take(B * tps * htc::op_bytes(d.d_kq));
-    w.dv_img = take(B * tps * htc::op_bytes(d.d_v));
-    w.xq_img = take(B * tps * size_t(d.d_in_q / 8) * tok::kXGrp);
-    w.xkv_img = take(B * tps * size_t(d.d_in_kv / 8) * tok::kXGrp);
-    w.wmn_q = take(size_t(d.d_in_q / 8) * size_t(2 * d.d_kq + d.d_v) * 16);
-    w.wmn_kv = take(size_t(d.d_in_kv / 8) * size_t(d.d_kq + d.d_v) * 16);
+    const size_t rows = B * size_t(d.seq_len);
+    w.g = static_cast<__nv_bfloat16*>(take(rows * size_t(2 * d.d_kq + d.d_v) * 2));
+    for (int i = 0; i < 2; ++i)
+      w.part[i] = tps > 1 ? static_cast<__nv_bfloat16*>(take(rows * size_t(d.d_kq + d.d_v) * 2)) : nullptr;
+    w.wbf = static_cast<__nv_bfloat16*>(take((size_t(d.d_kq) * d.d_in_q + size_t(d.d_kq + d.d_v) * d.d_in_kv) * 2));
   }
   w.bytes = off;
   return w;
@@ -931,25 +929,28 @@ static int token_check(const MmrcaTokenDesc* d) {
     return fail(MMRCA_ERR_INVALID, "token attention: d_in must be a multiple of 8, >= 16%s%s");
   return MMRCA_OK;
 }
-static int launch_cast(const float* src, __nv_bfloat16* dst, long long n, int sms, cudaStream_t st) {
+static int launch_cast3(const tok::Cast3Args& a, int sms, cudaStream_t st) {
+  const long long n = std::max(a.n[0], std::max(a.n[1], a.n[2]));
   {
     LaunchScope ls("cast_bf16", st);
-    tok::cast_bf16_kernel<<<int(std::min<long long>((n / 4 + 255) / 256 + 1, 4LL * sms)), 256, 0, st>>>(src, dst, n);
+    tok::cast3_bf16_kernel<<<int(std::min<long long>((n / 4 + 255) / 256 + 1, 4LL * sms)), 256, 0, st>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  return MMRCA_OK;
+}
+// the block's fp32 weights -> pre-swizzled bf16 images of the projection GEMM + the stacked bias, one launch
+static int launch_tok_wprep(const tok::WprepArgs& a, int sms, cudaStream_t st) {
+  long long chunks = 0;
+  for (int i = 0; i < 3; ++i)
+    chunks = std::max(chunks, (long long)((a.seg[i].K + tok::kBK - 1) / tok::kBK) * a.seg[i].n_rows * 8);
+  {
+    LaunchScope ls("tok_wprep", st);
+    tok::tok_wprep_kernel<<<int(std::min<long long>((chunks + 255) / 256, 4LL * sms)), 256, 0, st>>>(a);
   }
   MMRCA_CUDA(cudaGetLastError());
   return MMRCA_OK;
 }
 // one projection GEMM: x [B][L][K] bf16, w [N][K] bf16 (rows: the segments back to back), bias [N]
-static int launch_tok_wprep(const float* w, int n_rows, int K, int N, int n0, void* blob, int sms, cudaStream_t st) {
-  const long long chunks = (long long)((K + tok::kBK - 1) / tok::kBK) * n_rows * 8;
-  {
-    LaunchScope ls("tok_wprep", st);
-    tok::tok_wprep_kernel<<<int(std::min<long long>((chunks + 255) / 256, 4LL * sms)), 256, 0, st>>>(w, n_rows, K, N, n0,
-                                                                                                       static_cast<uint8_t*>(blob));
-  }
-  MMRCA_CUDA(cudaGetLastError());
-  return MMRCA_OK;
-}
 static int launch_tok_proj(const MmrcaTokenDesc& d, const void* x, int K, const __nv_bfloat16* w, const float* bias, int N,
                            const tok::ProjSeg (&segs)[3], int sms, cudaStream_t st) {
   int rc;
@@ -963,7 +964,7 @@ static int launch_tok_proj(const MmrcaTokenDesc& d, const void* x, int K, const 
   a.tiles_per_sample = (d.seq_len + tok::kTile - 1) / tok::kTile;
   a.L = d.seq_len; a.rows = d.batch * d.seq_len;
   CUtensorMap tx, tw;
-  if ((rc = make_tensor_map(&tx, x, uint64_t(K), uint64_t(a.rows), 1, tok::kTile, 2))) return rc;
+  if ((rc = make_tensor_map(&tx, x, uint64_t(K), uint64_t(a.rows), uint64_t(K), tok::kTile))) return rc;
   tw = tx;      // (the weights arrive as pre-swizzled images through the bulk-copy engine: no second tensor map)
   const size_t smem = tok::kStages * size_t(tok::proj_stage_bytes(N)) + 128 + size_t(N) * 4 + 1024;
   if ((rc = set_smem(tok::tok_proj_kernel, smem))) return rc;
@@ -999,34 +1000,38 @@ static int launch_tok_attn_bwd(const MmrcaTokenDesc& d, const tok::AttnBwdArgs& 
   MMRCA_CUDA(cudaGetLastError());
   return MMRCA_OK;
 }
-static int launch_tok_wgrad(const tok::WgradArgs& a, int nseg, int sms, cudaStream_t st) {
+// dW += G^T X for the gradient columns listed in a.out (x [rows][K] bf16, g [rows][NG] bf16 with row pitch ld_g)
+static int launch_tok_wgrad(tok::WgradArgs a, const void* x, const __nv_bfloat16* g, int ld_g, int sms, cudaStream_t st) {
   int rc;
-  if ((rc = set_smem(tok::tok_wgrad_kernel, tok::GradSmem::BYTES))) return rc;
-  const int nts = (a.K + 255) / 256;
-  const int splits = std::max(1, std::min(a.tiles, sms / (nts * nseg)));
+  CUtensorMap tx, tg;
+  if ((rc = make_tensor_map(&tx, x, uint64_t(a.K), uint64_t(a.rows), uint64_t(a.K), tok::kGradKT))) return rc;
+  if ((rc = make_tensor_map(&tg, g, uint64_t(a.NG), uint64_t(a.rows), uint64_t(ld_g), tok::kGradKT))) return rc;
+  const int nblk = (a.NG + 63) / 64, mtiles = (a.K + 127) / 128, chunks = (a.rows + tok::kGradKT - 1) / tok::kGradKT;
+  const size_t smem = size_t(tok::kGradStages) * (2 + nblk) * tok::kBoxBytes + 128 + 1024;
+  if ((rc = set_smem(tok::tok_wgrad_kernel, smem))) return rc;
+  const int splits = std::max(1, std::min(chunks, sms / mtiles));
   {
     LaunchScope ls("tok_wgrad", st);
-    tok::tok_wgrad_kernel<<<dim3(nts, nseg, splits), tok::kGradThreads, tok::GradSmem::BYTES, st>>>(a);
+    tok::tok_wgrad_kernel<<<dim3(mtiles, splits), tok::kGradThreads, smem, st>>>(tx, tg, a);
   }
   MMRCA_CUDA(cudaGetLastError());
   return MMRCA_OK;
 }
-static int launch_tok_dgrad(const tok::DgradArgs& a, int tiles, cudaStream_t st) {
+// dx [rows][K] = G [rows][NG] W [NG][K] (w: bf16)
+static int launch_tok_dgrad(float* dx, int rows, int K, int NG, const __nv_bfloat16* g, int ld_g, const __nv_bfloat16* w,
+                            cudaStream_t st) {
   int rc;
-  if ((rc = set_smem(tok::tok_dgrad_kernel, tok::GradSmem::BYTES))) return rc;
+  CUtensorMap tg, tw;
+  if ((rc = make_tensor_map(&tg, g, uint64_t(NG), uint64_t(rows), uint64_t(ld_g), tok::kTile))) return rc;
+  if ((rc = make_tensor_map(&tw, w, uint64_t(K), uint64_t(NG), uint64_t(K), 64))) return rc;
+  const int nb = (std::min(256, K) + 63) / 64;
+  const size_t smem = size_t(tok::kGradStages) * (tok::kTile * 128 + nb * tok::kBoxBytes) + 128 + 1024;
+  if ((rc = set_smem(tok::tok_dgrad_kernel, smem))) return rc;
+  tok::DgradArgs a;
+  a.dx = dx; a.rows = rows; a.K = K; a.NG = NG;
   {
     LaunchScope ls("tok_dgrad", st);
-    tok::tok_dgrad_kernel<<<dim3(tiles, (a.K + 255) / 256), tok::kGradThreads, tok::GradSmem::BYTES, st>>>(a);
-  }
-  MMRCA_CUDA(cudaGetLastError());
-  return MMRCA_OK;
-}
-static int launch_tok_wprep_mn(const float* w, int n_rows, int K, int N, int n0, void* blob, int sms, cudaStream_t st) {
-  const long long items = (long long)n_rows * (K / 8);
-  {
-    LaunchScope ls("tok_wprep_mn", st);
-    tok::tok_wprep_mn_kernel<<<int(std::min<long long>((items + 255) / 256, 4LL * sms)), 256, 0, st>>>(w, n_rows, K, N, n0,
-                                                                                                         static_cast<uint8_t*>(blob));
+    tok::tok_dgrad_kernel<<<dim3((rows + tok::kTile - 1) / tok::kTile, (K + 255) / 256), tok::kGradThreads, smem, st>>>(tg, tw, a);
   }
   MMRCA_CUDA(cudaGetLastError());
   return MMRCA_OK;
@@ -1366,19 +1371,20 @@ int mmrca_token_attention_forward(const MmrcaTokenDesc* desc, const MmrcaAttnPar
   __nv_bfloat16* wq = w.w;
   __nv_bfloat16* wk = wq + size_t(dkq) * kq_pad;      // cross: the second image starts here
   if (!(desc->flags & MMRCA_TOKEN_WEIGHTS_READY)) {
+    tok::WprepArgs wa;
+    memset(&wa, 0, sizeof(wa));
+    uint8_t *bq_ = reinterpret_cast<uint8_t*>(wq), *bk_ = reinterpret_cast<uint8_t*>(wk);
     if (self) {
       const int N = 2 * dkq + dv;
-      if ((rc = launch_tok_wprep(p->wq, dkq, kq, N, 0, wq, di.sms, st))) return rc;
-      if ((rc = launch_tok_wprep(p->wk, dkq, kq, N, dkq, wq, di.sms, st))) return rc;
-      if ((rc = launch_tok_wprep(p->wv, dv, kq, N, 2 * dkq, wq, di.sms, st))) return rc;
+      wa.seg[0] = {p->wq, p->bq, w.bias, bq_, dkq, kq, N, 0};
+      wa.seg[1] = {p->wk, p->bk, w.bias + dkq, bq_, dkq, kq, N, dkq};
+      wa.seg[2] = {p->wv, p->bv, w.bias + 2 * dkq, bq_, dv, kq, N, 2 * dkq};
     } else {
-      if ((rc = launch_tok_wprep(p->wq, dkq, kq, dkq, 0, wq, di.sms, st))) return rc;
-      if ((rc = launch_tok_wprep(p->wk, dkq, kkv, dkq + dv, 0, wk, di.sms, st))) return rc;
-      if ((rc = launch_tok_wprep(p->wv, dv, kkv, dkq + dv, dkq, wk, di.sms, st))) return rc;
+      wa.seg[0] = {p->wq, p->bq, w.bias, bq_, dkq, kq, dkq, 0};
+      wa.seg[1] = {p->wk, p->bk, w.bias + dkq, bk_, dkq, kkv, dkq + dv, 0};
+      wa.seg[2] = {p->wv, p->bv, w.bias + 2 * dkq, bk_, dv, kkv, dkq + dv, dkq};
     }
-    MMRCA_CUDA(cudaMemcpyAsync(w.bias, p->bq, size_t(dkq) * 4, cudaMemcpyDeviceToDevice, st));
-    MMRCA_CUDA(cudaMemcpyAsync(w.bias + dkq, p->bk, size_t(dkq) * 4, cudaMemcpyDeviceToDevice, st));
-    MMRCA_CUDA(cudaMemcpyAsync(w.bias + 2 * dkq, p->bv, size_t(dv) * 4, cudaMemcpyDeviceToDevice, st));
+    if ((rc = launch_tok_wprep(wa, di.sms, st))) return rc;
   }
   const float qscale = 1.0f / sqrtf(float(dkq));      // scores / sqrt(d_kq) (:58-60, :89-91) folded into Q
   if (self) {
@@ -1420,92 +1426,64 @@ int mmrca_token_attention_backward(const MmrcaTokenDesc* desc, const MmrcaAttnPa
   if (desc->batch == 0) return MMRCA_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int dkq = desc->d_kq, dv = desc->d_v, kq = desc->d_in_q, kkv = desc->d_in_kv, L = desc->seq_len;
-  const int tps = (L + tok::kTile - 1) / tok::kTile, tiles = desc->batch * tps;
+  const int tps = (L + tok::kTile - 1) / tok::kTile, rows = desc->batch * L;
+  // gradient rows: self attention keeps dQ | dK | dV side by side (one GEMM operand); cross attention keeps dQ apart from
+  // dK | dV (they meet different activations)
+  __nv_bfloat16* gq = w.g;
+  __nv_bfloat16* gkv = self ? w.g + dkq : w.g + size_t(rows) * dkq;
+  const int ldq = self ? 2 * dkq + dv : dkq, ldkv = self ? 2 * dkq + dv : dkq + dv;
   {
     tok::AttnBwdArgs a;
     memset(&a, 0, sizeof(a));
     a.q_img = w.q_img; a.k_img = w.k_img; a.v_img = w.v_img; a.p_img = w.p_img; a.sum = w.sum;
     a.ln_g = p->ln_g; a.ln_b = p->ln_b; a.d_out = d_out;
-    a.dq_img = w.dq_img; a.dk_out = tps > 1 ? w.dk_part : w.dk_img; a.dv_out = tps > 1 ? w.dv_part : w.dv_img;
+    a.g_q = gq; a.ld_q = ldq;
+    a.dkv_out[0] = tps > 1 ? w.part[0] : gkv; a.dkv_out[1] = w.part[1]; a.ld_kv = tps > 1 ? dkq + dv : ldkv;
     a.g_bq = grads->bq; a.g_bk = grads->bk; a.g_bv = grads->bv; a.qscale = 1.0f / sqrtf(float(dkq));
     a.g_ln_g = grads->ln_g; a.g_ln_b = grads->ln_b;
     a.L = L; a.tiles_per_sample = tps; a.reverse = desc->reverse ? 1 : 0;
-    static long long* dbgbuf = nullptr;
-    if (getenv("MMRCA_TOK_DBG")) { if (!dbgbuf) cudaMalloc(&dbgbuf, 64 * 8); a.dbg = dbgbuf; }
     if ((rc = dkq == 128 ? launch_tok_attn_bwd<128, 96>(*desc, a, st) : launch_tok_attn_bwd<64, 48>(*desc, a, st))) return rc;
-    if (a.dbg) {
-      long long h[16];
-      cudaStreamSynchronize(st);
-      cudaMemcpy(h, dbgbuf, sizeof(h), cudaMemcpyDeviceToHost);
-      fprintf(stderr, "tok_attn_bwd dkq=%d phases (cycles):", dkq);
-      for (int i = 1; i <= 14; ++i) fprintf(stderr, " %d:%lld", i, h[i] - h[i - 1]);
-      fprintf(stderr, "\n");
-    }
   }
   if (tps > 1) {
-    tok::GradSumArgs a;
-    memset(&a, 0, sizeof(a));
-    a.dk_part = w.dk_part; a.dv_part = w.dv_part; a.dk_img = w.dk_img; a.dv_img = w.dv_img;
-    a.tiles_per_sample = tps; a.dkq = dkq; a.dv = dv;
+    const long long n8 = (long long)rows * (dkq + dv) / 8;
     {
       LaunchScope ls("tok_grad_sum", st);
-      tok::tok_grad_sum_kernel<<<tiles, 256, 0, st>>>(a);
+      tok::tok_grad_sum_kernel<<<int(std::min<long long>((n8 + 255) / 256, 8LL * di.sms)), 256, 0, st>>>(w.part[0], w.part[1], dkq + dv,
+                                                                                                       rows, gkv, ldkv);
     }
     MMRCA_CUDA(cudaGetLastError());
   }
-  {
-    LaunchScope ls("tok_x_image", st);
-    tok::tok_x_image_kernel<<<tiles, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x_q), L, tps, kq, static_cast<uint8_t*>(w.xq_img));
-    if (!self)
-      tok::tok_x_image_kernel<<<tiles, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x_kv), L, tps, kkv, static_cast<uint8_t*>(w.xkv_img));
-  }
-  MMRCA_CUDA(cudaGetLastError());
   // weight gradients
   {
     tok::WgradArgs a;
     memset(&a, 0, sizeof(a));
-    a.tiles = tiles;
+    a.rows = rows;
     if (self) {
-      a.seg[0] = {w.dq_img, grads->wq, dkq}; a.seg[1] = {w.dk_img, grads->wk, dkq}; a.seg[2] = {w.dv_img, grads->wv, dv};
-      a.x_img = w.xq_img; a.K = kq;
-      if ((rc = launch_tok_wgrad(a, 3, di.sms, st))) return rc;
+      a.out[0] = {grads->wq, 0, dkq}; a.out[1] = {grads->wk, dkq, dkq}; a.out[2] = {grads->wv, 2 * dkq, dv}; a.nout = 3;
+      a.NG = 2 * dkq + dv; a.K = kq;
+      if ((rc = launch_tok_wgrad(a, x_q, w.g, ldq, di.sms, st))) return rc;
     } else {
-      a.seg[0] = {w.dq_img, grads->wq, dkq};
-      a.x_img = w.xq_img; a.K = kq;
-      if ((rc = launch_tok_wgrad(a, 1, di.sms, st))) return rc;
-      a.seg[0] = {w.dk_img, grads->wk, dkq}; a.seg[1] = {w.dv_img, grads->wv, dv};
-      a.x_img = w.xkv_img; a.K = kkv;
-      if ((rc = launch_tok_wgrad(a, 2, di.sms, st))) return rc;
+      a.out[0] = {grads->wq, 0, dkq}; a.nout = 1; a.NG = dkq; a.K = kq;
+      if ((rc = launch_tok_wgrad(a, x_q, gq, ldq, di.sms, st))) return rc;
+      a.out[0] = {grads->wk, 0, dkq}; a.out[1] = {grads->wv, dkq, dv}; a.nout = 2; a.NG = dkq + dv; a.K = kkv;
+      if ((rc = launch_tok_wgrad(a, x_kv, gkv, ldkv, di.sms, st))) return rc;
     }
   }
-  // input gradients
+  // input gradients: the bf16 weights as they lie ([gradient column][d_in]: MN-major for this product)
   if (d_x_q || d_x_kv) {
-    tok::DgradArgs a;
-    memset(&a, 0, sizeof(a));
-    a.L = L; a.tiles_per_sample = tps;
     if (self) {
       if (!d_x_q) return fail(MMRCA_ERR_INVALID, "self attention: the input gradient goes to d_x_q%s%s");
-      const int N = 2 * dkq + dv;
-      if ((rc = launch_tok_wprep_mn(p->wq, dkq, kq, N, 0, w.wmn_q, di.sms, st))) return rc;
-      if ((rc = launch_tok_wprep_mn(p->wk, dkq, kq, N, dkq, w.wmn_q, di.sms, st))) return rc;
-      if ((rc = launch_tok_wprep_mn(p->wv, dv, kq, N, 2 * dkq, w.wmn_q, di.sms, st))) return rc;
-      a.seg[0] = {w.dq_img, dkq, 0}; a.seg[1] = {w.dk_img, dkq, dkq}; a.seg[2] = {w.dv_img, dv, 2 * dkq}; a.nseg = 3;
-      a.wmn = w.wmn_q; a.Ntot = N; a.dx = d_x_q; a.K = kq;
-      if ((rc = launch_tok_dgrad(a, tiles, st))) return rc;
+      const tok::Cast3Args ca = {{p->wq, p->wk, p->wv}, {w.wbf, w.wbf + size_t(dkq) * kq, w.wbf + size_t(2 * dkq) * kq},
+                                 {(long long)dkq * kq, (long long)dkq * kq, (long long)dv * kq}};
+      if ((rc = launch_cast3(ca, di.sms, st))) return rc;
+      if ((rc = launch_tok_dgrad(d_x_q, rows, kq, 2 * dkq + dv, w.g, ldq, w.wbf, st))) return rc;
     } else {
-      if (d_x_q) {
-        if ((rc = launch_tok_wprep_mn(p->wq, dkq, kq, dkq, 0, w.wmn_q, di.sms, st))) return rc;
-        a.seg[0] = {w.dq_img, dkq, 0}; a.nseg = 1;
-        a.wmn = w.wmn_q; a.Ntot = dkq; a.dx = d_x_q; a.K = kq;
-        if ((rc = launch_tok_dgrad(a, tiles, st))) return rc;
-      }
-      if (d_x_kv) {
-        if ((rc = launch_tok_wprep_mn(p->wk, dkq, kkv, dkq + dv, 0, w.wmn_kv, di.sms, st))) return rc;
-        if ((rc = launch_tok_wprep_mn(p->wv, dv, kkv, dkq + dv, dkq, w.wmn_kv, di.sms, st))) return rc;
-        a.seg[0] = {w.dk_img, dkq, 0}; a.seg[1] = {w.dv_img, dv, dkq}; a.nseg = 2;
-        a.wmn = w.wmn_kv; a.Ntot = dkq + dv; a.dx = d_x_kv; a.K = kkv;
-        if ((rc = launch_tok_dgrad(a, tiles, st))) return rc;
-      }
+      __nv_bfloat16* wkv = w.wbf + size_t(dkq) * kq;
+      const tok::Cast3Args ca = {{p->wq, p->wk, p->wv}, {w.wbf, wkv, wkv + size_t(dkq) * kkv},
+                                 {d_x_q ? (long long)dkq * kq : 0, d_x_kv ? (long long)dkq * kkv : 0, d_x_kv ? (long long)dv * kkv : 0}};
+      if ((rc = launch_cast3(ca, di.sms, st))) return rc;
+      if (d_x_q && (rc = launch_tok_dgrad(d_x_q, rows, kq, dkq, gq, ldq, w.wbf, st))) return rc;
+      if (d_x_kv && (rc = launch_tok_dgrad(d_x_kv, rows, kkv, dkq + dv, gkv, ldkv, wkv, st))) return rc;
     }
   }
   return MMRCA_OK;

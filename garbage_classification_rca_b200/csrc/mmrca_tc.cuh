@@ -178,6 +178,18 @@ __device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) { r
 
 // Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16: bf16 x bf16 -> fp32.
 // a_major / b_major: 0 = K-major, 1 = MN-major.
+// MN-major operand in the 128-byte-swizzled layout a {64 columns, rows} SWIZZLE_128B tensor-map box lands from row-major
+// [rows = K dimension][columns = M / N dimension] memory: 64-column blocks lbo_bytes apart, 8-row groups 1024 bytes apart;
+// one K = 16 step advances the start address by 2048 bytes.  (Validated by the mode-16 self test.)
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr >> 4) & 0x3FFF);
+  d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= uint64_t((1024u >> 4) & 0x3FFF) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(2) << 61;
+  return d;
+}
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_major, int b_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(a_major) << 15) | (uint32_t(b_major) << 16) |
          (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);

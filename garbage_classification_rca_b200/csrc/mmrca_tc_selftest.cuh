@@ -124,15 +124,6 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(int mode, const f
 // from a row-major [K][columns] source: per 64-column block, K rows of 128 bytes whose 16-byte chunks are XOR-swizzled by
 // (row % 8); blocks K * 128 bytes apart (the descriptor's leading-dimension offset), 8-row groups 1024 bytes apart (stride
 // offset), one K = 16 step = two row groups = 2048 bytes.  a: [K][128], b: [K][N]; out[128][N] = A^T B.
-__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= uint64_t((smem_addr >> 4) & 0x3FFF);
-  d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= uint64_t((1024u >> 4) & 0x3FFF) << 32;
-  d |= uint64_t(1) << 46;
-  d |= uint64_t(2) << 61;
-  return d;
-}
 __global__ void __launch_bounds__(128, 1) umma_mn128_selftest_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                                     float* __restrict__ out, int N, int K) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];

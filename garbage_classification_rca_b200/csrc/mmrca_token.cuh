@@ -223,24 +223,51 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
   }
 }
 
+// up to three fp32 -> bf16 casts in one launch (the stacked bf16 weights of the input-gradient GEMM)
+struct Cast3Args { const float* src[3]; __nv_bfloat16* dst[3]; long long n[3]; };
+__global__ void __launch_bounds__(256) cast3_bf16_kernel(const Cast3Args a) {
+#pragma unroll 1
+  for (int s = 0; s < 3; ++s) {
+    const float* __restrict__ src = a.src[s];
+    __nv_bfloat16* __restrict__ dst = a.dst[s];
+    const long long n = a.n[s];
+    for (long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * 1024) {
+      if (i + 3 < n) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
+        *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+      } else {
+        for (long long j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+      }
+    }
+  }
+}
+
 // W [n_rows][K] fp32 (rows n0 .. n0 + n_rows of the stacked [W_query; W_key; W_value]) -> bf16 blob laid out as the
 // shared-memory IMAGE the projection's B operand wants: [k-block of 64][N rows][128 bytes, 16-byte chunks XOR-swizzled
 // by (row % 8)] - what a {64, N} SWIZZLE_128B tensor-map box would land - so that a stage's whole weight slab is ONE
 // contiguous bulk copy instead of N row requests through the tiled-TMA path.  Columns beyond K are zero.
-__global__ void __launch_bounds__(256) tok_wprep_kernel(const float* __restrict__ w, int n_rows, int K, int N, int n0,
-                                                        uint8_t* __restrict__ blob) {
-  const int kblocks = (K + kBK - 1) / kBK;
-  const long long chunks = (long long)kblocks * n_rows * 8;      // 16-byte chunks
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < chunks; i += (long long)gridDim.x * 256) {
-    const int ch = int(i & 7);
-    const long long t = i >> 3;
-    const int n = int(t % n_rows), kb = int(t / n_rows);
-    const int k0 = kb * kBK + ch * 8;
-    float v[8];
+struct WprepSeg { const float* w; const float* bias; float* bias_dst; uint8_t* blob; int n_rows, K, N, n0; };
+struct WprepArgs { WprepSeg seg[3]; };
+__global__ void __launch_bounds__(256) tok_wprep_kernel(const WprepArgs a) {
+#pragma unroll 1
+  for (int sgi = 0; sgi < 3; ++sgi) {
+    const WprepSeg sg = a.seg[sgi];
+    if (sg.n_rows == 0) continue;
+    const int kblocks = (sg.K + kBK - 1) / kBK;
+    const long long chunks = (long long)kblocks * sg.n_rows * 8;      // 16-byte chunks
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < chunks; i += (long long)gridDim.x * 256) {
+      const int ch = int(i & 7);
+      const long long t = i >> 3;
+      const int n = int(t % sg.n_rows), kb = int(t / sg.n_rows);
+      const int k0 = kb * kBK + ch * 8;
+      float v[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = k0 + e < K ? __ldg(w + (size_t)n * K + k0 + e) : 0.f;
-    const int row = n0 + n;
-    *reinterpret_cast<uint4*>(blob + ((size_t)kb * N + row) * 128 + uint32_t((ch ^ (row & 7)) * 16)) = pack_bf16x8(v);
+      for (int e = 0; e < 8; ++e) v[e] = k0 + e < sg.K ? __ldg(sg.w + (size_t)n * sg.K + k0 + e) : 0.f;
+      const int row = sg.n0 + n;
+      *reinterpret_cast<uint4*>(sg.blob + ((size_t)kb * sg.N + row) * 128 + uint32_t((ch ^ (row & 7)) * 16)) = pack_bf16x8(v);
+    }
+    if (blockIdx.x == 0)
+      for (int i = threadIdx.x; i < sg.n_rows; i += 256) sg.bias_dst[i] = __ldg(sg.bias + i);
   }
 }
 

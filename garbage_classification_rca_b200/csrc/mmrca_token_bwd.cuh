@@ -5,20 +5,20 @@
 //                    weights P (bf16 image) and row sums: C = P V again (tensor core), LayerNorm + ReLU backward per row,
 //                    d(weights) = E V^T, softmax backward in place (P -> dS), dV = P^T E, dQ = dS K, dK = dS^T Q - five
 //                    tcgen05 chains, accumulators in TMEM.  dQ rows are the tile's own; dK / dV are per-query-tile partials.
-//                    All three leave the kernel as bf16 gradient IMAGES (what the two GEMMs below load) together with the
-//                    bias gradients (column sums, from the fp32 accumulators).
-//   tok_grad_sum     two-tile samples only: adds the two query tiles' dK / dV partial images
-//   tok_x_image      token activations [B, L, K] bf16 -> per-(sample, tile) images (tokens contiguous per 8-column group)
-//   tok_wgrad        dW[N][K] += dQKV^T X: both operands MN-major over the token dimension, split-K over the token tiles
-//   tok_dgrad        dX[B, L, K] = dQKV [W_query; W_key; W_value]: A = the gradient images (K-major), B = the bf16 weights
-//                    in [K/8][N][8] order read MN-major
+//                    All three leave the kernel as bf16 ROWS of the flat gradient matrices G [B * L][columns] (dQ times
+//                    1/sqrt(d_kq); dK | dV side by side), together with the bias gradients (column sums, from the fp32
+//                    accumulators).  Two-tile samples: dK | dV are per-query-tile partials that tok_grad_sum adds up.
+//   tok_wgrad        dW^T[K tile of 128][gradient columns] += X^T G over the flat token dimension: BOTH operands are read as
+//                    they lie in HBM - row-major [tokens][columns] is MN-major for this product - through tensor maps
+//                    ({64 columns, 64 tokens} boxes, 128-byte swizzle), three-stage TMA pipeline, split-K over the tokens.
+//   tok_dgrad        dX[B * L][K] = G [W_query; W_key; W_value]: A = G (K-major, TMA), B = the bf16 weights [columns][K] as they
+//                    lie (MN-major, TMA), fp32 rows out.
 #pragma once
 #include "mmrca_token.cuh"
 
 namespace mmrca {
 namespace tok {
 
-constexpr uint32_t kXGrp = kTile * 16;            // one 8-column group of an X image tile: 128 tokens x 16 bytes
 
 struct AttnBwdArgs {
   const void* q_img; const void* k_img; const void* v_img;     // the forward's operand images
@@ -26,19 +26,15 @@ struct AttnBwdArgs {
   const float* sum;         // [B * tiles][128] softmax row sums
   const float* ln_g; const float* ln_b;
   const float* d_out;       // [B][L][DV]
-  // bf16 gradient IMAGES (the layout of the forward's Q / K / V images: what tok_wgrad / tok_dgrad load), rows beyond L zero.
-  // dQ (times 1/sqrt(d_kq)) is final; dK / dV are final for one-tile samples, else per-query-tile partials that
-  // tok_grad_sum adds up.
-  void* dq_img;             // [B * tiles][op_bytes(DKQ)]
-  void* dk_out;             // one tile per sample: [B][op_bytes(DKQ)]; else [B * tiles (query tile)][tiles (key tile)][op_bytes(DKQ)]
-  void* dv_out;             // likewise, op_bytes(DV)
+  // bf16 gradient rows, token r = b * L + t: dQ (times 1/sqrt(d_kq)) -> g_q[r * ld_q + ..]; dK | dV -> dkv_out[query tile][r * ld_kv + ..]
+  // (one-tile samples: dkv_out[0] is the final matrix; else per-query-tile partials that tok_grad_sum adds up)
+  __nv_bfloat16* g_q; int ld_q;
+  __nv_bfloat16* dkv_out[kMaxTiles]; int ld_kv;
   float* g_bq; float* g_bk; float* g_bv;     // += column sums (atomics)
   float qscale;
   float* g_ln_g; float* g_ln_b;     // += (atomics)
   int L, tiles_per_sample, reverse;
-  long long* dbg;
 };
-#define TOK_STAMP(i) do { if (a.dbg && tid == 0 && blockIdx.x == 0) a.dbg[(i)] = clock64(); } while (0)
 
 template <int DKQ, int DV>
 struct AttnBwdSmem {
@@ -164,7 +160,6 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
 #pragma unroll
     for (int e = 0; e < HC; ++e) dy[e] = 0.f;
   }
-  TOK_STAMP(0);
   mbar_wait(&bars[0], 0);
   tc_fence_after_sync();
   // rows beyond the sample's L tokens were never written by the forward: they meet zero weights in the products below
@@ -202,7 +197,6 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  TOK_STAMP(1);
   // ---- C = P V, as the forward did -----------------------------------------------------------------------------------------
   if (tid == 0) {
     for (int j = 0; j < tps; ++j)
@@ -212,7 +206,6 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
   }
   mbar_wait(&bars[1], 0);
   tc_fence_after_sync();
-  TOK_STAMP(2);
   // ---- LayerNorm + ReLU backward of my row (:65-66, :105-106) -> E = d(P_un V) = d(context) / sum (reverse: * -1/(L-1)) ------
   {
     float x[HC];
@@ -284,7 +277,6 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
   tc_fence_after_sync();
   if (a.reverse && tid < DV)      // d(colsum V) of the tile (vsum is dead: reuse); read after the softmax phase's barrier
     vsum[tid] = slots[2 * DV + tid] + slots[S::NS + 2 * DV + tid] + slots[2 * S::NS + 2 * DV + tid] + slots[3 * S::NS + 2 * DV + tid];
-  TOK_STAMP(3);
   // ---- d(weights) = E V^T (per key tile, N = 128) and dV = P^T E (per key tile, M = 128 keys) ------------------------------------
   if (tid == 0) {
     for (int j = 0; j < tps; ++j)
@@ -297,7 +289,6 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
   }
   mbar_wait(&bars[1], 1);
   tc_fence_after_sync();
-  TOK_STAMP(4);
   // the value tiles are dead: the query tile takes their place
   if (tid == 0) {
     mbar_arrive_expect_tx(&bars[0], S::QB);
@@ -339,7 +330,6 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
       }
     }
   }
-  TOK_STAMP(5);
   // ---- drain dV: my row is KEY 128 j + row of key tile j ------------------------------------------------------------------------
   {
     float vtot[HC];
@@ -353,20 +343,21 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
       tmem_wait_ld();
       const int key = j * kTile + row;
       const bool add_t = a.reverse && key < L;        // every valid key's value row feeds colsum(V)
-      uint8_t* dst = static_cast<uint8_t*>(a.dv_out) + (tps == 1 ? size_t(b) : tile_idx * tps + j) * S::VB + row_off(row);
+      __nv_bfloat16* dst = a.dkv_out[mt] + (size_t(b) * L + key) * a.ld_kv + DKQ + HC * half;
       float v[HC];
 #pragma unroll
       for (int e = 0; e < HC; ++e) {
         v[e] = __uint_as_float(raw[e]) + (add_t ? vsum[HC * half + e] : 0.f);
         vtot[e] += v[e];
       }
+      if (key < L) {
 #pragma unroll
-      for (int g8 = 0; g8 < HC / 8; ++g8)
-        *reinterpret_cast<uint4*>(dst + uint32_t((HC / 8) * half + g8) * kCS) = pack_bf16x8(*reinterpret_cast<const float(*)[8]>(&v[8 * g8]));
+        for (int g8 = 0; g8 < HC / 8; ++g8)
+          *reinterpret_cast<uint4*>(dst + 8 * g8) = pack_bf16x8(*reinterpret_cast<const float(*)[8]>(&v[8 * g8]));
+      }
     }
     warp_col_sums(vtot, lane, myslot + SLOT_B + 2 * DKQ + HC * half);
   }
-  TOK_STAMP(6);
   mbar_wait(&bars[0], 1);                           // the query tile has landed
   for (int i = tid; i < (kTile - qpad0) * (DKQ / 8); i += 256) {
     const int r = qpad0 + i / (DKQ / 8), g = i % (DKQ / 8);
@@ -376,7 +367,6 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  TOK_STAMP(7);
   // ---- dQ = dS K (accumulated over the key tiles), dK = dS^T Q (per key tile) ------------------------------------------------------
   if (tid == 0) {
     for (int j = 0; j < tps; ++j)
@@ -387,7 +377,6 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
                      make_smem_desc(smem_u32(sq), kRS, kCS), 2 * kRS, make_idesc_bf16(128, DKQ, 1, 1), 8, false);
     umma_commit(&bars[1]);
   }
-  TOK_STAMP(8);
   // LayerNorm-affine gradients of this tile
   if (tid < DV) {
     atomicAdd(a.g_ln_g + tid, slots[tid] + slots[S::NS + tid] + slots[2 * S::NS + tid] + slots[3 * S::NS + tid]);
@@ -395,9 +384,8 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
   }
   mbar_wait(&bars[1], 0);
   tc_fence_after_sync();
-  TOK_STAMP(9);
   {
-    uint8_t* dst = static_cast<uint8_t*>(a.dq_img) + tile_idx * S::QB + row_off(row);
+    __nv_bfloat16* dst = a.g_q + (size_t(b) * L + t) * a.ld_q + HQ * half;
     const uint32_t tq = tmem + lane_base + COL_DQ + HQ * half;
     uint32_t r[HQ];
 #pragma unroll
@@ -406,19 +394,20 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
     float v[HQ];
 #pragma unroll
     for (int e = 0; e < HQ; ++e) v[e] = __uint_as_float(r[e]) * a.qscale;      // scores = (q / sqrt(d_kq)) . k
+    if (valid) {
 #pragma unroll
-    for (int g8 = 0; g8 < HQ / 8; ++g8)
-      *reinterpret_cast<uint4*>(dst + uint32_t((HQ / 8) * half + g8) * kCS) = pack_bf16x8(*reinterpret_cast<const float(*)[8]>(&v[8 * g8]));
-    TOK_STAMP(10);
+      for (int g8 = 0; g8 < HQ / 8; ++g8)
+        *reinterpret_cast<uint4*>(dst + 8 * g8) = pack_bf16x8(*reinterpret_cast<const float(*)[8]>(&v[8 * g8]));
+    }
     warp_col_sums(v, lane, myslot + SLOT_B + HQ * half);
   }
-  TOK_STAMP(11);
   {
   float ktot[HQ];
 #pragma unroll
   for (int e = 0; e < HQ; ++e) ktot[e] = 0.f;
   for (int j = 0; j < tps; ++j) {
-    uint8_t* dst = static_cast<uint8_t*>(a.dk_out) + (tps == 1 ? size_t(b) : tile_idx * tps + j) * S::QB + row_off(row);
+    const int key = j * kTile + row;
+    __nv_bfloat16* dst = a.dkv_out[mt] + (size_t(b) * L + key) * a.ld_kv + HQ * half;
     const uint32_t tk = tmem + lane_base + COL_DK + DKQ * j + HQ * half;
     uint32_t r[HQ];
 #pragma unroll
@@ -427,192 +416,160 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
     float v[HQ];
 #pragma unroll
     for (int e = 0; e < HQ; ++e) { v[e] = __uint_as_float(r[e]); ktot[e] += v[e]; }
+    if (key < L) {
 #pragma unroll
-    for (int g8 = 0; g8 < HQ / 8; ++g8)
-      *reinterpret_cast<uint4*>(dst + uint32_t((HQ / 8) * half + g8) * kCS) = pack_bf16x8(*reinterpret_cast<const float(*)[8]>(&v[8 * g8]));
+      for (int g8 = 0; g8 < HQ / 8; ++g8)
+        *reinterpret_cast<uint4*>(dst + 8 * g8) = pack_bf16x8(*reinterpret_cast<const float(*)[8]>(&v[8 * g8]));
+    }
   }
-  TOK_STAMP(12);
   warp_col_sums(ktot, lane, myslot + SLOT_B + DKQ + HQ * half);
   }
-  TOK_STAMP(13);
   __syncthreads();
   for (int i = tid; i < 2 * DKQ + DV; i += 256) {
     const float* sl = slots + SLOT_B + i;
     atomicAdd(i < DKQ ? a.g_bq + i : (i < 2 * DKQ ? a.g_bk + (i - DKQ) : a.g_bv + (i - 2 * DKQ)),
               sl[0] + sl[S::NS] + sl[2 * S::NS] + sl[3 * S::NS]);
   }
-  TOK_STAMP(14);
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-// ---- two-tile samples: dK / dV image of key tile (b, j) = sum over the query tiles m of the partial images ((b, m), j) ----------
-struct GradSumArgs { const void* dk_part; const void* dv_part; void* dk_img; void* dv_img; int tiles_per_sample, dkq, dv; };
-__global__ void __launch_bounds__(256) tok_grad_sum_kernel(const GradSumArgs a) {
-  const int tps = a.tiles_per_sample, b = blockIdx.x / tps, j = blockIdx.x - b * tps;
-  for (int seg = 0; seg < 2; ++seg) {
-    const uint32_t n16 = htc::op_bytes(seg ? a.dv : a.dkq) / 16;
-    const uint4* src = static_cast<const uint4*>(seg ? a.dv_part : a.dk_part);
-    uint4* dst = static_cast<uint4*>(seg ? a.dv_img : a.dk_img) + size_t(blockIdx.x) * n16;
-    for (uint32_t i = threadIdx.x; i < n16; i += 256) {
-      float acc[8], v[8];
-      unpack_bf16x8(__ldg(src + ((size_t(b) * tps) * tps + j) * n16 + i), acc);
-      for (int m = 1; m < tps; ++m) {
-        unpack_bf16x8(__ldg(src + ((size_t(b) * tps + m) * tps + j) * n16 + i), v);
+// ---- two-tile samples: dK | dV rows = sum of the two query tiles' partial rows ------------------------------------------------------
+__global__ void __launch_bounds__(256) tok_grad_sum_kernel(const __nv_bfloat16* __restrict__ p0, const __nv_bfloat16* __restrict__ p1,
+                                                           int width, long long rows, __nv_bfloat16* __restrict__ out, int ld_out) {
+  const int w8 = width / 8;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < rows * w8; i += (long long)gridDim.x * 256) {
+    const long long r = i / w8;
+    const int c = int(i - r * w8) * 8;
+    float x[8], y[8];
+    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p0 + r * width + c)), x);
+    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p1 + r * width + c)), y);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] += v[e];
-      }
-      dst[i] = pack_bf16x8(acc);
-    }
-  }
-}
-
-// x [B][L][K] bf16 -> [B * tiles][K / 8][128 tokens][8], rows beyond L zero.  Eight column groups at a time through shared
-// memory: 128-byte row pieces in (one sector-complete read per 8 lanes), 512-byte runs of one group out.
-__global__ void __launch_bounds__(256) tok_x_image_kernel(const __nv_bfloat16* __restrict__ x, int L, int tps, int K,
-                                                          uint8_t* __restrict__ img) {
-  __shared__ uint4 st[8 * 129];
-  const int b = blockIdx.x / tps, j = blockIdx.x - b * tps, G = K / 8, tid = threadIdx.x;
-  for (int g0 = 0; g0 < G; g0 += 8) {
-    const int ng = min(8, G - g0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = tid + 256 * i, r = idx >> 3, g = idx & 7, t = j * kTile + r;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (t < L && g < ng) v = __ldg(reinterpret_cast<const uint4*>(x + (size_t(b) * L + t) * K + 8 * (g0 + g)));
-      st[g * 129 + r] = v;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = tid + 256 * i, g = idx >> 7, r = idx & 127;
-      if (g < ng) *reinterpret_cast<uint4*>(img + (size_t(blockIdx.x) * G + g0 + g) * kXGrp + uint32_t(r) * 16) = st[g * 129 + r];
-    }
-    __syncthreads();
-  }
-}
-
-// W [n_rows][K] fp32 (rows n0 .. of the stacked [W_query; W_key; W_value]) -> bf16 [K / 8][N][8]: the dgrad GEMM's B operand
-__global__ void __launch_bounds__(256) tok_wprep_mn_kernel(const float* __restrict__ w, int n_rows, int K, int N, int n0,
-                                                           uint8_t* __restrict__ blob) {
-  const int G = K / 8;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < (long long)n_rows * G; i += (long long)gridDim.x * 256) {
-    const int n = int(i / G), g = int(i - (long long)n * G);
-    const float4 v0 = __ldg(reinterpret_cast<const float4*>(w + (size_t)n * K + 8 * g));
-    const float4 v1 = __ldg(reinterpret_cast<const float4*>(w + (size_t)n * K + 8 * g + 4));
-    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-    *reinterpret_cast<uint4*>(blob + ((size_t)g * N + n0 + n) * 16) = pack_bf16x8(v);
+    for (int e = 0; e < 8; ++e) x[e] += y[e];
+    *reinterpret_cast<uint4*>(out + r * ld_out + c) = pack_bf16x8(x);
   }
 }
 
 // ---- weight gradients ---------------------------------------------------------------------------------------------------------------
 constexpr int kGradThreads = 192;                 // producer warp, MMA warp, 4 epilogue warps
-constexpr int kGradStages = 2;
-constexpr uint32_t kGradABytes = htc::op_bytes(128);      // 33 024
-constexpr uint32_t kGradBBytes = 32 * kXGrp;              // 256 columns x 128 tokens: 64 KB
-struct GradSmem {
-  static constexpr uint32_t A = 0, B = htc::al128(A + kGradStages * kGradABytes), BAR = B + kGradStages * kGradBBytes, BYTES = BAR + 128;
-  static_assert(BYTES <= 232448, "token gradient GEMMs do not fit shared memory");
-};
-struct WgradSeg { const void* img; float* g_w; int cols; };      // gradient image [tiles][op_bytes(cols)]; dW [cols][K] +=
-struct WgradArgs { WgradSeg seg[3]; const void* x_img; int K, tiles; };
+constexpr int kGradStages = 3;
+constexpr int kGradKT = 64;                       // tokens per pipeline stage
+constexpr uint32_t kBoxBytes = 64 * 128;          // one {64 columns, 64 rows} bf16 box, 128-byte swizzled: 8 KB
+constexpr int kMaxGBlocks = 6;                    // gradient columns <= 384
 
-// grid = (ceil(K / 256), segments, splits of the token tiles); D[m = gradient column][n = X column] over k = token
-__global__ void __launch_bounds__(kGradThreads, 1) tok_wgrad_kernel(const WgradArgs a) {
-  extern __shared__ __align__(128) uint8_t sm[];
-  using S = GradSmem;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sm + S::BAR);
+struct WgradOut { float* g_w; int n0, cols; };    // gradient columns [n0, n0 + cols) -> dW [cols][K] +=  (n0, cols: multiples of 16)
+struct WgradArgs { WgradOut out[3]; int nout, NG, K, rows; };
+
+// grid = (ceil(K / 128), splits of the 64-token chunks).  D[m = X column][n = gradient column] over k = token.
+// tm_x: X [rows][K], tm_g: G [rows][NG]; both with {64, 64} boxes: per stage 2 boxes of X columns, ceil(NG / 64) of G.
+__global__ void __launch_bounds__(kGradThreads, 1) tok_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x,
+                                                                    const __grid_constant__ CUtensorMap tm_g, const WgradArgs a) {
+  extern __shared__ __align__(1024) uint8_t sm_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~uintptr_t(1023));
+  const int nblk = (a.NG + 63) / 64;
+  const uint32_t stage = uint32_t(2 + nblk) * kBoxBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + kGradStages * stage);
   uint64_t* empty = full + kGradStages;
   uint64_t* accb = empty + kGradStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accb + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const WgradSeg sg = a.seg[blockIdx.y];
-  const int nt = blockIdx.x, G = a.K / 8, gb = min(32, G - nt * 32), bn = gb * 8;
-  const int t0 = int((long long)a.tiles * blockIdx.z / gridDim.z), t1 = int((long long)a.tiles * (blockIdx.z + 1) / gridDim.z);
-  const int n_it = t1 - t0;
+  const int m0 = blockIdx.x * 128;
+  const int chunks = (a.rows + kGradKT - 1) / kGradKT;
+  const int c0 = int((long long)chunks * blockIdx.y / gridDim.y), c1 = int((long long)chunks * (blockIdx.y + 1) / gridDim.y);
+  const int n_it = c1 - c0;
   if (n_it <= 0) return;
-  const uint32_t a_bytes = htc::op_bytes(sg.cols), b_bytes = uint32_t(gb) * kXGrp;
   if (tid == 0) {
     for (int i = 0; i < 2 * kGradStages + 1; ++i) mbar_init(&full[i], 1);
     mbar_fence_init();
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_g);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  // accumulators: the gradient columns [0, n1) and, beyond 256 columns, [192, NG) - both starting on a 64-column box
+  const int n1 = a.NG <= 256 ? a.NG : 192, n2 = a.NG - n1;
   if (warp == 0) {
     if (lane == 0) {
-      const uint8_t* pa = static_cast<const uint8_t*>(sg.img);
-      const uint8_t* pb = static_cast<const uint8_t*>(a.x_img) + size_t(nt) * 32 * kXGrp;
       for (int it = 0; it < n_it; ++it) {
-        const int s = it % kGradStages;
+        const int s = it % kGradStages, tok0 = (c0 + it) * kGradKT;
         if (it >= kGradStages) mbar_wait(&empty[s], uint32_t(it / kGradStages - 1) & 1u);
-        mbar_arrive_expect_tx(&full[s], a_bytes + b_bytes);
-        bulk_g2s(sm + S::A + s * kGradABytes, pa + size_t(t0 + it) * a_bytes, a_bytes, &full[s]);
-        bulk_g2s(sm + S::B + s * kGradBBytes, pb + size_t(t0 + it) * G * kXGrp, b_bytes, &full[s]);
+        mbar_arrive_expect_tx(&full[s], stage);
+        uint8_t* st = sm + s * stage;
+        tma_load_2d(st, &tm_x, m0, tok0, &full[s]);
+        tma_load_2d(st + kBoxBytes, &tm_x, m0 + 64, tok0, &full[s]);
+        for (int j = 0; j < nblk; ++j) tma_load_2d(st + (2 + j) * kBoxBytes, &tm_g, 64 * j, tok0, &full[s]);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, bn, 1, 1);
+      const uint32_t idesc1 = make_idesc_bf16(128, n1, 1, 1), idesc2 = make_idesc_bf16(128, n2 > 0 ? n2 : 16, 1, 1);
       for (int it = 0; it < n_it; ++it) {
         const int s = it % kGradStages;
         mbar_wait(&full[s], uint32_t(it / kGradStages) & 1u);
         tc_fence_after_sync();
-        const uint64_t ad = make_smem_desc(smem_u32(sm + S::A + s * kGradABytes), kRS, kCS);
-        const uint64_t bd = make_smem_desc(smem_u32(sm + S::B + s * kGradBBytes), 128, kXGrp);
+        const uint32_t st = smem_u32(sm + s * stage);
+        const uint64_t ad = make_smem_desc_sw128_mn(st, kBoxBytes);
+        const uint64_t bd1 = make_smem_desc_sw128_mn(st + 2 * kBoxBytes, kBoxBytes);
+        const uint64_t bd2 = make_smem_desc_sw128_mn(st + 5 * kBoxBytes, kBoxBytes);
 #pragma unroll
-        for (int ks = 0; ks < kTile / 16; ++ks)
-          umma_bf16(tmem, desc_advance(ad, ks * 2 * kRS), desc_advance(bd, ks * 256), idesc, (it | ks) ? 1u : 0u);
+        for (int ks = 0; ks < kGradKT / 16; ++ks) {
+          umma_bf16(tmem, desc_advance(ad, ks * 2048), desc_advance(bd1, ks * 2048), idesc1, (it | ks) ? 1u : 0u);
+          if (n2 > 0) umma_bf16(tmem + 192, desc_advance(ad, ks * 2048), desc_advance(bd2, ks * 2048), idesc2, (it | ks) ? 1u : 0u);
+        }
         umma_commit(&empty[s]);
       }
       umma_commit(accb);
     }
   } else {
-    const int q = warp & 3, row = 32 * q + lane;
-    float* dst = sg.g_w + size_t(row) * a.K + nt * 256;
+    const int q = warp & 3, gm = m0 + 32 * q + lane;
     mbar_wait(accb, 0);
     tc_fence_after_sync();
 #pragma unroll 1
-    for (int c0 = 0; c0 < bn; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld16_nw(tmem + (uint32_t(32 * q) << 16) + c0, r);
-      tmem_wait_ld();
-      if (row < sg.cols) {
+    for (int o = 0; o < a.nout; ++o) {
+      const WgradOut out = a.out[o];
+      float* dst = out.g_w + gm;
+#pragma unroll 1
+      for (int c = 0; c < out.cols; c += 16) {
+        uint32_t r[16];
+        tmem_ld16_nw(tmem + (uint32_t(32 * q) << 16) + uint32_t(out.n0 + c), r);
+        tmem_wait_ld();
+        if (gm < a.K) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) atomicAdd(dst + c0 + e, __uint_as_float(r[e]));
+          for (int e = 0; e < 16; ++e) atomicAdd(dst + size_t(c + e) * a.K, __uint_as_float(r[e]));      // lanes: consecutive floats
+        }
       }
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 256);
+  if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
 // ---- input gradients ------------------------------------------------------------------------------------------------------------------
-struct DgradSeg { const void* img; int cols; int woff; };      // gradient image; rows [woff, woff + cols) of the stacked weight
-struct DgradArgs {
-  DgradSeg seg[3]; int nseg;
-  const void* wmn;          // bf16 [K / 8][Ntot][8] (tok_wprep_mn_kernel)
-  int Ntot;
-  float* dx;                // [B][L][K]
-  int L, tiles_per_sample, K;
-};
-// grid = (B * tiles, ceil(K / 256)); one pipeline stage per segment (K dimension = the segment's gradient columns)
-__global__ void __launch_bounds__(kGradThreads, 1) tok_dgrad_kernel(const DgradArgs a) {
-  extern __shared__ __align__(128) uint8_t sm[];
-  using S = GradSmem;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sm + S::BAR);
+struct DgradArgs { float* dx; int rows, K, NG; };     // dx [rows][K] = G [rows][NG] W [NG][K]
+// grid = (ceil(rows / 128), ceil(K / 256)).  tm_g: G with {64 columns, 128 rows} boxes (K-major A), tm_w: bf16 W [NG][K] with
+// {64 columns, 64 rows} boxes (MN-major B); one stage per 64 gradient columns.
+__global__ void __launch_bounds__(kGradThreads, 1) tok_dgrad_kernel(const __grid_constant__ CUtensorMap tm_g,
+                                                                    const __grid_constant__ CUtensorMap tm_w, const DgradArgs a) {
+  extern __shared__ __align__(1024) uint8_t sm_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~uintptr_t(1023));
+  const int n0 = blockIdx.y * 256, bn = min(256, a.K - n0), nb = (bn + 63) / 64;
+  const uint32_t a_bytes = kTile * 128, stage = a_bytes + uint32_t(nb) * kBoxBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm + kGradStages * stage);
   uint64_t* empty = full + kGradStages;
   uint64_t* accb = empty + kGradStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accb + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.x, nt = blockIdx.y, G = a.K / 8, gb = min(32, G - nt * 32), bn = gb * 8;
+  const int row0 = blockIdx.x * kTile, n_it = (a.NG + 63) / 64;
   if (tid == 0) {
     for (int i = 0; i < 2 * kGradStages + 1; ++i) mbar_init(&full[i], 1);
     mbar_fence_init();
+    tma_prefetch_desc(&tm_g);
+    tma_prefetch_desc(&tm_w);
   }
   if (warp == 1) tmem_alloc(tmem_slot, 256);
   tc_fence_before_sync();
@@ -621,49 +578,45 @@ __global__ void __launch_bounds__(kGradThreads, 1) tok_dgrad_kernel(const DgradA
   const uint32_t tmem = *tmem_slot;
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < a.nseg; ++it) {
-        const DgradSeg sg = a.seg[it];
+      for (int it = 0; it < n_it; ++it) {
         const int s = it % kGradStages;
         if (it >= kGradStages) mbar_wait(&empty[s], uint32_t(it / kGradStages - 1) & 1u);
-        const uint32_t a_bytes = htc::op_bytes(sg.cols), col_bytes = uint32_t(sg.cols) * 16;
-        mbar_arrive_expect_tx(&full[s], a_bytes + uint32_t(gb) * col_bytes);
-        bulk_g2s(sm + S::A + s * kGradABytes, static_cast<const uint8_t*>(sg.img) + size_t(tile) * a_bytes, a_bytes, &full[s]);
-        const uint8_t* pb = static_cast<const uint8_t*>(a.wmn) + (size_t(nt) * 32 * a.Ntot + sg.woff) * 16;
-#pragma unroll 1
-        for (int g = 0; g < gb; ++g)
-          bulk_g2s(sm + S::B + s * kGradBBytes + uint32_t(g) * col_bytes, pb + size_t(g) * a.Ntot * 16, col_bytes, &full[s]);
+        mbar_arrive_expect_tx(&full[s], stage);
+        uint8_t* st = sm + s * stage;
+        tma_load_2d(st, &tm_g, 64 * it, row0, &full[s]);
+        for (int j = 0; j < nb; ++j) tma_load_2d(st + a_bytes + j * kBoxBytes, &tm_w, n0 + 64 * j, 64 * it, &full[s]);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, bn, 0, 1);
-      for (int it = 0; it < a.nseg; ++it) {
-        const DgradSeg sg = a.seg[it];
+      for (int it = 0; it < n_it; ++it) {
         const int s = it % kGradStages;
         mbar_wait(&full[s], uint32_t(it / kGradStages) & 1u);
         tc_fence_after_sync();
-        const uint64_t ad = make_smem_desc(smem_u32(sm + S::A + s * kGradABytes), kCS, kRS);
-        const uint64_t bd = make_smem_desc(smem_u32(sm + S::B + s * kGradBBytes), 128, uint32_t(sg.cols) * 16);
-        for (int ks = 0; ks < sg.cols / 16; ++ks)
-          umma_bf16(tmem, desc_advance(ad, ks * 2 * kCS), desc_advance(bd, ks * 256), idesc, (it | ks) ? 1u : 0u);
+        const uint32_t st = smem_u32(sm + s * stage);
+        const uint64_t ad = make_smem_desc_sw128(st);
+        const uint64_t bd = make_smem_desc_sw128_mn(st + a_bytes, kBoxBytes);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_bf16(tmem, desc_advance(ad, ks * 32), desc_advance(bd, ks * 2048), idesc, (it | ks) ? 1u : 0u);
         umma_commit(&empty[s]);
       }
       umma_commit(accb);
     }
   } else {
-    const int q = warp & 3, row = 32 * q + lane;
-    const int b = tile / a.tiles_per_sample, t = (tile - b * a.tiles_per_sample) * kTile + row;
-    float* dst = a.dx + (size_t(b) * a.L + t) * a.K + nt * 256;
+    const int q = warp & 3, r = row0 + 32 * q + lane;
+    float* dst = a.dx + size_t(r) * a.K + n0;
     mbar_wait(accb, 0);
     tc_fence_after_sync();
 #pragma unroll 1
-    for (int c0 = 0; c0 < bn; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld16_nw(tmem + (uint32_t(32 * q) << 16) + c0, r);
+    for (int c = 0; c < bn; c += 16) {
+      uint32_t v[16];
+      tmem_ld16_nw(tmem + (uint32_t(32 * q) << 16) + uint32_t(c), v);
       tmem_wait_ld();
-      if (t < a.L) {
+      if (r < a.rows) {
 #pragma unroll
-        for (int e = 0; e < 16; e += 4) *reinterpret_cast<uint4*>(dst + c0 + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+        for (int e = 0; e < 16; e += 4) *reinterpret_cast<uint4*>(dst + c + e) = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
       }
     }
   }

@@ -29,6 +29,7 @@ for (L, K, dkq, dv, cross) in [(197, 1024, 128, 96, False), (256, 768, 128, 96, 
     torch.cuda.synchronize()
     N.timing_begin(256)
     for _ in range(3):
+        blk.refresh_weights()
         blk(x, x2)
         blk.backward(d_out, grads, cross, cross)
     recs = N.timing_end(256)
