@@ -774,7 +774,9 @@ def run_full(args, rank, world, local_rank):
 
 def run_token(args, rank, world, local_rank):
     """Secondary workload (BASELINE.json configs[4] / SURVEY.md §8 d cfg 5): the attention blocks on real token sequences,
-    forward, `--batch` samples per GPU (replicas: inference shards by batch, no collective):
+    forward + backward (parameter gradients of the four blocks, input gradients of the cross blocks; the weight images are
+    rebuilt from the fp32 parameters every step, as after an optimizer step), `--batch` samples per GPU, data parallel with
+    one all-reduce of the gradient bucket; `--token-forward-only`: inference replicas, no collective:
       SelfAttention(1024 -> 128 / 96) on ViT-L/16 tokens [B, 197, 1024], SelfAttention(768 -> 128 / 96) on RoBERTa tokens
       [B, 256, 768], and a ReverseCrossAttention(96 -> 64 / 48) on each sequence length (the reference asserts square
       attention, multimodal_model.py:93: the partner sequence is the block output of the neighbouring sample).
@@ -836,6 +838,8 @@ def run_token(args, rank, world, local_rank):
         dq_t, dkv_t = ca_t.backward(d_ca_t, views[3], True, True)
         sa_i.backward(dq_i + torch.roll(dkv_i, -1, 0), views[0])
         sa_t.backward(dq_t + torch.roll(dkv_t, -1, 0), views[1])
+        if world > 1:   # data parallel: one all-reduce of the flat gradient bucket (1.3 M floats) per step
+            dist.all_reduce(flat_g)
 
     for i in range(W):
         one(i)
@@ -891,8 +895,9 @@ def run_token(args, rank, world, local_rank):
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"token-level attention blocks {'forward + backward' if train else 'forward'} (BASELINE.json configs[4]): SelfAttention on ViT-L/16 tokens "
                                    f"[{B},197,1024] and RoBERTa tokens [{B},256,768], ReverseCrossAttention 96->64/48 at L=197 and L=256; "
-                                   f"batch {B}/GPU, replicas (no collective); secondary workload",
-                       "parallelism": f"replicas x{world}", "l2": f"inputs rotate over {NB} batches"},
+                                   f"batch {B}/GPU, " + ("data parallel: one NCCL all-reduce of the flat gradient bucket per step"
+                                                         if train else "replicas (no collective)") + "; secondary workload",
+                       "parallelism": f"dp{world}" if train else f"replicas x{world}", "l2": f"inputs rotate over {NB} batches"},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "tok_proj [B*197 x 1024] x [1024 x 352]", "achieved": ach,
                          "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],

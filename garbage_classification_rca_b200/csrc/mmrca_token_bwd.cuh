@@ -108,8 +108,8 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
   extern __shared__ __align__(128) uint8_t sm[];
   using S = AttnBwdSmem<DKQ, DV>;
   constexpr int HC = DV / 2, HQ = DKQ / 2;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::BAR);      // [0] loads, [1] MMAs
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::BAR);      // [0] V, P loads; then Q  [1] MMAs  [2] K load  [3] the dQ chain
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   float* ln_s = reinterpret_cast<float*>(sm + S::LN);
   float* vsum = reinterpret_cast<float*>(sm + S::VSUM);
   float* slots = reinterpret_cast<float*>(sm + S::ACC);
@@ -123,15 +123,16 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
   const size_t tile_idx = size_t(b) * tps + mt;
   uint8_t *sk = sm + S::K, *sv = sm + S::VQ, *sq = sm + S::VQ, *sp = sm + S::P, *se = sm + S::E;
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
-    mbar_arrive_expect_tx(&bars[0], uint32_t(tps) * (S::QB + S::VB + 16 * kCS));
-    for (int j = 0; j < tps; ++j) {
-      bulk_g2s(sk + j * S::QB, static_cast<const uint8_t*>(a.k_img) + (size_t(b) * tps + j) * S::QB, S::QB, &bars[0]);
+    mbar_arrive_expect_tx(&bars[0], uint32_t(tps) * (S::VB + 16 * kCS));
+    for (int j = 0; j < tps; ++j)
       bulk_g2s(sv + j * S::VB, static_cast<const uint8_t*>(a.v_img) + (size_t(b) * tps + j) * S::VB, S::VB, &bars[0]);
-    }
     bulk_g2s(sp, static_cast<const uint8_t*>(a.p_img) + tile_idx * S::PB, uint32_t(tps) * 16 * kCS, &bars[0]);
+    // the key tiles are not needed before the dQ / dK chains: their own barrier, behind the operands of the first products
+    mbar_arrive_expect_tx(&bars[2], uint32_t(tps) * S::QB);
+    for (int j = 0; j < tps; ++j)
+      bulk_g2s(sk + j * S::QB, static_cast<const uint8_t*>(a.k_img) + (size_t(b) * tps + j) * S::QB, S::QB, &bars[2]);
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   for (int i = tid; i < DV; i += 256) { ln_s[i] = a.ln_g[i]; ln_s[DV + i] = a.ln_b[i]; }
@@ -169,11 +170,6 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
     for (int i = tid; i < (kTile - kpad0) * (DV / 8); i += 256) {
       const int r = kpad0 + i / (DV / 8), g = i % (DV / 8);
       *reinterpret_cast<uint4*>(vlast + uint32_t(g) * kCS + row_off(r)) = make_uint4(0u, 0u, 0u, 0u);
-    }
-    uint8_t* klast = sk + (tps - 1) * S::QB;
-    for (int i = tid; i < (kTile - kpad0) * (DKQ / 8); i += 256) {
-      const int r = kpad0 + i / (DKQ / 8), g = i % (DKQ / 8);
-      *reinterpret_cast<uint4*>(klast + uint32_t(g) * kCS + row_off(r)) = make_uint4(0u, 0u, 0u, 0u);
     }
     const int pg = ncols / 8;
     for (int i = tid; i < (kTile - qpad0) * pg; i += 256) {
@@ -330,6 +326,36 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
       }
     }
   }
+  // the query tile and the key tiles have landed; their rows beyond L must be finite (zero)
+  mbar_wait(&bars[0], 1);
+  mbar_wait(&bars[2], 0);
+  for (int i = tid; i < (kTile - qpad0) * (DKQ / 8); i += 256) {
+    const int r = qpad0 + i / (DKQ / 8), g = i % (DKQ / 8);
+    *reinterpret_cast<uint4*>(sq + uint32_t(g) * kCS + row_off(r)) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  {
+    uint8_t* klast = sk + (tps - 1) * S::QB;
+    for (int i = tid; i < (kTile - kpad0) * (DKQ / 8); i += 256) {
+      const int r = kpad0 + i / (DKQ / 8), g = i % (DKQ / 8);
+      *reinterpret_cast<uint4*>(klast + uint32_t(g) * kCS + row_off(r)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  // ---- dK = dS^T Q (per key tile) into the columns the softmax backward has just released; runs while dV is drained --------------
+  if (tid == 0) {
+    for (int j = 0; j < tps; ++j)
+      htc::mma_steps(tmem + COL_DK + DKQ * j, make_smem_desc(smem_u32(sp + uint32_t(16 * j) * kCS), kRS, kCS), 2 * kRS,
+                     make_smem_desc(smem_u32(sq), kRS, kCS), 2 * kRS, make_idesc_bf16(128, DKQ, 1, 1), 8, false);
+    umma_commit(&bars[1]);
+  }
+  // LayerNorm-affine gradients of this tile
+  if (tid < DV) {
+    atomicAdd(a.g_ln_g + tid, slots[tid] + slots[S::NS + tid] + slots[2 * S::NS + tid] + slots[3 * S::NS + tid]);
+    atomicAdd(a.g_ln_b + tid, slots[DV + tid] + slots[S::NS + DV + tid] + slots[2 * S::NS + DV + tid] + slots[3 * S::NS + DV + tid]);
+  }
   // ---- drain dV: my row is KEY 128 j + row of key tile j ------------------------------------------------------------------------
   {
     float vtot[HC];
@@ -358,49 +384,18 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
     }
     warp_col_sums(vtot, lane, myslot + SLOT_B + 2 * DKQ + HC * half);
   }
-  mbar_wait(&bars[0], 1);                           // the query tile has landed
-  for (int i = tid; i < (kTile - qpad0) * (DKQ / 8); i += 256) {
-    const int r = qpad0 + i / (DKQ / 8), g = i % (DKQ / 8);
-    *reinterpret_cast<uint4*>(sq + uint32_t(g) * kCS + row_off(r)) = make_uint4(0u, 0u, 0u, 0u);
-  }
-  fence_proxy_async();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  // ---- dQ = dS K (accumulated over the key tiles), dK = dS^T Q (per key tile) ------------------------------------------------------
+  // ---- dQ = dS K (accumulated over the key tiles) into the drained dV columns; runs while dK is drained ------------------------------
   if (tid == 0) {
     for (int j = 0; j < tps; ++j)
       htc::mma_steps(tmem + COL_DQ, make_smem_desc(smem_u32(sp + uint32_t(16 * j) * kCS), kCS, kRS), 2 * kCS,
                      make_smem_desc(smem_u32(sk + j * S::QB), kRS, kCS), 2 * kRS, make_idesc_bf16(128, DKQ, 0, 1), 8, j > 0);
-    for (int j = 0; j < tps; ++j)
-      htc::mma_steps(tmem + COL_DK + DKQ * j, make_smem_desc(smem_u32(sp + uint32_t(16 * j) * kCS), kRS, kCS), 2 * kRS,
-                     make_smem_desc(smem_u32(sq), kRS, kCS), 2 * kRS, make_idesc_bf16(128, DKQ, 1, 1), 8, false);
-    umma_commit(&bars[1]);
-  }
-  // LayerNorm-affine gradients of this tile
-  if (tid < DV) {
-    atomicAdd(a.g_ln_g + tid, slots[tid] + slots[S::NS + tid] + slots[2 * S::NS + tid] + slots[3 * S::NS + tid]);
-    atomicAdd(a.g_ln_b + tid, slots[DV + tid] + slots[S::NS + DV + tid] + slots[2 * S::NS + DV + tid] + slots[3 * S::NS + DV + tid]);
+    umma_commit(&bars[3]);
   }
   mbar_wait(&bars[1], 0);
   tc_fence_after_sync();
-  {
-    __nv_bfloat16* dst = a.g_q + (size_t(b) * L + t) * a.ld_q + HQ * half;
-    const uint32_t tq = tmem + lane_base + COL_DQ + HQ * half;
-    uint32_t r[HQ];
-#pragma unroll
-    for (int c0 = 0; c0 < HQ; c0 += 16) tmem_ld16_nw(tq + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[c0]));
-    tmem_wait_ld();
-    float v[HQ];
-#pragma unroll
-    for (int e = 0; e < HQ; ++e) v[e] = __uint_as_float(r[e]) * a.qscale;      // scores = (q / sqrt(d_kq)) . k
-    if (valid) {
-#pragma unroll
-      for (int g8 = 0; g8 < HQ / 8; ++g8)
-        *reinterpret_cast<uint4*>(dst + 8 * g8) = pack_bf16x8(*reinterpret_cast<const float(*)[8]>(&v[8 * g8]));
-    }
-    warp_col_sums(v, lane, myslot + SLOT_B + HQ * half);
-  }
   {
   float ktot[HQ];
 #pragma unroll
@@ -423,6 +418,25 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
     }
   }
   warp_col_sums(ktot, lane, myslot + SLOT_B + DKQ + HQ * half);
+  }
+  mbar_wait(&bars[3], 0);
+  tc_fence_after_sync();
+  {
+    __nv_bfloat16* dst = a.g_q + (size_t(b) * L + t) * a.ld_q + HQ * half;
+    const uint32_t tq = tmem + lane_base + COL_DQ + HQ * half;
+    uint32_t r[HQ];
+#pragma unroll
+    for (int c0 = 0; c0 < HQ; c0 += 16) tmem_ld16_nw(tq + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[c0]));
+    tmem_wait_ld();
+    float v[HQ];
+#pragma unroll
+    for (int e = 0; e < HQ; ++e) v[e] = __uint_as_float(r[e]) * a.qscale;      // scores = (q / sqrt(d_kq)) . k
+    if (valid) {
+#pragma unroll
+      for (int g8 = 0; g8 < HQ / 8; ++g8)
+        *reinterpret_cast<uint4*>(dst + 8 * g8) = pack_bf16x8(*reinterpret_cast<const float(*)[8]>(&v[8 * g8]));
+    }
+    warp_col_sums(v, lane, myslot + SLOT_B + HQ * half);
   }
   __syncthreads();
   for (int i = tid; i < 2 * DKQ + DV; i += 256) {
