@@ -284,16 +284,20 @@ struct AttnArgs {
 template <int DKQ, int DV>
 struct AttnSmem {
   static constexpr uint32_t QB = htc::op_bytes(DKQ), VB = htc::op_bytes(DV), PB = htc::op_bytes(kMaxTiles * kTile);
+  // The cross blocks (64 / 48) run TWO CTAs per SM: the attention weights P overwrite the key tiles (dead once the scores
+  // are in TMEM), which brings a CTA under half the shared memory, and the context accumulator reuses the score columns
+  // (256 TMEM columns per CTA).  The 128 / 96 blocks do not fit twice either way and keep separate regions.
+  static constexpr bool kTwoPerSm = DKQ == 64;
   static constexpr uint32_t Q = 0;
   static constexpr uint32_t K = htc::al128(Q + QB);                     // kMaxTiles key tiles
-  static constexpr uint32_t V = htc::al128(K + kMaxTiles * QB);         // kMaxTiles value tiles
-  static constexpr uint32_t P = htc::al128(V + kMaxTiles * VB);         // [128 x 256] unnormalised attention weights
-  static constexpr uint32_t LN = htc::al128(P + PB);                    // gamma, beta
+  static constexpr uint32_t V = htc::al128(K + (kTwoPerSm ? PB : kMaxTiles * QB));      // kMaxTiles value tiles
+  static constexpr uint32_t P = kTwoPerSm ? K : htc::al128(V + kMaxTiles * VB);         // [128 x 256] unnormalised attention weights
+  static constexpr uint32_t LN = htc::al128(kTwoPerSm ? V + kMaxTiles * VB : P + PB);   // gamma, beta
   static constexpr uint32_t VSUM = LN + 2 * DV * 4;                     // column sums of V over the valid keys (reverse weights)
   static constexpr uint32_t PART = VSUM + DV * 4;                       // [2 halves][128 rows] float2 exchange
   static constexpr uint32_t BAR = htc::al128(PART + 2 * kTile * 8);
   static constexpr uint32_t BYTES = BAR + 64;
-  static_assert(BYTES <= 232448, "token attention does not fit shared memory");
+  static_assert(BYTES <= (kTwoPerSm ? 113 * 1024 : 232448), "token attention does not fit shared memory");
 };
 
 // 256 threads: two threads per query row (warp w reads TMEM lanes 32 (w % 4) .., half = w / 4 takes every other 16-column
@@ -304,7 +308,7 @@ struct AttnSmem {
 // from the same unnormalised product: ((1 - A) V)[c] = colsum(V)[c] - (P_un V)[c] / sum, with colsum(V) over the sample's
 // L valid keys computed once per CTA.
 template <int DKQ, int DV>
-__global__ void __launch_bounds__(256, 1) tok_attn_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(256, DKQ == 64 ? 2 : 1) tok_attn_kernel(const AttnArgs a) {
   extern __shared__ __align__(128) uint8_t sm[];
   using S = AttnSmem<DKQ, DV>;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + S::BAR);      // [0] loads, [1] MMAs
@@ -328,14 +332,15 @@ __global__ void __launch_bounds__(256, 1) tok_attn_kernel(const AttnArgs a) {
       bulk_g2s(sv + j * S::VB, static_cast<const uint8_t*>(a.v_img) + (size_t(b) * tps + j) * S::VB, S::VB, &bars[0]);
     }
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  constexpr uint32_t kTmemCols = S::kTwoPerSm ? 256 : 512;
+  if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
   for (int i = tid; i < DV; i += 256) { ln_s[i] = a.ln_g[i]; ln_s[DV + i] = a.ln_b[i]; }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const uint32_t lane_base = uint32_t(32 * q) << 16;
-  constexpr uint32_t COL_S = 0, COL_C = 256;
+  constexpr uint32_t COL_S = 0, COL_C = S::kTwoPerSm ? 0 : 256;      // (two per SM: the context reuses the score columns)
   const int L = a.L, ncols = tps * kTile;
   mbar_wait(&bars[0], 0);
   tc_fence_after_sync();
@@ -479,7 +484,7 @@ __global__ void __launch_bounds__(256, 1) tok_attn_kernel(const AttnArgs a) {
   if (a.p_out && tid == 32) bulk_wait_all();
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 512);
+  if (warp == 0) tmem_dealloc(tmem, kTmemCols);
 }
 
 }  // namespace tok

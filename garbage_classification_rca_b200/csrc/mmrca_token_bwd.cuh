@@ -291,6 +291,9 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
     bulk_g2s(sq, static_cast<const uint8_t*>(a.q_img) + tile_idx * S::QB, S::QB, &bars[0]);
   }
   // ---- softmax backward in place: dS = P_un (dA' - dot / sum), dot = sum_j dA'_j P_un_j (dA' = dA / sum: E carries 1/sum) -----
+  // (measured and dropped: dot = E . (P_un V) from the LayerNorm phase's registers, which saves the first pass (2 us per
+  //  launch) - but the fp32 dot no longer matches the bf16 products term by term, the rows of dS stop summing to zero and
+  //  d(b_key), analytically zero, picks up noise at 1.5 % of d(b_query)'s scale)
   {
     const uint32_t ta = tmem + lane_base + COL_DA;
     const int nchunks = ncols / 16;
