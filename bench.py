@@ -803,8 +803,12 @@ def run_token(args, rank, world, local_rank):
     x_txt = [torch.randn(B, 256, 768, generator=g).bfloat16().to(dev) for _ in range(NB)]
     train = not args.token_forward_only
     blocks = [block(1024, 1024, 128, 96), block(768, 768, 128, 96), block(96, 96, 64, 48), block(96, 96, 64, 48)]
-    sa_i = F.TokenAttention(blocks[0], B, 197, training=train)
-    sa_t = F.TokenAttention(blocks[1], B, 256, training=train)
+    sa_i = F.TokenAttention(blocks[0], B, 197, training=train, out_dtype=torch.bfloat16)
+    sa_t = F.TokenAttention(blocks[1], B, 256, training=train, out_dtype=torch.bfloat16)
+    # the self blocks write bf16 straight into samples 1 .. B of a [B + 1] buffer; sample 0 is a copy of sample B: samples
+    # 1 .. B are the queries, samples 0 .. B - 1 the partner sequence (two contiguous views, no rolled copy)
+    ext_i = torch.zeros(B + 1, 197, 96, dtype=torch.bfloat16, device=dev)
+    ext_t = torch.zeros(B + 1, 256, 96, dtype=torch.bfloat16, device=dev)
     ca_i = F.TokenAttention(blocks[2], B, 197, reverse=True, training=train)
     ca_t = F.TokenAttention(blocks[3], B, 256, reverse=True, training=train)
     # gradient bucket: one flat fp32 buffer, the per-tensor views go to the backward calls; zeroed once per step
@@ -824,11 +828,12 @@ def run_token(args, rank, world, local_rank):
         if train:       # a training step follows an optimizer step: the bf16 weight images are rebuilt from the fp32 parameters
             for blk in (sa_i, sa_t, ca_i, ca_t):
                 blk.refresh_weights()
-        i_sa = sa_i(x_img[i % NB])
-        t_sa = sa_t(x_txt[i % NB])
-        i_16, t_16 = i_sa.to(torch.bfloat16), t_sa.to(torch.bfloat16)
-        ca_i(i_16, torch.roll(i_16, 1, 0))
-        ca_t(t_16, torch.roll(t_16, 1, 0))
+        sa_i(x_img[i % NB], out=ext_i[1:])
+        sa_t(x_txt[i % NB], out=ext_t[1:])
+        ext_i[0].copy_(ext_i[B])
+        ext_t[0].copy_(ext_t[B])
+        ca_i(ext_i[1:], ext_i[:B])
+        ca_t(ext_t[1:], ext_t[:B])
         if not train:
             return
         # backward of the four blocks: the cross blocks hand d(SA output) back (query side + the rolled key/value side),
@@ -836,8 +841,11 @@ def run_token(args, rank, world, local_rank):
         flat_g.zero_()
         dq_i, dkv_i = ca_i.backward(d_ca_i, views[2], True, True)
         dq_t, dkv_t = ca_t.backward(d_ca_t, views[3], True, True)
-        sa_i.backward(dq_i + torch.roll(dkv_i, -1, 0), views[0])
-        sa_t.backward(dq_t + torch.roll(dkv_t, -1, 0), views[1])
+        for dq, dkv in ((dq_i, dkv_i), (dq_t, dkv_t)):      # d(SA output of sample b) = dq[b] + dkv[b + 1] (partner of b + 1)
+            dq[:-1] += dkv[1:]
+            dq[-1] += dkv[0]
+        sa_i.backward(dq_i, views[0])
+        sa_t.backward(dq_t, views[1])
         if world > 1:   # data parallel: one all-reduce of the flat gradient bucket (1.3 M floats) per step
             dist.all_reduce(flat_g)
 

@@ -87,6 +87,7 @@ class TokenDesc(C.Structure):
 
 TOKEN_WEIGHTS_READY = 1
 TOKEN_TRAINING = 2
+TOKEN_OUT_BF16 = 4
 
 
 class CeDesc(C.Structure):

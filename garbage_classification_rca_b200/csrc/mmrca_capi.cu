@@ -883,6 +883,7 @@ static int make_tensor_map(CUtensorMap* tm, const void* base, uint64_t cols, uin
                                                      "d_in a multiple of 8)%s%s");
   return MMRCA_OK;
 }
+constexpr int kMaxSms = 160;      // bound on the split-K slabs of the token weight-gradient GEMM (B200: 148 SMs)
 struct TokenWorkspace {
   __nv_bfloat16* w;       // stacked bf16 weights: self [2 d_kq + d_v][d_in]; cross [d_kq][d_in_q] then [d_kq + d_v][d_in_kv]
   float* bias;            // stacked [2 d_kq + d_v]
@@ -891,6 +892,7 @@ struct TokenWorkspace {
   void* p_img; float* sum;
   __nv_bfloat16* g;             // gradient rows: self [rows][2 d_kq + d_v]; cross [rows][d_kq] then [rows][d_kq + d_v]
   __nv_bfloat16* part[2];       // two-tile samples: per-query-tile dK | dV partial rows [rows][d_kq + d_v]
+  float* wg_part;               // weight-gradient split-K slabs [splits][columns][d_in], splits * ceil(d_in / 128) <= SMs
   __nv_bfloat16* wbf;           // bf16 weights as they lie: self [2 d_kq + d_v][d_in]; cross [d_kq][d_in_q] then [d_kq + d_v][d_in_kv]
   size_t bytes;
 };
@@ -914,6 +916,7 @@ static TokenWorkspace token_carve(const MmrcaTokenDesc& d, void* base) {
     w.g = static_cast<__nv_bfloat16*>(take(rows * size_t(2 * d.d_kq + d.d_v) * 2));
     for (int i = 0; i < 2; ++i)
       w.part[i] = tps > 1 ? static_cast<__nv_bfloat16*>(take(rows * size_t(d.d_kq + d.d_v) * 2)) : nullptr;
+    w.wg_part = static_cast<float*>(take(size_t(kMaxSms) * size_t(2 * d.d_kq + d.d_v) * 128 * 4));
     w.wbf = static_cast<__nv_bfloat16*>(take((size_t(d.d_kq) * d.d_in_q + size_t(d.d_kq + d.d_v) * d.d_in_kv) * 2));
   }
   w.bytes = off;
@@ -1001,7 +1004,7 @@ static int launch_tok_attn_bwd(const MmrcaTokenDesc& d, const tok::AttnBwdArgs& 
   return MMRCA_OK;
 }
 // dW += G^T X for the gradient columns listed in a.out (x [rows][K] bf16, g [rows][NG] bf16 with row pitch ld_g)
-static int launch_tok_wgrad(tok::WgradArgs a, const void* x, const __nv_bfloat16* g, int ld_g, int sms, cudaStream_t st) {
+static int launch_tok_wgrad(tok::WgradArgs a, const void* x, const __nv_bfloat16* g, int ld_g, float* part, int sms, cudaStream_t st) {
   int rc;
   CUtensorMap tx, tg;
   if ((rc = make_tensor_map(&tx, x, uint64_t(a.K), uint64_t(a.rows), uint64_t(a.K), tok::kGradKT))) return rc;
@@ -1009,10 +1012,20 @@ static int launch_tok_wgrad(tok::WgradArgs a, const void* x, const __nv_bfloat16
   const int nblk = (a.NG + 63) / 64, mtiles = (a.K + 127) / 128, chunks = (a.rows + tok::kGradKT - 1) / tok::kGradKT;
   const size_t smem = size_t(tok::kGradStages) * (2 + nblk) * tok::kBoxBytes + 128 + 1024;
   if ((rc = set_smem(tok::tok_wgrad_kernel, smem))) return rc;
-  const int splits = std::max(1, std::min(chunks, sms / mtiles));
+  const int splits = std::max(1, std::min(chunks, std::min(sms, kMaxSms) / mtiles));
+  a.part = part;
   {
     LaunchScope ls("tok_wgrad", st);
     tok::tok_wgrad_kernel<<<dim3(mtiles, splits), tok::kGradThreads, smem, st>>>(tx, tg, a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
+  {
+    LaunchScope ls("tok_wgrad_reduce", st);
+    const long long quads = (long long)a.NG * a.K / 4;
+    if (quads >= 32768)
+      tok::tok_wgrad_reduce_kernel<1><<<int(std::min<long long>((quads + 255) / 256, 16LL * sms)), 256, 0, st>>>(a, splits);
+    else
+      tok::tok_wgrad_reduce_kernel<8><<<int(std::min<long long>((quads + 31) / 32, 16LL * sms)), 256, 0, st>>>(a, splits);
   }
   MMRCA_CUDA(cudaGetLastError());
   return MMRCA_OK;
@@ -1401,6 +1414,7 @@ int mmrca_token_attention_forward(const MmrcaTokenDesc* desc, const MmrcaAttnPar
   a.q_img = w.q_img; a.k_img = w.k_img; a.v_img = w.v_img; a.ln_g = p->ln_g; a.ln_b = p->ln_b; a.out = out;
   a.L = desc->seq_len; a.tiles_per_sample = (desc->seq_len + tok::kTile - 1) / tok::kTile; a.reverse = desc->reverse ? 1 : 0;
   a.p_out = w.p_img; a.sum_out = w.sum;      // null unless MMRCA_TOKEN_TRAINING
+  a.out_bf16 = (desc->flags & MMRCA_TOKEN_OUT_BF16) ? 1 : 0;
   return dkq == 128 ? launch_tok_attn<128, 96>(*desc, a, st) : launch_tok_attn<64, 48>(*desc, a, st);
 }
 
@@ -1461,12 +1475,12 @@ int mmrca_token_attention_backward(const MmrcaTokenDesc* desc, const MmrcaAttnPa
     if (self) {
       a.out[0] = {grads->wq, 0, dkq}; a.out[1] = {grads->wk, dkq, dkq}; a.out[2] = {grads->wv, 2 * dkq, dv}; a.nout = 3;
       a.NG = 2 * dkq + dv; a.K = kq;
-      if ((rc = launch_tok_wgrad(a, x_q, w.g, ldq, di.sms, st))) return rc;
+      if ((rc = launch_tok_wgrad(a, x_q, w.g, ldq, w.wg_part, di.sms, st))) return rc;
     } else {
       a.out[0] = {grads->wq, 0, dkq}; a.nout = 1; a.NG = dkq; a.K = kq;
-      if ((rc = launch_tok_wgrad(a, x_q, gq, ldq, di.sms, st))) return rc;
+      if ((rc = launch_tok_wgrad(a, x_q, gq, ldq, w.wg_part, di.sms, st))) return rc;
       a.out[0] = {grads->wk, 0, dkq}; a.out[1] = {grads->wv, dkq, dv}; a.nout = 2; a.NG = dkq + dv; a.K = kkv;
-      if ((rc = launch_tok_wgrad(a, x_kv, gkv, ldkv, di.sms, st))) return rc;
+      if ((rc = launch_tok_wgrad(a, x_kv, gkv, ldkv, w.wg_part, di.sms, st))) return rc;
     }
   }
   // input gradients: the bf16 weights as they lie ([gradient column][d_in]: MN-major for this product)

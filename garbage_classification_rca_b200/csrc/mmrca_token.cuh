@@ -275,7 +275,8 @@ __global__ void __launch_bounds__(256) tok_wprep_kernel(const WprepArgs a) {
 struct AttnArgs {
   const void* q_img; const void* k_img; const void* v_img;     // [B][tiles][cols/8 * kCS] operand images (tok_proj)
   const float* ln_g; const float* ln_b;
-  float* out;               // [B][L][DV] fp32
+  float* out;               // [B][L][DV] fp32 (or, out_bf16 != 0, bf16: what a following block reads)
+  int out_bf16;
   void* p_out;              // training: the unnormalised attention weights, [B * tiles][op_bytes(256)] bf16 images (null: not kept)
   float* sum_out;           // training: their row sums [B * tiles][128]
   int L, tiles_per_sample, reverse;
@@ -467,17 +468,18 @@ __global__ void __launch_bounds__(256, DKQ == 64 ? 2 : 1) tok_attn_kernel(const 
     const float rstd = rsqrtf(fmaxf((s2 + o.y) * (1.0f / float(DV)) - mean * mean, 0.f) + kLnEps);
     const int t = mt * kTile + row;
     if (t < L) {
-      float* dst = a.out + (size_t(b) * L + t) * DV + HC * half;
       const float* gam = ln_s + HC * half;
       const float* bet = ln_s + DV + HC * half;
 #pragma unroll
-      for (int e = 0; e < HC; e += 4) {
-        float4 v;
-        v.x = fmaxf(fmaf((x[e] - mean) * rstd, gam[e], bet[e]), 0.f);
-        v.y = fmaxf(fmaf((x[e + 1] - mean) * rstd, gam[e + 1], bet[e + 1]), 0.f);
-        v.z = fmaxf(fmaf((x[e + 2] - mean) * rstd, gam[e + 2], bet[e + 2]), 0.f);
-        v.w = fmaxf(fmaf((x[e + 3] - mean) * rstd, gam[e + 3], bet[e + 3]), 0.f);
-        *reinterpret_cast<float4*>(dst + e) = v;
+      for (int e = 0; e < HC; ++e) x[e] = fmaxf(fmaf((x[e] - mean) * rstd, gam[e], bet[e]), 0.f);
+      if (a.out_bf16) {
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.out) + (size_t(b) * L + t) * DV + HC * half;
+#pragma unroll
+        for (int e = 0; e < HC; e += 8) *reinterpret_cast<uint4*>(dst + e) = pack_bf16x8(*reinterpret_cast<const float(*)[8]>(&x[e]));
+      } else {
+        float* dst = a.out + (size_t(b) * L + t) * DV + HC * half;
+#pragma unroll
+        for (int e = 0; e < HC; e += 4) *reinterpret_cast<float4*>(dst + e) = make_float4(x[e], x[e + 1], x[e + 2], x[e + 3]);
       }
     }
   }

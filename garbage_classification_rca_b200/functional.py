@@ -787,7 +787,9 @@ class TokenAttention:
     block under torch.autograd."""
 
     def __init__(self, params: Sequence[torch.Tensor], batch: int, seq_len: int, *, d_in_kv: Optional[int] = None,
-                 reverse: bool = False, training: bool = False):
+                 reverse: bool = False, training: bool = False, out_dtype: torch.dtype = torch.float32):
+        if out_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("out_dtype must be torch.float32 or torch.bfloat16")
         self.param_tensors = list(params)
         self.training = training
         self._saved = None
@@ -798,17 +800,24 @@ class TokenAttention:
         kkv = self.params[2].shape[1]
         if d_in_kv is not None and d_in_kv != kkv:
             raise ValueError("d_in_kv does not match W_key")
-        self.desc = N.TokenDesc(batch, seq_len, d_in_q, kkv, d_kq, d_v, 1 if reverse else 0, N.TOKEN_TRAINING if training else 0)
+        self.desc = N.TokenDesc(batch, seq_len, d_in_q, kkv, d_kq, d_v, 1 if reverse else 0,
+                                (N.TOKEN_TRAINING if training else 0) | (N.TOKEN_OUT_BF16 if out_dtype == torch.bfloat16 else 0))
         self.ap = _attn_struct(self.params)
         nbytes = N.lib().mmrca_token_attention_workspace_bytes(C.byref(self.desc))
         if nbytes == 0:
             raise ValueError("unsupported token attention shape: " + N.last_error())
         self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        self.out = torch.empty(batch, seq_len, d_v, dtype=torch.float32, device=dev)
+        self.out = torch.empty(batch, seq_len, d_v, dtype=out_dtype, device=dev)
         self.device = dev
 
-    def __call__(self, x_q: torch.Tensor, x_kv: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def __call__(self, x_q: torch.Tensor, x_kv: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """out: optional destination (contiguous, [B, L, d_v], the block's out_dtype) instead of the block's own buffer."""
         d = self.desc
+        if out is None:
+            out = self.out
+        elif (tuple(out.shape) != tuple(self.out.shape) or out.dtype != self.out.dtype or not out.is_contiguous()
+              or out.device != self.device):
+            raise ValueError("out must be a contiguous tensor shaped and typed like the block's output")
         xs = []
         for x, k, what in ((x_q, d.d_in_q, "x_q"), (x_kv, d.d_in_kv, "x_kv")):
             if x is None:
@@ -823,11 +832,11 @@ class TokenAttention:
         with torch.cuda.device(self.device):
             N.check(N.lib().mmrca_token_attention_forward(
                 C.byref(self.desc), C.byref(self.ap), xs[0].data_ptr(), xs[1].data_ptr() if xs[1] is not None else None,
-                self.out.data_ptr(), self.ws.data_ptr(), self.ws.numel(), _stream_ptr(self.device)),
+                out.data_ptr(), self.ws.data_ptr(), self.ws.numel(), _stream_ptr(self.device)),
                 "mmrca_token_attention_forward")
         self.desc.flags |= N.TOKEN_WEIGHTS_READY      # the bf16 weights now sit in the workspace
         self._saved = (xs[0], xs[1])
-        return self.out
+        return out
 
     def backward(self, d_out: torch.Tensor, grads: Sequence[torch.Tensor], need_dx_q: bool = False,
                  need_dx_kv: bool = False) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:

@@ -278,6 +278,7 @@ int mmrca_hier_train_step(const MmrcaHierDesc* desc, const MmrcaHierParams* para
                                        unchanged parameters on the same workspace): skip their conversion */
 #define MMRCA_TOKEN_TRAINING 2u      /* the forward keeps the attention weights for mmrca_token_attention_backward (larger
                                        workspace; set on the descriptor of the workspace query, forward and backward) */
+#define MMRCA_TOKEN_OUT_BF16 4u      /* forward: `out` is bf16 [B, L, d_v] (the activation format of a following block) instead of fp32 */
 typedef struct MmrcaTokenDesc {
   int32_t batch, seq_len, d_in_q, d_in_kv, d_kq, d_v;
   int32_t reverse;    /* (1 - A) / (L - 1) weights (:95-99) */

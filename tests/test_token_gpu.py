@@ -194,3 +194,20 @@ def test_token_attention_under_autograd(pkg):
     assert _rel(xg.grad, x64.grad) < TOK_GRAD_LIMIT
     with pytest.raises(RuntimeError):
         F.TokenAttention([t.detach() for t in params], B, L).backward(out.detach(), [torch.zeros_like(t) for t in params])
+
+
+def test_token_attention_bf16_output_into_a_caller_buffer(pkg):
+    """out_dtype=bfloat16 + out=: a block writes the next block's activation format straight into a caller's buffer."""
+    from garbage_classification_rca_b200 import functional as F
+    B, L, K = 3, 100, 256
+    p = _block_params("sa", K, K, 128, 96, seed=11)
+    x = torch.randn(B, L, K, generator=torch.Generator().manual_seed(2)).bfloat16().cuda()
+    params = [p[f"sa.{l}"].cuda() for l in LEAVES]
+    ref = F.TokenAttention(params, B, L)(x).clone()
+    ext = torch.zeros(B + 1, L, 96, dtype=torch.bfloat16, device="cuda")
+    out = F.TokenAttention(params, B, L, out_dtype=torch.bfloat16)(x, out=ext[1:])
+    torch.cuda.synchronize()
+    assert out.data_ptr() == ext[1:].data_ptr() and ext[0].abs().max().item() == 0
+    assert torch.equal(ext[1:], ref.to(torch.bfloat16))
+    with pytest.raises(ValueError):
+        F.TokenAttention(params, B, L, out_dtype=torch.bfloat16)(x, out=torch.zeros(B, L, 96, device="cuda"))
