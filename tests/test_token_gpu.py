@@ -116,8 +116,8 @@ def _gate_mask(out_product, out_oracle):
     return ((out_product.cpu() > 0) & (out_oracle > 0)).float()
 
 
-@pytest.mark.parametrize("B,L,K", [(3, 197, 1024), (2, 256, 768), (4, 16, 96), (1, 77, 208), (2, 129, 1024)],
-                         ids=["vit_l16", "roberta", "pseudo_tokens", "ragged", "two_tiles_ragged"])
+@pytest.mark.parametrize("B,L,K", [(3, 197, 1024), (2, 256, 768), (4, 16, 96), (1, 77, 208), (2, 129, 1024), (3, 5, 32), (2, 128, 64)],
+                         ids=["vit_l16", "roberta", "pseudo_tokens", "ragged", "two_tiles_ragged", "tiny", "one_full_tile"])
 def test_token_self_attention_backward_matches_oracle(pkg, B, L, K):
     from garbage_classification_rca_b200 import functional as F
     p = _block_params("sa", K, K, 128, 96, seed=L + K, gain=2.0)
@@ -148,7 +148,7 @@ def test_token_self_attention_backward_matches_oracle(pkg, B, L, K):
 
 
 @pytest.mark.parametrize("reverse", [True, False], ids=["rca", "ca"])
-@pytest.mark.parametrize("B,L", [(3, 197), (2, 256), (4, 16), (1, 100)])
+@pytest.mark.parametrize("B,L", [(3, 197), (2, 256), (4, 16), (1, 100), (2, 3), (1, 128)])
 def test_token_cross_attention_backward_matches_oracle(pkg, B, L, reverse):
     from garbage_classification_rca_b200 import functional as F
     p = _block_params("ca", 96, 96, 64, 48, seed=7 * L + int(reverse), gain=2.0)
