@@ -824,29 +824,44 @@ def run_token(args, rank, world, local_rank):
     d_ca_i = (torch.randn(B, 197, 48, generator=g) / (B * 197)).to(dev)
     d_ca_t = (torch.randn(B, 256, 48, generator=g) / (B * 256)).to(dev)
 
-    def one(i):
+    # the image and the text branch are independent (self block -> cross block -> backward of both): each runs on its own
+    # stream, so one branch's CTAs fill the SMs the other's last wave leaves idle (every attention kernel is ~3.5 waves
+    # of one-CTA-per-SM work).  The per-kernel timing pass below runs them on one stream.
+    s_img, s_txt = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def branch(sa, ca, x, ext, d_ca, v_sa, v_ca):
         if train:       # a training step follows an optimizer step: the bf16 weight images are rebuilt from the fp32 parameters
-            for blk in (sa_i, sa_t, ca_i, ca_t):
-                blk.refresh_weights()
-        sa_i(x_img[i % NB], out=ext_i[1:])
-        sa_t(x_txt[i % NB], out=ext_t[1:])
-        ext_i[0].copy_(ext_i[B])
-        ext_t[0].copy_(ext_t[B])
-        ca_i(ext_i[1:], ext_i[:B])
-        ca_t(ext_t[1:], ext_t[:B])
+            sa.refresh_weights()
+            ca.refresh_weights()
+        sa(x, out=ext[1:])
+        ext[0].copy_(ext[B])
+        ca(ext[1:], ext[:B])
         if not train:
             return
-        # backward of the four blocks: the cross blocks hand d(SA output) back (query side + the rolled key/value side),
-        # the self blocks stop at the frozen backbone's tokens (no input gradient)
-        flat_g.zero_()
-        dq_i, dkv_i = ca_i.backward(d_ca_i, views[2], True, True)
-        dq_t, dkv_t = ca_t.backward(d_ca_t, views[3], True, True)
-        for dq, dkv in ((dq_i, dkv_i), (dq_t, dkv_t)):      # d(SA output of sample b) = dq[b] + dkv[b + 1] (partner of b + 1)
-            dq[:-1] += dkv[1:]
-            dq[-1] += dkv[0]
-        sa_i.backward(dq_i, views[0])
-        sa_t.backward(dq_t, views[1])
-        if world > 1:   # data parallel: one all-reduce of the flat gradient bucket (1.3 M floats) per step
+        # backward: the cross block hands d(SA output) back (query side + the partner side), the self block stops at the
+        # frozen backbone's tokens (no input gradient)
+        dq, dkv = ca.backward(d_ca, v_ca, True, True)
+        dq[:-1] += dkv[1:]      # d(SA output of sample b) = dq[b] + dkv[b + 1] (b is the partner of b + 1)
+        dq[-1] += dkv[0]
+        sa.backward(dq, v_sa)
+
+    def one(i, two_streams=True):
+        if train:
+            flat_g.zero_()
+        jobs = ((s_img, (sa_i, ca_i, x_img[i % NB], ext_i, d_ca_i, views[0], views[2])),
+                (s_txt, (sa_t, ca_t, x_txt[i % NB], ext_t, d_ca_t, views[1], views[3])))
+        if two_streams:
+            cur = torch.cuda.current_stream(dev)
+            for st, job in jobs:
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    branch(*job)
+            for st, _ in jobs:
+                cur.wait_stream(st)
+        else:
+            for _, job in jobs:
+                branch(*job)
+        if train and world > 1:   # data parallel: one all-reduce of the flat gradient bucket (1.3 M floats) per step
             dist.all_reduce(flat_g)
 
     for i in range(W):
@@ -868,7 +883,7 @@ def run_token(args, rank, world, local_rank):
     per_kernel = {}
     N.timing_begin(launches + 64)
     for i in range(K):
-        one(W + i)
+        one(W + i, two_streams=False)
     recs = N.timing_end(launches + 64)
     torch.cuda.synchronize()
     if world > 1:
@@ -905,7 +920,8 @@ def run_token(args, rank, world, local_rank):
                                    f"[{B},197,1024] and RoBERTa tokens [{B},256,768], ReverseCrossAttention 96->64/48 at L=197 and L=256; "
                                    f"batch {B}/GPU, " + ("data parallel: one NCCL all-reduce of the flat gradient bucket per step"
                                                          if train else "replicas (no collective)") + "; secondary workload",
-                       "parallelism": f"dp{world}" if train else f"replicas x{world}", "l2": f"inputs rotate over {NB} batches"},
+                       "parallelism": f"dp{world}" if train else f"replicas x{world}", "l2": f"inputs rotate over {NB} batches",
+                       "streams": "image and text branch on two CUDA streams"},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "tok_proj [B*197 x 1024] x [1024 x 352]", "achieved": ach,
                          "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
