@@ -774,8 +774,8 @@ def run_full(args, rank, world, local_rank):
 
 def run_token(args, rank, world, local_rank):
     """Secondary workload (BASELINE.json configs[4] / SURVEY.md §8 d cfg 5): the attention blocks on real token sequences,
-    forward + backward (parameter gradients of the four blocks, input gradients of the cross blocks; the weight images are
-    rebuilt from the fp32 parameters every step, as after an optimizer step), `--batch` samples per GPU, data parallel with
+    forward + backward (parameter gradients of the four blocks, input gradients of the cross blocks) + one fused SGD launch over
+    the flat parameter bucket (the bf16 weight images are rebuilt from the updated fp32 parameters every step), `--batch` samples per GPU, data parallel with
     one all-reduce of the gradient bucket; `--token-forward-only`: inference replicas, no collective:
       SelfAttention(1024 -> 128 / 96) on ViT-L/16 tokens [B, 197, 1024], SelfAttention(768 -> 128 / 96) on RoBERTa tokens
       [B, 256, 768], and a ReverseCrossAttention(96 -> 64 / 48) on each sequence length (the reference asserts square
@@ -803,6 +803,22 @@ def run_token(args, rank, world, local_rank):
     x_txt = [torch.randn(B, 256, 768, generator=g).bfloat16().to(dev) for _ in range(NB)]
     train = not args.token_forward_only
     blocks = [block(1024, 1024, 128, 96), block(768, 768, 128, 96), block(96, 96, 64, 48), block(96, 96, 64, 48)]
+    # parameter bucket: one flat fp32 buffer (16-byte aligned tensors), the blocks read views of it; one fused SGD launch
+    # updates all 32 tensors after the backward (mmrca_sgd_step), the gradient bucket below has the same layout
+    offs, off = [], 0
+    for blk in blocks:
+        for t in blk:
+            offs.append(off)
+            off += (t.numel() + 3) // 4 * 4
+    n_par = off
+    flat_p = torch.zeros(n_par, device=dev)
+    it_off = iter(offs)
+    for blk in blocks:
+        for j, t in enumerate(blk):
+            o = next(it_off)
+            v = flat_p[o:o + t.numel()].view_as(t)
+            v.copy_(t)
+            blk[j] = v
     sa_i = F.TokenAttention(blocks[0], B, 197, training=train, out_dtype=torch.bfloat16)
     sa_t = F.TokenAttention(blocks[1], B, 256, training=train, out_dtype=torch.bfloat16)
     # the self blocks write bf16 straight into samples 1 .. B of a [B + 1] buffer; sample 0 is a copy of sample B: samples
@@ -812,14 +828,13 @@ def run_token(args, rank, world, local_rank):
     ca_i = F.TokenAttention(blocks[2], B, 197, reverse=True, training=train)
     ca_t = F.TokenAttention(blocks[3], B, 256, reverse=True, training=train)
     # gradient bucket: one flat fp32 buffer, the per-tensor views go to the backward calls; zeroed once per step
-    n_par = sum(t.numel() for blk in blocks for t in blk)
     flat_g = torch.zeros(n_par, device=dev)
-    views, off = [], 0
+    views, it_off = [], iter(offs)
     for blk in blocks:
         vs = []
         for t in blk:
-            vs.append(flat_g[off:off + t.numel()].view_as(t))
-            off += t.numel()
+            o = next(it_off)
+            vs.append(flat_g[o:o + t.numel()].view_as(t))
         views.append(vs)
     d_ca_i = (torch.randn(B, 197, 48, generator=g) / (B * 197)).to(dev)
     d_ca_t = (torch.randn(B, 256, 48, generator=g) / (B * 256)).to(dev)
@@ -863,6 +878,9 @@ def run_token(args, rank, world, local_rank):
                 branch(*job)
         if train and world > 1:   # data parallel: one all-reduce of the flat gradient bucket (1.3 M floats) per step
             dist.all_reduce(flat_g)
+        if train:                 # torch.optim.SGD(lr) on the whole bucket, one launch; the next step rebuilds the bf16 weight images
+            N.check(N.lib().mmrca_sgd_step(flat_p.data_ptr(), flat_g.data_ptr(), None, n_par, 1e-3 / world, 0.0, 0.0, 0.0, 0, 0,
+                                           torch.cuda.current_stream(dev).cuda_stream), "mmrca_sgd_step")
 
     for i in range(W):
         one(i)
@@ -916,7 +934,7 @@ def run_token(args, rank, world, local_rank):
             "metric": "token_level_rca_blocks_fwd_bwd_samples_per_s" if train else "token_level_rca_blocks_fwd_samples_per_s", "value": world * B * K / (ms * 1e-3), "unit": "samples/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"token-level attention blocks {'forward + backward' if train else 'forward'} (BASELINE.json configs[4]): SelfAttention on ViT-L/16 tokens "
+            "config": {"workload": f"token-level attention blocks {'forward + backward + fused SGD step' if train else 'forward'} (BASELINE.json configs[4]): SelfAttention on ViT-L/16 tokens "
                                    f"[{B},197,1024] and RoBERTa tokens [{B},256,768], ReverseCrossAttention 96->64/48 at L=197 and L=256; "
                                    f"batch {B}/GPU, " + ("data parallel: one NCCL all-reduce of the flat gradient bucket per step"
                                                          if train else "replicas (no collective)") + "; secondary workload",
