@@ -33,7 +33,8 @@ constexpr int kTile = 128;            // tokens per tile
 constexpr int kMaxTiles = 2;          // L <= 256
 constexpr int kBK = 64;               // K per pipeline stage: one 128-byte swizzle span of bf16
 constexpr int kStages = 3;
-constexpr int kProjThreads = 64 + 256;      // producer warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
+constexpr int kProjEpiGroups = 2;           // epilogue warps per TMEM lane quarter (4 measured: no change, the tile count per CTA - 394 tiles on 148 CTAs - sets the time)
+constexpr int kProjThreads = 64 + 128 * kProjEpiGroups;      // producer warp, MMA warp, 4 x kProjEpiGroups epilogue warps
 
 // ---- TMA tensor-map loads, 128B-swizzled shared-memory descriptors ------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(kProjThreads, 1) tok_proj_kernel(const __grid_
     // ---- epilogue: 8 warps; warp w reads TMEM lanes 32 (w % 4) .. + 31 (its row of the tile) and every other 32-column
     //      chunk (half = (w - 2) / 4).  Measured on the first version (4 warps, per-chunk address arithmetic, segment
     //      table indexed dynamically): 9.5 us of fixed cost per 128-row tile against 13.7 us of main loop at K = 1024.
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int q = warp & 3, half = (warp - 2) >> 2;      // (the chunk group of this warp, 0 .. kProjEpiGroups - 1)
     int ti = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++ti) {
       const int r_flat = tile * kTile + 32 * q + lane;
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(kProjThreads, 1) tok_proj_kernel(const __grid_
         const float sc = sg.scale;
 #pragma unroll 1
         for (int c = 0; c < sg.cols; c += 32, ++chunk) {
-          if ((chunk & 1) != half) continue;
+          if (chunk % kProjEpiGroups != half) continue;
           const bool two = c + 16 < sg.cols;
           uint32_t r0[16], r1[16];
           tmem_ld16_nw(tmem + (uint32_t(32 * q) << 16) + uint32_t(n0 + c), r0);
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(kProjThreads, 1) tok_proj_kernel(const __grid_
       }
       // the accumulators are drained: hand TMEM back to the MMA thread
       tc_fence_before_sync();
-      named_bar_sync(1, 256);
+      named_bar_sync(1, 128 * kProjEpiGroups);
       if (tid == 64) mbar_arrive(tmem_empty);
     }
   }
