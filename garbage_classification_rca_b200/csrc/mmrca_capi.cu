@@ -1080,9 +1080,13 @@ static int fusion_check(const MmrcaFusionDesc* d) {
 }
 static int launch_sgemm(const fus::GemmArgs& g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return MMRCA_OK;
+  const int tiles = ((g.N + fus::kTN - 1) / fus::kTN) * ((g.M + fus::kTM - 1) / fus::kTM);
+  // accumulating GEMMs with few output tiles and a long contraction (weight gradients: K = batch): split K over ~4 waves
+  int splits = 1;
+  if (g.accumulate && tiles < 600) splits = std::max(1, std::min((600 + tiles - 1) / tiles, g.K / 256));
   {
     LaunchScope ls("fusion_sgemm", st);
-    fus::sgemm_kernel<<<dim3((g.N + fus::kTN - 1) / fus::kTN, (g.M + fus::kTM - 1) / fus::kTM), 256, 0, st>>>(g);
+    fus::sgemm_kernel<<<dim3((g.N + fus::kTN - 1) / fus::kTN, (g.M + fus::kTM - 1) / fus::kTM, splits), 256, 0, st>>>(g);
   }
   MMRCA_CUDA(cudaGetLastError());
   return MMRCA_OK;

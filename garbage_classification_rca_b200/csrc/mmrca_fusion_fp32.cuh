@@ -35,8 +35,10 @@ struct GemmArgs {
   int M, N, K, accumulate;
 };
 
-// C (+)= A B.  grid = (ceil(N / 64), ceil(M / 64)), 256 threads; thread (ty, tx) owns rows 4 ty.. and columns 4 tx.. of
-// the tile.  The tile loads pick the thread mapping that walks the operand's contiguous axis.
+// C (+)= A B.  grid = (ceil(N / 64), ceil(M / 64), K splits), 256 threads; thread (ty, tx) owns rows 4 ty.. and columns
+// 4 tx.. of the tile.  The tile loads pick the thread mapping that walks the operand's contiguous axis.  K splits > 1
+// (accumulating GEMMs only: the weight gradients contract over the batch and have few output tiles) add their partial
+// products with red.global.add.
 __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
   __shared__ __align__(16) float As[kTK][kTM + 4];
   __shared__ __align__(16) float Bs[kTK][kTN + 4];
@@ -48,14 +50,16 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < g.K; k0 += kTK) {
+  const int kper = ((g.K + int(gridDim.z) - 1) / int(gridDim.z) + kTK - 1) / kTK * kTK;
+  const int k_begin = int(blockIdx.z) * kper, k_end = min(g.K, k_begin + kper);
+  for (int k0 = k_begin; k0 < k_end; k0 += kTK) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int idx = tid + 256 * u;
       {
         const int i = a_kfast ? idx / kTK : idx % kTM, k = a_kfast ? idx % kTK : idx / kTM;
         float v = 0.f;
-        if (m0 + i < g.M && k0 + k < g.K) {
+        if (m0 + i < g.M && k0 + k < k_end) {
           v = __ldg(g.a + (long long)(m0 + i) * g.sa_m + (long long)(k0 + k) * g.sa_k);
           if (g.inv_m) v = v / __ldg(g.inv_m + m0 + i);
           if (g.inv_k) v = v / __ldg(g.inv_k + k0 + k);
@@ -65,7 +69,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
       {
         const int j = b_nfast ? idx % kTN : idx / kTK, k = b_nfast ? idx / kTN : idx % kTK;
         float v = 0.f;
-        if (n0 + j < g.N && k0 + k < g.K) v = __ldg(g.b + (long long)(k0 + k) * g.sb_k + (long long)(n0 + j) * g.sb_n);
+        if (n0 + j < g.N && k0 + k < k_end) v = __ldg(g.b + (long long)(k0 + k) * g.sb_k + (long long)(n0 + j) * g.sb_n);
         Bs[k][j] = v;
       }
     }
@@ -92,6 +96,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
       if (n >= g.N) continue;
       float* p = g.c + (long long)m * g.ldc + n;
       float v = acc[i][j];
+      if (gridDim.z > 1) { atomicAdd(p, v); continue; }
       if (g.accumulate) v += *p;
       else if (g.bias) v += __ldg(g.bias + n);
       *p = v;
