@@ -78,6 +78,7 @@ class FusionDesc(C.Structure):
 
 
 FUSION_NORMALIZED = 1
+FUSION_BF16 = 2
 
 
 class TokenDesc(C.Structure):

@@ -1004,10 +1004,11 @@ static int launch_tok_attn_bwd(const MmrcaTokenDesc& d, const tok::AttnBwdArgs& 
   return MMRCA_OK;
 }
 // dW += G^T X for the gradient columns listed in a.out (x [rows][K] bf16, g [rows][NG] bf16 with row pitch ld_g)
-static int launch_tok_wgrad(tok::WgradArgs a, const void* x, const __nv_bfloat16* g, int ld_g, float* part, int sms, cudaStream_t st) {
+static int launch_tok_wgrad(tok::WgradArgs a, const void* x, const __nv_bfloat16* g, int ld_g, float* part, int sms, cudaStream_t st,
+                            int ld_x = 0) {
   int rc;
   CUtensorMap tx, tg;
-  if ((rc = make_tensor_map(&tx, x, uint64_t(a.K), uint64_t(a.rows), uint64_t(a.K), tok::kGradKT))) return rc;
+  if ((rc = make_tensor_map(&tx, x, uint64_t(a.K), uint64_t(a.rows), uint64_t(ld_x ? ld_x : a.K), tok::kGradKT))) return rc;
   if ((rc = make_tensor_map(&tg, g, uint64_t(a.NG), uint64_t(a.rows), uint64_t(ld_g), tok::kGradKT))) return rc;
   const int nblk = (a.NG + 63) / 64, mtiles = (a.K + 127) / 128, chunks = (a.rows + tok::kGradKT - 1) / tok::kGradKT;
   const size_t smem = size_t(tok::kGradStages) * (2 + nblk) * tok::kBoxBytes + 128 + 1024;
@@ -1030,21 +1031,31 @@ static int launch_tok_wgrad(tok::WgradArgs a, const void* x, const __nv_bfloat16
   MMRCA_CUDA(cudaGetLastError());
   return MMRCA_OK;
 }
-// dx [rows][K] = G [rows][NG] W [NG][K] (w: bf16)
+// dx [rows][K] = G [rows][NG] W (+ bias); w bf16: [NG][K] (w_is_linear_weight = false: the input gradient dY W) or
+// [K][NG] (true: torch.nn.Linear's weight, the forward X W^T + bias)
 static int launch_tok_dgrad(float* dx, int rows, int K, int NG, const __nv_bfloat16* g, int ld_g, const __nv_bfloat16* w,
-                            cudaStream_t st) {
+                            cudaStream_t st, bool w_is_linear_weight = false, const float* bias = nullptr, int ld_w = 0) {
   int rc;
   CUtensorMap tg, tw;
   if ((rc = make_tensor_map(&tg, g, uint64_t(NG), uint64_t(rows), uint64_t(ld_g), tok::kTile))) return rc;
-  if ((rc = make_tensor_map(&tw, w, uint64_t(K), uint64_t(NG), uint64_t(K), 64))) return rc;
-  const int nb = (std::min(256, K) + 63) / 64;
-  const size_t smem = size_t(tok::kGradStages) * (tok::kTile * 128 + nb * tok::kBoxBytes) + 128 + 1024;
-  if ((rc = set_smem(tok::tok_dgrad_kernel, smem))) return rc;
+  const int bn_max = std::min(256, K);
+  if (w_is_linear_weight) rc = make_tensor_map(&tw, w, uint64_t(NG), uint64_t(K), uint64_t(ld_w ? ld_w : NG), uint32_t(bn_max));
+  else rc = make_tensor_map(&tw, w, uint64_t(K), uint64_t(NG), uint64_t(ld_w ? ld_w : K), 64);
+  if (rc) return rc;
+  const int nb = (bn_max + 63) / 64;
+  const size_t b_bytes = w_is_linear_weight ? size_t(bn_max) * 128 : size_t(nb) * tok::kBoxBytes;
+  const size_t smem = size_t(tok::kGradStages) * ((tok::kTile * 128 + b_bytes + 1023) & ~size_t(1023)) + 128 + 1024;
   tok::DgradArgs a;
-  a.dx = dx; a.rows = rows; a.K = K; a.NG = NG;
-  {
+  a.dx = dx; a.rows = rows; a.K = K; a.NG = NG; a.bias = bias;
+  const dim3 grid((rows + tok::kTile - 1) / tok::kTile, (K + 255) / 256);
+  if (w_is_linear_weight) {
+    if ((rc = set_smem(tok::tok_dgrad_kernel<true>, smem))) return rc;
+    LaunchScope ls("tma_gemm_nt", st);
+    tok::tok_dgrad_kernel<true><<<grid, tok::kGradThreads, smem, st>>>(tg, tw, a);
+  } else {
+    if ((rc = set_smem(tok::tok_dgrad_kernel<false>, smem))) return rc;
     LaunchScope ls("tok_dgrad", st);
-    tok::tok_dgrad_kernel<<<dim3((rows + tok::kTile - 1) / tok::kTile, (K + 255) / 256), tok::kGradThreads, smem, st>>>(tg, tw, a);
+    tok::tok_dgrad_kernel<false><<<grid, tok::kGradThreads, smem, st>>>(tg, tw, a);
   }
   MMRCA_CUDA(cudaGetLastError());
   return MMRCA_OK;
@@ -1054,6 +1065,10 @@ static int launch_tok_dgrad(float* dx, int rows, int K, int NG, const __nv_bfloa
 struct FusionWorkspace {
   float *h_img, *h_txt, *n_img, *n_txt, *c, *d_c, *d_h_img, *d_h_txt, *dlogits;
   uint8_t* mask;
+  // MMRCA_FUSION_BF16: bf16 copies of the features, the two projection weights and d(hidden), split-K slabs of the weight gradients
+  __nv_bfloat16 *x_bf[2], *w_bf[2], *dh_bf[2];
+  __nv_bfloat16 *cat_bf, *wcat_bf, *dc_bf;      // [B][2H] (normalised) hidden vectors side by side, W_cat [H][2H], d(concat_layer output) [B][H]
+  float* wg_part;
   size_t bytes;
 };
 static FusionWorkspace fusion_carve(const MmrcaFusionDesc& d, void* base) {
@@ -1067,6 +1082,18 @@ static FusionWorkspace fusion_carve(const MmrcaFusionDesc& d, void* base) {
   w.mask = reinterpret_cast<uint8_t*>(take((B * H + 3) / 4));
   w.d_c = take(B * H); w.d_h_img = take(B * H); w.d_h_txt = take(B * H);
   w.dlogits = take(B * size_t(d.n_classes > 0 ? d.n_classes : 0));
+  if (d.flags & MMRCA_FUSION_BF16) {
+    const size_t dins[2] = {size_t(d.d_img > 0 ? d.d_img : 0), size_t(d.d_txt > 0 ? d.d_txt : 0)};
+    for (int m = 0; m < 2; ++m) {
+      w.x_bf[m] = reinterpret_cast<__nv_bfloat16*>(take((B * dins[m] + 1) / 2));
+      w.w_bf[m] = reinterpret_cast<__nv_bfloat16*>(take((H * dins[m] + 1) / 2));
+      w.dh_bf[m] = reinterpret_cast<__nv_bfloat16*>(take((B * H + 1) / 2));
+    }
+    w.cat_bf = reinterpret_cast<__nv_bfloat16*>(take(B * H));
+    w.wcat_bf = reinterpret_cast<__nv_bfloat16*>(take(H * H));
+    w.dc_bf = reinterpret_cast<__nv_bfloat16*>(take((B * H + 1) / 2));
+    w.wg_part = take(size_t(kMaxSms) * H * 128);
+  }
   w.bytes = off;
   return w;
 }
@@ -1076,6 +1103,8 @@ static int fusion_check(const MmrcaFusionDesc* d) {
     return fail(MMRCA_ERR_INVALID, "fusion head: batch >= 0, positive widths, hidden a multiple of 4%s%s");
   if (d->n_classes < 1 || d->n_classes > 8) return fail(MMRCA_ERR_INVALID, "n_classes must be in [1, 8]%s%s");
   if (!(d->drop_p >= 0.f && d->drop_p <= 1.f)) return fail(MMRCA_ERR_INVALID, "drop_p must be in [0, 1]%s%s");
+  if ((d->flags & MMRCA_FUSION_BF16) && ((d->hidden & 15) || d->hidden > 256 || (d->d_img & 15) || (d->d_txt & 15)))
+    return fail(MMRCA_ERR_INVALID, "fusion head, bf16: hidden a multiple of 16, <= 256; feature widths multiples of 16%s%s");
   return MMRCA_OK;
 }
 static int launch_sgemm(const fus::GemmArgs& g, cudaStream_t st) {
@@ -1133,21 +1162,47 @@ static int fusion_forward_impl(const MmrcaFusionDesc& d, const MmrcaFusionParams
   int rc;
   if (B == 0) return MMRCA_OK;
   // image_to_hidden_size / text_to_hidden_size (multimodal_model.py:521-522, :566-567)
-  if ((rc = launch_sgemm(gemm_args(img, d.d_img, 1, p.w_img, 1, d.d_img, w.h_img, H, B, H, d.d_img, p.b_img, false), st))) return rc;
-  if ((rc = launch_sgemm(gemm_args(txt, d.d_txt, 1, p.w_txt, 1, d.d_txt, w.h_txt, H, B, H, d.d_txt, p.b_txt, false), st))) return rc;
+  if (d.flags & MMRCA_FUSION_BF16) {
+    // the two projections on the tensor cores: bf16 copies of the features and of the weights as they lie, TMA-fed tcgen05
+    // GEMM with the bias in the epilogue (mmrca_token_bwd.cuh, tok_dgrad_kernel<true>); everything after them is fp32
+    const tok::Cast3Args c1 = {{img, txt, p.w_img}, {w.x_bf[0], w.x_bf[1], w.w_bf[0]},
+                               {(long long)B * d.d_img, (long long)B * d.d_txt, (long long)H * d.d_img}};
+    if ((rc = launch_cast3(c1, sms, st))) return rc;
+    const tok::Cast3Args c2 = {{p.w_txt, nullptr, nullptr}, {w.w_bf[1], nullptr, nullptr}, {(long long)H * d.d_txt, 0, 0}};
+    if ((rc = launch_cast3(c2, sms, st))) return rc;
+    if ((rc = launch_tok_dgrad(w.h_img, B, H, d.d_img, w.x_bf[0], d.d_img, w.w_bf[0], st, true, p.b_img))) return rc;
+    if ((rc = launch_tok_dgrad(w.h_txt, B, H, d.d_txt, w.x_bf[1], d.d_txt, w.w_bf[1], st, true, p.b_txt))) return rc;
+  } else {
+    if ((rc = launch_sgemm(gemm_args(img, d.d_img, 1, p.w_img, 1, d.d_img, w.h_img, H, B, H, d.d_img, p.b_img, false), st))) return rc;
+    if ((rc = launch_sgemm(gemm_args(txt, d.d_txt, 1, p.w_txt, 1, d.d_txt, w.h_txt, H, B, H, d.d_txt, p.b_txt, false), st))) return rc;
+  }
   if (nrm) {      // :569-570, no epsilon
     const int grid = min((B + kWarps - 1) / kWarps, 8 * sms);
     { LaunchScope ls("l2norm", st); l2norm_kernel<<<grid, kThreads, 0, st>>>(w.h_img, w.n_img, B, H); }
     { LaunchScope ls("l2norm", st); l2norm_kernel<<<grid, kThreads, 0, st>>>(w.h_txt, w.n_txt, B, H); }
     MMRCA_CUDA(cudaGetLastError());
   }
-  // concat + concat_layer (:524-527, :572-575): two accumulating GEMMs over the halves of W_cat
-  fus::GemmArgs g = gemm_args(w.h_img, H, 1, p.w_cat, 1, 2 * H, w.c, H, B, H, H, p.b_cat, false);
-  g.inv_m = nrm ? w.n_img : nullptr;
-  if ((rc = launch_sgemm(g, st))) return rc;
-  g = gemm_args(w.h_txt, H, 1, p.w_cat + H, 1, 2 * H, w.c, H, B, H, H, nullptr, true);
-  g.inv_m = nrm ? w.n_txt : nullptr;
-  if ((rc = launch_sgemm(g, st))) return rc;
+  if (d.flags & MMRCA_FUSION_BF16) {
+    // concat + concat_layer on the tensor cores: the (normalised) hidden vectors side by side as one bf16 [B, 2H] operand
+    const int grid = int(std::min<long long>(((long long)B * H / 8 + 255) / 256, 8LL * sms));
+    {
+      LaunchScope ls("cast_rows", st);
+      tok::cast_rows_scaled_kernel<<<grid, 256, 0, st>>>(w.h_img, nrm ? w.n_img : nullptr, B, H, w.cat_bf, 2 * H);
+      tok::cast_rows_scaled_kernel<<<grid, 256, 0, st>>>(w.h_txt, nrm ? w.n_txt : nullptr, B, H, w.cat_bf + H, 2 * H);
+    }
+    MMRCA_CUDA(cudaGetLastError());
+    const tok::Cast3Args cw = {{p.w_cat, nullptr, nullptr}, {w.wcat_bf, nullptr, nullptr}, {(long long)H * 2 * H, 0, 0}};
+    if ((rc = launch_cast3(cw, sms, st))) return rc;
+    if ((rc = launch_tok_dgrad(w.c, B, H, 2 * H, w.cat_bf, 2 * H, w.wcat_bf, st, true, p.b_cat))) return rc;
+  } else {
+    // concat + concat_layer (:524-527, :572-575): two accumulating GEMMs over the halves of W_cat
+    fus::GemmArgs g = gemm_args(w.h_img, H, 1, p.w_cat, 1, 2 * H, w.c, H, B, H, H, p.b_cat, false);
+    g.inv_m = nrm ? w.n_img : nullptr;
+    if ((rc = launch_sgemm(g, st))) return rc;
+    g = gemm_args(w.h_txt, H, 1, p.w_cat + H, 1, 2 * H, w.c, H, B, H, H, nullptr, true);
+    g.inv_m = nrm ? w.n_txt : nullptr;
+    if ((rc = launch_sgemm(g, st))) return rc;
+  }
   // self.drop + fc_layer (:528-529, :576-577)
   if (!mask && d.drop_p > 0.f) {
     const DropSpec ds = fusion_drop(d);
@@ -1179,11 +1234,26 @@ static int fusion_backward_impl(const MmrcaFusionDesc& d, const MmrcaFusionParam
   const float* hs[2] = {w.h_img, w.h_txt};
   const float* ns[2] = {w.n_img, w.n_txt};
   float* dhs[2] = {w.d_h_img, w.d_h_txt};
+  const bool tc_gemms = (d.flags & MMRCA_FUSION_BF16) != 0;
+  if (tc_gemms) {
+    const tok::Cast3Args cd = {{w.d_c, nullptr, nullptr}, {w.dc_bf, nullptr, nullptr}, {(long long)B * H, 0, 0}};
+    if ((rc = launch_cast3(cd, sms, st))) return rc;
+  }
   for (int m = 0; m < 2; ++m) {
-    fus::GemmArgs a = gemm_args(w.d_c, 1, H, hs[m], H, 1, g.w_cat + m * H, 2 * H, H, H, B, nullptr, true);
-    a.inv_k = nrm ? ns[m] : nullptr;
-    if ((rc = launch_sgemm(a, st))) return rc;
-    if ((rc = launch_sgemm(gemm_args(w.d_c, H, 1, p.w_cat + m * H, 2 * H, 1, dhs[m], H, B, H, H, nullptr, false), st))) return rc;
+    if (tc_gemms) {
+      // dW_cat[:, half m] += d_c^T (normalised hidden half m); d(hidden half m) = d_c W_cat[:, half m]: bf16 TMA GEMMs over the
+      // forward's cat_bf / wcat_bf (operands addressed in place through their row pitch 2H)
+      tok::WgradArgs a;
+      memset(&a, 0, sizeof(a));
+      a.out[0] = {g.w_cat + m * H, 0, H, 2 * H}; a.nout = 1; a.NG = H; a.K = H; a.rows = B;
+      if ((rc = launch_tok_wgrad(a, w.cat_bf + m * H, w.dc_bf, H, w.wg_part, sms, st, 2 * H))) return rc;
+      if ((rc = launch_tok_dgrad(dhs[m], B, H, H, w.dc_bf, H, w.wcat_bf + m * H, st, false, nullptr, 2 * H))) return rc;
+    } else {
+      fus::GemmArgs a = gemm_args(w.d_c, 1, H, hs[m], H, 1, g.w_cat + m * H, 2 * H, H, H, B, nullptr, true);
+      a.inv_k = nrm ? ns[m] : nullptr;
+      if ((rc = launch_sgemm(a, st))) return rc;
+      if ((rc = launch_sgemm(gemm_args(w.d_c, H, 1, p.w_cat + m * H, 2 * H, 1, dhs[m], H, B, H, H, nullptr, false), st))) return rc;
+    }
     if (nrm) {      // through h / ||h||
       const int grid = min((B + kWarps - 1) / kWarps, 8 * sms);
       { LaunchScope ls("l2norm_bwd", st); l2norm_bwd_kernel<<<grid, kThreads, 0, st>>>(hs[m], ns[m], dhs[m], B, H); }
@@ -1197,9 +1267,20 @@ static int fusion_backward_impl(const MmrcaFusionDesc& d, const MmrcaFusionParam
   float* gbs[2] = {g.b_img, g.b_txt};
   const float* ws[2] = {p.w_img, p.w_txt};
   float* dxs[2] = {d_img, d_txt};
+  if (tc_gemms) {
+    const tok::Cast3Args cd = {{dhs[0], dhs[1], nullptr}, {w.dh_bf[0], w.dh_bf[1], nullptr}, {(long long)B * H, (long long)B * H, 0}};
+    if ((rc = launch_cast3(cd, sms, st))) return rc;
+  }
   for (int m = 0; m < 2; ++m) {
     if ((rc = launch_colsum(dhs[m], H, B, H, gbs[m], sms, st))) return rc;
-    if ((rc = launch_sgemm(gemm_args(dhs[m], 1, H, xs[m], dins[m], 1, gws[m], dins[m], H, dins[m], B, nullptr, true), st))) return rc;
+    if (tc_gemms) {      // dW += d(hidden)^T X: the token path's split-K TMA GEMM over the bf16 copies (the forward's x_bf)
+      tok::WgradArgs a;
+      memset(&a, 0, sizeof(a));
+      a.out[0] = {gws[m], 0, H, 0}; a.nout = 1; a.NG = H; a.K = dins[m]; a.rows = B;
+      if ((rc = launch_tok_wgrad(a, w.x_bf[m], w.dh_bf[m], H, w.wg_part, sms, st))) return rc;
+    } else if ((rc = launch_sgemm(gemm_args(dhs[m], 1, H, xs[m], dins[m], 1, gws[m], dins[m], H, dins[m], B, nullptr, true), st))) {
+      return rc;
+    }
     if (dxs[m] && (rc = launch_sgemm(gemm_args(dhs[m], H, 1, ws[m], dins[m], 1, dxs[m], dins[m], B, dins[m], H, nullptr, false), st)))
       return rc;
   }
@@ -1477,13 +1558,13 @@ int mmrca_token_attention_backward(const MmrcaTokenDesc* desc, const MmrcaAttnPa
     memset(&a, 0, sizeof(a));
     a.rows = rows;
     if (self) {
-      a.out[0] = {grads->wq, 0, dkq}; a.out[1] = {grads->wk, dkq, dkq}; a.out[2] = {grads->wv, 2 * dkq, dv}; a.nout = 3;
+      a.out[0] = {grads->wq, 0, dkq, 0}; a.out[1] = {grads->wk, dkq, dkq, 0}; a.out[2] = {grads->wv, 2 * dkq, dv, 0}; a.nout = 3;
       a.NG = 2 * dkq + dv; a.K = kq;
       if ((rc = launch_tok_wgrad(a, x_q, w.g, ldq, w.wg_part, di.sms, st))) return rc;
     } else {
-      a.out[0] = {grads->wq, 0, dkq}; a.nout = 1; a.NG = dkq; a.K = kq;
+      a.out[0] = {grads->wq, 0, dkq, 0}; a.nout = 1; a.NG = dkq; a.K = kq;
       if ((rc = launch_tok_wgrad(a, x_q, gq, ldq, w.wg_part, di.sms, st))) return rc;
-      a.out[0] = {grads->wk, 0, dkq}; a.out[1] = {grads->wv, dkq, dv}; a.nout = 2; a.NG = dkq + dv; a.K = kkv;
+      a.out[0] = {grads->wk, 0, dkq, 0}; a.out[1] = {grads->wv, dkq, dv, 0}; a.nout = 2; a.NG = dkq + dv; a.K = kkv;
       if ((rc = launch_tok_wgrad(a, x_kv, gkv, ldkv, w.wg_part, di.sms, st))) return rc;
     }
   }

@@ -243,6 +243,21 @@ __global__ void __launch_bounds__(256) cast3_bf16_kernel(const Cast3Args a) {
   }
 }
 
+// dst[r][c] = bf16(src[r][c] / norm[r]) (norm null: plain cast), dst row pitch ld_dst: the hidden vectors of the classic /
+// normalized heads, normalised and side by side, as the concat layer's GEMM operand
+__global__ void __launch_bounds__(256) cast_rows_scaled_kernel(const float* __restrict__ src, const float* __restrict__ norm, int rows,
+                                                               int width, __nv_bfloat16* __restrict__ dst, int ld_dst) {
+  const int w8 = width / 8;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < (long long)rows * w8; i += (long long)gridDim.x * 256) {
+    const int r = int(i / w8), c = int(i - (long long)r * w8) * 8;
+    const float inv = norm ? 1.0f / __ldg(norm + r) : 1.0f;
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * width + c));
+    const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * width + c + 4));
+    const float v[8] = {v0.x * inv, v0.y * inv, v0.z * inv, v0.w * inv, v1.x * inv, v1.y * inv, v1.z * inv, v1.w * inv};
+    *reinterpret_cast<uint4*>(dst + (size_t)r * ld_dst + c) = pack_bf16x8(v);
+  }
+}
+
 // W [n_rows][K] fp32 (rows n0 .. n0 + n_rows of the stacked [W_query; W_key; W_value]) -> bf16 blob laid out as the
 // shared-memory IMAGE the projection's B operand wants: [k-block of 64][N rows][128 bytes, 16-byte chunks XOR-swizzled
 // by (row % 8)] - what a {64, N} SWIZZLE_128B tensor-map box would land - so that a stage's whole weight slab is ONE

@@ -475,7 +475,8 @@ constexpr int kGradKT = 64;                       // tokens per pipeline stage
 constexpr uint32_t kBoxBytes = 64 * 128;          // one {64 columns, 64 rows} bf16 box, 128-byte swizzled: 8 KB
 constexpr int kMaxGBlocks = 6;                    // gradient columns <= 384
 
-struct WgradOut { float* g_w; int n0, cols; };    // gradient columns [n0, n0 + cols) -> dW [cols][K] +=  (n0, cols: multiples of 16)
+struct WgradOut { float* g_w; int n0, cols, ld; };      // gradient columns [n0, n0 + cols) -> dW [cols][K] += (row pitch ld, 0: K;
+                                                        // n0, cols: multiples of 16)
 struct WgradArgs {
   WgradOut out[3]; int nout, NG, K, rows;
   float* part;       // [splits][NG][K] fp32: every split writes its own slab (plain coalesced stores), tok_wgrad_reduce adds
@@ -603,7 +604,7 @@ __global__ void __launch_bounds__(256) tok_wgrad_reduce_kernel(const WgradArgs a
 #pragma unroll
       for (int o = 0; o < 3; ++o)
         if (o < a.nout && n >= a.out[o].n0 && n < a.out[o].n0 + a.out[o].cols) {
-          float4* dst = reinterpret_cast<float4*>(a.out[o].g_w + size_t(n - a.out[o].n0) * a.K + m);
+          float4* dst = reinterpret_cast<float4*>(a.out[o].g_w + size_t(n - a.out[o].n0) * (a.out[o].ld ? a.out[o].ld : a.K) + m);
           float4 g = *dst;
           g.x += acc.x; g.y += acc.y; g.z += acc.z; g.w += acc.w;
           *dst = g;
@@ -614,15 +615,21 @@ __global__ void __launch_bounds__(256) tok_wgrad_reduce_kernel(const WgradArgs a
 }
 
 // ---- input gradients ------------------------------------------------------------------------------------------------------------------
-struct DgradArgs { float* dx; int rows, K, NG; };     // dx [rows][K] = G [rows][NG] W [NG][K]
-// grid = (ceil(rows / 128), ceil(K / 256)).  tm_g: G with {64 columns, 128 rows} boxes (K-major A), tm_w: bf16 W [NG][K] with
-// {64 columns, 64 rows} boxes (MN-major B); one stage per 64 gradient columns.
+struct DgradArgs { float* dx; int rows, K, NG; const float* bias; };     // dx [rows][K] = G [rows][NG] W (+ bias [K])
+// grid = (ceil(rows / 128), ceil(K / 256)).  tm_g: G with {64 columns, 128 rows} boxes (K-major A); one stage per 64 columns
+// of the contraction.  The second operand, as it lies in memory:
+//   B_KMAJOR = false: W [NG][K] (contraction index outermost: MN-major B), {64 columns, 64 rows} boxes - the input gradient
+//                     of a Linear layer, dX = dY W;
+//   B_KMAJOR = true:  W [K][NG] (torch.nn.Linear's weight, contraction index contiguous: K-major B), one {64, bn rows} box
+//                     per stage - the layer's forward, Y = X W^T + bias (the classic / normalized heads' projections).
+template <bool B_KMAJOR>
 __global__ void __launch_bounds__(kGradThreads, 1) tok_dgrad_kernel(const __grid_constant__ CUtensorMap tm_g,
                                                                     const __grid_constant__ CUtensorMap tm_w, const DgradArgs a) {
   extern __shared__ __align__(1024) uint8_t sm_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~uintptr_t(1023));
   const int n0 = blockIdx.y * 256, bn = min(256, a.K - n0), nb = (bn + 63) / 64;
-  const uint32_t a_bytes = kTile * 128, stage = a_bytes + uint32_t(nb) * kBoxBytes;
+  const uint32_t a_bytes = kTile * 128, b_bytes = B_KMAJOR ? uint32_t(bn) * 128 : uint32_t(nb) * kBoxBytes;
+  const uint32_t stage = (a_bytes + b_bytes + 1023) & ~1023u;
   uint64_t* full = reinterpret_cast<uint64_t*>(sm + kGradStages * stage);
   uint64_t* empty = full + kGradStages;
   uint64_t* accb = empty + kGradStages;
@@ -645,25 +652,29 @@ __global__ void __launch_bounds__(kGradThreads, 1) tok_dgrad_kernel(const __grid
       for (int it = 0; it < n_it; ++it) {
         const int s = it % kGradStages;
         if (it >= kGradStages) mbar_wait(&empty[s], uint32_t(it / kGradStages - 1) & 1u);
-        mbar_arrive_expect_tx(&full[s], stage);
+        mbar_arrive_expect_tx(&full[s], a_bytes + b_bytes);
         uint8_t* st = sm + s * stage;
         tma_load_2d(st, &tm_g, 64 * it, row0, &full[s]);
-        for (int j = 0; j < nb; ++j) tma_load_2d(st + a_bytes + j * kBoxBytes, &tm_w, n0 + 64 * j, 64 * it, &full[s]);
+        if (B_KMAJOR) {
+          tma_load_2d(st + a_bytes, &tm_w, 64 * it, n0, &full[s]);
+        } else {
+          for (int j = 0; j < nb; ++j) tma_load_2d(st + a_bytes + j * kBoxBytes, &tm_w, n0 + 64 * j, 64 * it, &full[s]);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, bn, 0, 1);
+      const uint32_t idesc = make_idesc_bf16(128, bn, 0, B_KMAJOR ? 0 : 1);
       for (int it = 0; it < n_it; ++it) {
         const int s = it % kGradStages;
         mbar_wait(&full[s], uint32_t(it / kGradStages) & 1u);
         tc_fence_after_sync();
         const uint32_t st = smem_u32(sm + s * stage);
         const uint64_t ad = make_smem_desc_sw128(st);
-        const uint64_t bd = make_smem_desc_sw128_mn(st + a_bytes, kBoxBytes);
+        const uint64_t bd = B_KMAJOR ? make_smem_desc_sw128(st + a_bytes) : make_smem_desc_sw128_mn(st + a_bytes, kBoxBytes);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          umma_bf16(tmem, desc_advance(ad, ks * 32), desc_advance(bd, ks * 2048), idesc, (it | ks) ? 1u : 0u);
+          umma_bf16(tmem, desc_advance(ad, ks * 32), desc_advance(bd, B_KMAJOR ? ks * 32 : ks * 2048), idesc, (it | ks) ? 1u : 0u);
         umma_commit(&empty[s]);
       }
       umma_commit(accb);
@@ -679,6 +690,10 @@ __global__ void __launch_bounds__(kGradThreads, 1) tok_dgrad_kernel(const __grid
       tmem_ld16_nw(tmem + (uint32_t(32 * q) << 16) + uint32_t(c), v);
       tmem_wait_ld();
       if (r < a.rows) {
+        if (a.bias) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __ldg(a.bias + n0 + c + e));
+        }
 #pragma unroll
         for (int e = 0; e < 16; e += 4) *reinterpret_cast<uint4*>(dst + c + e) = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
       }

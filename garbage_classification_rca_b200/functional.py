@@ -633,29 +633,34 @@ def _fusion_struct(tensors: Sequence[Optional[torch.Tensor]]) -> N.FusionParams:
     return N.FusionParams(*[t.data_ptr() if t is not None else None for t in tensors])
 
 
-def _fusion_desc(B, params, normalized, drop_p, drop_seed) -> N.FusionDesc:
+def _fusion_desc(B, params, normalized, drop_p, drop_seed, compute: str = "fp32") -> N.FusionDesc:
     H, d_img = params[0].shape
     d_txt = params[2].shape[1]
     if tuple(params[4].shape) != (H, 2 * H) or params[6].shape[1] != H:
         raise ValueError("fusion head: concat_layer must be [H, 2H] and fc_layer [n_classes, H]")
-    return N.FusionDesc(B, d_img, d_txt, H, params[6].shape[0], N.FUSION_NORMALIZED if normalized else 0,
-                        float(drop_p), int(drop_seed) & (2 ** 64 - 1))
+    if compute not in ("fp32", "bf16"):
+        raise ValueError("compute must be 'fp32' or 'bf16'")
+    flags = (N.FUSION_NORMALIZED if normalized else 0) | (N.FUSION_BF16 if compute == "bf16" else 0)
+    return N.FusionDesc(B, d_img, d_txt, H, params[6].shape[0], flags, float(drop_p), int(drop_seed) & (2 ** 64 - 1))
 
 
 class _FusionFunction(torch.autograd.Function):
     """logits = classic / normalized fusion head(pooled image features, text CLS features)."""
 
     @staticmethod
-    def forward(ctx, img, txt, drop_mask, drop_scale, normalized, drop_p, drop_seed, *params):
+    def forward(ctx, img, txt, drop_mask, drop_scale, normalized, drop_p, drop_seed, compute, *params):
         img, txt = _check_dev(img, "image features"), _check_dev(txt, "text features")
         params = [_check_dev(p, "fusion parameter") for p in params]
         B = img.shape[0]
-        desc = _fusion_desc(B, params, normalized, drop_p, drop_seed)
+        desc = _fusion_desc(B, params, normalized, drop_p, drop_seed, compute)
         if img.shape[1] != desc.d_img or txt.shape != (B, desc.d_txt):
             raise ValueError("feature shapes do not match the projection weights")
         drop_mask = _check_mask(drop_mask, B, desc.hidden, "fusion head")
         L = N.lib()
-        ws = _pool.take(L.mmrca_fusion_workspace_bytes(C.byref(desc)), img.device)
+        nbytes = L.mmrca_fusion_workspace_bytes(C.byref(desc))
+        if nbytes == 0:
+            raise ValueError("unsupported fusion head shape: " + N.last_error())
+        ws = _pool.take(nbytes, img.device)
         ctx.lease = _Lease(ws)
         logits = torch.empty(B, desc.n_classes, dtype=torch.float32, device=img.device)
         ctx.save_for_backward(img, txt, drop_mask, ws, *params)
@@ -688,19 +693,21 @@ class _FusionFunction(torch.autograd.Function):
         elif want_feat:
             d_img.zero_(); d_txt.zero_()
         return (d_img if ctx.needs_input_grad[0] else None, d_txt if ctx.needs_input_grad[1] else None, None, None, None,
-                None, None, *[v if ctx.needs_input_grad[7 + i] else None for i, v in enumerate(fg.views)])
+                None, None, None, *[v if ctx.needs_input_grad[8 + i] else None for i, v in enumerate(fg.views)])
 
 
 def fusion_head(img_feat: torch.Tensor, txt_feat: torch.Tensor, params: Sequence[torch.Tensor], *, normalized: bool,
                 drop_mask: Optional[torch.Tensor] = None, drop_scale: float = 1.0, drop_p: float = 0.0,
-                drop_seed: int = 0) -> torch.Tensor:
+                drop_seed: int = 0, compute: str = "fp32") -> torch.Tensor:
     """Classic (`normalized=False`) / Normalized late-fusion head after the backbones (reference
     multimodal_model.py:521-529 / :566-577).  params: the eight tensors of FUSION_PARAM_NAMES.  Dropout on the
-    concat_layer output [B, H]: seeded (drop_p, drop_seed; dropout_mask(seed, p, B, H) returns the mask) or caller-drawn."""
+    concat_layer output [B, H]: seeded (drop_p, drop_seed; dropout_mask(seed, p, B, H) returns the mask) or caller-drawn.
+    compute="bf16": the three Linear layers' GEMMs and their weight / hidden gradients on the tensor cores (bf16 operands,
+    fp32 accumulate; 2e-2-absolute logits contract); "fp32": the 1e-4-relative contract."""
     if drop_mask is not None:
         drop_p, drop_seed = 0.0, 0
     return _FusionFunction.apply(img_feat, txt_feat, drop_mask, float(drop_scale), bool(normalized), float(drop_p),
-                                 int(drop_seed), *params)
+                                 int(drop_seed), str(compute), *params)
 
 
 class FusionTrainStep:
@@ -709,10 +716,15 @@ class FusionTrainStep:
 
     def __init__(self, params: Sequence[torch.Tensor], batch: int, *, normalized: bool,
                  class_weight: Optional[torch.Tensor] = None, label_smoothing: float = 0.0, drop_p: float = 0.0,
-                 feature_grads: bool = False):
+                 feature_grads: bool = False, compute: str = "fp32"):
+        """compute="bf16": the three Linear layers' GEMMs (projections, concat_layer) and their weight / hidden gradients
+        run as TMA-fed bf16 tcgen05 GEMMs (fp32 accumulate; the 2e-2-absolute logits contract instead of 1e-4 relative);
+        normalisation, dropout, fc_layer and the loss stay fp32."""
         self.params = [_check_dev(p.detach(), "fusion parameter") for p in params]
         dev = self.params[0].device
-        self.desc = _fusion_desc(batch, self.params, normalized, drop_p, 0)
+        self.desc = _fusion_desc(batch, self.params, normalized, drop_p, 0, compute)
+        if N.lib().mmrca_fusion_workspace_bytes(C.byref(self.desc)) == 0:
+            raise ValueError("unsupported fusion head shape: " + N.last_error())
         self.grads = FlatGrads(self.params)
         self.hp, self.hg = _fusion_struct(self.params), _fusion_struct(self.grads.views)
         self.ws = torch.empty(max(1, N.lib().mmrca_fusion_workspace_bytes(C.byref(self.desc))), dtype=torch.uint8, device=dev)

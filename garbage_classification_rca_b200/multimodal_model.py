@@ -513,9 +513,10 @@ class EffV2MediumAndDistilbertClassic(EffV2MediumAndDistilbertGated):
             drop_scale = 1.0
         elif drop_scale is None:
             drop_scale = 1.0 / (1.0 - float(self.drop.p))
+        # head_compute = "bf16" (attribute; default "fp32", the 1e-4 contract): the Linear layers on the tensor cores
         return F.fusion_head(image_features.float(), text_features.float(), self.fusion_parameters(),
                              normalized=self.NORMALIZED, drop_mask=drop_mask, drop_scale=drop_scale, drop_p=drop_p,
-                             drop_seed=drop_seed)
+                             drop_seed=drop_seed, compute=getattr(self, "head_compute", "fp32"))
 
     def forward(self, _input_ids, _attention_mask, _images, eval=False, remove_image=False, remove_text=False):
         print("Normalized forward" if self.NORMALIZED else "Classic forward")       # reference :500, :545

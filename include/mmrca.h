@@ -303,6 +303,9 @@ int mmrca_token_attention_backward(const MmrcaTokenDesc* desc, const MmrcaAttnPa
  * backward, fp32 (the 1e-4 contract).  (The reference hands image_to_hidden_size the extractor's TUPLE, which raises a
  * TypeError; the pooled vector, its third element, is what is meant and what img_feat is.) ---- */
 #define MMRCA_FUSION_NORMALIZED 1u
+#define MMRCA_FUSION_BF16 2u /* the two projections and their weight gradients as bf16 tcgen05 GEMMs (fp32 accumulate): the
+                                2e-2-absolute logits contract instead of 1e-4 relative; hidden % 16 == 0, <= 256, feature
+                                widths % 16 == 0.  The backward needs the unmodified workspace of the forward. */
 typedef struct MmrcaFusionParams {
   const float* w_img; const float* b_img; /* image_to_hidden_size [H, d_img], [H]   (:199-201) */
   const float* w_txt; const float* b_txt; /* text_to_hidden_size  [H, d_txt], [H]   (:203-206) */
@@ -314,7 +317,7 @@ typedef struct MmrcaFusionGrads { /* accumulated into (+=) */
 } MmrcaFusionGrads;
 typedef struct MmrcaFusionDesc {
   int32_t batch, d_img, d_txt, hidden, n_classes;
-  uint32_t flags;     /* MMRCA_FUSION_NORMALIZED */
+  uint32_t flags;     /* MMRCA_FUSION_NORMALIZED | MMRCA_FUSION_BF16 */
   float drop_p;       /* self.drop on the concat_layer output [B, H]: seeded mask = mmrca_dropout_mask(seed, p, B, H) */
   uint64_t drop_seed;
 } MmrcaFusionDesc;

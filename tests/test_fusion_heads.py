@@ -122,6 +122,50 @@ def test_cuda_train_step_matches_oracle(pkg, normalized, B):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("normalized", [False, True], ids=["classic", "normalized"])
+@pytest.mark.parametrize("B", [1, 100, 1000])
+def test_cuda_train_step_bf16_projections(pkg, normalized, B):
+    """compute="bf16": the two projections and their weight gradients as bf16 tcgen05 GEMMs (TMA-fed, fp32 accumulate),
+    the rest fp32.  Contract: logits within 2e-2 absolute of the float64 oracle, gradients within 1e-2 relative L2 per
+    tensor (the oracle sees the fp32 inputs: the bf16 rounding of features and weights is part of the error)."""
+    from garbage_classification_rca_b200 import functional as F
+    p = orc.init_fusion_params(seed=70 + B)
+    g = torch.Generator().manual_seed(B + 1)
+    img = torch.randn(B, 1280, generator=g) * 0.7 + 0.1
+    txt = torch.randn(B, 768, generator=g) * 1.3 - 0.05
+    labels = torch.randint(0, 4, (B,), generator=g)
+    seed, drop_p = 5, 0.6
+    mask = F.dropout_mask(seed, drop_p, B, 256, "cuda").cpu()
+    rl, rloss, rg, rdi, rdt = orc.fusion_loss_and_grads(p, img, txt, labels, normalized, drop_mask=mask,
+                                                        drop_scale=1.0 / (1.0 - drop_p))
+    names = F.FUSION_PARAM_NAMES
+    step = pkg.FusionTrainStep([p[n].cuda() for n in names], B, normalized=normalized, drop_p=drop_p, feature_grads=True,
+                               compute="bf16")
+    step.zero_grad()
+    loss, logits = step(img.cuda(), txt.cuda(), labels.cuda(), drop_seed=seed)
+    torch.cuda.synchronize()
+    assert (logits.cpu().double() - rl).abs().max().item() < 2e-2
+    assert abs(loss.item() - float(rloss)) < 5e-3
+    for n, v in zip(names, step.grads.views):
+        r = rg[n].double()
+        rel = ((v.cpu().double() - r).norm() / r.norm().clamp_min(1e-30)).item()
+        assert rel < 1e-2, f"{n}: {rel:.3e}"
+    for got, ref in ((step.d_img, rdi), (step.d_txt, rdt)):
+        rel = ((got.cpu().double() - ref.double()).norm() / ref.double().norm()).item()
+        assert rel < 1e-2
+    # the autograd entry point with the same switch
+    ps = [p[n].cuda().requires_grad_(True) for n in names]
+    lg = F.fusion_head(img.cuda(), txt.cuda(), ps, normalized=normalized, drop_p=drop_p, drop_seed=seed, compute="bf16")
+    torch.nn.functional.cross_entropy(lg, labels.cuda()).backward()
+    assert torch.allclose(lg, logits, atol=1e-6)
+    r = rg[names[0]].double()
+    assert ((ps[0].grad.cpu().double() - r).norm() / r.norm()).item() < 1e-2
+    with pytest.raises(ValueError):      # hidden width the tensor-core path does not cover
+        q = orc.init_fusion_params(hidden=40, seed=1)
+        pkg.FusionTrainStep([q[n].cuda() for n in names], 4, normalized=normalized, compute="bf16")
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("cls_name", ["EffV2MediumAndDistilbertClassic", "EffV2MediumAndDistilbertNormalized"])
 def test_module_drop_in(pkg, cls_name):
     """The nn.Module mirrors (reference ctor, forward(_input_ids, _attention_mask, _images, ...), shared state_dict) with
