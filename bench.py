@@ -772,6 +772,64 @@ def run_full(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_fusion(args, normalized):
+    """Secondary workload (not the BASELINE line): the classic / normalized late-fusion heads (--late_fusion=classic |
+    normalized, reference multimodal_model.py:489-579) fwd + CrossEntropyLoss + bwd at batch `--batch` on one B200, inputs
+    resident in HBM, seeded dropout 0.6; --compute fp32 (1e-4 contract) or bf16 (Linear layers on the tensor cores)."""
+    import torch
+    from garbage_classification_rca_b200 import _native as N, functional as F
+    from oracle import mmrca_oracle as orc      # parameter initialisation only (bench.py may use oracle/)
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    p = orc.init_fusion_params(seed=0)
+    step = F.FusionTrainStep([p[n].to(dev) for n in F.FUSION_PARAM_NAMES], B, normalized=normalized, drop_p=args.dropout,
+                             compute=args.compute)
+    gen = torch.Generator().manual_seed(3)
+    NB = 8      # 8 x 32 MB of features: rotates over more than the L2
+    img = [torch.randn(B, D_IMG, generator=gen).to(dev) for _ in range(NB)]
+    txt = [torch.randn(B, D_TXT, generator=gen).to(dev) for _ in range(NB)]
+    labels = torch.randint(0, N_CLASSES, (B,), generator=gen).to(dev)
+
+    def one(i):
+        step.zero_grad()
+        step(img[i % NB], txt[i % NB], labels, drop_seed=100 + i)
+
+    for i in range(W):
+        one(i)
+    torch.cuda.synchronize()
+    N.kernel_launches(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        one(W + i)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = N.kernel_launches()
+    ms = e0.elapsed_time(e1)
+    per_kernel = {}
+    N.timing_begin(launches + 64)
+    for i in range(K):
+        one(W + i)
+    for name, t in N.timing_end(launches + 64):
+        per_kernel.setdefault(name, []).append(t)
+    H = 256
+    flops = 3 * 2.0 * (D_IMG * H + D_TXT * H + 2 * H * H + H * N_CLASSES) - 2.0 * (D_IMG + D_TXT) * H   # no feature gradients
+    peaks = load_peaks()
+    emit(json.dumps({
+        "metric": ("normalized" if normalized else "classic") + "_head_fwd_bwd_samples_per_s", "value": B * K / (ms * 1e-3),
+        "unit": "samples/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+        "dtype": args.compute, "data": "synthetic",
+        "config": {"workload": f"{'Normalized' if normalized else 'Classic'} late-fusion head fwd+CE+bwd, batch {B}, features "
+                               f"1280 + 768, hidden 256, 4 classes, dropout {args.dropout}; secondary workload",
+                   "l2": f"inputs rotate over {NB} batches"},
+        "gpu_launches": launches,
+        "roofline_step": {"bound": "tensor" if args.compute == "bf16" else "fp32", "achieved": B * K / (ms * 1e-3) * flops / 1e12,
+                          "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "flops_per_sample": flops,
+                          "note": "launch-latency-bound at this size: ~30 launches of 4-20 us"},
+        "kernels_ms_per_step": {k: round(sum(v) / K, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -sum(kv[1]))}}))
+
+
 def run_token(args, rank, world, local_rank):
     """Secondary workload (BASELINE.json configs[4] / SURVEY.md §8 d cfg 5): the attention blocks on real token sequences,
     forward + backward (parameter gradients of the four blocks, input gradients of the cross blocks) + one fused SGD launch over
@@ -983,7 +1041,7 @@ def main():
     ap.add_argument("--token-forward-only", action="store_true", help="--workload token: forward only (inference)")
     ap.add_argument("--nccl", action="store_true", help="N > 1: all-reduce the gradient bucket with NCCL instead of the "
                                                         "one-shot peer-memory kernel")
-    ap.add_argument("--workload", default="mmrca", choices=("mmrca", "hierarchical", "full", "token"),
+    ap.add_argument("--workload", default="mmrca", choices=("mmrca", "hierarchical", "classic", "normalized", "full", "token"),
                     help="mmrca: the BASELINE.json line (default); hierarchical: the second --late_fusion head (1 GPU); full: a whole "
                          "training step with the stock backbones (BASELINE.json configs[2], use --batch 256)")
     ap.add_argument("--variant", default="rca", choices=("rca", "ca", "cross_only", "features_only"),
@@ -997,6 +1055,9 @@ def main():
     if args.workload == "hierarchical":
         if rank == 0:
             run_hier(args)
+    elif args.workload in ("classic", "normalized"):
+        if rank == 0:
+            run_fusion(args, args.workload == "normalized")
     elif args.workload == "full":
         run_full(args, rank, world, local_rank)
     elif args.workload == "token":
