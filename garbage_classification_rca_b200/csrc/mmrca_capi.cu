@@ -62,6 +62,47 @@ static int fail(int code, const char* fmt, const char* a = "", const char* b = "
 
 static size_t align_up_256(size_t v) { return (v + 255) & ~size_t(255); }
 
+// Side streams for the independent GEMMs of one call (token-level blocks: the four weight / input gradient GEMMs of a
+// cross block, its two projections): fork from the caller's stream with an event, join back with events - small
+// latency-bound launches then overlap instead of queueing.  Per calling thread and device (two host threads never share
+// events); the fork / join pattern is legal under stream capture.
+struct SideStreams {
+  bool ready = false;
+  cudaStream_t s[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
+};
+static thread_local SideStreams g_side[16][4];      // [device][hash of the caller's stream]: calls on different streams (the image
+                                                    // and the text branch of a step) mostly get their own side streams
+static int side_streams(SideStreams** out, cudaStream_t st) {
+  int dev = 0;
+  MMRCA_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) return fail(MMRCA_ERR_INVALID, "device index out of range%s%s");
+  const uintptr_t h = reinterpret_cast<uintptr_t>(st);
+  SideStreams& p = g_side[dev][((h >> 4) ^ (h >> 9) ^ (h >> 14)) & 3];
+  if (!p.ready) {
+    MMRCA_CUDA(cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming));
+    for (int i = 0; i < 3; ++i) {
+      MMRCA_CUDA(cudaStreamCreateWithFlags(&p.s[i], cudaStreamNonBlocking));
+      MMRCA_CUDA(cudaEventCreateWithFlags(&p.join[i], cudaEventDisableTiming));
+    }
+    p.ready = true;
+  }
+  *out = &p;
+  return MMRCA_OK;
+}
+static int side_fork(SideStreams* ss, cudaStream_t st, int n) {
+  MMRCA_CUDA(cudaEventRecord(ss->fork, st));
+  for (int i = 0; i < n; ++i) MMRCA_CUDA(cudaStreamWaitEvent(ss->s[i], ss->fork, 0));
+  return MMRCA_OK;
+}
+static int side_join(SideStreams* ss, cudaStream_t st, int n) {
+  for (int i = 0; i < n; ++i) {
+    MMRCA_CUDA(cudaEventRecord(ss->join[i], ss->s[i]));
+    MMRCA_CUDA(cudaStreamWaitEvent(st, ss->join[i], 0));
+  }
+  return MMRCA_OK;
+}
+
 struct DeviceInfo { int ok; int sms; };
 
 static int device_info(DeviceInfo* out) {
@@ -1489,10 +1530,14 @@ int mmrca_token_attention_forward(const MmrcaTokenDesc* desc, const MmrcaAttnPar
     const tok::ProjSeg segs[3] = {{w.q_img, dkq, qscale}, {w.k_img, dkq, 1.0f}, {w.v_img, dv, 1.0f}};
     if ((rc = launch_tok_proj(*desc, x_q, kq, wq, w.bias, 2 * dkq + dv, segs, di.sms, st))) return rc;
   } else {
+    // the query and the key / value projection read different activations: side by side on two streams
+    SideStreams* ss;
+    if ((rc = side_streams(&ss, st)) || (rc = side_fork(ss, st, 1))) return rc;
     const tok::ProjSeg sq[3] = {{w.q_img, dkq, qscale}, {nullptr, 0, 1.0f}, {nullptr, 0, 1.0f}};
     if ((rc = launch_tok_proj(*desc, x_q, kq, wq, w.bias, dkq, sq, di.sms, st))) return rc;
     const tok::ProjSeg skv[3] = {{w.k_img, dkq, 1.0f}, {w.v_img, dv, 1.0f}, {nullptr, 0, 1.0f}};
-    if ((rc = launch_tok_proj(*desc, x_kv, kkv, wk, w.bias + dkq, dkq + dv, skv, di.sms, st))) return rc;
+    if ((rc = launch_tok_proj(*desc, x_kv, kkv, wk, w.bias + dkq, dkq + dv, skv, di.sms, ss->s[0]))) return rc;
+    if ((rc = side_join(ss, st, 1))) return rc;
   }
   tok::AttnArgs a;
   memset(&a, 0, sizeof(a));
@@ -1552,38 +1597,42 @@ int mmrca_token_attention_backward(const MmrcaTokenDesc* desc, const MmrcaAttnPa
     }
     MMRCA_CUDA(cudaGetLastError());
   }
-  // weight gradients
-  {
-    tok::WgradArgs a;
-    memset(&a, 0, sizeof(a));
-    a.rows = rows;
-    if (self) {
-      a.out[0] = {grads->wq, 0, dkq, 0}; a.out[1] = {grads->wk, dkq, dkq, 0}; a.out[2] = {grads->wv, 2 * dkq, dv, 0}; a.nout = 3;
-      a.NG = 2 * dkq + dv; a.K = kq;
-      if ((rc = launch_tok_wgrad(a, x_q, w.g, ldq, w.wg_part, di.sms, st))) return rc;
-    } else {
-      a.out[0] = {grads->wq, 0, dkq, 0}; a.nout = 1; a.NG = dkq; a.K = kq;
-      if ((rc = launch_tok_wgrad(a, x_q, gq, ldq, w.wg_part, di.sms, st))) return rc;
-      a.out[0] = {grads->wk, 0, dkq, 0}; a.out[1] = {grads->wv, dkq, dv, 0}; a.nout = 2; a.NG = dkq + dv; a.K = kkv;
-      if ((rc = launch_tok_wgrad(a, x_kv, gkv, ldkv, w.wg_part, di.sms, st))) return rc;
-    }
-  }
-  // input gradients: the bf16 weights as they lie ([gradient column][d_in]: MN-major for this product)
-  if (d_x_q || d_x_kv) {
-    if (self) {
-      if (!d_x_q) return fail(MMRCA_ERR_INVALID, "self attention: the input gradient goes to d_x_q%s%s");
+  // weight and input gradients: up to four independent GEMMs (cross block: dW_query | dW_key, dW_value | d x_q | d x_kv), each a
+  // short latency-bound launch: forked onto side streams, joined before returning to the caller's stream
+  SideStreams* ss;
+  if ((rc = side_streams(&ss, st))) return rc;
+  tok::WgradArgs a;
+  memset(&a, 0, sizeof(a));
+  a.rows = rows;
+  if (self) {
+    if (d_x_kv) return fail(MMRCA_ERR_INVALID, "self attention: the input gradient goes to d_x_q%s%s");
+    const int nside = d_x_q ? 1 : 0;
+    if ((rc = side_fork(ss, st, nside))) return rc;
+    a.out[0] = {grads->wq, 0, dkq, 0}; a.out[1] = {grads->wk, dkq, dkq, 0}; a.out[2] = {grads->wv, 2 * dkq, dv, 0}; a.nout = 3;
+    a.NG = 2 * dkq + dv; a.K = kq;
+    if ((rc = launch_tok_wgrad(a, x_q, w.g, ldq, w.wg_part, di.sms, st))) return rc;
+    if (d_x_q) {      // the bf16 weights as they lie ([gradient column][d_in]: MN-major for this product)
       const tok::Cast3Args ca = {{p->wq, p->wk, p->wv}, {w.wbf, w.wbf + size_t(dkq) * kq, w.wbf + size_t(2 * dkq) * kq},
                                  {(long long)dkq * kq, (long long)dkq * kq, (long long)dv * kq}};
-      if ((rc = launch_cast3(ca, di.sms, st))) return rc;
-      if ((rc = launch_tok_dgrad(d_x_q, rows, kq, 2 * dkq + dv, w.g, ldq, w.wbf, st))) return rc;
-    } else {
-      __nv_bfloat16* wkv = w.wbf + size_t(dkq) * kq;
+      if ((rc = launch_cast3(ca, di.sms, ss->s[0]))) return rc;
+      if ((rc = launch_tok_dgrad(d_x_q, rows, kq, 2 * dkq + dv, w.g, ldq, w.wbf, ss->s[0]))) return rc;
+    }
+    if ((rc = side_join(ss, st, nside))) return rc;
+  } else {
+    __nv_bfloat16* wkv = w.wbf + size_t(dkq) * kq;
+    if (d_x_q || d_x_kv) {
       const tok::Cast3Args ca = {{p->wq, p->wk, p->wv}, {w.wbf, wkv, wkv + size_t(dkq) * kkv},
                                  {d_x_q ? (long long)dkq * kq : 0, d_x_kv ? (long long)dkq * kkv : 0, d_x_kv ? (long long)dv * kkv : 0}};
       if ((rc = launch_cast3(ca, di.sms, st))) return rc;
-      if (d_x_q && (rc = launch_tok_dgrad(d_x_q, rows, kq, dkq, gq, ldq, w.wbf, st))) return rc;
-      if (d_x_kv && (rc = launch_tok_dgrad(d_x_kv, rows, kkv, dkq + dv, gkv, ldkv, wkv, st))) return rc;
     }
+    if ((rc = side_fork(ss, st, 3))) return rc;
+    a.out[0] = {grads->wq, 0, dkq, 0}; a.nout = 1; a.NG = dkq; a.K = kq;
+    if ((rc = launch_tok_wgrad(a, x_q, gq, ldq, w.wg_part, di.sms, st))) return rc;
+    a.out[0] = {grads->wk, 0, dkq, 0}; a.out[1] = {grads->wv, dkq, dv, 0}; a.nout = 2; a.NG = dkq + dv; a.K = kkv;
+    if ((rc = launch_tok_wgrad(a, x_kv, gkv, ldkv, w.wg_part + size_t(kMaxSms) * dkq * 128, di.sms, ss->s[0]))) return rc;
+    if (d_x_q && (rc = launch_tok_dgrad(d_x_q, rows, kq, dkq, gq, ldq, w.wbf, ss->s[1]))) return rc;
+    if (d_x_kv && (rc = launch_tok_dgrad(d_x_kv, rows, kkv, dkq + dv, gkv, ldkv, wkv, ss->s[2]))) return rc;
+    if ((rc = side_join(ss, st, 3))) return rc;
   }
   return MMRCA_OK;
 }
