@@ -1133,7 +1133,7 @@ static FusionWorkspace fusion_carve(const MmrcaFusionDesc& d, void* base) {
     w.cat_bf = reinterpret_cast<__nv_bfloat16*>(take(B * H));
     w.wcat_bf = reinterpret_cast<__nv_bfloat16*>(take(H * H));
     w.dc_bf = reinterpret_cast<__nv_bfloat16*>(take((B * H + 1) / 2));
-    w.wg_part = take(size_t(kMaxSms) * H * 128);
+    w.wg_part = take(2 * size_t(kMaxSms) * H * 128);      // one slab set per modality chain (they run side by side)
   }
   w.bytes = off;
   return w;
@@ -1211,8 +1211,11 @@ static int fusion_forward_impl(const MmrcaFusionDesc& d, const MmrcaFusionParams
     if ((rc = launch_cast3(c1, sms, st))) return rc;
     const tok::Cast3Args c2 = {{p.w_txt, nullptr, nullptr}, {w.w_bf[1], nullptr, nullptr}, {(long long)H * d.d_txt, 0, 0}};
     if ((rc = launch_cast3(c2, sms, st))) return rc;
+    SideStreams* ss;
+    if ((rc = side_streams(&ss, st)) || (rc = side_fork(ss, st, 1))) return rc;
     if ((rc = launch_tok_dgrad(w.h_img, B, H, d.d_img, w.x_bf[0], d.d_img, w.w_bf[0], st, true, p.b_img))) return rc;
-    if ((rc = launch_tok_dgrad(w.h_txt, B, H, d.d_txt, w.x_bf[1], d.d_txt, w.w_bf[1], st, true, p.b_txt))) return rc;
+    if ((rc = launch_tok_dgrad(w.h_txt, B, H, d.d_txt, w.x_bf[1], d.d_txt, w.w_bf[1], ss->s[0], true, p.b_txt))) return rc;
+    if ((rc = side_join(ss, st, 1))) return rc;
   } else {
     if ((rc = launch_sgemm(gemm_args(img, d.d_img, 1, p.w_img, 1, d.d_img, w.h_img, H, B, H, d.d_img, p.b_img, false), st))) return rc;
     if ((rc = launch_sgemm(gemm_args(txt, d.d_txt, 1, p.w_txt, 1, d.d_txt, w.h_txt, H, B, H, d.d_txt, p.b_txt, false), st))) return rc;
@@ -1275,26 +1278,52 @@ static int fusion_backward_impl(const MmrcaFusionDesc& d, const MmrcaFusionParam
   const float* hs[2] = {w.h_img, w.h_txt};
   const float* ns[2] = {w.n_img, w.n_txt};
   float* dhs[2] = {w.d_h_img, w.d_h_txt};
-  const bool tc_gemms = (d.flags & MMRCA_FUSION_BF16) != 0;
-  if (tc_gemms) {
+  const float* xs[2] = {img, txt};
+  const int dins[2] = {d.d_img, d.d_txt};
+  float* gws[2] = {g.w_img, g.w_txt};
+  float* gbs[2] = {g.b_img, g.b_txt};
+  const float* ws[2] = {p.w_img, p.w_txt};
+  float* dxs[2] = {d_img, d_txt};
+  if (d.flags & MMRCA_FUSION_BF16) {
+    // Tensor-core path.  After d_c the two modalities are independent chains (concat_layer half -> normalisation backward ->
+    // projection): the text chain runs on a side stream next to the image chain (every launch here is short and
+    // latency-bound), with its own split-K slabs.
     const tok::Cast3Args cd = {{w.d_c, nullptr, nullptr}, {w.dc_bf, nullptr, nullptr}, {(long long)B * H, 0, 0}};
     if ((rc = launch_cast3(cd, sms, st))) return rc;
-  }
-  for (int m = 0; m < 2; ++m) {
-    if (tc_gemms) {
+    SideStreams* ss;
+    if ((rc = side_streams(&ss, st)) || (rc = side_fork(ss, st, 1))) return rc;
+    for (int m = 0; m < 2; ++m) {
+      cudaStream_t sm = m ? ss->s[0] : st;
+      float* part = w.wg_part + size_t(m) * kMaxSms * H * 128;
       // dW_cat[:, half m] += d_c^T (normalised hidden half m); d(hidden half m) = d_c W_cat[:, half m]: bf16 TMA GEMMs over the
       // forward's cat_bf / wcat_bf (operands addressed in place through their row pitch 2H)
       tok::WgradArgs a;
       memset(&a, 0, sizeof(a));
       a.out[0] = {g.w_cat + m * H, 0, H, 2 * H}; a.nout = 1; a.NG = H; a.K = H; a.rows = B;
-      if ((rc = launch_tok_wgrad(a, w.cat_bf + m * H, w.dc_bf, H, w.wg_part, sms, st, 2 * H))) return rc;
-      if ((rc = launch_tok_dgrad(dhs[m], B, H, H, w.dc_bf, H, w.wcat_bf + m * H, st, false, nullptr, 2 * H))) return rc;
-    } else {
-      fus::GemmArgs a = gemm_args(w.d_c, 1, H, hs[m], H, 1, g.w_cat + m * H, 2 * H, H, H, B, nullptr, true);
-      a.inv_k = nrm ? ns[m] : nullptr;
-      if ((rc = launch_sgemm(a, st))) return rc;
-      if ((rc = launch_sgemm(gemm_args(w.d_c, H, 1, p.w_cat + m * H, 2 * H, 1, dhs[m], H, B, H, H, nullptr, false), st))) return rc;
+      if ((rc = launch_tok_wgrad(a, w.cat_bf + m * H, w.dc_bf, H, part, sms, sm, 2 * H))) return rc;
+      if ((rc = launch_tok_dgrad(dhs[m], B, H, H, w.dc_bf, H, w.wcat_bf + m * H, sm, false, nullptr, 2 * H))) return rc;
+      if (nrm) {      // through h / ||h||
+        const int grid = min((B + kWarps - 1) / kWarps, 8 * sms);
+        { LaunchScope ls("l2norm_bwd", sm); l2norm_bwd_kernel<<<grid, kThreads, 0, sm>>>(hs[m], ns[m], dhs[m], B, H); }
+        MMRCA_CUDA(cudaGetLastError());
+      }
+      // the projection: db, dW += d(hidden)^T X over the bf16 copies (the forward's x_bf), optionally d(features) in fp32
+      const tok::Cast3Args ch = {{dhs[m], nullptr, nullptr}, {w.dh_bf[m], nullptr, nullptr}, {(long long)B * H, 0, 0}};
+      if ((rc = launch_cast3(ch, sms, sm))) return rc;
+      if ((rc = launch_colsum(dhs[m], H, B, H, gbs[m], sms, sm))) return rc;
+      memset(&a, 0, sizeof(a));
+      a.out[0] = {gws[m], 0, H, 0}; a.nout = 1; a.NG = H; a.K = dins[m]; a.rows = B;
+      if ((rc = launch_tok_wgrad(a, w.x_bf[m], w.dh_bf[m], H, part, sms, sm))) return rc;
+      if (dxs[m] && (rc = launch_sgemm(gemm_args(dhs[m], H, 1, ws[m], dins[m], 1, dxs[m], dins[m], B, dins[m], H, nullptr, false), sm)))
+        return rc;
     }
+    return side_join(ss, st, 1);
+  }
+  for (int m = 0; m < 2; ++m) {
+    fus::GemmArgs a = gemm_args(w.d_c, 1, H, hs[m], H, 1, g.w_cat + m * H, 2 * H, H, H, B, nullptr, true);
+    a.inv_k = nrm ? ns[m] : nullptr;
+    if ((rc = launch_sgemm(a, st))) return rc;
+    if ((rc = launch_sgemm(gemm_args(w.d_c, H, 1, p.w_cat + m * H, 2 * H, 1, dhs[m], H, B, H, H, nullptr, false), st))) return rc;
     if (nrm) {      // through h / ||h||
       const int grid = min((B + kWarps - 1) / kWarps, 8 * sms);
       { LaunchScope ls("l2norm_bwd", st); l2norm_bwd_kernel<<<grid, kThreads, 0, st>>>(hs[m], ns[m], dhs[m], B, H); }
@@ -1302,26 +1331,9 @@ static int fusion_backward_impl(const MmrcaFusionDesc& d, const MmrcaFusionParam
     }
   }
   // the two projections: db, dW, optionally d(features)
-  const float* xs[2] = {img, txt};
-  const int dins[2] = {d.d_img, d.d_txt};
-  float* gws[2] = {g.w_img, g.w_txt};
-  float* gbs[2] = {g.b_img, g.b_txt};
-  const float* ws[2] = {p.w_img, p.w_txt};
-  float* dxs[2] = {d_img, d_txt};
-  if (tc_gemms) {
-    const tok::Cast3Args cd = {{dhs[0], dhs[1], nullptr}, {w.dh_bf[0], w.dh_bf[1], nullptr}, {(long long)B * H, (long long)B * H, 0}};
-    if ((rc = launch_cast3(cd, sms, st))) return rc;
-  }
   for (int m = 0; m < 2; ++m) {
     if ((rc = launch_colsum(dhs[m], H, B, H, gbs[m], sms, st))) return rc;
-    if (tc_gemms) {      // dW += d(hidden)^T X: the token path's split-K TMA GEMM over the bf16 copies (the forward's x_bf)
-      tok::WgradArgs a;
-      memset(&a, 0, sizeof(a));
-      a.out[0] = {gws[m], 0, H, 0}; a.nout = 1; a.NG = H; a.K = dins[m]; a.rows = B;
-      if ((rc = launch_tok_wgrad(a, w.x_bf[m], w.dh_bf[m], H, w.wg_part, sms, st))) return rc;
-    } else if ((rc = launch_sgemm(gemm_args(dhs[m], 1, H, xs[m], dins[m], 1, gws[m], dins[m], H, dins[m], B, nullptr, true), st))) {
-      return rc;
-    }
+    if ((rc = launch_sgemm(gemm_args(dhs[m], 1, H, xs[m], dins[m], 1, gws[m], dins[m], H, dins[m], B, nullptr, true), st))) return rc;
     if (dxs[m] && (rc = launch_sgemm(gemm_args(dhs[m], H, 1, ws[m], dins[m], 1, dxs[m], dins[m], B, dins[m], H, nullptr, false), st)))
       return rc;
   }
