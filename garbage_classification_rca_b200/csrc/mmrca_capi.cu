@@ -932,7 +932,6 @@ struct TokenWorkspace {
   // MMRCA_TOKEN_TRAINING: kept by the forward for the backward, and the backward's own buffers
   void* p_img; float* sum;
   __nv_bfloat16* g;             // gradient rows: self [rows][2 d_kq + d_v]; cross [rows][d_kq] then [rows][d_kq + d_v]
-  __nv_bfloat16* part[2];       // two-tile samples: per-query-tile dK | dV partial rows [rows][d_kq + d_v]
   float* wg_part;               // weight-gradient split-K slabs [splits][columns][d_in], splits * ceil(d_in / 128) <= SMs
   __nv_bfloat16* wbf;           // bf16 weights as they lie: self [2 d_kq + d_v][d_in]; cross [d_kq][d_in_q] then [d_kq + d_v][d_in_kv]
   size_t bytes;
@@ -955,8 +954,6 @@ static TokenWorkspace token_carve(const MmrcaTokenDesc& d, void* base) {
     w.sum = static_cast<float*>(take(B * tps * tok::kTile * 4));
     const size_t rows = B * size_t(d.seq_len);
     w.g = static_cast<__nv_bfloat16*>(take(rows * size_t(2 * d.d_kq + d.d_v) * 2));
-    for (int i = 0; i < 2; ++i)
-      w.part[i] = tps > 1 ? static_cast<__nv_bfloat16*>(take(rows * size_t(d.d_kq + d.d_v) * 2)) : nullptr;
     w.wg_part = static_cast<float*>(take(size_t(kMaxSms) * size_t(2 * d.d_kq + d.d_v) * 128 * 4));
     w.wbf = static_cast<__nv_bfloat16*>(take((size_t(d.d_kq) * d.d_in_q + size_t(d.d_kq + d.d_v) * d.d_in_kv) * 2));
   }
@@ -1594,20 +1591,13 @@ int mmrca_token_attention_backward(const MmrcaTokenDesc* desc, const MmrcaAttnPa
     a.q_img = w.q_img; a.k_img = w.k_img; a.v_img = w.v_img; a.p_img = w.p_img; a.sum = w.sum;
     a.ln_g = p->ln_g; a.ln_b = p->ln_b; a.d_out = d_out;
     a.g_q = gq; a.ld_q = ldq;
-    a.dkv_out[0] = tps > 1 ? w.part[0] : gkv; a.dkv_out[1] = w.part[1]; a.ld_kv = tps > 1 ? dkq + dv : ldkv;
+    a.g_kv = gkv; a.ld_kv = ldkv; a.kv_atomic = tps > 1 ? 1 : 0;
+    if (tps > 1)      // both query tiles of a sample add into the dK | dV columns
+      MMRCA_CUDA(self ? cudaMemsetAsync(w.g, 0, size_t(rows) * ldq * 2, st) : cudaMemsetAsync(gkv, 0, size_t(rows) * ldkv * 2, st));
     a.g_bq = grads->bq; a.g_bk = grads->bk; a.g_bv = grads->bv; a.qscale = 1.0f / sqrtf(float(dkq));
     a.g_ln_g = grads->ln_g; a.g_ln_b = grads->ln_b;
     a.L = L; a.tiles_per_sample = tps; a.reverse = desc->reverse ? 1 : 0;
     if ((rc = dkq == 128 ? launch_tok_attn_bwd<128, 96>(*desc, a, st) : launch_tok_attn_bwd<64, 48>(*desc, a, st))) return rc;
-  }
-  if (tps > 1) {
-    const long long n8 = (long long)rows * (dkq + dv) / 8;
-    {
-      LaunchScope ls("tok_grad_sum", st);
-      tok::tok_grad_sum_kernel<<<int(std::min<long long>((n8 + 255) / 256, 8LL * di.sms)), 256, 0, st>>>(w.part[0], w.part[1], dkq + dv,
-                                                                                                       rows, gkv, ldkv);
-    }
-    MMRCA_CUDA(cudaGetLastError());
   }
   // weight and input gradients: up to four independent GEMMs (cross block: dW_query | dW_key, dW_value | d x_q | d x_kv), each a
   // short latency-bound launch: forked onto side streams, joined before returning to the caller's stream

@@ -4,10 +4,10 @@
 //   tok_attn_bwd     per (sample, 128-query tile), from the forward's operand images (Q, K, V), its unnormalised attention
 //                    weights P (bf16 image) and row sums: C = P V again (tensor core), LayerNorm + ReLU backward per row,
 //                    d(weights) = E V^T, softmax backward in place (P -> dS), dV = P^T E, dQ = dS K, dK = dS^T Q - five
-//                    tcgen05 chains, accumulators in TMEM.  dQ rows are the tile's own; dK / dV are per-query-tile partials.
+//                    tcgen05 chains, accumulators in TMEM.  dQ rows are the tile's own; dK / dV rows collect both query tiles.
 //                    All three leave the kernel as bf16 ROWS of the flat gradient matrices G [B * L][columns] (dQ times
 //                    1/sqrt(d_kq); dK | dV side by side), together with the bias gradients (column sums, from the fp32
-//                    accumulators).  Two-tile samples: dK | dV are per-query-tile partials that tok_grad_sum adds up.
+//                    accumulators).  Two-tile samples: both query tiles add their dK | dV rows with 16-byte vector atomics.
 //   tok_wgrad        dW^T[K tile of 128][gradient columns] += X^T G over the flat token dimension: BOTH operands are read as
 //                    they lie in HBM - row-major [tokens][columns] is MN-major for this product - through tensor maps
 //                    ({64 columns, 64 tokens} boxes, 128-byte swizzle), three-stage TMA pipeline, split-K over the tokens.
@@ -26,10 +26,12 @@ struct AttnBwdArgs {
   const float* sum;         // [B * tiles][128] softmax row sums
   const float* ln_g; const float* ln_b;
   const float* d_out;       // [B][L][DV]
-  // bf16 gradient rows, token r = b * L + t: dQ (times 1/sqrt(d_kq)) -> g_q[r * ld_q + ..]; dK | dV -> dkv_out[query tile][r * ld_kv + ..]
-  // (one-tile samples: dkv_out[0] is the final matrix; else per-query-tile partials that tok_grad_sum adds up)
+  // bf16 gradient rows, token r = b * L + t: dQ (times 1/sqrt(d_kq)) -> g_q[r * ld_q + ..]; dK | dV -> g_kv[r * ld_kv + ..]
   __nv_bfloat16* g_q; int ld_q;
-  __nv_bfloat16* dkv_out[kMaxTiles]; int ld_kv;
+  __nv_bfloat16* g_kv; int ld_kv;
+  int kv_atomic;            // two-tile samples: both query tiles ADD their dK | dV rows into the zeroed matrix with 16-byte vector
+                            // atomics (red.global.add.noftz.v4.bf16x2: eight bf16 per operation; two addends per element, so the
+                            // result does not depend on their order)
   float* g_bq; float* g_bk; float* g_bv;     // += column sums (atomics)
   float qscale;
   float* g_ln_g; float* g_ln_b;     // += (atomics)
@@ -63,6 +65,14 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4 u, float* v) {
 __device__ __forceinline__ void ld_chunks16(const uint8_t* op, int row, int col0, float (&v)[16]) {
   unpack_bf16x8(*reinterpret_cast<const uint4*>(op + uint32_t(col0 >> 3) * kCS + row_off(row)), v);
   unpack_bf16x8(*reinterpret_cast<const uint4*>(op + uint32_t((col0 >> 3) + 1) * kCS + row_off(row)), v + 8);
+}
+// dst[0 .. 8) (bf16) (+)= v: plain 16-byte store, or one vector atomic
+__device__ __forceinline__ void put_bf16x8(__nv_bfloat16* dst, const float (&v)[8], bool atomic) {
+  const uint4 u = pack_bf16x8(v);
+  if (atomic)
+    asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+  else
+    *reinterpret_cast<uint4*>(dst) = u;
 }
 __device__ __forceinline__ float warp_sum32(float v) {
 #pragma unroll
@@ -372,7 +382,7 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
       tmem_wait_ld();
       const int key = j * kTile + row;
       const bool add_t = a.reverse && key < L;        // every valid key's value row feeds colsum(V)
-      __nv_bfloat16* dst = a.dkv_out[mt] + (size_t(b) * L + key) * a.ld_kv + DKQ + HC * half;
+      __nv_bfloat16* dst = a.g_kv + (size_t(b) * L + key) * a.ld_kv + DKQ + HC * half;
       float v[HC];
 #pragma unroll
       for (int e = 0; e < HC; ++e) {
@@ -381,8 +391,7 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
       }
       if (key < L) {
 #pragma unroll
-        for (int g8 = 0; g8 < HC / 8; ++g8)
-          *reinterpret_cast<uint4*>(dst + 8 * g8) = pack_bf16x8(*reinterpret_cast<const float(*)[8]>(&v[8 * g8]));
+        for (int g8 = 0; g8 < HC / 8; ++g8) put_bf16x8(dst + 8 * g8, *reinterpret_cast<const float(*)[8]>(&v[8 * g8]), a.kv_atomic != 0);
       }
     }
     warp_col_sums(vtot, lane, myslot + SLOT_B + 2 * DKQ + HC * half);
@@ -405,7 +414,7 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
   for (int e = 0; e < HQ; ++e) ktot[e] = 0.f;
   for (int j = 0; j < tps; ++j) {
     const int key = j * kTile + row;
-    __nv_bfloat16* dst = a.dkv_out[mt] + (size_t(b) * L + key) * a.ld_kv + HQ * half;
+    __nv_bfloat16* dst = a.g_kv + (size_t(b) * L + key) * a.ld_kv + HQ * half;
     const uint32_t tk = tmem + lane_base + COL_DK + DKQ * j + HQ * half;
     uint32_t r[HQ];
 #pragma unroll
@@ -416,8 +425,7 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
     for (int e = 0; e < HQ; ++e) { v[e] = __uint_as_float(r[e]); ktot[e] += v[e]; }
     if (key < L) {
 #pragma unroll
-      for (int g8 = 0; g8 < HQ / 8; ++g8)
-        *reinterpret_cast<uint4*>(dst + 8 * g8) = pack_bf16x8(*reinterpret_cast<const float(*)[8]>(&v[8 * g8]));
+      for (int g8 = 0; g8 < HQ / 8; ++g8) put_bf16x8(dst + 8 * g8, *reinterpret_cast<const float(*)[8]>(&v[8 * g8]), a.kv_atomic != 0);
     }
   }
   warp_col_sums(ktot, lane, myslot + SLOT_B + DKQ + HQ * half);
@@ -450,22 +458,6 @@ __global__ void __launch_bounds__(256, 1) tok_attn_bwd_kernel(const AttnBwdArgs 
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
-}
-
-// ---- two-tile samples: dK | dV rows = sum of the two query tiles' partial rows ------------------------------------------------------
-__global__ void __launch_bounds__(256) tok_grad_sum_kernel(const __nv_bfloat16* __restrict__ p0, const __nv_bfloat16* __restrict__ p1,
-                                                           int width, long long rows, __nv_bfloat16* __restrict__ out, int ld_out) {
-  const int w8 = width / 8;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < rows * w8; i += (long long)gridDim.x * 256) {
-    const long long r = i / w8;
-    const int c = int(i - r * w8) * 8;
-    float x[8], y[8];
-    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p0 + r * width + c)), x);
-    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p1 + r * width + c)), y);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) x[e] += y[e];
-    *reinterpret_cast<uint4*>(out + r * ld_out + c) = pack_bf16x8(x);
-  }
 }
 
 // ---- weight gradients ---------------------------------------------------------------------------------------------------------------
