@@ -505,7 +505,6 @@ __global__ void __launch_bounds__(kCaBwdThreads, 1) ca_bwd_kernel(const CaBwdArg
   MMRCA_STAMP(0); stamp_n = 1;
   MMRCA_STAMP_NS(250);
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, stamp_n += 16) {
-    const int b0 = tile * 8;
     MMRCA_STAMP(0);
     // ---- P0: DL from dlogits; block inputs (SA images): requested by the loader warp once the previous tile's dM / dWv
     //      MMAs were done, which also makes their operand buffers (dZ, dV) free to overwrite below -------------------------
@@ -818,7 +817,7 @@ __device__ __forceinline__ void sa_bwd_body(const SaBwdArgs& a, uint8_t* sm) {
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   BwCtx c = make_bwctx(tmem, &bars[2]);
-  uint32_t ph_in[2] = {0, 0}, ph_ld = 0, ph_g2 = 0, ph_g3 = 0;
+  uint32_t ph_in[2] = {0, 0}, ph_g2 = 0, ph_g3 = 0;
   uint8_t *dcb = sm + S::DC, *dyx = sm + S::DYX, *dls = sm + S::DLS, *ones = sm + S::ONES;
   bool first = true;
   int buf = 0, stamp_n = 0;

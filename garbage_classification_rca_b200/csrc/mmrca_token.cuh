@@ -212,18 +212,6 @@ __global__ void __launch_bounds__(kProjThreads, 1) tok_proj_kernel(const __grid_
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-// fp32 -> bf16 (activations that arrive in fp32; weights [W_query | W_key | W_value] stacked row-wise)
-__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
-  for (long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * 1024) {
-    if (i + 3 < n) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
-      *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
-    } else {
-      for (long long j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
-    }
-  }
-}
-
 // up to three fp32 -> bf16 casts in one launch (the stacked bf16 weights of the input-gradient GEMM)
 struct Cast3Args { const float* src[3]; __nv_bfloat16* dst[3]; long long n[3]; };
 __global__ void __launch_bounds__(256) cast3_bf16_kernel(const Cast3Args a) {
