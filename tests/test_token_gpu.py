@@ -211,3 +211,45 @@ def test_token_attention_bf16_output_into_a_caller_buffer(pkg):
     assert torch.equal(ext[1:], ref.to(torch.bfloat16))
     with pytest.raises(ValueError):
         F.TokenAttention(params, B, L, out_dtype=torch.bfloat16)(x, out=torch.zeros(B, L, 96, device="cuda"))
+
+
+def test_token_block_under_cuda_graph_capture(pkg):
+    """Forward + backward of a cross block captured into a CUDA graph (the calls fork GEMMs onto library-owned side streams and
+    join them with events: legal under capture) and replayed: same results as the eager calls."""
+    from garbage_classification_rca_b200 import functional as F
+    B, L = 3, 150
+    p = _block_params("ca", 96, 96, 64, 48, seed=21)
+    g = torch.Generator().manual_seed(9)
+    x1 = torch.relu(torch.randn(B, L, 96, generator=g)).bfloat16().cuda()
+    x2 = torch.relu(torch.randn(B, L, 96, generator=g)).bfloat16().cuda()
+    d_out = (torch.randn(B, L, 48, generator=g) / (B * L)).cuda()
+    params = [p[f"ca.{l}"].cuda() for l in LEAVES]
+    blk = F.TokenAttention(params, B, L, reverse=True, training=True)
+    grads = [torch.zeros_like(t) for t in params]
+    out_eager = blk(x1, x2).clone()
+    dx1_e, dx2_e = blk.backward(d_out, grads, True, True)
+    torch.cuda.synchronize()
+    grads_eager = [t.clone() for t in grads]
+    for t in grads:
+        t.zero_()
+    blk.refresh_weights()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):          # warm-up on the capture stream (lazy initialisation must not happen inside the capture)
+        blk(x1, x2)
+        blk.backward(d_out, [torch.zeros_like(t) for t in params], True, True)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    blk.refresh_weights()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out_g = blk(x1, x2)
+        dx1_g, dx2_g = blk.backward(d_out, grads, True, True)
+    for t in grads:
+        t.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out_g, out_eager)
+    assert torch.allclose(dx1_g, dx1_e, rtol=1e-5, atol=1e-8) and torch.allclose(dx2_g, dx2_e, rtol=1e-5, atol=1e-8)
+    for a, b in zip(grads, grads_eager):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-7)
