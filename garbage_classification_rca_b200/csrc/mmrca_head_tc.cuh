@@ -270,8 +270,10 @@ __device__ __forceinline__ void feat_emit(const FeatArgs& a, const FeatSrc& S, c
       if (a.drop.thresh) drop_apply8(a.drop, uint32_t(b), uint32_t(S.cls_off + it * 8), o);
 #pragma unroll
       for (int cc = 0; cc < kClasses; ++cc) {
-        const float4 w0 = *reinterpret_cast<const float4*>(ws + cc * (kL * DIN) + it * 8);
-        const float4 w1 = *reinterpret_cast<const float4*>(ws + cc * (kL * DIN) + it * 8 + 4);
+        // (staged as two planes per class - first / second four columns of every item - so that a warp's 16-byte reads are
+        //  contiguous: with the natural order the 32-byte lane stride made every read a two-way bank conflict)
+        const float4 w0 = reinterpret_cast<const float4*>(ws)[cc * (2 * ITEMS) + it];
+        const float4 w1 = reinterpret_cast<const float4*>(ws)[cc * (2 * ITEMS) + ITEMS + it];
         acc[cc] = fmaf(o[0], w0.x, fmaf(o[1], w0.y, fmaf(o[2], w0.z, fmaf(o[3], w0.w, acc[cc]))));
         acc[cc] = fmaf(o[4], w1.x, fmaf(o[5], w1.y, fmaf(o[6], w1.z, fmaf(o[7], w1.w, acc[cc]))));
       }
@@ -310,7 +312,13 @@ __global__ void __launch_bounds__(256) prep_feat_kernel(const PrepArgs pa, const
         t[u] = __ldg(reinterpret_cast<const float4*>(fa.wf + size_t(cc) * fa.drop.D + off + j));
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) reinterpret_cast<float4*>(wsm_f)[int(threadIdx.x) + 256 * (u0 + u)] = t[u];
+      for (int u = 0; u < 4; ++u) {      // float4 (class cc, item j / 8, half (j / 4) & 1) -> plane `half` of the class
+        const int f = 4 * (int(threadIdx.x) + 256 * (u0 + u));
+        const bool im = f < kClasses * 1280;
+        const int g = im ? f : f - kClasses * 1280, w = im ? 1280 : 768, items = w / 8;
+        const int cc = g / w, j = g - cc * w;
+        reinterpret_cast<float4*>(wsm_f)[(im ? 0 : kClasses * 1280 / 4) + cc * (2 * items) + ((j >> 2) & 1) * items + (j >> 3)] = t[u];
+      }
     }
   }
   __syncthreads();
