@@ -1008,6 +1008,9 @@ def run_token(args, rank, world, local_rank):
             per_shape.setdefault(shapes[j % 6], []).append(t_ms)
         for name, t_ms in recs:
             per_kernel.setdefault(name, []).append(t_ms)
+        # weight-gradient GEMMs, host launch order per step: cross-image (q, k|v), self-image, cross-text (q, k|v), self-text
+        wg = [t_ms for name, t_ms in recs if name == "tok_wgrad"]
+        wg_big = [t for j, t in enumerate(wg) if j % 6 == 2] if train and len(wg) % 6 == 0 else []
         peaks = load_peaks()
         big = (197, 1024, 352)
         big_ms = statistics.mean(per_shape[big])
@@ -1038,6 +1041,11 @@ def run_token(args, rank, world, local_rank):
             "roofline_step": {"bound": "tensor", "achieved": B * K / (ms * 1e-3) * flops_sample / 1e12,
                               "peak": peaks["bf16_sustained"], "frac": B * K / (ms * 1e-3) * flops_sample / 1e12 / peaks["bf16_sustained"],
                               "flops_per_sample": flops_sample},
+            "roofline_wgrad": ({"bound": "tensor", "kernel": "tok_wgrad dW^T[1024 x 352] += X^T[1024 x B*197] G[B*197 x 352] (split-K slabs; "
+                                                           "the reduce kernel is separate)",
+                                "achieved": big_flops / (statistics.mean(wg_big) * 1e-3) / 1e12, "peak": peaks["bf16_sustained"],
+                                "unit": "TFLOP/s", "frac": big_flops / (statistics.mean(wg_big) * 1e-3) / 1e12 / peaks["bf16_sustained"],
+                                "kernel_ms": statistics.mean(wg_big)} if wg_big else None),
             "proj_ms_by_shape": {f"L{L}_K{Kd}_N{Nn}": round(statistics.mean(v), 4) for (L, Kd, Nn), v in per_shape.items()},
             "kernels_ms_per_step": {k: round(sum(v) / K, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -sum(kv[1]))}}))
     if world > 1:
