@@ -833,6 +833,16 @@ static int hier_forward_impl(const MmrcaHierDesc& d, const MmrcaHierParams& p, c
     if (!feats[i] || (reinterpret_cast<uintptr_t>(feats[i]) & 15))
       return fail(MMRCA_ERR_INVALID, "the six feature pointers must be non-null and 16-byte aligned%s%s");
   const int tiles = (d.batch + hier::kTile - 1) / hier::kTile;
+  // the weight images (16 MB, a few microseconds) are built on a side stream next to the HBM-bound feature pass
+  SideStreams* ss;
+  if ((rc = side_streams(&ss, st)) || (rc = side_fork(ss, st, 1))) return rc;
+  {
+    hier::WPrepArgs a;
+    a.w[0] = p.w_img; a.w[1] = p.w_txt; a.blob[0] = w.wb_img; a.blob[1] = w.wb_txt;
+    LaunchScope ls("hier_wprep", ss->s[0]);
+    hier::hier_wprep_kernel<<<dim3(hier::kHid / 32, hier::kGImg / 32 + hier::kGTxt / 32), 256, 0, ss->s[0]>>>(a);
+  }
+  MMRCA_CUDA(cudaGetLastError());
   {
     hier::PrepArgs a;
     memset(&a, 0, sizeof(a));
@@ -843,13 +853,7 @@ static int hier_forward_impl(const MmrcaHierDesc& d, const MmrcaHierParams& p, c
     hier::hier_prep_kernel<<<tiles * hier::kTile, 256, 0, st>>>(a);
   }
   MMRCA_CUDA(cudaGetLastError());
-  {
-    hier::WPrepArgs a;
-    a.w[0] = p.w_img; a.w[1] = p.w_txt; a.blob[0] = w.wb_img; a.blob[1] = w.wb_txt;
-    LaunchScope ls("hier_wprep", st);
-    hier::hier_wprep_kernel<<<dim3(hier::kHid / 32, hier::kGImg / 32 + hier::kGTxt / 32), 256, 0, st>>>(a);
-  }
-  MMRCA_CUDA(cudaGetLastError());
+  if ((rc = side_join(ss, st, 1))) return rc;
   {
     hier::GemmArgs a;
     memset(&a, 0, sizeof(a));
