@@ -36,6 +36,33 @@ def test_workspace_size_is_monotone(native_lib):
         prev = inf
 
 
+def test_token_and_fusion_descriptors_are_validated_on_the_host(native_lib):
+    """Host-side logic of the token-level / classic-head entry points that needs no GPU: workspace sizing (the training and
+    bf16 flags grow it), shape validation, and the backward's refusal to run without the training flag."""
+    import ctypes as C
+    from garbage_classification_rca_b200 import _native as N
+    ws = lambda d: int(native_lib.mmrca_token_attention_workspace_bytes(C.byref(d)))
+    inf = N.TokenDesc(8, 197, 1024, 1024, 128, 96, 0, 0)
+    trn = N.TokenDesc(8, 197, 1024, 1024, 128, 96, 0, N.TOKEN_TRAINING)
+    assert 0 < ws(inf) < ws(trn)
+    assert ws(N.TokenDesc(16, 197, 1024, 1024, 128, 96, 0, N.TOKEN_TRAINING)) > ws(trn)
+    for bad in (N.TokenDesc(8, 257, 1024, 1024, 128, 96, 0, 0),       # L > 256
+                N.TokenDesc(8, 1, 1024, 1024, 128, 96, 0, 0),         # L < 2
+                N.TokenDesc(8, 197, 1024, 1024, 100, 96, 0, 0),       # widths outside {(128, 96), (64, 48)}
+                N.TokenDesc(8, 197, 1020, 1020, 128, 96, 0, 0)):      # d_in not a multiple of 8
+        assert ws(bad) == 0 and N.last_error()
+    # the backward needs MMRCA_TOKEN_TRAINING on the descriptor: refused before any device is touched
+    rc = native_lib.mmrca_token_attention_backward(C.byref(inf), None, None, None, None, None, None, None, None, 0, None)
+    assert rc == 1 and "MMRCA_TOKEN_TRAINING" in N.last_error()      # MMRCA_ERR_INVALID
+    fws = lambda d: int(native_lib.mmrca_fusion_workspace_bytes(C.byref(d)))
+    f32 = N.FusionDesc(64, 1280, 768, 256, 4, 0, 0.0, 0)
+    b16 = N.FusionDesc(64, 1280, 768, 256, 4, N.FUSION_BF16, 0.0, 0)
+    assert 0 < fws(f32) < fws(b16)
+    assert fws(N.FusionDesc(64, 1280, 768, 40, 4, 0, 0.0, 0)) > 0                       # fp32: any hidden width % 4
+    assert fws(N.FusionDesc(64, 1280, 768, 40, 4, N.FUSION_BF16, 0.0, 0)) == 0          # bf16: hidden % 16
+    assert fws(N.FusionDesc(64, 1280, 768, 512, 4, N.FUSION_BF16, 0.0, 0)) == 0         # bf16: hidden <= 256
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
 def test_no_cpu_fallback(native_lib):
     import garbage_classification_rca_b200 as g
