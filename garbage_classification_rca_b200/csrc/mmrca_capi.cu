@@ -1653,6 +1653,8 @@ static int fusion_common(const MmrcaFusionDesc* desc, const void* a, const void*
   int rc;
   if ((rc = fusion_check(desc))) return rc;
   if (!a || !b || !c || !e || !ws) return fail(MMRCA_ERR_INVALID, "null pointer argument%s%s");
+  if ((desc->flags & MMRCA_FUSION_BF16) && ((reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15))
+    return fail(MMRCA_ERR_INVALID, "fusion head, bf16: the feature tensors must be 16-byte aligned%s%s");
   if ((rc = device_info(di))) return rc;
   *w = fusion_carve(*desc, ws);
   if (ws_bytes < w->bytes) return fail(MMRCA_ERR_WORKSPACE, "workspace too small%s%s");

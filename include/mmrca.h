@@ -305,7 +305,8 @@ int mmrca_token_attention_backward(const MmrcaTokenDesc* desc, const MmrcaAttnPa
 #define MMRCA_FUSION_NORMALIZED 1u
 #define MMRCA_FUSION_BF16 2u /* the two projections and their weight gradients as bf16 tcgen05 GEMMs (fp32 accumulate): the
                                 2e-2-absolute logits contract instead of 1e-4 relative; hidden % 16 == 0, <= 256, feature
-                                widths % 16 == 0.  The backward needs the unmodified workspace of the forward. */
+                                widths % 16 == 0, feature tensors and gradient tensors 16-byte aligned.  The backward needs the
+                                unmodified workspace of the forward. */
 typedef struct MmrcaFusionParams {
   const float* w_img; const float* b_img; /* image_to_hidden_size [H, d_img], [H]   (:199-201) */
   const float* w_txt; const float* b_txt; /* text_to_hidden_size  [H, d_txt], [H]   (:203-206) */
