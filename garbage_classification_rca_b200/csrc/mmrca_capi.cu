@@ -1576,6 +1576,10 @@ int mmrca_token_attention_backward(const MmrcaTokenDesc* desc, const MmrcaAttnPa
   if ((reinterpret_cast<uintptr_t>(x_q) & 15) || (!self && (reinterpret_cast<uintptr_t>(x_kv) & 15)) ||
       (reinterpret_cast<uintptr_t>(d_out) & 15) || (reinterpret_cast<uintptr_t>(d_x_q) & 15) || (reinterpret_cast<uintptr_t>(d_x_kv) & 15))
     return fail(MMRCA_ERR_INVALID, "token activations and gradients must be 16-byte aligned%s%s");
+  if ((reinterpret_cast<uintptr_t>(grads->wq) | reinterpret_cast<uintptr_t>(grads->wk) | reinterpret_cast<uintptr_t>(grads->wv)) & 15)
+    return fail(MMRCA_ERR_INVALID, "the weight-gradient tensors must be 16-byte aligned%s%s");
+  if (!grads->wq || !grads->wk || !grads->wv || !grads->bq || !grads->bk || !grads->bv || !grads->ln_g || !grads->ln_b)
+    return fail(MMRCA_ERR_INVALID, "null gradient pointer%s%s");
   DeviceInfo di;
   if ((rc = device_info(&di))) return rc;
   const TokenWorkspace w = token_carve(*desc, workspace);
